@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS (fp64) of the D3Q19 Channel-Flow time step on N B200s, with the HBM
+roofline of the collide-stream kernel and the CPU baseline beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c4|NXxNYxNZ]
+
+A "step" is one collision_MRT (fused collide + force + propagate + wall bounce-back + z-face
+exchange) over the whole channel.  At N=1 the workload is BASELINE.json configs[1]:
+512x256x256 (nx x ny x nz, x wall-normal), turbulent parameter set, fp64.  For N>1 the
+default is weak scaling with one 512x256x256 slab per GPU (global nz = 256 N); `--scaling
+strong` keeps the global 512x256x256 (configs[2]).  One JSON line is printed by rank 0.
+
+value      device-timed: populations resident in HBM, K steps between CUDA events on the
+           stream the kernels run on, max over ranks.
+e2e        the same K steps through the reference-facing interface with HOST buffers inside
+           the timed region: upload of f(0:18,lx,ly,lz) from pinned host memory, then per step
+           collision_MRT + macrovar (the shim's download policy: rho,u come back every
+           nflowout/ndiag steps and after the last step) + a `probe` read-back of the centre
+           node (32 B D2H) every step.
+roofline   304 B per node update (19 fp64 in + 19 fp64 out) / mean step-kernel time, against
+           MEASURED_PEAKS.json's hbm_gbs.
+cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/, built -O3
+           -march=native), one thread per emulated MPI rank on all host cores, on a bounded
+           sample of the same workload.  (The Fortran reference itself cannot be built here:
+           no Fortran compiler, no MPI.)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_NODE = 304.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scheme", default="aa", choices=["aa", "ab"])
+    ap.add_argument("--math", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def workload_dims(name):
+    named = {"c1": (64, 32, 32), "c2": (512, 256, 256), "c4": (1024, 1024, 944)}
+    if name in named:
+        return named[name]
+    nx, ny, nz = (int(t) for t in name.lower().split("x"))
+    return nx, ny, nz
+
+
+# ---- clocks during the timed region (B200_PROFILING.md "clocks line") -------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- the CPU arm: the restated reference on the host cores -----------------------------------------
+def cpu_reference_run(nx, ny, nz, steps, warmup):
+    """collision_MRT + macrovar per step like main.f90:157-161, one thread per emulated rank."""
+    from oracle import oracle as orc
+    ncores = os.cpu_count() or 1
+    # a y/z block grid with as many ranks as cores (para.f90:219-228 wants nprocY | nproc)
+    npz = 1
+    while npz * 2 <= ncores and nz % (npz * 2) == 0 and (npz * 2) ** 2 <= ncores * 2:
+        npz *= 2
+    npy = max(1, ncores // npz)
+    while ny % npy:
+        npy -= 1
+    orc.lib(fast=True).orc_set_num_threads(ncores)
+    w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=False, fast=True, nprocY=npy, nprocZ=npz)
+    w.macrovar()
+    for _ in range(warmup):
+        w.collision_MRT(); w.macrovar()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w.collision_MRT(); w.macrovar()
+    dt = time.perf_counter() - t0
+    w.close()
+    mlups = nx * ny * nz * steps / dt / 1e6
+    return {"value": mlups, "unit": "MLUPS", "cores": min(ncores, npy * npz), "kind": "port",
+            "sample": "%dx%dx%d, %d warm-up + %d timed steps of collision_MRT+macrovar, %dx%d ranks as threads, "
+                      "C restatement of collision.f90 built -O3 -march=native (no Fortran/MPI in this image)"
+                      % (nx, ny, nz, warmup, steps, npy, npz),
+            "ms_per_step": dt / steps * 1e3}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    nx, ny, nz_unit = workload_dims(args.workload)
+    n_gpus = max(args.gpus, world)
+    nz = nz_unit * n_gpus if (args.scaling == "weak" and n_gpus > 1) else nz_unit
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded sample: the single-GPU workload (the per-GPU block), a few steps
+        cpu_steps = max(1, min(args.steps, args.cpu_steps))
+        res = cpu_reference_run(nx, ny, nz_unit, cpu_steps, min(args.warmup, 1))
+        line = {
+            "impl": "reference", "metric": "MLUPS (fp64)", "value": res["value"], "unit": "MLUPS",
+            "n_gpus": n_gpus, "steps": cpu_steps, "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "D3Q19 MRT channel %dx%dx%d (nx x ny x nz), turbulent set Re_tau=180" % (nx, ny, nz_unit),
+                       "note": "CPU arm: restated reference on host cores; bounded sample of the per-GPU block"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+
+    pkg = entry.load_package()
+    capi = pkg.capi
+    if not torch.cuda.is_available() or capi.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.tensor(list(capi.nccl_unique_id()), dtype=torch.uint8)
+        dist.broadcast(idt, src=0)
+        nccl_id = bytes(idt.tolist())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    scheme = capi.SCHEME_AA if args.scheme == "aa" else capi.SCHEME_AB
+    math_mode = capi.MATH_FAST if args.math == "fast" else capi.MATH_STRICT
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local_rank, scheme=scheme,
+                          math_mode=math_mode, nccl_id=nccl_id, overlap=not args.no_overlap, allocate_host=False)
+    nodes_global = nx * ny * nz
+    do_e2e = not args.no_e2e and args.workload != "c4"
+
+    # synthetic initial state (turbulent set: log-law + perturbation + seeded noise), host side, once
+    sim.allocarray(pinned=True)
+    sim.initvel(A9=0.3)
+    rng = np.random.default_rng(54321 + rank)
+    for a in (sim.ux, sim.uy, sim.uz):
+        a += 1e-3 * sim.v.ustar * (2.0 * rng.random(a.shape) - 1.0)
+    sim.FORCING()
+    sim.initpop()
+
+    # ---- device-timed value -------------------------------------------------------------------
+    sim.upload_f()
+    sim.run_device(args.warmup)
+    sim.sync()
+    c0 = sim.counters()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier(); sim.sync()
+    sim.timer_start()
+    sim.run_device(args.steps)
+    ms = sim.timer_stop()
+    sim.sync(); barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    c1 = sim.counters()
+    ms = max_over_ranks(ms)
+    mlups = nodes_global * args.steps / (ms * 1e-3) / 1e6
+    launches = (c1["step_kernels"] - c0["step_kernels"]) + (c1["other_kernels"] - c0["other_kernels"])
+
+    # sanity: the field is finite and still a channel flow
+    pr = sim.probe(nx // 2, ny // 2, max(1, sim.lz // 2))
+    if not np.all(np.isfinite(pr)):
+        raise SystemExit("bench: non-finite field after the timed region")
+
+    # roofline of the dominant kernel: per-launch algorithmic bytes / mean launch duration
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    nodes_local = nx * ny * sim.lz
+    achieved = BYTES_PER_NODE * nodes_local / (ms * 1e-3 / args.steps) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("%s_%dx%dx%d" % (args.scheme, nx, ny, sim.lz))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "bytes_per_node": BYTES_PER_NODE, "peak_source": peak_src,
+                "kernel": "k_step<%s>" % ("AA even/odd" if args.scheme == "aa" else "AB pull")}
+
+    # ---- end to end through the reference-facing interface, host buffers ------------------------
+    e2e = None
+    if do_e2e:
+        sim.v.nsteps = args.steps
+        sim.host_f_changed()                       # host f is the initial state again -> upload inside the timed region
+        sim.initpop()
+        barrier(); sim.sync()
+        t0 = time.perf_counter()
+        d2h = 0
+        for sim.istep in range(1, args.steps + 1):
+            sim.collision_MRT()                    # first call uploads f (H2D, pinned)
+            sim.macrovar()                         # shim policy: downloads rho,u on output steps + the last
+            pr = sim.probe(nx // 2, ny // 2, max(1, sim.lz // 2))
+            d2h += 32
+            if sim.istep % sim.v.nflowout == 0 or sim.istep % sim.v.ndiag == 0 or sim.istep == args.steps:
+                d2h += 4 * 8 * nodes_local
+        sim.sync(); barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": nodes_global * args.steps / dt / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": 19 * 8 * nodes_local / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps,
+               "what": "upload f from pinned host + K x (collision_MRT; macrovar; probe) through the shim entry points"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu and world == 1:
+        sim.close()
+        cpu = cpu_reference_run(nx, ny, nz_unit, args.cpu_steps, 1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "MLUPS (fp64)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "D3Q19 MRT channel %dx%dx%d (nx x ny x nz, x wall-normal), turbulent set Re_tau=180, "
+                                   "uniform body force, half-way bounce-back walls" % (nx, ny, nz),
+                       "per_gpu": "%dx%dx%d z-slab" % (nx, ny, sim.lz), "scheme": args.scheme, "math": args.math,
+                       "parallelism": "z-slab x%d, NCCL send/recv faces" % world if world > 1 else "1 GPU",
+                       "l2": "populations %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (c1["population_bytes"] / 1e9)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "impl": "ours",
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

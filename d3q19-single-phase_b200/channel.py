@@ -1,0 +1,349 @@
+"""Host-side mirror of the reference driver's interface for the Channel-Flow hot path.
+
+The reference is a flat Fortran program: `main.f90` calls argument-less subroutines that talk
+through `module var_inc`.  No Fortran compiler exists in this image, so this module plays the
+part of the (intact) driver above the C-ABI: `ChannelFlow` owns the host arrays of var_inc
+(same names, same layouts), and its methods carry the reference's subroutine names and call
+the very entry points the replacement `collision.f90` shim binds
+(`fortran/collision_b200.f90`): d3q19_shim_collision_mrt, d3q19_shim_macrovar, ...
+
+    para / allocarray      para.f90:21-413, :418-503
+    initvel / initpop      initial.f90:75-147, :19-46      (host, run once -- out of the hot path)
+    FORCING                collision.f90:515-527
+    rhoupdat               collision.f90:469-480
+    collision_MRT          collision.f90:24-273
+    macrovar               collision.f90:378-463
+    avedensity             collision.f90:487-513
+    prerelax / run         main.f90:70-90, :142-208
+
+All compute goes through libd3q19b200.so on the GPU; there is no CPU fallback here.
+Host arrays are numpy C-order views of the Fortran layouts: f[iz,iy,ix,ip], a[iz,iy,ix].
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi
+
+CIX = np.array([0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0])
+CIY = np.array([0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1])
+CIZ = np.array([0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1])
+IPOPP = np.array([0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15])
+
+
+class VarInc:
+    """The scalars of `module var_inc` that the path reads, as `para` sets them."""
+
+    def __init__(self, nx, ny, nz, laminar=True, **overrides):
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.npop = 19
+        self.rho0 = 1.0
+        self.rhopart = 1.0                      # var_inc.f90:65
+        self.pi = 4.0 * math.atan(1.0)          # var_inc.f90:71
+        self.pi2 = 2.0 * self.pi
+        self.ndiag, self.nflowout = 250, 100    # var_inc.f90:58-59
+        self.nsteps = 1000                      # para.f90:43
+        self.istep0 = 0
+        self.rhoepsl = 1.0e-05                  # para.f90:285
+        self.ipart = False                      # para.f90:332
+        self.laminar = bool(laminar)
+        if not laminar:                         # para.f90:61-70
+            self.visc = 0.0036
+            self.Rstar = 180.0
+            self.ustar = 2.0 * self.Rstar * self.visc / float(nx)
+            self.force_in_y = 2.0 * self.rho0 * self.ustar * self.ustar / float(nx)
+            self.ystar = self.visc / self.ustar
+            self.force_mag = 1.0
+            self.ivel = True
+            self.MRTtype = 1
+        else:                                   # para.f90:75-88
+            self.Rstar = 20.0
+            self.ustar = 0.05
+            self.visc = 2.0 * self.ustar * float(nx) / self.Rstar
+            self.force_in_y = 8.0 * self.visc * self.ustar / float(nx) ** 2
+            self.ystar = self.visc / self.ustar
+            self.force_mag = 1.0
+            self.ivel = False
+            self.MRTtype = 2
+        for k, v in overrides.items():
+            if not hasattr(self, k):
+                raise AttributeError("unknown var_inc scalar %r" % k)
+            setattr(self, k, v)
+        self.set_mrt()
+        for k, v in overrides.items():          # explicit rates win over the MRTtype presets
+            if k.startswith("s") or k.startswith("omeg"):
+                setattr(self, k, v)
+        self.ww0, self.ww1, self.ww2 = 1.0 / 3.0, 1.0 / 18.0, 1.0 / 36.0   # para.f90:172-174
+
+    def set_mrt(self):
+        """para.f90:106-143"""
+        self.tau = 3.0 * self.visc + 0.5
+        self.s9 = 1.0 / self.tau
+        self.s13 = self.s9
+        if self.MRTtype == 1:
+            self.s1, self.s2, self.s4, self.s10, self.s16 = 1.5, 1.4, 1.2, 1.4, 1.98
+            self.omegepsl, self.omegepslj, self.omegxx = 0.0, -475.0 / 63.0, 0.0
+        elif self.MRTtype == 2:
+            self.s1 = self.s2 = self.s4 = self.s10 = self.s16 = self.s9
+            self.omegepsl, self.omegepslj, self.omegxx = 3.0, -11.0 / 2.0, -1.0 / 2.0
+        else:
+            self.s1 = 1.8
+            self.s2 = self.s10 = self.s16 = self.s1
+            self.s4 = self.s9
+            self.omegepsl, self.omegepslj, self.omegxx = 3.0, -11.0 / 2.0, -1.0 / 2.0
+
+
+def slab(nz, nranks, rank):
+    """z-slab of `rank`: para.f90:240-244 (uneven split) and :259-261 (global offset),
+    with nprocY = 1 and nprocZ = nranks."""
+    base, extra = (nz - nz % nranks) // nranks, nz - nranks * (nz // nranks)
+    lz = base + 1 if rank < extra else base
+    globalz = sum((base + 1 if r < extra else base) for r in range(rank))
+    return lz, globalz
+
+
+class ChannelFlow:
+    """One rank (= one GPU) of a Channel-Flow run behind the reference's subroutine names."""
+
+    def __init__(self, nx, ny, nz, laminar=True, rank=0, nranks=1, device=None, scheme=capi.SCHEME_AA,
+                 math_mode=capi.MATH_FAST, nccl_id=None, overlap=True, allocate_host=True, **overrides):
+        self.v = VarInc(nx, ny, nz, laminar, **overrides)
+        self.rank, self.nranks = int(rank), int(nranks)
+        self.lx, self.ly = self.v.nx, self.v.ny
+        self.lz, self.globalz = slab(self.v.nz, self.nranks, self.rank)
+        self.istep = 0
+        self.L = capi.load()
+        cfg = capi.Config()
+        cfg.abi_version = capi.ABI_VERSION
+        cfg.lx, cfg.ly, cfg.lz = self.lx, self.ly, self.lz
+        cfg.nx, cfg.ny, cfg.nz = self.v.nx, self.v.ny, self.v.nz
+        cfg.globalz = self.globalz
+        cfg.rank, cfg.nranks = self.rank, self.nranks
+        cfg.device = int(device if device is not None else 0)
+        cfg.scheme, cfg.math = int(scheme), int(math_mode)
+        cfg.ipart = int(bool(self.v.ipart))
+        cfg.overlap = int(bool(overlap))
+        for k in ("s1", "s2", "s4", "s9", "s10", "s13", "s16", "omegepsl", "omegepslj", "omegxx", "rhopart"):
+            setattr(cfg, k, float(getattr(self.v, k)))
+        if self.nranks > 1:
+            if nccl_id is None or len(nccl_id) != 128:
+                raise ValueError("nranks > 1 needs the 128-byte ncclUniqueId of rank 0")
+            C.memmove(cfg.nccl_id, bytes(nccl_id), 128)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        capi.check(self.L.d3q19_create(C.byref(cfg), C.byref(self.h)))
+        self._bound = False
+        if allocate_host:
+            self.allocarray()
+
+    # ---- para.f90:418-503 ------------------------------------------------------------------
+    def allocarray(self, pinned=False):
+        shp = (self.lz, self.ly, self.lx)
+        if pinned:
+            import torch
+            self._pin = [torch.zeros(shp + (19,), dtype=torch.float64).pin_memory()] + \
+                        [torch.zeros(shp, dtype=torch.float64).pin_memory() for _ in range(7)]
+            arrs = [t.numpy() for t in self._pin]
+        else:
+            arrs = [np.zeros(shp + (19,))] + [np.zeros(shp) for _ in range(7)]
+        (self.f, self.rho, self.ux, self.uy, self.uz,
+         self.force_realx, self.force_realy, self.force_realz) = arrs
+        self.ibnodes = np.full((self.lz + 2, self.ly + 2, self.lx + 2), -1, dtype=np.int32)   # para.f90:442,447
+        self.isnodes = None
+        self._bind()
+
+    def _bind(self):
+        a = capi.ShimArrays()
+        a.f = capi.dptr(self.f)
+        a.rho, a.ux, a.uy, a.uz = (capi.dptr(x) for x in (self.rho, self.ux, self.uy, self.uz))
+        a.force_realx, a.force_realy, a.force_realz = (capi.dptr(x) for x in
+                                                       (self.force_realx, self.force_realy, self.force_realz))
+        a.ibnodes = capi.iptr(self.ibnodes)
+        a.isnodes = capi.iptr(self.isnodes)
+        a.ndiag, a.nflowout = self.v.ndiag, self.v.nflowout
+        a.nsteps_total, a.istep0 = self.v.nsteps, self.v.istep0
+        self._shim_arrays = a
+        capi.check(self.L.d3q19_shim_bind(self.h, C.byref(a)))
+        self._bound = True
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.d3q19_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- initial.f90:75-147 (host, once) ---------------------------------------------------
+    def initvel(self, A9=0.0):
+        v = self.v
+        self.ux[...] = 0.0
+        self.uy[...] = 0.0
+        self.uz[...] = 0.0
+        if not v.ivel:
+            return
+        nx = v.nx
+        nxh = (nx + 1) // 2
+        i = np.arange(1, nxh + 1, dtype=np.float64)
+        yplus = (i - 0.5) / v.ystar
+        prof = np.where(yplus < 10.8, yplus * v.ustar, (np.log(yplus) / 0.41 + 5.0) * v.ustar)
+        self.uy[:, :, :nxh] = prof
+        self.uy[:, :, nx - 1 - np.arange(nxh)] = prof          # uy(nx+1-i) = uy(i)
+        if A9 != 0.0:
+            alpha, beta9, cc = 1.0, 1.0, 60.0
+            ccc1 = -float(v.ny) / v.pi2 / alpha / v.ystar * A9 * v.ustar / cc / cc
+            kk = np.arange(1, self.lz + 1) + self.globalz
+            jj = np.arange(1, self.ly + 1)
+            z9 = (v.pi2 * (kk - 0.5) / float(v.nz))[:, None, None]
+            y9 = (v.pi2 * (jj - 0.5) / float(v.ny))[None, :, None]
+            yp = yplus[None, None, :]
+            ccc9 = np.exp(-yp / cc)
+            ph = alpha * y9 + beta9 * z9
+            du = ccc1 * yp * ccc9 * np.sin(ph)
+            dv = (A9 * v.ustar * (1.0 - ccc9 - yp / cc * ccc9)) * np.cos(ph)
+            mirror = nx - 1 - np.arange(nxh)
+            self.uy[:, :, :nxh] += du
+            np.add.at(self.uy, (slice(None), slice(None), mirror), du)
+            self.ux[:, :, :nxh] += dv
+            np.add.at(self.ux, (slice(None), slice(None), mirror), dv)
+
+    # ---- initial.f90:19-46 (host, once) ----------------------------------------------------
+    def initpop(self):
+        v = self.v
+        usqr = self.ux * self.ux + self.uy * self.uy + self.uz * self.uz
+        usqr = 1.5 * usqr
+        self.rho[...] = 0.0
+        rho = self.rho
+        self.f[..., 0] = v.ww0 * (rho - usqr)
+        for ip in range(1, 19):
+            G = CIX[ip] * self.ux + CIY[ip] * self.uy + CIZ[ip] * self.uz
+            ww = v.ww1 if ip <= 6 else v.ww2
+            self.f[..., ip] = ww * (rho + 3.0 * G + 4.5 * G * G - usqr)
+        capi.check(self.L.d3q19_shim_sync_f_to_device(self.h))
+
+    def host_f_changed(self):
+        """Tell the shim the host copy of f was rewritten (loadcntdflow, saveload.f90:296-332)."""
+        capi.check(self.L.d3q19_shim_sync_f_to_device(self.h))
+
+    def sync_f_to_host(self):
+        """Make host f current (before savecntdflow / saveinitflow, saveload.f90:120,227)."""
+        capi.check(self.L.d3q19_shim_sync_f_to_host(self.h))
+        return self.f
+
+    # ---- the subroutines main.f90 calls ----------------------------------------------------
+    def FORCING(self):
+        capi.check(self.L.d3q19_shim_forcing(self.h, self.v.force_in_y, self.v.force_mag))
+
+    def rhoupdat(self):
+        capi.check(self.L.d3q19_shim_rhoupdat(self.h))
+
+    def collision_MRT(self):
+        capi.check(self.L.d3q19_shim_collision_mrt(self.h))
+
+    def macrovar(self):
+        capi.check(self.L.d3q19_shim_macrovar(self.h, self.istep))
+
+    def avedensity(self):
+        capi.check(self.L.d3q19_shim_avedensity(self.h))
+
+    def probe(self, ix, iy, iz):
+        out = np.zeros(4)
+        capi.check(self.L.d3q19_probe(self.h, ix, iy, iz, capi.dptr(out)))
+        return out
+
+    def profiles(self):
+        out = np.zeros((11, self.lx))
+        capi.check(self.L.d3q19_profiles(self.h, capi.dptr(out)))
+        return out
+
+    # ---- main.f90:70-90 through the intact-driver calls -------------------------------------
+    def prerelax(self, allreduce_max=None, maxiter=15000, verbose=False):
+        self.istep = 0
+        while True:
+            rhop = self.rho.copy()
+            self.rhoupdat()
+            self.collision_MRT()
+            rhoerr = float(np.max(np.abs(self.rho - rhop)))
+            rhoerrmax = allreduce_max(rhoerr) if allreduce_max else rhoerr
+            if verbose:
+                print(self.istep, rhoerrmax)
+            if rhoerrmax <= self.v.rhoepsl or self.istep > maxiter:
+                return self.istep, rhoerrmax
+            self.istep += 1
+
+    # ---- the same loop kept on the device -----------------------------
+    def prerelax_device(self, maxiter=15000):
+        capi.check(self.L.d3q19_upload_f(self.h, capi.dptr(self.f)))
+        capi.check(self.L.d3q19_set_macro(self.h, capi.dptr(self.rho), capi.dptr(self.ux), capi.dptr(self.uy),
+                                          capi.dptr(self.uz)))
+        it, err = C.c_int32(0), C.c_double(0.0)
+        capi.check(self.L.d3q19_prerelax(self.h, self.v.rhoepsl, maxiter, C.byref(it), C.byref(err)))
+        capi.check(self.L.d3q19_download_macro(self.h, capi.dptr(self.rho), None, None, None))
+        capi.check(self.L.d3q19_download_f(self.h, capi.dptr(self.f)))
+        return it.value, err.value
+
+    # ---- main.f90:142-208 -------------------------------------------------------------------
+    def run(self, nsteps=None, on_step=None):
+        v = self.v
+        nsteps = v.nsteps if nsteps is None else nsteps
+        v.nsteps = nsteps
+        capi.check(self.L.d3q19_shim_set_schedule(self.h, v.ndiag, v.nflowout, nsteps, v.istep0))
+        for self.istep in range(v.istep0 + 1, v.istep0 + nsteps + 1):
+            self.collision_MRT()
+            self.macrovar()
+            if v.ipart and self.istep % 100 == 0:
+                self.avedensity()
+            if on_step:
+                on_step(self)
+        return self.istep
+
+    # ---- raw C-ABI conveniences (tests, bench) ------------------------------------------------
+    def upload_f(self, f=None):
+        capi.check(self.L.d3q19_upload_f(self.h, capi.dptr(self.f if f is None else f)))
+
+    def download_f(self, out=None):
+        out = self.f if out is None else out
+        capi.check(self.L.d3q19_download_f(self.h, capi.dptr(out)))
+        return out
+
+    def collide_stream(self, mode=capi.MACRO_MAIN):
+        capi.check(self.L.d3q19_collide_stream(self.h, mode))
+
+    def run_device(self, nsteps):
+        capi.check(self.L.d3q19_run(self.h, nsteps))
+
+    def device_macrovar(self, download=True):
+        capi.check(self.L.d3q19_macrovar(self.h))
+        if download:
+            capi.check(self.L.d3q19_download_macro(self.h, capi.dptr(self.rho), capi.dptr(self.ux),
+                                                   capi.dptr(self.uy), capi.dptr(self.uz)))
+
+    def set_macro(self, rho=None, ux=None, uy=None, uz=None):
+        capi.check(self.L.d3q19_set_macro(self.h, capi.dptr(rho), capi.dptr(ux), capi.dptr(uy), capi.dptr(uz)))
+
+    def set_force_uniform(self, fx, fy, fz):
+        capi.check(self.L.d3q19_set_force_uniform(self.h, fx, fy, fz))
+
+    def set_force_field(self, fx, fy, fz):
+        capi.check(self.L.d3q19_set_force_field(self.h, capi.dptr(fx), capi.dptr(fy), capi.dptr(fz)))
+
+    def sync(self):
+        capi.check(self.L.d3q19_sync(self.h))
+
+    def timer_start(self):
+        capi.check(self.L.d3q19_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0.0)
+        capi.check(self.L.d3q19_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def counters(self):
+        out = (C.c_int64 * 8)()
+        capi.check(self.L.d3q19_get_counters(self.h, out))
+        return dict(step_kernels=out[0], other_kernels=out[1], nccl_ops=out[2], steps=out[3],
+                    population_bytes=out[4], phase=out[5], x_pitch=out[6])

@@ -1,0 +1,865 @@
+// d3q19_api.cu -- the C-ABI of include/d3q19_b200.h: handle, state transfer, step
+// orchestration (split boundary/interior launches, NCCL z-face exchange on a second stream),
+// macrovar / rhoupdat / avedensity / probe / profiles, and the shim state machine that the
+// replacement collision.f90 calls.  There is no CPU path in this file: every entry point
+// that computes launches a kernel from kernels.cuh on the handle's GPU.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/d3q19_b200.h"
+#include "kernels.cuh"
+#include "nccl_dl.h"
+
+using namespace d3q;
+
+// ---- error plumbing ------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        int e_ = (call);                                                                           \
+        if (e_ != 0) return fail("%s:%d %s -> NCCL %s", __FILE__, __LINE__, #call, nccl_api().GetErrorString(e_)); \
+    } while (0)
+#define RK_(call)                                 \
+    do {                                          \
+        int e_ = (call);                          \
+        if (e_ != 0) return e_;                   \
+    } while (0)
+
+extern "C" const char *d3q19_last_error(void) { return g_err.c_str(); }
+
+// ---- the handle --------------------------------------------------------------------------------
+struct Shim {
+    d3q19_shim_arrays a;
+    bool bound = false;
+    bool f_dev_valid = false;     // device populations reflect the latest state
+    bool f_host_valid = false;    // host f(:,:,:,:) reflects the latest state
+    bool macro_dev_valid = false; // device rho,u = moments of the current f (or what the driver set)
+    bool u_dev_loaded = false;    // host ux,uy,uz were uploaded (frozen-u pre-relaxation)
+    int next_mode = D3Q19_MACRO_MAIN;
+};
+
+struct d3q19_handle {
+    d3q19_config cfg;
+    Geom g;
+    size_t nfield = 0;            // xp*ly*lz
+    double *A = nullptr, *B = nullptr;
+    int phase = 0;                // AA: 0 canonical, 1 swapped post-collision.  AB: always post-collision.
+    double *rho = nullptr, *ux = nullptr, *uy = nullptr, *uz = nullptr;
+    double *ffx = nullptr, *ffy = nullptr, *ffz = nullptr;
+    int32_t *solid = nullptr, *isn = nullptr;
+    double *ypglb = nullptr, *wp = nullptr, *omgp = nullptr;
+    int npart = 0;
+    double Fx = 0, Fy = 0, Fz = 0, rho_shift = 0;
+    cudaStream_t sc = nullptr, sx = nullptr;
+    cudaEvent_t evB = nullptr, evX = nullptr, t0 = nullptr, t1 = nullptr, evC[2] = {nullptr, nullptr},
+                evS[2] = {nullptr, nullptr};
+    bool exchange_pending = false;
+    NcclComm comm = nullptr;
+    double *send_up = nullptr, *send_dn = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
+    double *stage[2] = {nullptr, nullptr};
+    int stage_planes = 0;
+    double *scal = nullptr;       // small device scratch (64 doubles)
+    double *red_d = nullptr;      // reduction partials
+    long long *red_c = nullptr;
+    double *prof_partial = nullptr, *prof_out = nullptr;
+    int prof_chunks = 0, prof_rows = 0;
+    long long n_step_kernels = 0, n_other_kernels = 0, n_nccl = 0, n_steps = 0;
+    Shim shim;
+};
+
+static const FaceSlots SLOTS_PZ = {{5, 11, 12, 15, 16}};   // c_z = +1 (collision.f90:337-341)
+static const FaceSlots SLOTS_MZ = {{6, 13, 14, 17, 18}};   // c_z = -1 (collision.f90:343-347)
+
+static inline dim3 grid_nodes(const d3q19_handle *h, int nplanes) {
+    return dim3((unsigned)((h->g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)h->g.ly, (unsigned)nplanes);
+}
+
+static int read_kind(const d3q19_handle *h) {
+    if (h->cfg.scheme == D3Q19_SCHEME_AB) return READ_PULL_NAT;
+    return h->phase == 0 ? READ_DIRECT : READ_PULL_SWAP;
+}
+
+static int ensure_macro_arrays(d3q19_handle *h) {
+    if (h->rho) return 0;
+    const size_t bytes = h->nfield * sizeof(double);
+    CK(cudaMalloc(&h->rho, bytes)); CK(cudaMalloc(&h->ux, bytes));
+    CK(cudaMalloc(&h->uy, bytes)); CK(cudaMalloc(&h->uz, bytes));
+    CK(cudaMemsetAsync(h->rho, 0, bytes, h->sc)); CK(cudaMemsetAsync(h->ux, 0, bytes, h->sc));
+    CK(cudaMemsetAsync(h->uy, 0, bytes, h->sc)); CK(cudaMemsetAsync(h->uz, 0, bytes, h->sc));
+    return 0;
+}
+
+static int ensure_stage(d3q19_handle *h) {
+    if (h->stage[0]) return 0;
+    const size_t per_plane = (size_t)NPOP * h->g.lx * h->g.ly * sizeof(double);
+    size_t planes = (size_t)(192u << 20) / per_plane;
+    if (planes < 1) planes = 1;
+    if (planes > (size_t)h->g.lz) planes = (size_t)h->g.lz;
+    h->stage_planes = (int)planes;
+    CK(cudaMalloc(&h->stage[0], planes * per_plane));
+    CK(cudaMalloc(&h->stage[1], planes * per_plane));
+    return 0;
+}
+
+// sc must not read ghost/boundary data before the last exchange finished
+static int wait_exchange(d3q19_handle *h) {
+    if (h->exchange_pending) {
+        CK(cudaStreamWaitEvent(h->sc, h->evX, 0));
+        h->exchange_pending = false;
+    }
+    return 0;
+}
+
+// ---- z-face exchange (collisionExchnge's z phase, collision.f90:337-370) --------------------------
+// "up" data goes to the +z neighbour, which stores it at plane lo_dst; "dn" data goes to the
+// -z neighbour, which stores it at plane hi_dst.  Runs on h->sx after `after` (an event on sc).
+static int exchange_faces(d3q19_handle *h, double *arr, int up_src, const FaceSlots &up_slots, int lo_dst,
+                          int dn_src, const FaceSlots &dn_slots, int hi_dst, int exclude_walls, cudaStream_t s) {
+    const Geom &g = h->g;
+    const size_t cnt = (size_t)5 * g.plane;
+    const int up = (h->cfg.rank + 1) % h->cfg.nranks;                       // mzp, para.f90:266
+    const int dn = (h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks;       // mzm, para.f90:267
+    const dim3 gp((unsigned)((g.xp + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 5u);
+    k_face_pack<<<gp, BLOCK_X, 0, s>>>(g, arr, h->send_up, up_src, up_slots);
+    k_face_pack<<<gp, BLOCK_X, 0, s>>>(g, arr, h->send_dn, dn_src, dn_slots);
+    CK(cudaGetLastError());
+    NcclApi &n = nccl_api();
+    NK(n.GroupStart());
+    NK(n.Send(h->send_up, cnt, NCCL_FLOAT64, up, h->comm, s));
+    NK(n.Send(h->send_dn, cnt, NCCL_FLOAT64, dn, h->comm, s));
+    NK(n.Recv(h->recv_lo, cnt, NCCL_FLOAT64, dn, h->comm, s));
+    NK(n.Recv(h->recv_hi, cnt, NCCL_FLOAT64, up, h->comm, s));
+    NK(n.GroupEnd());
+    const dim3 gu((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 5u);
+    k_face_unpack<<<gu, BLOCK_X, 0, s>>>(g, arr, h->recv_lo, lo_dst, up_slots, exclude_walls);
+    k_face_unpack<<<gu, BLOCK_X, 0, s>>>(g, arr, h->recv_hi, hi_dst, dn_slots, exclude_walls);
+    CK(cudaGetLastError());
+    h->n_other_kernels += 4;
+    h->n_nccl += 4;
+    return 0;
+}
+
+// the exchange that must follow a step of the given kind
+static int exchange_after_step(d3q19_handle *h, int step_kind, double *arr, cudaStream_t s) {
+    const int lz = h->g.lz;
+    switch (step_kind) {
+    case STEP_AB:       // post-collision, natural slots: my plane lz (c_z=+1 slots) -> +z ghost 0
+        return exchange_faces(h, arr, lz, SLOTS_PZ, 0, 1, SLOTS_MZ, lz + 1, 0, s);
+    case STEP_AA_EVEN:  // post-collision, swapped slots: f*_i sits in slot opp(i)
+        return exchange_faces(h, arr, lz, SLOTS_MZ, 0, 1, SLOTS_PZ, lz + 1, 0, s);
+    default:            // AA odd pushed across the faces into my ghosts: ghost -> neighbour's real plane
+        return exchange_faces(h, arr, lz + 1, SLOTS_PZ, 1, 0, SLOTS_MZ, lz, 1, s);
+    }
+}
+
+// ---- life cycle ----------------------------------------------------------------------------------
+extern "C" int d3q19_device_count(int32_t *n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *n = 0; return fail("cudaGetDeviceCount -> %s", cudaGetErrorString(e)); }
+    *n = c;
+    return 0;
+}
+
+extern "C" int d3q19_nccl_unique_id(unsigned char out[128]) {
+    NcclApi &n = nccl_api();
+    if (const char *m = n.load()) return fail("%s", m);
+    NcclUniqueId id;
+    NK(n.GetUniqueId(&id));
+    memcpy(out, id.internal, 128);
+    return 0;
+}
+
+extern "C" int d3q19_destroy(d3q19_handle *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    if (h->sc) cudaStreamSynchronize(h->sc);
+    if (h->sx) cudaStreamSynchronize(h->sx);
+    if (h->comm) nccl_api().CommDestroy(h->comm);
+    void *ptrs[] = {h->A, h->B, h->rho, h->ux, h->uy, h->uz, h->ffx, h->ffy, h->ffz, h->solid, h->isn, h->ypglb,
+                    h->wp, h->omgp, h->send_up, h->send_dn, h->recv_lo, h->recv_hi, h->stage[0], h->stage[1],
+                    h->scal, h->red_d, h->red_c, h->prof_partial, h->prof_out};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    cudaEvent_t evs[] = {h->evB, h->evX, h->t0, h->t1, h->evC[0], h->evC[1], h->evS[0], h->evS[1]};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    if (h->sc) cudaStreamDestroy(h->sc);
+    if (h->sx) cudaStreamDestroy(h->sx);
+    delete h;
+    return 0;
+}
+
+extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
+    if (!cfg || !out) return fail("d3q19_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != D3Q19_ABI_VERSION)
+        return fail("d3q19_create: abi_version %d, library speaks %d", cfg->abi_version, D3Q19_ABI_VERSION);
+    if (cfg->lx < 2 || cfg->ly < 1 || cfg->lz < 1) return fail("d3q19_create: bad local extents %d %d %d", cfg->lx, cfg->ly, cfg->lz);
+    if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail("d3q19_create: bad rank %d of %d", cfg->rank, cfg->nranks);
+    if (cfg->scheme != D3Q19_SCHEME_AA && cfg->scheme != D3Q19_SCHEME_AB) return fail("d3q19_create: unknown scheme %d", cfg->scheme);
+    if (cfg->ly > 65535 || cfg->lz + 2 > 65535) return fail("d3q19_create: ly, lz must be < 65535");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail("d3q19_create: no CUDA device -- this library has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("d3q19_create: device %d of %d", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+
+    d3q19_handle *h = new (std::nothrow) d3q19_handle();
+    if (!h) return fail("d3q19_create: out of host memory");
+    h->cfg = *cfg;
+    Geom &g = h->g;
+    g.lx = cfg->lx; g.ly = cfg->ly; g.lz = cfg->lz;
+    g.xp = (cfg->lx + 15) / 16 * 16;
+    g.plane = (long long)g.xp * g.ly;
+    g.slab = g.plane * (g.lz + 2);
+    g.zlo_src = cfg->nranks == 1 ? g.lz : 0;
+    g.zhi_src = cfg->nranks == 1 ? 1 : g.lz + 1;
+    h->nfield = (size_t)g.plane * g.lz;
+
+#define CKH(call)                                                      \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) {                                       \
+            fail("d3q19_create: %s -> %s", #call, cudaGetErrorString(e_)); \
+            d3q19_destroy(h);                                          \
+            return 1;                                                  \
+        }                                                              \
+    } while (0)
+    int lo = 0, hi = 0;
+    CKH(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CKH(cudaStreamCreateWithPriority(&h->sc, cudaStreamNonBlocking, lo));
+    CKH(cudaStreamCreateWithPriority(&h->sx, cudaStreamNonBlocking, hi));
+    CKH(cudaEventCreateWithFlags(&h->evB, cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->evX, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CKH(cudaEventCreateWithFlags(&h->evC[i], cudaEventDisableTiming));
+        CKH(cudaEventCreateWithFlags(&h->evS[i], cudaEventDisableTiming));
+    }
+    CKH(cudaEventCreate(&h->t0));
+    CKH(cudaEventCreate(&h->t1));
+    const size_t fbytes = (size_t)NPOP * g.slab * sizeof(double);
+    CKH(cudaMalloc(&h->A, fbytes));
+    CKH(cudaMemsetAsync(h->A, 0, fbytes, h->sc));
+    if (cfg->scheme == D3Q19_SCHEME_AB) {
+        CKH(cudaMalloc(&h->B, fbytes));
+        CKH(cudaMemsetAsync(h->B, 0, fbytes, h->sc));
+    }
+    CKH(cudaMalloc(&h->scal, 64 * sizeof(double)));
+    CKH(cudaMemsetAsync(h->scal, 0, 64 * sizeof(double), h->sc));
+    if (cfg->nranks > 1) {
+        NcclApi &n = nccl_api();
+        if (const char *m = n.load()) { fail("d3q19_create: %s", m); d3q19_destroy(h); return 1; }
+        NcclUniqueId id;
+        memcpy(id.internal, cfg->nccl_id, 128);
+        int e = n.CommInitRank(&h->comm, cfg->nranks, id, cfg->rank);
+        if (e != 0) { fail("d3q19_create: ncclCommInitRank -> %s", n.GetErrorString(e)); h->comm = nullptr; d3q19_destroy(h); return 1; }
+        const size_t fb = (size_t)5 * g.plane * sizeof(double);
+        CKH(cudaMalloc(&h->send_up, fb)); CKH(cudaMalloc(&h->send_dn, fb));
+        CKH(cudaMalloc(&h->recv_lo, fb)); CKH(cudaMalloc(&h->recv_hi, fb));
+    }
+    CKH(cudaStreamSynchronize(h->sc));
+#undef CKH
+    *out = h;
+    return 0;
+}
+
+extern "C" int d3q19_sync(d3q19_handle *h) {
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->sc));
+    CK(cudaStreamSynchronize(h->sx));
+    return 0;
+}
+
+// ---- state transfer ----------------------------------------------------------------------------------
+extern "C" int d3q19_upload_f(d3q19_handle *h, const double *f_aos) {
+    CK(cudaSetDevice(h->cfg.device));
+    RK_(ensure_stage(h));
+    RK_(wait_exchange(h));
+    const Geom &g = h->g;
+    const size_t per_plane = (size_t)NPOP * g.lx * g.ly;
+    // canonical populations land in A (AA) or in B (AB, un-streamed into A below)
+    double *dst = h->cfg.scheme == D3Q19_SCHEME_AB ? h->B : h->A;
+    int c = 0;
+    for (int z0 = 0; z0 < g.lz; z0 += h->stage_planes, ++c) {
+        const int nz = (z0 + h->stage_planes <= g.lz) ? h->stage_planes : g.lz - z0;
+        const int b = c & 1;
+        if (c >= 2) CK(cudaStreamWaitEvent(h->sx, h->evS[b], 0));          // stage b free again
+        CK(cudaMemcpyAsync(h->stage[b], f_aos + (size_t)z0 * per_plane, (size_t)nz * per_plane * sizeof(double),
+                           cudaMemcpyHostToDevice, h->sx));
+        CK(cudaEventRecord(h->evC[b], h->sx));
+        CK(cudaStreamWaitEvent(h->sc, h->evC[b], 0));
+        k_scatter_aos<<<grid_nodes(h, nz), BLOCK_X, 0, h->sc>>>(g, dst, h->stage[b], 1 + z0);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->evS[b], h->sc));
+        h->n_other_kernels++;
+    }
+    if (h->cfg.scheme == D3Q19_SCHEME_AB) {
+        if (h->cfg.nranks > 1) {
+            // canonical neighbours of the boundary planes: plane lz (c_z=-1 slots) -> +z ghost 0,
+            // plane 1 (c_z=+1 slots) -> -z ghost lz+1
+            CK(cudaEventRecord(h->evB, h->sc));
+            CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
+            RK_(exchange_faces(h, h->B, g.lz, SLOTS_MZ, 0, 1, SLOTS_PZ, g.lz + 1, 0, h->sx));
+            CK(cudaEventRecord(h->evX, h->sx));
+            CK(cudaStreamWaitEvent(h->sc, h->evX, 0));
+        }
+        k_unstream<<<grid_nodes(h, g.lz), BLOCK_X, 0, h->sc>>>(g, h->B, h->A);
+        CK(cudaGetLastError());
+        h->n_other_kernels++;
+        if (h->cfg.nranks > 1) {
+            CK(cudaEventRecord(h->evB, h->sc));
+            CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
+            RK_(exchange_after_step(h, STEP_AB, h->A, h->sx));
+            CK(cudaEventRecord(h->evX, h->sx));
+            h->exchange_pending = true;
+        }
+    }
+    h->phase = 0;
+    CK(cudaStreamSynchronize(h->sx));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+template <int RKIND>
+static int download_f_impl(d3q19_handle *h, double *f_aos) {
+    const Geom &g = h->g;
+    const size_t per_plane = (size_t)NPOP * g.lx * g.ly;
+    int c = 0;
+    for (int z0 = 0; z0 < g.lz; z0 += h->stage_planes, ++c) {
+        const int nz = (z0 + h->stage_planes <= g.lz) ? h->stage_planes : g.lz - z0;
+        const int b = c & 1;
+        if (c >= 2) CK(cudaStreamWaitEvent(h->sc, h->evC[b], 0));          // copy-out of stage b finished
+        k_gather_aos<RKIND><<<grid_nodes(h, nz), BLOCK_X, 0, h->sc>>>(g, h->A, h->stage[b], 1 + z0);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->evS[b], h->sc));
+        CK(cudaStreamWaitEvent(h->sx, h->evS[b], 0));
+        CK(cudaMemcpyAsync(f_aos + (size_t)z0 * per_plane, h->stage[b], (size_t)nz * per_plane * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->sx));
+        CK(cudaEventRecord(h->evC[b], h->sx));
+        h->n_other_kernels++;
+    }
+    CK(cudaStreamSynchronize(h->sx));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+extern "C" int d3q19_download_f(d3q19_handle *h, double *f_aos) {
+    CK(cudaSetDevice(h->cfg.device));
+    RK_(ensure_stage(h));
+    RK_(wait_exchange(h));
+    switch (read_kind(h)) {
+    case READ_DIRECT: return download_f_impl<READ_DIRECT>(h, f_aos);
+    case READ_PULL_NAT: return download_f_impl<READ_PULL_NAT>(h, f_aos);
+    default: return download_f_impl<READ_PULL_SWAP>(h, f_aos);
+    }
+}
+
+// pitched device field <-> host (lx,ly,lz) through the staging buffer
+static int field_to_host(d3q19_handle *h, const double *dev, double *host) {
+    if (!host) return 0;
+    const Geom &g = h->g;
+    RK_(ensure_stage(h));
+    if (g.xp == g.lx) {
+        CK(cudaMemcpyAsync(host, dev, h->nfield * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
+        return 0;
+    }
+    CK(cudaMemcpy2DAsync(host, (size_t)g.lx * sizeof(double), dev, (size_t)g.xp * sizeof(double),
+                         (size_t)g.lx * sizeof(double), (size_t)g.ly * g.lz, cudaMemcpyDeviceToHost, h->sc));
+    return 0;
+}
+static int field_from_host(d3q19_handle *h, double *dev, const double *host) {
+    if (!host) return 0;
+    const Geom &g = h->g;
+    CK(cudaMemcpy2DAsync(dev, (size_t)g.xp * sizeof(double), host, (size_t)g.lx * sizeof(double),
+                         (size_t)g.lx * sizeof(double), (size_t)g.ly * g.lz, cudaMemcpyHostToDevice, h->sc));
+    return 0;
+}
+
+extern "C" int d3q19_set_macro(d3q19_handle *h, const double *rho, const double *ux, const double *uy, const double *uz) {
+    CK(cudaSetDevice(h->cfg.device));
+    RK_(ensure_macro_arrays(h));
+    RK_(field_from_host(h, h->rho, rho)); RK_(field_from_host(h, h->ux, ux));
+    RK_(field_from_host(h, h->uy, uy)); RK_(field_from_host(h, h->uz, uz));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+extern "C" int d3q19_download_macro(d3q19_handle *h, double *rho, double *ux, double *uy, double *uz) {
+    CK(cudaSetDevice(h->cfg.device));
+    RK_(ensure_macro_arrays(h));
+    RK_(field_to_host(h, h->rho, rho)); RK_(field_to_host(h, h->ux, ux));
+    RK_(field_to_host(h, h->uy, uy)); RK_(field_to_host(h, h->uz, uz));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+// ---- forcing ---------------------------------------------------------------------------------------
+extern "C" int d3q19_set_force_uniform(d3q19_handle *h, double fx, double fy, double fz) {
+    CK(cudaSetDevice(h->cfg.device));
+    h->Fx = fx; h->Fy = fy; h->Fz = fz;
+    if (h->ffx) {
+        CK(cudaStreamSynchronize(h->sc));
+        cudaFree(h->ffx); cudaFree(h->ffy); cudaFree(h->ffz);
+        h->ffx = h->ffy = h->ffz = nullptr;
+    }
+    return 0;
+}
+
+extern "C" int d3q19_set_force_field(d3q19_handle *h, const double *fx, const double *fy, const double *fz) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!fx || !fy || !fz) return fail("d3q19_set_force_field: null array");
+    const size_t bytes = h->nfield * sizeof(double);
+    if (!h->ffx) {
+        CK(cudaMalloc(&h->ffx, bytes)); CK(cudaMalloc(&h->ffy, bytes)); CK(cudaMalloc(&h->ffz, bytes));
+        CK(cudaMemsetAsync(h->ffx, 0, bytes, h->sc)); CK(cudaMemsetAsync(h->ffy, 0, bytes, h->sc));
+        CK(cudaMemsetAsync(h->ffz, 0, bytes, h->sc));
+    }
+    RK_(field_from_host(h, h->ffx, fx)); RK_(field_from_host(h, h->ffy, fy)); RK_(field_from_host(h, h->ffz, fz));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+// ---- the step ----------------------------------------------------------------------------------------
+template <int SK, bool STRICT, bool GENERIC>
+static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int nplanes, cudaStream_t s) {
+    if (nplanes <= 0) return 0;
+    StepParams p = p0;
+    p.z0 = z0;
+    k_step<SK, STRICT, GENERIC><<<grid_nodes(h, nplanes), BLOCK_X, 0, s>>>(p);
+    CK(cudaGetLastError());
+    h->n_step_kernels++;
+    return 0;
+}
+
+template <int SK, bool STRICT, bool GENERIC>
+static int step_impl(d3q19_handle *h, const StepParams &p, double *written) {
+    const int lz = h->g.lz;
+    if (h->cfg.nranks == 1) return launch_step_range<SK, STRICT, GENERIC>(h, p, 1, lz, h->sc);
+    // boundary planes first, so that their faces travel while the interior is computed
+    RK_(wait_exchange(h));
+    if (h->cfg.overlap && lz > 2) {
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 1, h->sc)));
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, lz, 1, h->sc)));
+        CK(cudaEventRecord(h->evB, h->sc));
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 2, lz - 2, h->sc)));
+    } else {
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, lz, h->sc)));
+        CK(cudaEventRecord(h->evB, h->sc));
+    }
+    CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
+    RK_(exchange_after_step(h, SK, written, h->sx));
+    CK(cudaEventRecord(h->evX, h->sx));
+    h->exchange_pending = true;
+    return 0;
+}
+
+template <bool STRICT, bool GENERIC>
+static int step_dispatch(d3q19_handle *h, StepParams &p) {
+    if (h->cfg.scheme == D3Q19_SCHEME_AB) {
+        p.A = h->A; p.B = h->B;
+        RK_((step_impl<STEP_AB, STRICT, GENERIC>(h, p, h->B)));
+        double *t = h->A; h->A = h->B; h->B = t;
+    } else if (h->phase == 0) {
+        p.A = h->A; p.B = nullptr;
+        RK_((step_impl<STEP_AA_EVEN, STRICT, GENERIC>(h, p, h->A)));
+        h->phase = 1;
+    } else {
+        p.A = h->A; p.B = nullptr;
+        RK_((step_impl<STEP_AA_ODD, STRICT, GENERIC>(h, p, h->A)));
+        h->phase = 0;
+    }
+    h->n_steps++;
+    return 0;
+}
+
+static int collide_stream_impl(d3q19_handle *h, int macro_mode, unsigned long long *rhoerr_bits) {
+    if (macro_mode < 0 || macro_mode > 2) return fail("d3q19_collide_stream: bad macro_mode %d", macro_mode);
+    StepParams p;
+    memset(&p, 0, sizeof p);
+    p.g = h->g;
+    p.mrt = Mrt{h->cfg.s1, h->cfg.s2, h->cfg.s4, h->cfg.s9, h->cfg.s10, h->cfg.s13, h->cfg.s16,
+                h->cfg.omegepsl, h->cfg.omegepslj, h->cfg.omegxx};
+    p.Fx = h->Fx; p.Fy = h->Fy; p.Fz = h->Fz;
+    p.rho_shift = h->rho_shift;
+    p.macro_mode = macro_mode;
+    const bool generic = macro_mode != D3Q19_MACRO_MAIN || h->ffx || h->solid || h->rho_shift != 0.0;
+    if (macro_mode != D3Q19_MACRO_MAIN) RK_(ensure_macro_arrays(h));
+    p.rho = h->rho; p.ux = h->ux; p.uy = h->uy; p.uz = h->uz;
+    p.ffx = h->ffx; p.ffy = h->ffy; p.ffz = h->ffz;
+    p.solid = h->solid;
+    p.rhoerr_bits = rhoerr_bits;
+    const bool strict = h->cfg.math == D3Q19_MATH_STRICT;
+    int rc;
+    if (generic) rc = strict ? step_dispatch<true, true>(h, p) : step_dispatch<false, true>(h, p);
+    else rc = strict ? step_dispatch<true, false>(h, p) : step_dispatch<false, false>(h, p);
+    if (rc) return rc;
+    if (macro_mode == D3Q19_MACRO_MAIN) h->rho_shift = 0.0;   // the shift lives for one collision (macrovar recomputes rho)
+    return 0;
+}
+
+extern "C" int d3q19_collide_stream(d3q19_handle *h, int32_t macro_mode) {
+    CK(cudaSetDevice(h->cfg.device));
+    return collide_stream_impl(h, macro_mode, nullptr);
+}
+
+extern "C" int d3q19_run(d3q19_handle *h, int32_t nsteps) {
+    CK(cudaSetDevice(h->cfg.device));
+    for (int i = 0; i < nsteps; ++i) RK_(collide_stream_impl(h, D3Q19_MACRO_MAIN, nullptr));
+    return 0;
+}
+
+// ---- macrovar / rhoupdat ---------------------------------------------------------------------------------
+static int macro_launch(d3q19_handle *h, int rho_only) {
+    RK_(ensure_macro_arrays(h));
+    RK_(wait_exchange(h));
+    MacroParams p;
+    memset(&p, 0, sizeof p);
+    p.g = h->g; p.A = h->A;
+    p.rho = h->rho; p.ux = h->ux; p.uy = h->uy; p.uz = h->uz;
+    p.Fx = h->Fx; p.Fy = h->Fy; p.Fz = h->Fz;
+    p.ffx = h->ffx; p.ffy = h->ffy; p.ffz = h->ffz;
+    p.solid = h->solid; p.isnodes = h->isn;
+    p.ypglb = h->ypglb; p.wp = h->wp; p.omgp = h->omgp;
+    p.rhopart = h->cfg.rhopart;
+    p.ipart = h->cfg.ipart && h->isn && h->ypglb;
+    p.ny = h->cfg.ny; p.nz = h->cfg.nz; p.globalz = h->cfg.globalz;
+    p.rho_only = rho_only;
+    const dim3 gr = grid_nodes(h, h->g.lz);
+    switch (read_kind(h)) {
+    case READ_DIRECT: k_macro<READ_DIRECT><<<gr, BLOCK_X, 0, h->sc>>>(p); break;
+    case READ_PULL_NAT: k_macro<READ_PULL_NAT><<<gr, BLOCK_X, 0, h->sc>>>(p); break;
+    default: k_macro<READ_PULL_SWAP><<<gr, BLOCK_X, 0, h->sc>>>(p); break;
+    }
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    return 0;
+}
+
+extern "C" int d3q19_macrovar(d3q19_handle *h) {
+    CK(cudaSetDevice(h->cfg.device));
+    h->rho_shift = 0.0;     // macrovar recomputes rho from f: a pending avedensity shift is gone (collision.f90:418)
+    return macro_launch(h, 0);
+}
+
+extern "C" int d3q19_rhoupdat(d3q19_handle *h) {
+    CK(cudaSetDevice(h->cfg.device));
+    return macro_launch(h, 1);
+}
+
+extern "C" int d3q19_probe(d3q19_handle *h, int32_t ix, int32_t iy, int32_t iz, double out4[4]) {
+    CK(cudaSetDevice(h->cfg.device));
+    const Geom &g = h->g;
+    if (ix < 1 || ix > g.lx || iy < 1 || iy > g.ly || iz < 1 || iz > g.lz) return fail("d3q19_probe: node out of range");
+    RK_(wait_exchange(h));
+    switch (read_kind(h)) {
+    case READ_DIRECT: k_probe<READ_DIRECT><<<1, 1, 0, h->sc>>>(g, h->A, ix - 1, iy - 1, iz, h->Fx, h->Fy, h->Fz, h->scal); break;
+    case READ_PULL_NAT: k_probe<READ_PULL_NAT><<<1, 1, 0, h->sc>>>(g, h->A, ix - 1, iy - 1, iz, h->Fx, h->Fy, h->Fz, h->scal); break;
+    default: k_probe<READ_PULL_SWAP><<<1, 1, 0, h->sc>>>(g, h->A, ix - 1, iy - 1, iz, h->Fx, h->Fy, h->Fz, h->scal); break;
+    }
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    CK(cudaMemcpyAsync(out4, h->scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+// ---- avedensity (collision.f90:487-513) ----------------------------------------------------------------------
+extern "C" int d3q19_avedensity(d3q19_handle *h, double *rhomean, int64_t *nfluid_total) {
+    CK(cudaSetDevice(h->cfg.device));
+    RK_(ensure_macro_arrays(h));
+    const Geom &g = h->g;
+    const int nblk = 1024;
+    if (!h->red_d) {
+        CK(cudaMalloc(&h->red_d, nblk * sizeof(double)));
+        CK(cudaMalloc(&h->red_c, (nblk + 8) * sizeof(long long)));
+    }
+    const long long nrows = (long long)g.ly * g.lz;
+    double *sum_dev = h->scal + 8;
+    long long *cnt_dev = h->red_c + nblk;
+    k_rho_partial<<<nblk, 256, 0, h->sc>>>(g.lx, g.xp, nrows, h->rho, h->solid, h->red_d, h->red_c);
+    k_rho_final<<<1, 32, 0, h->sc>>>(nblk, h->red_d, h->red_c, sum_dev, cnt_dev);
+    CK(cudaGetLastError());
+    h->n_other_kernels += 2;
+    if (h->cfg.nranks > 1) {           // MPI_ALLREDUCE x2, collision.f90:500-501
+        NcclApi &n = nccl_api();
+        NK(n.GroupStart());
+        NK(n.AllReduce(sum_dev, sum_dev, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
+        NK(n.AllReduce(cnt_dev, cnt_dev, 1, NCCL_INT64, NCCL_SUM, h->comm, h->sc));
+        NK(n.GroupEnd());
+        h->n_nccl += 2;
+    }
+    double s = 0;
+    long long c = 0;
+    CK(cudaMemcpyAsync(&s, sum_dev, sizeof s, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaMemcpyAsync(&c, cnt_dev, sizeof c, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    if (c <= 0) return fail("d3q19_avedensity: no fluid nodes");
+    const double mean = s / (double)c;                                 // collision.f90:503
+    double *mean_dev = h->scal + 9;
+    CK(cudaMemcpyAsync(mean_dev, &mean, sizeof mean, cudaMemcpyHostToDevice, h->sc));
+    k_rho_shift<<<grid_nodes(h, g.lz), BLOCK_X, 0, h->sc>>>(g.lx, g.xp, h->rho, mean_dev);
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    CK(cudaStreamSynchronize(h->sc));
+    h->rho_shift += mean;      // what the next collision_MRT sees in its rho array
+    if (rhomean) *rhomean = mean;
+    if (nfluid_total) *nfluid_total = c;
+    return 0;
+}
+
+// ---- device pre-relaxation (main.f90:70-90) -----------------------------------------------------------------------
+extern "C" int d3q19_prerelax(d3q19_handle *h, double tol, int32_t maxiter, int32_t *iters, double *rhoerrmax) {
+    CK(cudaSetDevice(h->cfg.device));
+    RK_(ensure_macro_arrays(h));
+    unsigned long long *bits = reinterpret_cast<unsigned long long *>(h->scal + 16);
+    int istep = 0;
+    double err = 0.0;
+    for (;;) {
+        CK(cudaMemsetAsync(bits, 0, sizeof(unsigned long long), h->sc));
+        RK_(collide_stream_impl(h, D3Q19_MACRO_PRERELAX, bits));      // rhoupdat fused into the collision
+        if (h->cfg.nranks > 1) {                                       // MPI_ALLREDUCE MAX, main.f90:80
+            NK(nccl_api().AllReduce(bits, bits, 1, NCCL_UINT64, NCCL_MAX, h->comm, h->sc));
+            h->n_nccl++;
+        }
+        unsigned long long b = 0;
+        CK(cudaMemcpyAsync(&b, bits, sizeof b, cudaMemcpyDeviceToHost, h->sc));
+        CK(cudaStreamSynchronize(h->sc));
+        memcpy(&err, &b, sizeof err);
+        if (err <= tol || istep > maxiter) break;                     // main.f90:85
+        istep++;
+    }
+    if (iters) *iters = istep;
+    if (rhoerrmax) *rhoerrmax = err;
+    return 0;
+}
+
+// ---- particles: masks and tables -------------------------------------------------------------------------------------
+extern "C" int d3q19_set_solid_mask(d3q19_handle *h, const int32_t *ibnodes_ghosted, const int32_t *isnodes) {
+    CK(cudaSetDevice(h->cfg.device));
+    const Geom &g = h->g;
+    if (!ibnodes_ghosted) {
+        if (h->solid) { CK(cudaStreamSynchronize(h->sc)); cudaFree(h->solid); h->solid = nullptr; }
+        return 0;
+    }
+    const size_t nb = h->nfield * sizeof(int32_t);
+    if (!h->solid) CK(cudaMalloc(&h->solid, nb));
+    const size_t nghost = (size_t)(g.lx + 2) * (g.ly + 2) * (g.lz + 2);
+    int32_t *tmp = nullptr;
+    CK(cudaMalloc(&tmp, nghost * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(tmp, ibnodes_ghosted, nghost * sizeof(int32_t), cudaMemcpyHostToDevice, h->sc));
+    k_field_unpack_i32<<<grid_nodes(h, g.lz), BLOCK_X, 0, h->sc>>>(g.lx, g.xp, h->solid, tmp, 1, g.ly);
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    if (isnodes) {
+        if (!h->isn) CK(cudaMalloc(&h->isn, nb));
+        CK(cudaMemcpyAsync(tmp, isnodes, (size_t)g.lx * g.ly * g.lz * sizeof(int32_t), cudaMemcpyHostToDevice, h->sc));
+        k_field_unpack_i32<<<grid_nodes(h, g.lz), BLOCK_X, 0, h->sc>>>(g.lx, g.xp, h->isn, tmp, 0, g.ly);
+        CK(cudaGetLastError());
+        h->n_other_kernels++;
+    }
+    CK(cudaStreamSynchronize(h->sc));
+    cudaFree(tmp);
+    return 0;
+}
+
+extern "C" int d3q19_set_particles(d3q19_handle *h, int32_t npart, const double *ypglb, const double *wp, const double *omgp) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (npart <= 0 || !ypglb || !wp || !omgp) return fail("d3q19_set_particles: bad arguments");
+    const size_t nb = (size_t)3 * npart * sizeof(double);
+    if (npart != h->npart) {
+        CK(cudaStreamSynchronize(h->sc));
+        if (h->ypglb) { cudaFree(h->ypglb); cudaFree(h->wp); cudaFree(h->omgp); }
+        CK(cudaMalloc(&h->ypglb, nb)); CK(cudaMalloc(&h->wp, nb)); CK(cudaMalloc(&h->omgp, nb));
+        h->npart = npart;
+    }
+    CK(cudaMemcpyAsync(h->ypglb, ypglb, nb, cudaMemcpyHostToDevice, h->sc));
+    CK(cudaMemcpyAsync(h->wp, wp, nb, cudaMemcpyHostToDevice, h->sc));
+    CK(cudaMemcpyAsync(h->omgp, omgp, nb, cudaMemcpyHostToDevice, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+// ---- profiles (statistc, saveload.f90:1241-1300) -------------------------------------------------------------------------
+extern "C" int d3q19_profiles(d3q19_handle *h, double *out) {
+    CK(cudaSetDevice(h->cfg.device));
+    const Geom &g = h->g;
+    RK_(wait_exchange(h));
+    const long long nrows = (long long)g.ly * g.lz;
+    if (!h->prof_partial) {
+        int chunks = 296;                                     // 2 per SM
+        if (chunks > nrows) chunks = (int)nrows;
+        h->prof_rows = (int)((nrows + chunks - 1) / chunks);
+        h->prof_chunks = (int)((nrows + h->prof_rows - 1) / h->prof_rows);
+        CK(cudaMalloc(&h->prof_partial, (size_t)h->prof_chunks * NPROF * g.lx * sizeof(double)));
+        CK(cudaMalloc(&h->prof_out, (size_t)NPROF * g.lx * sizeof(double)));
+    }
+    const dim3 gr((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)h->prof_chunks);
+    switch (read_kind(h)) {
+    case READ_DIRECT: k_profiles<READ_DIRECT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, h->prof_rows, h->prof_partial); break;
+    case READ_PULL_NAT: k_profiles<READ_PULL_NAT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, h->prof_rows, h->prof_partial); break;
+    default: k_profiles<READ_PULL_SWAP><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, h->prof_rows, h->prof_partial); break;
+    }
+    const dim3 g2((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), NPROF);
+    k_profiles_final<<<g2, BLOCK_X, 0, h->sc>>>(g.lx, h->prof_chunks, h->prof_partial, h->prof_out);
+    CK(cudaGetLastError());
+    h->n_other_kernels += 2;
+    if (h->cfg.nranks > 1) {
+        NK(nccl_api().AllReduce(h->prof_out, h->prof_out, (size_t)NPROF * g.lx, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
+        h->n_nccl++;
+    }
+    CK(cudaMemcpyAsync(out, h->prof_out, (size_t)NPROF * g.lx * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+// ---- measurement ---------------------------------------------------------------------------------------------------
+extern "C" int d3q19_timer_start(d3q19_handle *h) {
+    CK(cudaSetDevice(h->cfg.device));
+    RK_(wait_exchange(h));
+    CK(cudaEventRecord(h->t0, h->sc));
+    return 0;
+}
+
+extern "C" int d3q19_timer_stop(d3q19_handle *h, float *ms) {
+    CK(cudaSetDevice(h->cfg.device));
+    RK_(wait_exchange(h));     // the last exchange is part of the last step
+    CK(cudaEventRecord(h->t1, h->sc));
+    CK(cudaEventSynchronize(h->t1));
+    CK(cudaEventElapsedTime(ms, h->t0, h->t1));
+    return 0;
+}
+
+extern "C" int d3q19_get_counters(d3q19_handle *h, int64_t out[8]) {
+    out[0] = h->n_step_kernels; out[1] = h->n_other_kernels; out[2] = h->n_nccl; out[3] = h->n_steps;
+    out[4] = (int64_t)((size_t)NPOP * h->g.slab * sizeof(double) * (h->cfg.scheme == D3Q19_SCHEME_AB ? 2 : 1));
+    out[5] = h->phase; out[6] = h->g.xp; out[7] = 0;
+    return 0;
+}
+
+// ---- shim state machine (SURVEY.md section 8(b) "state coherence") ----------------------------------------------------
+extern "C" int d3q19_shim_bind(d3q19_handle *h, const d3q19_shim_arrays *a) {
+    if (!a || !a->f) return fail("d3q19_shim_bind: f is required");
+    h->shim.a = *a;
+    h->shim.bound = true;
+    h->shim.f_host_valid = true;
+    h->shim.f_dev_valid = false;
+    h->shim.macro_dev_valid = false;
+    h->shim.u_dev_loaded = false;
+    h->shim.next_mode = D3Q19_MACRO_MAIN;
+    return 0;
+}
+
+extern "C" int d3q19_shim_set_schedule(d3q19_handle *h, int32_t ndiag, int32_t nflowout, int32_t nsteps_total, int32_t istep0) {
+    if (!h->shim.bound) return fail("d3q19_shim_*: call d3q19_shim_bind first");
+    h->shim.a.ndiag = ndiag; h->shim.a.nflowout = nflowout;
+    h->shim.a.nsteps_total = nsteps_total; h->shim.a.istep0 = istep0;
+    return 0;
+}
+
+static int shim_f_on_device(d3q19_handle *h) {
+    Shim &s = h->shim;
+    if (!s.bound) return fail("d3q19_shim_*: call d3q19_shim_bind first");
+    if (!s.f_dev_valid) {
+        RK_(d3q19_upload_f(h, s.a.f));
+        if (h->cfg.ipart && s.a.ibnodes) RK_(d3q19_set_solid_mask(h, s.a.ibnodes, s.a.isnodes));
+        s.f_dev_valid = true;
+    }
+    return 0;
+}
+
+extern "C" int d3q19_shim_forcing(d3q19_handle *h, double force_in_y, double force_mag) {
+    Shim &s = h->shim;
+    const double fy = force_in_y * force_mag;                 // collision.f90:523
+    if (s.bound && s.a.force_realx && s.a.force_realy && s.a.force_realz) {
+        const size_t n = (size_t)h->g.lx * h->g.ly * h->g.lz;  // keep the host arrays what FORCING makes them
+        for (size_t i = 0; i < n; ++i) { s.a.force_realx[i] = 0.0; s.a.force_realy[i] = fy; s.a.force_realz[i] = 0.0; }
+    }
+    return d3q19_set_force_uniform(h, 0.0, fy, 0.0);
+}
+
+extern "C" int d3q19_shim_rhoupdat(d3q19_handle *h) {
+    Shim &s = h->shim;
+    RK_(shim_f_on_device(h));
+    if (!s.u_dev_loaded) {                                     // u stays frozen at the driver's values
+        RK_(d3q19_set_macro(h, s.a.rho, s.a.ux, s.a.uy, s.a.uz));
+        s.u_dev_loaded = true;
+    }
+    RK_(d3q19_rhoupdat(h));
+    RK_(d3q19_download_macro(h, s.a.rho, nullptr, nullptr, nullptr));
+    s.next_mode = D3Q19_MACRO_EXTERNAL;                        // collision reads the arrays as they now are
+    return 0;
+}
+
+extern "C" int d3q19_shim_collision_mrt(d3q19_handle *h) {
+    Shim &s = h->shim;
+    RK_(shim_f_on_device(h));
+    RK_(d3q19_collide_stream(h, s.next_mode));
+    s.next_mode = D3Q19_MACRO_MAIN;
+    s.f_host_valid = false;
+    s.macro_dev_valid = false;
+    return 0;
+}
+
+extern "C" int d3q19_shim_macrovar(d3q19_handle *h, int32_t istep) {
+    Shim &s = h->shim;
+    RK_(shim_f_on_device(h));
+    const d3q19_shim_arrays &a = s.a;
+    const bool wanted = istep <= a.istep0                                   // initialisation calls, main.f90:102,136
+                        || (a.ndiag > 0 && istep % a.ndiag == 0)            // diag, main.f90:171
+                        || (a.nflowout > 0 && istep % a.nflowout == 0)      // outputflow, main.f90:184
+                        || istep >= a.istep0 + a.nsteps_total               // probe after the loop, main.f90:221
+                        || (h->cfg.ipart && istep % 100 == 0);              // avedensity, main.f90:163
+    s.u_dev_loaded = false;
+    if (!wanted) return 0;                                                  // the next collision recomputes moments in registers
+    RK_(d3q19_macrovar(h));
+    s.macro_dev_valid = true;
+    return d3q19_download_macro(h, a.rho, a.ux, a.uy, a.uz);
+}
+
+extern "C" int d3q19_shim_avedensity(d3q19_handle *h) {
+    Shim &s = h->shim;
+    RK_(shim_f_on_device(h));
+    if (!s.macro_dev_valid) { RK_(d3q19_macrovar(h)); s.macro_dev_valid = true; }
+    RK_(d3q19_avedensity(h, nullptr, nullptr));
+    return d3q19_download_macro(h, s.a.rho, nullptr, nullptr, nullptr);
+}
+
+extern "C" int d3q19_shim_sync_f_to_host(d3q19_handle *h) {
+    Shim &s = h->shim;
+    if (!s.bound) return fail("d3q19_shim_*: call d3q19_shim_bind first");
+    if (s.f_dev_valid && !s.f_host_valid) {
+        RK_(d3q19_download_f(h, s.a.f));
+        s.f_host_valid = true;
+    }
+    return 0;
+}
+
+extern "C" int d3q19_shim_sync_f_to_device(d3q19_handle *h) {
+    Shim &s = h->shim;
+    if (!s.bound) return fail("d3q19_shim_*: call d3q19_shim_bind first");
+    s.f_dev_valid = false;
+    s.f_host_valid = true;
+    s.macro_dev_valid = false;
+    s.u_dev_loaded = false;
+    return 0;
+}

@@ -1,0 +1,421 @@
+// kernels.cuh -- device kernels of the Channel-Flow time step for sm_100a.
+//
+// HBM layout: structure of arrays, x contiguous,
+//     A[ip][zg][y][x],  x in [0,xp) (xp = lx rounded up to 16 doubles = 128 B),
+//                       y in [0,ly), zg in [0,lz+2) with zg = 0 and lz+1 the ghost planes,
+// so one population of one z plane ("face") is xp*ly contiguous doubles and a warp reads or
+// writes 256 contiguous bytes per population.  rho/u/force arrays are [z][y][x] with the
+// same pitch and no ghosts.
+//
+// A step is one pass: each thread owns one node, gathers its 19 populations according to
+// the storage phase, collides in registers (collide.cuh) and scatters:
+//     AB        read  g_i   = A[i][n - c_i]      (wall: A[opp i][n])   write B[i][n]
+//     AA even   read  f_i   = A[i][n]                                  write A[opp i][n]
+//     AA odd    read  f_i   = A[opp i][n - c_i]  (wall: A[i][n])       write f*_opp(i) to the
+//                                                                      address f_i was read from
+// 19 loads + 19 stores of 8 B per node = 304 B, nothing else in the main-loop instantiation.
+// The reference gets the same post-streaming values with its sequential in-place "swap" sweep
+// (collision.f90:224-264), which cannot be parallelised as written.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "collide.cuh"
+
+namespace d3q {
+
+enum ReadKind { READ_DIRECT = 0, READ_PULL_NAT = 1, READ_PULL_SWAP = 2 };
+enum StepKind { STEP_AB = 0, STEP_AA_EVEN = 1, STEP_AA_ODD = 2 };
+
+constexpr int BLOCK_X = 128;
+
+struct Geom {
+    int lx, ly, lz, xp;
+    long long plane;      // xp*ly
+    long long slab;       // plane*(lz+2): elements per population
+    int zlo_src;          // ghosted plane index that acts as "z-1" of plane 1   (lz if 1 rank, else 0)
+    int zhi_src;          // ghosted plane index that acts as "z+1" of plane lz  (1  if 1 rank, else lz+1)
+};
+
+struct StepParams {
+    Geom g;
+    double *A;            // source (and destination for AA)
+    double *B;            // destination for AB
+    int z0;               // first ghosted plane index handled by this launch
+    Mrt mrt;
+    double Fx, Fy, Fz;    // uniform force (FORCING, collision.f90:522-524)
+    double rho_shift;     // pending avedensity shift (collision.f90:505-511)
+    // generic instantiation only:
+    int macro_mode;       // D3Q19_MACRO_*
+    double *rho;          // device arrays [lz][ly][xp]
+    const double *ux, *uy, *uz;
+    const double *ffx, *ffy, *ffz;   // force field or nullptr
+    const int32_t *solid;            // >0 solid, [lz][ly][xp], or nullptr
+    unsigned long long *rhoerr_bits; // PRERELAX: max |rho_new - rho_old| as ordered bits
+};
+
+// ---- neighbour addressing ------------------------------------------------------------------
+struct NodeIdx {
+    int x, y, zg;
+    long long n;              // x + xp*(y + ly*zg)
+    long long oy[3], oz[3];   // row / plane offsets of (y-1,y,y+1), (z-1,z,z+1) with wraps
+    bool wall_lo, wall_hi;    // x == 0 / x == lx-1
+};
+
+__device__ __forceinline__ NodeIdx make_node(const Geom &g, int x, int y, int zg) {
+    NodeIdx k;
+    k.x = x; k.y = y; k.zg = zg;
+    const int ym = (y == 0) ? g.ly - 1 : y - 1;
+    const int yp = (y == g.ly - 1) ? 0 : y + 1;
+    const int zm = (zg == 1) ? g.zlo_src : zg - 1;
+    const int zp = (zg == g.lz) ? g.zhi_src : zg + 1;
+    k.oy[0] = (long long)ym * g.xp; k.oy[1] = (long long)y * g.xp; k.oy[2] = (long long)yp * g.xp;
+    k.oz[0] = (long long)zm * g.plane; k.oz[1] = (long long)zg * g.plane; k.oz[2] = (long long)zp * g.plane;
+    k.n = x + k.oy[1] + k.oz[1];
+    k.wall_lo = (x == 0);
+    k.wall_hi = (x == g.lx - 1);
+    return k;
+}
+
+// element offset (inside the whole SoA array) from which direction I is gathered
+template <int RK, int I>
+__device__ __forceinline__ long long gather_offset(const Geom &g, const NodeIdx &k) {
+    constexpr int cx = dir_cx(I), cy = dir_cy(I), cz = dir_cz(I), opp = dir_opp(I);
+    if (RK == READ_DIRECT) return (long long)I * g.slab + k.n;
+    const long long nb = (k.x - cx) + k.oy[1 - cy] + k.oz[1 - cz];   // n - c_i with periodic y,z
+    constexpr int slot_nb = (RK == READ_PULL_NAT) ? I : opp;
+    constexpr int slot_wall = (RK == READ_PULL_NAT) ? opp : I;
+    if (cx == 0) return (long long)slot_nb * g.slab + nb;
+    const bool wall = (cx > 0) ? k.wall_lo : k.wall_hi;               // half-way bounce-back, wall at rest
+    return wall ? (long long)slot_wall * g.slab + k.n : (long long)slot_nb * g.slab + nb;
+}
+
+template <int RK>
+__device__ __forceinline__ void gather19(const double *__restrict__ A, const Geom &g, const NodeIdx &k,
+                                         double (&f)[NPOP]) {
+    static_for<NPOP>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        f[i] = A[gather_offset<RK, i>(g, k)];
+    });
+}
+
+// ---- the step kernel ---------------------------------------------------------------------------
+// GENERIC = false: main loop, uniform force, no solids, moments in registers (304 B/node).
+// GENERIC = true : run-time macro mode / force field / solid mask.
+template <int SK, bool STRICT, bool GENERIC>
+__global__ void __launch_bounds__(BLOCK_X) k_step(const __grid_constant__ StepParams p) {
+    const Geom &g = p.g;
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    double rhoerr = 0.0;
+    if (x < g.lx) {
+        const NodeIdx k = make_node(g, x, blockIdx.y, p.z0 + blockIdx.z);
+        constexpr int RK = (SK == STEP_AB) ? READ_PULL_NAT : (SK == STEP_AA_EVEN ? READ_DIRECT : READ_PULL_SWAP);
+        double f[NPOP];
+        gather19<RK>(p.A, g, k, f);
+
+        double Fx = p.Fx, Fy = p.Fy, Fz = p.Fz;
+        bool is_solid = false;
+        if (GENERIC) {
+            const long long m = x + (long long)g.xp * (k.y + (long long)g.ly * (k.zg - 1));
+            if (p.ffx) { Fx = p.ffx[m]; Fy = p.ffy[m]; Fz = p.ffz[m]; }
+            if (p.solid) is_solid = p.solid[m] > 0;
+            if (!is_solid) {
+                if (p.macro_mode == 0) {                      // D3Q19_MACRO_MAIN
+                    if (STRICT) {
+                        double r, a, b, c;
+                        moments_strict(f, Fx, Fy, Fz, r, a, b, c);
+                        collide_strict(f, (R(r) - R(p.rho_shift)).v, a, b, c, Fx, Fy, Fz, p.mrt);
+                    } else {
+                        collide_fast<true>(f, 0, 0, 0, 0, Fx, Fy, Fz, p.rho_shift, p.mrt);
+                    }
+                } else {
+                    double r;
+                    if (p.macro_mode == 1) {                  // D3Q19_MACRO_PRERELAX: fused rhoupdat
+                        r = rho_index_order(f);
+                        rhoerr = fabs(r - p.rho[m]);
+                        p.rho[m] = r;
+                    } else {
+                        r = p.rho[m];
+                    }
+                    const double a = p.ux[m], b = p.uy[m], c = p.uz[m];
+                    if (STRICT) collide_strict(f, r, a, b, c, Fx, Fy, Fz, p.mrt);
+                    else collide_fast<false>(f, r, a, b, c, Fx, Fy, Fz, 0.0, p.mrt);
+                }
+            }
+        } else {
+            if (STRICT) {
+                double r, a, b, c;
+                moments_strict(f, Fx, Fy, Fz, r, a, b, c);
+                collide_strict(f, r, a, b, c, Fx, Fy, Fz, p.mrt);
+            } else {
+                collide_fast<true>(f, 0, 0, 0, 0, Fx, Fy, Fz, 0.0, p.mrt);
+            }
+        }
+
+        if (SK == STEP_AB) {
+            static_for<NPOP>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                p.B[(long long)i * g.slab + k.n] = f[i];
+            });
+        } else if (SK == STEP_AA_EVEN) {
+            static_for<NPOP>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                p.A[(long long)dir_opp(i) * g.slab + k.n] = f[i];
+            });
+        } else {
+            static_for<NPOP>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                p.A[gather_offset<READ_PULL_SWAP, i>(g, k)] = f[dir_opp(i)];
+            });
+        }
+    }
+    if (GENERIC && p.macro_mode == 1 && p.rhoerr_bits) {
+        // block max of a non-negative double: its bit pattern is order-preserving
+        __shared__ unsigned long long smax[BLOCK_X / 32];
+        unsigned long long b = (unsigned long long)__double_as_longlong(rhoerr);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
+            b = t > b ? t : b;
+        }
+        if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int wi = 1; wi < BLOCK_X / 32; ++wi) b = smax[wi] > b ? smax[wi] : b;
+            if (b) atomicMax(p.rhoerr_bits, b);
+        }
+    }
+}
+
+// ---- macrovar (collision.f90:378-463) / rhoupdat (:469-480) -----------------------------------
+struct MacroParams {
+    Geom g;
+    const double *A;
+    double *rho, *ux, *uy, *uz;       // [lz][ly][xp]
+    double Fx, Fy, Fz;
+    const double *ffx, *ffy, *ffz;
+    const int32_t *solid;             // ibnodes > 0
+    const int32_t *isnodes;           // owning particle, 1-based
+    const double *ypglb, *wp, *omgp;  // (3,npart)
+    double rhopart;
+    int ipart, ny, nz, globalz;
+    int rho_only;                     // rhoupdat: all nodes, index order, rho only
+};
+
+template <int RK>
+__global__ void __launch_bounds__(BLOCK_X) k_macro(const __grid_constant__ MacroParams p) {
+    const Geom &g = p.g;
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.lx) return;
+    const NodeIdx k = make_node(g, x, blockIdx.y, 1 + blockIdx.z);
+    const long long m = x + (long long)g.xp * (k.y + (long long)g.ly * (k.zg - 1));
+    double f[NPOP];
+    gather19<RK>(p.A, g, k, f);
+    if (p.rho_only) { p.rho[m] = rho_index_order(f); return; }
+    const bool is_solid = p.solid && p.solid[m] > 0;
+    if (!is_solid) {
+        double Fx = p.Fx, Fy = p.Fy, Fz = p.Fz;
+        if (p.ffx) { Fx = p.ffx[m]; Fy = p.ffy[m]; Fz = p.ffz[m]; }
+        double r, a, b, c;
+        moments_strict(f, Fx, Fy, Fz, r, a, b, c);
+        p.rho[m] = r; p.ux[m] = a; p.uy[m] = b; p.uz[m] = c;
+    } else if (p.ipart) {
+        // rigid-body velocity of the owning particle, nearest periodic image in y,z (collision.f90:420-459)
+        const int id = p.isnodes[m] - 1;
+        const double xpnt = (double)(x + 1) - 0.5;
+        const double ypnt = (double)(k.y + 1) - 0.5;                 // y is not decomposed: globaly = 0
+        const double zpnt = (double)(k.zg) - 0.5 + (double)p.globalz;
+        double xc = p.ypglb[3 * id], yc = p.ypglb[3 * id + 1], zc = p.ypglb[3 * id + 2];
+        const double nyh = (double)(p.ny / 2), nzh = (double)(p.nz / 2);
+        if ((yc - ypnt) > nyh) yc = yc - (double)p.ny;
+        if ((yc - ypnt) < -nyh) yc = yc + (double)p.ny;
+        if ((zc - zpnt) > nzh) zc = zc - (double)p.nz;
+        if ((zc - zpnt) < -nzh) zc = zc + (double)p.nz;
+        const double xx0 = xpnt - xc, yy0 = ypnt - yc, zz0 = zpnt - zc;
+        const double w1 = p.wp[3 * id], w2 = p.wp[3 * id + 1], w3 = p.wp[3 * id + 2];
+        const double o1 = p.omgp[3 * id], o2 = p.omgp[3 * id + 1], o3 = p.omgp[3 * id + 2];
+        p.ux[m] = (R(w1) + (R(o2) * R(zz0) - R(o3) * R(yy0))).v;
+        p.uy[m] = (R(w2) + (R(o3) * R(xx0) - R(o1) * R(zz0))).v;
+        p.uz[m] = (R(w3) + (R(o1) * R(yy0) - R(o2) * R(xx0))).v;
+        p.rho[m] = p.rhopart;
+    }
+}
+
+// one node -> out[4] (probe, saveload.f90:4059-4100)
+template <int RK>
+__global__ void k_probe(Geom g, const double *A, int x, int y, int zg, double Fx, double Fy, double Fz, double *out) {
+    const NodeIdx k = make_node(g, x, y, zg);
+    double f[NPOP];
+    gather19<RK>(A, g, k, f);
+    moments_strict(f, Fx, Fy, Fz, out[0], out[1], out[2], out[3]);
+}
+
+// ---- canonical AoS <-> device SoA (upload_f / download_f) ----------------------------------------
+// aos holds planes [zg0, zg0+nz) of the host layout f(0:18,lx,ly,:) without pitch.
+template <int RK>
+__global__ void __launch_bounds__(BLOCK_X) k_gather_aos(Geom g, const double *A, double *aos, int zg0) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.lx) return;
+    const NodeIdx k = make_node(g, x, blockIdx.y, zg0 + blockIdx.z);
+    double f[NPOP];
+    gather19<RK>(A, g, k, f);
+    double *o = aos + (long long)NPOP * (x + (long long)g.lx * (k.y + (long long)g.ly * blockIdx.z));
+#pragma unroll
+    for (int i = 0; i < NPOP; ++i) o[i] = f[i];
+}
+
+__global__ void __launch_bounds__(BLOCK_X) k_scatter_aos(Geom g, double *A, const double *aos, int zg0) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.lx) return;
+    const int y = blockIdx.y, zg = zg0 + blockIdx.z;
+    const long long n = x + (long long)g.xp * (y + (long long)g.ly * zg);
+    const double *s = aos + (long long)NPOP * (x + (long long)g.lx * (y + (long long)g.ly * blockIdx.z));
+#pragma unroll
+    for (int i = 0; i < NPOP; ++i) A[(long long)i * g.slab + n] = s[i];
+}
+
+// AB upload: canonical C (post-streaming) -> post-collision storage, the inverse permutation
+// of streaming:  g_i(x) = f_i(x + c_i), at a wall g_i(x) = f_opp(i)(x).
+__global__ void __launch_bounds__(BLOCK_X) k_unstream(Geom g, const double *Cn, double *A) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.lx) return;
+    const NodeIdx k = make_node(g, x, blockIdx.y, 1 + blockIdx.z);
+    static_for<NPOP>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int cx = dir_cx(i), cy = dir_cy(i), cz = dir_cz(i);
+        const bool wall = (cx > 0) ? k.wall_hi : (cx < 0 ? k.wall_lo : false);
+        const long long nb = (k.x + cx) + k.oy[1 + cy] + k.oz[1 + cz];
+        A[(long long)i * g.slab + k.n] =
+            wall ? Cn[(long long)dir_opp(i) * g.slab + k.n] : Cn[(long long)i * g.slab + nb];
+    });
+}
+
+// pitched scalar field <-> host layout (lx,ly,lz)
+__global__ void __launch_bounds__(BLOCK_X) k_field_pack(int lx, int xp, const double *dev, double *host_layout, int to_host) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= lx) return;
+    const long long row = blockIdx.y + (long long)gridDim.y * blockIdx.z;
+    if (to_host) host_layout[row * lx + x] = dev[row * xp + x];
+}
+__global__ void __launch_bounds__(BLOCK_X) k_field_unpack(int lx, int xp, double *dev, const double *host_layout) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= lx) return;
+    const long long row = blockIdx.y + (long long)gridDim.y * blockIdx.z;
+    dev[row * xp + x] = host_layout[row * lx + x];
+}
+__global__ void __launch_bounds__(BLOCK_X) k_field_unpack_i32(int lx, int xp, int32_t *dev, const int32_t *host_layout,
+                                                              int src_ghosted, int ly) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= lx) return;
+    const int y = blockIdx.y, z = blockIdx.z;
+    const long long row = y + (long long)gridDim.y * z;
+    long long s;
+    if (src_ghosted)   // ibnodes(0:lx+1,0:ly+1,0:lz+1)
+        s = (x + 1) + (long long)(lx + 2) * ((y + 1) + (long long)(ly + 2) * (z + 1));
+    else
+        s = row * lx + x;
+    dev[row * xp + x] = host_layout[s];
+}
+
+// ---- z-face pack / unpack (collisionExchnge, collision.f90:337-370) ------------------------------
+// buf[s][y][x] (pitch xp) <- A[slots[s]][plane][y][x]
+struct FaceSlots { int s[5]; };
+__global__ void __launch_bounds__(BLOCK_X) k_face_pack(Geom g, const double *A, double *buf, int zg, FaceSlots fs) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.xp) return;
+    const int y = blockIdx.y, s = blockIdx.z;
+    buf[(long long)s * g.plane + (long long)y * g.xp + x] =
+        A[(long long)fs.s[s] * g.slab + (long long)zg * g.plane + (long long)y * g.xp + x];
+}
+// exclude_walls: populations with c_x = +1 skip x = 0, c_x = -1 skip x = lx-1 -- the slices
+// 2:lx / 1:lx-1 of collision.f90:361-362,367-368 that keep the locally bounced value.
+__global__ void __launch_bounds__(BLOCK_X) k_face_unpack(Geom g, double *A, const double *buf, int zg, FaceSlots fs,
+                                                         int exclude_walls) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.lx) return;
+    const int y = blockIdx.y, s = blockIdx.z;
+    const int slot = fs.s[s];
+    if (exclude_walls) {
+        const int cx = (slot == 11 || slot == 13 || slot == 7 || slot == 9 || slot == 1) ? 1
+                     : ((slot == 12 || slot == 14 || slot == 8 || slot == 10 || slot == 2) ? -1 : 0);
+        if ((cx > 0 && x == 0) || (cx < 0 && x == g.lx - 1)) return;
+    }
+    A[(long long)slot * g.slab + (long long)zg * g.plane + (long long)y * g.xp + x] =
+        buf[(long long)s * g.plane + (long long)y * g.xp + x];
+}
+
+// ---- reductions ------------------------------------------------------------------------------------
+// avedensity (collision.f90:497-498): per-block partial (count, sum) over fluid nodes, fixed order.
+__global__ void __launch_bounds__(256) k_rho_partial(int lx, int xp, long long nrows, const double *rho,
+                                                     const int32_t *solid, double *psum, long long *pcnt) {
+    __shared__ double ss[256];
+    __shared__ long long sc[256];
+    double s = 0.0;
+    long long c = 0;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x)
+        for (int x = threadIdx.x; x < lx; x += 256) {
+            const long long m = row * xp + x;
+            if (!solid || solid[m] < 0) { s += rho[m]; c += 1; }
+        }
+    ss[threadIdx.x] = s; sc[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { ss[threadIdx.x] += ss[threadIdx.x + o]; sc[threadIdx.x] += sc[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { psum[blockIdx.x] = ss[0]; pcnt[blockIdx.x] = sc[0]; }
+}
+__global__ void k_rho_final(int nblk, const double *psum, const long long *pcnt, double *out_sum, long long *out_cnt) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0; long long c = 0;
+        for (int i = 0; i < nblk; ++i) { s += psum[i]; c += pcnt[i]; }
+        *out_sum = s; *out_cnt = c;
+    }
+}
+__global__ void __launch_bounds__(BLOCK_X) k_rho_shift(int lx, int xp, double *rho, const double *mean_dev) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= lx) return;
+    const long long row = blockIdx.y + (long long)gridDim.y * blockIdx.z;
+    rho[row * xp + x] -= *mean_dev;            // collision.f90:508, every node
+}
+
+// statistc (saveload.f90:1241-1300): per-x sums over (y,z) of 11 quantities.  Stage 1: each
+// block owns BLOCK_X x-columns and a contiguous chunk of (y,z) rows; stage 2 adds chunks in order.
+constexpr int NPROF = 11;
+template <int RK>
+__global__ void __launch_bounds__(BLOCK_X) k_profiles(Geom g, const double *A, double Fx, double Fy, double Fz,
+                                                      const int32_t *solid, int rows_per_chunk, double *partial) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.lx) return;
+    const long long nrows = (long long)g.ly * g.lz;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    const long long r1 = r0 + rows_per_chunk < nrows ? r0 + rows_per_chunk : nrows;
+    double acc[NPROF];
+#pragma unroll
+    for (int q = 0; q < NPROF; ++q) acc[q] = 0.0;
+    for (long long row = r0; row < r1; ++row) {
+        const int y = (int)(row % g.ly), z = (int)(row / g.ly);
+        if (solid && solid[row * g.xp + x] > 0) continue;
+        const NodeIdx k = make_node(g, x, y, z + 1);
+        double f[NPOP], r, a, b, c;
+        gather19<RK>(A, g, k, f);
+        moments_strict(f, Fx, Fy, Fz, r, a, b, c);
+        acc[0] += a; acc[1] += b; acc[2] += c;
+        acc[3] += a * a; acc[4] += b * b; acc[5] += c * c;
+        acc[6] += a * b; acc[7] += a * c; acc[8] += b * c;
+        acc[9] += r; acc[10] += r * r;
+    }
+#pragma unroll
+    for (int q = 0; q < NPROF; ++q) partial[((long long)blockIdx.y * NPROF + q) * g.lx + x] = acc[q];
+}
+__global__ void __launch_bounds__(BLOCK_X) k_profiles_final(int lx, int nchunks, const double *partial, double *out) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= lx) return;
+    const int q = blockIdx.y;
+    double s = 0.0;
+    for (int cidx = 0; cidx < nchunks; ++cidx) s += partial[((long long)cidx * NPROF + q) * lx + x];
+    out[(long long)q * lx + x] = s;
+}
+
+}  // namespace d3q

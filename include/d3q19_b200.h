@@ -1,0 +1,174 @@
+/*
+ * d3q19_b200.h -- C-ABI of libd3q19b200.so: the B200 (sm_100a) implementation of the
+ * UDel-CFD D3Q19 Channel-Flow time-step hot path.
+ *
+ * This is the drop-in boundary.  The reference's time loop (main.f90:142-208) calls the
+ * argument-less Fortran subroutines of collision.f90, which talk through `module var_inc`.
+ * A replacement collision.f90 (d3q19-single-phase_b200/fortran/collision_b200.f90) keeps
+ * those subroutine names and forwards each to one entry point below through ISO_C_BINDING;
+ * INTEGRATION.md shows the binding.  Reference interface replaced (file:line relative to
+ * /root/reference/Channel-Flow/):
+ *
+ *   collision_MRT  collision.f90:24-273 (+ collisionExchnge :281-372) -> d3q19_collide_stream / d3q19_shim_collision_mrt
+ *   macrovar       collision.f90:378-463                              -> d3q19_macrovar + d3q19_download_macro / d3q19_shim_macrovar
+ *   rhoupdat       collision.f90:469-480                              -> d3q19_rhoupdat / d3q19_shim_rhoupdat
+ *   avedensity     collision.f90:487-513                              -> d3q19_avedensity / d3q19_shim_avedensity
+ *   FORCING        collision.f90:515-527                              -> d3q19_set_force_uniform / d3q19_shim_forcing
+ *   FORCINGP       collision.f90:529-602 (force arrays)               -> d3q19_set_force_field
+ *   allocarray     para.f90:418-503 (f, rho, u, ibnodes)              -> d3q19_create (device-side twins)
+ *   MPI_ISEND/IRECV collision.f90:309-314,351-356                     -> NCCL send/recv inside d3q19_collide_stream
+ *   MPI_ALLREDUCE  collision.f90:500-501                              -> ncclAllReduce inside d3q19_avedensity
+ *
+ * Conventions: plain C types only (double = Fortran real under -r8, int32_t = integer);
+ * every function returns 0 on success, nonzero on failure with a message available from
+ * d3q19_last_error(); no exceptions cross the ABI.  One host thread per handle; a handle
+ * owns one GPU (1 rank <-> 1 GPU), all device memory, its streams and its NCCL communicator.
+ * Host arrays stay caller-owned and are only touched during upload/download calls.
+ * There is no CPU fallback: without a CUDA device d3q19_create fails.
+ *
+ * Host array layouts are the reference's (column-major, var_inc.f90 / para.f90:418-503):
+ *   f(0:18,lx,ly,lz)    f_aos[ip + 19*((ix-1) + lx*((iy-1) + ly*(iz-1)))]   ("canonical" = post-streaming,
+ *                       exactly what the reference holds after collision_MRT returns)
+ *   rho,ux,uy,uz,force  a[(ix-1) + lx*((iy-1) + ly*(iz-1))]
+ *   ibnodes(0:lx+1,0:ly+1,0:lz+1) ghosted int32, -1 fluid / >0 solid (para.f90:442,447)
+ * x is wall-normal and never decomposed; y is periodic and local; z is periodic and
+ * slab-decomposed over ranks (rank r owns global planes [globalz, globalz+lz)).
+ */
+#ifndef D3Q19_B200_H
+#define D3Q19_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3Q19_NPOP 19
+#define D3Q19_ABI_VERSION 1
+
+/* Streaming scheme (how populations live in HBM). */
+enum {
+    D3Q19_SCHEME_AA = 0,   /* in-place, one array: even step local, odd step pull/push (default) */
+    D3Q19_SCHEME_AB = 1    /* two arrays, one-step pull                                          */
+};
+
+/* Arithmetic of the collision. */
+enum {
+    D3Q19_MATH_FAST = 0,   /* moment-space algebra with FMA contraction (production)              */
+    D3Q19_MATH_STRICT = 1  /* the reference's expression order, no contraction: bit-exact vs oracle */
+};
+
+/* Where collision_MRT takes the conserved moments from. */
+enum {
+    D3Q19_MACRO_MAIN = 0,     /* rho,u = moments of f, in registers (main loop, main.f90:157)     */
+    D3Q19_MACRO_PRERELAX = 1, /* rho = sum f (rhoupdat), u frozen in the device arrays (main.f90:70-90) */
+    D3Q19_MACRO_EXTERNAL = 2  /* rho,u all read from the device arrays (set_macro / macrovar / avedensity) */
+};
+
+typedef struct d3q19_handle d3q19_handle;
+
+/* All sizes are run-time (the reference fixes them at compile time, var_inc.f90:51). */
+typedef struct d3q19_config {
+    int32_t abi_version;      /* D3Q19_ABI_VERSION                                               */
+    int32_t lx, ly, lz;       /* local extents; lx = nx, ly = ny (y not decomposed), lz = slab   */
+    int32_t nx, ny, nz;       /* global extents                                                  */
+    int32_t globalz;          /* first owned global z plane (0-based), para.f90:259-261          */
+    int32_t rank, nranks;     /* z-slab ring; mzp/mzm = (rank +- 1) mod nranks, para.f90:266-267  */
+    int32_t device;           /* CUDA ordinal (normally the local rank)                          */
+    int32_t scheme;           /* D3Q19_SCHEME_*                                                  */
+    int32_t math;             /* D3Q19_MATH_*                                                    */
+    int32_t ipart;            /* para.f90:332 -- enables the solid-node paths                    */
+    int32_t overlap;          /* 1: boundary/interior split with exchange on a second stream     */
+    int32_t reserved_i[5];
+    /* MRT constants, para.f90:106-143 */
+    double s1, s2, s4, s9, s10, s13, s16;
+    double omegepsl, omegepslj, omegxx;
+    double rhopart;           /* var_inc.f90:65 */
+    double reserved_d[5];
+    /* 128-byte ncclUniqueId made by rank 0 (d3q19_nccl_unique_id) and broadcast by the caller
+     * (MPI_BCAST in the Fortran shim, torch.distributed in the Python host); ignored if nranks==1 */
+    unsigned char nccl_id[128];
+} d3q19_config;
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+int d3q19_create(const d3q19_config *cfg, d3q19_handle **out);
+int d3q19_destroy(d3q19_handle *h);
+int d3q19_sync(d3q19_handle *h);
+const char *d3q19_last_error(void);
+int d3q19_nccl_unique_id(unsigned char out[128]);
+int d3q19_device_count(int32_t *n);
+
+/* ---- state transfer (canonical AoS layout, see above) --------------------------------- */
+int d3q19_upload_f(d3q19_handle *h, const double *f_aos);
+int d3q19_download_f(d3q19_handle *h, double *f_aos);
+/* any pointer may be NULL (left untouched) */
+int d3q19_set_macro(d3q19_handle *h, const double *rho, const double *ux, const double *uy, const double *uz);
+int d3q19_download_macro(d3q19_handle *h, double *rho, double *ux, double *uy, double *uz);
+
+/* ---- forcing (FORCING / FORCINGP) ------------------------------------------------------ */
+int d3q19_set_force_uniform(d3q19_handle *h, double fx, double fy, double fz);
+int d3q19_set_force_field(d3q19_handle *h, const double *fx, const double *fy, const double *fz);
+
+/* ---- the time step --------------------------------------------------------------------- */
+/* one collision_MRT (collide + force + propagate + wall bounce-back + ghost exchange) */
+int d3q19_collide_stream(d3q19_handle *h, int32_t macro_mode);
+/* nsteps back-to-back main-loop steps (MACRO_MAIN), enqueued without host synchronisation */
+int d3q19_run(d3q19_handle *h, int32_t nsteps);
+/* macrovar on the device arrays (fluid branch + solid branch when ipart) */
+int d3q19_macrovar(d3q19_handle *h);
+int d3q19_rhoupdat(d3q19_handle *h);
+/* global mean over fluid nodes removed from the device rho array; the next collide_stream
+ * sees the shifted density exactly as the reference's does (collision.f90:505-511)       */
+int d3q19_avedensity(d3q19_handle *h, double *rhomean, int64_t *nfluid_total);
+/* rho,ux,uy,uz of one local node (1-based ix,iy,iz) computed from the current populations:
+ * the reference's `probe` regression vector (saveload.f90:4059-4100)                      */
+int d3q19_probe(d3q19_handle *h, int32_t ix, int32_t iy, int32_t iz, double out4[4]);
+/* device-side pre-relaxation loop (main.f90:70-90): repeats rhoupdat + collision_MRT with u
+ * frozen until max|rho - rho_prev| <= tol (all ranks) or iters > maxiter                  */
+int d3q19_prerelax(d3q19_handle *h, double tol, int32_t maxiter, int32_t *iters, double *rhoerrmax);
+
+/* ---- particles (ibnodes / isnodes, var_inc.f90:113-114) -------------------------------- */
+int d3q19_set_solid_mask(d3q19_handle *h, const int32_t *ibnodes_ghosted, const int32_t *isnodes);
+int d3q19_set_particles(d3q19_handle *h, int32_t npart, const double *ypglb, const double *wp, const double *omgp);
+
+/* ---- device-side statistics ------------------------------------ */
+/* per-x-plane sums over the local (y,z) of ux,uy,uz,ux^2,uy^2,uz^2,uxuy,uxuz,uyuz,rho,rho^2
+ * (statistc, saveload.f90:1241-1300), all-reduced over ranks; out is [11][lx]             */
+int d3q19_profiles(d3q19_handle *h, double *out_11_by_lx);
+
+/* ---- measurement ----------------------------------------------------------------------- */
+/* CUDA events on the stream the step kernels are launched on */
+int d3q19_timer_start(d3q19_handle *h);
+int d3q19_timer_stop(d3q19_handle *h, float *elapsed_ms);
+/* counters: [0] step kernels launched, [1] other kernels launched, [2] NCCL ops,
+ *           [3] steps taken, [4] bytes of populations resident, [5] storage phase          */
+int d3q19_get_counters(d3q19_handle *h, int64_t out[8]);
+
+/* ---- the shim state machine (what the replacement collision.f90 calls) ------------------ */
+/* These carry the download policy of SURVEY.md section 8(b): device-resident f is
+ * authoritative; host rho,u are refreshed only on steps where the intact driver reads them. */
+typedef struct d3q19_shim_arrays {
+    double *f;                       /* f(0:18,lx,ly,lz)                       */
+    double *rho, *ux, *uy, *uz;      /* (lx,ly,lz)                             */
+    double *force_realx, *force_realy, *force_realz;
+    int32_t *ibnodes, *isnodes;
+    int32_t ndiag, nflowout, nsteps_total, istep0;   /* var_inc.f90:58-59, para.f90:43-45 */
+} d3q19_shim_arrays;
+
+int d3q19_shim_bind(d3q19_handle *h, const d3q19_shim_arrays *a);
+/* change the output cadence / loop bounds the download policy keys on (main.f90:142,171,184) */
+int d3q19_shim_set_schedule(d3q19_handle *h, int32_t ndiag, int32_t nflowout, int32_t nsteps_total, int32_t istep0);
+int d3q19_shim_forcing(d3q19_handle *h, double force_in_y, double force_mag);
+int d3q19_shim_rhoupdat(d3q19_handle *h);
+int d3q19_shim_collision_mrt(d3q19_handle *h);
+int d3q19_shim_macrovar(d3q19_handle *h, int32_t istep);
+int d3q19_shim_avedensity(d3q19_handle *h);
+/* make the host copy of f current (before savecntdflow / saveinitflow, saveload.f90:120,227) */
+int d3q19_shim_sync_f_to_host(d3q19_handle *h);
+/* the host copy of f changed (after loadcntdflow / initpop) */
+int d3q19_shim_sync_f_to_device(d3q19_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

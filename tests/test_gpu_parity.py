@@ -1,0 +1,260 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle.  Needs a B200.
+
+Tolerances are BASELINE.json's: fp64 max error normalised by the field's max-norm
+< 1e-12 after 1 step and < 1e-9 after 1000 steps; STRICT arithmetic is bit-identical;
+layout / streaming / indexing work (upload, download, phases, pitch padding) is bit-exact.
+"""
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+
+pytestmark = pytest.mark.gpu
+
+pkg = entry.load_package()
+capi = pkg.capi
+
+SCHEMES = [capi.SCHEME_AA, capi.SCHEME_AB]
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def make_pair(oracle, nx, ny, nz, laminar=False, scheme=capi.SCHEME_AA, math_mode=capi.MATH_FAST, perturb=0.0,
+              **overrides):
+    w, p = oracle.make_initial_state(nx, ny, nz, laminar=laminar, noise=not laminar, **overrides)
+    if perturb:
+        rng = np.random.default_rng(99)
+        w.set_f(w.get_f() + perturb * rng.normal(size=(nz, ny, nx, 19)))
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=laminar, scheme=scheme, math_mode=math_mode, **overrides)
+    sim.f[...] = w.get_f()
+    sim.host_f_changed()
+    sim.FORCING()
+    w.macrovar()
+    return w, p, sim
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("shape", [(64, 32, 32), (23, 10, 7), (199, 8, 6), (16, 1, 1), (130, 3, 2)])
+def test_upload_download_roundtrip_bitexact(oracle, scheme, shape):
+    nx, ny, nz = shape
+    rng = np.random.default_rng(1)
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme)
+    f0 = rng.normal(size=(nz, ny, nx, 19))
+    sim.upload_f(f0)
+    out = np.empty_like(f0)
+    sim.download_f(out)
+    assert np.array_equal(out, f0)
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("shape,laminar", [((64, 32, 32), False), ((64, 32, 32), True), ((23, 10, 7), False),
+                                           ((199, 6, 5), False), ((16, 1, 1), False), ((9, 2, 3), True)])
+def test_strict_is_bit_identical_to_oracle(oracle, scheme, shape, laminar):
+    nx, ny, nz = shape
+    w, p, sim = make_pair(oracle, nx, ny, nz, laminar=laminar, scheme=scheme, math_mode=capi.MATH_STRICT,
+                          perturb=1e-4)
+    out = np.empty((nz, ny, nx, 19))
+    for step in range(1, 8):
+        w.collision_MRT()
+        w.macrovar()
+        sim.collide_stream()
+        sim.download_f(out)              # canonical layout at either storage phase
+        assert np.array_equal(out, w.get_f()), "step %d" % step
+        sim.device_macrovar()
+        for k in ("rho", "ux", "uy", "uz"):
+            assert np.array_equal(getattr(sim, k), w.get(k)), (k, step)
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("mrt", [1, 2, 3])
+def test_fast_one_step_within_1e12(oracle, scheme, mrt):
+    nx, ny, nz = 64, 32, 32
+    w, p, sim = make_pair(oracle, nx, ny, nz, laminar=False, scheme=scheme, perturb=1e-4, MRTtype=mrt)
+    w.collision_MRT()
+    sim.collide_stream()
+    f = sim.download_f(np.empty((nz, ny, nx, 19)))
+    assert relerr(f, w.get_f()) < 1e-12
+    w.macrovar()
+    sim.device_macrovar()
+    for k in ("rho", "ux", "uy", "uz"):
+        assert np.max(np.abs(getattr(sim, k) - w.get(k))) < 1e-12 * np.max(np.abs(w.get_f()))
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("laminar", [True, False])
+def test_1000_steps_within_1e9_config1(oracle, scheme, laminar):
+    # BASELINE.json configs[0]: 64x32x32 channel (laminar set as shipped, plus the turbulent set)
+    nx, ny, nz = 64, 32, 32
+    w, p, sim = make_pair(oracle, nx, ny, nz, laminar=laminar, scheme=scheme)
+    nsteps = 1000
+    sim.run(nsteps)                     # the driver loop: collision_MRT; macrovar (lazy)
+    for _ in range(nsteps):
+        w.collision_MRT()
+        w.macrovar()
+    f = sim.sync_f_to_host()
+    assert relerr(f, w.get_f()) < 1e-9
+    for k in ("rho", "ux", "uy", "uz"):   # final-step macrovar was downloaded by the shim policy
+        scale = max(np.max(np.abs(w.get(k))), np.max(np.abs(w.get("uy"))))
+        assert np.max(np.abs(getattr(sim, k) - w.get(k))) < 1e-9 * scale, k
+    # mean velocity profile and wall shear stress (acceptance quantities)
+    prof = sim.profiles()
+    uy_mean = prof[1] / (ny * nz)
+    ref_mean = w.get("uy").mean(axis=(0, 1))
+    assert np.max(np.abs(uy_mean - ref_mean)) < 1e-9 * np.max(np.abs(ref_mean))
+    tau_w = p.visc * (uy_mean[0] / 0.5)          # wall half a spacing below node 1
+    tau_ref = p.visc * (ref_mean[0] / 0.5)
+    assert abs(tau_w - tau_ref) <= 1e-9 * abs(tau_ref)
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("math_mode", [capi.MATH_STRICT, capi.MATH_FAST])
+def test_prerelax_through_the_driver_calls(oracle, scheme, math_mode):
+    # main.f90:70-90: rhop = rho; rhoupdat; collision_MRT (u frozen); rhoerr = max|rho - rhop|
+    nx, ny, nz = 32, 8, 8
+    w, p = oracle.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=math_mode)
+    for k in ("ux", "uy", "uz", "rho"):
+        getattr(sim, k)[...] = w.get(k)
+    sim.f[...] = w.get_f()
+    sim.host_f_changed()
+    sim.FORCING()
+    for it in range(6):
+        rhop = w.get("rho").copy()
+        w.rhoupdat()
+        w.collision_MRT()
+        err_ref = np.max(np.abs(w.get("rho") - rhop))
+        rhop_s = sim.rho.copy()
+        sim.rhoupdat()
+        sim.collision_MRT()
+        err = np.max(np.abs(sim.rho - rhop_s))
+        if math_mode == capi.MATH_STRICT:
+            assert np.array_equal(sim.rho, w.get("rho")) and err == err_ref
+        else:
+            assert abs(err - err_ref) <= 1e-12 * max(err_ref, np.max(np.abs(w.get_f())))
+    f = sim.sync_f_to_host()
+    if math_mode == capi.MATH_STRICT:
+        assert np.array_equal(f, w.get_f())
+    else:
+        assert relerr(f, w.get_f()) < 1e-12
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_device_prerelax_matches_driver_loop(oracle, scheme):
+    nx, ny, nz = 32, 8, 8
+    w, p = oracle.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+    it_ref = 0
+    while True:
+        rhop = w.get("rho").copy()
+        w.rhoupdat()
+        w.collision_MRT()
+        err_ref = np.max(np.abs(w.get("rho") - rhop))
+        if err_ref <= 1e-5 or it_ref > 200:
+            break
+        it_ref += 1
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT)
+    w0, _ = oracle.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+    for k in ("ux", "uy", "uz", "rho"):
+        getattr(sim, k)[...] = w0.get(k)
+    sim.f[...] = w0.get_f()
+    sim.FORCING()
+    it, err = sim.prerelax_device(maxiter=200)
+    assert it == it_ref and err == err_ref
+    assert np.array_equal(sim.f, w.get_f())
+    assert np.array_equal(sim.rho, w.get("rho"))
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_external_macro_and_force_field(oracle, scheme):
+    nx, ny, nz = 24, 6, 5
+    w, p, sim = make_pair(oracle, nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT, perturb=1e-4)
+    rng = np.random.default_rng(2)
+    shp = (nz, ny, nx)
+    F = [1e-5 * rng.normal(size=shp) for _ in range(3)]
+    for k, a in zip(("fx", "fy", "fz"), F):
+        w.set(k, a)
+    sim.set_force_field(*F)
+    macro = [1e-3 * rng.normal(size=shp)] + [0.02 * rng.normal(size=shp) for _ in range(3)]
+    for k, a in zip(("rho", "ux", "uy", "uz"), macro):
+        w.set(k, a)
+    sim.set_macro(*macro)
+    out = np.empty((nz, ny, nx, 19))
+    for _ in range(3):                      # arrays stay frozen: EXTERNAL every time
+        w.collision_MRT()
+        sim.collide_stream(capi.MACRO_EXTERNAL)
+        assert np.array_equal(sim.download_f(out), w.get_f())
+    w.macrovar()                            # macrovar with a force field
+    sim.device_macrovar()
+    for k in ("rho", "ux", "uy", "uz"):
+        assert np.array_equal(getattr(sim, k), w.get(k))
+    w.collision_MRT()
+    sim.collide_stream(capi.MACRO_MAIN)
+    assert np.array_equal(sim.download_f(out), w.get_f())
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_avedensity_shift_enters_next_collision(oracle, scheme):
+    nx, ny, nz = 20, 6, 4
+    w, p, sim = make_pair(oracle, nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT, perturb=1e-3)
+    sim.v.ipart = True
+    for step in range(1, 4):
+        w.collision_MRT(); w.macrovar()
+        sim.collision_MRT(); sim.istep = step; sim.device_macrovar()
+    mean_ref, n_ref = w.avedensity()
+    sim.avedensity()
+    assert np.allclose(sim.rho, w.get("rho"), rtol=0, atol=1e-15 * np.max(np.abs(w.get_f())))
+    w.collision_MRT()
+    sim.collision_MRT()
+    f = sim.sync_f_to_host()
+    assert relerr(f, w.get_f()) < 1e-13
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_probe_and_profiles(oracle, scheme):
+    nx, ny, nz = 40, 6, 5
+    w, p, sim = make_pair(oracle, nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT, perturb=1e-4)
+    for _ in range(3):
+        w.collision_MRT(); sim.collide_stream()
+        w.macrovar()
+        got = sim.probe(nx // 2, ny // 2 + 1, nz // 2 + 1)
+        ref = [w.get(k)[nz // 2, ny // 2, nx // 2 - 1] for k in ("rho", "ux", "uy", "uz")]
+        assert list(got) == ref
+        prof = sim.profiles()
+        ux, uy, uz, rho = (w.get(k) for k in ("ux", "uy", "uz", "rho"))
+        refs = [ux, uy, uz, ux * ux, uy * uy, uz * uz, ux * uy, ux * uz, uy * uz, rho, rho * rho]
+        for q, a in enumerate(refs):
+            s = a.sum(axis=(0, 1))
+            assert np.allclose(prof[q], s, rtol=1e-12, atol=1e-14 * np.max(np.abs(a)) * ny * nz), q
+    sim.close()
+
+
+def test_poiseuille_startup_on_gpu(oracle):
+    # the reference's own known-answer (saveload.f90:921-935) reproduced by the CUDA path
+    from oracle import textbook as tb
+    nx, ny, nz = 32, 4, 4
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=True)
+    sim.initvel(); sim.FORCING(); sim.initpop()
+    sim.v.nflowout = 100
+    sim.run(600)
+    uy = sim.uy[nz // 2, 0, : nx // 2] / sim.v.ustar
+    uut, _ = tb.poiseuille_startup(nx, sim.v.ustar, sim.v.visc, 600)
+    assert np.max(np.abs(uy - uut)) < 2e-3
+    sim.close()
+
+
+def test_counters_prove_kernels_ran(oracle):
+    sim = pkg.ChannelFlow(32, 8, 8, laminar=True)
+    sim.initvel(); sim.FORCING(); sim.initpop()
+    sim.run(10)
+    c = sim.counters()
+    assert c["step_kernels"] == 10 and c["steps"] == 10
+    sim.close()
