@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--scheme", default="aa", choices=["aa", "ab"])
+    ap.add_argument("--scheme", default="auto", choices=["auto", "aa", "ab"])
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -197,11 +197,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    scheme = capi.SCHEME_AA if args.scheme == "aa" else capi.SCHEME_AB
+    scheme = {"aa": capi.SCHEME_AA, "ab": capi.SCHEME_AB, "auto": capi.SCHEME_AUTO}[args.scheme]
     math_mode = capi.MATH_FAST if args.math == "fast" else capi.MATH_STRICT
     sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local_rank, scheme=scheme,
                           math_mode=math_mode, nccl_id=nccl_id, overlap=not args.no_overlap, allocate_host=False)
     nodes_global = nx * ny * nz
+    args.scheme = "ab" if sim.counters()["scheme"] == capi.SCHEME_AB else "aa"     # what AUTO resolved to
     do_e2e = not args.no_e2e and args.workload != "c4"
 
     # synthetic initial state (turbulent set: log-law + perturbation + seeded noise), host side, once

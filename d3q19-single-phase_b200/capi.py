@@ -9,10 +9,10 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libd3q19b200.so")
+LIB_PATH = os.environ.get("D3Q19_LIB") or os.path.join(HERE, "libd3q19b200.so")   # D3Q19_LIB: kernel-variant experiments
 
 ABI_VERSION = 1
-SCHEME_AA, SCHEME_AB = 0, 1
+SCHEME_AA, SCHEME_AB, SCHEME_AUTO = 0, 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
 MACRO_MAIN, MACRO_PRERELAX, MACRO_EXTERNAL = 0, 1, 2
 NPOP = 19

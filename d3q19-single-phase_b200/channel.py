@@ -346,4 +346,4 @@ class ChannelFlow:
         out = (C.c_int64 * 8)()
         capi.check(self.L.d3q19_get_counters(self.h, out))
         return dict(step_kernels=out[0], other_kernels=out[1], nccl_ops=out[2], steps=out[3],
-                    population_bytes=out[4], phase=out[5], x_pitch=out[6])
+                    population_bytes=out[4], phase=out[5], x_pitch=out[6], scheme=out[7])

@@ -64,6 +64,8 @@ struct d3q19_handle {
     Geom g;
     size_t nfield = 0;            // xp*ly*lz
     double *A = nullptr, *B = nullptr;
+    double *A_alloc = nullptr, *B_alloc = nullptr;   // A, B sit PAD elements inside these (x-1 / x+1 past the ends stays mapped)
+    bool idx32 = true;            // a population has < 2^32 elements: 32-bit in-slab indices
     int phase = 0;                // AA: 0 canonical, 1 swapped post-collision.  AB: always post-collision.
     double *rho = nullptr, *ux = nullptr, *uy = nullptr, *uz = nullptr;
     double *ffx = nullptr, *ffy = nullptr, *ffz = nullptr;
@@ -197,7 +199,7 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
     if (h->sc) cudaStreamSynchronize(h->sc);
     if (h->sx) cudaStreamSynchronize(h->sx);
     if (h->comm) nccl_api().CommDestroy(h->comm);
-    void *ptrs[] = {h->A, h->B, h->rho, h->ux, h->uy, h->uz, h->ffx, h->ffy, h->ffz, h->solid, h->isn, h->ypglb,
+    void *ptrs[] = {h->A_alloc, h->B_alloc, h->rho, h->ux, h->uy, h->uz, h->ffx, h->ffy, h->ffz, h->solid, h->isn, h->ypglb,
                     h->wp, h->omgp, h->send_up, h->send_dn, h->recv_lo, h->recv_hi, h->stage[0], h->stage[1],
                     h->scal, h->red_d, h->red_c, h->prof_partial, h->prof_out};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -216,7 +218,8 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
         return fail("d3q19_create: abi_version %d, library speaks %d", cfg->abi_version, D3Q19_ABI_VERSION);
     if (cfg->lx < 2 || cfg->ly < 1 || cfg->lz < 1) return fail("d3q19_create: bad local extents %d %d %d", cfg->lx, cfg->ly, cfg->lz);
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) return fail("d3q19_create: bad rank %d of %d", cfg->rank, cfg->nranks);
-    if (cfg->scheme != D3Q19_SCHEME_AA && cfg->scheme != D3Q19_SCHEME_AB) return fail("d3q19_create: unknown scheme %d", cfg->scheme);
+    if (cfg->scheme != D3Q19_SCHEME_AA && cfg->scheme != D3Q19_SCHEME_AB && cfg->scheme != D3Q19_SCHEME_AUTO)
+        return fail("d3q19_create: unknown scheme %d", cfg->scheme);
     if (cfg->ly > 65535 || cfg->lz + 2 > 65535) return fail("d3q19_create: ly, lz must be < 65535");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
@@ -235,6 +238,13 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
     g.zlo_src = cfg->nranks == 1 ? g.lz : 0;
     g.zhi_src = cfg->nranks == 1 ? 1 : g.lz + 1;
     h->nfield = (size_t)g.plane * g.lz;
+    if (h->cfg.scheme == D3Q19_SCHEME_AUTO) {
+        // two arrays (one-step pull) when they fit comfortably, else in place
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { fail("d3q19_create: cudaMemGetInfo failed"); delete h; return 1; }
+        const double two = 2.0 * NPOP * (double)g.slab * sizeof(double);
+        h->cfg.scheme = (two < 0.45 * (double)free_b) ? D3Q19_SCHEME_AB : D3Q19_SCHEME_AA;
+    }
 
 #define CKH(call)                                                      \
     do {                                                               \
@@ -257,12 +267,16 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
     }
     CKH(cudaEventCreate(&h->t0));
     CKH(cudaEventCreate(&h->t1));
-    const size_t fbytes = (size_t)NPOP * g.slab * sizeof(double);
-    CKH(cudaMalloc(&h->A, fbytes));
-    CKH(cudaMemsetAsync(h->A, 0, fbytes, h->sc));
-    if (cfg->scheme == D3Q19_SCHEME_AB) {
-        CKH(cudaMalloc(&h->B, fbytes));
-        CKH(cudaMemsetAsync(h->B, 0, fbytes, h->sc));
+    const size_t PAD = 32;        // doubles (256 B) before and after
+    const size_t fbytes = ((size_t)NPOP * g.slab + 2 * PAD) * sizeof(double);
+    h->idx32 = (unsigned long long)g.slab + 2 < 0xffffffffull && !getenv("D3Q19_FORCE_IDX64");
+    CKH(cudaMalloc(&h->A_alloc, fbytes));
+    CKH(cudaMemsetAsync(h->A_alloc, 0, fbytes, h->sc));
+    h->A = h->A_alloc + PAD;
+    if (h->cfg.scheme == D3Q19_SCHEME_AB) {
+        CKH(cudaMalloc(&h->B_alloc, fbytes));
+        CKH(cudaMemsetAsync(h->B_alloc, 0, fbytes, h->sc));
+        h->B = h->B_alloc + PAD;
     }
     CKH(cudaMalloc(&h->scal, 64 * sizeof(double)));
     CKH(cudaMemsetAsync(h->scal, 0, 64 * sizeof(double), h->sc));
@@ -445,7 +459,8 @@ static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int 
     if (nplanes <= 0) return 0;
     StepParams p = p0;
     p.z0 = z0;
-    k_step<SK, STRICT, GENERIC><<<grid_nodes(h, nplanes), BLOCK_X, 0, s>>>(p);
+    if (h->idx32) k_step<SK, STRICT, GENERIC, uint32_t><<<grid_nodes(h, nplanes), BLOCK_X, 0, s>>>(p);
+    else k_step<SK, STRICT, GENERIC, unsigned long long><<<grid_nodes(h, nplanes), BLOCK_X, 0, s>>>(p);
     CK(cudaGetLastError());
     h->n_step_kernels++;
     return 0;
@@ -752,7 +767,7 @@ extern "C" int d3q19_timer_stop(d3q19_handle *h, float *ms) {
 extern "C" int d3q19_get_counters(d3q19_handle *h, int64_t out[8]) {
     out[0] = h->n_step_kernels; out[1] = h->n_other_kernels; out[2] = h->n_nccl; out[3] = h->n_steps;
     out[4] = (int64_t)((size_t)NPOP * h->g.slab * sizeof(double) * (h->cfg.scheme == D3Q19_SCHEME_AB ? 2 : 1));
-    out[5] = h->phase; out[6] = h->g.xp; out[7] = 0;
+    out[5] = h->phase; out[6] = h->g.xp; out[7] = h->cfg.scheme;
     return 0;
 }
 

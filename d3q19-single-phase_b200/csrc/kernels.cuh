@@ -27,7 +27,47 @@ namespace d3q {
 enum ReadKind { READ_DIRECT = 0, READ_PULL_NAT = 1, READ_PULL_SWAP = 2 };
 enum StepKind { STEP_AB = 0, STEP_AA_EVEN = 1, STEP_AA_ODD = 2 };
 
-constexpr int BLOCK_X = 128;
+#ifndef D3Q_BLOCK_X
+#define D3Q_BLOCK_X 128
+#endif
+// Resident CTAs per SM the step kernels are compiled for.  Measured on B200 (profiles/
+// r01_variant_sweep.md): AB and AA-even sit at the DRAM limit with 4 CTAs (<= 128 registers);
+// the AA odd step, which keeps 19 addresses live across the collision, is FASTER with 3 CTAs
+// and 155 registers than squeezed into 128 (1.70 ms vs 1.80 ms on 512x256x256).
+#ifndef D3Q_MIN_BLOCKS
+#define D3Q_MIN_BLOCKS 4
+#endif
+#ifndef D3Q_MIN_BLOCKS_ODD
+#define D3Q_MIN_BLOCKS_ODD 3
+#endif
+constexpr int BLOCK_X = D3Q_BLOCK_X;
+
+// cache policy of the population accesses (each address is read once and written once per step)
+#ifndef D3Q_HINT
+#define D3Q_HINT 0
+#endif
+#ifndef D3Q_ADDR                 // 0: wall handled by an offset select; 1: by a predicated second access
+#define D3Q_ADDR 0
+#endif
+
+__device__ __forceinline__ double pop_load(const double *p) {
+#if D3Q_HINT == 1
+    return __ldcs(p);          // streaming: evict-first
+#elif D3Q_HINT == 2
+    return __ldcg(p);          // L2 only
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ void pop_store(double *p, double v) {
+#if D3Q_HINT == 1
+    __stcs(p, v);
+#elif D3Q_HINT == 2
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
 
 struct Geom {
     int lx, ly, lz, xp;
@@ -55,60 +95,111 @@ struct StepParams {
 };
 
 // ---- neighbour addressing ------------------------------------------------------------------
+// Offsets are element indices INSIDE one population (a "slab"); the population base
+// A + slot*slab is warp-uniform.  IDX is uint32_t whenever a slab has < 2^32 elements (any
+// realistic size: 34 GB per population), which halves the registers held across the collision
+// in the AA odd step, where every address is used twice (load, then store).
+template <class IDX>
 struct NodeIdx {
     int x, y, zg;
-    long long n;              // x + xp*(y + ly*zg)
-    long long oy[3], oz[3];   // row / plane offsets of (y-1,y,y+1), (z-1,z,z+1) with wraps
+    IDX n;                    // x + xp*(y + ly*zg)
+    IDX row[3][3];            // x + xp*(y' + ly*z') for y' in (y-1,y,y+1), z' in (z-1,z,z+1), periodic
     bool wall_lo, wall_hi;    // x == 0 / x == lx-1
 };
 
-__device__ __forceinline__ NodeIdx make_node(const Geom &g, int x, int y, int zg) {
-    NodeIdx k;
+template <class IDX>
+__device__ __forceinline__ NodeIdx<IDX> make_node(const Geom &g, int x, int y, int zg) {
+    NodeIdx<IDX> k;
     k.x = x; k.y = y; k.zg = zg;
     const int ym = (y == 0) ? g.ly - 1 : y - 1;
     const int yp = (y == g.ly - 1) ? 0 : y + 1;
     const int zm = (zg == 1) ? g.zlo_src : zg - 1;
     const int zp = (zg == g.lz) ? g.zhi_src : zg + 1;
-    k.oy[0] = (long long)ym * g.xp; k.oy[1] = (long long)y * g.xp; k.oy[2] = (long long)yp * g.xp;
-    k.oz[0] = (long long)zm * g.plane; k.oz[1] = (long long)zg * g.plane; k.oz[2] = (long long)zp * g.plane;
-    k.n = x + k.oy[1] + k.oz[1];
+    const IDX oy[3] = {(IDX)ym * (IDX)g.xp, (IDX)y * (IDX)g.xp, (IDX)yp * (IDX)g.xp};
+    const IDX oz[3] = {(IDX)zm * (IDX)g.plane, (IDX)zg * (IDX)g.plane, (IDX)zp * (IDX)g.plane};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) k.row[a][b] = (IDX)x + oy[a] + oz[b];
+    k.n = k.row[1][1];
     k.wall_lo = (x == 0);
     k.wall_hi = (x == g.lx - 1);
     return k;
 }
 
-// element offset (inside the whole SoA array) from which direction I is gathered
+// Where direction I of node k is gathered from, for the three storage phases:
+//   regular: population `slot_nb` at index n - c_i   (periodic y,z)
+//   at a wall (x - c_ix outside): population `slot_wall` at the node itself (half-way
+//   bounce-back, wall at rest -- the imove<1 .or. imove>lx branch of collision.f90:229-230)
 template <int RK, int I>
-__device__ __forceinline__ long long gather_offset(const Geom &g, const NodeIdx &k) {
-    constexpr int cx = dir_cx(I), cy = dir_cy(I), cz = dir_cz(I), opp = dir_opp(I);
-    if (RK == READ_DIRECT) return (long long)I * g.slab + k.n;
-    const long long nb = (k.x - cx) + k.oy[1 - cy] + k.oz[1 - cz];   // n - c_i with periodic y,z
-    constexpr int slot_nb = (RK == READ_PULL_NAT) ? I : opp;
-    constexpr int slot_wall = (RK == READ_PULL_NAT) ? opp : I;
-    if (cx == 0) return (long long)slot_nb * g.slab + nb;
-    const bool wall = (cx > 0) ? k.wall_lo : k.wall_hi;               // half-way bounce-back, wall at rest
-    return wall ? (long long)slot_wall * g.slab + k.n : (long long)slot_nb * g.slab + nb;
-}
+struct Gather {
+    static constexpr int cx = dir_cx(I), cy = dir_cy(I), cz = dir_cz(I), opp = dir_opp(I);
+    static constexpr int slot_nb = (RK == READ_PULL_SWAP) ? opp : I;
+    static constexpr int slot_wall = (RK == READ_PULL_SWAP) ? I : opp;
+    static constexpr bool pulls = (RK != READ_DIRECT);
+    static constexpr bool can_bounce = pulls && cx != 0;
 
-template <int RK>
-__device__ __forceinline__ void gather19(const double *__restrict__ A, const Geom &g, const NodeIdx &k,
-                                         double (&f)[NPOP]) {
+    template <class IDX>
+    static __device__ __forceinline__ bool at_wall(const NodeIdx<IDX> &k) {
+        return can_bounce && ((cx > 0) ? k.wall_lo : k.wall_hi);
+    }
+    // index inside the population; the allocation is padded so that index -1 / +1 past the ends is mapped
+    template <class IDX>
+    static __device__ __forceinline__ IDX index_nb(const NodeIdx<IDX> &k) {
+        return pulls ? (IDX)(k.row[1 - cy][1 - cz] - (IDX)cx) : k.n;
+    }
+    // one address per direction: the wall case is a select on the element offset, so every
+    // direction costs exactly one LDG (and one STG in the AA odd step)
+    template <class IDX>
+    static __device__ __forceinline__ long long offset(const Geom &g, const NodeIdx<IDX> &k) {
+        const long long reg = (long long)slot_nb * g.slab + (long long)index_nb(k);
+        if (!can_bounce) return reg;
+        return at_wall(k) ? (long long)slot_wall * g.slab + (long long)k.n : reg;
+    }
+    template <class IDX>
+    static __device__ __forceinline__ double load(const double *A, const Geom &g, const NodeIdx<IDX> &k) {
+#if D3Q_ADDR == 0
+        return pop_load(A + offset(g, k));
+#else
+        double v = pop_load(A + (long long)slot_nb * g.slab + index_nb(k));
+        if (can_bounce) {
+            if (at_wall(k)) v = pop_load(A + (long long)slot_wall * g.slab + k.n);
+        }
+        return v;
+#endif
+    }
+    // AA odd: the post-collision value of direction opp(I) goes back to where f_I came from
+    template <class IDX>
+    static __device__ __forceinline__ void store_back(double *A, const Geom &g, const NodeIdx<IDX> &k, double v) {
+#if D3Q_ADDR == 0
+        pop_store(A + offset(g, k), v);
+#else
+        if (can_bounce) {
+            if (at_wall(k)) { pop_store(A + (long long)slot_wall * g.slab + k.n, v); return; }
+        }
+        pop_store(A + (long long)slot_nb * g.slab + index_nb(k), v);
+#endif
+    }
+};
+
+template <int RK, class IDX>
+__device__ __forceinline__ void gather19(const double *A, const Geom &g, const NodeIdx<IDX> &k, double (&f)[NPOP]) {
     static_for<NPOP>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
-        f[i] = A[gather_offset<RK, i>(g, k)];
+        f[i] = Gather<RK, i>::load(A, g, k);
     });
 }
 
 // ---- the step kernel ---------------------------------------------------------------------------
 // GENERIC = false: main loop, uniform force, no solids, moments in registers (304 B/node).
 // GENERIC = true : run-time macro mode / force field / solid mask.
-template <int SK, bool STRICT, bool GENERIC>
-__global__ void __launch_bounds__(BLOCK_X) k_step(const __grid_constant__ StepParams p) {
+template <int SK, bool STRICT, bool GENERIC, class IDX>
+__global__ void __launch_bounds__(BLOCK_X, SK == STEP_AA_ODD ? D3Q_MIN_BLOCKS_ODD : D3Q_MIN_BLOCKS) k_step(const __grid_constant__ StepParams p) {
     const Geom &g = p.g;
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     double rhoerr = 0.0;
     if (x < g.lx) {
-        const NodeIdx k = make_node(g, x, blockIdx.y, p.z0 + blockIdx.z);
+        const NodeIdx<IDX> k = make_node<IDX>(g, x, blockIdx.y, p.z0 + blockIdx.z);
         constexpr int RK = (SK == STEP_AB) ? READ_PULL_NAT : (SK == STEP_AA_EVEN ? READ_DIRECT : READ_PULL_SWAP);
         double f[NPOP];
         gather19<RK>(p.A, g, k, f);
@@ -155,17 +246,17 @@ __global__ void __launch_bounds__(BLOCK_X) k_step(const __grid_constant__ StepPa
         if (SK == STEP_AB) {
             static_for<NPOP>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
-                p.B[(long long)i * g.slab + k.n] = f[i];
+                pop_store(p.B + (long long)i * g.slab + k.n, f[i]);
             });
         } else if (SK == STEP_AA_EVEN) {
             static_for<NPOP>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
-                p.A[(long long)dir_opp(i) * g.slab + k.n] = f[i];
+                pop_store(p.A + (long long)dir_opp(i) * g.slab + k.n, f[i]);
             });
         } else {
             static_for<NPOP>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
-                p.A[gather_offset<READ_PULL_SWAP, i>(g, k)] = f[dir_opp(i)];
+                Gather<READ_PULL_SWAP, i>::store_back(p.A, g, k, f[dir_opp(i)]);
             });
         }
     }
@@ -208,7 +299,7 @@ __global__ void __launch_bounds__(BLOCK_X) k_macro(const __grid_constant__ Macro
     const Geom &g = p.g;
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     if (x >= g.lx) return;
-    const NodeIdx k = make_node(g, x, blockIdx.y, 1 + blockIdx.z);
+    const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, blockIdx.y, 1 + blockIdx.z);
     const long long m = x + (long long)g.xp * (k.y + (long long)g.ly * (k.zg - 1));
     double f[NPOP];
     gather19<RK>(p.A, g, k, f);
@@ -245,7 +336,7 @@ __global__ void __launch_bounds__(BLOCK_X) k_macro(const __grid_constant__ Macro
 // one node -> out[4] (probe, saveload.f90:4059-4100)
 template <int RK>
 __global__ void k_probe(Geom g, const double *A, int x, int y, int zg, double Fx, double Fy, double Fz, double *out) {
-    const NodeIdx k = make_node(g, x, y, zg);
+    const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, y, zg);
     double f[NPOP];
     gather19<RK>(A, g, k, f);
     moments_strict(f, Fx, Fy, Fz, out[0], out[1], out[2], out[3]);
@@ -257,7 +348,7 @@ template <int RK>
 __global__ void __launch_bounds__(BLOCK_X) k_gather_aos(Geom g, const double *A, double *aos, int zg0) {
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     if (x >= g.lx) return;
-    const NodeIdx k = make_node(g, x, blockIdx.y, zg0 + blockIdx.z);
+    const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, blockIdx.y, zg0 + blockIdx.z);
     double f[NPOP];
     gather19<RK>(A, g, k, f);
     double *o = aos + (long long)NPOP * (x + (long long)g.lx * (k.y + (long long)g.ly * blockIdx.z));
@@ -280,12 +371,12 @@ __global__ void __launch_bounds__(BLOCK_X) k_scatter_aos(Geom g, double *A, cons
 __global__ void __launch_bounds__(BLOCK_X) k_unstream(Geom g, const double *Cn, double *A) {
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     if (x >= g.lx) return;
-    const NodeIdx k = make_node(g, x, blockIdx.y, 1 + blockIdx.z);
+    const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, blockIdx.y, 1 + blockIdx.z);
     static_for<NPOP>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
         constexpr int cx = dir_cx(i), cy = dir_cy(i), cz = dir_cz(i);
         const bool wall = (cx > 0) ? k.wall_hi : (cx < 0 ? k.wall_lo : false);
-        const long long nb = (k.x + cx) + k.oy[1 + cy] + k.oz[1 + cz];
+        const unsigned long long nb = k.row[1 + cy][1 + cz] + (unsigned long long)(long long)cx;
         A[(long long)i * g.slab + k.n] =
             wall ? Cn[(long long)dir_opp(i) * g.slab + k.n] : Cn[(long long)i * g.slab + nb];
     });
@@ -397,7 +488,7 @@ __global__ void __launch_bounds__(BLOCK_X) k_profiles(Geom g, const double *A, d
     for (long long row = r0; row < r1; ++row) {
         const int y = (int)(row % g.ly), z = (int)(row / g.ly);
         if (solid && solid[row * g.xp + x] > 0) continue;
-        const NodeIdx k = make_node(g, x, y, z + 1);
+        const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, y, z + 1);
         double f[NPOP], r, a, b, c;
         gather19<RK>(A, g, k, f);
         moments_strict(f, Fx, Fy, Fz, r, a, b, c);

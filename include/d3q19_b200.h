@@ -49,7 +49,8 @@ extern "C" {
 /* Streaming scheme (how populations live in HBM). */
 enum {
     D3Q19_SCHEME_AA = 0,   /* in-place, one array: even step local, odd step pull/push (default) */
-    D3Q19_SCHEME_AB = 1    /* two arrays, one-step pull                                          */
+    D3Q19_SCHEME_AB = 1,   /* two arrays, one-step pull                                          */
+    D3Q19_SCHEME_AUTO = 2  /* AB when both arrays fit in < 45 % of free HBM, else AA             */
 };
 
 /* Arithmetic of the collision. */
@@ -141,7 +142,8 @@ int d3q19_profiles(d3q19_handle *h, double *out_11_by_lx);
 int d3q19_timer_start(d3q19_handle *h);
 int d3q19_timer_stop(d3q19_handle *h, float *elapsed_ms);
 /* counters: [0] step kernels launched, [1] other kernels launched, [2] NCCL ops,
- *           [3] steps taken, [4] bytes of populations resident, [5] storage phase          */
+ *           [3] steps taken, [4] bytes of populations resident, [5] storage phase,
+ *           [6] x pitch, [7] scheme in use                                                 */
 int d3q19_get_counters(d3q19_handle *h, int64_t out[8]);
 
 /* ---- the shim state machine (what the replacement collision.f90 calls) ------------------ */

@@ -1,0 +1,120 @@
+"""Multi-GPU parity worker (launched by tests/test_gpu_multi.py under torch.distributed.run).
+
+Each rank owns one z-slab on its own GPU.  The global result must be BIT-IDENTICAL to the
+single-domain oracle (streaming is a copy, collision is node-local), for
+both storage schemes, with and without the boundary/interior overlap, for even and uneven
+slabs; scalar reductions (avedensity, pre-relaxation error, profiles) must agree over ranks.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+pkg = entry.load_package()
+capi = pkg.capi
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(local)
+    ok = True
+
+    def new_id():
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.tensor(list(capi.nccl_unique_id()), dtype=torch.uint8)
+        dist.broadcast(idt, src=0)
+        return bytes(idt.tolist())
+
+    cases = [((24, 6, 4 * world), True), ((33, 5, 3 * world + 1), True), ((16, 4, world), True),
+             ((24, 6, 4 * world), False), ((40, 3, 2 * world), True)]
+    for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
+        for (nx, ny, nz), overlap in cases:
+            w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+            rng = np.random.default_rng(7)
+            w.set_f(w.get_f() + 1e-4 * rng.normal(size=(nz, ny, nx, 19)))
+            sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local, scheme=scheme,
+                                  math_mode=capi.MATH_STRICT, nccl_id=new_id(), overlap=overlap)
+            z0, z1 = sim.globalz, sim.globalz + sim.lz
+            sim.FORCING()
+            sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
+            w.macrovar()
+            out = np.empty((sim.lz, ny, nx, 19))
+            for step in range(1, 8):
+                w.collision_MRT()
+                w.macrovar()
+                sim.collide_stream()
+                sim.download_f(out)
+                if not np.array_equal(out, w.get_f()[z0:z1]):
+                    print("rank %d: MISMATCH scheme %d case %s step %d" % (rank, scheme, (nx, ny, nz, overlap), step))
+                    ok = False
+                    break
+                if step in (3, 4):
+                    sim.device_macrovar()
+                    for k in ("rho", "ux", "uy", "uz"):
+                        ok &= bool(np.array_equal(getattr(sim, k), w.get(k)[z0:z1]))
+                    pr = sim.profiles()
+                    ref = w.get("uy").sum(axis=(0, 1))
+                    ok &= bool(np.allclose(pr[1], ref, rtol=1e-12, atol=1e-15))
+            # avedensity across ranks (MPI_ALLREDUCE, collision.f90:500-501)
+            sim.device_macrovar()
+            mean_ref, n_ref = w.avedensity()
+            import ctypes as C
+            m, n = C.c_double(0), C.c_int64(0)
+            capi.check(sim.L.d3q19_avedensity(sim.h, C.byref(m), C.byref(n)))
+            ok &= (n.value == n_ref) and abs(m.value - mean_ref) <= 1e-13 * max(abs(mean_ref), 1e-30) + 1e-18
+            w.collision_MRT()
+            sim.collide_stream()
+            sim.download_f(out)
+            err = np.max(np.abs(out - w.get_f()[z0:z1])) / np.max(np.abs(w.get_f()))
+            ok &= bool(err < 1e-13)
+            sim.close()
+            w.close()
+            if not ok:
+                break
+        if not ok:
+            break
+
+    # device pre-relaxation across ranks (main.f90:70-90 with MPI_ALLREDUCE MAX)
+    if ok:
+        nx, ny, nz = 32, 8, 4 * world
+        w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+        w0f, w0 = w.get_f().copy(), {k: w.get(k).copy() for k in ("rho", "ux", "uy", "uz")}
+        it_ref = 0
+        while True:
+            rhop = w.get("rho").copy()
+            w.rhoupdat(); w.collision_MRT()
+            err_ref = np.max(np.abs(w.get("rho") - rhop))
+            if err_ref <= 1e-5 or it_ref > 100:
+                break
+            it_ref += 1
+        sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local,
+                              math_mode=capi.MATH_STRICT, nccl_id=new_id())
+        z0, z1 = sim.globalz, sim.globalz + sim.lz
+        sim.f[...] = w0f[z0:z1]
+        for k in ("rho", "ux", "uy", "uz"):
+            getattr(sim, k)[...] = w0[k][z0:z1]
+        sim.FORCING()
+        it, err = sim.prerelax_device(maxiter=100)
+        ok &= (it == it_ref) and (err == err_ref) and bool(np.array_equal(sim.f, w.get_f()[z0:z1]))
+        sim.close()
+
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MGPU_PARITY_OK" if t.item() == 1 else "MGPU_PARITY_FAILED")
+    dist.destroy_process_group()
+    return 0 if t.item() == 1 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
