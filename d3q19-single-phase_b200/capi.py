@@ -26,6 +26,7 @@ SYMBOLS = [
     "d3q19_prerelax", "d3q19_set_solid_mask", "d3q19_set_particles", "d3q19_profiles",
     "d3q19_timer_start", "d3q19_timer_stop", "d3q19_get_counters",
     "d3q19_shim_bind", "d3q19_shim_set_schedule", "d3q19_shim_forcing", "d3q19_shim_rhoupdat", "d3q19_shim_collision_mrt",
+    "d3q19_shim_prerelax_state",
     "d3q19_shim_macrovar", "d3q19_shim_avedensity", "d3q19_shim_sync_f_to_host", "d3q19_shim_sync_f_to_device",
 ]
 
@@ -60,6 +61,7 @@ class ShimArrays(C.Structure):
         ("force_realz", C.POINTER(C.c_double)),
         ("ibnodes", C.POINTER(C.c_int32)), ("isnodes", C.POINTER(C.c_int32)),
         ("ndiag", C.c_int32), ("nflowout", C.c_int32), ("nsteps_total", C.c_int32), ("istep0", C.c_int32),
+        ("ntime", C.c_int32), ("prerelax_maxiter", C.c_int32), ("rhoepsl", C.c_double),
     ]
 
 
@@ -111,6 +113,7 @@ def load():
     L.d3q19_shim_forcing.argtypes = [vp, C.c_double, C.c_double]
     L.d3q19_shim_rhoupdat.argtypes = [vp]
     L.d3q19_shim_collision_mrt.argtypes = [vp]
+    L.d3q19_shim_prerelax_state.argtypes = [vp, dp, ip]
     L.d3q19_shim_macrovar.argtypes = [vp, C.c_int32]
     L.d3q19_shim_avedensity.argtypes = [vp]
     L.d3q19_shim_sync_f_to_host.argtypes = [vp]

@@ -43,6 +43,7 @@ class VarInc:
         self.pi = 4.0 * math.atan(1.0)          # var_inc.f90:71
         self.pi2 = 2.0 * self.pi
         self.ndiag, self.nflowout = 250, 100    # var_inc.f90:58-59
+        self.ntime = 10000                      # var_inc.f90:59
         self.nsteps = 1000                      # para.f90:43
         self.istep0 = 0
         self.rhoepsl = 1.0e-05                  # para.f90:285
@@ -163,6 +164,7 @@ class ChannelFlow:
         a.isnodes = capi.iptr(self.isnodes)
         a.ndiag, a.nflowout = self.v.ndiag, self.v.nflowout
         a.nsteps_total, a.istep0 = self.v.nsteps, self.v.istep0
+        a.ntime, a.prerelax_maxiter, a.rhoepsl = self.v.ntime, 15000, self.v.rhoepsl
         self._shim_arrays = a
         capi.check(self.L.d3q19_shim_bind(self.h, C.byref(a)))
         self._bound = True

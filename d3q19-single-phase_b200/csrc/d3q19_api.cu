@@ -57,6 +57,10 @@ struct Shim {
     bool macro_dev_valid = false; // device rho,u = moments of the current f (or what the driver set)
     bool u_dev_loaded = false;    // host ux,uy,uz were uploaded (frozen-u pre-relaxation)
     int next_mode = D3Q19_MACRO_MAIN;
+    bool collided_since_macrovar = false;  // a main-loop collision_MRT ran since the last macrovar
+    bool in_prerelax = false;     // the last rhoupdat has not been followed by its collision_MRT yet
+    int prerelax_iter = 0;        // main.f90's istep inside the pre-relaxation loop
+    double prerelax_err = 0.0;    // max|rho - rhop| over all ranks of the current iteration (main.f90:79-80)
 };
 
 struct d3q19_handle {
@@ -544,7 +548,7 @@ extern "C" int d3q19_run(d3q19_handle *h, int32_t nsteps) {
 }
 
 // ---- macrovar / rhoupdat ---------------------------------------------------------------------------------
-static int macro_launch(d3q19_handle *h, int rho_only) {
+static int macro_launch(d3q19_handle *h, int rho_only, unsigned long long *rhoerr_bits = nullptr) {
     RK_(ensure_macro_arrays(h));
     RK_(wait_exchange(h));
     MacroParams p;
@@ -559,6 +563,7 @@ static int macro_launch(d3q19_handle *h, int rho_only) {
     p.ipart = h->cfg.ipart && h->isn && h->ypglb;
     p.ny = h->cfg.ny; p.nz = h->cfg.nz; p.globalz = h->cfg.globalz;
     p.rho_only = rho_only;
+    p.rhoerr_bits = rhoerr_bits;
     const dim3 gr = grid_nodes(h, h->g.lz);
     switch (read_kind(h)) {
     case READ_DIRECT: k_macro<READ_DIRECT><<<gr, BLOCK_X, 0, h->sc>>>(p); break;
@@ -781,6 +786,11 @@ extern "C" int d3q19_shim_bind(d3q19_handle *h, const d3q19_shim_arrays *a) {
     h->shim.macro_dev_valid = false;
     h->shim.u_dev_loaded = false;
     h->shim.next_mode = D3Q19_MACRO_MAIN;
+    h->shim.collided_since_macrovar = false;
+    h->shim.in_prerelax = false;
+    h->shim.prerelax_iter = 0;
+    h->shim.prerelax_err = 0.0;
+    if (h->shim.a.prerelax_maxiter <= 0) h->shim.a.prerelax_maxiter = 15000;   // main.f90:85
     return 0;
 }
 
@@ -818,20 +828,48 @@ extern "C" int d3q19_shim_rhoupdat(d3q19_handle *h) {
     if (!s.u_dev_loaded) {                                     // u stays frozen at the driver's values
         RK_(d3q19_set_macro(h, s.a.rho, s.a.ux, s.a.uy, s.a.uz));
         s.u_dev_loaded = true;
+        s.prerelax_iter = 0;
     }
-    RK_(d3q19_rhoupdat(h));
-    RK_(d3q19_download_macro(h, s.a.rho, nullptr, nullptr, nullptr));
+    // rho = sum f, and the number main.f90:79-80 is about to form from the host arrays
+    unsigned long long *bits = reinterpret_cast<unsigned long long *>(h->scal + 17);
+    CK(cudaMemsetAsync(bits, 0, sizeof(unsigned long long), h->sc));
+    RK_(macro_launch(h, 1, bits));
+    if (h->cfg.nranks > 1) {                                   // MPI_ALLREDUCE MAX, main.f90:80
+        NK(nccl_api().AllReduce(bits, bits, 1, NCCL_UINT64, NCCL_MAX, h->comm, h->sc));
+        h->n_nccl++;
+    }
+    unsigned long long b = 0;
+    CK(cudaMemcpyAsync(&b, bits, sizeof b, cudaMemcpyDeviceToHost, h->sc));
+    RK_(d3q19_download_macro(h, s.a.rho, nullptr, nullptr, nullptr));   // synchronises sc
+    memcpy(&s.prerelax_err, &b, sizeof b);
+    s.in_prerelax = true;
     s.next_mode = D3Q19_MACRO_EXTERNAL;                        // collision reads the arrays as they now are
+    return 0;
+}
+
+extern "C" int d3q19_shim_prerelax_state(d3q19_handle *h, double *rhoerrmax, int32_t *iteration) {
+    if (rhoerrmax) *rhoerrmax = h->shim.prerelax_err;
+    if (iteration) *iteration = h->shim.prerelax_iter;
     return 0;
 }
 
 extern "C" int d3q19_shim_collision_mrt(d3q19_handle *h) {
     Shim &s = h->shim;
     RK_(shim_f_on_device(h));
+    const bool main_loop = s.next_mode == D3Q19_MACRO_MAIN;
     RK_(d3q19_collide_stream(h, s.next_mode));
     s.next_mode = D3Q19_MACRO_MAIN;
     s.f_host_valid = false;
     s.macro_dev_valid = false;
+    if (main_loop) s.collided_since_macrovar = true;
+    if (s.in_prerelax) {
+        // main.f90:85: the driver leaves the loop after THIS iteration iff the test below holds;
+        // what follows is saveinitflow (main.f90:101), which writes the host f
+        s.in_prerelax = false;
+        const bool leaving = s.prerelax_err <= s.a.rhoepsl || s.prerelax_iter > s.a.prerelax_maxiter;
+        s.prerelax_iter++;
+        if (leaving) RK_(d3q19_shim_sync_f_to_host(h));
+    }
     return 0;
 }
 
@@ -839,11 +877,16 @@ extern "C" int d3q19_shim_macrovar(d3q19_handle *h, int32_t istep) {
     Shim &s = h->shim;
     RK_(shim_f_on_device(h));
     const d3q19_shim_arrays &a = s.a;
-    const bool wanted = istep <= a.istep0                                   // initialisation calls, main.f90:102,136
+    // A macrovar that does not follow a main-loop collision_MRT is one of the initialisation
+    // calls (main.f90:102,136): its output is always read.  Inside the loop the host arrays are
+    // refreshed only on the steps where the intact driver reads them.
+    const bool wanted = !s.collided_since_macrovar
                         || (a.ndiag > 0 && istep % a.ndiag == 0)            // diag, main.f90:171
                         || (a.nflowout > 0 && istep % a.nflowout == 0)      // outputflow, main.f90:184
+                        || (a.ntime > 0 && istep % a.ntime == 0)            // the loop may exit here, main.f90:197-206
                         || istep >= a.istep0 + a.nsteps_total               // probe after the loop, main.f90:221
                         || (h->cfg.ipart && istep % 100 == 0);              // avedensity, main.f90:163
+    s.collided_since_macrovar = false;
     s.u_dev_loaded = false;
     if (!wanted) return 0;                                                  // the next collision recomputes moments in registers
     RK_(d3q19_macrovar(h));

@@ -190,6 +190,25 @@ __device__ __forceinline__ void gather19(const double *A, const Geom &g, const N
     });
 }
 
+// block maximum of a non-negative double, then one atomicMax per block: the bit pattern of a
+// non-negative IEEE double is order-preserving as an unsigned integer
+__device__ __forceinline__ void block_max_to(unsigned long long *dst, double v) {
+    __shared__ unsigned long long smax[BLOCK_X / 32];
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
+        b = t > b ? t : b;
+    }
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int wi = 1; wi < BLOCK_X / 32; ++wi) b = smax[wi] > b ? smax[wi] : b;
+        if (b) atomicMax(dst, b);
+    }
+}
+
 // ---- the step kernel ---------------------------------------------------------------------------
 // GENERIC = false: main loop, uniform force, no solids, moments in registers (304 B/node).
 // GENERIC = true : run-time macro mode / force field / solid mask.
@@ -260,23 +279,7 @@ __global__ void __launch_bounds__(BLOCK_X, SK == STEP_AA_ODD ? D3Q_MIN_BLOCKS_OD
             });
         }
     }
-    if (GENERIC && p.macro_mode == 1 && p.rhoerr_bits) {
-        // block max of a non-negative double: its bit pattern is order-preserving
-        __shared__ unsigned long long smax[BLOCK_X / 32];
-        unsigned long long b = (unsigned long long)__double_as_longlong(rhoerr);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
-            b = t > b ? t : b;
-        }
-        if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = b;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int wi = 1; wi < BLOCK_X / 32; ++wi) b = smax[wi] > b ? smax[wi] : b;
-            if (b) atomicMax(p.rhoerr_bits, b);
-        }
-    }
+    if (GENERIC && p.macro_mode == 1 && p.rhoerr_bits) block_max_to(p.rhoerr_bits, rhoerr);
 }
 
 // ---- macrovar (collision.f90:378-463) / rhoupdat (:469-480) -----------------------------------
@@ -292,12 +295,28 @@ struct MacroParams {
     double rhopart;
     int ipart, ny, nz, globalz;
     int rho_only;                     // rhoupdat: all nodes, index order, rho only
+    unsigned long long *rhoerr_bits;  // rhoupdat: max |rho_new - rho_old| as ordered bits (main.f90:79), or nullptr
 };
 
 template <int RK>
 __global__ void __launch_bounds__(BLOCK_X) k_macro(const __grid_constant__ MacroParams p) {
     const Geom &g = p.g;
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (p.rho_only && p.rhoerr_bits) {
+        // whole blocks stay alive for the block maximum
+        double err = 0.0;
+        if (x < g.lx) {
+            const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, blockIdx.y, 1 + blockIdx.z);
+            const long long m = x + (long long)g.xp * (k.y + (long long)g.ly * (k.zg - 1));
+            double f[NPOP];
+            gather19<RK>(p.A, g, k, f);
+            const double r = rho_index_order(f);
+            err = fabs(r - p.rho[m]);
+            p.rho[m] = r;
+        }
+        block_max_to(p.rhoerr_bits, err);
+        return;
+    }
     if (x >= g.lx) return;
     const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, blockIdx.y, 1 + blockIdx.z);
     const long long m = x + (long long)g.xp * (k.y + (long long)g.ly * (k.zg - 1));

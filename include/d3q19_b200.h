@@ -155,14 +155,23 @@ typedef struct d3q19_shim_arrays {
     double *force_realx, *force_realy, *force_realz;
     int32_t *ibnodes, *isnodes;
     int32_t ndiag, nflowout, nsteps_total, istep0;   /* var_inc.f90:58-59, para.f90:43-45 */
+    int32_t ntime;                   /* wall-clock guard cadence, var_inc.f90:59 / main.f90:197 (0 = never) */
+    int32_t prerelax_maxiter;        /* main.f90:85 (15000); 0 = library default 15000     */
+    double rhoepsl;                  /* para.f90:285; pre-relaxation exit tolerance        */
 } d3q19_shim_arrays;
 
 int d3q19_shim_bind(d3q19_handle *h, const d3q19_shim_arrays *a);
 /* change the output cadence / loop bounds the download policy keys on (main.f90:142,171,184) */
 int d3q19_shim_set_schedule(d3q19_handle *h, int32_t ndiag, int32_t nflowout, int32_t nsteps_total, int32_t istep0);
 int d3q19_shim_forcing(d3q19_handle *h, double force_in_y, double force_mag);
+/* rhoupdat also forms max|rho_new - rho_old| over all ranks on the device: it is the number
+ * main.f90:79-80 is about to compute, so the shim knows when the intact driver will leave the
+ * pre-relaxation loop (main.f90:85) and makes the host f current for saveinitflow (main.f90:101)
+ * in the collision_MRT of that very iteration -- and in no other.                          */
 int d3q19_shim_rhoupdat(d3q19_handle *h);
 int d3q19_shim_collision_mrt(d3q19_handle *h);
+/* last pre-relaxation error / iteration index seen by d3q19_shim_rhoupdat */
+int d3q19_shim_prerelax_state(d3q19_handle *h, double *rhoerrmax, int32_t *iteration);
 int d3q19_shim_macrovar(d3q19_handle *h, int32_t istep);
 int d3q19_shim_avedensity(d3q19_handle *h);
 /* make the host copy of f current (before savecntdflow / saveinitflow, saveload.f90:120,227) */
