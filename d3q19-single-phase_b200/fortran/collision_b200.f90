@@ -1,0 +1,301 @@
+!=============================================================================
+! collision_b200.f90 -- drop-in replacement of the reference's collision.f90
+! (UDel-CFD/D3Q19-Single-Phase, Channel-Flow/collision.f90).
+!
+! It defines the SAME argument-less subroutines that main.f90's time loop calls
+!     collision_MRT   (collision.f90:24)      main.f90:76,157
+!     macrovar        (collision.f90:378)     main.f90:102,136,161
+!     rhoupdat        (collision.f90:469)     main.f90:74
+!     avedensity      (collision.f90:487)     main.f90:166
+!     FORCING         (collision.f90:515)     main.f90:61,132
+!     FORCINGP        (collision.f90:529)     (no live call site)
+! and forwards each of them through ISO_C_BINDING to libd3q19b200.so
+! (include/d3q19_b200.h), whose device-resident populations are authoritative
+! between calls.  main.f90, para.f90, var_inc.f90, initial.f90 and saveload.f90
+! stay as they are; link this file instead of collision.f90:
+!
+!     mpif90 -O3 -r8 var_inc.f90 main.f90 para.f90 collision_b200.f90 \
+!            initial.f90 saveload.f90 -L<repo>/d3q19-single-phase_b200 -ld3q19b200
+!
+! Host-array coherence (SURVEY.md section 8(b)):
+!   * f is uploaded lazily by the first call that needs it (after initpop /
+!     loadcntdflow) and written back to the host f only when the driver is about to
+!     read it: in the last pre-relaxation iteration (for saveinitflow, main.f90:101;
+!     the library predicts the loop exit of main.f90:85 from the same max|rho-rhop|)
+!     and on request (d3q19_b200_sync_f_to_host, to be called before savecntdflow if
+!     that call at main.f90:224 is re-enabled).
+!   * rho,ux,uy,uz come back on the steps where the driver reads them: the
+!     initialisation calls, mod(istep,ndiag)==0, mod(istep,nflowout)==0,
+!     mod(istep,ntime)==0, the last step (probe, main.f90:221) and avedensity steps.
+!
+! Topology: the library decomposes in z only (x is never split; y is periodic inside
+! the kernel), so para.f90:219 must read `nprocY = 1` (then nprocZ = nproc, one rank
+! per GPU).  The shim stops with a message otherwise.
+!
+! NOTE: no Fortran compiler exists in the build image of this repository, so this
+! file is exercised only by inspection; the identical call sequence is exercised by
+! d3q19-single-phase_b200/channel.py (ctypes) in tests/test_gpu_parity.py.
+!=============================================================================
+      module d3q19_b200_shim
+      use iso_c_binding
+      implicit none
+
+      integer(c_int32_t), parameter :: D3Q19_ABI_VERSION = 1
+      integer(c_int32_t), parameter :: D3Q19_SCHEME_AUTO = 2
+      integer(c_int32_t), parameter :: D3Q19_MATH_FAST = 0
+
+      ! mirror of d3q19_config (include/d3q19_b200.h)
+      type, bind(c) :: d3q19_config
+        integer(c_int32_t) :: abi_version
+        integer(c_int32_t) :: lx, ly, lz
+        integer(c_int32_t) :: nx, ny, nz
+        integer(c_int32_t) :: globalz
+        integer(c_int32_t) :: rank, nranks
+        integer(c_int32_t) :: device
+        integer(c_int32_t) :: scheme
+        integer(c_int32_t) :: math
+        integer(c_int32_t) :: ipart
+        integer(c_int32_t) :: overlap
+        integer(c_int32_t) :: reserved_i(5)
+        real(c_double) :: s1, s2, s4, s9, s10, s13, s16
+        real(c_double) :: omegepsl, omegepslj, omegxx
+        real(c_double) :: rhopart
+        real(c_double) :: reserved_d(5)
+        integer(c_signed_char) :: nccl_id(128)
+      end type d3q19_config
+
+      ! mirror of d3q19_shim_arrays
+      type, bind(c) :: d3q19_shim_arrays
+        type(c_ptr) :: f
+        type(c_ptr) :: rho, ux, uy, uz
+        type(c_ptr) :: force_realx, force_realy, force_realz
+        type(c_ptr) :: ibnodes, isnodes
+        integer(c_int32_t) :: ndiag, nflowout, nsteps_total, istep0
+        integer(c_int32_t) :: ntime, prerelax_maxiter
+        real(c_double) :: rhoepsl
+      end type d3q19_shim_arrays
+
+      type(c_ptr), save :: handle = c_null_ptr
+      logical, save :: bound = .false.
+
+      interface
+        integer(c_int) function d3q19_create(cfg, out) bind(c, name='d3q19_create')
+          import :: c_int, c_ptr, d3q19_config
+          type(d3q19_config), intent(in) :: cfg
+          type(c_ptr), intent(out) :: out
+        end function
+        integer(c_int) function d3q19_destroy(h) bind(c, name='d3q19_destroy')
+          import :: c_int, c_ptr
+          type(c_ptr), value :: h
+        end function
+        integer(c_int) function d3q19_nccl_unique_id(id) bind(c, name='d3q19_nccl_unique_id')
+          import :: c_int, c_signed_char
+          integer(c_signed_char), intent(out) :: id(128)
+        end function
+        integer(c_int) function d3q19_device_count(n) bind(c, name='d3q19_device_count')
+          import :: c_int, c_int32_t
+          integer(c_int32_t), intent(out) :: n
+        end function
+        function d3q19_last_error() bind(c, name='d3q19_last_error') result(msg)
+          import :: c_ptr
+          type(c_ptr) :: msg
+        end function
+        integer(c_int) function d3q19_shim_bind(h, a) bind(c, name='d3q19_shim_bind')
+          import :: c_int, c_ptr, d3q19_shim_arrays
+          type(c_ptr), value :: h
+          type(d3q19_shim_arrays), intent(in) :: a
+        end function
+        integer(c_int) function d3q19_shim_set_schedule(h, ndiag, nflowout, nsteps, istep0) &
+            bind(c, name='d3q19_shim_set_schedule')
+          import :: c_int, c_ptr, c_int32_t
+          type(c_ptr), value :: h
+          integer(c_int32_t), value :: ndiag, nflowout, nsteps, istep0
+        end function
+        integer(c_int) function d3q19_shim_forcing(h, force_in_y, force_mag) bind(c, name='d3q19_shim_forcing')
+          import :: c_int, c_ptr, c_double
+          type(c_ptr), value :: h
+          real(c_double), value :: force_in_y, force_mag
+        end function
+        integer(c_int) function d3q19_set_force_field(h, fx, fy, fz) bind(c, name='d3q19_set_force_field')
+          import :: c_int, c_ptr, c_double
+          type(c_ptr), value :: h
+          real(c_double), intent(in) :: fx(*), fy(*), fz(*)
+        end function
+        integer(c_int) function d3q19_shim_rhoupdat(h) bind(c, name='d3q19_shim_rhoupdat')
+          import :: c_int, c_ptr
+          type(c_ptr), value :: h
+        end function
+        integer(c_int) function d3q19_shim_collision_mrt(h) bind(c, name='d3q19_shim_collision_mrt')
+          import :: c_int, c_ptr
+          type(c_ptr), value :: h
+        end function
+        integer(c_int) function d3q19_shim_macrovar(h, istep) bind(c, name='d3q19_shim_macrovar')
+          import :: c_int, c_ptr, c_int32_t
+          type(c_ptr), value :: h
+          integer(c_int32_t), value :: istep
+        end function
+        integer(c_int) function d3q19_shim_avedensity(h) bind(c, name='d3q19_shim_avedensity')
+          import :: c_int, c_ptr
+          type(c_ptr), value :: h
+        end function
+        integer(c_int) function d3q19_shim_sync_f_to_host(h) bind(c, name='d3q19_shim_sync_f_to_host')
+          import :: c_int, c_ptr
+          type(c_ptr), value :: h
+        end function
+        integer(c_int) function d3q19_shim_sync_f_to_device(h) bind(c, name='d3q19_shim_sync_f_to_device')
+          import :: c_int, c_ptr
+          type(c_ptr), value :: h
+        end function
+        integer(c_size_t) function c_strlen(s) bind(c, name='strlen')
+          import :: c_size_t, c_ptr
+          type(c_ptr), value :: s
+        end function
+      end interface
+
+      contains
+
+!     ---- error convention: the reference's subroutines cannot fail (SURVEY 8(b));
+!     a nonzero status is printed and the run is aborted
+      subroutine d3q19_b200_check(rc, where)
+      use mpi
+      integer(c_int), intent(in) :: rc
+      character(len=*), intent(in) :: where
+      type(c_ptr) :: cmsg
+      character(kind=c_char), pointer :: fmsg(:)
+      integer :: n, ierr_
+      if (rc == 0) return
+      cmsg = d3q19_last_error()
+      n = int(c_strlen(cmsg))
+      call c_f_pointer(cmsg, fmsg, [n])
+      write(*,*) 'd3q19_b200: ', where, ' failed: ', fmsg(1:n)
+      call MPI_ABORT(MPI_COMM_WORLD, 1, ierr_)
+      end subroutine d3q19_b200_check
+
+!     ---- lazy creation: para and allocarray have run by the first hot-path call
+      subroutine d3q19_b200_ensure
+      use mpi
+      use var_inc
+      type(d3q19_config) :: cfg
+      type(d3q19_shim_arrays) :: a
+      integer(c_int32_t) :: ndev
+      integer :: ierr_
+      if (bound) return
+      if (nprocY /= 1) then
+        if (myid == 0) write(*,*) 'd3q19_b200: set nprocY = 1 in para.f90:219 (z-slab decomposition, one rank per GPU)'
+        call MPI_ABORT(MPI_COMM_WORLD, 1, ierr_)
+      endif
+      call d3q19_b200_check(d3q19_device_count(ndev), 'd3q19_device_count')
+      cfg%abi_version = D3Q19_ABI_VERSION
+      cfg%lx = lx;  cfg%ly = ly;  cfg%lz = lz
+      cfg%nx = nx;  cfg%ny = ny;  cfg%nz = nz
+      cfg%globalz = globalz
+      cfg%rank = indz
+      cfg%nranks = nprocZ
+      cfg%device = mod(myid, max(ndev, 1))
+      cfg%scheme = D3Q19_SCHEME_AUTO
+      cfg%math = D3Q19_MATH_FAST
+      cfg%ipart = merge(1, 0, ipart)
+      cfg%overlap = 1
+      cfg%reserved_i = 0
+      cfg%s1 = s1;  cfg%s2 = s2;  cfg%s4 = s4;  cfg%s9 = s9
+      cfg%s10 = s10;  cfg%s13 = s13;  cfg%s16 = s16
+      cfg%omegepsl = omegepsl;  cfg%omegepslj = omegepslj;  cfg%omegxx = omegxx
+      cfg%rhopart = rhopart
+      cfg%reserved_d = 0.0d0
+      cfg%nccl_id = 0
+      if (nprocZ > 1) then
+        ! the bootstrap the reference's MPI job already has: rank 0 makes the id, everybody gets it
+        if (myid == 0) call d3q19_b200_check(d3q19_nccl_unique_id(cfg%nccl_id), 'd3q19_nccl_unique_id')
+        call MPI_BCAST(cfg%nccl_id, 128, MPI_BYTE, 0, MPI_COMM_WORLD, ierr_)
+      endif
+      call d3q19_b200_check(d3q19_create(cfg, handle), 'd3q19_create')
+
+      a%f = c_loc(f)
+      a%rho = c_loc(rho);  a%ux = c_loc(ux);  a%uy = c_loc(uy);  a%uz = c_loc(uz)
+      a%force_realx = c_loc(force_realx)
+      a%force_realy = c_loc(force_realy)
+      a%force_realz = c_loc(force_realz)
+      a%ibnodes = c_loc(ibnodes)
+      a%isnodes = c_null_ptr
+      if (ipart) a%isnodes = c_loc(isnodes)
+      a%ndiag = ndiag;  a%nflowout = nflowout
+      a%nsteps_total = nsteps;  a%istep0 = 0
+      a%ntime = ntime
+      a%prerelax_maxiter = 15000        ! main.f90:85
+      a%rhoepsl = rhoepsl               ! para.f90:285
+      call d3q19_b200_check(d3q19_shim_bind(handle, a), 'd3q19_shim_bind')
+      bound = .true.
+      end subroutine d3q19_b200_ensure
+
+!     ---- for the checkpoint writers/readers of saveload.f90 (optional, see header)
+      subroutine d3q19_b200_sync_f_to_host
+      call d3q19_b200_ensure
+      call d3q19_b200_check(d3q19_shim_sync_f_to_host(handle), 'd3q19_shim_sync_f_to_host')
+      end subroutine
+
+      subroutine d3q19_b200_host_f_changed
+      call d3q19_b200_ensure
+      call d3q19_b200_check(d3q19_shim_sync_f_to_device(handle), 'd3q19_shim_sync_f_to_device')
+      end subroutine
+
+      end module d3q19_b200_shim
+
+!=============================================================================
+! The subroutines main.f90 calls -- same names, no arguments, as collision.f90
+!=============================================================================
+      subroutine collision_MRT
+      use var_inc
+      use d3q19_b200_shim
+      implicit none
+      call d3q19_b200_ensure
+      call d3q19_b200_check(d3q19_shim_collision_mrt(handle), 'collision_MRT')
+      end subroutine collision_MRT
+
+      subroutine macrovar
+      use var_inc
+      use d3q19_b200_shim
+      implicit none
+      call d3q19_b200_ensure
+      ! istep0/nsteps are final only after loading (main.f90:103,120): refresh the schedule
+      call d3q19_b200_check(d3q19_shim_set_schedule(handle, ndiag, nflowout, nsteps, istep0), 'set_schedule')
+      call d3q19_b200_check(d3q19_shim_macrovar(handle, istep), 'macrovar')
+      end subroutine macrovar
+
+      subroutine rhoupdat
+      use var_inc
+      use d3q19_b200_shim
+      implicit none
+      call d3q19_b200_ensure
+      call d3q19_b200_check(d3q19_shim_rhoupdat(handle), 'rhoupdat')
+      end subroutine rhoupdat
+
+      subroutine avedensity
+      use var_inc
+      use d3q19_b200_shim
+      implicit none
+      call d3q19_b200_ensure
+      call d3q19_b200_check(d3q19_shim_avedensity(handle), 'avedensity')
+      end subroutine avedensity
+
+      SUBROUTINE FORCING
+      use var_inc
+      use d3q19_b200_shim
+      implicit none
+      call d3q19_b200_ensure
+      ! fills force_real{x,y,z} on the host exactly as collision.f90:522-524 and keeps the
+      ! force as three kernel scalars on the device
+      call d3q19_b200_check(d3q19_shim_forcing(handle, force_in_y, force_mag), 'FORCING')
+      END SUBROUTINE FORCING
+
+      SUBROUTINE FORCINGP
+      use var_inc
+      use d3q19_b200_shim
+      implicit none
+      ! The perturbation forcing of collision.f90:529-602 is host arithmetic on
+      ! force_real{x,y,z}; keep the reference's body (renamed FORCINGP_HOST, unchanged)
+      ! in the build and hand the arrays it fills to the device force-field path:
+      external FORCINGP_HOST
+      call d3q19_b200_ensure
+      call FORCINGP_HOST
+      call d3q19_b200_check(d3q19_set_force_field(handle, force_realx, force_realy, force_realz), 'FORCINGP')
+      END SUBROUTINE FORCINGP

@@ -5,15 +5,22 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it,
  * and only as the checker (or as the reported CPU baseline), never as the thing shipped.
  *
- * PARITY PINNING: "parity unpinned" with respect to an executable reference -- the reference
- * is Fortran 90 + MPI and there is no Fortran compiler or MPI in this image, and the
- * reference ships no tests, fixtures or golden vectors.  What the restatement IS pinned to:
+ * PARITY PINNING: pinned to the reference itself for the fluid path.  The reference is Fortran 90
+ * + MPI and this image has no Fortran compiler and no MPI, so it cannot be built as shipped;
+ * instead oracle/f90toc.py machine-translates the reference's own collision.f90 / para.f90 /
+ * initial.f90 / var_inc.f90, from the sources where they lie under /root/reference, into C
+ * (oracle/_ref/, git-ignored) and runs it with one thread per MPI rank (oracle/ref_runtime.h).
+ * This restatement agrees with that translation BIT FOR BIT on every case of
+ * tests/test_oracle_ref.py (1x1 ... 3x2 rank grids, uneven splits, all three MRT types,
+ * pre-relaxation, avedensity, force fields, solid nodes), and reproduces bit for bit the
+ * golden vectors the translation generated (tests/golden/*.npz, tests/test_golden.py) --
+ * those travel to the GPU box, where /root/reference does not exist.  Further anchors:
  *   (1) the analytic start-up / steady Poiseuille known-answers the reference itself embeds
  *       in saveload.f90:921-935 (tests/test_oracle.py),
- *   (2) an independent matrix-form ("textbook") numpy restatement (oracle/textbook.py),
- *   (3) oracle/_ref: the reference's own collision.f90 machine-translated to C by
- *       oracle/f90toc.py from the sources where they lie under /root/reference
- *       (bit-exact agreement required; see oracle/Makefile and tests/test_oracle_ref.py).
+ *   (2) an independent matrix-form ("textbook") numpy restatement (oracle/textbook.py).
+ * The reference ships no tests, fixtures or golden vectors of its own.
+ * The PARTICLE path (interpolated bounce-back, refill, force) is "parity unpinned": the
+ * reference snapshot does not contain partlib.f90.
  *
  * Every function cites the reference file:line (relative to Channel-Flow/) it follows.
  * Arrays use the Fortran column-major layouts of var_inc.f90 / para.f90:418-503:

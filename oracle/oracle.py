@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.
 cpu_baseline / --impl reference legs -- never by the product package.  See
 oracle/d3q19_oracle.h for what the oracle is (a restatement of
 /root/reference/Channel-Flow/collision.f90, para.f90, initial.f90) and how far its
-parity is pinned ("parity unpinned" against an executable reference: no Fortran here).
+parity is pinned (bit for bit against the machine-translated reference, oracle/ref.py).
 """
 import ctypes as C
 import os

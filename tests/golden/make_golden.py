@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by RUNNING THE REFERENCE: the Fortran hot path of
+/root/reference/Channel-Flow machine-translated to C (oracle/f90toc.py -> oracle/_ref/libref.so,
+built only in the container where the reference is mounted), one thread per MPI rank.
+
+    python tests/golden/make_golden.py          # needs oracle/_ref/libref.so (make -C oracle ref)
+
+Every fixture stores the inputs (initial populations f0, frozen u or force arrays where the
+case needs them) and the reference's outputs after `steps` steps of the driver sequence named
+in `kind`, plus the parameters as a JSON string.  Consumers: tests/test_golden.py (the oracle
+on CPU; the CUDA path through the C-ABI on the GPU box, where /root/reference does not exist).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIELDS = ("rho", "ux", "uy", "uz")
+
+
+def noise(shape, ustar, seed):
+    rng = np.random.default_rng(seed)
+    return [1e-3 * ustar * (2.0 * rng.random(shape) - 1.0) for _ in range(3)]
+
+
+def start(nx, ny, nz, npy, npz, laminar, seed=None, a9=0.0, **ov):
+    w = ref.RefWorld(nx, ny, nz, nprocY=npy, nprocZ=npz, laminar=laminar, a9=a9, **ov)
+    w.run("initvel")                                   # main.f90:58
+    if seed is not None:
+        for k, d in zip(("ux", "uy", "uz"), noise((nz, ny, nx), w.scalar("ustar"), seed)):
+            w.set(k, w.get(k) + d)
+    w.run("forcing")                                   # main.f90:61
+    w.run("initpop")                                   # main.f90:65
+    return w
+
+
+def scalars(w):
+    keys = ("visc", "ustar", "ystar", "force_in_y", "force_mag", "s1", "s2", "s4", "s9", "s10", "s13", "s16",
+            "omegepsl", "omegepslj", "omegxx")
+    d = {k: float(w.scalar(k)) for k in keys}
+    d["mrttype"] = int(w.scalar("mrttype"))
+    return d
+
+
+def save(name, meta, **arrays):
+    meta = dict(meta)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), **arrays)
+    print("wrote %s.npz: %s" % (name, {k: v.shape for k, v in arrays.items()}))
+
+
+def main_loop_case(name, nx, ny, nz, npy, npz, laminar, steps, seed, a9=0.0, **ov):
+    w = start(nx, ny, nz, npy, npz, laminar, seed, a9, **ov)
+    f0 = w.get_f().copy()
+    w.run("macrovar")                                  # main.f90:136
+    for _ in range(steps):
+        w.run("collision_mrt")                         # main.f90:157
+        w.run("macrovar")                              # main.f90:161
+    meta = dict(kind="main_loop", nx=nx, ny=ny, nz=nz, ranks=[npy, npz], laminar=laminar, steps=steps,
+                overrides=ov, scalars=scalars(w))
+    save(name, meta, f0=f0, f=w.get_f(), **{k: w.get(k) for k in FIELDS})
+    w.close()
+
+
+def prerelax_case(name, nx, ny, nz, npy, npz, iters, seed, **ov):
+    w = start(nx, ny, nz, npy, npz, False, seed, **ov)
+    f0 = w.get_f().copy()
+    u0 = {k + "0": w.get(k).copy() for k in FIELDS}
+    errs = []
+    for _ in range(iters):                             # main.f90:70-90
+        rhop = w.get("rho").copy()
+        w.run("rhoupdat")
+        w.run("collision_mrt")
+        errs.append(float(np.max(np.abs(w.get("rho") - rhop))))
+    meta = dict(kind="prerelax", nx=nx, ny=ny, nz=nz, ranks=[npy, npz], laminar=False, steps=iters, overrides=ov,
+                scalars=scalars(w))
+    save(name, meta, f0=f0, f=w.get_f(), rho=w.get("rho"), rhoerr=np.array(errs), **u0)
+    w.close()
+
+
+def force_field_case(name, nx, ny, nz, npy, npz, steps, seed, **ov):
+    w = start(nx, ny, nz, npy, npz, False, seed, **ov)
+    f0 = w.get_f().copy()
+    w.set_scalar("istep", 123)
+    w.run("forcingp")                                  # collision.f90:529-602
+    force = {k: w.get("force_real" + k[-1]).copy() for k in ("fx", "fy", "fz")}
+    w.run("macrovar")
+    for _ in range(steps):
+        w.run("collision_mrt")
+        w.run("macrovar")
+    meta = dict(kind="force_field", nx=nx, ny=ny, nz=nz, ranks=[npy, npz], laminar=False, steps=steps, overrides=ov,
+                scalars=scalars(w))
+    save(name, meta, f0=f0, f=w.get_f(), **force, **{k: w.get(k) for k in FIELDS})
+    w.close()
+
+
+if __name__ == "__main__":
+    if not ref.available():
+        raise SystemExit("oracle/_ref/libref.so missing: run `make -C oracle ref` where /root/reference is mounted")
+    # The turbulent set's u* = 2 Re_tau nu / nx (para.f90:64) is meant for nx ~ 200-500; on these
+    # tiny channels it is replaced by configs[1]'s wall units (u* = 0.0025) so the flow is stable.
+    U = dict(ustar=0.0025)
+    main_loop_case("ref_turb_mrt1_7x8x8_r2x2_s20", 7, 8, 8, 2, 2, False, 20, seed=54321, a9=0.3, **U)
+    main_loop_case("ref_lam_lbgk_7x8x8_r1x2_s60", 7, 8, 8, 1, 2, True, 60, seed=None)
+    main_loop_case("ref_turb_mrt3_9x10x7_r3x2_s10", 9, 10, 7, 3, 2, False, 10, seed=777, mrttype=3, **U)
+    main_loop_case("ref_turb_mrt1_39x4x3_r1x1_s8", 39, 4, 3, 1, 1, False, 8, seed=4242, **U)   # reaches the log-law branch
+    prerelax_case("ref_prerelax_7x8x8_r2x2_i6", 7, 8, 8, 2, 2, 6, seed=99, **U)
+    force_field_case("ref_forcingp_15x8x8_r2x2_s4", 15, 8, 8, 2, 2, 4, seed=5, **U)

@@ -1,0 +1,133 @@
+"""Golden vectors produced by RUNNING THE REFERENCE (tests/golden/make_golden.py: the Fortran
+hot path machine-translated to C, one thread per MPI rank).  The oracle must reproduce them
+bit for bit on CPU; the CUDA path (through the C-ABI) must reproduce them bit for bit in STRICT
+arithmetic and within 1e-12 (1 step) / 1e-9 (1000 steps) -- here < 1e-12 over <= 60 steps -- in
+FAST arithmetic, on the GPU box where /root/reference does not exist."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+FIELDS = ("rho", "ux", "uy", "uz")
+
+
+def load(path):
+    z = np.load(path)
+    return json.loads(str(z["meta"])), z
+
+
+def test_fixtures_exist():
+    assert len(CASES) >= 6
+
+
+def oracle_overrides(meta):
+    ov = dict(meta["overrides"])
+    if "mrttype" in ov:
+        ov["MRTtype"] = ov.pop("mrttype")
+    if "ustar" in ov:                       # para.f90:64-66: force and y* follow u*
+        nx = meta["nx"]
+        ov["force_in_y"] = 2.0 * 1.0 * ov["ustar"] * ov["ustar"] / float(nx)
+        ov["ystar"] = 0.0036 / ov["ustar"]
+    return ov
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+@pytest.mark.parametrize("ranks", ["as_recorded", "single"])
+def test_oracle_reproduces_reference_output(path, ranks):
+    meta, z = load(path)
+    nx, ny, nz = meta["nx"], meta["ny"], meta["nz"]
+    npy, npz = meta["ranks"] if ranks == "as_recorded" else (1, 1)
+    para = orc.make_para(nx, ny, nz, laminar=meta["laminar"], nprocY=npy, nprocZ=npz, **oracle_overrides(meta))
+    for k, v in meta["scalars"].items():
+        if k != "mrttype":
+            assert getattr(para, k) == v, k
+    w = orc.World(para)
+    w.FORCING()
+    w.set_f(z["f0"])
+    if meta["kind"] == "prerelax":
+        for k in FIELDS:
+            w.set(k, z[k + "0"])
+        for it in range(meta["steps"]):
+            rhop = w.get("rho").copy()
+            w.rhoupdat(); w.collision_MRT()
+            assert float(np.max(np.abs(w.get("rho") - rhop))) == z["rhoerr"][it]
+        assert np.array_equal(w.get("rho"), z["rho"])
+    else:
+        if meta["kind"] == "force_field":
+            for k in ("fx", "fy", "fz"):
+                w.set(k, z[k])
+        w.macrovar()
+        for _ in range(meta["steps"]):
+            w.collision_MRT(); w.macrovar()
+        for k in FIELDS:
+            assert np.array_equal(w.get(k), z[k]), k
+    assert np.array_equal(w.get_f(), z["f"])
+    w.close()
+
+
+# ---- the CUDA path against the same vectors -------------------------------------------------------
+def _sim(meta, scheme, math_mode):
+    pkg = entry.load_package()
+    ov = dict(meta["overrides"])
+    kw = {}
+    if "mrttype" in ov:
+        kw["MRTtype"] = ov["mrttype"]
+    if "ustar" in ov:
+        kw.update(ustar=ov["ustar"], force_in_y=2.0 * ov["ustar"] * ov["ustar"] / float(meta["nx"]),
+                  ystar=0.0036 / ov["ustar"])
+    sim = pkg.ChannelFlow(meta["nx"], meta["ny"], meta["nz"], laminar=meta["laminar"], scheme=scheme,
+                          math_mode=math_mode, **kw)
+    for k, v in meta["scalars"].items():
+        if k != "mrttype":
+            assert getattr(sim.v, k) == v, k
+    return pkg, sim
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+@pytest.mark.parametrize("scheme", ["aa", "ab"])
+@pytest.mark.parametrize("math_mode", ["strict", "fast"])
+def test_cuda_path_reproduces_reference_output(path, scheme, math_mode):
+    meta, z = load(path)
+    pkg = entry.load_package()
+    capi = pkg.capi
+    pkg, sim = _sim(meta, capi.SCHEME_AA if scheme == "aa" else capi.SCHEME_AB,
+                    capi.MATH_STRICT if math_mode == "strict" else capi.MATH_FAST)
+    strict = math_mode == "strict"
+    sim.f[...] = z["f0"]
+    sim.host_f_changed()
+    sim.FORCING()
+    scale = max(float(np.max(np.abs(z["f"]))), 1e-300)
+
+    def check(a, b, what):
+        if strict:
+            assert np.array_equal(a, b), what
+        else:
+            assert np.max(np.abs(a - b)) < 1e-12 * scale, what
+
+    if meta["kind"] == "prerelax":
+        for k in FIELDS:
+            getattr(sim, k)[...] = z[k + "0"]
+        for it in range(meta["steps"]):                  # the driver's loop, main.f90:70-90
+            rhop = sim.rho.copy()
+            sim.rhoupdat(); sim.collision_MRT()
+            err = float(np.max(np.abs(sim.rho - rhop)))
+            if strict:
+                assert err == z["rhoerr"][it]
+        check(sim.rho, z["rho"], "rho")
+    else:
+        if meta["kind"] == "force_field":
+            sim.set_force_field(np.ascontiguousarray(z["fx"]), np.ascontiguousarray(z["fy"]), np.ascontiguousarray(z["fz"]))
+        sim.v.nflowout = 7                               # exercise the download policy too
+        sim.run(meta["steps"])                           # collision_MRT; macrovar per step, main.f90:157-161
+        for k in FIELDS:                                 # last-step macrovar was downloaded
+            check(getattr(sim, k), z[k], k)
+    check(sim.sync_f_to_host(), z["f"], "f")
+    sim.close()
