@@ -783,7 +783,7 @@ class Translator:
                 self.emit("ref_arr %s = ref_view(%s_arg, %s, %d, (int[]){%s}, (int[]){%s});"
                           % (s.name, s.name, kind, s.rank, los, his))
             else:
-                self.emit("ref_arr %s = ref_alloc(%s, %d, (int[]){%s}, (int[]){%s});" % (s.name, kind, s.rank, los, his))
+                self.emit("ref_arr %s = ref_alloc_auto(%s, %d, (int[]){%s}, (int[]){%s});" % (s.name, kind, s.rank, los, his))
                 frees.append("ref_free(&%s);" % s.name)
         return frees
 

@@ -75,6 +75,21 @@ static inline ref_arr ref_alloc(int kind, int rank, const int *lo, const int *hi
     return a;
 }
 
+/* automatic (stack) arrays of a subroutine: Fortran leaves them uninitialised; the parity build
+ * zeroes them for determinism, the timing build (-DREF_AUTO_MALLOC) does not pay for that */
+static inline ref_arr ref_alloc_auto(int kind, int rank, const int *lo, const int *hi)
+{
+#ifdef REF_AUTO_MALLOC
+    ref_arr a = ref_view(0, kind, rank, lo, hi);
+    size_t c = ref_count(&a);
+    a.p = malloc((c ? c : 1) * (size_t)kind);
+    a.owned = 1;
+    return a;
+#else
+    return ref_alloc(kind, rank, lo, hi);
+#endif
+}
+
 static inline void ref_free(ref_arr *a)
 {
     if (a->owned && a->p) free(a->p);
