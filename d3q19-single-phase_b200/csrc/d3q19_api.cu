@@ -146,9 +146,11 @@ static int exchange_faces(d3q19_handle *h, double *arr, int up_src, const FaceSl
     const size_t cnt = (size_t)5 * g.plane;
     const int up = (h->cfg.rank + 1) % h->cfg.nranks;                       // mzp, para.f90:266
     const int dn = (h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks;       // mzm, para.f90:267
-    const dim3 gp((unsigned)((g.xp + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 5u);
-    k_face_pack<<<gp, BLOCK_X, 0, s>>>(g, arr, h->send_up, up_src, up_slots);
-    k_face_pack<<<gp, BLOCK_X, 0, s>>>(g, arr, h->send_dn, dn_src, dn_slots);
+    const dim3 gp((unsigned)((g.xp + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 10u);
+    FacePair pk;
+    pk.buf[0] = h->send_up; pk.zg[0] = up_src; pk.slots[0] = up_slots;
+    pk.buf[1] = h->send_dn; pk.zg[1] = dn_src; pk.slots[1] = dn_slots;
+    k_face_pack<<<gp, BLOCK_X, 0, s>>>(g, arr, pk);
     CK(cudaGetLastError());
     NcclApi &n = nccl_api();
     NK(n.GroupStart());
@@ -157,11 +159,13 @@ static int exchange_faces(d3q19_handle *h, double *arr, int up_src, const FaceSl
     NK(n.Recv(h->recv_lo, cnt, NCCL_FLOAT64, dn, h->comm, s));
     NK(n.Recv(h->recv_hi, cnt, NCCL_FLOAT64, up, h->comm, s));
     NK(n.GroupEnd());
-    const dim3 gu((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 5u);
-    k_face_unpack<<<gu, BLOCK_X, 0, s>>>(g, arr, h->recv_lo, lo_dst, up_slots, exclude_walls);
-    k_face_unpack<<<gu, BLOCK_X, 0, s>>>(g, arr, h->recv_hi, hi_dst, dn_slots, exclude_walls);
+    const dim3 gu((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 10u);
+    FacePair un;
+    un.buf[0] = h->recv_lo; un.zg[0] = lo_dst; un.slots[0] = up_slots;
+    un.buf[1] = h->recv_hi; un.zg[1] = hi_dst; un.slots[1] = dn_slots;
+    k_face_unpack<<<gu, BLOCK_X, 0, s>>>(g, arr, un, exclude_walls);
     CK(cudaGetLastError());
-    h->n_other_kernels += 4;
+    h->n_other_kernels += 2;
     h->n_nccl += 4;
     return 0;
 }
@@ -459,10 +463,11 @@ extern "C" int d3q19_set_force_field(d3q19_handle *h, const double *fx, const do
 
 // ---- the step ----------------------------------------------------------------------------------------
 template <int SK, bool STRICT, bool GENERIC>
-static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int nplanes, cudaStream_t s) {
+static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int nplanes, cudaStream_t s, int zstride = 1) {
     if (nplanes <= 0) return 0;
     StepParams p = p0;
     p.z0 = z0;
+    p.zstride = zstride;
     if (h->idx32) k_step<SK, STRICT, GENERIC, uint32_t><<<grid_nodes(h, nplanes), BLOCK_X, 0, s>>>(p);
     else k_step<SK, STRICT, GENERIC, unsigned long long><<<grid_nodes(h, nplanes), BLOCK_X, 0, s>>>(p);
     CK(cudaGetLastError());
@@ -477,8 +482,7 @@ static int step_impl(d3q19_handle *h, const StepParams &p, double *written) {
     // boundary planes first, so that their faces travel while the interior is computed
     RK_(wait_exchange(h));
     if (h->cfg.overlap && lz > 2) {
-        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 1, h->sc)));
-        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, lz, 1, h->sc)));
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 2, h->sc, lz - 1)));   // planes 1 and lz in one launch
         CK(cudaEventRecord(h->evB, h->sc));
         RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 2, lz - 2, h->sc)));
     } else {

@@ -82,6 +82,7 @@ struct StepParams {
     double *A;            // source (and destination for AA)
     double *B;            // destination for AB
     int z0;               // first ghosted plane index handled by this launch
+    int zstride;          // plane = z0 + blockIdx.z * zstride (boundary launch: planes 1 and lz in one grid)
     Mrt mrt;
     double Fx, Fy, Fz;    // uniform force (FORCING, collision.f90:522-524)
     double rho_shift;     // pending avedensity shift (collision.f90:505-511)
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(BLOCK_X, SK == STEP_AA_ODD ? D3Q_MIN_BLOCKS_OD
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     double rhoerr = 0.0;
     if (x < g.lx) {
-        const NodeIdx<IDX> k = make_node<IDX>(g, x, blockIdx.y, p.z0 + blockIdx.z);
+        const NodeIdx<IDX> k = make_node<IDX>(g, x, blockIdx.y, p.z0 + (int)blockIdx.z * p.zstride);
         constexpr int RK = (SK == STEP_AB) ? READ_PULL_NAT : (SK == STEP_AA_EVEN ? READ_DIRECT : READ_PULL_SWAP);
         double f[NPOP];
         gather19<RK>(p.A, g, k, f);
@@ -431,28 +432,33 @@ __global__ void __launch_bounds__(BLOCK_X) k_field_unpack_i32(int lx, int xp, in
 // ---- z-face pack / unpack (collisionExchnge, collision.f90:337-370) ------------------------------
 // buf[s][y][x] (pitch xp) <- A[slots[s]][plane][y][x]
 struct FaceSlots { int s[5]; };
-__global__ void __launch_bounds__(BLOCK_X) k_face_pack(Geom g, const double *A, double *buf, int zg, FaceSlots fs) {
+// both faces in one launch: blockIdx.z in [0,10), face = z / 5 (0: "up" data, 1: "dn" data)
+struct FacePair {
+    double *buf[2];
+    int zg[2];
+    FaceSlots slots[2];
+};
+__global__ void __launch_bounds__(BLOCK_X) k_face_pack(Geom g, const double *A, FacePair fp) {
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     if (x >= g.xp) return;
-    const int y = blockIdx.y, s = blockIdx.z;
-    buf[(long long)s * g.plane + (long long)y * g.xp + x] =
-        A[(long long)fs.s[s] * g.slab + (long long)zg * g.plane + (long long)y * g.xp + x];
+    const int y = blockIdx.y, face = blockIdx.z / 5, s = blockIdx.z % 5;
+    fp.buf[face][(long long)s * g.plane + (long long)y * g.xp + x] =
+        A[(long long)fp.slots[face].s[s] * g.slab + (long long)fp.zg[face] * g.plane + (long long)y * g.xp + x];
 }
 // exclude_walls: populations with c_x = +1 skip x = 0, c_x = -1 skip x = lx-1 -- the slices
 // 2:lx / 1:lx-1 of collision.f90:361-362,367-368 that keep the locally bounced value.
-__global__ void __launch_bounds__(BLOCK_X) k_face_unpack(Geom g, double *A, const double *buf, int zg, FaceSlots fs,
-                                                         int exclude_walls) {
+__global__ void __launch_bounds__(BLOCK_X) k_face_unpack(Geom g, double *A, FacePair fp, int exclude_walls) {
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     if (x >= g.lx) return;
-    const int y = blockIdx.y, s = blockIdx.z;
-    const int slot = fs.s[s];
+    const int y = blockIdx.y, face = blockIdx.z / 5, s = blockIdx.z % 5;
+    const int slot = fp.slots[face].s[s];
     if (exclude_walls) {
         const int cx = (slot == 11 || slot == 13 || slot == 7 || slot == 9 || slot == 1) ? 1
                      : ((slot == 12 || slot == 14 || slot == 8 || slot == 10 || slot == 2) ? -1 : 0);
         if ((cx > 0 && x == 0) || (cx < 0 && x == g.lx - 1)) return;
     }
-    A[(long long)slot * g.slab + (long long)zg * g.plane + (long long)y * g.xp + x] =
-        buf[(long long)s * g.plane + (long long)y * g.xp + x];
+    A[(long long)slot * g.slab + (long long)fp.zg[face] * g.plane + (long long)y * g.xp + x] =
+        fp.buf[face][(long long)s * g.plane + (long long)y * g.xp + x];
 }
 
 // ---- reductions ------------------------------------------------------------------------------------
