@@ -21,7 +21,7 @@ NPOP = 19
 SYMBOLS = [
     "d3q19_create", "d3q19_destroy", "d3q19_sync", "d3q19_last_error", "d3q19_nccl_unique_id", "d3q19_device_count",
     "d3q19_upload_f", "d3q19_download_f", "d3q19_set_macro", "d3q19_download_macro",
-    "d3q19_set_force_uniform", "d3q19_set_force_field",
+    "d3q19_init_channel", "d3q19_set_force_uniform", "d3q19_set_force_field",
     "d3q19_collide_stream", "d3q19_run", "d3q19_macrovar", "d3q19_rhoupdat", "d3q19_avedensity", "d3q19_probe",
     "d3q19_prerelax", "d3q19_set_solid_mask", "d3q19_set_particles", "d3q19_profiles",
     "d3q19_timer_start", "d3q19_timer_stop", "d3q19_get_counters",
@@ -93,6 +93,7 @@ def load():
     L.d3q19_download_f.argtypes = [vp, dp]
     L.d3q19_set_macro.argtypes = [vp, dp, dp, dp, dp]
     L.d3q19_download_macro.argtypes = [vp, dp, dp, dp, dp]
+    L.d3q19_init_channel.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int32]
     L.d3q19_set_force_uniform.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     L.d3q19_set_force_field.argtypes = [vp, dp, dp, dp]
     L.d3q19_collide_stream.argtypes = [vp, C.c_int32]

@@ -213,6 +213,31 @@ class ChannelFlow:
             self.ux[:, :, :nxh] += dv
             np.add.at(self.ux, (slice(None), slice(None), mirror), dv)
 
+    # ---- initvel + initpop evaluated on the device (fields too large for the host) -----------
+    def init_channel_device(self, A9=0.0, noise_amp=0.0, seed=54321):
+        v = self.v
+        capi.check(self.L.d3q19_init_channel(self.h, v.ustar, v.ystar, A9, noise_amp, seed, int(bool(v.ivel))))
+
+    @staticmethod
+    def splitmix_unit(seed, comp, node):
+        """numpy mirror of the device noise generator (csrc/kernels.cuh splitmix_unit)."""
+        with np.errstate(over="ignore"):
+            z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (np.uint64(3) * node.astype(np.uint64) + np.uint64(comp + 1))
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+        return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0) * 2.0 - 1.0
+
+    def add_hash_noise(self, noise_amp, seed=54321):
+        """Host twin of the noise init_channel_device adds (same global-node hash)."""
+        v = self.v
+        kz = (np.arange(self.lz) + self.globalz)[:, None, None]
+        jy = np.arange(self.ly)[None, :, None]
+        ix = np.arange(self.lx)[None, None, :]
+        node = (ix + v.nx * (jy + v.ny * kz)).astype(np.uint64)
+        for comp, a in enumerate((self.ux, self.uy, self.uz)):
+            a += noise_amp * self.splitmix_unit(seed, comp, node)
+
     # ---- initial.f90:19-46 (host, once) ----------------------------------------------------
     def initpop(self):
         v = self.v

@@ -551,6 +551,38 @@ extern "C" int d3q19_run(d3q19_handle *h, int32_t nsteps) {
     return 0;
 }
 
+// ---- device-side initvel + initpop (initial.f90:75-147, :19-46) ------------------------------------------
+extern "C" int d3q19_init_channel(d3q19_handle *h, double ustar, double ystar, double A9, double noise_amp,
+                                  uint64_t seed, int32_t ivel) {
+    CK(cudaSetDevice(h->cfg.device));
+    RK_(wait_exchange(h));
+    InitParams p;
+    memset(&p, 0, sizeof p);
+    p.g = h->g; p.A = h->A;
+    p.nx = h->cfg.nx; p.ny = h->cfg.ny; p.nz = h->cfg.nz; p.globalz = h->cfg.globalz;
+    p.ustar = ustar; p.ystar = ystar; p.A9 = A9; p.noise_amp = noise_amp;
+    p.pi2 = 2.0 * (4.0 * atan(1.0));
+    p.seed = seed; p.ivel = ivel;
+    p.unstream = h->cfg.scheme == D3Q19_SCHEME_AB;
+    k_init_channel<<<grid_nodes(h, h->g.lz), BLOCK_X, 0, h->sc>>>(p);
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    h->phase = 0;
+    if (h->cfg.scheme == D3Q19_SCHEME_AB && h->cfg.nranks > 1) {
+        // ghost planes of the post-collision storage, as after a step
+        CK(cudaEventRecord(h->evB, h->sc));
+        CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
+        RK_(exchange_after_step(h, STEP_AB, h->A, h->sx));
+        CK(cudaEventRecord(h->evX, h->sx));
+        h->exchange_pending = true;
+    }
+    h->shim.f_dev_valid = true;
+    h->shim.f_host_valid = false;
+    h->shim.macro_dev_valid = false;
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
 // ---- macrovar / rhoupdat ---------------------------------------------------------------------------------
 static int macro_launch(d3q19_handle *h, int rho_only, unsigned long long *rhoerr_bits = nullptr) {
     RK_(ensure_macro_arrays(h));

@@ -283,6 +283,103 @@ __global__ void __launch_bounds__(BLOCK_X, SK == STEP_AA_ODD ? D3Q_MIN_BLOCKS_OD
     if (GENERIC && p.macro_mode == 1 && p.rhoerr_bits) block_max_to(p.rhoerr_bits, rhoerr);
 }
 
+// ---- initvel + initpop on the device (initial.f90:75-147, :19-46) -----------------------------------
+// For fields too large to stage through the host (configs[3]: 150 GB of populations per GPU).  The
+// velocity is a pure function of the GLOBAL node coordinates: log-law mean (initial.f90:104-115),
+// the sinusoidal perturbation block (:119-144, amplitude A9; the reference ships A9 = 0) and a
+// counter-based uniform noise (splitmix64 of (seed, component, global node); SURVEY.md 8(d)
+// "synthetic inputs"), so every storage scheme can be filled without a halo exchange.
+struct InitParams {
+    Geom g;
+    double *A;
+    int nx, ny, nz, globalz;
+    double ustar, ystar, A9, noise_amp, pi2;
+    unsigned long long seed;
+    int ivel;
+    int unstream;         // 1: AB storage (post-collision, "un-streamed" canonical), 0: canonical
+};
+
+__host__ __device__ inline double splitmix_unit(unsigned long long seed, unsigned long long comp, unsigned long long node) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (3ull * node + comp + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;      // [-1, 1)
+}
+
+__device__ __forceinline__ void init_velocity(const InitParams &p, int ix, int iy, int izg, double &ux, double &uy, double &uz) {
+    // ix in [1,nx], iy in [1,ny] (periodic), izg in [1,nz] global (periodic)
+    ux = 0.0; uy = 0.0; uz = 0.0;
+    if (p.ivel) {
+        const int nxh = (p.nx + 1) / 2;
+        const int i = ix <= nxh ? ix : p.nx + 1 - ix;          // mirrored about the centre plane (:107,:112)
+        const double yplus = ((double)i - 0.5) / p.ystar;
+        if (yplus < 10.8) uy = yplus * p.ustar;
+        else uy = (log(yplus) / 0.41 + 5.0) * p.ustar;
+        if (p.A9 != 0.0) {
+            const double cc = 60.0;
+            const double ccc1 = -(double)p.ny / p.pi2 / 1.0 / p.ystar * p.A9 * p.ustar / cc / cc;
+            const double z9 = p.pi2 * ((double)izg - 0.5) / (double)p.nz;
+            const double y9 = p.pi2 * ((double)iy - 0.5) / (double)p.ny;
+            const double ccc9 = exp(-yplus / cc);
+            uy += ccc1 * yplus * ccc9 * sin(y9 + z9);
+            ux += p.A9 * p.ustar * (1. - ccc9 - yplus / cc * ccc9) * cos(y9 + z9);
+        }
+    }
+    if (p.noise_amp != 0.0) {
+        const unsigned long long node = (unsigned long long)(ix - 1) +
+            (unsigned long long)p.nx * ((unsigned long long)(iy - 1) + (unsigned long long)p.ny * (unsigned long long)(izg - 1));
+        ux += p.noise_amp * splitmix_unit(p.seed, 0, node);
+        uy += p.noise_amp * splitmix_unit(p.seed, 1, node);
+        uz += p.noise_amp * splitmix_unit(p.seed, 2, node);
+    }
+}
+
+template <int I>
+__device__ __forceinline__ double init_feq(double ux, double uy, double uz) {
+    // initial.f90:26-44 with rho = 0
+    const double usqr = 1.5 * (ux * ux + uy * uy + uz * uz);
+    if (I == 0) return (1.0 / 3.0) * (0.0 - usqr);
+    const double G = dir_cx(I) * ux + dir_cy(I) * uy + dir_cz(I) * uz;
+    const double ww = I <= 6 ? 1.0 / 18.0 : 1.0 / 36.0;
+    return ww * (0.0 + 3.0 * G + 4.5 * G * G - usqr);
+}
+
+__global__ void __launch_bounds__(BLOCK_X) k_init_channel(const __grid_constant__ InitParams p) {
+    const Geom &g = p.g;
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.lx) return;
+    const int y = blockIdx.y, zg = 1 + blockIdx.z;
+    const long long n = x + (long long)g.xp * (y + (long long)g.ly * zg);
+    const int ix = x + 1, iy = y + 1, iz = p.globalz + zg;          // global 1-based
+    double ux, uy, uz;
+    init_velocity(p, ix, iy, iz, ux, uy, uz);
+    static_for<NPOP>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        double v;
+        if (!p.unstream) {
+            v = init_feq<i>(ux, uy, uz);
+        } else {
+            // AB storage holds g_i(x) = f_i(x + c_i); at a wall g_i(x) = f_opp(i)(x)
+            constexpr int cx = dir_cx(i), cy = dir_cy(i), cz = dir_cz(i);
+            const int jx = ix + cx;
+            if (jx < 1 || jx > p.nx) {
+                v = init_feq<dir_opp(i)>(ux, uy, uz);
+            } else if (i == 0) {
+                v = init_feq<0>(ux, uy, uz);
+            } else {
+                int jy = iy + cy, jz = iz + cz;
+                jy = jy < 1 ? p.ny : (jy > p.ny ? 1 : jy);
+                jz = jz < 1 ? p.nz : (jz > p.nz ? 1 : jz);
+                double a, b, c;
+                init_velocity(p, jx, jy, jz, a, b, c);
+                v = init_feq<i>(a, b, c);
+            }
+        }
+        p.A[(long long)i * g.slab + n] = v;
+    });
+}
+
 // ---- macrovar (collision.f90:378-463) / rhoupdat (:469-480) -----------------------------------
 struct MacroParams {
     Geom g;

@@ -106,6 +106,14 @@ int d3q19_download_f(d3q19_handle *h, double *f_aos);
 int d3q19_set_macro(d3q19_handle *h, const double *rho, const double *ux, const double *uy, const double *uz);
 int d3q19_download_macro(d3q19_handle *h, double *rho, double *ux, double *uy, double *uz);
 
+/* initvel + initpop evaluated on the device (initial.f90:75-147 with ivel, :19-46): log-law mean
+ * profile, the A9 perturbation block, plus a counter-based uniform noise of amplitude noise_amp
+ * (splitmix64 of seed/component/global node -- SURVEY.md 8(d) synthetic inputs).  For fields too
+ * large to stage through the host (configs[3], 150 GB per GPU).  No halo exchange is needed:
+ * the velocity is a pure function of the global node coordinates.                          */
+int d3q19_init_channel(d3q19_handle *h, double ustar, double ystar, double A9, double noise_amp,
+                       uint64_t seed, int32_t ivel);
+
 /* ---- forcing (FORCING / FORCINGP) ------------------------------------------------------ */
 int d3q19_set_force_uniform(d3q19_handle *h, double fx, double fy, double fz);
 int d3q19_set_force_field(d3q19_handle *h, const double *fx, const double *fy, const double *fz);

@@ -267,3 +267,28 @@ def test_counters_prove_kernels_ran(oracle):
     c = sim.counters()
     assert c["step_kernels"] == 10 and c["steps"] == 10
     sim.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_device_init_channel_matches_host_initvel_initpop(oracle, scheme):
+    # initvel + initpop on the device (for configs[3]-sized fields) against the host twins, which
+    # tests/test_capi_symbols.py checks against the oracle (initial.f90:75-147, :19-46)
+    nx, ny, nz = 40, 6, 5
+    ov = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+    host = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, **ov)
+    host.initvel(A9=0.3)
+    host.add_hash_noise(1e-3 * host.v.ustar, seed=777)
+    host.FORCING(); host.initpop()
+    dev = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, **ov)
+    dev.FORCING()
+    dev.init_channel_device(A9=0.3, noise_amp=1e-3 * dev.v.ustar, seed=777)
+    f = dev.download_f(np.empty((nz, ny, nx, 19)))
+    assert relerr(f, host.f) < 1e-13            # log/exp/sin/cos differ from libm in the last place
+    # and it steps like the uploaded field does
+    host.upload_f()
+    for s in (host, dev):
+        s.run_device(3)
+    a = host.download_f(np.empty((nz, ny, nx, 19)))
+    b = dev.download_f(np.empty((nz, ny, nx, 19)))
+    assert relerr(b, a) < 1e-12
+    host.close(); dev.close()
