@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="z-face exchange: stores into the neighbour GPU's memory over NVLink (default) or NCCL send/recv")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--device-init", action="store_true",
                     help="initvel+initpop on the device (implied by c4: the field does not fit a host staging copy)")
@@ -235,6 +237,17 @@ def main():
     math_mode = capi.MATH_FAST if args.math == "fast" else capi.MATH_STRICT
     sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local_rank, scheme=scheme,
                           math_mode=math_mode, nccl_id=nccl_id, overlap=not args.no_overlap, allocate_host=False)
+    halo = "none"
+    if world > 1:
+        halo = "nccl"
+        if args.halo == "peer":
+            def allgather_bytes(b):
+                t = torch.tensor(list(b), dtype=torch.uint8)
+                out = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(out, t)
+                return [bytes(o.tolist()) for o in out]
+            sim.connect_halo(allgather_bytes)
+            halo = "peer"
     nodes_global = nx * ny * nz
     args.scheme = "ab" if sim.counters()["scheme"] == capi.SCHEME_AB else "aa"     # what AUTO resolved to
     device_init = args.device_init or args.workload == "c4"
@@ -332,7 +345,8 @@ def main():
             "config": {"workload": "D3Q19 MRT channel %dx%dx%d (nx x ny x nz, x wall-normal), turbulent set Re_tau=180, "
                                    "uniform body force, half-way bounce-back walls" % (nx, ny, nz),
                        "per_gpu": "%dx%dx%d z-slab" % (nx, ny, sim.lz), "scheme": args.scheme, "math": args.math,
-                       "parallelism": "z-slab x%d, NCCL send/recv faces" % world if world > 1 else "1 GPU",
+                       "parallelism": ("z-slab x%d, faces %s" % (world, "stored into the neighbour GPU's memory over NVLink "
+                                       "inside the step kernel" if halo == "peer" else "by NCCL send/recv")) if world > 1 else "1 GPU",
                        "l2": "populations %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (c1["population_bytes"] / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "impl": "ours",

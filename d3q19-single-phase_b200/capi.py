@@ -16,14 +16,17 @@ SCHEME_AA, SCHEME_AB, SCHEME_AUTO = 0, 1, 2
 MATH_FAST, MATH_STRICT = 0, 1
 MACRO_MAIN, MACRO_PRERELAX, MACRO_EXTERNAL = 0, 1, 2
 NPOP = 19
+IPC_BYTES = 256
 
 # every symbol include/d3q19_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "d3q19_create", "d3q19_destroy", "d3q19_sync", "d3q19_last_error", "d3q19_nccl_unique_id", "d3q19_device_count",
-    "d3q19_upload_f", "d3q19_download_f", "d3q19_set_macro", "d3q19_download_macro",
+    "d3q19_ipc_export", "d3q19_ipc_connect", "d3q19_upload_f", "d3q19_download_f", "d3q19_set_macro", "d3q19_download_macro",
     "d3q19_init_channel", "d3q19_set_force_uniform", "d3q19_set_force_field",
     "d3q19_collide_stream", "d3q19_run", "d3q19_macrovar", "d3q19_rhoupdat", "d3q19_avedensity", "d3q19_probe",
     "d3q19_prerelax", "d3q19_set_solid_mask", "d3q19_set_particles", "d3q19_profiles",
+    "d3q19_particles_init", "d3q19_beads_links", "d3q19_beads_collision", "d3q19_beads_lubforce", "d3q19_beads_move",
+    "d3q19_beads_filling", "d3q19_particle_step", "d3q19_get_particles", "d3q19_get_links", "d3q19_get_mask",
     "d3q19_timer_start", "d3q19_timer_stop", "d3q19_get_counters",
     "d3q19_shim_bind", "d3q19_shim_set_schedule", "d3q19_shim_forcing", "d3q19_shim_rhoupdat", "d3q19_shim_collision_mrt",
     "d3q19_shim_prerelax_state",
@@ -65,6 +68,13 @@ class ShimArrays(C.Structure):
     ]
 
 
+class ParticleParams(C.Structure):
+    """Mirror of d3q19_particle_params."""
+    _fields_ = [("rad", C.c_double), ("rho0", C.c_double), ("mingap", C.c_double), ("mingap_w", C.c_double),
+                ("stf0", C.c_double), ("stf1", C.c_double), ("stf0_w", C.c_double), ("stf1_w", C.c_double),
+                ("fscale", C.c_double), ("gforce", C.c_double * 3), ("maxlink", C.c_int64)]
+
+
 class D3Q19Error(RuntimeError):
     pass
 
@@ -89,6 +99,8 @@ def load():
     L.d3q19_sync.argtypes = [vp]
     L.d3q19_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
     L.d3q19_device_count.argtypes = [C.POINTER(C.c_int32)]
+    L.d3q19_ipc_export.argtypes = [vp, C.POINTER(C.c_ubyte)]
+    L.d3q19_ipc_connect.argtypes = [vp, C.POINTER(C.c_ubyte)]
     L.d3q19_upload_f.argtypes = [vp, dp]
     L.d3q19_download_f.argtypes = [vp, dp]
     L.d3q19_set_macro.argtypes = [vp, dp, dp, dp, dp]
@@ -106,6 +118,17 @@ def load():
     L.d3q19_set_solid_mask.argtypes = [vp, ip, ip]
     L.d3q19_set_particles.argtypes = [vp, C.c_int32, dp, dp, dp]
     L.d3q19_profiles.argtypes = [vp, dp]
+    i64p = C.POINTER(C.c_int64)
+    L.d3q19_particles_init.argtypes = [vp, C.c_int32, C.POINTER(ParticleParams)]
+    L.d3q19_beads_links.argtypes = [vp, i64p]
+    L.d3q19_beads_collision.argtypes = [vp]
+    L.d3q19_beads_lubforce.argtypes = [vp]
+    L.d3q19_beads_move.argtypes = [vp]
+    L.d3q19_beads_filling.argtypes = [vp, i64p]
+    L.d3q19_particle_step.argtypes = [vp, C.c_int32]
+    L.d3q19_get_particles.argtypes = [vp, dp, dp, dp, dp, dp]
+    L.d3q19_get_links.argtypes = [vp, C.c_int64, ip, ip, ip, ip, ip, dp, i64p]
+    L.d3q19_get_mask.argtypes = [vp, ip]
     L.d3q19_timer_start.argtypes = [vp]
     L.d3q19_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.d3q19_get_counters.argtypes = [vp, C.POINTER(C.c_int64)]

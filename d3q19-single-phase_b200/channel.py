@@ -328,6 +328,78 @@ class ChannelFlow:
                 on_step(self)
         return self.istep
 
+    # ---- particles (the reference's beads_* phases; device-side bookkeeping) -----------------------
+    def particles_init(self, ypglb, rad, wp=None, omgp=None, rho0=1.0, mingap=3.0, mingap_w=3.0, stf0=0.025, stf1=0.002,
+                       stf0_w=0.025, stf1_w=0.002, fscale=0.0, gforce=(0.0, 0.0, 0.0), maxlink=0):
+        ypglb = np.ascontiguousarray(ypglb, dtype=np.float64).reshape(-1, 3)
+        self.npart = ypglb.shape[0]
+        prm = capi.ParticleParams(rad, rho0, mingap, mingap_w, stf0, stf1, stf0_w, stf1_w, fscale,
+                                  (C.c_double * 3)(*gforce), maxlink)
+        capi.check(self.L.d3q19_particles_init(self.h, self.npart, C.byref(prm)))
+        self.set_particles(ypglb, wp, omgp)
+
+    def set_particles(self, ypglb, wp=None, omgp=None):
+        z = np.zeros((self.npart, 3))
+        a = [np.ascontiguousarray(z if t is None else t, dtype=np.float64).reshape(-1, 3) for t in (ypglb, wp, omgp)]
+        capi.check(self.L.d3q19_set_particles(self.h, self.npart, capi.dptr(a[0]), capi.dptr(a[1]), capi.dptr(a[2])))
+
+    def beads_links(self):
+        n = C.c_int64(0)
+        capi.check(self.L.d3q19_beads_links(self.h, C.byref(n)))
+        return n.value
+
+    def beads_collision(self):
+        capi.check(self.L.d3q19_beads_collision(self.h))
+
+    def beads_lubforce(self):
+        capi.check(self.L.d3q19_beads_lubforce(self.h))
+
+    def beads_move(self):
+        capi.check(self.L.d3q19_beads_move(self.h))
+
+    def beads_filling(self):
+        n = C.c_int64(0)
+        capi.check(self.L.d3q19_beads_filling(self.h, C.byref(n)))
+        return n.value
+
+    def particle_step(self, move=True):
+        capi.check(self.L.d3q19_particle_step(self.h, int(bool(move))))
+
+    def get_particles(self):
+        out = {k: np.zeros((self.npart, 3)) for k in ("ypglb", "wp", "omgp", "fHIp", "torqp")}
+        capi.check(self.L.d3q19_get_particles(self.h, *(capi.dptr(out[k]) for k in ("ypglb", "wp", "omgp", "fHIp", "torqp"))))
+        return out
+
+    def get_links(self):
+        n = C.c_int64(0)
+        cap = 1 << 16
+        while True:
+            a = [np.zeros(cap, dtype=np.int32) for _ in range(5)]
+            q = np.zeros(cap)
+            rc = self.L.d3q19_get_links(self.h, cap, *(capi.iptr(t) for t in a), capi.dptr(q), C.byref(n))
+            if rc == 0:
+                break
+            if n.value > cap:
+                cap = int(n.value)
+                continue
+            capi.check(rc)
+        m = n.value
+        return dict(x=a[0][:m], y=a[1][:m], z=a[2][:m], ip=a[3][:m], part=a[4][:m], q=q[:m])
+
+    def get_mask(self):
+        own = np.zeros((self.lz, self.ly, self.lx), dtype=np.int32)
+        capi.check(self.L.d3q19_get_mask(self.h, capi.iptr(own)))
+        return own
+
+    # ---- halo in NVLink peer memory (collective; `allgather(bytes) -> [bytes per rank]`) ----------
+    def connect_halo(self, allgather):
+        blob = (C.c_ubyte * capi.IPC_BYTES)()
+        capi.check(self.L.d3q19_ipc_export(self.h, blob))
+        blobs = allgather(bytes(blob))
+        assert len(blobs) == self.nranks and all(len(b) == capi.IPC_BYTES for b in blobs)
+        buf = (C.c_ubyte * (capi.IPC_BYTES * self.nranks)).from_buffer_copy(b"".join(blobs))
+        capi.check(self.L.d3q19_ipc_connect(self.h, buf))
+
     # ---- raw C-ABI conveniences (tests, bench) ------------------------------------------------
     def upload_f(self, f=None):
         capi.check(self.L.d3q19_upload_f(self.h, capi.dptr(self.f if f is None else f)))

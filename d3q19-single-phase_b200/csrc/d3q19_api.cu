@@ -13,6 +13,7 @@
 
 #include "../../include/d3q19_b200.h"
 #include "kernels.cuh"
+#include "particles.cuh"
 #include "nccl_dl.h"
 
 using namespace d3q;
@@ -91,8 +92,31 @@ struct d3q19_handle {
     double *prof_partial = nullptr, *prof_out = nullptr;
     int prof_chunks = 0, prof_rows = 0;
     long long n_step_kernels = 0, n_other_kernels = 0, n_nccl = 0, n_steps = 0;
+    // particle path (particles.cuh)
+    bool part_on = false, links_valid = false, mask_built = false;
+    d3q19_particle_params pp;
+    int32_t *own = nullptr, *own0 = nullptr;     // ghosted owner masks [lz+2][ly][xp], now / before the last move
+    double *pbuf = nullptr;                      // 10 tables of (3,npart)
+    double *ypglb0 = nullptr, *fHIp = nullptr, *torqp = nullptr, *flubp = nullptr, *forcepp = nullptr, *torqpp = nullptr,
+           *thetap = nullptr;
+    Links links = {nullptr, nullptr, nullptr, nullptr};
+    long long maxlink = 0, nlink = 0;
+    long long *lcount = nullptr, *loffset = nullptr;
+    unsigned long long *nfilled_dev = nullptr;
+    double amp = 0, aip = 0;
+    // halo in peer memory (cudaIpc): [0] = lower neighbour (mzm), [1] = upper neighbour (mzp)
+    bool halo_on = false;
+    unsigned int halo_epoch = 0;
+    unsigned int *halo_flags = nullptr;          // local: [0] wait_lo, [1] wait_hi, [2..3] block counters
+    void *peer_base[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // opened A_alloc, B_alloc, flags
+    double *peer_A[2] = {nullptr, nullptr}, *peer_B[2] = {nullptr, nullptr};
+    unsigned int *peer_flags[2] = {nullptr, nullptr};
+    long long peer_slab[2] = {0, 0};
+    int peer_lz[2] = {0, 0};
     Shim shim;
 };
+
+static const size_t POP_PAD = 32;     // doubles (256 B) in front of and behind the populations
 
 static const FaceSlots SLOTS_PZ = {{5, 11, 12, 15, 16}};   // c_z = +1 (collision.f90:337-341)
 static const FaceSlots SLOTS_MZ = {{6, 13, 14, 17, 18}};   // c_z = -1 (collision.f90:343-347)
@@ -130,6 +154,11 @@ static int ensure_stage(d3q19_handle *h) {
 
 // sc must not read ghost/boundary data before the last exchange finished
 static int wait_exchange(d3q19_handle *h) {
+    if (h->halo_on && h->halo_epoch > 0) {
+        // the neighbours' stores of the last halo step must have landed before anybody reads the planes
+        k_halo_wait<<<1, 1, 0, h->sc>>>(h->halo_flags, h->halo_flags + 1, h->halo_epoch);
+        CK(cudaGetLastError());
+    }
     if (h->exchange_pending) {
         CK(cudaStreamWaitEvent(h->sc, h->evX, 0));
         h->exchange_pending = false;
@@ -206,6 +235,25 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->sc) cudaStreamSynchronize(h->sc);
     if (h->sx) cudaStreamSynchronize(h->sx);
+    if (h->halo_on) {
+        // nobody may still be storing into our planes, and we must let go of theirs before they free them
+        for (int d = 0; d < 2; ++d)
+            for (int a = 0; a < 3; ++a)
+                if (h->peer_base[d][a] && !(d == 1 && h->peer_base[0][a] == h->peer_base[1][a])) cudaIpcCloseMemHandle(h->peer_base[d][a]);
+        if (h->comm && h->scal) {
+            NcclApi &n = nccl_api();
+            n.AllReduce(h->scal + 32, h->scal + 32, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc);
+            cudaStreamSynchronize(h->sc);
+        }
+        h->halo_on = false;
+    }
+    if (h->part_on) {
+        void *pp_[] = {h->own, h->own0, h->pbuf, h->links.node, h->links.dir, h->links.part, h->links.q, h->lcount, h->loffset,
+                       h->nfilled_dev};
+        for (void *q : pp_) if (q) cudaFree(q);
+        h->solid = h->isn = nullptr; h->ypglb = h->wp = h->omgp = nullptr;
+    }
+    if (h->halo_flags) cudaFree(h->halo_flags);
     if (h->comm) nccl_api().CommDestroy(h->comm);
     void *ptrs[] = {h->A_alloc, h->B_alloc, h->rho, h->ux, h->uy, h->uz, h->ffx, h->ffy, h->ffz, h->solid, h->isn, h->ypglb,
                     h->wp, h->omgp, h->send_up, h->send_dn, h->recv_lo, h->recv_hi, h->stage[0], h->stage[1],
@@ -275,7 +323,7 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
     }
     CKH(cudaEventCreate(&h->t0));
     CKH(cudaEventCreate(&h->t1));
-    const size_t PAD = 32;        // doubles (256 B) before and after
+    const size_t PAD = POP_PAD;
     const size_t fbytes = ((size_t)NPOP * g.slab + 2 * PAD) * sizeof(double);
     h->idx32 = (unsigned long long)g.slab + 2 < 0xffffffffull && !getenv("D3Q19_FORCE_IDX64");
     CKH(cudaMalloc(&h->A_alloc, fbytes));
@@ -307,8 +355,88 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
 
 extern "C" int d3q19_sync(d3q19_handle *h) {
     CK(cudaSetDevice(h->cfg.device));
+    if (h->halo_on) RK_(wait_exchange(h));       // the neighbours' stores of the last step have landed
     CK(cudaStreamSynchronize(h->sc));
     CK(cudaStreamSynchronize(h->sx));
+    return 0;
+}
+
+// ---- halo in peer memory: cudaIpc bootstrap ---------------------------------------------------------------
+// blob layout (D3Q19_IPC_BYTES = 256): [0,64) handle of the first population array, [64,128) of the
+// second (AB) or zeros, [128,192) of the flag words, then int32 lz, int32 scheme, int64 slab.
+extern "C" int d3q19_ipc_export(d3q19_handle *h, unsigned char *blob) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->cfg.nranks < 2) return fail("d3q19_ipc_export: needs nranks > 1");
+    if (!h->halo_flags) {
+        CK(cudaMalloc(&h->halo_flags, 64 * sizeof(unsigned int)));
+        CK(cudaMemset(h->halo_flags, 0, 64 * sizeof(unsigned int)));
+    }
+    memset(blob, 0, D3Q19_IPC_BYTES);
+    cudaIpcMemHandle_t mh;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CK(cudaIpcGetMemHandle(&mh, h->A_alloc)); memcpy(blob, &mh, 64);
+    if (h->B_alloc) { CK(cudaIpcGetMemHandle(&mh, h->B_alloc)); memcpy(blob + 64, &mh, 64); }
+    CK(cudaIpcGetMemHandle(&mh, h->halo_flags)); memcpy(blob + 128, &mh, 64);
+    int32_t meta[2] = {h->g.lz, h->cfg.scheme};
+    memcpy(blob + 192, meta, sizeof meta);
+    long long slab = h->g.slab;
+    memcpy(blob + 200, &slab, sizeof slab);
+    // A and B may have been swapped by earlier steps: say which allocation is the current source
+    int32_t a_is_first = (h->A == h->A_alloc + POP_PAD) ? 1 : 0;
+    memcpy(blob + 208, &a_is_first, sizeof a_is_first);
+    return 0;
+}
+
+extern "C" int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->cfg.nranks < 2) return fail("d3q19_ipc_connect: needs nranks > 1");
+    if (h->cfg.ipart) return fail("d3q19_ipc_connect: the particle path exchanges its halo through NCCL");
+    if (h->g.lz < 2) return fail("d3q19_ipc_connect: slabs must be at least 2 planes thick");
+    if (!h->halo_flags) return fail("d3q19_ipc_connect: call d3q19_ipc_export first");
+    if (h->halo_on) return fail("d3q19_ipc_connect: already connected");
+    RK_(wait_exchange(h));
+    const int nb[2] = {(h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks, (h->cfg.rank + 1) % h->cfg.nranks};
+    for (int d = 0; d < 2; ++d) {
+        const unsigned char *b = blobs + (size_t)nb[d] * D3Q19_IPC_BYTES;
+        int32_t meta[2]; long long slab; int32_t a_first;
+        memcpy(meta, b + 192, sizeof meta); memcpy(&slab, b + 200, sizeof slab); memcpy(&a_first, b + 208, sizeof a_first);
+        if (meta[1] != h->cfg.scheme) return fail("d3q19_ipc_connect: rank %d runs scheme %d, this rank %d", nb[d], meta[1], h->cfg.scheme);
+        h->peer_lz[d] = meta[0];
+        h->peer_slab[d] = slab;
+        if (d == 1 && nb[1] == nb[0]) {                 // two ranks: both neighbours are the same process
+            for (int a = 0; a < 3; ++a) h->peer_base[1][a] = h->peer_base[0][a];
+        } else {
+            cudaIpcMemHandle_t mh;
+            const unsigned char zero[64] = {0};
+            for (int a = 0; a < 3; ++a) {
+                if (a == 1 && !memcmp(b + 64, zero, 64)) continue;
+                memcpy(&mh, b + 64 * a, 64);
+                CK(cudaIpcOpenMemHandle(&h->peer_base[d][a], mh, cudaIpcMemLazyEnablePeerAccess));
+            }
+        }
+        double *first = (double *)h->peer_base[d][0] + POP_PAD;
+        double *second = h->peer_base[d][1] ? (double *)h->peer_base[d][1] + POP_PAD : nullptr;
+        h->peer_A[d] = a_first ? first : second;
+        h->peer_B[d] = a_first ? second : first;
+        h->peer_flags[d] = (unsigned int *)h->peer_base[d][2];
+    }
+    // everybody has opened everybody: a barrier before the first remote store
+    if (h->comm) {
+        NK(nccl_api().AllReduce(h->scal + 32, h->scal + 32, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
+        h->n_nccl++;
+    }
+    CK(cudaStreamSynchronize(h->sc));
+    h->halo_on = true;
+    return 0;
+}
+
+// collective operations that rewrite the populations end with a barrier in halo mode, so that no
+// neighbour starts storing into planes that are still being filled
+static int halo_barrier(d3q19_handle *h) {
+    if (!h->halo_on || !h->comm) return 0;
+    NK(nccl_api().AllReduce(h->scal + 32, h->scal + 32, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
+    h->n_nccl++;
+    CK(cudaStreamSynchronize(h->sc));
     return 0;
 }
 
@@ -359,7 +487,7 @@ extern "C" int d3q19_upload_f(d3q19_handle *h, const double *f_aos) {
     h->phase = 0;
     CK(cudaStreamSynchronize(h->sx));
     CK(cudaStreamSynchronize(h->sc));
-    return 0;
+    return halo_barrier(h);
 }
 
 template <int RKIND>
@@ -475,10 +603,45 @@ static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int 
     return 0;
 }
 
+// one launch for the whole slab, boundary planes first, halo stored into the neighbours' memory
+template <int SK, bool STRICT, bool GENERIC>
+static int launch_step_halo(d3q19_handle *h, const StepParams &p0) {
+    StepParams p = p0;
+    Halo &q = p.halo;
+    const bool ab = SK == STEP_AB;
+    // AB: this step writes B here and in the neighbours; AA: the single array
+    q.peer_dn = ab ? h->peer_B[0] : h->peer_A[0];
+    q.peer_up = ab ? h->peer_B[1] : h->peer_A[1];
+    q.slab_dn = h->peer_slab[0]; q.slab_up = h->peer_slab[1];
+    q.lz_dn = h->peer_lz[0];
+    q.wait_lo = h->halo_flags; q.wait_hi = h->halo_flags + 1;
+    q.sig_dn = h->peer_flags[0] + 1;      // the lower neighbour's wait_hi
+    q.sig_up = h->peer_flags[1];          // the upper neighbour's wait_lo
+    q.ctr = h->halo_flags + 2;
+    q.epoch = ++h->halo_epoch;
+    const dim3 gr = grid_nodes(h, h->g.lz);
+    q.nblk_face = gr.x * gr.y;
+    if (h->idx32) k_step<SK, STRICT, GENERIC, uint32_t, true><<<gr, BLOCK_X, 0, h->sc>>>(p);
+    else k_step<SK, STRICT, GENERIC, unsigned long long, true><<<gr, BLOCK_X, 0, h->sc>>>(p);
+    CK(cudaGetLastError());
+    h->n_step_kernels++;
+    if (ab) {                             // the neighbours swap their arrays in lockstep
+        for (int d = 0; d < 2; ++d) { double *t = h->peer_A[d]; h->peer_A[d] = h->peer_B[d]; h->peer_B[d] = t; }
+    }
+    return 0;
+}
+
 template <int SK, bool STRICT, bool GENERIC>
 static int step_impl(d3q19_handle *h, const StepParams &p, double *written) {
     const int lz = h->g.lz;
     if (h->cfg.nranks == 1) return launch_step_range<SK, STRICT, GENERIC>(h, p, 1, lz, h->sc);
+    if (h->halo_on) {
+        if (h->exchange_pending) {          // a ghost fill by NCCL (upload, init) precedes the first halo step
+            CK(cudaStreamWaitEvent(h->sc, h->evX, 0));
+            h->exchange_pending = false;
+        }
+        return launch_step_halo<SK, STRICT, GENERIC>(h, p);
+    }
     // boundary planes first, so that their faces travel while the interior is computed
     RK_(wait_exchange(h));
     if (h->cfg.overlap && lz > 2) {
@@ -580,7 +743,8 @@ extern "C" int d3q19_init_channel(d3q19_handle *h, double ustar, double ystar, d
     h->shim.f_host_valid = false;
     h->shim.macro_dev_valid = false;
     CK(cudaStreamSynchronize(h->sc));
-    return 0;
+    CK(cudaStreamSynchronize(h->sx));
+    return halo_barrier(h);
 }
 
 // ---- macrovar / rhoupdat ---------------------------------------------------------------------------------
@@ -738,11 +902,65 @@ extern "C" int d3q19_set_solid_mask(d3q19_handle *h, const int32_t *ibnodes_ghos
     return 0;
 }
 
+// ---- particles: device-side bookkeeping (particles.cuh) --------------------------------------------------------------
+static PartGeom part_geom(const d3q19_handle *h) {
+    PartGeom pg;
+    pg.g = h->g; pg.nx = h->cfg.nx; pg.ny = h->cfg.ny; pg.nz = h->cfg.nz; pg.globalz = h->cfg.globalz; pg.rad = h->pp.rad;
+    return pg;
+}
+
+extern "C" int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_particle_params *prm) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (npart <= 0 || !prm || !(prm->rad > 0.0)) return fail("d3q19_particles_init: bad arguments");
+    if (h->part_on) return fail("d3q19_particles_init: already initialised");
+    if (!h->cfg.ipart) return fail("d3q19_particles_init: create the handle with ipart = 1");
+    if (h->halo_on) return fail("d3q19_particles_init: the particle path exchanges its halo through NCCL (do not call d3q19_ipc_connect)");
+    if (!h->idx32) return fail("d3q19_particles_init: slab too large for 32-bit link indices");
+    if (2.0 * prm->rad + 4.0 > h->cfg.ny || 2.0 * prm->rad + 4.0 > h->cfg.nz) return fail("d3q19_particles_init: particle larger than the periodic box");
+    h->pp = *prm;
+    if (h->ypglb) { cudaFree(h->ypglb); cudaFree(h->wp); cudaFree(h->omgp); }
+    if (h->solid) { cudaFree(h->solid); h->solid = nullptr; }
+    if (h->isn) { cudaFree(h->isn); h->isn = nullptr; }
+    h->npart = npart;
+    const size_t tb = (size_t)3 * npart;
+    CK(cudaMalloc(&h->pbuf, 10 * tb * sizeof(double)));
+    CK(cudaMemsetAsync(h->pbuf, 0, 10 * tb * sizeof(double), h->sc));
+    double *q = h->pbuf;
+    h->ypglb = q; q += tb; h->ypglb0 = q; q += tb; h->wp = q; q += tb; h->omgp = q; q += tb; h->fHIp = q; q += tb;
+    h->torqp = q; q += tb; h->flubp = q; q += tb; h->forcepp = q; q += tb; h->torqpp = q; q += tb; h->thetap = q;
+    const size_t nown = (size_t)h->g.plane * (h->g.lz + 2);
+    CK(cudaMalloc(&h->own, nown * sizeof(int32_t)));
+    CK(cudaMalloc(&h->own0, nown * sizeof(int32_t)));
+    CK(cudaMemsetAsync(h->own, 0xFF, nown * sizeof(int32_t), h->sc));
+    CK(cudaMemsetAsync(h->own0, 0xFF, nown * sizeof(int32_t), h->sc));
+    const double pi = 4.0 * atan(1.0);
+    h->maxlink = prm->maxlink > 0 ? prm->maxlink : (long long)(8.0 * npart * 4.0 * pi * (prm->rad + 1.0) * (prm->rad + 1.0)) + 64;
+    CK(cudaMalloc(&h->links.node, h->maxlink * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->links.dir, h->maxlink * sizeof(int32_t)));
+    CK(cudaMalloc(&h->links.part, h->maxlink * sizeof(int32_t)));
+    CK(cudaMalloc(&h->links.q, h->maxlink * sizeof(double)));
+    CK(cudaMalloc(&h->lcount, (npart + 1) * sizeof(long long)));
+    CK(cudaMalloc(&h->loffset, (npart + 1) * sizeof(long long)));
+    CK(cudaMalloc(&h->nfilled_dev, sizeof(unsigned long long)));
+    const double volp = 4.0 / 3.0 * pi * prm->rad * prm->rad * prm->rad;      // para.f90:340
+    h->amp = h->cfg.rhopart * volp;                                           // :341
+    h->aip = 0.4 * h->amp * prm->rad * prm->rad;                              // :342
+    h->solid = h->own + h->g.plane;
+    h->isn = h->own + h->g.plane;
+    h->part_on = true;
+    h->links_valid = false; h->mask_built = false;
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
 extern "C" int d3q19_set_particles(d3q19_handle *h, int32_t npart, const double *ypglb, const double *wp, const double *omgp) {
     CK(cudaSetDevice(h->cfg.device));
     if (npart <= 0 || !ypglb || !wp || !omgp) return fail("d3q19_set_particles: bad arguments");
     const size_t nb = (size_t)3 * npart * sizeof(double);
-    if (npart != h->npart) {
+    if (h->part_on) {
+        if (npart != h->npart) return fail("d3q19_set_particles: %d particles, initialised for %d", npart, h->npart);
+        h->links_valid = false;
+    } else if (npart != h->npart) {
         CK(cudaStreamSynchronize(h->sc));
         if (h->ypglb) { cudaFree(h->ypglb); cudaFree(h->wp); cudaFree(h->omgp); }
         CK(cudaMalloc(&h->ypglb, nb)); CK(cudaMalloc(&h->wp, nb)); CK(cudaMalloc(&h->omgp, nb));
@@ -751,6 +969,173 @@ extern "C" int d3q19_set_particles(d3q19_handle *h, int32_t npart, const double 
     CK(cudaMemcpyAsync(h->ypglb, ypglb, nb, cudaMemcpyHostToDevice, h->sc));
     CK(cudaMemcpyAsync(h->wp, wp, nb, cudaMemcpyHostToDevice, h->sc));
     CK(cudaMemcpyAsync(h->omgp, omgp, nb, cudaMemcpyHostToDevice, h->sc));
+    if (h->part_on) CK(cudaMemcpyAsync(h->ypglb0, ypglb, nb, cudaMemcpyHostToDevice, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+// beads_links: solid mask from the particle table, then the boundary-link list
+extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->part_on) return fail("d3q19_beads_links: call d3q19_particles_init first");
+    const PartGeom pg = part_geom(h);
+    const size_t nown = (size_t)h->g.plane * (h->g.lz + 2);
+    int32_t *t = h->own; h->own = h->own0; h->own0 = t;          // the old mask is what beads_filling compares against
+    h->solid = h->own + h->g.plane; h->isn = h->own + h->g.plane;
+    CK(cudaMemsetAsync(h->own, 0xFF, nown * sizeof(int32_t), h->sc));
+    k_beads_mask<<<h->npart, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own);
+    if (!h->mask_built) {                                         // first mask: nothing was uncovered
+        CK(cudaMemcpyAsync(h->own0, h->own, nown * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->sc));
+        h->mask_built = true;
+    }
+    k_beads_links<false><<<h->npart, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
+    k_beads_scan<<<1, 32, 0, h->sc>>>(h->npart, h->lcount, h->loffset);
+    k_beads_links<true><<<h->npart, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
+    CK(cudaGetLastError());
+    h->n_other_kernels += 4;
+    long long n = 0;
+    CK(cudaMemcpyAsync(&n, h->loffset + h->npart, sizeof n, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    if (n > h->maxlink) return fail("d3q19_beads_links: %lld links exceed maxlink %lld", n, h->maxlink);
+    h->nlink = n;
+    h->links_valid = true;
+    if (nlink_local) *nlink_local = n;
+    return 0;
+}
+
+// beads_collision: interpolated bounce-back on every link + hydrodynamic force and torque
+extern "C" int d3q19_beads_collision(d3q19_handle *h) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->part_on || !h->links_valid) return fail("d3q19_beads_collision: no valid link list (d3q19_beads_links)");
+    RK_(wait_exchange(h));
+    const size_t tb = (size_t)3 * h->npart * sizeof(double);
+    CK(cudaMemsetAsync(h->fHIp, 0, 2 * tb, h->sc));                // fHIp and torqp are adjacent
+    if (h->nlink > 0) {
+        IbbParams P;
+        P.pg = part_geom(h); P.S = h->A; P.own = h->own; P.L = h->links; P.nlink = h->nlink;
+        P.ypglb = h->ypglb; P.wp = h->wp; P.omgp = h->omgp; P.rho0 = h->pp.rho0; P.fHIp = h->fHIp; P.torqp = h->torqp;
+        const unsigned nb = (unsigned)((h->nlink + 127) / 128);
+        switch (read_kind(h)) {
+        case READ_DIRECT: k_beads_ibb<READ_DIRECT><<<nb, 128, 0, h->sc>>>(P); break;
+        case READ_PULL_NAT: k_beads_ibb<READ_PULL_NAT><<<nb, 128, 0, h->sc>>>(P); break;
+        default: k_beads_ibb<READ_PULL_SWAP><<<nb, 128, 0, h->sc>>>(P); break;
+        }
+        CK(cudaGetLastError());
+        h->n_other_kernels++;
+    }
+    if (h->cfg.nranks > 1) {                                       // force reduction over the slabs
+        NK(nccl_api().AllReduce(h->fHIp, h->fHIp, (size_t)6 * h->npart, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
+        h->n_nccl++;
+    }
+    h->shim.f_host_valid = false;
+    return 0;
+}
+
+extern "C" int d3q19_beads_lubforce(d3q19_handle *h) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->part_on) return fail("d3q19_beads_lubforce: call d3q19_particles_init first");
+    LubParams lp = {h->pp.mingap, h->pp.mingap_w, h->pp.stf0, h->pp.stf1, h->pp.stf0_w, h->pp.stf1_w, h->pp.fscale};
+    k_beads_lubforce<<<(h->npart + 127) / 128, 128, 0, h->sc>>>(part_geom(h), h->npart, h->ypglb, lp, h->flubp);
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    return 0;
+}
+
+extern "C" int d3q19_beads_move(d3q19_handle *h) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->part_on) return fail("d3q19_beads_move: call d3q19_particles_init first");
+    MoveParams M = {h->amp, h->aip, h->pp.gforce[0], h->pp.gforce[1], h->pp.gforce[2], h->fHIp, h->torqp, h->flubp,
+                    h->forcepp, h->torqpp, h->ypglb, h->ypglb0, h->wp, h->omgp, h->thetap};
+    k_beads_move<<<(h->npart + 127) / 128, 128, 0, h->sc>>>(part_geom(h), h->npart, M);
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    h->links_valid = false;
+    return 0;
+}
+
+// beads_filling: populations of the nodes the last move uncovered (needs the rebuilt mask)
+extern "C" int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->part_on || !h->links_valid) return fail("d3q19_beads_filling: rebuild the mask first (d3q19_beads_links)");
+    RK_(wait_exchange(h));
+    CK(cudaMemsetAsync(h->nfilled_dev, 0, sizeof(unsigned long long), h->sc));
+    FillParams P;
+    P.pg = part_geom(h); P.S = h->A; P.own0 = h->own0; P.own = h->own; P.ypglb0 = h->ypglb0;
+    P.ypglb = h->ypglb; P.wp = h->wp; P.omgp = h->omgp; P.nfilled = h->nfilled_dev;
+    switch (read_kind(h)) {
+    case READ_DIRECT: k_beads_fill<READ_DIRECT><<<h->npart, 128, 0, h->sc>>>(P); break;
+    case READ_PULL_NAT: k_beads_fill<READ_PULL_NAT><<<h->npart, 128, 0, h->sc>>>(P); break;
+    default: k_beads_fill<READ_PULL_SWAP><<<h->npart, 128, 0, h->sc>>>(P); break;
+    }
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, h->nfilled_dev, sizeof n, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    if (nfilled) *nfilled = (int64_t)n;
+    h->shim.f_host_valid = false;
+    return 0;
+}
+
+// one particle-laden time step in the order of the reference's timers (var_inc.f90:166-168)
+extern "C" int d3q19_particle_step(d3q19_handle *h, int32_t move) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->part_on) return fail("d3q19_particle_step: call d3q19_particles_init first");
+    if (!h->links_valid) RK_(d3q19_beads_links(h, nullptr));
+    RK_(collide_stream_impl(h, D3Q19_MACRO_MAIN, nullptr));       // fluid nodes only (solid nodes skipped)
+    RK_(d3q19_beads_collision(h));
+    if (move) {
+        RK_(d3q19_beads_lubforce(h));
+        RK_(d3q19_beads_move(h));
+        RK_(d3q19_beads_links(h, nullptr));
+        RK_(d3q19_beads_filling(h, nullptr));
+    }
+    return 0;
+}
+
+extern "C" int d3q19_get_particles(d3q19_handle *h, double *ypglb, double *wp, double *omgp, double *fHIp, double *torqp) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->part_on) return fail("d3q19_get_particles: call d3q19_particles_init first");
+    const size_t tb = (size_t)3 * h->npart * sizeof(double);
+    const double *src[5] = {h->ypglb, h->wp, h->omgp, h->fHIp, h->torqp};
+    double *dst[5] = {ypglb, wp, omgp, fHIp, torqp};
+    for (int i = 0; i < 5; ++i) if (dst[i]) CK(cudaMemcpyAsync(dst[i], src[i], tb, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+// the link list of this slab in list order: global 1-based node coordinates, direction, particle, q
+extern "C" int d3q19_get_links(d3q19_handle *h, int64_t capacity, int32_t *x, int32_t *y, int32_t *z, int32_t *ip,
+                               int32_t *part, double *q, int64_t *nlink) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->part_on || !h->links_valid) return fail("d3q19_get_links: no valid link list");
+    if (nlink) *nlink = h->nlink;
+    if (capacity < h->nlink) return fail("d3q19_get_links: capacity %lld < %lld links", (long long)capacity, h->nlink);
+    if (h->nlink == 0) return 0;
+    int32_t *tmp = nullptr;
+    const size_t nb = (size_t)h->nlink * sizeof(int32_t);
+    CK(cudaMalloc(&tmp, 3 * nb));
+    k_links_export<<<(unsigned)((h->nlink + 127) / 128), 128, 0, h->sc>>>(h->g, h->cfg.globalz, h->nlink, h->links, tmp,
+                                                                        tmp + h->nlink, tmp + 2 * h->nlink);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(x, tmp, nb, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaMemcpyAsync(y, tmp + h->nlink, nb, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaMemcpyAsync(z, tmp + 2 * h->nlink, nb, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaMemcpyAsync(ip, h->links.dir, nb, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaMemcpyAsync(part, h->links.part, nb, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaMemcpyAsync(q, h->links.q, (size_t)h->nlink * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    cudaFree(tmp);
+    return 0;
+}
+
+// owner mask of the local slab without ghosts, (lx,ly,lz): particle id (1-based) or -1 (= isnodes; ibnodes = sign)
+extern "C" int d3q19_get_mask(d3q19_handle *h, int32_t *own_lx_ly_lz) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->part_on || !h->mask_built) return fail("d3q19_get_mask: no mask yet");
+    const Geom &g = h->g;
+    CK(cudaMemcpy2DAsync(own_lx_ly_lz, (size_t)g.lx * sizeof(int32_t), h->own + g.plane, (size_t)g.xp * sizeof(int32_t),
+                         (size_t)g.lx * sizeof(int32_t), (size_t)g.ly * g.lz, cudaMemcpyDeviceToHost, h->sc));
     CK(cudaStreamSynchronize(h->sc));
     return 0;
 }

@@ -77,6 +77,21 @@ struct Geom {
     int zhi_src;          // ghosted plane index that acts as "z+1" of plane lz  (1  if 1 rank, else lz+1)
 };
 
+// Halo over NVLink peer memory: the boundary planes of a step store their
+// five outgoing populations straight into the neighbour GPU's array (cudaIpc-mapped) and raise a
+// flag there; the neighbour's next step spins on that flag before it touches the planes.  No pack
+// kernel, no NCCL call, no second stream: one launch per step.
+struct Halo {
+    double *peer_up, *peer_dn;          // the neighbours' array this step writes (population 0 base)
+    long long slab_up, slab_dn;         // their elements per population
+    int lz_dn;                          // thickness of the lower neighbour's slab
+    unsigned int *wait_lo, *wait_hi;    // local flags raised by the lower / upper neighbour
+    unsigned int *sig_up, *sig_dn;      // remote flags: the upper neighbour's wait_lo, the lower's wait_hi
+    unsigned int *ctr;                  // two local block counters (plane 1, plane lz)
+    unsigned int epoch;                 // number of this halo step (1, 2, ...)
+    unsigned int nblk_face;             // blocks per plane
+};
+
 struct StepParams {
     Geom g;
     double *A;            // source (and destination for AA)
@@ -93,6 +108,7 @@ struct StepParams {
     const double *ffx, *ffy, *ffz;   // force field or nullptr
     const int32_t *solid;            // >0 solid, [lz][ly][xp], or nullptr
     unsigned long long *rhoerr_bits; // PRERELAX: max |rho_new - rho_old| as ordered bits
+    Halo halo;                       // HALO instantiation only
 };
 
 // ---- neighbour addressing ------------------------------------------------------------------
@@ -169,6 +185,26 @@ struct Gather {
         return v;
 #endif
     }
+    // AA odd with the halo in peer memory: a value that would land in a z ghost plane is stored
+    // into the neighbour's real plane instead (same slot, same row): ghost lz+1 -> the upper
+    // neighbour's plane 1, ghost 0 -> the lower neighbour's plane lz_dn.
+    template <class IDX>
+    static __device__ __forceinline__ void store_back_halo(double *A, const Geom &g, const NodeIdx<IDX> &k, double v,
+                                                           const Halo &h) {
+        if (cz != 0 && !at_wall(k)) {
+            if (cz < 0 && k.zg == g.lz) {          // pulled from z+1
+                const long long o = (long long)index_nb(k) - (long long)(g.lz + 1) * g.plane + g.plane;
+                pop_store(h.peer_up + (long long)slot_nb * h.slab_up + o, v);
+                return;
+            }
+            if (cz > 0 && k.zg == 1) {             // pulled from z-1
+                const long long o = (long long)index_nb(k) + (long long)h.lz_dn * g.plane;
+                pop_store(h.peer_dn + (long long)slot_nb * h.slab_dn + o, v);
+                return;
+            }
+        }
+        store_back(A, g, k, v);
+    }
     // AA odd: the post-collision value of direction opp(I) goes back to where f_I came from
     template <class IDX>
     static __device__ __forceinline__ void store_back(double *A, const Geom &g, const NodeIdx<IDX> &k, double v) {
@@ -213,13 +249,28 @@ __device__ __forceinline__ void block_max_to(unsigned long long *dst, double v) 
 // ---- the step kernel ---------------------------------------------------------------------------
 // GENERIC = false: main loop, uniform force, no solids, moments in registers (304 B/node).
 // GENERIC = true : run-time macro mode / force field / solid mask.
-template <int SK, bool STRICT, bool GENERIC, class IDX>
+// HALO = true : z-slab run with the halo in peer memory; one launch covers the whole slab with the
+//                two boundary planes first in block order (blockIdx.z 0 -> plane 1, 1 -> plane lz).
+template <int SK, bool STRICT, bool GENERIC, class IDX, bool HALO = false>
 __global__ void __launch_bounds__(BLOCK_X, SK == STEP_AA_ODD ? D3Q_MIN_BLOCKS_ODD : D3Q_MIN_BLOCKS) k_step(const __grid_constant__ StepParams p) {
     const Geom &g = p.g;
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     double rhoerr = 0.0;
+    const int zg_blk = HALO ? (blockIdx.z == 0 ? 1 : (blockIdx.z == 1 ? g.lz : (int)blockIdx.z))
+                            : p.z0 + (int)blockIdx.z * p.zstride;
+    if (HALO) {
+        // the planes next to a face read what the neighbour's previous step stored here
+        if (zg_blk == 1 || zg_blk == g.lz) {
+            if (threadIdx.x == 0) {
+                const volatile unsigned int *fl = (zg_blk == 1) ? p.halo.wait_lo : p.halo.wait_hi;
+                while (*fl + 1u < p.halo.epoch) { }
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
+    }
     if (x < g.lx) {
-        const NodeIdx<IDX> k = make_node<IDX>(g, x, blockIdx.y, p.z0 + (int)blockIdx.z * p.zstride);
+        const NodeIdx<IDX> k = make_node<IDX>(g, x, blockIdx.y, zg_blk);
         constexpr int RK = (SK == STEP_AB) ? READ_PULL_NAT : (SK == STEP_AA_EVEN ? READ_DIRECT : READ_PULL_SWAP);
         double f[NPOP];
         gather19<RK>(p.A, g, k, f);
@@ -263,21 +314,48 @@ __global__ void __launch_bounds__(BLOCK_X, SK == STEP_AA_ODD ? D3Q_MIN_BLOCKS_OD
             }
         }
 
+        // in-plane offset of this node (y not decomposed: the same in every slab)
+        const long long inplane = (long long)k.y * g.xp + x;
         if (SK == STEP_AB) {
             static_for<NPOP>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 pop_store(p.B + (long long)i * g.slab + k.n, f[i]);
+                if (HALO && dir_cz(i) > 0 && zg_blk == g.lz)       // -> the upper neighbour's ghost plane 0
+                    pop_store(p.halo.peer_up + (long long)i * p.halo.slab_up + inplane, f[i]);
+                if (HALO && dir_cz(i) < 0 && zg_blk == 1)          // -> the lower neighbour's ghost plane lz_dn+1
+                    pop_store(p.halo.peer_dn + (long long)i * p.halo.slab_dn + (long long)(p.halo.lz_dn + 1) * g.plane + inplane, f[i]);
             });
         } else if (SK == STEP_AA_EVEN) {
             static_for<NPOP>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 pop_store(p.A + (long long)dir_opp(i) * g.slab + k.n, f[i]);
+                if (HALO && dir_cz(i) > 0 && zg_blk == g.lz)
+                    pop_store(p.halo.peer_up + (long long)dir_opp(i) * p.halo.slab_up + inplane, f[i]);
+                if (HALO && dir_cz(i) < 0 && zg_blk == 1)
+                    pop_store(p.halo.peer_dn + (long long)dir_opp(i) * p.halo.slab_dn + (long long)(p.halo.lz_dn + 1) * g.plane + inplane, f[i]);
             });
         } else {
             static_for<NPOP>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
-                Gather<READ_PULL_SWAP, i>::store_back(p.A, g, k, f[dir_opp(i)]);
+                if (HALO) Gather<READ_PULL_SWAP, i>::store_back_halo(p.A, g, k, f[dir_opp(i)], p.halo);
+                else Gather<READ_PULL_SWAP, i>::store_back(p.A, g, k, f[dir_opp(i)]);
             });
+        }
+    }
+    if (HALO) {
+        // last block of a boundary plane: everything it stored remotely is visible -> raise the neighbour's flag
+        if (zg_blk == 1 || zg_blk == g.lz) {
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int *c = p.halo.ctr + (zg_blk == g.lz ? 1 : 0);
+                const unsigned int prev = atomicAdd(c, 1u);
+                if (prev == p.halo.nblk_face - 1u) {
+                    *c = 0u;
+                    __threadfence_system();
+                    *(volatile unsigned int *)(zg_blk == g.lz ? p.halo.sig_up : p.halo.sig_dn) = p.halo.epoch;
+                }
+            }
         }
     }
     if (GENERIC && p.macro_mode == 1 && p.rhoerr_bits) block_max_to(p.rhoerr_bits, rhoerr);
@@ -378,6 +456,12 @@ __global__ void __launch_bounds__(BLOCK_X) k_init_channel(const __grid_constant_
         }
         p.A[(long long)i * g.slab + n] = v;
     });
+}
+
+// readers of the ghost planes (download, macrovar, probe, profiles) run after the neighbours' stores
+__global__ void k_halo_wait(const volatile unsigned int *lo, const volatile unsigned int *hi, unsigned int epoch) {
+    while (*lo < epoch || *hi < epoch) { }
+    __threadfence_system();
 }
 
 // ---- macrovar (collision.f90:378-463) / rhoupdat (:469-480) -----------------------------------

@@ -1,0 +1,478 @@
+// particles.cuh -- device kernels of the particle path: solid mask and boundary links
+// (beads_links), interpolated bounce-back with momentum-exchange force (beads_collision),
+// short-range repulsion (beads_lubforce), rigid-body update (beads_move) and refill of the nodes
+// a particle uncovered (beads_filling).  The names are the reference's timer names
+// (var_inc.f90:166-168); the reference snapshot does NOT contain the code behind them
+// (partlib.f90 is absent), so these kernels implement the published algorithms
+// the reference's data structures point to -- Bouzidi et al. 2001 / Lallemand & Luo 2003 linear
+// interpolated bounce-back, Galilean-invariant momentum exchange (Wen et al. 2014, Peng et al.
+// 2016), equilibrium + non-equilibrium refill (Caiazzo 2008), Feng & Michaelides 2005 repulsion --
+// and are checked against oracle/particles_oracle.c ("parity unpinned" against the reference).
+//
+// Geometry conventions are the reference's: node (ix,iy,iz) sits at (ix-0.5, iy-0.5, iz-0.5)
+// (collision.f90:424-426); a node is solid iff |r - r_c| < rad; periodic images in y and z only
+// (collision.f90:433-440); ibnodes = -1 fluid / > 0 solid, isnodes = owning particle id.  Here one
+// ghosted int32 array `own[zg][y][x]` holds the owner id (1-based) or -1: own + plane is both the
+// `solid` and the `isnodes` array the fluid kernels take.  The mask is a pure function of the
+// replicated particle table, so every GPU fills its own ghost planes without any exchange.
+//
+// Integer work (mask, link list) uses non-contracted arithmetic (the R type of collide.cuh) so
+// that it is bit-identical to the CPU checker.
+#pragma once
+#include "kernels.cuh"
+
+namespace d3q {
+
+struct PartGeom {
+    Geom g;
+    int nx, ny, nz, globalz;
+    double rad;
+};
+
+__device__ __forceinline__ int wrap1(int j, int n) {
+    int r = (j - 1) % n;
+    if (r < 0) r += n;
+    return r + 1;
+}
+
+struct BBox { int lo[3], n[3]; };
+
+__device__ __forceinline__ BBox part_bbox(const PartGeom &pg, const double *c) {
+    BBox b;
+    int hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        b.lo[d] = (int)floor((R(c[d]) - R(pg.rad) + R(0.5)).v) - 1;
+        hi[d] = (int)ceil((R(c[d]) + R(pg.rad) + R(0.5)).v) + 1;
+    }
+    if (b.lo[0] < 1) b.lo[0] = 1;
+    if (hi[0] > pg.nx) hi[0] = pg.nx;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) b.n[d] = hi[d] - b.lo[d] + 1 > 0 ? hi[d] - b.lo[d] + 1 : 0;
+    return b;
+}
+
+__device__ __forceinline__ double dist2_node(const double *c, int jx, int jy, int jz) {
+    const R dx = R((double)jx - 0.5) - R(c[0]), dy = R((double)jy - 0.5) - R(c[1]), dz = R((double)jz - 0.5) - R(c[2]);
+    return (dx * dx + dy * dy + dz * dz).v;
+}
+
+// local ghosted plane(s) of global plane iz (1..nz): up to two (a real plane and a periodic ghost copy)
+__device__ __forceinline__ int local_planes(const PartGeom &pg, int iz, int out[3]) {
+    int n = 0;
+#pragma unroll
+    for (int s = -1; s <= 1; ++s) {
+        const int zg = iz - pg.globalz + s * pg.nz;
+        if (zg >= 0 && zg <= pg.g.lz + 1) out[n++] = zg;
+    }
+    return n;
+}
+
+// ---- beads_links, part 1: solid mask (own must be preset to -1) -----------------------------------
+__global__ void __launch_bounds__(256) k_beads_mask(PartGeom pg, int npart, const double *ypglb, int32_t *own) {
+    const int p = blockIdx.x;
+    const double *c = ypglb + 3 * p;
+    const BBox b = part_bbox(pg, c);
+    const double r2 = (R(pg.rad) * R(pg.rad)).v;
+    const long long nbox = (long long)b.n[0] * b.n[1] * b.n[2];
+    for (long long t = threadIdx.x; t < nbox; t += blockDim.x) {
+        const int jx = b.lo[0] + (int)(t % b.n[0]);
+        const int jy = b.lo[1] + (int)((t / b.n[0]) % b.n[1]);
+        const int jz = b.lo[2] + (int)(t / ((long long)b.n[0] * b.n[1]));
+        if (!(dist2_node(c, jx, jy, jz) < r2)) continue;
+        const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
+        int zs[3];
+        const int nz = local_planes(pg, iz, zs);
+        for (int q = 0; q < nz; ++q) {
+            int32_t *a = own + ((long long)(jx - 1) + (long long)pg.g.xp * ((iy - 1) + (long long)pg.g.ly * zs[q]));
+            int32_t old = *a;                       // the lowest id wins where particles overlap
+            while (old < 0 || old > p + 1) {
+                const int32_t assumed = old;
+                old = atomicCAS(a, assumed, p + 1);
+                if (old == assumed) break;
+            }
+        }
+    }
+}
+
+// ---- beads_links, part 2: boundary links ------------------------------------------------------------
+// Order: particle, then its box in z,y,x order, then direction 1..18 -- each thread owns a contiguous
+// chunk of the box so that the block-wide exclusive scan of the per-thread counts keeps that order.
+struct Links {
+    uint32_t *node;      // ghosted in-slab index of the fluid node
+    int32_t *dir;        // direction pointing into the solid
+    int32_t *part;       // particle id, 1-based
+    double *q;           // fraction of the link on the fluid side, (0,1]
+};
+
+__device__ __forceinline__ bool link_here(const PartGeom &pg, const int32_t *own, const double *c, int p, int jx, int jy,
+                                          int jz, int zg, int ip, double r2, double &q) {
+    const int cx = dir_cx(ip), cy = dir_cy(ip), cz = dir_cz(ip);
+    const int kx = jx + cx;
+    if (kx < 1 || kx > pg.nx) return false;
+    const int ky = wrap1(jy + cy, pg.ny);
+    const int kzg = zg + cz;                         // ghost planes carry the mask too
+    if (own[(long long)(kx - 1) + (long long)pg.g.xp * ((ky - 1) + (long long)pg.g.ly * kzg)] != p + 1) return false;
+    const R dx = R((double)jx - 0.5) - R(c[0]), dy = R((double)jy - 0.5) - R(c[1]), dz = R((double)jz - 0.5) - R(c[2]);
+    const R a((double)(cx * cx + cy * cy + cz * cz));
+    const R b = R(2.0) * (R((double)cx) * dx + R((double)cy) * dy + R((double)cz) * dz);
+    const R cc = dx * dx + dy * dy + dz * dz - R(r2);
+    double disc = (b * b - R(4.0) * a * cc).v;
+    if (disc < 0.0) disc = 0.0;
+    q = __ddiv_rn((-b - R(__dsqrt_rn(disc))).v, (R(2.0) * a).v);
+    if (q < 0.0) q = 0.0;
+    if (q > 1.0) q = 1.0;
+    return true;
+}
+
+// FILL = false: count[p] = number of links of particle p on this slab; FILL = true: write them at offset[p]
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_beads_links(PartGeom pg, int npart, const double *ypglb, const int32_t *own,
+                                                     long long *count, const long long *offset, long long maxlink, Links L) {
+    __shared__ long long sh[256];
+    const int p = blockIdx.x;
+    const double *c = ypglb + 3 * p;
+    const BBox b = part_bbox(pg, c);
+    const double r2 = (R(pg.rad) * R(pg.rad)).v;
+    const long long nbox = (long long)b.n[0] * b.n[1] * b.n[2];
+    const long long chunk = (nbox + blockDim.x - 1) / blockDim.x;
+    const long long t0 = (long long)threadIdx.x * chunk, t1 = t0 + chunk < nbox ? t0 + chunk : nbox;
+    long long mine = 0;
+    for (int pass = 0; pass < (FILL ? 2 : 1); ++pass) {
+        long long w = 0;
+        if (pass == 1) {                              // exclusive scan of the per-thread counts
+            sh[threadIdx.x] = mine;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                long long acc = offset[p];
+                for (int i = 0; i < 256; ++i) { const long long v = sh[i]; sh[i] = acc; acc += v; }
+            }
+            __syncthreads();
+            w = sh[threadIdx.x];
+        }
+        for (long long t = t0; t < t1; ++t) {
+            const int jx = b.lo[0] + (int)(t % b.n[0]);
+            const int jy = b.lo[1] + (int)((t / b.n[0]) % b.n[1]);
+            const int jz = b.lo[2] + (int)(t / ((long long)b.n[0] * b.n[1]));
+            const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
+            const int zg = iz - pg.globalz;          // links belong to the GPU that owns the fluid node
+            if (zg < 1 || zg > pg.g.lz) continue;
+            const long long n = (long long)(jx - 1) + (long long)pg.g.xp * ((iy - 1) + (long long)pg.g.ly * zg);
+            if (own[n] > 0) continue;
+            for (int ip = 1; ip < NPOP; ++ip) {
+                double q;
+                if (!link_here(pg, own, c, p, jx, jy, jz, zg, ip, r2, q)) continue;
+                if (pass == 0) { ++mine; continue; }
+                if (w < maxlink) { L.node[w] = (uint32_t)n; L.dir[w] = ip; L.part[w] = p + 1; L.q[w] = q; }
+                ++w;
+            }
+        }
+    }
+    if (!FILL) {
+        sh[threadIdx.x] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long acc = 0;
+            for (int i = 0; i < 256; ++i) acc += sh[i];
+            count[p] = acc;
+        }
+    }
+}
+
+__global__ void k_beads_scan(int npart, const long long *count, long long *offset) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        long long acc = 0;
+        for (int p = 0; p < npart; ++p) { offset[p] = acc; acc += count[p]; }
+        offset[npart] = acc;
+    }
+}
+
+// ---- beads_collision: interpolated bounce-back + momentum exchange ---------------------------------
+// One thread per link, after the step (and after its halo exchange).  Where the three post-collision
+// values live and where the result goes, by storage state:
+//   READ_PULL_NAT  (AB):        f*_i(x) = S[i][x];        result -> S[opp i][x_s]   (x_f pulls it from there)
+//   READ_PULL_SWAP (AA, even):  f*_i(x) = S[opp i][x];    result -> S[i][x_s]
+//   READ_DIRECT    (AA, odd):   f*_i(x) = S[i][x + c_i];  result -> S[opp i][x_f]   (already streamed)
+struct IbbParams {
+    PartGeom pg;
+    double *S;
+    const int32_t *own;
+    Links L;
+    long long nlink;
+    const double *ypglb, *wp, *omgp;
+    double rho0;
+    double *fHIp, *torqp;     // (3,npart), accumulated with atomics
+};
+
+template <int RK>
+__device__ __forceinline__ long long post_addr(const Geom &g, int i, long long n, long long nplus) {
+    // address of f*_i of the node with in-slab index n; nplus = index of that node + c_i
+    if (RK == READ_PULL_NAT) return (long long)i * g.slab + n;
+    if (RK == READ_PULL_SWAP) return (long long)dir_opp(i) * g.slab + n;
+    return (long long)i * g.slab + nplus;
+}
+
+template <int RK>
+__global__ void __launch_bounds__(128) k_beads_ibb(const __grid_constant__ IbbParams P) {
+    const Geom &g = P.pg.g;
+    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double F[6] = {0, 0, 0, 0, 0, 0};
+    int part = 0;
+    if (l < P.nlink) {
+        const uint32_t n = P.L.node[l];
+        const int ip = P.L.dir[l], io = dir_opp(ip);
+        part = P.L.part[l];
+        const int p = part - 1;
+        const double q = P.L.q[l];
+        const int x = (int)(n % (uint32_t)g.xp), y = (int)((n / (uint32_t)g.xp) % (uint32_t)g.ly),
+                  zg = (int)(n / ((uint32_t)g.xp * (uint32_t)g.ly));
+        int cx = 0, cy = 0, cz = 0;
+        static_for<NPOP>([&](auto ic) { constexpr int i = decltype(ic)::value; if (i == ip) { cx = dir_cx(i); cy = dir_cy(i); cz = dir_cz(i); } });
+        const double ww = ip <= 6 ? 1.0 / 18.0 : 1.0 / 36.0;
+        // neighbours along the link: x_s = x_f + c, x_b = x_f - c (periodic y; z through wrap or ghosts)
+        auto wrapz = [&](int z) { return z < 1 ? g.zlo_src : (z > g.lz ? g.zhi_src : z); };
+        auto wrapy = [&](int yy) { return yy < 0 ? g.ly - 1 : (yy >= g.ly ? 0 : yy); };
+        const long long ns = (long long)(x + cx) + (long long)g.xp * (wrapy(y + cy) + (long long)g.ly * wrapz(zg + cz));
+        const bool back_in = (x - cx) >= 0 && (x - cx) < g.lx;
+        const long long nb = back_in ? (long long)(x - cx) + (long long)g.xp * (wrapy(y - cy) + (long long)g.ly * wrapz(zg - cz)) : (long long)n;
+        // wall point relative to the particle centre (nearest image)
+        double c0 = P.ypglb[3 * p], c1 = P.ypglb[3 * p + 1], c2 = P.ypglb[3 * p + 2];
+        const double xf0 = (double)(x + 1) - 0.5, xf1 = (double)(y + 1) - 0.5, xf2 = (double)(zg + P.pg.globalz) - 0.5;
+        if (c1 - xf1 > 0.5 * P.pg.ny) c1 -= P.pg.ny;
+        if (c1 - xf1 < -0.5 * P.pg.ny) c1 += P.pg.ny;
+        if (c2 - xf2 > 0.5 * P.pg.nz) c2 -= P.pg.nz;
+        if (c2 - xf2 < -0.5 * P.pg.nz) c2 += P.pg.nz;
+        const double rx = xf0 + q * cx - c0, ry = xf1 + q * cy - c1, rz = xf2 + q * cz - c2;
+        const double uwx = P.wp[3 * p] + (P.omgp[3 * p + 1] * rz - P.omgp[3 * p + 2] * ry);
+        const double uwy = P.wp[3 * p + 1] + (P.omgp[3 * p + 2] * rx - P.omgp[3 * p] * rz);
+        const double uwz = P.wp[3 * p + 2] + (P.omgp[3 * p] * ry - P.omgp[3 * p + 1] * rx);
+        const double delta = 6.0 * ww * P.rho0 * (-(cx * uwx + cy * uwy + cz * uwz));
+        const double fs_i = P.S[post_addr<RK>(g, ip, n, ns)];                    // f*_i(x_f)
+        double fnew;
+        if (q >= 0.5) {
+            // f*_opp(x_f); at a channel wall behind the node it has bounced back into direction ip
+            double fs_o;
+            if (back_in) fs_o = P.S[post_addr<RK>(g, io, n, nb)];
+            else fs_o = (RK == READ_DIRECT) ? P.S[(long long)ip * g.slab + n] : P.S[post_addr<RK>(g, io, n, n)];
+            const double i2q = 1.0 / (2.0 * q);
+            fnew = i2q * fs_i + (2.0 * q - 1.0) * i2q * fs_o + i2q * delta;
+        } else {
+            const bool have_ff = back_in && P.own[nb] < 0;
+            if (have_ff) fnew = 2.0 * q * fs_i + (1.0 - 2.0 * q) * P.S[post_addr<RK>(g, ip, nb, n)] + delta;   // f*_i(x_f - c_i)
+            else fnew = fs_i + delta;
+        }
+        // where x_f will find f_opp(i) at the next step
+        long long dst;
+        if (RK == READ_PULL_NAT) dst = (long long)io * g.slab + ns;
+        else if (RK == READ_PULL_SWAP) dst = (long long)ip * g.slab + ns;
+        else dst = (long long)io * g.slab + n;
+        P.S[dst] = fnew;
+        const double fin = fs_i + ww * P.rho0, fout = fnew + ww * P.rho0;
+        F[0] = (cx - uwx) * fin - (-cx - uwx) * fout;
+        F[1] = (cy - uwy) * fin - (-cy - uwy) * fout;
+        F[2] = (cz - uwz) * fin - (-cz - uwz) * fout;
+        F[3] = ry * F[2] - rz * F[1];
+        F[4] = rz * F[0] - rx * F[2];
+        F[5] = rx * F[1] - ry * F[0];
+    }
+    // links are ordered by particle: a warp usually serves one particle -> one atomic per component per warp
+    const unsigned full = 0xffffffffu;
+    const int p0 = __shfl_sync(full, part, 0);
+    const bool uniform = __all_sync(full, part == p0 || part == 0);
+    if (uniform) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double v = F[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+            F[k] = v;
+        }
+        const int pw = __reduce_max_sync(full, part);
+        if ((threadIdx.x & 31) == 0 && pw > 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { atomicAdd(P.fHIp + 3 * (pw - 1) + k, F[k]); atomicAdd(P.torqp + 3 * (pw - 1) + k, F[3 + k]); }
+        }
+    } else if (part > 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicAdd(P.fHIp + 3 * (part - 1) + k, F[k]); atomicAdd(P.torqp + 3 * (part - 1) + k, F[3 + k]); }
+    }
+}
+
+// ---- beads_filling: nodes solid before the move and fluid after it ----------------------------------
+struct FillParams {
+    PartGeom pg;
+    double *S;
+    const int32_t *own0, *own;
+    const double *ypglb0;         // positions before the move (their boxes cover every uncovered node)
+    const double *ypglb, *wp, *omgp;
+    unsigned long long *nfilled;
+};
+
+__device__ __forceinline__ void feq19(double rho, double ux, double uy, double uz, double (&fe)[NPOP]) {
+    const double usqr = 1.5 * (ux * ux + uy * uy + uz * uz);
+    static_for<NPOP>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if (i == 0) fe[0] = (1.0 / 3.0) * (rho - usqr);
+        else {
+            const double G = dir_cx(i) * ux + dir_cy(i) * uy + dir_cz(i) * uz;
+            fe[i] = (i <= 6 ? 1.0 / 18.0 : 1.0 / 36.0) * (rho + 3.0 * G + 4.5 * G * G - usqr);
+        }
+    });
+}
+
+template <int RK>
+__global__ void __launch_bounds__(128) k_beads_fill(const __grid_constant__ FillParams P) {
+    const PartGeom &pg = P.pg;
+    const Geom &g = pg.g;
+    const int p = blockIdx.x;
+    const BBox b = part_bbox(pg, P.ypglb0 + 3 * p);
+    const long long nbox = (long long)b.n[0] * b.n[1] * b.n[2];
+    for (long long t = threadIdx.x; t < nbox; t += blockDim.x) {
+        const int jx = b.lo[0] + (int)(t % b.n[0]);
+        const int jy = b.lo[1] + (int)((t / b.n[0]) % b.n[1]);
+        const int jz = b.lo[2] + (int)(t / ((long long)b.n[0] * b.n[1]));
+        const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
+        const int zg = iz - pg.globalz;
+        if (zg < 1 || zg > g.lz) continue;
+        const int x = jx - 1, y = iy - 1;
+        const long long n = (long long)x + (long long)g.xp * (y + (long long)g.ly * zg);
+        if (!(P.own0[n] == p + 1 && P.own[n] < 0)) continue;
+        // surface velocity of the particle that uncovered the node, at the node (state after the move)
+        double c0 = P.ypglb[3 * p], c1 = P.ypglb[3 * p + 1], c2 = P.ypglb[3 * p + 2];
+        const double xf0 = (double)jx - 0.5, xf1 = (double)iy - 0.5, xf2 = (double)iz - 0.5;
+        if (c1 - xf1 > 0.5 * pg.ny) c1 -= pg.ny;
+        if (c1 - xf1 < -0.5 * pg.ny) c1 += pg.ny;
+        if (c2 - xf2 > 0.5 * pg.nz) c2 -= pg.nz;
+        if (c2 - xf2 < -0.5 * pg.nz) c2 += pg.nz;
+        const double rx = xf0 - c0, ry = xf1 - c1, rz = xf2 - c2;
+        const double uwx = P.wp[3 * p] + (P.omgp[3 * p + 1] * rz - P.omgp[3 * p + 2] * ry);
+        const double uwy = P.wp[3 * p + 1] + (P.omgp[3 * p + 2] * rx - P.omgp[3 * p] * rz);
+        const double uwz = P.wp[3 * p + 2] + (P.omgp[3 * p] * ry - P.omgp[3 * p + 1] * rx);
+        double rsum = 0.0, best = -2.0;
+        int nn = 0, jbest = 0;
+        double fbest[NPOP];
+        for (int ip = 1; ip < NPOP; ++ip) {
+            int cx = 0, cy = 0, cz = 0;
+            static_for<NPOP>([&](auto ic) { constexpr int i = decltype(ic)::value; if (i == ip) { cx = dir_cx(i); cy = dir_cy(i); cz = dir_cz(i); } });
+            const int kx = x + cx;
+            if (kx < 0 || kx >= g.lx) continue;
+            const int ky = (y + cy < 0) ? g.ly - 1 : (y + cy >= g.ly ? 0 : y + cy);
+            int kz = zg + cz;
+            if (g.zlo_src != 0) kz = kz < 1 ? g.lz : (kz > g.lz ? 1 : kz);       // single slab: periodic wrap
+            else if (kz < 1 || kz > g.lz) continue;                                // neighbours in a ghost plane are not sources
+            const long long m = (long long)kx + (long long)g.xp * (ky + (long long)g.ly * kz);
+            if (P.own0[m] > 0 || P.own[m] > 0) continue;
+            const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, kx, ky, kz);
+            double fm[NPOP];
+            gather19<RK>(P.S, g, k, fm);
+            double r = 0.0;
+#pragma unroll
+            for (int i = 0; i < NPOP; ++i) r += fm[i];
+            rsum += r; ++nn;
+            const double cn = (cx * rx + cy * ry + cz * rz) / sqrt((double)(cx * cx + cy * cy + cz * cz));
+            if (cn > best) {
+                best = cn; jbest = ip;
+#pragma unroll
+                for (int i = 0; i < NPOP; ++i) fbest[i] = fm[i];
+            }
+        }
+        const double rbar = nn ? rsum / (double)nn : 0.0;
+        double out[NPOP];
+        feq19(rbar, uwx, uwy, uwz, out);
+        if (jbest) {
+            double r = 0.0, jx_ = 0.0, jy_ = 0.0, jz_ = 0.0, fe2[NPOP];
+            static_for<NPOP>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                r += fbest[i]; jx_ += dir_cx(i) * fbest[i]; jy_ += dir_cy(i) * fbest[i]; jz_ += dir_cz(i) * fbest[i];
+            });
+            feq19(r, jx_, jy_, jz_, fe2);
+#pragma unroll
+            for (int i = 0; i < NPOP; ++i) out[i] += fbest[i] - fe2[i];
+        }
+        // write each population where this node will read it from
+        const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, y, zg);
+        static_for<NPOP>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            P.S[Gather<RK, i>::offset(g, k)] = out[i];
+        });
+        atomicAdd(P.nfilled, 1ull);
+    }
+}
+
+// ---- beads_lubforce / beads_move: npart threads ------------------------------------------------------
+struct LubParams { double mingap, mingap_w, stf0, stf1, stf0_w, stf1_w, fscale; };
+
+__global__ void k_beads_lubforce(PartGeom pg, int npart, const double *ypglb, LubParams lp, double *flubp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npart) return;
+    const double *a = ypglb + 3 * i;
+    const double Rr = pg.rad;
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    for (int j = 0; j < npart; ++j) {
+        if (j == i) continue;
+        const double *b = ypglb + 3 * j;
+        double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+        if (dy > 0.5 * pg.ny) dy -= pg.ny;
+        if (dy < -0.5 * pg.ny) dy += pg.ny;
+        if (dz > 0.5 * pg.nz) dz -= pg.nz;
+        if (dz < -0.5 * pg.nz) dz += pg.nz;
+        const double d = sqrt(dx * dx + dy * dy + dz * dz);
+        const double gap = d - 2.0 * Rr;
+        if (gap >= lp.mingap || d == 0.0) continue;
+        double mag = lp.fscale / lp.stf0 * ((gap - lp.mingap) / lp.mingap) * ((gap - lp.mingap) / lp.mingap);
+        if (gap < 0.0) mag += lp.fscale / lp.stf1 * (-gap / lp.mingap);
+        f0 += mag * dx / d; f1 += mag * dy / d; f2 += mag * dz / d;
+    }
+    for (int s = 0; s < 2; ++s) {
+        const double dxw = s == 0 ? a[0] : a[0] - (double)pg.nx;
+        const double gap = fabs(dxw) - Rr;
+        if (gap >= lp.mingap_w) continue;
+        double mag = lp.fscale / lp.stf0_w * ((gap - lp.mingap_w) / lp.mingap_w) * ((gap - lp.mingap_w) / lp.mingap_w);
+        if (gap < 0.0) mag += lp.fscale / lp.stf1_w * (-gap / lp.mingap_w);
+        f0 += (dxw >= 0.0 ? mag : -mag);
+    }
+    flubp[3 * i] = f0; flubp[3 * i + 1] = f1; flubp[3 * i + 2] = f2;
+}
+
+struct MoveParams {
+    double amp, aip;
+    double g0, g1, g2;
+    const double *fHIp, *torqp, *flubp;
+    double *forcepp, *torqpp, *ypglb, *ypglb0, *wp, *omgp, *thetap;
+};
+
+__global__ void k_beads_move(PartGeom pg, int npart, MoveParams M) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npart) return;
+    const double gf[3] = {M.g0, M.g1, M.g2};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int k = 3 * p + d;
+        const double F = 0.5 * (M.fHIp[k] + M.forcepp[k]) + M.flubp[k] + gf[d];
+        const double T = 0.5 * (M.torqp[k] + M.torqpp[k]);
+        const double wnew = M.wp[k] + F / M.amp;
+        const double onew = M.omgp[k] + T / M.aip;
+        M.ypglb0[k] = M.ypglb[k];
+        M.ypglb[k] += 0.5 * (M.wp[k] + wnew);
+        M.thetap[k] += 0.5 * (M.omgp[k] + onew);
+        M.wp[k] = wnew; M.omgp[k] = onew;
+        M.forcepp[k] = M.fHIp[k]; M.torqpp[k] = M.torqp[k];
+    }
+    double *c = M.ypglb + 3 * p;
+    if (c[1] >= (double)pg.ny) c[1] -= pg.ny;
+    if (c[1] < 0.0) c[1] += pg.ny;
+    if (c[2] >= (double)pg.nz) c[2] -= pg.nz;
+    if (c[2] < 0.0) c[2] += pg.nz;
+}
+
+// link list -> host-friendly (global 1-based node coordinates)
+__global__ void k_links_export(Geom g, int globalz, long long nlink, Links L, int32_t *ox, int32_t *oy, int32_t *oz) {
+    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlink) return;
+    const uint32_t n = L.node[l];
+    ox[l] = (int)(n % (uint32_t)g.xp) + 1;
+    oy[l] = (int)((n / (uint32_t)g.xp) % (uint32_t)g.ly) + 1;
+    oz[l] = (int)(n / ((uint32_t)g.xp * (uint32_t)g.ly)) + globalz;
+}
+
+}  // namespace d3q

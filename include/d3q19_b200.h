@@ -99,6 +99,17 @@ const char *d3q19_last_error(void);
 int d3q19_nccl_unique_id(unsigned char out[128]);
 int d3q19_device_count(int32_t *n);
 
+/* ---- halo in NVLink peer memory (optional, nranks > 1) ----------------------------------------
+ * Replaces the MPI_ISEND/IRECV/WAITALL ghost exchange (collision.f90:349-356) inside the step:
+ * the boundary planes store their five outgoing populations straight into the neighbour GPU's
+ * array and raise a flag there.  Bootstrap: every rank exports a blob of
+ * D3Q19_IPC_BYTES, the caller all-gathers them (MPI_ALLGATHER in the Fortran shim,
+ * torch.distributed in Python) and hands the nranks blobs, in rank order, to d3q19_ipc_connect.
+ * Collective: every rank must call both.  Without it the exchange goes through NCCL send/recv. */
+#define D3Q19_IPC_BYTES 256
+int d3q19_ipc_export(d3q19_handle *h, unsigned char *blob);
+int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs_in_rank_order);
+
 /* ---- state transfer (canonical AoS layout, see above) --------------------------------- */
 int d3q19_upload_f(d3q19_handle *h, const double *f_aos);
 int d3q19_download_f(d3q19_handle *h, double *f_aos);
@@ -139,6 +150,35 @@ int d3q19_prerelax(d3q19_handle *h, double tol, int32_t maxiter, int32_t *iters,
 /* ---- particles (ibnodes / isnodes, var_inc.f90:113-114) -------------------------------- */
 int d3q19_set_solid_mask(d3q19_handle *h, const int32_t *ibnodes_ghosted, const int32_t *isnodes);
 int d3q19_set_particles(d3q19_handle *h, int32_t npart, const double *ypglb, const double *wp, const double *omgp);
+
+/* Device-side particle bookkeeping.  The reference snapshot does not contain its particle library
+ * (main.f90:64 names partlib.f90), so these follow the published algorithms its
+ * data structures point to and are "parity unpinned" (DESIGN.md section 8).  Entry points carry the
+ * names of the reference's per-phase timers (var_inc.f90:166-168).                           */
+typedef struct d3q19_particle_params {
+    double rad;                 /* var_inc.f90:67                                            */
+    double rho0;                /* var_inc.f90:65: density in the moving-wall / force terms  */
+    double mingap, mingap_w;    /* var_inc.f90:67                                            */
+    double stf0, stf1, stf0_w, stf1_w;   /* para.f90:356-360                                 */
+    double fscale;              /* force scale of the repulsion (0 = off)                    */
+    double gforce[3];           /* constant body force on each particle (gravity - buoyancy) */
+    int64_t maxlink;            /* link capacity; 0 = 8 npart 4 pi (rad+1)^2 (cf. para.f90:371) */
+} d3q19_particle_params;
+int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_particle_params *prm);
+/* solid mask (ibnodes/isnodes, ghost planes included) and boundary links from the particle table */
+int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local);
+/* interpolated bounce-back on every link after a collide_stream; force and torque reduced over ranks */
+int d3q19_beads_collision(d3q19_handle *h);
+int d3q19_beads_lubforce(d3q19_handle *h);
+int d3q19_beads_move(d3q19_handle *h);
+/* refill of the nodes uncovered by the last move (after d3q19_beads_links rebuilt the mask)  */
+int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled_local);
+/* links (if stale); collide_stream; beads_collision; [lubforce; move; links; filling]         */
+int d3q19_particle_step(d3q19_handle *h, int32_t move);
+int d3q19_get_particles(d3q19_handle *h, double *ypglb, double *wp, double *omgp, double *fHIp, double *torqp);
+int d3q19_get_links(d3q19_handle *h, int64_t capacity, int32_t *x, int32_t *y, int32_t *z, int32_t *ip,
+                    int32_t *part, double *q, int64_t *nlink);
+int d3q19_get_mask(d3q19_handle *h, int32_t *own_lx_ly_lz);
 
 /* ---- device-side statistics ------------------------------------ */
 /* per-x-plane sums over the local (y,z) of ux,uy,uz,ux^2,uy^2,uz^2,uxuy,uxuz,uyuz,rho,rho^2

@@ -43,11 +43,20 @@ def main():
         dist.broadcast(idt, src=0)
         return bytes(idt.tolist())
 
-    cases = [((24, 6, 4 * world), True), ((33, 5, 3 * world + 1), True), ((16, 4, world), True),
-             ((24, 6, 4 * world), False), ((40, 3, 2 * world), True)]
+    def allgather_bytes(b):
+        t = torch.tensor(list(b), dtype=torch.uint8)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [bytes(o.tolist()) for o in out]
+
+    # (size, overlap, halo): halo = "peer" stores the faces straight into the neighbour GPU's memory
+    cases = [((24, 6, 4 * world), True, "nccl"), ((33, 5, 3 * world + 1), True, "nccl"), ((16, 4, world), True, "nccl"),
+             ((24, 6, 4 * world), False, "nccl"), ((40, 3, 2 * world), True, "nccl"),
+             ((24, 6, 4 * world), True, "peer"), ((33, 5, 3 * world + 1), True, "peer"), ((40, 3, 2 * world), True, "peer"),
+             ((130, 7, 2 * world + 1), True, "peer")]
     for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
-        for (nx, ny, nz), overlap in cases:
-            ctx[0] = "scheme %d case %s overlap %s" % (scheme, (nx, ny, nz), overlap)
+        for (nx, ny, nz), overlap, halo in cases:
+            ctx[0] = "scheme %d case %s overlap %s halo %s" % (scheme, (nx, ny, nz), overlap, halo)
             w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
             rng = np.random.default_rng(7)
             w.set_f(w.get_f() + 1e-4 * rng.normal(size=(nz, ny, nx, 19)))
@@ -55,6 +64,8 @@ def main():
                                   math_mode=capi.MATH_STRICT, nccl_id=new_id(), overlap=overlap)
             z0, z1 = sim.globalz, sim.globalz + sim.lz
             sim.FORCING()
+            if halo == "peer":
+                sim.connect_halo(allgather_bytes)
             sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
             w.macrovar()
             out = np.empty((sim.lz, ny, nx, 19))
