@@ -146,6 +146,16 @@
           import :: c_int, c_ptr
           type(c_ptr), value :: h
         end function
+        integer(c_int) function d3q19_ipc_export(h, blob) bind(c, name='d3q19_ipc_export')
+          import :: c_int, c_ptr, c_signed_char
+          type(c_ptr), value :: h
+          integer(c_signed_char), intent(out) :: blob(256)
+        end function
+        integer(c_int) function d3q19_ipc_connect(h, blobs) bind(c, name='d3q19_ipc_connect')
+          import :: c_int, c_ptr, c_signed_char
+          type(c_ptr), value :: h
+          integer(c_signed_char), intent(in) :: blobs(*)
+        end function
         integer(c_size_t) function c_strlen(s) bind(c, name='strlen')
           import :: c_size_t, c_ptr
           type(c_ptr), value :: s
@@ -179,6 +189,8 @@
       type(d3q19_shim_arrays) :: a
       integer(c_int32_t) :: ndev
       integer :: ierr_
+      integer(c_signed_char) :: ipc_mine(256)
+      integer(c_signed_char), allocatable :: ipc_all(:)
       if (bound) return
       if (nprocY /= 1) then
         if (myid == 0) write(*,*) 'd3q19_b200: set nprocY = 1 in para.f90:219 (z-slab decomposition, one rank per GPU)'
@@ -209,6 +221,16 @@
         call MPI_BCAST(cfg%nccl_id, 128, MPI_BYTE, 0, MPI_COMM_WORLD, ierr_)
       endif
       call d3q19_b200_check(d3q19_create(cfg, handle), 'd3q19_create')
+      if (nprocZ > 1 .and. .not. ipart .and. lz >= 2) then
+        ! halo in NVLink peer memory: every rank exports its cudaIpc handles, MPI_ALLGATHER replaces
+        ! nothing in the reference -- it is the bootstrap of what replaces MPI_ISEND/IRECV/WAITALL
+        ! (collision.f90:349-356) inside the step kernel
+        allocate(ipc_all(256*nproc))
+        call d3q19_b200_check(d3q19_ipc_export(handle, ipc_mine), 'd3q19_ipc_export')
+        call MPI_ALLGATHER(ipc_mine, 256, MPI_BYTE, ipc_all, 256, MPI_BYTE, MPI_COMM_WORLD, ierr_)
+        call d3q19_b200_check(d3q19_ipc_connect(handle, ipc_all), 'd3q19_ipc_connect')
+        deallocate(ipc_all)
+      endif
 
       a%f = c_loc(f)
       a%rho = c_loc(rho);  a%ux = c_loc(ux);  a%uy = c_loc(uy);  a%uz = c_loc(uz)
