@@ -55,6 +55,10 @@ def parse_args():
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="z-face exchange: stores into the neighbour GPU's memory over NVLink (default) or NCCL send/recv")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--particles", type=int, default=0,
+                    help="configs[4]: N finite-size spheres (interpolated bounce-back, refill, momentum-exchange force); "
+                         "a step is then links + collide-stream + IBB + lubrication + move + refill")
+    ap.add_argument("--rad", type=float, default=15.0, help="sphere radius (var_inc.f90:67)")
     ap.add_argument("--device-init", action="store_true",
                     help="initvel+initpop on the device (implied by c4: the field does not fit a host staging copy)")
     return ap.parse_args()
@@ -236,7 +240,10 @@ def main():
     scheme = {"aa": capi.SCHEME_AA, "ab": capi.SCHEME_AB, "auto": capi.SCHEME_AUTO}[args.scheme]
     math_mode = capi.MATH_FAST if args.math == "fast" else capi.MATH_STRICT
     sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local_rank, scheme=scheme,
-                          math_mode=math_mode, nccl_id=nccl_id, overlap=not args.no_overlap, allocate_host=False)
+                          math_mode=math_mode, nccl_id=nccl_id, overlap=not args.no_overlap, allocate_host=False,
+                          ipart=args.particles > 0)
+    if args.particles > 0:
+        args.halo = "nccl"              # the particle path keeps its halo on NCCL
     halo = "none"
     if world > 1:
         halo = "nccl"
@@ -265,17 +272,36 @@ def main():
         sim.initpop()
         sim.upload_f()
 
+    if args.particles > 0:
+        # spheres on a regular lattice with more than mingap clearance, released from rest
+        pitch = 2.0 * args.rad + 8.0
+        slots = [(pitch * (i + 0.5) + 2.0, pitch * (j + 0.5), pitch * (k + 0.5))
+                 for k in range(int(nz // pitch)) for j in range(int(ny // pitch)) for i in range(int((nx - 4) // pitch))]
+        if len(slots) < args.particles:
+            raise SystemExit("bench: %d spheres of radius %g do not fit %dx%dx%d" % (args.particles, args.rad, nx, ny, nz))
+        stride = len(slots) / float(args.particles)
+        pos = np.array([slots[int(i * stride)] for i in range(args.particles)], dtype=np.float64)
+        sim.particles_init(pos, args.rad)
+        do_e2e = False
+
+    def advance(n):
+        if args.particles > 0:
+            for _ in range(n):
+                sim.particle_step(move=True)
+        else:
+            sim.run_device(n)
+
     # ---- device-timed value -------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                 # nvidia-smi needs ~0.1 s to deliver its first sample: start before the warm-up
-    sim.run_device(args.warmup)
+    advance(args.warmup)
     sim.sync()
     c0 = sim.counters()
     barrier(); sim.sync()
     sampler.mark()
     sim.timer_start()
-    sim.run_device(args.steps)
+    advance(args.steps)
     ms = sim.timer_stop()
     sim.sync(); barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -345,6 +371,8 @@ def main():
             "config": {"workload": "D3Q19 MRT channel %dx%dx%d (nx x ny x nz, x wall-normal), turbulent set Re_tau=180, "
                                    "uniform body force, half-way bounce-back walls" % (nx, ny, nz),
                        "per_gpu": "%dx%dx%d z-slab" % (nx, ny, sim.lz), "scheme": args.scheme, "math": args.math,
+                       "particles": ("%d moving spheres of radius %g: links, interpolated bounce-back, momentum-exchange force, "
+                                     "lubrication, move, refill every step" % (args.particles, args.rad)) if args.particles else "none",
                        "parallelism": ("z-slab x%d, faces %s" % (world, "stored into the neighbour GPU's memory over NVLink "
                                        "inside the step kernel" if halo == "peer" else "by NCCL send/recv")) if world > 1 else "1 GPU",
                        "l2": "populations %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (c1["population_bytes"] / 1e9)},

@@ -134,6 +134,62 @@ def main():
         chk("f after prerelax", bool(np.array_equal(sim.f, w.get_f()[z0:z1])))
         sim.close()
 
+    # particle path across slab faces: links partition exactly, IBB + forces as on one domain
+    if ok:
+        from oracle import particles as P
+        nx, ny, nz, rad = 24, 20, 8 * world, 3.6
+        U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+        pos = [[11.7, 1.2, 8.0 * world - 0.9], [8.3, 12.0, 8.1], [15.5, 8.4, 4.2]]      # two of them cut by slab faces
+        vel = [[0.010, 0.020, -0.010], [0.0, 0.015, 0.0], [-0.005, 0.0, 0.012]]
+        omg = [[1e-3, 0.0, 2e-3], [0.0, -1e-3, 0.0], [5e-4, 5e-4, 0.0]]
+        for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
+            ctx[0] = "particles scheme %d" % scheme
+            w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True, ipart=1, **U)
+            pt = P.Particles(nx, ny, nz, rad, pos, vel, omg)
+            pt.build_mask(); pt.build_links()
+            w.set_solid(np.where(pt.own > 0, 1, -1).astype(np.int32), pt.own)
+            w.set_particles(pt.ypglb, pt.wp, pt.omgp)
+            sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local, scheme=scheme,
+                                  nccl_id=new_id(), ipart=True, **U)
+            z0, z1 = sim.globalz, sim.globalz + sim.lz
+            sim.FORCING()
+            sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
+            sim.particles_init(pos, rad, vel, omg)
+            nl = sim.beads_links()
+            tot = torch.tensor([nl]); dist.all_reduce(tot)
+            chk("link count %d vs %d" % (int(tot.item()), len(pt.links["q"])), int(tot.item()) == len(pt.links["q"]))
+            chk("mask", bool(np.array_equal(sim.get_mask(), pt.own[z0:z1])))
+            gl = sim.get_links()
+            mine = (pt.links["z"] > z0) & (pt.links["z"] <= z1)        # the oracle's links whose fluid node I own, in order
+            for key in ("x", "y", "z", "ip", "part"):
+                chk("links " + key, bool(np.array_equal(gl[key], pt.links[key][mine])))
+            chk("links q", bool(np.array_equal(gl["q"], pt.links["q"][mine])))
+            w.macrovar()
+            out = np.empty((sim.lz, ny, nx, 19))
+            for step in range(4):
+                w.collision_MRT()
+                f = w.get_f(); pt.ibb(f); w.set_f(f); w.macrovar()
+                sim.particle_step(move=False)
+                sim.download_f(out)
+                fluid = pt.own[z0:z1] < 0
+                err = np.max(np.abs(out[fluid] - f[z0:z1][fluid])) / np.max(np.abs(f))
+                chk("ibb step %d err %g" % (step, err), bool(err < 1e-12))
+                g = sim.get_particles()
+                ferr = np.max(np.abs(g["fHIp"] - pt.fHIp)) / np.max(np.abs(pt.fHIp))
+                chk("force step %d err %g" % (step, ferr), bool(ferr < 1e-10))
+            for step in range(3):                                   # moving: positions, mask and forces stay together
+                w.collision_MRT()
+                f = w.get_f(); pt.ibb(f); pt.lubforce(); pt.move(); pt.build_mask(); pt.build_links(); pt.refill(f)
+                w.set_f(f); w.set_solid(np.where(pt.own > 0, 1, -1).astype(np.int32), pt.own)
+                w.set_particles(pt.ypglb, pt.wp, pt.omgp); w.macrovar()
+                sim.particle_step(move=True)
+                g = sim.get_particles()
+                chk("moving positions %d" % step, bool(np.max(np.abs(g["ypglb"] - pt.ypglb)) < 1e-9))
+                chk("moving mask %d" % step, bool(np.array_equal(sim.get_mask(), pt.own[z0:z1])))
+                ferr = np.max(np.abs(g["fHIp"] - pt.fHIp)) / np.max(np.abs(pt.fHIp))
+                chk("moving force %d err %g" % (step, ferr), bool(ferr < 1e-6))   # refills next to a face may pick another source
+            sim.close(); w.close()
+
     t = torch.tensor([1 if ok else 0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
