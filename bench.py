@@ -323,11 +323,13 @@ def main():
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     nodes_local = nx * ny * sim.lz
     achieved = BYTES_PER_NODE * nodes_local / (ms * 1e-3 / args.steps) / 1e9
+    # DRAM bytes per launch of the same kernel at the same per-GPU size from the committed ncu --set full
+    # capture (profiles/traffic.json, made by tools/summarize_ncu.py); null when that size was not captured
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("%s_%dx%dx%d" % (args.scheme, nx, ny, sim.lz))
+            traffic = json.load(open(tp)).get("%s_%dx%dx%d" % (args.scheme, nx, ny, sim.lz), {}).get("gb_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -338,6 +340,7 @@ def main():
     e2e = None
     if do_e2e:
         sim.v.nsteps = args.steps
+        sim.set_schedule()
         sim.host_f_changed()                       # host f is the initial state again -> upload inside the timed region
         sim.initpop()
         barrier(); sim.sync()

@@ -24,11 +24,11 @@ SYMBOLS = [
     "d3q19_ipc_export", "d3q19_ipc_connect", "d3q19_upload_f", "d3q19_download_f", "d3q19_set_macro", "d3q19_download_macro",
     "d3q19_init_channel", "d3q19_set_force_uniform", "d3q19_set_force_field",
     "d3q19_collide_stream", "d3q19_run", "d3q19_macrovar", "d3q19_rhoupdat", "d3q19_avedensity", "d3q19_probe",
-    "d3q19_prerelax", "d3q19_set_solid_mask", "d3q19_set_particles", "d3q19_profiles",
+    "d3q19_prerelax", "d3q19_set_solid_mask", "d3q19_set_particles", "d3q19_profiles", "d3q19_diag",
     "d3q19_particles_init", "d3q19_beads_links", "d3q19_beads_collision", "d3q19_beads_lubforce", "d3q19_beads_move",
     "d3q19_beads_filling", "d3q19_particle_step", "d3q19_get_particles", "d3q19_get_links", "d3q19_get_mask",
     "d3q19_timer_start", "d3q19_timer_stop", "d3q19_get_counters",
-    "d3q19_shim_bind", "d3q19_shim_set_schedule", "d3q19_shim_forcing", "d3q19_shim_rhoupdat", "d3q19_shim_collision_mrt",
+    "d3q19_shim_bind", "d3q19_shim_bind_arrays", "d3q19_shim_set_schedule", "d3q19_shim_forcing", "d3q19_shim_rhoupdat", "d3q19_shim_collision_mrt",
     "d3q19_shim_prerelax_state",
     "d3q19_shim_macrovar", "d3q19_shim_avedensity", "d3q19_shim_sync_f_to_host", "d3q19_shim_sync_f_to_device",
 ]
@@ -118,6 +118,7 @@ def load():
     L.d3q19_set_solid_mask.argtypes = [vp, ip, ip]
     L.d3q19_set_particles.argtypes = [vp, C.c_int32, dp, dp, dp]
     L.d3q19_profiles.argtypes = [vp, dp]
+    L.d3q19_diag.argtypes = [vp, C.c_double, dp]
     i64p = C.POINTER(C.c_int64)
     L.d3q19_particles_init.argtypes = [vp, C.c_int32, C.POINTER(ParticleParams)]
     L.d3q19_beads_links.argtypes = [vp, i64p]
@@ -133,6 +134,7 @@ def load():
     L.d3q19_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.d3q19_get_counters.argtypes = [vp, C.POINTER(C.c_int64)]
     L.d3q19_shim_bind.argtypes = [vp, C.POINTER(ShimArrays)]
+    L.d3q19_shim_bind_arrays.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip] + [C.c_int32] * 7 + [C.c_double]
     L.d3q19_shim_set_schedule.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     L.d3q19_shim_forcing.argtypes = [vp, C.c_double, C.c_double]
     L.d3q19_shim_rhoupdat.argtypes = [vp]

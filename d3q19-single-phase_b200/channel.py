@@ -282,6 +282,17 @@ class ChannelFlow:
         capi.check(self.L.d3q19_probe(self.h, ix, iy, iz, capi.dptr(out)))
         return out
 
+    def diag(self):
+        """saveload.f90:1507-1676 on the device; returns the fields of a diag.dat line."""
+        out = np.zeros(14)
+        capi.check(self.L.d3q19_diag(self.h, self.v.ustar, capi.dptr(out)))
+        keys = ("vmax", "imout", "jmout", "kmout", "umean", "vmean", "wmean", "urms", "vrms", "wrms", "volf", "rhomax",
+                "rhomin", "nfluid")
+        d = dict(zip(keys, out))
+        for k in ("imout", "jmout", "kmout", "nfluid"):
+            d[k] = int(d[k])
+        return d
+
     def profiles(self):
         out = np.zeros((11, self.lx))
         capi.check(self.L.d3q19_profiles(self.h, capi.dptr(out)))
@@ -313,12 +324,17 @@ class ChannelFlow:
         capi.check(self.L.d3q19_download_f(self.h, capi.dptr(self.f)))
         return it.value, err.value
 
+    def set_schedule(self):
+        """tell the shim the loop bounds / output cadence the download policy keys on (main.f90:142,171,184)"""
+        v = self.v
+        capi.check(self.L.d3q19_shim_set_schedule(self.h, v.ndiag, v.nflowout, v.nsteps, v.istep0))
+
     # ---- main.f90:142-208 -------------------------------------------------------------------
     def run(self, nsteps=None, on_step=None):
         v = self.v
         nsteps = v.nsteps if nsteps is None else nsteps
         v.nsteps = nsteps
-        capi.check(self.L.d3q19_shim_set_schedule(self.h, v.ndiag, v.nflowout, nsteps, v.istep0))
+        self.set_schedule()
         for self.istep in range(v.istep0 + 1, v.istep0 + nsteps + 1):
             self.collision_MRT()
             self.macrovar()

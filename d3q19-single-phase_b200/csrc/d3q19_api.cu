@@ -1173,6 +1173,85 @@ extern "C" int d3q19_profiles(d3q19_handle *h, double *out) {
     return 0;
 }
 
+// ---- diag (saveload.f90:1507-1676) on the device ------------------------------------------------------------------------
+// out[14]: vmax, imout, jmout, kmout (global 1-based), umean, vmean, wmean, urms, vrms, wrms (all / ustar),
+//          volf, rhomax, rhomin, nfluid -- what the reference writes to diag.dat (format 260).
+extern "C" int d3q19_diag(d3q19_handle *h, double ustar, double *out14) {
+    CK(cudaSetDevice(h->cfg.device));
+    const Geom &g = h->g;
+    RK_(wait_exchange(h));
+    const long long nrows = (long long)g.ly * g.lz;
+    int chunks = 296;
+    if (chunks > nrows) chunks = (int)nrows;
+    const int rows = (int)((nrows + chunks - 1) / chunks);
+    chunks = (int)((nrows + rows - 1) / rows);
+    const dim3 gr((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)chunks);
+    const int npartial = (int)(gr.x * gr.y);
+    double *partial = nullptr;
+    CK(cudaMalloc(&partial, ((size_t)npartial + 1) * NDIAG * sizeof(double)));
+    double *res = partial + (size_t)npartial * NDIAG;
+    switch (read_kind(h)) {
+    case READ_DIRECT: k_diag<READ_DIRECT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, rows, partial); break;
+    case READ_PULL_NAT: k_diag<READ_PULL_NAT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, rows, partial); break;
+    default: k_diag<READ_PULL_SWAP><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, rows, partial); break;
+    }
+    k_diag_final<<<1, 32, 0, h->sc>>>(npartial, partial, res);
+    CK(cudaGetLastError());
+    h->n_other_kernels += 2;
+    double loc[NDIAG];
+    CK(cudaMemcpyAsync(loc, res, sizeof loc, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    cudaFree(partial);
+    // this rank's maximum in global coordinates (saveload.f90:1566-1574)
+    double mine[4] = {loc[7], 0, 0, 0};
+    if (loc[8] >= 0.0) {
+        const long long li = (long long)loc[8];
+        mine[1] = (double)(li % g.lx + 1);
+        mine[2] = (double)((li / g.lx) % g.ly + 1);
+        mine[3] = (double)(li / ((long long)g.lx * g.ly) + 1 + h->cfg.globalz);
+    }
+    double sums[7] = {loc[0], loc[1], loc[2], loc[3], loc[4], loc[5], loc[6]};
+    double rmax = loc[9], rmin = loc[10];
+    std::vector<double> all((size_t)4 * h->cfg.nranks, 0.0);
+    if (h->cfg.nranks > 1) {
+        // MPI_ALLREDUCE of the sums, the per-rank maxima and rho extrema (saveload.f90:1544-1551,1582-1586,1617-1622)
+        const int nr = h->cfg.nranks;
+        double *d = nullptr;
+        CK(cudaMalloc(&d, (size_t)(9 + 4 + 4 * nr) * sizeof(double)));
+        double pack[13] = {sums[0], sums[1], sums[2], sums[3], sums[4], sums[5], sums[6], rmax, -rmin, mine[0], mine[1], mine[2], mine[3]};
+        CK(cudaMemcpyAsync(d, pack, sizeof pack, cudaMemcpyHostToDevice, h->sc));
+        NcclApi &n = nccl_api();
+        NK(n.GroupStart());
+        NK(n.AllReduce(d, d, 7, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
+        NK(n.AllReduce(d + 7, d + 7, 2, NCCL_FLOAT64, NCCL_MAX, h->comm, h->sc));
+        NK(n.AllGather(d + 9, d + 13, 4, NCCL_FLOAT64, h->comm, h->sc));
+        NK(n.GroupEnd());
+        h->n_nccl += 3;
+        CK(cudaMemcpyAsync(pack, d, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
+        CK(cudaMemcpyAsync(all.data(), d + 13, (size_t)4 * nr * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
+        CK(cudaStreamSynchronize(h->sc));
+        cudaFree(d);
+        for (int q = 0; q < 7; ++q) sums[q] = pack[q];
+        rmax = pack[7]; rmin = -pack[8];
+    } else {
+        for (int q = 0; q < 4; ++q) all[q] = mine[q];
+    }
+    double vmax = 0.0, im = 0, jm = 0, km = 0;
+    for (int r = 0; r < h->cfg.nranks; ++r)                       // first rank with a strictly larger value (saveload.f90:1649-1656)
+        if (all[4 * r] > vmax) { vmax = all[4 * r]; im = all[4 * r + 1]; jm = all[4 * r + 2]; km = all[4 * r + 3]; }
+    const double nf = sums[0];
+    if (nf <= 0.0) return fail("d3q19_diag: no fluid nodes");
+    const double um = sums[1] / nf, vm = sums[2] / nf, wm = sums[3] / nf;
+    out14[0] = vmax; out14[1] = im; out14[2] = jm; out14[3] = km;
+    out14[4] = um / ustar; out14[5] = vm / ustar; out14[6] = wm / ustar;
+    out14[7] = sqrt(sums[4] / nf - um * um) / ustar;
+    out14[8] = sqrt(sums[5] / nf - vm * vm) / ustar;
+    out14[9] = sqrt(sums[6] / nf - wm * wm) / ustar;
+    out14[10] = 1.0 - nf / ((double)h->cfg.nx * h->cfg.ny * h->cfg.nz);
+    out14[11] = rmax; out14[12] = rmin; out14[13] = nf;
+    return 0;
+}
+
 // ---- measurement ---------------------------------------------------------------------------------------------------
 extern "C" int d3q19_timer_start(d3q19_handle *h) {
     CK(cudaSetDevice(h->cfg.device));
@@ -1213,6 +1292,23 @@ extern "C" int d3q19_shim_bind(d3q19_handle *h, const d3q19_shim_arrays *a) {
     h->shim.prerelax_err = 0.0;
     if (h->shim.a.prerelax_maxiter <= 0) h->shim.a.prerelax_maxiter = 15000;   // main.f90:85
     return 0;
+}
+
+// the same binding with the arrays as plain by-reference arguments: what a Fortran caller passes
+// without C_LOC (var_inc's arrays have no TARGET attribute)
+extern "C" int d3q19_shim_bind_arrays(d3q19_handle *h, double *f, double *rho, double *ux, double *uy, double *uz,
+                                      double *force_realx, double *force_realy, double *force_realz, int32_t *ibnodes,
+                                      int32_t *isnodes, int32_t has_isnodes, int32_t ndiag, int32_t nflowout,
+                                      int32_t nsteps_total, int32_t istep0, int32_t ntime, int32_t prerelax_maxiter,
+                                      double rhoepsl) {
+    d3q19_shim_arrays a;
+    memset(&a, 0, sizeof a);
+    a.f = f; a.rho = rho; a.ux = ux; a.uy = uy; a.uz = uz;
+    a.force_realx = force_realx; a.force_realy = force_realy; a.force_realz = force_realz;
+    a.ibnodes = ibnodes; a.isnodes = has_isnodes ? isnodes : nullptr;
+    a.ndiag = ndiag; a.nflowout = nflowout; a.nsteps_total = nsteps_total; a.istep0 = istep0;
+    a.ntime = ntime; a.prerelax_maxiter = prerelax_maxiter; a.rhoepsl = rhoepsl;
+    return d3q19_shim_bind(h, &a);
 }
 
 extern "C" int d3q19_shim_set_schedule(d3q19_handle *h, int32_t ndiag, int32_t nflowout, int32_t nsteps_total, int32_t istep0) {

@@ -715,4 +715,66 @@ __global__ void __launch_bounds__(BLOCK_X) k_profiles_final(int lx, int nchunks,
     out[(long long)q * lx + x] = s;
 }
 
+// diag (saveload.f90:1507-1676): over the fluid nodes, count, sums of u and u^2, max |u| with the
+// location of its first occurrence in the reference's loop order (z, y, x), max / min of rho.
+// Stage 1 like k_profiles (a block owns BLOCK_X x-columns and a chunk of (y,z) rows), stage 2 one thread.
+constexpr int NDIAG = 12;   // cnt, su, sv, sw, suu, svv, sww, vmax, vidx, rhomax, rhomin, (pad)
+template <int RK>
+__global__ void __launch_bounds__(BLOCK_X) k_diag(Geom g, const double *A, double Fx, double Fy, double Fz,
+                                                  const int32_t *solid, int rows_per_chunk, double *partial) {
+    __shared__ double sh[BLOCK_X][NDIAG];
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    const long long nrows = (long long)g.ly * g.lz;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    const long long r1 = r0 + rows_per_chunk < nrows ? r0 + rows_per_chunk : nrows;
+    double acc[NDIAG];
+#pragma unroll
+    for (int q = 0; q < NDIAG; ++q) acc[q] = 0.0;
+    acc[8] = -1.0; acc[9] = -1.0e300; acc[10] = 1.0e300;
+    if (x < g.lx) {
+        for (long long row = r0; row < r1; ++row) {
+            const int y = (int)(row % g.ly), z = (int)(row / g.ly);
+            if (solid && solid[row * g.xp + x] > 0) continue;
+            const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, y, z + 1);
+            double f[NPOP], r, a, b, c;
+            gather19<RK>(A, g, k, f);
+            moments_strict(f, Fx, Fy, Fz, r, a, b, c);
+            acc[0] += 1.0; acc[1] += a; acc[2] += b; acc[3] += c;
+            acc[4] += a * a; acc[5] += b * b; acc[6] += c * c;
+            const double vel = sqrt(a * a + b * b + c * c);
+            if (vel > acc[7]) { acc[7] = vel; acc[8] = (double)(row * g.lx + x); }     // loop-order index, exact below 2^53
+            acc[9] = r > acc[9] ? r : acc[9];
+            acc[10] = r < acc[10] ? r : acc[10];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NDIAG; ++q) sh[threadIdx.x][q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < BLOCK_X; ++t) {
+            for (int q = 0; q < 7; ++q) acc[q] += sh[t][q];
+            if (sh[t][7] > acc[7] || (sh[t][7] == acc[7] && sh[t][8] >= 0.0 && (acc[8] < 0.0 || sh[t][8] < acc[8]))) {
+                acc[7] = sh[t][7]; acc[8] = sh[t][8];
+            }
+            acc[9] = sh[t][9] > acc[9] ? sh[t][9] : acc[9];
+            acc[10] = sh[t][10] < acc[10] ? sh[t][10] : acc[10];
+        }
+        double *o = partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * NDIAG;
+        for (int q = 0; q < NDIAG; ++q) o[q] = acc[q];
+    }
+}
+__global__ void k_diag_final(int npartial, const double *partial, double *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double acc[NDIAG];
+    for (int q = 0; q < NDIAG; ++q) acc[q] = partial[q];
+    for (int p = 1; p < npartial; ++p) {
+        const double *s = partial + (long long)p * NDIAG;
+        for (int q = 0; q < 7; ++q) acc[q] += s[q];
+        if (s[7] > acc[7] || (s[7] == acc[7] && s[8] >= 0.0 && (acc[8] < 0.0 || s[8] < acc[8]))) { acc[7] = s[7]; acc[8] = s[8]; }
+        acc[9] = s[9] > acc[9] ? s[9] : acc[9];
+        acc[10] = s[10] < acc[10] ? s[10] : acc[10];
+    }
+    for (int q = 0; q < NDIAG; ++q) out[q] = acc[q];
+}
+
 }  // namespace d3q

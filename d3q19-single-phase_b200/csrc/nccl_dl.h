@@ -21,6 +21,7 @@ struct NcclApi {
     int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -43,6 +44,7 @@ struct NcclApi {
         D3Q_NCCL_SYM(Send, "ncclSend")
         D3Q_NCCL_SYM(Recv, "ncclRecv")
         D3Q_NCCL_SYM(AllReduce, "ncclAllReduce")
+        D3Q_NCCL_SYM(AllGather, "ncclAllGather")
         D3Q_NCCL_SYM(GroupStart, "ncclGroupStart")
         D3Q_NCCL_SYM(GroupEnd, "ncclGroupEnd")
         D3Q_NCCL_SYM(GetErrorString, "ncclGetErrorString")

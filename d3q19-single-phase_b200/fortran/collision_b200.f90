@@ -64,17 +64,6 @@
         integer(c_signed_char) :: nccl_id(128)
       end type d3q19_config
 
-      ! mirror of d3q19_shim_arrays
-      type, bind(c) :: d3q19_shim_arrays
-        type(c_ptr) :: f
-        type(c_ptr) :: rho, ux, uy, uz
-        type(c_ptr) :: force_realx, force_realy, force_realz
-        type(c_ptr) :: ibnodes, isnodes
-        integer(c_int32_t) :: ndiag, nflowout, nsteps_total, istep0
-        integer(c_int32_t) :: ntime, prerelax_maxiter
-        real(c_double) :: rhoepsl
-      end type d3q19_shim_arrays
-
       type(c_ptr), save :: handle = c_null_ptr
       logical, save :: bound = .false.
 
@@ -100,10 +89,17 @@
           import :: c_ptr
           type(c_ptr) :: msg
         end function
-        integer(c_int) function d3q19_shim_bind(h, a) bind(c, name='d3q19_shim_bind')
-          import :: c_int, c_ptr, d3q19_shim_arrays
+        integer(c_int) function d3q19_shim_bind_arrays(h, f, rho, ux, uy, uz, frx, fry, frz, ibnodes, isnodes,   &
+            has_isnodes, ndiag, nflowout, nsteps, istep0, ntime, maxiter, rhoepsl)                              &
+            bind(c, name='d3q19_shim_bind_arrays')
+          import :: c_int, c_ptr, c_int32_t, c_double
           type(c_ptr), value :: h
-          type(d3q19_shim_arrays), intent(in) :: a
+          ! the arrays go by reference, as Fortran passes them: the library keeps their addresses
+          ! (allocarray allocates them once and never frees them, para.f90:418-503)
+          real(c_double) :: f(*), rho(*), ux(*), uy(*), uz(*), frx(*), fry(*), frz(*)
+          integer(c_int32_t) :: ibnodes(*), isnodes(*)
+          integer(c_int32_t), value :: has_isnodes, ndiag, nflowout, nsteps, istep0, ntime, maxiter
+          real(c_double), value :: rhoepsl
         end function
         integer(c_int) function d3q19_shim_set_schedule(h, ndiag, nflowout, nsteps, istep0) &
             bind(c, name='d3q19_shim_set_schedule')
@@ -186,7 +182,6 @@
       use mpi
       use var_inc
       type(d3q19_config) :: cfg
-      type(d3q19_shim_arrays) :: a
       integer(c_int32_t) :: ndev
       integer :: ierr_
       integer(c_signed_char) :: ipc_mine(256)
@@ -232,20 +227,14 @@
         deallocate(ipc_all)
       endif
 
-      a%f = c_loc(f)
-      a%rho = c_loc(rho);  a%ux = c_loc(ux);  a%uy = c_loc(uy);  a%uz = c_loc(uz)
-      a%force_realx = c_loc(force_realx)
-      a%force_realy = c_loc(force_realy)
-      a%force_realz = c_loc(force_realz)
-      a%ibnodes = c_loc(ibnodes)
-      a%isnodes = c_null_ptr
-      if (ipart) a%isnodes = c_loc(isnodes)
-      a%ndiag = ndiag;  a%nflowout = nflowout
-      a%nsteps_total = nsteps;  a%istep0 = 0
-      a%ntime = ntime
-      a%prerelax_maxiter = 15000        ! main.f90:85
-      a%rhoepsl = rhoepsl               ! para.f90:285
-      call d3q19_b200_check(d3q19_shim_bind(handle, a), 'd3q19_shim_bind')
+      ! main.f90:85: the pre-relaxation loop ends after 15000 iterations; rhoepsl: para.f90:285
+      if (ipart) then
+        call d3q19_b200_check(d3q19_shim_bind_arrays(handle, f, rho, ux, uy, uz, force_realx, force_realy,      &
+             force_realz, ibnodes, isnodes, 1, ndiag, nflowout, nsteps, 0, ntime, 15000, rhoepsl), 'd3q19_shim_bind_arrays')
+      else
+        call d3q19_b200_check(d3q19_shim_bind_arrays(handle, f, rho, ux, uy, uz, force_realx, force_realy,      &
+             force_realz, ibnodes, ibnodes, 0, ndiag, nflowout, nsteps, 0, ntime, 15000, rhoepsl), 'd3q19_shim_bind_arrays')
+      endif
       bound = .true.
       end subroutine d3q19_b200_ensure
 

@@ -185,6 +185,11 @@ int d3q19_get_mask(d3q19_handle *h, int32_t *own_lx_ly_lz);
  * (statistc, saveload.f90:1241-1300), all-reduced over ranks; out is [11][lx]             */
 int d3q19_profiles(d3q19_handle *h, double *out_11_by_lx);
 
+/* diag (saveload.f90:1507-1676) from the current populations, reduced over ranks.  out[14]: vmax,
+ * imout, jmout, kmout (global, 1-based, first occurrence in the reference's loop order), umean, vmean,
+ * wmean, urms, vrms, wrms (divided by ustar like the reference), volf, rhomax, rhomin, nfluid.       */
+int d3q19_diag(d3q19_handle *h, double ustar, double *out14);
+
 /* ---- measurement ----------------------------------------------------------------------- */
 /* CUDA events on the stream the step kernels are launched on */
 int d3q19_timer_start(d3q19_handle *h);
@@ -209,6 +214,12 @@ typedef struct d3q19_shim_arrays {
 } d3q19_shim_arrays;
 
 int d3q19_shim_bind(d3q19_handle *h, const d3q19_shim_arrays *a);
+/* the same with the arrays as by-reference arguments (a Fortran caller needs no C_LOC/TARGET) */
+int d3q19_shim_bind_arrays(d3q19_handle *h, double *f, double *rho, double *ux, double *uy, double *uz,
+                           double *force_realx, double *force_realy, double *force_realz, int32_t *ibnodes,
+                           int32_t *isnodes, int32_t has_isnodes, int32_t ndiag, int32_t nflowout,
+                           int32_t nsteps_total, int32_t istep0, int32_t ntime, int32_t prerelax_maxiter,
+                           double rhoepsl);
 /* change the output cadence / loop bounds the download policy keys on (main.f90:142,171,184) */
 int d3q19_shim_set_schedule(d3q19_handle *h, int32_t ndiag, int32_t nflowout, int32_t nsteps_total, int32_t istep0);
 int d3q19_shim_forcing(d3q19_handle *h, double force_in_y, double force_mag);

@@ -292,3 +292,35 @@ def test_device_init_channel_matches_host_initvel_initpop(oracle, scheme):
     b = dev.download_f(np.empty((nz, ny, nx, 19)))
     assert relerr(b, a) < 1e-12
     host.close(); dev.close()
+
+
+def reference_diag(w, ustar, solid=None):
+    """numpy mirror of diag (saveload.f90:1535-1640) on the oracle's macroscopic arrays"""
+    ux, uy, uz, rho = (w.get(k) for k in ("ux", "uy", "uz", "rho"))
+    fluid = np.ones(ux.shape, bool) if solid is None else ~solid
+    nf = int(fluid.sum())
+    um, vm, wm = (a[fluid].sum() / nf for a in (ux, uy, uz))
+    rms = [np.sqrt((a[fluid] ** 2).sum() / nf - m * m) / ustar for a, m in ((ux, um), (uy, vm), (uz, wm))]
+    vel = np.sqrt(ux * ux + uy * uy + uz * uz)
+    vel[~fluid] = 0.0
+    k, j, i = np.unravel_index(int(np.argmax(vel)), vel.shape)        # first occurrence in (z, y, x) order
+    return dict(vmax=float(vel.max()), imout=i + 1, jmout=j + 1, kmout=k + 1, umean=um / ustar, vmean=vm / ustar,
+                wmean=wm / ustar, urms=rms[0], vrms=rms[1], wrms=rms[2], volf=1.0 - nf / vel.size,
+                rhomax=float(rho[fluid].max()), rhomin=float(rho[fluid].min()), nfluid=nf)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_device_diag_matches_reference_diag(oracle, scheme):
+    nx, ny, nz = 40, 6, 5
+    w, p, sim = make_pair(oracle, nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT, perturb=1e-4)
+    for _ in range(3):
+        w.collision_MRT(); sim.collide_stream()
+        w.macrovar()
+        got, ref = sim.diag(), reference_diag(w, p.ustar)
+        for k in ("imout", "jmout", "kmout", "nfluid"):
+            assert got[k] == ref[k], k
+        assert abs(got["vmax"] - ref["vmax"]) <= 1e-14 * ref["vmax"]          # FMA in the norm
+        assert got["rhomax"] == ref["rhomax"] and got["rhomin"] == ref["rhomin"]
+        for k in ("umean", "vmean", "wmean", "urms", "vrms", "wrms", "volf"):
+            assert abs(got[k] - ref[k]) <= 1e-10 * max(abs(ref[k]), 1e-3), k     # sums are order dependent
+    sim.close()
