@@ -939,8 +939,8 @@ extern "C" int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_
     CK(cudaMalloc(&h->links.dir, h->maxlink * sizeof(int32_t)));
     CK(cudaMalloc(&h->links.part, h->maxlink * sizeof(int32_t)));
     CK(cudaMalloc(&h->links.q, h->maxlink * sizeof(double)));
-    CK(cudaMalloc(&h->lcount, (npart + 1) * sizeof(long long)));
-    CK(cudaMalloc(&h->loffset, (npart + 1) * sizeof(long long)));
+    CK(cudaMalloc(&h->lcount, ((size_t)npart * PART_SPLIT + 1) * sizeof(long long)));
+    CK(cudaMalloc(&h->loffset, ((size_t)npart * PART_SPLIT + 1) * sizeof(long long)));
     CK(cudaMalloc(&h->nfilled_dev, sizeof(unsigned long long)));
     const double volp = 4.0 / 3.0 * pi * prm->rad * prm->rad * prm->rad;      // para.f90:340
     h->amp = h->cfg.rhopart * volp;                                           // :341
@@ -974,6 +974,17 @@ extern "C" int d3q19_set_particles(d3q19_handle *h, int32_t npart, const double 
     return 0;
 }
 
+// the link count lives on the device (the step sequence never waits for it); the host asks when it must
+static int fetch_nlink(d3q19_handle *h) {
+    if (h->nlink >= 0) return 0;
+    long long n = 0;
+    CK(cudaMemcpyAsync(&n, h->loffset + (size_t)h->npart * PART_SPLIT, sizeof n, cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaStreamSynchronize(h->sc));
+    if (n > h->maxlink) return fail("d3q19_beads_links: %lld links exceed maxlink %lld", n, h->maxlink);
+    h->nlink = n;
+    return 0;
+}
+
 // beads_links: solid mask from the particle table, then the boundary-link list
 extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local) {
     CK(cudaSetDevice(h->cfg.device));
@@ -983,23 +994,21 @@ extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local) {
     int32_t *t = h->own; h->own = h->own0; h->own0 = t;          // the old mask is what beads_filling compares against
     h->solid = h->own + h->g.plane; h->isn = h->own + h->g.plane;
     CK(cudaMemsetAsync(h->own, 0xFF, nown * sizeof(int32_t), h->sc));
-    k_beads_mask<<<h->npart, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own);
+    const dim3 gp((unsigned)h->npart, PART_SPLIT);
+    k_beads_mask<<<gp, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own);
     if (!h->mask_built) {                                         // first mask: nothing was uncovered
         CK(cudaMemcpyAsync(h->own0, h->own, nown * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->sc));
         h->mask_built = true;
     }
-    k_beads_links<false><<<h->npart, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
-    k_beads_scan<<<1, 32, 0, h->sc>>>(h->npart, h->lcount, h->loffset);
-    k_beads_links<true><<<h->npart, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
+    const int nslot = h->npart * PART_SPLIT;
+    k_beads_links<false><<<gp, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
+    k_beads_scan<<<1, 32, 0, h->sc>>>(nslot, h->lcount, h->loffset);
+    k_beads_links<true><<<gp, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
     CK(cudaGetLastError());
     h->n_other_kernels += 4;
-    long long n = 0;
-    CK(cudaMemcpyAsync(&n, h->loffset + h->npart, sizeof n, cudaMemcpyDeviceToHost, h->sc));
-    CK(cudaStreamSynchronize(h->sc));
-    if (n > h->maxlink) return fail("d3q19_beads_links: %lld links exceed maxlink %lld", n, h->maxlink);
-    h->nlink = n;
     h->links_valid = true;
-    if (nlink_local) *nlink_local = n;
+    h->nlink = -1;                                                // known on the device; fetched on demand
+    if (nlink_local) { RK_(fetch_nlink(h)); *nlink_local = h->nlink; }
     return 0;
 }
 
@@ -1010,18 +1019,23 @@ extern "C" int d3q19_beads_collision(d3q19_handle *h) {
     RK_(wait_exchange(h));
     const size_t tb = (size_t)3 * h->npart * sizeof(double);
     CK(cudaMemsetAsync(h->fHIp, 0, 2 * tb, h->sc));                // fHIp and torqp are adjacent
-    if (h->nlink > 0) {
+    {
         IbbParams P;
-        P.pg = part_geom(h); P.S = h->A; P.own = h->own; P.L = h->links; P.nlink = h->nlink;
+        P.pg = part_geom(h); P.S = h->A; P.own = h->own; P.L = h->links;
+        P.nlink_dev = h->loffset + (size_t)h->npart * PART_SPLIT; P.maxlink = h->maxlink;
         P.ypglb = h->ypglb; P.wp = h->wp; P.omgp = h->omgp; P.rho0 = h->pp.rho0; P.fHIp = h->fHIp; P.torqp = h->torqp;
-        const unsigned nb = (unsigned)((h->nlink + 127) / 128);
-        switch (read_kind(h)) {
-        case READ_DIRECT: k_beads_ibb<READ_DIRECT><<<nb, 128, 0, h->sc>>>(P); break;
-        case READ_PULL_NAT: k_beads_ibb<READ_PULL_NAT><<<nb, 128, 0, h->sc>>>(P); break;
-        default: k_beads_ibb<READ_PULL_SWAP><<<nb, 128, 0, h->sc>>>(P); break;
+        // the count is on the device: size the grid for the known count if the host has it, else for the capacity
+        const long long nthreads = h->nlink >= 0 ? h->nlink : h->maxlink;
+        const unsigned nb = (unsigned)((nthreads + 127) / 128);
+        if (nb > 0) {
+            switch (read_kind(h)) {
+            case READ_DIRECT: k_beads_ibb<READ_DIRECT><<<nb, 128, 0, h->sc>>>(P); break;
+            case READ_PULL_NAT: k_beads_ibb<READ_PULL_NAT><<<nb, 128, 0, h->sc>>>(P); break;
+            default: k_beads_ibb<READ_PULL_SWAP><<<nb, 128, 0, h->sc>>>(P); break;
+            }
+            CK(cudaGetLastError());
+            h->n_other_kernels++;
         }
-        CK(cudaGetLastError());
-        h->n_other_kernels++;
     }
     if (h->cfg.nranks > 1) {                                       // force reduction over the slabs
         NK(nccl_api().AllReduce(h->fHIp, h->fHIp, (size_t)6 * h->npart, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
@@ -1062,17 +1076,20 @@ extern "C" int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled) {
     FillParams P;
     P.pg = part_geom(h); P.S = h->A; P.own0 = h->own0; P.own = h->own; P.ypglb0 = h->ypglb0;
     P.ypglb = h->ypglb; P.wp = h->wp; P.omgp = h->omgp; P.nfilled = h->nfilled_dev;
+    const dim3 gp((unsigned)h->npart, PART_SPLIT);
     switch (read_kind(h)) {
-    case READ_DIRECT: k_beads_fill<READ_DIRECT><<<h->npart, 128, 0, h->sc>>>(P); break;
-    case READ_PULL_NAT: k_beads_fill<READ_PULL_NAT><<<h->npart, 128, 0, h->sc>>>(P); break;
-    default: k_beads_fill<READ_PULL_SWAP><<<h->npart, 128, 0, h->sc>>>(P); break;
+    case READ_DIRECT: k_beads_fill<READ_DIRECT><<<gp, 128, 0, h->sc>>>(P); break;
+    case READ_PULL_NAT: k_beads_fill<READ_PULL_NAT><<<gp, 128, 0, h->sc>>>(P); break;
+    default: k_beads_fill<READ_PULL_SWAP><<<gp, 128, 0, h->sc>>>(P); break;
     }
     CK(cudaGetLastError());
     h->n_other_kernels++;
-    unsigned long long n = 0;
-    CK(cudaMemcpyAsync(&n, h->nfilled_dev, sizeof n, cudaMemcpyDeviceToHost, h->sc));
-    CK(cudaStreamSynchronize(h->sc));
-    if (nfilled) *nfilled = (int64_t)n;
+    if (nfilled) {
+        unsigned long long n = 0;
+        CK(cudaMemcpyAsync(&n, h->nfilled_dev, sizeof n, cudaMemcpyDeviceToHost, h->sc));
+        CK(cudaStreamSynchronize(h->sc));
+        *nfilled = (int64_t)n;
+    }
     h->shim.f_host_valid = false;
     return 0;
 }
@@ -1109,6 +1126,7 @@ extern "C" int d3q19_get_links(d3q19_handle *h, int64_t capacity, int32_t *x, in
                                int32_t *part, double *q, int64_t *nlink) {
     CK(cudaSetDevice(h->cfg.device));
     if (!h->part_on || !h->links_valid) return fail("d3q19_get_links: no valid link list");
+    RK_(fetch_nlink(h));
     if (nlink) *nlink = h->nlink;
     if (capacity < h->nlink) return fail("d3q19_get_links: capacity %lld < %lld links", (long long)capacity, h->nlink);
     if (h->nlink == 0) return 0;

@@ -69,13 +69,15 @@ __device__ __forceinline__ int local_planes(const PartGeom &pg, int iz, int out[
 }
 
 // ---- beads_links, part 1: solid mask (own must be preset to -1) -----------------------------------
+// grid (npart, PART_SPLIT): the box of a particle is shared by PART_SPLIT blocks
+constexpr int PART_SPLIT = 32;
 __global__ void __launch_bounds__(256) k_beads_mask(PartGeom pg, int npart, const double *ypglb, int32_t *own) {
     const int p = blockIdx.x;
     const double *c = ypglb + 3 * p;
     const BBox b = part_bbox(pg, c);
     const double r2 = (R(pg.rad) * R(pg.rad)).v;
     const long long nbox = (long long)b.n[0] * b.n[1] * b.n[2];
-    for (long long t = threadIdx.x; t < nbox; t += blockDim.x) {
+    for (long long t = (long long)blockIdx.y * blockDim.x + threadIdx.x; t < nbox; t += (long long)blockDim.x * gridDim.y) {
         const int jx = b.lo[0] + (int)(t % b.n[0]);
         const int jy = b.lo[1] + (int)((t / b.n[0]) % b.n[1]);
         const int jz = b.lo[2] + (int)(t / ((long long)b.n[0] * b.n[1]));
@@ -135,8 +137,13 @@ __global__ void __launch_bounds__(256) k_beads_links(PartGeom pg, int npart, con
     const BBox b = part_bbox(pg, c);
     const double r2 = (R(pg.rad) * R(pg.rad)).v;
     const long long nbox = (long long)b.n[0] * b.n[1] * b.n[2];
-    const long long chunk = (nbox + blockDim.x - 1) / blockDim.x;
-    const long long t0 = (long long)threadIdx.x * chunk, t1 = t0 + chunk < nbox ? t0 + chunk : nbox;
+    // block blockIdx.y owns a contiguous part of the box, each of its threads a contiguous chunk of that
+    const long long per_block = (nbox + gridDim.y - 1) / gridDim.y;
+    const long long b0 = (long long)blockIdx.y * per_block, b1 = b0 + per_block < nbox ? b0 + per_block : nbox;
+    const long long chunk = (per_block + blockDim.x - 1) / blockDim.x;
+    long long t0 = b0 + (long long)threadIdx.x * chunk, t1 = t0 + chunk < b1 ? t0 + chunk : b1;
+    if (t0 > b1) t0 = b1;
+    const int slot = p * gridDim.y + blockIdx.y;      // position of this block in the canonical order
     long long mine = 0;
     for (int pass = 0; pass < (FILL ? 2 : 1); ++pass) {
         long long w = 0;
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(256) k_beads_links(PartGeom pg, int npart, con
             sh[threadIdx.x] = mine;
             __syncthreads();
             if (threadIdx.x == 0) {
-                long long acc = offset[p];
+                long long acc = offset[slot];
                 for (int i = 0; i < 256; ++i) { const long long v = sh[i]; sh[i] = acc; acc += v; }
             }
             __syncthreads();
@@ -174,17 +181,28 @@ __global__ void __launch_bounds__(256) k_beads_links(PartGeom pg, int npart, con
         if (threadIdx.x == 0) {
             long long acc = 0;
             for (int i = 0; i < 256; ++i) acc += sh[i];
-            count[p] = acc;
+            count[slot] = acc;
         }
     }
 }
 
-__global__ void k_beads_scan(int npart, const long long *count, long long *offset) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        long long acc = 0;
-        for (int p = 0; p < npart; ++p) { offset[p] = acc; acc += count[p]; }
-        offset[npart] = acc;
+// exclusive scan over the npart * PART_SPLIT block counts (one warp; a few thousand entries)
+__global__ void k_beads_scan(int n, const long long *count, long long *offset) {
+    const int lane = threadIdx.x;
+    long long carry = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const long long v = i < n ? count[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (i < n) offset[i] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) offset[n] = carry;
 }
 
 // ---- beads_collision: interpolated bounce-back + momentum exchange ---------------------------------
@@ -198,7 +216,8 @@ struct IbbParams {
     double *S;
     const int32_t *own;
     Links L;
-    long long nlink;
+    const long long *nlink_dev;   // total written by k_beads_scan: no host round trip between links and IBB
+    long long maxlink;
     const double *ypglb, *wp, *omgp;
     double rho0;
     double *fHIp, *torqp;     // (3,npart), accumulated with atomics
@@ -218,7 +237,8 @@ __global__ void __launch_bounds__(128) k_beads_ibb(const __grid_constant__ IbbPa
     const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double F[6] = {0, 0, 0, 0, 0, 0};
     int part = 0;
-    if (l < P.nlink) {
+    const long long nlink = *P.nlink_dev < P.maxlink ? *P.nlink_dev : P.maxlink;
+    if (l < nlink) {
         const uint32_t n = P.L.node[l];
         const int ip = P.L.dir[l], io = dir_opp(ip);
         part = P.L.part[l];
@@ -327,7 +347,7 @@ __global__ void __launch_bounds__(128) k_beads_fill(const __grid_constant__ Fill
     const int p = blockIdx.x;
     const BBox b = part_bbox(pg, P.ypglb0 + 3 * p);
     const long long nbox = (long long)b.n[0] * b.n[1] * b.n[2];
-    for (long long t = threadIdx.x; t < nbox; t += blockDim.x) {
+    for (long long t = (long long)blockIdx.y * blockDim.x + threadIdx.x; t < nbox; t += (long long)blockDim.x * gridDim.y) {
         const int jx = b.lo[0] + (int)(t % b.n[0]);
         const int jy = b.lo[1] + (int)((t / b.n[0]) % b.n[1]);
         const int jz = b.lo[2] + (int)(t / ((long long)b.n[0] * b.n[1]));
