@@ -396,11 +396,15 @@ extern "C" int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs) {
     if (h->halo_on) return fail("d3q19_ipc_connect: already connected");
     RK_(wait_exchange(h));
     const int nb[2] = {(h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks, (h->cfg.rank + 1) % h->cfg.nranks};
-    for (int d = 0; d < 2; ++d) {
+    // Opening can fail on one rank only (no peer access between two devices, a foreign container ...):
+    // every rank tries, then all agree through an all-reduce, so that either all use the peer halo or none.
+    int failed = 0;
+    std::string why;
+    for (int d = 0; d < 2 && !failed; ++d) {
         const unsigned char *b = blobs + (size_t)nb[d] * D3Q19_IPC_BYTES;
         int32_t meta[2]; long long slab; int32_t a_first;
         memcpy(meta, b + 192, sizeof meta); memcpy(&slab, b + 200, sizeof slab); memcpy(&a_first, b + 208, sizeof a_first);
-        if (meta[1] != h->cfg.scheme) return fail("d3q19_ipc_connect: rank %d runs scheme %d, this rank %d", nb[d], meta[1], h->cfg.scheme);
+        if (meta[1] != h->cfg.scheme) { failed = 1; why = "neighbour runs another storage scheme"; break; }
         h->peer_lz[d] = meta[0];
         h->peer_slab[d] = slab;
         if (d == 1 && nb[1] == nb[0]) {                 // two ranks: both neighbours are the same process
@@ -411,21 +415,40 @@ extern "C" int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs) {
             for (int a = 0; a < 3; ++a) {
                 if (a == 1 && !memcmp(b + 64, zero, 64)) continue;
                 memcpy(&mh, b + 64 * a, 64);
-                CK(cudaIpcOpenMemHandle(&h->peer_base[d][a], mh, cudaIpcMemLazyEnablePeerAccess));
+                cudaError_t e = cudaIpcOpenMemHandle(&h->peer_base[d][a], mh, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    failed = 1; why = std::string("cudaIpcOpenMemHandle -> ") + cudaGetErrorString(e);
+                    h->peer_base[d][a] = nullptr;
+                    cudaGetLastError();
+                    break;
+                }
             }
         }
+        if (failed) break;
         double *first = (double *)h->peer_base[d][0] + POP_PAD;
         double *second = h->peer_base[d][1] ? (double *)h->peer_base[d][1] + POP_PAD : nullptr;
         h->peer_A[d] = a_first ? first : second;
         h->peer_B[d] = a_first ? second : first;
         h->peer_flags[d] = (unsigned int *)h->peer_base[d][2];
     }
-    // everybody has opened everybody: a barrier before the first remote store
-    if (h->comm) {
-        NK(nccl_api().AllReduce(h->scal + 32, h->scal + 32, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
-        h->n_nccl++;
-    }
+    // agreement + barrier: everybody has opened everybody before the first remote store
+    double nfail = (double)failed;
+    CK(cudaMemcpyAsync(h->scal + 32, &nfail, sizeof nfail, cudaMemcpyHostToDevice, h->sc));
+    NK(nccl_api().AllReduce(h->scal + 32, h->scal + 32, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
+    h->n_nccl++;
+    CK(cudaMemcpyAsync(&nfail, h->scal + 32, sizeof nfail, cudaMemcpyDeviceToHost, h->sc));
     CK(cudaStreamSynchronize(h->sc));
+    if (nfail > 0.0) {
+        for (int d = 0; d < 2; ++d)
+            for (int a = 0; a < 3; ++a) {
+                if (h->peer_base[d][a] && !(d == 1 && h->peer_base[0][a] == h->peer_base[1][a])) cudaIpcCloseMemHandle(h->peer_base[d][a]);
+            }
+        for (int d = 0; d < 2; ++d)
+            for (int a = 0; a < 3; ++a) h->peer_base[d][a] = nullptr;
+        fail("d3q19_ipc_connect: peer memory unavailable on %d rank(s)%s%s; the halo stays on NCCL", (int)nfail,
+             failed ? ": " : "", failed ? why.c_str() : "");
+        return 2;
+    }
     h->halo_on = true;
     return 0;
 }
@@ -1002,7 +1025,7 @@ extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local) {
     }
     const int nslot = h->npart * PART_SPLIT;
     k_beads_links<false><<<gp, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
-    k_beads_scan<<<1, 32, 0, h->sc>>>(nslot, h->lcount, h->loffset);
+    k_beads_scan<<<1, 1024, 0, h->sc>>>(nslot, h->lcount, h->loffset);
     k_beads_links<true><<<gp, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
     CK(cudaGetLastError());
     h->n_other_kernels += 4;

@@ -23,6 +23,12 @@
 
 namespace d3q {
 
+// lattice tables for kernels that index directions at run time (one link = one thread)
+__device__ __constant__ signed char DIR_CX[NPOP] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};
+__device__ __constant__ signed char DIR_CY[NPOP] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1};
+__device__ __constant__ signed char DIR_CZ[NPOP] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
+__device__ __constant__ signed char DIR_OPP[NPOP] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
+
 struct PartGeom {
     Geom g;
     int nx, ny, nz, globalz;
@@ -107,24 +113,32 @@ struct Links {
     double *q;           // fraction of the link on the fluid side, (0,1]
 };
 
-__device__ __forceinline__ bool link_here(const PartGeom &pg, const int32_t *own, const double *c, int p, int jx, int jy,
-                                          int jz, int zg, int ip, double r2, double &q) {
-    const int cx = dir_cx(ip), cy = dir_cy(ip), cz = dir_cz(ip);
+// owner of the neighbour of (jx,jy,zg) along direction IP, or -2 beyond a channel wall
+template <int IP>
+__device__ __forceinline__ int32_t link_owner(const PartGeom &pg, const int32_t *own, int jx, int jy, int zg) {
+    constexpr int cx = dir_cx(IP), cy = dir_cy(IP), cz = dir_cz(IP);
     const int kx = jx + cx;
-    if (kx < 1 || kx > pg.nx) return false;
+    if (kx < 1 || kx > pg.nx) return -2;
     const int ky = wrap1(jy + cy, pg.ny);
     const int kzg = zg + cz;                         // ghost planes carry the mask too
-    if (own[(long long)(kx - 1) + (long long)pg.g.xp * ((ky - 1) + (long long)pg.g.ly * kzg)] != p + 1) return false;
+    return own[(long long)(kx - 1) + (long long)pg.g.xp * ((ky - 1) + (long long)pg.g.ly * kzg)];
+}
+
+// fraction of the link from (jx,jy,jz) along IP that lies in the fluid: smallest root of
+// |x_f + t c - r_c|^2 = rad^2, non-contracted arithmetic (bit-identical to the CPU checker)
+template <int IP>
+__device__ __forceinline__ double link_q(const double *c, int jx, int jy, int jz, double r2) {
+    constexpr int cx = dir_cx(IP), cy = dir_cy(IP), cz = dir_cz(IP);
     const R dx = R((double)jx - 0.5) - R(c[0]), dy = R((double)jy - 0.5) - R(c[1]), dz = R((double)jz - 0.5) - R(c[2]);
     const R a((double)(cx * cx + cy * cy + cz * cz));
     const R b = R(2.0) * (R((double)cx) * dx + R((double)cy) * dy + R((double)cz) * dz);
     const R cc = dx * dx + dy * dy + dz * dz - R(r2);
     double disc = (b * b - R(4.0) * a * cc).v;
     if (disc < 0.0) disc = 0.0;
-    q = __ddiv_rn((-b - R(__dsqrt_rn(disc))).v, (R(2.0) * a).v);
+    double q = __ddiv_rn((-b - R(__dsqrt_rn(disc))).v, (R(2.0) * a).v);
     if (q < 0.0) q = 0.0;
     if (q > 1.0) q = 1.0;
-    return true;
+    return q;
 }
 
 // FILL = false: count[p] = number of links of particle p on this slab; FILL = true: write them at offset[p]
@@ -166,13 +180,26 @@ __global__ void __launch_bounds__(256) k_beads_links(PartGeom pg, int npart, con
             if (zg < 1 || zg > pg.g.lz) continue;
             const long long n = (long long)(jx - 1) + (long long)pg.g.xp * ((iy - 1) + (long long)pg.g.ly * zg);
             if (own[n] > 0) continue;
-            for (int ip = 1; ip < NPOP; ++ip) {
-                double q;
-                if (!link_here(pg, own, c, p, jx, jy, jz, zg, ip, r2, q)) continue;
-                if (pass == 0) { ++mine; continue; }
-                if (w < maxlink) { L.node[w] = (uint32_t)n; L.dir[w] = ip; L.part[w] = p + 1; L.q[w] = q; }
-                ++w;
-            }
+            // all 18 neighbour owners first (independent loads), then the links among them
+            int32_t nbo[NPOP - 1];
+            static_for<NPOP - 1>([&](auto ic) {
+                constexpr int ip = decltype(ic)::value + 1;
+                nbo[ip - 1] = link_owner<ip>(pg, own, jx, iy, zg);
+            });
+            static_for<NPOP - 1>([&](auto ic) {
+                constexpr int ip = decltype(ic)::value + 1;
+                if (nbo[ip - 1] == p + 1) {
+                    if (pass == 0) {
+                        ++mine;
+                    } else {
+                        if (w < maxlink) {
+                            L.node[w] = (uint32_t)n; L.dir[w] = ip; L.part[w] = p + 1;
+                            L.q[w] = link_q<ip>(c, jx, jy, jz, r2);
+                        }
+                        ++w;
+                    }
+                }
+            });
         }
     }
     if (!FILL) {
@@ -186,23 +213,36 @@ __global__ void __launch_bounds__(256) k_beads_links(PartGeom pg, int npart, con
     }
 }
 
-// exclusive scan over the npart * PART_SPLIT block counts (one warp; a few thousand entries)
-__global__ void k_beads_scan(int n, const long long *count, long long *offset) {
-    const int lane = threadIdx.x;
-    long long carry = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const long long v = i < n ? count[i] : 0;
-        long long incl = v;
+// exclusive scan over the npart * PART_SPLIT block counts: one block of 1024 threads, each owns a
+// contiguous group of entries (a few thousand entries in all)
+__global__ void __launch_bounds__(1024) k_beads_scan(int n, const long long *count, long long *offset) {
+    __shared__ long long wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int i0 = tid * per, i1 = i0 + per < n ? i0 + per : n;
+    long long mine = 0;
+    for (int i = i0; i < i1; ++i) mine += count[i];
+    long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        long long v = wsum[lane], inc2 = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const long long t = __shfl_up_sync(0xffffffffu, inc2, o);
+            if (lane >= o) inc2 += t;
         }
-        if (i < n) offset[i] = carry + incl - v;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        wsum[lane] = inc2 - v;                 // exclusive prefix of the warp totals
+        if (lane == 31) offset[n] = inc2;      // grand total
     }
-    if (lane == 0) offset[n] = carry;
+    __syncthreads();
+    long long acc = wsum[wid] + incl - mine;
+    for (int i = i0; i < i1; ++i) { offset[i] = acc; acc += count[i]; }
 }
 
 // ---- beads_collision: interpolated bounce-back + momentum exchange ---------------------------------
@@ -227,7 +267,7 @@ template <int RK>
 __device__ __forceinline__ long long post_addr(const Geom &g, int i, long long n, long long nplus) {
     // address of f*_i of the node with in-slab index n; nplus = index of that node + c_i
     if (RK == READ_PULL_NAT) return (long long)i * g.slab + n;
-    if (RK == READ_PULL_SWAP) return (long long)dir_opp(i) * g.slab + n;
+    if (RK == READ_PULL_SWAP) return (long long)DIR_OPP[i] * g.slab + n;
     return (long long)i * g.slab + nplus;
 }
 
@@ -240,14 +280,13 @@ __global__ void __launch_bounds__(128) k_beads_ibb(const __grid_constant__ IbbPa
     const long long nlink = *P.nlink_dev < P.maxlink ? *P.nlink_dev : P.maxlink;
     if (l < nlink) {
         const uint32_t n = P.L.node[l];
-        const int ip = P.L.dir[l], io = dir_opp(ip);
+        const int ip = P.L.dir[l], io = DIR_OPP[ip];
         part = P.L.part[l];
         const int p = part - 1;
         const double q = P.L.q[l];
         const int x = (int)(n % (uint32_t)g.xp), y = (int)((n / (uint32_t)g.xp) % (uint32_t)g.ly),
                   zg = (int)(n / ((uint32_t)g.xp * (uint32_t)g.ly));
-        int cx = 0, cy = 0, cz = 0;
-        static_for<NPOP>([&](auto ic) { constexpr int i = decltype(ic)::value; if (i == ip) { cx = dir_cx(i); cy = dir_cy(i); cz = dir_cz(i); } });
+        const int cx = DIR_CX[ip], cy = DIR_CY[ip], cz = DIR_CZ[ip];
         const double ww = ip <= 6 ? 1.0 / 18.0 : 1.0 / 36.0;
         // neighbours along the link: x_s = x_f + c, x_b = x_f - c (periodic y; z through wrap or ghosts)
         auto wrapz = [&](int z) { return z < 1 ? g.zlo_src : (z > g.lz ? g.zhi_src : z); };
@@ -372,8 +411,7 @@ __global__ void __launch_bounds__(128) k_beads_fill(const __grid_constant__ Fill
         int nn = 0, jbest = 0;
         double fbest[NPOP];
         for (int ip = 1; ip < NPOP; ++ip) {
-            int cx = 0, cy = 0, cz = 0;
-            static_for<NPOP>([&](auto ic) { constexpr int i = decltype(ic)::value; if (i == ip) { cx = dir_cx(i); cy = dir_cy(i); cz = dir_cz(i); } });
+            const int cx = DIR_CX[ip], cy = DIR_CY[ip], cz = DIR_CZ[ip];
             const int kx = x + cx;
             if (kx < 0 || kx >= g.lx) continue;
             const int ky = (y + cy < 0) ? g.ly - 1 : (y + cy >= g.ly ? 0 : y + cy);
