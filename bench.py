@@ -239,50 +239,70 @@ def main():
 
     scheme = {"aa": capi.SCHEME_AA, "ab": capi.SCHEME_AB, "auto": capi.SCHEME_AUTO}[args.scheme]
     math_mode = capi.MATH_FAST if args.math == "fast" else capi.MATH_STRICT
-    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local_rank, scheme=scheme,
-                          math_mode=math_mode, nccl_id=nccl_id, overlap=not args.no_overlap, allocate_host=False,
-                          ipart=args.particles > 0)
     if args.particles > 0:
         args.halo = "nccl"              # the particle path keeps its halo on NCCL
-    halo = "none"
-    if world > 1:
-        halo = "nccl"
-        if args.halo == "peer":
-            def allgather_bytes(b):
-                t = torch.tensor(list(b), dtype=torch.uint8)
-                out = [torch.zeros_like(t) for _ in range(world)]
-                dist.all_gather(out, t)
-                return [bytes(o.tolist()) for o in out]
-            sim.connect_halo(allgather_bytes)
-            halo = "peer"
     nodes_global = nx * ny * nz
-    args.scheme = "ab" if sim.counters()["scheme"] == capi.SCHEME_AB else "aa"     # what AUTO resolved to
     device_init = args.device_init or args.workload == "c4"
-    do_e2e = not args.no_e2e and not device_init
+    do_e2e = not args.no_e2e and not device_init and args.particles == 0
 
-    # synthetic initial state (turbulent set: log-law + perturbation + seeded noise)
-    if device_init:
-        sim.FORCING()
-        sim.init_channel_device(A9=0.3, noise_amp=1e-3 * sim.v.ustar, seed=54321)
-    else:
-        sim.allocarray(pinned=True)
-        sim.initvel(A9=0.3)
-        sim.add_hash_noise(1e-3 * sim.v.ustar, seed=54321)
-        sim.FORCING()
-        sim.initpop()
-        sim.upload_f()
+    def fresh_nccl_id():
+        if world == 1:
+            return None
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.tensor(list(capi.nccl_unique_id()), dtype=torch.uint8)
+        dist.broadcast(idt, src=0)
+        return bytes(idt.tolist())
 
-    if args.particles > 0:
-        # spheres on a regular lattice with more than mingap clearance, released from rest
-        pitch = 2.0 * args.rad + 8.0
-        slots = [(pitch * (i + 0.5) + 2.0, pitch * (j + 0.5), pitch * (k + 0.5))
-                 for k in range(int(nz // pitch)) for j in range(int(ny // pitch)) for i in range(int((nx - 4) // pitch))]
-        if len(slots) < args.particles:
-            raise SystemExit("bench: %d spheres of radius %g do not fit %dx%dx%d" % (args.particles, args.rad, nx, ny, nz))
-        stride = len(slots) / float(args.particles)
-        pos = np.array([slots[int(i * stride)] for i in range(args.particles)], dtype=np.float64)
-        sim.particles_init(pos, args.rad)
-        do_e2e = False
+    def all_ok(ok):
+        """True when every rank says ok (the ranks must take the same branch afterwards)"""
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
+
+    def build_sim(halo_req, nccl_id):
+        """the channel on this rank's slab with its synthetic initial state; returns (sim, halo actually in use)"""
+        sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local_rank, scheme=scheme,
+                              math_mode=math_mode, nccl_id=nccl_id, overlap=not args.no_overlap, allocate_host=False,
+                              ipart=args.particles > 0)
+        halo = "none"
+        if world > 1:
+            halo = "nccl"
+            if halo_req == "peer":
+                def allgather_bytes(b):
+                    t = torch.tensor(list(b), dtype=torch.uint8)
+                    out = [torch.zeros_like(t) for _ in range(world)]
+                    dist.all_gather(out, t)
+                    return [bytes(o.tolist()) for o in out]
+                # collective: either every rank maps its neighbours or none does (d3q19_ipc_connect agrees by all-reduce)
+                halo = "peer" if sim.connect_halo(allgather_bytes) else "nccl"
+        # synthetic initial state (turbulent set: log-law + perturbation + seeded noise)
+        if device_init:
+            sim.FORCING()
+            sim.init_channel_device(A9=0.3, noise_amp=1e-3 * sim.v.ustar, seed=54321)
+        else:
+            sim.allocarray(pinned=True)
+            sim.initvel(A9=0.3)
+            sim.add_hash_noise(1e-3 * sim.v.ustar, seed=54321)
+            sim.FORCING()
+            sim.initpop()
+            sim.upload_f()
+        if args.particles > 0:
+            # spheres on a regular lattice with more than mingap clearance, released from rest
+            pitch = 2.0 * args.rad + 8.0
+            slots = [(pitch * (i + 0.5) + 2.0, pitch * (j + 0.5), pitch * (k + 0.5))
+                     for k in range(int(nz // pitch)) for j in range(int(ny // pitch)) for i in range(int((nx - 4) // pitch))]
+            if len(slots) < args.particles:
+                raise SystemExit("bench: %d spheres of radius %g do not fit %dx%dx%d" % (args.particles, args.rad, nx, ny, nz))
+            stride = len(slots) / float(args.particles)
+            pos = np.array([slots[int(i * stride)] for i in range(args.particles)], dtype=np.float64)
+            sim.particles_init(pos, args.rad)
+        return sim, halo
+
+    sim, halo = build_sim(args.halo, nccl_id)
+    args.scheme = "ab" if sim.counters()["scheme"] == capi.SCHEME_AB else "aa"     # what AUTO resolved to
 
     def advance(n):
         if args.particles > 0:
@@ -295,8 +315,23 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                 # nvidia-smi needs ~0.1 s to deliver its first sample: start before the warm-up
-    advance(args.warmup)
-    sim.sync()
+    ok = True
+    try:
+        advance(args.warmup)
+        sim.sync()
+    except RuntimeError as exc:          # the halo watchdog (d3q19_sync): a neighbour's flag never arrived
+        ok = False
+        sys.stderr.write("bench[rank %d]: %s\n" % (rank, exc))
+    if not all_ok(ok):
+        if halo != "peer":
+            raise SystemExit("bench: the warm-up failed")
+        # the peer-memory halo does not work on this box: rebuild everything on the NCCL transport
+        if rank == 0:
+            sys.stderr.write("bench: peer-memory halo failed, falling back to NCCL send/recv\n")
+        sim.close()
+        sim, halo = build_sim("nccl", fresh_nccl_id())
+        advance(args.warmup)
+        sim.sync()
     c0 = sim.counters()
     barrier(); sim.sync()
     sampler.mark()

@@ -414,7 +414,11 @@ class ChannelFlow:
         blobs = allgather(bytes(blob))
         assert len(blobs) == self.nranks and all(len(b) == capi.IPC_BYTES for b in blobs)
         buf = (C.c_ubyte * (capi.IPC_BYTES * self.nranks)).from_buffer_copy(b"".join(blobs))
-        capi.check(self.L.d3q19_ipc_connect(self.h, buf))
+        rc = self.L.d3q19_ipc_connect(self.h, buf)
+        if rc == 2:          # agreed by all ranks: peer memory is not available, the halo stays on NCCL
+            return False
+        capi.check(rc)
+        return True
 
     # ---- raw C-ABI conveniences (tests, bench) ------------------------------------------------
     def upload_f(self, f=None):

@@ -107,7 +107,8 @@ struct d3q19_handle {
     // halo in peer memory (cudaIpc): [0] = lower neighbour (mzm), [1] = upper neighbour (mzp)
     bool halo_on = false;
     unsigned int halo_epoch = 0;
-    unsigned int *halo_flags = nullptr;          // local: [0] wait_lo, [1] wait_hi, [2..3] block counters
+    unsigned int *halo_flags = nullptr;          // local: [0] wait_lo, [1] wait_hi, [2..3] block counters, [8] watchdog
+    unsigned long long halo_timeout_ns = 30ull * 1000000000ull;   // D3Q19_HALO_TIMEOUT_S
     void *peer_base[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // opened A_alloc, B_alloc, flags
     double *peer_A[2] = {nullptr, nullptr}, *peer_B[2] = {nullptr, nullptr};
     unsigned int *peer_flags[2] = {nullptr, nullptr};
@@ -156,7 +157,7 @@ static int ensure_stage(d3q19_handle *h) {
 static int wait_exchange(d3q19_handle *h) {
     if (h->halo_on && h->halo_epoch > 0) {
         // the neighbours' stores of the last halo step must have landed before anybody reads the planes
-        k_halo_wait<<<1, 1, 0, h->sc>>>(h->halo_flags, h->halo_flags + 1, h->halo_epoch);
+        k_halo_wait<<<1, 1, 0, h->sc>>>(h->halo_flags, h->halo_flags + 1, h->halo_epoch, h->halo_flags + 8, h->halo_timeout_ns);
         CK(cudaGetLastError());
     }
     if (h->exchange_pending) {
@@ -358,6 +359,15 @@ extern "C" int d3q19_sync(d3q19_handle *h) {
     if (h->halo_on) RK_(wait_exchange(h));       // the neighbours' stores of the last step have landed
     CK(cudaStreamSynchronize(h->sc));
     CK(cudaStreamSynchronize(h->sx));
+    if (h->halo_on) {
+        // watchdog of the flag waits (kernels.cuh halo_spin): a neighbour's flag that never came
+        unsigned int bad = 0;
+        CK(cudaMemcpy(&bad, h->halo_flags + 8, sizeof bad, cudaMemcpyDeviceToHost));
+        if (bad)
+            return fail("d3q19_sync: rank %d waited more than %.0f s for a neighbour's halo flag of step %u; the populations "
+                        "are void (a neighbour rank died or peer memory is broken)", h->cfg.rank,
+                        (double)h->halo_timeout_ns * 1e-9, bad);
+    }
     return 0;
 }
 
@@ -448,6 +458,10 @@ extern "C" int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs) {
         fail("d3q19_ipc_connect: peer memory unavailable on %d rank(s)%s%s; the halo stays on NCCL", (int)nfail,
              failed ? ": " : "", failed ? why.c_str() : "");
         return 2;
+    }
+    if (const char *t = getenv("D3Q19_HALO_TIMEOUT_S")) {
+        const double sec = atof(t);
+        if (sec > 0.0) h->halo_timeout_ns = (unsigned long long)(sec * 1e9);
     }
     h->halo_on = true;
     return 0;
@@ -641,6 +655,8 @@ static int launch_step_halo(d3q19_handle *h, const StepParams &p0) {
     q.sig_dn = h->peer_flags[0] + 1;      // the lower neighbour's wait_hi
     q.sig_up = h->peer_flags[1];          // the upper neighbour's wait_lo
     q.ctr = h->halo_flags + 2;
+    q.err = h->halo_flags + 8;
+    q.timeout_ns = h->halo_timeout_ns;
     q.epoch = ++h->halo_epoch;
     const dim3 gr = grid_nodes(h, h->g.lz);
     q.nblk_face = gr.x * gr.y;

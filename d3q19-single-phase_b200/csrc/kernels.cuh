@@ -88,9 +88,29 @@ struct Halo {
     unsigned int *wait_lo, *wait_hi;    // local flags raised by the lower / upper neighbour
     unsigned int *sig_up, *sig_dn;      // remote flags: the upper neighbour's wait_lo, the lower's wait_hi
     unsigned int *ctr;                  // two local block counters (plane 1, plane lz)
+    unsigned int *err;                  // local watchdog word: the epoch whose flag never arrived, or 0
+    unsigned long long timeout_ns;      // how long a boundary block spins before it gives up
     unsigned int epoch;                 // number of this halo step (1, 2, ...)
     unsigned int nblk_face;             // blocks per plane
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *flag >= want.  A neighbour that died (or a broken peer mapping) must not hang the GPU:
+// after timeout_ns the waiter records `want` in *err and goes on -- the results are then void and
+// d3q19_sync reports the failure.  Once *err is set every later waiter leaves at once.
+__device__ __forceinline__ void halo_spin(const volatile unsigned int *flag, unsigned int want,
+                                          unsigned int *err, unsigned long long timeout_ns) {
+    if (*flag >= want) return;
+    const unsigned long long t0 = global_ns();
+    while (*flag < want) {
+        if (*(volatile unsigned int *)err != 0u) return;
+        if (global_ns() - t0 > timeout_ns) { atomicMax(err, want ? want : 1u); return; }
+    }
+}
 
 struct StepParams {
     Geom g;
@@ -263,7 +283,7 @@ __global__ void __launch_bounds__(BLOCK_X, SK == STEP_AA_ODD ? D3Q_MIN_BLOCKS_OD
         if (zg_blk == 1 || zg_blk == g.lz) {
             if (threadIdx.x == 0) {
                 const volatile unsigned int *fl = (zg_blk == 1) ? p.halo.wait_lo : p.halo.wait_hi;
-                while (*fl + 1u < p.halo.epoch) { }
+                halo_spin(fl, p.halo.epoch - 1u, p.halo.err, p.halo.timeout_ns);
                 __threadfence_system();
             }
             __syncthreads();
@@ -459,8 +479,10 @@ __global__ void __launch_bounds__(BLOCK_X) k_init_channel(const __grid_constant_
 }
 
 // readers of the ghost planes (download, macrovar, probe, profiles) run after the neighbours' stores
-__global__ void k_halo_wait(const volatile unsigned int *lo, const volatile unsigned int *hi, unsigned int epoch) {
-    while (*lo < epoch || *hi < epoch) { }
+__global__ void k_halo_wait(const volatile unsigned int *lo, const volatile unsigned int *hi, unsigned int epoch,
+                            unsigned int *err, unsigned long long timeout_ns) {
+    halo_spin(lo, epoch, err, timeout_ns);
+    halo_spin(hi, epoch, err, timeout_ns);
     __threadfence_system();
 }
 

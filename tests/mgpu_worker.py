@@ -65,7 +65,8 @@ def main():
             z0, z1 = sim.globalz, sim.globalz + sim.lz
             sim.FORCING()
             if halo == "peer":
-                sim.connect_halo(allgather_bytes)
+                if not sim.connect_halo(allgather_bytes):
+                    raise RuntimeError("peer-memory halo unavailable between the GPUs of this box: " + ctx[0])
             sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
             w.macrovar()
             out = np.empty((sim.lz, ny, nx, 19))
