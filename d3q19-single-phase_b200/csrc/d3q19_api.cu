@@ -108,6 +108,8 @@ struct d3q19_handle {
     bool halo_on = false;
     unsigned int halo_epoch = 0;
     unsigned int *halo_flags = nullptr;          // local: [0] wait_lo, [1] wait_hi, [2..3] block counters, [8] watchdog
+    int halo_split_min = 64;      // peer-memory halo: slabs at least this thick run boundary and interior as two launches
+    long long pf_ahead = 0;       // AA steps: L2 prefetch distance in elements (kernels.cuh "Software prefetch")
     unsigned long long halo_timeout_ns = 30ull * 1000000000ull;   // D3Q19_HALO_TIMEOUT_S
     void *peer_base[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // opened A_alloc, B_alloc, flags
     double *peer_A[2] = {nullptr, nullptr}, *peer_B[2] = {nullptr, nullptr};
@@ -295,6 +297,15 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
     g.zlo_src = cfg->nranks == 1 ? g.lz : 0;
     g.zhi_src = cfg->nranks == 1 ? 1 : g.lz + 1;
     h->nfield = (size_t)g.plane * g.lz;
+    {
+        // prefetch about 128 thread blocks ahead of the running front, in whole x-rows (measured optimum on
+        // B200: profiles/r01c_prefetch_sweep.md); D3Q19_PF_BLOCKS overrides, 0 switches it off
+        int pf_blocks = 128;
+        if (const char *t = getenv("D3Q19_PF_BLOCKS")) pf_blocks = atoi(t);
+        const int blocks_per_row = (g.lx + BLOCK_X - 1) / BLOCK_X;
+        const long long rows = pf_blocks > 0 ? (pf_blocks + blocks_per_row - 1) / blocks_per_row : 0;
+        h->pf_ahead = rows * g.xp;
+    }
     if (h->cfg.scheme == D3Q19_SCHEME_AUTO) {
         // two arrays (one-step pull) when they fit comfortably, else in place
         size_t free_b = 0, total_b = 0;
@@ -459,6 +470,7 @@ extern "C" int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs) {
              failed ? ": " : "", failed ? why.c_str() : "");
         return 2;
     }
+    if (const char *t = getenv("D3Q19_HALO_SPLIT_MIN")) h->halo_split_min = atoi(t);
     if (const char *t = getenv("D3Q19_HALO_TIMEOUT_S")) {
         const double sec = atof(t);
         if (sec > 0.0) h->halo_timeout_ns = (unsigned long long)(sec * 1e9);
@@ -640,7 +652,10 @@ static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int 
     return 0;
 }
 
-// one launch for the whole slab, boundary planes first, halo stored into the neighbours' memory
+// Halo stored into the neighbours' memory.  Thin slabs: ONE launch for the whole slab, boundary planes first
+// in block order.  Thick slabs (lz >= halo_split_min): the two boundary planes run the halo instantiation,
+// the interior the plain one (which needs fewer registers -- the AA odd step keeps its 4 CTAs/SM); the
+// order of the two launches is free, no node of one reads or writes an address the other writes.
 template <int SK, bool STRICT, bool GENERIC>
 static int launch_step_halo(d3q19_handle *h, const StepParams &p0) {
     StepParams p = p0;
@@ -658,12 +673,14 @@ static int launch_step_halo(d3q19_handle *h, const StepParams &p0) {
     q.err = h->halo_flags + 8;
     q.timeout_ns = h->halo_timeout_ns;
     q.epoch = ++h->halo_epoch;
-    const dim3 gr = grid_nodes(h, h->g.lz);
+    const bool split = h->g.lz >= h->halo_split_min && h->g.lz > 2;
+    const dim3 gr = grid_nodes(h, split ? 2 : h->g.lz);
     q.nblk_face = gr.x * gr.y;
     if (h->idx32) k_step<SK, STRICT, GENERIC, uint32_t, true><<<gr, BLOCK_X, 0, h->sc>>>(p);
     else k_step<SK, STRICT, GENERIC, unsigned long long, true><<<gr, BLOCK_X, 0, h->sc>>>(p);
     CK(cudaGetLastError());
     h->n_step_kernels++;
+    if (split) RK_((launch_step_range<SK, STRICT, GENERIC>(h, p0, 2, h->g.lz - 2, h->sc)));
     if (ab) {                             // the neighbours swap their arrays in lockstep
         for (int d = 0; d < 2; ++d) { double *t = h->peer_A[d]; h->peer_A[d] = h->peer_B[d]; h->peer_B[d] = t; }
     }
@@ -726,6 +743,7 @@ static int collide_stream_impl(d3q19_handle *h, int macro_mode, unsigned long lo
                 h->cfg.omegepsl, h->cfg.omegepslj, h->cfg.omegxx};
     p.Fx = h->Fx; p.Fy = h->Fy; p.Fz = h->Fz;
     p.rho_shift = h->rho_shift;
+    p.pf_ahead = h->pf_ahead;
     p.macro_mode = macro_mode;
     const bool generic = macro_mode != D3Q19_MACRO_MAIN || h->ffx || h->solid || h->rho_shift != 0.0;
     if (macro_mode != D3Q19_MACRO_MAIN) RK_(ensure_macro_arrays(h));

@@ -31,14 +31,20 @@ enum StepKind { STEP_AB = 0, STEP_AA_EVEN = 1, STEP_AA_ODD = 2 };
 #define D3Q_BLOCK_X 128
 #endif
 // Resident CTAs per SM the step kernels are compiled for.  Measured on B200 (profiles/
-// r01_variant_sweep.md): AB and AA-even sit at the DRAM limit with 4 CTAs (<= 128 registers);
-// the AA odd step, which keeps 19 addresses live across the collision, is FASTER with 3 CTAs
-// and 155 registers than squeezed into 128 (1.70 ms vs 1.80 ms on 512x256x256).
+// r01_variant_sweep.md, r01c_prefetch_sweep.md): AB and AA-even sit at the DRAM limit with 4 CTAs
+// (<= 128 registers).  The AA odd step keeps 19 addresses live across the collision; without the L2
+// prefetch it is faster with 3 CTAs and 155 registers (1.70 ms) than squeezed into 128 (1.78 ms,
+// one load sinks below the collision), with the prefetch 4 CTAs win (1.55 ms vs 1.65 ms).
 #ifndef D3Q_MIN_BLOCKS
 #define D3Q_MIN_BLOCKS 4
 #endif
 #ifndef D3Q_MIN_BLOCKS_ODD
-#define D3Q_MIN_BLOCKS_ODD 3
+#define D3Q_MIN_BLOCKS_ODD 4
+#endif
+// the other AA odd instantiations (run-time macro mode / force field / solid mask, strict arithmetic,
+// halo in peer memory) need more registers and would spill at 128
+#ifndef D3Q_MIN_BLOCKS_ODD_WIDE
+#define D3Q_MIN_BLOCKS_ODD_WIDE 3
 #endif
 constexpr int BLOCK_X = D3Q_BLOCK_X;
 
@@ -49,6 +55,24 @@ constexpr int BLOCK_X = D3Q_BLOCK_X;
 #ifndef D3Q_ADDR                 // 0: wall handled by an offset select; 1: by a predicated second access
 #define D3Q_ADDR 0
 #endif
+// TIMING EXPERIMENTS ONLY (tools/kernel_sweep.py; results are wrong): bit 0 = the AA odd step stores
+// x-aligned, bit 1 = it also loads x-aligned.  Never set in the shipped library.
+#ifndef D3Q_EXP
+#define D3Q_EXP 0
+#endif
+
+// Software prefetch into L2: the step kernels are bound by memory latency at
+// 12-16 resident warps per SM (ncu: long-scoreboard stalls, 0.39 eligible warps per cycle), so in the
+// in-place (AA) steps one lane per 128-byte line asks L2 for the lines `pf_ahead` elements further
+// down each population.  Every (population, node) element is read exactly once per step, so the
+// lines of "my own node shifted ahead" are exactly what the blocks launched a little later will
+// read; it holds no registers across the collision.  Measured on B200, 512x256x256
+// (profiles/r01c_prefetch_sweep.md): ~128 blocks ahead is best (AA odd 1.706 -> 1.550 ms together with
+// 4 CTAs/SM, AA even 1.519 -> 1.503 ms); >= 1 plane ahead thrashes L2; the two-array AB step gets
+// SLOWER with any distance (1.512 -> 1.58 ms) and does not prefetch.
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
 
 __device__ __forceinline__ double pop_load(const double *p) {
 #if D3Q_HINT == 1
@@ -121,6 +145,7 @@ struct StepParams {
     Mrt mrt;
     double Fx, Fy, Fz;    // uniform force (FORCING, collision.f90:522-524)
     double rho_shift;     // pending avedensity shift (collision.f90:505-511)
+    long long pf_ahead;   // AA steps: L2 prefetch distance in elements (whole x-rows), 0 = off
     // generic instantiation only:
     int macro_mode;       // D3Q19_MACRO_*
     double *rho;          // device arrays [lz][ly][xp]
@@ -195,6 +220,9 @@ struct Gather {
     }
     template <class IDX>
     static __device__ __forceinline__ double load(const double *A, const Geom &g, const NodeIdx<IDX> &k) {
+#if D3Q_EXP & 2
+        if (RK == READ_PULL_SWAP) return pop_load(A + offset(g, k) + cx);
+#endif
 #if D3Q_ADDR == 0
         return pop_load(A + offset(g, k));
 #else
@@ -228,6 +256,9 @@ struct Gather {
     // AA odd: the post-collision value of direction opp(I) goes back to where f_I came from
     template <class IDX>
     static __device__ __forceinline__ void store_back(double *A, const Geom &g, const NodeIdx<IDX> &k, double v) {
+#if D3Q_EXP & 1
+        pop_store(A + offset(g, k) + cx, v); return;
+#endif
 #if D3Q_ADDR == 0
         pop_store(A + offset(g, k), v);
 #else
@@ -272,7 +303,9 @@ __device__ __forceinline__ void block_max_to(unsigned long long *dst, double v) 
 // HALO = true : z-slab run with the halo in peer memory; one launch covers the whole slab with the
 //                two boundary planes first in block order (blockIdx.z 0 -> plane 1, 1 -> plane lz).
 template <int SK, bool STRICT, bool GENERIC, class IDX, bool HALO = false>
-__global__ void __launch_bounds__(BLOCK_X, SK == STEP_AA_ODD ? D3Q_MIN_BLOCKS_ODD : D3Q_MIN_BLOCKS) k_step(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(BLOCK_X, SK != STEP_AA_ODD ? D3Q_MIN_BLOCKS
+                                            : ((STRICT || GENERIC || HALO) ? D3Q_MIN_BLOCKS_ODD_WIDE : D3Q_MIN_BLOCKS_ODD))
+k_step(const __grid_constant__ StepParams p) {
     const Geom &g = p.g;
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     double rhoerr = 0.0;
@@ -293,6 +326,13 @@ __global__ void __launch_bounds__(BLOCK_X, SK == STEP_AA_ODD ? D3Q_MIN_BLOCKS_OD
         const NodeIdx<IDX> k = make_node<IDX>(g, x, blockIdx.y, zg_blk);
         constexpr int RK = (SK == STEP_AB) ? READ_PULL_NAT : (SK == STEP_AA_EVEN ? READ_DIRECT : READ_PULL_SWAP);
         double f[NPOP];
+        if (SK != STEP_AB && p.pf_ahead > 0 && (threadIdx.x & 15) == 0) {
+            const long long ahead = (long long)k.n + p.pf_ahead;
+            if (ahead < g.slab) {          // stays inside the population (the last rows run into the upper ghost plane)
+#pragma unroll
+                for (int i = 0; i < NPOP; ++i) prefetch_l2(p.A + (long long)i * g.slab + ahead);
+            }
+        }
         gather19<RK>(p.A, g, k, f);
 
         double Fx = p.Fx, Fy = p.Fy, Fz = p.Fz;

@@ -53,7 +53,9 @@ def main():
     cases = [((24, 6, 4 * world), True, "nccl"), ((33, 5, 3 * world + 1), True, "nccl"), ((16, 4, world), True, "nccl"),
              ((24, 6, 4 * world), False, "nccl"), ((40, 3, 2 * world), True, "nccl"),
              ((24, 6, 4 * world), True, "peer"), ((33, 5, 3 * world + 1), True, "peer"), ((40, 3, 2 * world), True, "peer"),
-             ((130, 7, 2 * world + 1), True, "peer")]
+             ((130, 7, 2 * world + 1), True, "peer"),
+             # thick-slab mode of the peer halo: boundary planes and interior as two launches
+             ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split")]
     for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
         for (nx, ny, nz), overlap, halo in cases:
             ctx[0] = "scheme %d case %s overlap %s halo %s" % (scheme, (nx, ny, nz), overlap, halo)
@@ -64,8 +66,12 @@ def main():
                                   math_mode=capi.MATH_STRICT, nccl_id=new_id(), overlap=overlap)
             z0, z1 = sim.globalz, sim.globalz + sim.lz
             sim.FORCING()
-            if halo == "peer":
-                if not sim.connect_halo(allgather_bytes):
+            if halo.startswith("peer"):
+                if halo == "peer-split":
+                    os.environ["D3Q19_HALO_SPLIT_MIN"] = "3"
+                connected = sim.connect_halo(allgather_bytes)
+                os.environ.pop("D3Q19_HALO_SPLIT_MIN", None)
+                if not connected:
                     raise RuntimeError("peer-memory halo unavailable between the GPUs of this box: " + ctx[0])
             sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
             w.macrovar()
@@ -190,6 +196,33 @@ def main():
                 ferr = np.max(np.abs(g["fHIp"] - pt.fHIp)) / np.max(np.abs(pt.fHIp))
                 chk("moving force %d err %g" % (step, ferr), bool(ferr < 1e-6))   # refills next to a face may pick another source
             sim.close(); w.close()
+
+    # halo watchdog: the last rank never steps; a neighbour waiting for its flag must give up after the
+    # timeout and d3q19_sync must say so (kernels.cuh halo_spin) -- a dead rank may not hang the others' GPUs
+    if ok:
+        ctx[0] = "halo watchdog"
+        os.environ["D3Q19_HALO_TIMEOUT_S"] = "1.5"
+        nx, ny, nz = 24, 6, 4 * world
+        sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local, scheme=capi.SCHEME_AB,
+                              nccl_id=new_id(), allocate_host=False)
+        sim.FORCING()
+        if not sim.connect_halo(allgather_bytes):
+            raise RuntimeError("peer-memory halo unavailable")
+        sim.init_channel_device(A9=0.0, noise_amp=1e-4)
+        del os.environ["D3Q19_HALO_TIMEOUT_S"]
+        stalled = world - 1
+        msg = ""
+        if rank != stalled:
+            sim.run_device(3)          # step 2 needs the stalled rank's flag of step 1
+            try:
+                sim.sync()
+            except capi.D3Q19Error as exc:
+                msg = str(exc)
+        dist.barrier()
+        is_nb = rank in ((stalled + 1) % world, (stalled - 1) % world) and rank != stalled
+        if is_nb:
+            chk("neighbour of the stalled rank reports the timeout: %r" % msg, "halo flag" in msg)
+        sim.close()
 
     t = torch.tensor([1 if ok else 0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
