@@ -52,8 +52,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
-    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
-                    help="z-face exchange: stores into the neighbour GPU's memory over NVLink (default) or NCCL send/recv")
+    ap.add_argument("--halo", default="nccl", choices=["peer", "nccl"],
+                    help="z-face exchange: NCCL send/recv of the packed faces on a second stream, overlapped with the interior "
+                         "(default; equal or faster in every configuration measured, profiles/r01d_halo_transports.md) or "
+                         "stores into the neighbour GPU's memory over NVLink inside the step kernel")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--particles", type=int, default=0,
                     help="configs[4]: N finite-size spheres (interpolated bounce-back, refill, momentum-exchange force); "

@@ -25,6 +25,7 @@ SYMBOLS = [
     "d3q19_init_channel", "d3q19_set_force_uniform", "d3q19_set_force_field",
     "d3q19_collide_stream", "d3q19_run", "d3q19_macrovar", "d3q19_rhoupdat", "d3q19_avedensity", "d3q19_probe",
     "d3q19_prerelax", "d3q19_set_solid_mask", "d3q19_set_particles", "d3q19_profiles", "d3q19_diag",
+    "d3q19_vortcalc", "d3q19_download_vort",
     "d3q19_particles_init", "d3q19_beads_links", "d3q19_beads_collision", "d3q19_beads_lubforce", "d3q19_beads_move",
     "d3q19_beads_filling", "d3q19_particle_step", "d3q19_get_particles", "d3q19_get_links", "d3q19_get_mask",
     "d3q19_timer_start", "d3q19_timer_stop", "d3q19_get_counters",
@@ -119,6 +120,8 @@ def load():
     L.d3q19_set_particles.argtypes = [vp, C.c_int32, dp, dp, dp]
     L.d3q19_profiles.argtypes = [vp, dp]
     L.d3q19_diag.argtypes = [vp, C.c_double, dp]
+    L.d3q19_vortcalc.argtypes = [vp]
+    L.d3q19_download_vort.argtypes = [vp, dp, dp, dp]
     i64p = C.POINTER(C.c_int64)
     L.d3q19_particles_init.argtypes = [vp, C.c_int32, C.POINTER(ParticleParams)]
     L.d3q19_beads_links.argtypes = [vp, i64p]

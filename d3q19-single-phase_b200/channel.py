@@ -293,6 +293,14 @@ class ChannelFlow:
             d[k] = int(d[k])
         return d
 
+    def vortcalc(self):
+        """saveload.f90:3929-4054 on the device: vorticity of the velocity field of the last macrovar;
+        returns this rank's (ox, oy, oz)[iz, iy, ix] (the reference's ox,oy,oz(lx,ly,lz), var_inc.f90:140)."""
+        o = [np.zeros((self.lz, self.ly, self.lx)) for _ in range(3)]
+        capi.check(self.L.d3q19_vortcalc(self.h))
+        capi.check(self.L.d3q19_download_vort(self.h, *[capi.dptr(a) for a in o]))
+        return o
+
     def profiles(self):
         out = np.zeros((11, self.lx))
         capi.check(self.L.d3q19_profiles(self.h, capi.dptr(out)))
@@ -354,7 +362,21 @@ class ChannelFlow:
         capi.check(self.L.d3q19_particles_init(self.h, self.npart, C.byref(prm)))
         self.set_particles(ypglb, wp, omgp)
 
+    def set_solid_mask(self, ibnodes, isnodes=None):
+        """Static solid mask as the reference keeps it: ibnodes (-1 fluid / >0 solid) and isnodes (owning
+        particle, 1-based), both given here WITHOUT ghosts as [lz, ly, lx]; the C-ABI takes the reference's
+        ghosted ibnodes(0:lx+1,0:ly+1,0:lz+1) (para.f90:442), so the ghost shell is added (fluid)."""
+        if ibnodes is None:
+            capi.check(self.L.d3q19_set_solid_mask(self.h, None, None))
+            return
+        gh = np.full((self.lz + 2, self.ly + 2, self.lx + 2), -1, dtype=np.int32)
+        gh[1:-1, 1:-1, 1:-1] = ibnodes
+        isn = None if isnodes is None else np.ascontiguousarray(isnodes, dtype=np.int32)
+        capi.check(self.L.d3q19_set_solid_mask(self.h, capi.iptr(gh), None if isn is None else capi.iptr(isn)))
+
     def set_particles(self, ypglb, wp=None, omgp=None):
+        npart = getattr(self, "npart", 0) or np.asarray(ypglb).reshape(-1, 3).shape[0]
+        self.npart = npart
         z = np.zeros((self.npart, 3))
         a = [np.ascontiguousarray(z if t is None else t, dtype=np.float64).reshape(-1, 3) for t in (ypglb, wp, omgp)]
         capi.check(self.L.d3q19_set_particles(self.h, self.npart, capi.dptr(a[0]), capi.dptr(a[1]), capi.dptr(a[2])))

@@ -74,6 +74,8 @@ struct d3q19_handle {
     int phase = 0;                // AA: 0 canonical, 1 swapped post-collision.  AB: always post-collision.
     double *rho = nullptr, *ux = nullptr, *uy = nullptr, *uz = nullptr;
     double *ffx = nullptr, *ffy = nullptr, *ffz = nullptr;
+    double *vort = nullptr;       // ox, oy, oz: 3 x nfield (vortcalc)
+    double *vort_halo = nullptr;  // exchanged velocity planes: [lo: ux,uy,uz][hi: ux,uy,uz]
     int32_t *solid = nullptr, *isn = nullptr;
     double *ypglb = nullptr, *wp = nullptr, *omgp = nullptr;
     int npart = 0;
@@ -260,7 +262,7 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
     if (h->comm) nccl_api().CommDestroy(h->comm);
     void *ptrs[] = {h->A_alloc, h->B_alloc, h->rho, h->ux, h->uy, h->uz, h->ffx, h->ffy, h->ffz, h->solid, h->isn, h->ypglb,
                     h->wp, h->omgp, h->send_up, h->send_dn, h->recv_lo, h->recv_hi, h->stage[0], h->stage[1],
-                    h->scal, h->red_d, h->red_c, h->prof_partial, h->prof_out};
+                    h->scal, h->red_d, h->red_c, h->prof_partial, h->prof_out, h->vort, h->vort_halo};
     for (void *p : ptrs) if (p) cudaFree(p);
     cudaEvent_t evs[] = {h->evB, h->evX, h->t0, h->t1, h->evC[0], h->evC[1], h->evS[0], h->evS[1]};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -608,6 +610,55 @@ extern "C" int d3q19_download_macro(d3q19_handle *h, double *rho, double *ux, do
     RK_(ensure_macro_arrays(h));
     RK_(field_to_host(h, h->rho, rho)); RK_(field_to_host(h, h->ux, ux));
     RK_(field_to_host(h, h->uy, uy)); RK_(field_to_host(h, h->uz, uz));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
+// ---- vortcalc (saveload.f90:3929-4054) ----------------------------------------------------------------
+// Works on the device rho,u arrays d3q19_macrovar made (the reference's vortcalc reads the ux,uy,uz macrovar
+// left behind).  The z phase of exchng8 (:4039-4045) is three contiguous planes each way over NCCL; its y
+// phase is the periodic index wrap.
+extern "C" int d3q19_vortcalc(d3q19_handle *h) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->rho) return fail("d3q19_vortcalc: no velocity field on the device -- call d3q19_macrovar first");
+    if (h->g.ly < 2 || h->g.lz < 2) return fail("d3q19_vortcalc: needs ly >= 2 and lz >= 2 (saveload.f90:3982-3999)");
+    const Geom &g = h->g;
+    if (!h->vort) CK(cudaMalloc(&h->vort, 3 * h->nfield * sizeof(double)));
+    VortParams p;
+    memset(&p, 0, sizeof p);
+    p.g = g;
+    p.ux = h->ux; p.uy = h->uy; p.uz = h->uz;
+    p.ox = h->vort; p.oy = h->vort + h->nfield; p.oz = h->vort + 2 * h->nfield;
+    p.solid = h->solid; p.isnodes = h->isn; p.omgp = h->omgp;
+    if (h->solid && (!h->isn || !h->omgp)) return fail("d3q19_vortcalc: solid nodes need isnodes and the particle table");
+    if (h->cfg.nranks > 1) {
+        if (!h->vort_halo) CK(cudaMalloc(&h->vort_halo, 6 * (size_t)g.plane * sizeof(double)));
+        const int up = (h->cfg.rank + 1) % h->cfg.nranks, dn = (h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks;
+        const size_t cnt = (size_t)g.plane;
+        const double *fld[3] = {h->ux, h->uy, h->uz};
+        NcclApi &n = nccl_api();
+        NK(n.GroupStart());
+        for (int c = 0; c < 3; ++c) {
+            NK(n.Send(fld[c] + (size_t)(g.lz - 1) * g.plane, cnt, NCCL_FLOAT64, up, h->comm, h->sc));   // my plane lz  -> mzp's tmpu?F
+            NK(n.Send(fld[c], cnt, NCCL_FLOAT64, dn, h->comm, h->sc));                                   // my plane 1   -> mzm's tmpu?B
+            NK(n.Recv(h->vort_halo + (size_t)c * g.plane, cnt, NCCL_FLOAT64, dn, h->comm, h->sc));
+            NK(n.Recv(h->vort_halo + (size_t)(3 + c) * g.plane, cnt, NCCL_FLOAT64, up, h->comm, h->sc));
+        }
+        NK(n.GroupEnd());
+        h->n_nccl += 12;
+        p.zlo = h->vort_halo; p.zhi = h->vort_halo + 3 * (size_t)g.plane;
+    }
+    k_vortcalc<<<grid_nodes(h, g.lz), BLOCK_X, 0, h->sc>>>(p);
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    return 0;
+}
+
+extern "C" int d3q19_download_vort(d3q19_handle *h, double *ox, double *oy, double *oz) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->vort) return fail("d3q19_download_vort: call d3q19_vortcalc first");
+    RK_(field_to_host(h, h->vort, ox)); RK_(field_to_host(h, h->vort + h->nfield, oy));
+    RK_(field_to_host(h, h->vort + 2 * h->nfield, oz));
     CK(cudaStreamSynchronize(h->sc));
     return 0;
 }

@@ -605,6 +605,68 @@ __global__ void k_probe(Geom g, const double *A, int x, int y, int zg, double Fx
     moments_strict(f, Fx, Fy, Fz, out[0], out[1], out[2], out[3]);
 }
 
+// ---- vortcalc (saveload.f90:3929-4025) ---------------------------------------------------------------
+// Vorticity of the device-resident ux,uy,uz ([lz][ly][xp], made by k_macro): central differences,
+// one-sided at the channel walls (:3971-3980), periodic in y by index wrap (the reference's tmpu?L/R
+// rows of exchng8 collapse for one rank in y), z neighbours across a slab face from the planes the
+// caller exchanged (exchng8's z phase, :4039-4045): zlo = the lower neighbour's plane lz, zhi = the
+// upper neighbour's plane 1, three fields of `plane` elements each; nullptr = one rank, periodic wrap.
+// A solid node gets twice its particle's angular velocity (:4008-4019).  Same expression order as the
+// reference without contraction: bit-identical to the oracle.
+struct VortParams {
+    Geom g;
+    const double *ux, *uy, *uz;
+    double *ox, *oy, *oz;
+    const double *zlo, *zhi;
+    const int32_t *solid, *isnodes;
+    const double *omgp;
+};
+__global__ void __launch_bounds__(BLOCK_X) k_vortcalc(const __grid_constant__ VortParams p) {
+    const Geom &g = p.g;
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.lx) return;
+    const int y = blockIdx.y, z = blockIdx.z;                  // 0-based local
+    const long long row = (long long)g.xp * (y + (long long)g.ly * z);
+    const long long m = row + x;
+    if (p.solid && !(p.solid[m] < 0)) {
+        const int id = p.isnodes[m] - 1;
+        p.ox[m] = (R(2.0) * R(p.omgp[3 * id])).v;
+        p.oy[m] = (R(2.0) * R(p.omgp[3 * id + 1])).v;
+        p.oz[m] = (R(2.0) * R(p.omgp[3 * id + 2])).v;
+        return;
+    }
+    const int ym = (y == 0) ? g.ly - 1 : y - 1, yp = (y == g.ly - 1) ? 0 : y + 1;
+    const long long rym = (long long)g.xp * (ym + (long long)g.ly * z) + x;
+    const long long ryp = (long long)g.xp * (yp + (long long)g.ly * z) + x;
+    const long long inpl = (long long)g.xp * y + x;
+    // z neighbours: inside the slab, or the exchanged planes, or the periodic wrap of a single rank
+    const double *uxm, *uym, *uxp, *uyp;
+    if (z > 0) { uxm = p.ux + m - g.plane; uym = p.uy + m - g.plane; }
+    else if (p.zlo) { uxm = p.zlo + inpl; uym = p.zlo + g.plane + inpl; }
+    else { uxm = p.ux + (long long)(g.lz - 1) * g.plane + inpl; uym = p.uy + (long long)(g.lz - 1) * g.plane + inpl; }
+    if (z < g.lz - 1) { uxp = p.ux + m + g.plane; uyp = p.uy + m + g.plane; }
+    else if (p.zhi) { uxp = p.zhi + inpl; uyp = p.zhi + g.plane + inpl; }
+    else { uxp = p.ux + inpl; uyp = p.uy + inpl; }
+    R pwx, pvx;
+    if (x == 0) {
+        pwx = R(__ddiv_rn((R(3.0) * R(p.uz[m]) + R(p.uz[m + 1])).v, 3.0));
+        pvx = R(__ddiv_rn((R(3.0) * R(p.uy[m]) + R(p.uy[m + 1])).v, 3.0));
+    } else if (x == g.lx - 1) {
+        pwx = R(__ddiv_rn(-(R(3.0) * R(p.uz[m]) + R(p.uz[m - 1])).v, 3.0));
+        pvx = R(__ddiv_rn(-(R(3.0) * R(p.uy[m]) + R(p.uy[m - 1])).v, 3.0));
+    } else {
+        pwx = R(__ddiv_rn((R(p.uz[m + 1]) - R(p.uz[m - 1])).v, 2.0));
+        pvx = R(__ddiv_rn((R(p.uy[m + 1]) - R(p.uy[m - 1])).v, 2.0));
+    }
+    const R pwy = R(__ddiv_rn((R(p.uz[ryp]) - R(p.uz[rym])).v, 2.0));
+    const R puy = R(__ddiv_rn((R(p.ux[ryp]) - R(p.ux[rym])).v, 2.0));
+    const R puz = R(__ddiv_rn((R(*uxp) - R(*uxm)).v, 2.0));
+    const R pvz = R(__ddiv_rn((R(*uyp) - R(*uym)).v, 2.0));
+    p.ox[m] = (pwy - pvz).v;
+    p.oy[m] = (puz - pwx).v;
+    p.oz[m] = (pvx - puy).v;
+}
+
 // ---- canonical AoS <-> device SoA (upload_f / download_f) ----------------------------------------
 // aos holds planes [zg0, zg0+nz) of the host layout f(0:18,lx,ly,:) without pitch.
 template <int RK>

@@ -190,6 +190,13 @@ int d3q19_profiles(d3q19_handle *h, double *out_11_by_lx);
  * wmean, urms, vrms, wrms (divided by ustar like the reference), volf, rhomax, rhomin, nfluid.       */
 int d3q19_diag(d3q19_handle *h, double ustar, double *out14);
 
+/* vortcalc + exchng8 (saveload.f90:3929-4054): vorticity of the device velocity
+ * field (call d3q19_macrovar first) by central differences, one-sided at the walls, z-neighbour planes
+ * exchanged over NCCL, solid nodes = twice the particle's angular velocity.  Bit-identical to the
+ * reference's expression order.  The arrays are the reference's ox,oy,oz(lx,ly,lz) (var_inc.f90:140).  */
+int d3q19_vortcalc(d3q19_handle *h);
+int d3q19_download_vort(d3q19_handle *h, double *ox, double *oy, double *oz);
+
 /* ---- measurement ----------------------------------------------------------------------- */
 /* CUDA events on the stream the step kernels are launched on */
 int d3q19_timer_start(d3q19_handle *h);

@@ -785,6 +785,78 @@ static void pf_macrovar(void *c, int id)
     }
 }
 
+/* ---- saveload.f90:3929-4054 -- vortcalc + exchng8 ------------------------------------------
+ * Vorticity of the velocity field held in ux,uy,uz (the caller ran macrovar): central
+ * differences, one-sided at the channel walls where the no-slip wall sits half a spacing
+ * outside the first node (:3971-3980), neighbours across a subdomain face from the planes
+ * exchng8 (:4027-4054) brings in: tmp?B = the +z neighbour's plane 1, tmp?F = the -z neighbour's
+ * plane lz, tmp?R = the +y neighbour's row 1, tmp?L = the -y neighbour's row ly.  A node inside
+ * a particle gets twice the particle's angular velocity (:4011-4020).  Results go to global
+ * arrays in the (lx,ny,nz) layout. */
+void orc_vortcalc(const orc_world *w, double *oxg, double *oyg, double *ozg)
+{
+    const orc_para *p = &w->p;
+    int id;
+    for (id = 0; id < w->nproc; ++id) {
+        const orc_rank *r = &w->r[id];
+        const orc_rank *zp = &w->r[r->mzp], *zm = &w->r[r->mzm], *yp = &w->r[r->myp], *ym = &w->r[r->mym];
+        const int lx = r->lx, ly = r->ly, lz = r->lz;
+        int i, j, k;
+#define U_(rr, a, i, j, k) ((rr)->a[(size_t)((i)-1) + (size_t)(rr)->lx * ((size_t)((j)-1) + (size_t)(rr)->ly * (size_t)((k)-1))])
+        for (k = 1; k <= lz; ++k)
+        for (j = 1; j <= ly; ++j)
+        for (i = 1; i <= lx; ++i) {
+            double ox, oy, oz;
+            if (IB_(r, i, j, k) < 0) {                                         /* :3969 */
+                double pwx, pvx, pwy, puy, puz, pvz;
+                if (i == 1) {                                                  /* :3971-3973 */
+                    pwx = (3.0 * U_(r, uz, i, j, k) + U_(r, uz, i + 1, j, k)) / 3.0;
+                    pvx = (3.0 * U_(r, uy, i, j, k) + U_(r, uy, i + 1, j, k)) / 3.0;
+                } else if (i == lx) {                                          /* :3974-3976 */
+                    pwx = -(3.0 * U_(r, uz, i, j, k) + U_(r, uz, i - 1, j, k)) / 3.0;
+                    pvx = -(3.0 * U_(r, uy, i, j, k) + U_(r, uy, i - 1, j, k)) / 3.0;
+                } else {                                                       /* :3977-3980 */
+                    pwx = (U_(r, uz, i + 1, j, k) - U_(r, uz, i - 1, j, k)) / 2.0;
+                    pvx = (U_(r, uy, i + 1, j, k) - U_(r, uy, i - 1, j, k)) / 2.0;
+                }
+                if (j == 1) {                                                  /* :3982-3984: tmpu?L = mym's row ly */
+                    pwy = (U_(r, uz, i, j + 1, k) - U_(ym, uz, i, ym->ly, k)) / 2.0;
+                    puy = (U_(r, ux, i, j + 1, k) - U_(ym, ux, i, ym->ly, k)) / 2.0;
+                } else if (j == ly) {                                          /* :3985-3987: tmpu?R = myp's row 1 */
+                    pwy = (U_(yp, uz, i, 1, k) - U_(r, uz, i, j - 1, k)) / 2.0;
+                    puy = (U_(yp, ux, i, 1, k) - U_(r, ux, i, j - 1, k)) / 2.0;
+                } else {
+                    pwy = (U_(r, uz, i, j + 1, k) - U_(r, uz, i, j - 1, k)) / 2.0;
+                    puy = (U_(r, ux, i, j + 1, k) - U_(r, ux, i, j - 1, k)) / 2.0;
+                }
+                if (k == 1) {                                                  /* :3993-3995: tmpu?F = mzm's plane lz */
+                    puz = (U_(r, ux, i, j, k + 1) - U_(zm, ux, i, j, zm->lz)) / 2.0;
+                    pvz = (U_(r, uy, i, j, k + 1) - U_(zm, uy, i, j, zm->lz)) / 2.0;
+                } else if (k == lz) {                                          /* :3996-3998: tmpu?B = mzp's plane 1 */
+                    puz = (U_(zp, ux, i, j, 1) - U_(r, ux, i, j, k - 1)) / 2.0;
+                    pvz = (U_(zp, uy, i, j, 1) - U_(r, uy, i, j, k - 1)) / 2.0;
+                } else {
+                    puz = (U_(r, ux, i, j, k + 1) - U_(r, ux, i, j, k - 1)) / 2.0;
+                    pvz = (U_(r, uy, i, j, k + 1) - U_(r, uy, i, j, k - 1)) / 2.0;
+                }
+                ox = pwy - pvz;                                                /* :4004-4006 */
+                oy = puz - pwx;
+                oz = pvx - puy;
+            } else {                                                           /* :4008-4019 */
+                const int id1 = S_(r, r->isnodes, i, j, k);
+                ox = 2.0 * w->omgp[0 + 3 * (id1 - 1)];
+                oy = 2.0 * w->omgp[1 + 3 * (id1 - 1)];
+                oz = 2.0 * w->omgp[2 + 3 * (id1 - 1)];
+            }
+            {
+                const size_t g = (size_t)(i - 1) + (size_t)p->nx * ((size_t)(j - 1 + r->globaly) + (size_t)p->ny * (size_t)(k - 1 + r->globalz));
+                oxg[g] = ox; oyg[g] = oy; ozg[g] = oz;
+            }
+        }
+#undef U_
+    }
+}
+
 /* ---- collision.f90:469-480 ----------------------------------------------------------- */
 static void pf_rhoupdat(void *c, int id);
 void orc_rhoupdat(orc_world *w) { orc_parallel_for(w->nproc, pf_rhoupdat, w); }

@@ -12,6 +12,7 @@ This script reads the reference's own sources WHERE THEY LIE (default
                   allocarray
     initial.f90   initpop, initvel
     collision.f90 collision_MRT, collisionExchnge, macrovar, rhoupdat, avedensity, FORCING, FORCINGP
+    saveload.f90  vortcalc, exchng8
 
 The translation is statement by statement: every expression keeps the Fortran evaluation
 order (left to right for equal precedence; `**` by repeated multiplication), `real` is double
@@ -732,8 +733,33 @@ class Translator:
             self.emit("ref_%s(S, %s);" % (name, ", ".join(cargs)))
             return
         if name in self.wanted:
-            cargs = [self.by_ref(parse_expr(a)) for a in args]
+            cargs, after = [], []
+            for a in args:
+                e = parse_expr(a)
+                sec = isinstance(e, Index) and self.sym(e.name) and self.sym(e.name).dims \
+                    and any(isinstance(x, Range) for x in e.args)
+                if not sec:
+                    cargs.append(self.by_ref(e))
+                    continue
+                # array-section actual argument (e.g. ux(:,1,:)): copy-in / copy-out through a contiguous
+                # temporary, which is what a Fortran compiler does for a non-contiguous section
+                s0 = self.sym(e.name)
+                shape = self.section_shape(e)
+                self.tmp_id += 1
+                t = "sec%d" % self.tmp_id
+                kind, acc = ("REF_KIND_R", "REF_R") if s0.typ == "real" else ("REF_KIND_I", "REF_I")
+                self.emit("ref_arr %s = ref_alloc_auto(%s, %d, (int[]){%s}, (int[]){%s});"
+                          % (t, kind, len(shape), ", ".join("1" for _ in shape), ", ".join(shape)))
+                op, cl, names = self.loops(shape)
+                tel = "%s%d(%s, %s)" % (acc, len(shape), t, ", ".join("1 + %s" % n for n in names))
+                self.emit("%s%s = %s;%s" % (op, tel, self.cx(e, names), cl))
+                op2, cl2, names2 = self.loops(shape)
+                tel2 = "%s%d(%s, %s)" % (acc, len(shape), t, ", ".join("1 + %s" % n for n in names2))
+                after.append("%s%s = %s;%s ref_free(&%s);" % (op2, self.cx(e, names2), tel2, cl2, t))
+                cargs.append("%s.p" % t)
             self.emit("ref_%s(%s);" % (name, ", ".join(["S"] + cargs)))
+            for a in after:
+                self.emit(a)
             return
         self.emit("/* call %s skipped (outside the translated path) */;" % name)
 
@@ -966,7 +992,7 @@ class Translator:
     def generate(self):
         self.in_case = False
         self.wanted = ["para", "allocarray", "initpop", "initvel", "collisionexchnge", "collision_mrt", "macrovar",
-                       "rhoupdat", "avedensity", "forcing", "forcingp"]
+                       "rhoupdat", "avedensity", "forcing", "forcingp", "exchng8", "vortcalc"]
         o = self.emit
         o("/* GENERATED by oracle/f90toc.py from the reference's Fortran sources -- do not edit, do not commit. */")
         o('#include "../ref_runtime.h"')
@@ -984,6 +1010,7 @@ class Translator:
         o("};")
         # prototypes (collisionExchnge is called before it is defined)
         o("void ref_collisionexchnge(ref_state *S, void *a, void *b, void *c, void *d);")
+        o("void ref_exchng8(ref_state *S, void *a, void *b, void *c, void *d, void *e, void *f, void *g, void *h);")
         # ---- parameters and fixed-shape module arrays
         self.local, self.cur_sub = {}, "var_inc"
         o("\nvoid ref_module_init(ref_state *S)\n{")
@@ -1018,10 +1045,14 @@ class Translator:
         self.translate_sub("initvel", init["initvel"], override_assignments=True)
         for n in ("collision_mrt", "collisionexchnge", "macrovar", "rhoupdat", "avedensity", "forcing", "forcingp"):
             self.translate_sub(n, coll[n])
+        # next-tier diagnostics: vorticity and its ghost-plane exchange
+        save = self.subroutines_of("saveload.f90")
+        self.translate_sub("vortcalc", save["vortcalc"])
+        self.translate_sub("exchng8", save["exchng8"])
         # ---- dispatch + reflection tables for the Python wrapper
         o("\nint ref_dispatch(ref_state *S, const char *name)\n{")
         for n in self.wanted:
-            if n == "collisionexchnge":
+            if n in ("collisionexchnge", "exchng8"):
                 continue
             o('    if (!strcmp(name, "%s")) { ref_%s(S); return 0; }' % (n, n))
         o('    if (!strcmp(name, "module_init")) { ref_module_init(S); return 0; }')

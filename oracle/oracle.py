@@ -65,6 +65,8 @@ def lib(fast=False):
                      "orc_deliver_y", "orc_deliver_z"):
             getattr(L, name).argtypes = [vp]
             getattr(L, name).restype = None
+        L.orc_vortcalc.argtypes = [vp, dp, dp, dp]
+        L.orc_vortcalc.restype = None
         L.orc_avedensity.argtypes = [vp, C.POINTER(C.c_int64)]
         L.orc_avedensity.restype = C.c_double
         L.orc_gather_f.argtypes = [vp, dp]
@@ -154,6 +156,13 @@ class World:
 
     def rhoupdat(self):
         self.L.orc_rhoupdat(self.h)
+
+    def vortcalc(self):
+        """saveload.f90:3929-4054 on the current ux,uy,uz -> global (ox, oy, oz)[iz,iy,ix]"""
+        shape = (self.para.nz, self.para.ny, self.para.nx)
+        o = [np.zeros(shape) for _ in range(3)]
+        self.L.orc_vortcalc(self.h, *[a.ctypes.data_as(C.POINTER(C.c_double)) for a in o])
+        return o
 
     def avedensity(self):
         n = C.c_int64(0)

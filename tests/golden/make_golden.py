@@ -54,16 +54,20 @@ def save(name, meta, **arrays):
     print("wrote %s.npz: %s" % (name, {k: v.shape for k, v in arrays.items()}))
 
 
-def main_loop_case(name, nx, ny, nz, npy, npz, laminar, steps, seed, a9=0.0, **ov):
+def main_loop_case(name, nx, ny, nz, npy, npz, laminar, steps, seed, a9=0.0, vort=False, **ov):
     w = start(nx, ny, nz, npy, npz, laminar, seed, a9, **ov)
     f0 = w.get_f().copy()
     w.run("macrovar")                                  # main.f90:136
     for _ in range(steps):
         w.run("collision_mrt")                         # main.f90:157
         w.run("macrovar")                              # main.f90:161
+    extra = {}
+    if vort:
+        w.run("vortcalc")                              # saveload.f90:3929 (as called by outputvort1, :1138)
+        extra = {k: w.get(k) for k in ("ox", "oy", "oz")}
     meta = dict(kind="main_loop", nx=nx, ny=ny, nz=nz, ranks=[npy, npz], laminar=laminar, steps=steps,
                 overrides=ov, scalars=scalars(w))
-    save(name, meta, f0=f0, f=w.get_f(), **{k: w.get(k) for k in FIELDS})
+    save(name, meta, f0=f0, f=w.get_f(), **extra, **{k: w.get(k) for k in FIELDS})
     w.close()
 
 
@@ -109,5 +113,6 @@ if __name__ == "__main__":
     main_loop_case("ref_lam_lbgk_7x8x8_r1x2_s60", 7, 8, 8, 1, 2, True, 60, seed=None)
     main_loop_case("ref_turb_mrt3_9x10x7_r3x2_s10", 9, 10, 7, 3, 2, False, 10, seed=777, mrttype=3, **U)
     main_loop_case("ref_turb_mrt1_39x4x3_r1x1_s8", 39, 4, 3, 1, 1, False, 8, seed=4242, **U)   # reaches the log-law branch
+    main_loop_case("ref_turb_vort_21x6x5_r2x2_s6", 21, 6, 5, 2, 2, False, 6, seed=31337, a9=0.3, vort=True, **U)
     prerelax_case("ref_prerelax_7x8x8_r2x2_i6", 7, 8, 8, 2, 2, 6, seed=99, **U)
     force_field_case("ref_forcingp_15x8x8_r2x2_s4", 15, 8, 8, 2, 2, 4, seed=5, **U)

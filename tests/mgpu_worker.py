@@ -56,6 +56,9 @@ def main():
              ((130, 7, 2 * world + 1), True, "peer"),
              # thick-slab mode of the peer halo: boundary planes and interior as two launches
              ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split")]
+    only = os.environ.get("MGPU_ONLY", "")          # e.g. "peer": just the peer-memory halo cases (short runs on many GPUs)
+    if only:
+        cases = [c for c in cases if c[2].startswith(only)]
     for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
         for (nx, ny, nz), overlap, halo in cases:
             ctx[0] = "scheme %d case %s overlap %s halo %s" % (scheme, (nx, ny, nz), overlap, halo)
@@ -89,6 +92,9 @@ def main():
                     sim.device_macrovar()
                     for k in ("rho", "ux", "uy", "uz"):
                         chk("macrovar " + k, bool(np.array_equal(getattr(sim, k), w.get(k)[z0:z1])))
+                    if sim.lz >= 2 and ny >= 2:              # vortcalc + exchng8's z phase over NCCL: bit-exact
+                        for name, got, want in zip(("ox", "oy", "oz"), sim.vortcalc(), w.vortcalc()):
+                            chk("vortcalc " + name, bool(np.array_equal(got, want[z0:z1])))
                     pr = sim.profiles()
                     ref = w.get("uy").sum(axis=(0, 1))
                     chk("profiles", bool(np.allclose(pr[1], ref, rtol=1e-12, atol=1e-13 * np.max(np.abs(ref)))))
@@ -115,7 +121,7 @@ def main():
             break
 
     # device pre-relaxation across ranks (main.f90:70-90 with MPI_ALLREDUCE MAX)
-    if ok:
+    if ok and not only:
         nx, ny, nz = 32, 8, 4 * world
         w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
         w0f, w0 = w.get_f().copy(), {k: w.get(k).copy() for k in ("rho", "ux", "uy", "uz")}
@@ -142,7 +148,7 @@ def main():
         sim.close()
 
     # particle path across slab faces: links partition exactly, IBB + forces as on one domain
-    if ok:
+    if ok and not only:
         from oracle import particles as P
         nx, ny, nz, rad = 24, 20, 8 * world, 3.6
         U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)

@@ -68,6 +68,9 @@ def test_oracle_reproduces_reference_output(path, ranks):
             w.collision_MRT(); w.macrovar()
         for k in FIELDS:
             assert np.array_equal(w.get(k), z[k]), k
+        if "ox" in z.files:                              # vortcalc, saveload.f90:3929-4054
+            for k, a in zip(("ox", "oy", "oz"), w.vortcalc()):
+                assert np.array_equal(a, z[k]), k
     assert np.array_equal(w.get_f(), z["f"])
     w.close()
 
@@ -129,5 +132,12 @@ def test_cuda_path_reproduces_reference_output(path, scheme, math_mode):
         sim.run(meta["steps"])                           # collision_MRT; macrovar per step, main.f90:157-161
         for k in FIELDS:                                 # last-step macrovar was downloaded
             check(getattr(sim, k), z[k], k)
+        if "ox" in z.files:                              # device vortcalc on the device velocity field
+            vscale = max(float(np.max(np.abs(z["oz"]))), 1e-300)
+            for k, a in zip(("ox", "oy", "oz"), sim.vortcalc()):
+                if strict:
+                    assert np.array_equal(a, z[k]), k
+                else:
+                    assert np.max(np.abs(a - z[k])) < 1e-11 * vscale, k
     check(sim.sync_f_to_host(), z["f"], "f")
     sim.close()

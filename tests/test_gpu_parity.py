@@ -324,3 +324,49 @@ def test_device_diag_matches_reference_diag(oracle, scheme):
         for k in ("umean", "vmean", "wmean", "urms", "vrms", "wrms", "volf"):
             assert abs(got[k] - ref[k]) <= 1e-10 * max(abs(ref[k]), 1e-3), k     # sums are order dependent
     sim.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("shape", [(64, 32, 32), (23, 10, 7), (130, 3, 2)])
+def test_device_vortcalc_bit_exact(oracle, scheme, shape):
+    # saveload.f90:3929-4054 on the device velocity field; the oracle's restatement is pinned bit for bit to the
+    # translated reference (tests/test_oracle_ref.py), pitch padding (nx = 23, 130) must not leak into x +- 1
+    nx, ny, nz = shape
+    w, p, sim = make_pair(oracle, nx, ny, nz, scheme=scheme, math_mode=capi.MATH_STRICT, perturb=1e-4)
+    for _ in range(3):
+        w.collision_MRT(); w.macrovar()
+        sim.collide_stream()
+    sim.device_macrovar()
+    for k in ("ux", "uy", "uz"):
+        assert np.array_equal(getattr(sim, k), w.get(k)), k
+    for name, got, want in zip(("ox", "oy", "oz"), sim.vortcalc(), w.vortcalc()):
+        assert np.array_equal(got, want), name
+    sim.close(); w.close()
+
+
+def test_device_vortcalc_solid_nodes(oracle):
+    nx, ny, nz = 24, 12, 12
+    U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+    w, p = oracle.make_initial_state(nx, ny, nz, laminar=False, noise=True, ipart=1, **U)
+    zz, yy, xx = np.meshgrid(np.arange(nz) + 0.5, np.arange(ny) + 0.5, np.arange(nx) + 0.5, indexing="ij")
+    c = np.array([11.3, 6.1, 6.4])
+    solid = (xx - c[0]) ** 2 + (yy - c[1]) ** 2 + (zz - c[2]) ** 2 < 3.1 ** 2
+    ib = np.where(solid, 1, -1).astype(np.int32)
+    isn = np.where(solid, 2, -1).astype(np.int32)
+    yp = np.zeros((2, 3)); wp = np.zeros((2, 3)); om = np.zeros((2, 3))
+    yp[1], wp[1], om[1] = c, [0.01, -0.02, 0.005], [1e-3, 2e-3, -1e-3]
+    w.set_solid(ib, isn); w.set_particles(yp, wp, om)
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, math_mode=capi.MATH_STRICT, ipart=True, **U)
+    sim.FORCING()
+    sim.upload_f(w.get_f())
+    sim.set_solid_mask(ib, isn)
+    sim.set_particles(yp, wp, om)
+    w.macrovar()
+    sim.device_macrovar()
+    for k in ("rho", "ux", "uy", "uz"):          # macrovar's solid branch, collision.f90:420-459
+        assert np.array_equal(getattr(sim, k), w.get(k)), k
+    assert np.all(sim.rho[solid] == p.rhopart)
+    for name, got, want in zip(("ox", "oy", "oz"), sim.vortcalc(), w.vortcalc()):
+        assert np.array_equal(got, want), name
+    assert np.all(got[solid] == -2e-3)
+    sim.close(); w.close()

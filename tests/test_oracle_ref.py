@@ -185,3 +185,62 @@ def test_solid_nodes_and_macrovar_solid_branch():
         ow.collision_MRT(); ow.macrovar()
         same(rw, ow, "solid step %d" % step)
     rw.close(); ow.close()
+
+
+def _vort_equal(rw, ow, what):
+    rw.run("vortcalc")
+    got = ow.vortcalc()
+    for k, g in zip(("ox", "oy", "oz"), got):
+        assert np.array_equal(rw.get(k), g), "%s %s" % (k, what)
+    return got
+
+
+@pytest.mark.parametrize("npy,npz", [(1, 1), (1, 2), (2, 2), (3, 2), (1, 4)])
+def test_vortcalc_bit_exact(npy, npz):
+    # saveload.f90:3929-4054: vorticity by central differences, one-sided at the walls, neighbour planes
+    # through exchng8 -- the translated reference (array-section arguments copied in and out) vs the restatement
+    rw, ow, p = pair(9, 12, 8, npy, npz, False, A9=0.3)
+    rw.run("macrovar"); ow.macrovar()
+    for step in range(3):
+        rw.run("collision_mrt"); rw.run("macrovar")
+        ow.collision_MRT(); ow.macrovar()
+    ox, oy, oz = _vort_equal(rw, ow, "grid %dx%d" % (npy, npz))
+    assert np.max(np.abs(oz)) > 0 and np.max(np.abs(ox)) > 0
+    # the result does not depend on the decomposition
+    p1 = orc.make_para(9, 12, 8, laminar=False)
+    o1 = orc.World(p1)
+    for k in ("ux", "uy", "uz"):
+        o1.set(k, ow.get(k))
+    for a, b in zip(o1.vortcalc(), (ox, oy, oz)):
+        assert np.array_equal(a, b)
+    rw.close(); ow.close(); o1.close()
+
+
+def test_vortcalc_solid_nodes():
+    # inside a particle the vorticity is twice the particle's angular velocity (saveload.f90:4008-4019)
+    nx, ny, nz = 11, 12, 12
+    rw = ref.RefWorld(nx, ny, nz, nprocY=1, nprocZ=2, laminar=False, ipart=True)
+    para = orc.make_para(nx, ny, nz, laminar=False, nprocY=1, nprocZ=2, ipart=1)
+    ow = orc.World(para)
+    rw.run("initvel"); ow.initvel(0.0)
+    for k, d in zip(("ux", "uy", "uz"), orc.synthetic_velocity(nx, ny, nz, para.ustar)):
+        rw.set(k, rw.get(k) + d); ow.set(k, ow.get(k) + d)
+    rw.run("forcing"); ow.FORCING()
+    rw.run("initpop"); ow.initpop()
+    zz, yy, xx = np.meshgrid(np.arange(nz) + 0.5, np.arange(ny) + 0.5, np.arange(nx) + 0.5, indexing="ij")
+    c = np.array([5.3, 6.1, 6.4])
+    solid = (xx - c[0]) ** 2 + (yy - c[1]) ** 2 + (zz - c[2]) ** 2 < 2.6 ** 2
+    ib = np.where(solid, 1, -1).astype(np.int32)
+    isn = np.where(solid, 3, -1).astype(np.int32)
+    npart = rw.array("ypglb")[0].shape[0]
+    yp = np.zeros((npart, 3)); wp = np.zeros((npart, 3)); om = np.zeros((npart, 3))
+    yp[2], wp[2], om[2] = c, [0.01, -0.02, 0.005], [1e-3, 2e-3, -1e-3]
+    rw.set_solid(ib, isn); ow.set_solid(ib, isn)
+    for r in range(rw.nproc):
+        for name, a in (("ypglb", yp), ("wp", wp), ("omgp", om)):
+            rw.array(name, r)[0][...] = a
+    ow.set_particles(yp, wp, om)
+    rw.run("macrovar"); ow.macrovar()
+    ox, oy, oz = _vort_equal(rw, ow, "solid")
+    assert np.all(ox[solid] == 2e-3) and np.all(oy[solid] == 4e-3) and np.all(oz[solid] == -2e-3)
+    rw.close(); ow.close()
