@@ -242,7 +242,7 @@ def main():
     scheme = {"aa": capi.SCHEME_AA, "ab": capi.SCHEME_AB, "auto": capi.SCHEME_AUTO}[args.scheme]
     math_mode = capi.MATH_FAST if args.math == "fast" else capi.MATH_STRICT
     if args.particles > 0:
-        args.halo = "nccl"              # the particle path keeps its halo on NCCL (DESIGN.md section 8)
+        args.halo = "nccl"              # the particle path keeps its halo on NCCL (DESIGN.md section 7)
     nodes_global = nx * ny * nz
     device_init = args.device_init or args.workload == "c4"
     do_e2e = not args.no_e2e and not device_init and args.particles == 0

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(1024) k_beads_scan(int n, const long long *cou
 
 // ---- beads_collision: interpolated bounce-back + momentum exchange ---------------------------------
 // One thread per link, after the step (and after its halo exchange).  Where the three post-collision
-// values live and where the result goes, by storage state (DESIGN.md section 8):
+// values live and where the result goes, by storage state (DESIGN.md section 7):
 //   READ_PULL_NAT  (AB):        f*_i(x) = S[i][x];        result -> S[opp i][x_s]   (x_f pulls it from there)
 //   READ_PULL_SWAP (AA, even):  f*_i(x) = S[opp i][x];    result -> S[i][x_s]
 //   READ_DIRECT    (AA, odd):   f*_i(x) = S[i][x + c_i];  result -> S[opp i][x_f]   (already streamed)

@@ -186,6 +186,7 @@
       integer :: ierr_
       integer(c_signed_char) :: ipc_mine(256)
       integer(c_signed_char), allocatable :: ipc_all(:)
+      character(len=16) :: halo_env
       if (bound) return
       if (nprocY /= 1) then
         if (myid == 0) write(*,*) 'd3q19_b200: set nprocY = 1 in para.f90:219 (z-slab decomposition, one rank per GPU)'
@@ -216,14 +217,19 @@
         call MPI_BCAST(cfg%nccl_id, 128, MPI_BYTE, 0, MPI_COMM_WORLD, ierr_)
       endif
       call d3q19_b200_check(d3q19_create(cfg, handle), 'd3q19_create')
-      if (nprocZ > 1 .and. .not. ipart .and. lz >= 2) then
-        ! halo in NVLink peer memory: every rank exports its cudaIpc handles, MPI_ALLGATHER replaces
-        ! nothing in the reference -- it is the bootstrap of what replaces MPI_ISEND/IRECV/WAITALL
-        ! (collision.f90:349-356) inside the step kernel
+      ! The z faces travel by NCCL send/recv on a second stream (the library's default; equal or faster than
+      ! the alternative in every measured configuration, profiles/r01d_halo_transports.md).  D3Q19_HALO=peer
+      ! selects the halo in NVLink peer memory instead: every rank exports its cudaIpc handles and
+      ! MPI_ALLGATHER distributes them -- the bootstrap of what then replaces MPI_ISEND/IRECV/WAITALL
+      ! (collision.f90:349-356) inside the step kernel.  d3q19_ipc_connect returns 2 when all ranks agreed
+      ! that peer memory is unavailable; the halo then stays on NCCL.
+      call get_environment_variable('D3Q19_HALO', halo_env, status=ierr_)
+      if (ierr_ == 0 .and. trim(halo_env) == 'peer' .and. nprocZ > 1 .and. .not. ipart .and. lz >= 2) then
         allocate(ipc_all(256*nproc))
         call d3q19_b200_check(d3q19_ipc_export(handle, ipc_mine), 'd3q19_ipc_export')
         call MPI_ALLGATHER(ipc_mine, 256, MPI_BYTE, ipc_all, 256, MPI_BYTE, MPI_COMM_WORLD, ierr_)
-        call d3q19_b200_check(d3q19_ipc_connect(handle, ipc_all), 'd3q19_ipc_connect')
+        ierr_ = d3q19_ipc_connect(handle, ipc_all)
+        if (ierr_ /= 0 .and. ierr_ /= 2) call d3q19_b200_check(ierr_, 'd3q19_ipc_connect')
         deallocate(ipc_all)
       endif
 

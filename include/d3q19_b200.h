@@ -153,7 +153,7 @@ int d3q19_set_particles(d3q19_handle *h, int32_t npart, const double *ypglb, con
 
 /* Device-side particle bookkeeping.  The reference snapshot does not contain its particle library
  * (main.f90:64 names partlib.f90), so these follow the published algorithms its
- * data structures point to and are "parity unpinned" (DESIGN.md section 8).  Entry points carry the
+ * data structures point to and are "parity unpinned" (DESIGN.md section 7).  Entry points carry the
  * names of the reference's per-phase timers (var_inc.f90:166-168).                           */
 typedef struct d3q19_particle_params {
     double rad;                 /* var_inc.f90:67                                            */
