@@ -265,6 +265,15 @@ class ChannelFlow:
     def FORCING(self):
         capi.check(self.L.d3q19_shim_forcing(self.h, self.v.force_in_y, self.v.force_mag))
 
+    def FORCINGP(self, istep=None):
+        """collision.f90:529-602 on the device for step `istep` (default: the driver's current istep)."""
+        capi.check(self.L.d3q19_forcingp(self.h, int(self.istep if istep is None else istep), self.v.force_in_y))
+
+    def download_force_field(self):
+        o = [np.zeros((self.lz, self.ly, self.lx)) for _ in range(3)]
+        capi.check(self.L.d3q19_download_force_field(self.h, *[capi.dptr(a) for a in o]))
+        return o
+
     def rhoupdat(self):
         capi.check(self.L.d3q19_shim_rhoupdat(self.h))
 

@@ -689,6 +689,43 @@ extern "C" int d3q19_set_force_field(d3q19_handle *h, const double *fx, const do
     return 0;
 }
 
+// FORCINGP (collision.f90:529-602) on the device: fills the force field for step `istep` without touching
+// the host (the reference's host loop + an upload would move 24 B per node over PCIe every step).
+extern "C" int d3q19_forcingp(d3q19_handle *h, int32_t istep, double force_in_y) {
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t bytes = h->nfield * sizeof(double);
+    if (!h->ffx) {
+        CK(cudaMalloc(&h->ffx, bytes)); CK(cudaMalloc(&h->ffy, bytes)); CK(cudaMalloc(&h->ffz, bytes));
+    }
+    ForcingpParams p;
+    memset(&p, 0, sizeof p);
+    const Geom &g = h->g;
+    p.lx = g.lx; p.ly = g.ly; p.lz = g.lz; p.xp = g.xp;
+    p.nx = h->cfg.nx; p.ny = h->cfg.ny; p.nz = h->cfg.nz; p.globalz = h->cfg.globalz;
+    const double pi = 4.0 * atan(1.0);                          // var_inc.f90:71
+    p.pi2 = 2.0 * pi;
+    const double Tpd = 2000.0;                                  // :538
+    p.beta9 = 3.0; p.gamma9 = 2.0; p.phase9 = 0.25; p.ixs0 = 2; // :540-545
+    p.ihh = (g.lx / 2) / 2;                                     // lxh/2, var_inc.f90:53
+    p.force_in_y = force_in_y;
+    p.Amp0 = 40.00 * p.beta9 / (double)p.ny * sin(p.pi2 * (double)istep / Tpd);   // :543
+    if (p.ihh < 1) return fail("d3q19_forcingp: channel too narrow (lx = %d)", g.lx);
+    p.fx = h->ffx; p.fy = h->ffy; p.fz = h->ffz;
+    k_forcingp<<<grid_nodes(h, g.lz), BLOCK_X, 0, h->sc>>>(p);
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    return 0;
+}
+
+// device force field -> host arrays in the reference's layout (force_realx/y/z(lx,ly,lz), para.f90:443-445)
+extern "C" int d3q19_download_force_field(d3q19_handle *h, double *fx, double *fy, double *fz) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->ffx) return fail("d3q19_download_force_field: no force field is set (uniform force)");
+    RK_(field_to_host(h, h->ffx, fx)); RK_(field_to_host(h, h->ffy, fy)); RK_(field_to_host(h, h->ffz, fz));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
 // ---- the step ----------------------------------------------------------------------------------------
 template <int SK, bool STRICT, bool GENERIC>
 static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int nplanes, cudaStream_t s, int zstride = 1) {

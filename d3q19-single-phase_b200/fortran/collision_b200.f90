@@ -117,6 +117,12 @@
           type(c_ptr), value :: h
           real(c_double), intent(in) :: fx(*), fy(*), fz(*)
         end function
+        integer(c_int) function d3q19_forcingp(h, istep, force_in_y) bind(c, name='d3q19_forcingp')
+          import :: c_int, c_ptr, c_double, c_int32_t
+          type(c_ptr), value :: h
+          integer(c_int32_t), value :: istep
+          real(c_double), value :: force_in_y
+        end function
         integer(c_int) function d3q19_shim_rhoupdat(h) bind(c, name='d3q19_shim_rhoupdat')
           import :: c_int, c_ptr
           type(c_ptr), value :: h
@@ -308,11 +314,10 @@
       use var_inc
       use d3q19_b200_shim
       implicit none
-      ! The perturbation forcing of collision.f90:529-602 is host arithmetic on
-      ! force_real{x,y,z}; keep the reference's body (renamed FORCINGP_HOST, unchanged)
-      ! in the build and hand the arrays it fills to the device force-field path:
-      external FORCINGP_HOST
+      ! The perturbation forcing of collision.f90:529-602 is evaluated on the device for the
+      ! current istep and written into the device force field: nothing crosses PCIe.  The host
+      ! arrays force_real{x,y,z} are read by nothing but collision_MRT / macrovar
+      ! (collision.f90:65-67,415-417), which live on the device now, so they are left alone.
       call d3q19_b200_ensure
-      call FORCINGP_HOST
-      call d3q19_b200_check(d3q19_set_force_field(handle, force_realx, force_realy, force_realz), 'FORCINGP')
+      call d3q19_b200_check(d3q19_forcingp(handle, int(istep, c_int32_t), real(force_in_y, c_double)), 'FORCINGP')
       END SUBROUTINE FORCINGP

@@ -14,7 +14,7 @@
  *   rhoupdat       collision.f90:469-480                              -> d3q19_rhoupdat / d3q19_shim_rhoupdat
  *   avedensity     collision.f90:487-513                              -> d3q19_avedensity / d3q19_shim_avedensity
  *   FORCING        collision.f90:515-527                              -> d3q19_set_force_uniform / d3q19_shim_forcing
- *   FORCINGP       collision.f90:529-602 (force arrays)               -> d3q19_set_force_field
+ *   FORCINGP       collision.f90:529-602 (force arrays)               -> d3q19_forcingp (device) / d3q19_set_force_field (host arrays)
  *   allocarray     para.f90:418-503 (f, rho, u, ibnodes)              -> d3q19_create (device-side twins)
  *   MPI_ISEND/IRECV collision.f90:309-314,351-356                     -> NCCL send/recv inside d3q19_collide_stream
  *   MPI_ALLREDUCE  collision.f90:500-501                              -> ncclAllReduce inside d3q19_avedensity
@@ -128,6 +128,10 @@ int d3q19_init_channel(d3q19_handle *h, double ustar, double ystar, double A9, d
 /* ---- forcing (FORCING / FORCINGP) ------------------------------------------------------ */
 int d3q19_set_force_uniform(d3q19_handle *h, double fx, double fy, double fz);
 int d3q19_set_force_field(d3q19_handle *h, const double *fx, const double *fy, const double *fz);
+/* FORCINGP (collision.f90:529-602) evaluated on the device for step `istep`: the uniform force plus the
+ * sinusoidal perturbation in two near-wall x-bands, written straight into the device force field. */
+int d3q19_forcingp(d3q19_handle *h, int32_t istep, double force_in_y);
+int d3q19_download_force_field(d3q19_handle *h, double *fx, double *fy, double *fz);
 
 /* ---- the time step --------------------------------------------------------------------- */
 /* one collision_MRT (collide + force + propagate + wall bounce-back + ghost exchange) */
