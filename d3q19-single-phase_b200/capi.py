@@ -24,7 +24,7 @@ SYMBOLS = [
     "d3q19_ipc_export", "d3q19_ipc_connect", "d3q19_upload_f", "d3q19_download_f", "d3q19_set_macro", "d3q19_download_macro",
     "d3q19_init_channel", "d3q19_set_force_uniform", "d3q19_set_force_field", "d3q19_forcingp", "d3q19_download_force_field",
     "d3q19_collide_stream", "d3q19_run", "d3q19_macrovar", "d3q19_rhoupdat", "d3q19_avedensity", "d3q19_probe",
-    "d3q19_prerelax", "d3q19_set_solid_mask", "d3q19_set_particles", "d3q19_profiles", "d3q19_diag",
+    "d3q19_prerelax", "d3q19_set_solid_mask", "d3q19_set_particles", "d3q19_profiles", "d3q19_profiles2", "d3q19_diag",
     "d3q19_vortcalc", "d3q19_download_vort",
     "d3q19_particles_init", "d3q19_beads_links", "d3q19_beads_collision", "d3q19_beads_lubforce", "d3q19_beads_move",
     "d3q19_beads_filling", "d3q19_particle_step", "d3q19_get_particles", "d3q19_get_links", "d3q19_get_mask",
@@ -119,6 +119,7 @@ def load():
     L.d3q19_set_solid_mask.argtypes = [vp, ip, ip]
     L.d3q19_set_particles.argtypes = [vp, C.c_int32, dp, dp, dp]
     L.d3q19_profiles.argtypes = [vp, dp]
+    L.d3q19_profiles2.argtypes = [vp, dp]
     L.d3q19_diag.argtypes = [vp, C.c_double, dp]
     L.d3q19_forcingp.argtypes = [vp, C.c_int32, C.c_double]
     L.d3q19_download_force_field.argtypes = [vp, dp, dp, dp]

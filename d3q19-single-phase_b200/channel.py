@@ -302,6 +302,45 @@ class ChannelFlow:
             d[k] = int(d[k])
         return d
 
+    def profiles2(self):
+        out = np.zeros((12, self.lx))
+        capi.check(self.L.d3q19_profiles2(self.h, capi.dptr(out)))
+        return out
+
+    @staticmethod
+    def statistc_rows(sums, count, ustar, ystar, with_volf=False, nynz=None):
+        """What statistc / statistc2 do on rank 0 after their MPI_ALLREDUCEs (saveload.f90:1281-1338, :1446-1498):
+        sums = the 11 plane sums in d3q19_profiles order, count = ny*nz (statistc) or the per-plane fluid count
+        (statistc2).  Returns one row per x-plane in the column order of profiles.dat / profiles2.dat."""
+        sums = np.asarray(sums, dtype=np.float64)
+        lx = sums.shape[1]
+        cnt = np.broadcast_to(np.asarray(count, dtype=np.float64), (lx,))
+        u2, u4 = ustar * ustar, (ustar * ustar) * (ustar * ustar)
+        vx, vy, vz = (sums[k] / cnt / ustar for k in (0, 1, 2))
+        sqx, sqy, sqz = (sums[k] / cnt / u2 for k in (3, 4, 5))
+        sxy, sxz, syz = (sums[k] / cnt / u2 for k in (6, 7, 8))
+        sqx, sqy, sqz = sqx - vx ** 2, sqy - vy ** 2, sqz - vz ** 2
+        sxz, sxy, syz = sxz - vx * vz, sxy - vx * vy, syz - vy * vz
+        pr = sums[9] / cnt / u2
+        prsq = sums[10] / cnt / u4 - pr * pr
+        i = np.arange(1, lx + 1, dtype=np.float64)
+        lxh = lx // 2                                            # var_inc.f90:53
+        yplus = np.where(i > lxh, ((lx - i) + 0.5) / ystar, (i - 0.5) / ystar)
+        cols = [i - 0.5, yplus, vx, vy, vz, sqx, sqy, sqz, sxz, sxy, syz, pr, prsq]
+        if with_volf:
+            volf = cnt / float(nynz)
+            cols += [volf, 1.0 - volf]
+        return np.stack(cols, axis=1)
+
+    def statistc(self):
+        """rows of profiles.dat (saveload.f90:1202-1342) from device-side plane sums"""
+        return self.statistc_rows(self.profiles(), self.ny * self.nz, self.v.ustar, self.v.ystar)
+
+    def statistc2(self):
+        """rows of profiles2.dat (saveload.f90:1348-1502): fluid nodes only, with the solid volume fraction"""
+        s = self.profiles2()
+        return self.statistc_rows(s[:11], s[11], self.v.ustar, self.v.ystar, with_volf=True, nynz=self.ny * self.nz)
+
     def vortcalc(self):
         """saveload.f90:3929-4054 on the device: vorticity of the velocity field of the last macrovar;
         returns this rank's (ox, oy, oz)[iz, iy, ix] (the reference's ox,oy,oz(lx,ly,lz), var_inc.f90:140)."""

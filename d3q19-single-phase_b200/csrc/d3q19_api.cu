@@ -1304,7 +1304,11 @@ extern "C" int d3q19_get_mask(d3q19_handle *h, int32_t *own_lx_ly_lz) {
 }
 
 // ---- profiles (statistc, saveload.f90:1241-1300) -------------------------------------------------------------------------
-extern "C" int d3q19_profiles(d3q19_handle *h, double *out) {
+static int profiles_impl(d3q19_handle *h, double *out, int nrows_out);
+extern "C" int d3q19_profiles(d3q19_handle *h, double *out) { return profiles_impl(h, out, 11); }
+// statistc2 (saveload.f90:1348-1502): the same masked sums plus, as row 11, the fluid-node count of each x-plane
+extern "C" int d3q19_profiles2(d3q19_handle *h, double *out) { return profiles_impl(h, out, 12); }
+static int profiles_impl(d3q19_handle *h, double *out, int nrows_out) {
     CK(cudaSetDevice(h->cfg.device));
     const Geom &g = h->g;
     RK_(wait_exchange(h));
@@ -1331,7 +1335,7 @@ extern "C" int d3q19_profiles(d3q19_handle *h, double *out) {
         NK(nccl_api().AllReduce(h->prof_out, h->prof_out, (size_t)NPROF * g.lx, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
         h->n_nccl++;
     }
-    CK(cudaMemcpyAsync(out, h->prof_out, (size_t)NPROF * g.lx * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaMemcpyAsync(out, h->prof_out, (size_t)nrows_out * g.lx * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
     CK(cudaStreamSynchronize(h->sc));
     return 0;
 }

@@ -847,9 +847,10 @@ __global__ void __launch_bounds__(BLOCK_X) k_rho_shift(int lx, int xp, double *r
     rho[row * xp + x] -= *mean_dev;            // collision.f90:508, every node
 }
 
-// statistc (saveload.f90:1241-1300): per-x sums over (y,z) of 11 quantities.  Stage 1: each
+// statistc / statistc2 (saveload.f90:1241-1300, :1393-1421): per-x sums over (y,z) of 11 quantities and,
+// as the 12th, the number of fluid nodes of the plane (statistc2's nfluid0).  Stage 1: each
 // block owns BLOCK_X x-columns and a contiguous chunk of (y,z) rows; stage 2 adds chunks in order.
-constexpr int NPROF = 11;
+constexpr int NPROF = 12;
 template <int RK>
 __global__ void __launch_bounds__(BLOCK_X) k_profiles(Geom g, const double *A, double Fx, double Fy, double Fz,
                                                       const int32_t *solid, int rows_per_chunk, double *partial) {
@@ -872,6 +873,7 @@ __global__ void __launch_bounds__(BLOCK_X) k_profiles(Geom g, const double *A, d
         acc[3] += a * a; acc[4] += b * b; acc[5] += c * c;
         acc[6] += a * b; acc[7] += a * c; acc[8] += b * c;
         acc[9] += r; acc[10] += r * r;
+        acc[11] += 1.0;
     }
 #pragma unroll
     for (int q = 0; q < NPROF; ++q) partial[((long long)blockIdx.y * NPROF + q) * g.lx + x] = acc[q];

@@ -188,6 +188,9 @@ int d3q19_get_mask(d3q19_handle *h, int32_t *own_lx_ly_lz);
 /* per-x-plane sums over the local (y,z) of ux,uy,uz,ux^2,uy^2,uz^2,uxuy,uxuz,uyuz,rho,rho^2
  * (statistc, saveload.f90:1241-1300), all-reduced over ranks; out is [11][lx]             */
 int d3q19_profiles(d3q19_handle *h, double *out_11_by_lx);
+/* statistc2 (saveload.f90:1348-1502): with a solid mask the sums run over the fluid nodes only; row 11 is
+ * the number of fluid nodes of each x-plane (nfluid, :1428), exact in fp64; out is [12][lx]            */
+int d3q19_profiles2(d3q19_handle *h, double *out_12_by_lx);
 
 /* diag (saveload.f90:1507-1676) from the current populations, reduced over ranks.  out[14]: vmax,
  * imout, jmout, kmout (global, 1-based, first occurrence in the reference's loop order), umean, vmean,

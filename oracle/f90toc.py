@@ -12,7 +12,8 @@ This script reads the reference's own sources WHERE THEY LIE (default
                   allocarray
     initial.f90   initpop, initvel
     collision.f90 collision_MRT, collisionExchnge, macrovar, rhoupdat, avedensity, FORCING, FORCINGP
-    saveload.f90  vortcalc, exchng8
+    saveload.f90  vortcalc, exchng8, statistc, statistc2, diag (values written to file units are
+                  captured: ref_capture)
 
 The translation is statement by statement: every expression keeps the Fortran evaluation
 order (left to right for equal precedence; `**` by repeated multiplication), `real` is double
@@ -694,7 +695,8 @@ class Translator:
             self.emit("%s%s = %s;%s" % (op, self.cx(lhs, names), self.cx(rhs, names), cl))
             return
         # scalar on the left: reductions on the right?
-        if isinstance(rhs, Index) and rhs.name in ("count", "sum") and not (self.sym(rhs.name) and self.sym(rhs.name).dims):
+        if isinstance(rhs, Index) and rhs.name in ("count", "sum", "maxval", "minval") \
+                and not (self.sym(rhs.name) and self.sym(rhs.name).dims):
             self.reduction(lhs, rhs)
             return
         r = self.cx(rhs)
@@ -712,6 +714,13 @@ class Translator:
         acc = self.cx(lhs)
         if rhs.name == "count":
             self.emit("%s = 0; %sif (%s) %s += 1;%s" % (acc, op, self.cx(pos[0], names), acc, cl))
+        elif rhs.name in ("maxval", "minval"):
+            cond = "if (%s) " % self.cx(kws["mask"], names) if "mask" in kws else ""
+            self.tmp_id += 1
+            t = "red%d" % self.tmp_id
+            init, cmp_ = ("-HUGE_VAL", ">") if rhs.name == "maxval" else ("HUGE_VAL", "<")
+            self.emit("{ double %s = %s; %s%sif (%s %s %s) %s = %s;%s %s = %s; }"
+                      % (t, init, op, cond, self.cx(pos[0], names), cmp_, t, t, self.cx(pos[0], names), cl, acc, t))
         else:
             cond = "if (%s) " % self.cx(kws["mask"], names) if "mask" in kws else ""
             # accumulate in a temporary like the intrinsic does, then assign
@@ -866,9 +875,38 @@ class Translator:
                 return
         if t == "continue":
             return
+        m = re.match(r"^write\s*\(\s*(\d+)\s*,", t)
+        if m:
+            # formatted output to a file unit: hand the numeric items to the capture buffer in list order
+            # (character items are dropped; a whole array contributes all its elements)
+            close = matching_paren(t, t.index("("))
+            for item in split_top(t[close + 1:]):
+                item = item.strip()
+                if not item or item[0] in "'\"":
+                    continue
+                e = parse_expr(item)
+                shape = self.section_shape(e) if isinstance(e, (Var, Index)) else None
+                if shape:
+                    op, cl, names = self.loops(shape)
+                    self.emit("%sref_capture(S, %s, (double)(%s));%s" % (op, m.group(1), self.cx(e, names), cl))
+                else:
+                    self.emit("ref_capture(S, %s, (double)(%s));" % (m.group(1), self.cx(e)))
+            return
         if t.startswith("write") or t.startswith("print") or t.startswith("open") or t.startswith("close") \
                 or t.startswith("format") or t.startswith("read"):
             self.emit("/* i/o statement skipped */;")
+            return
+        m = re.match(r"^where\s*\(", t)
+        if m:
+            # single-statement WHERE: masked elementwise assignment
+            k = t.index("(")
+            e = matching_paren(t, k)
+            mask = parse_expr(t[k + 1:e])
+            rest = t[e + 1:].strip()
+            eq = rest.index("=")
+            lhs, rhs = parse_expr(rest[:eq].strip()), parse_expr(rest[eq + 1:].strip())
+            op, cl, names = self.loops(self.section_shape(lhs))
+            self.emit("%sif (%s) %s = %s;%s" % (op, self.cx(mask, names), self.cx(lhs, names), self.cx(rhs, names), cl))
             return
         if t == "return":
             self.emit("goto ref_end;")
@@ -968,6 +1006,11 @@ class Translator:
             elif ch == "=" and depth == 0:
                 if t[i + 1:i + 2] == "=" or t[i - 1] in "/<>=":
                     continue
+                lname = re.match(r"[a-z_0-9]+", t[:i].strip())
+                ls = self.sym(lname.group(0)) if lname else None
+                if ls is not None and ls.typ == "other":
+                    self.emit("/* character assignment skipped */;")
+                    return
                 self.assignment(t[:i].strip(), t[i + 1:].strip(), override_ok=ov)
                 return
         raise SyntaxError("statement not understood: %r" % t)
@@ -992,7 +1035,8 @@ class Translator:
     def generate(self):
         self.in_case = False
         self.wanted = ["para", "allocarray", "initpop", "initvel", "collisionexchnge", "collision_mrt", "macrovar",
-                       "rhoupdat", "avedensity", "forcing", "forcingp", "exchng8", "vortcalc"]
+                       "rhoupdat", "avedensity", "forcing", "forcingp", "exchng8", "vortcalc",
+                       "statistc", "statistc2", "diag"]
         o = self.emit
         o("/* GENERATED by oracle/f90toc.py from the reference's Fortran sources -- do not edit, do not commit. */")
         o('#include "../ref_runtime.h"')
@@ -1049,6 +1093,9 @@ class Translator:
         save = self.subroutines_of("saveload.f90")
         self.translate_sub("vortcalc", save["vortcalc"])
         self.translate_sub("exchng8", save["exchng8"])
+        # rank 1: profile statistics and the diag monitor; their write(unit, ...) lists are captured
+        for n in ("statistc", "statistc2", "diag"):
+            self.translate_sub(n, save[n])
         # ---- dispatch + reflection tables for the Python wrapper
         o("\nint ref_dispatch(ref_state *S, const char *name)\n{")
         for n in self.wanted:

@@ -242,3 +242,31 @@ def make_initial_state(nx, ny, nz, laminar=False, A9=0.0, noise=True, seed=54321
     w.FORCING()
     w.initpop()
     return w, para
+
+
+# ---- saveload.f90 monitors restated in numpy (pinned to the translated reference's captured file output in
+#      tests/test_oracle_ref.py; sums are order dependent, so these carry a 1e-12 tolerance, integers are exact) ----
+def diag_line(w, ustar, solid=None):
+    """diag (saveload.f90:1535-1640): fluid-node count, mean and rms velocity over the fluid nodes in wall units,
+    the largest speed with the global 1-based location of its FIRST occurrence in the reference's k-j-i loop order
+    (:1560-1573), solid volume fraction, max/min density fluctuation -- the numbers of one diag.dat line (:1662)."""
+    ux, uy, uz, rho = (w.get(k) for k in ("ux", "uy", "uz", "rho"))
+    fluid = np.ones(ux.shape, bool) if solid is None else ~solid
+    nf = int(fluid.sum())
+    um, vm, wm = (a[fluid].sum() / nf for a in (ux, uy, uz))
+    rms = [np.sqrt((a[fluid] ** 2).sum() / nf - m * m) / ustar for a, m in ((ux, um), (uy, vm), (uz, wm))]
+    vel = np.sqrt(ux * ux + uy * uy + uz * uz)
+    vel[~fluid] = 0.0
+    k, j, i = np.unravel_index(int(np.argmax(vel)), vel.shape)        # first occurrence in (z, y, x) order
+    return dict(vmax=float(vel.max()), imout=i + 1, jmout=j + 1, kmout=k + 1, umean=um / ustar, vmean=vm / ustar,
+                wmean=wm / ustar, urms=rms[0], vrms=rms[1], wrms=rms[2], volf=1.0 - nf / vel.size,
+                rhomax=float(rho[fluid].max()), rhomin=float(rho[fluid].min()), nfluid=nf)
+
+
+def plane_sums(w, solid=None):
+    """the 11 per-x-plane sums of statistc / statistc2 (saveload.f90:1241-1266, :1393-1421) in d3q19_profiles
+    order (ux,uy,uz,ux2,uy2,uz2,uxuy,uxuz,uyuz,rho,rho2) and the fluid-node count per plane"""
+    ux, uy, uz, rho = (w.get(k) for k in ("ux", "uy", "uz", "rho"))
+    m = np.ones(ux.shape) if solid is None else (~solid).astype(np.float64)
+    q = [ux, uy, uz, ux * ux, uy * uy, uz * uz, ux * uy, ux * uz, uy * uz, rho, rho * rho]
+    return np.stack([(a * m).sum(axis=(0, 1)) for a in q]), m.sum(axis=(0, 1))

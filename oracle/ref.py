@@ -48,6 +48,9 @@ def lib(fast=False):
         L.ref_world_loop.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
         L.ref_scalar.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
         L.ref_scalar.restype = C.c_void_p
+        L.ref_capture_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.ref_capture_get.restype = C.c_int
+        L.ref_capture_clear.argtypes = [C.c_void_p]
         L.ref_array.argtypes = [C.c_void_p, C.c_char_p]
         L.ref_array.restype = C.POINTER(Arr)
         _libs[fast] = L
@@ -97,6 +100,20 @@ class RefWorld:
 
     def loop(self, a, b, nsteps):
         self.L.ref_world_loop(self.h, a.lower().encode(), (b or "").lower().encode(), nsteps)
+
+    # ---- values the translated code wrote to file units (write(unit, fmt) lists) -----------------
+    def captured(self, unit=None, rank=0):
+        """numbers handed to write(unit, ...) by `rank` since the last clear, in the order written"""
+        n = self.L.ref_capture_get(self.h, rank, 0, None, None)
+        units = (C.c_int * max(n, 1))()
+        vals = (C.c_double * max(n, 1))()
+        self.L.ref_capture_get(self.h, rank, n, units, vals)
+        u = np.array(units[:n], dtype=np.int64)
+        v = np.array(vals[:n], dtype=np.float64)
+        return v if unit is None else v[u == unit]
+
+    def clear_captured(self):
+        self.L.ref_capture_clear(self.h)
 
     # ---- reflection ---------------------------------------------------------------------------
     def _scalar_ptr(self, name, rank):

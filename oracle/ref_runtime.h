@@ -148,7 +148,24 @@ typedef struct ref_common {
     double ov_val[REF_MAX_OVERRIDES];
     int npend;
     ref_pending pend[16];
+    /* values the translated code handed to write(unit, fmt) statements (file output of statistc, diag, ...):
+     * unit numbers and values in the order written; read back by the tests through ref_capture_get */
+    int ncap, capcap;
+    int *cap_unit;
+    double *cap_val;
 } ref_common;
+
+static inline void ref_capture(void *S, int unit, double v)
+{
+    ref_common *c = (ref_common *)S;
+    if (c->ncap == c->capcap) {
+        c->capcap = c->capcap ? 2 * c->capcap : 256;
+        c->cap_unit = (int *)realloc(c->cap_unit, (size_t)c->capcap * sizeof(int));
+        c->cap_val = (double *)realloc(c->cap_val, (size_t)c->capcap * sizeof(double));
+    }
+    c->cap_unit[c->ncap] = unit;
+    c->cap_val[c->ncap++] = v;
+}
 
 struct ref_state;
 typedef struct ref_state ref_state;
@@ -341,7 +358,11 @@ ref_world *ref_world_create(int nproc) { return ref_world_create_(nproc); }
 void ref_world_destroy(ref_world *w)
 {
     if (!w) return;
-    for (int r = 0; r < w->nproc; ++r) { ref_module_free(w->st[r]); free(w->st[r]); }
+    for (int r = 0; r < w->nproc; ++r) {
+        ref_common *c = (ref_common *)w->st[r];
+        free(c->cap_unit); free(c->cap_val);
+        ref_module_free(w->st[r]); free(w->st[r]);
+    }
     while (w->comm.head) { ref_msg *m = w->comm.head; w->comm.head = m->next; free(m->data); free(m); }
     free(w->st); free(w->comm.slot);
     pthread_mutex_destroy(&w->comm.mu);
@@ -350,6 +371,18 @@ void ref_world_destroy(ref_world *w)
 }
 
 ref_state *ref_world_state(ref_world *w, int rank) { return w->st[rank]; }
+
+/* captured write() values of one rank: returns the count, copies up to `max` (unit, value) pairs */
+int ref_capture_get(ref_world *w, int rank, int max, int *units, double *vals)
+{
+    ref_common *c = (ref_common *)w->st[rank];
+    for (int i = 0; i < c->ncap && i < max; ++i) { units[i] = c->cap_unit[i]; vals[i] = c->cap_val[i]; }
+    return c->ncap;
+}
+void ref_capture_clear(ref_world *w)
+{
+    for (int r = 0; r < w->nproc; ++r) ((ref_common *)w->st[r])->ncap = 0;
+}
 
 int ref_world_set_override(ref_world *w, const char *name, double v)
 {

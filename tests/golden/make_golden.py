@@ -103,6 +103,45 @@ def force_field_case(name, nx, ny, nz, npy, npz, steps, seed, **ov):
     w.close()
 
 
+def stats_case(name, nx, ny, nz, npy, npz, steps, seed, solid=False, a9=0.3, **ov):
+    """profiles.dat / profiles2.dat / diag.dat numbers (statistc, statistc2, diag: saveload.f90:1202-1676) as the
+    reference writes them after `steps` steps; with solid=True a sphere is marked solid (ibnodes > 0, owned by
+    particle 2) in the INITIAL state and the monitors run right after macrovar -- the reference ships no
+    particle code, so a field evolved next to solid nodes is not defined by it."""
+    w = start(nx, ny, nz, npy, npz, False, seed, a9, **({"ipart": True} if solid else {}), **ov)
+    extra = {}
+    if solid:
+        zz, yy, xx = np.meshgrid(np.arange(nz) + 0.5, np.arange(ny) + 0.5, np.arange(nx) + 0.5, indexing="ij")
+        c = np.array([nx * 0.45, ny * 0.5 + 0.3, nz * 0.5 - 0.2])
+        mask = (xx - c[0]) ** 2 + (yy - c[1]) ** 2 + (zz - c[2]) ** 2 < (0.3 * min(nx, ny, nz)) ** 2
+        ib = np.where(mask, 1, -1).astype(np.int32)
+        isn = np.where(mask, 2, -1).astype(np.int32)
+        npart = w.array("ypglb")[0].shape[0]
+        yp = np.zeros((npart, 3)); wp = np.zeros((npart, 3)); om = np.zeros((npart, 3))
+        yp[1], wp[1], om[1] = c, [0.004, -0.002, 0.001], [1e-3, 2e-3, -1e-3]
+        w.set_solid(ib, isn)
+        for r in range(w.nproc):
+            for nm, a in (("ypglb", yp), ("wp", wp), ("omgp", om)):
+                w.array(nm, r)[0][...] = a
+        extra = dict(ib=ib, isn=isn, ypglb=yp, wp=wp, omgp=om)
+        steps = 0
+    w.run("macrovar")
+    for _ in range(steps):
+        w.run("collision_mrt")
+        w.run("macrovar")
+    w.set_scalar("istep", steps)
+    w.clear_captured()
+    w.run("statistc"); w.run("statistc2"); w.run("diag")
+    u27 = w.captured(27)
+    rows1 = u27[1:1 + 13 * nx].reshape(nx, 13)
+    rows2 = u27[2 + 13 * nx:].reshape(nx, 15)
+    meta = dict(kind="stats", nx=nx, ny=ny, nz=nz, ranks=[npy, npz], laminar=False, steps=steps, overrides=ov,
+                scalars=scalars(w), solid=bool(solid))
+    save(name, meta, f=w.get_f(), profiles=rows1, profiles2=rows2, diag=w.captured(26), **extra,
+         **{k: w.get(k) for k in FIELDS})
+    w.close()
+
+
 if __name__ == "__main__":
     if not ref.available():
         raise SystemExit("oracle/_ref/libref.so missing: run `make -C oracle ref` where /root/reference is mounted")
@@ -114,5 +153,7 @@ if __name__ == "__main__":
     main_loop_case("ref_turb_mrt3_9x10x7_r3x2_s10", 9, 10, 7, 3, 2, False, 10, seed=777, mrttype=3, **U)
     main_loop_case("ref_turb_mrt1_39x4x3_r1x1_s8", 39, 4, 3, 1, 1, False, 8, seed=4242, **U)   # reaches the log-law branch
     main_loop_case("ref_turb_vort_21x6x5_r2x2_s6", 21, 6, 5, 2, 2, False, 6, seed=31337, a9=0.3, vort=True, **U)
+    stats_case("ref_stats_21x8x6_r2x2_s6", 21, 8, 6, 2, 2, 6, seed=2024, **U)
+    stats_case("ref_stats_solid_24x12x12_r1x2", 24, 12, 12, 1, 2, 0, seed=11, solid=True, **U)
     prerelax_case("ref_prerelax_7x8x8_r2x2_i6", 7, 8, 8, 2, 2, 6, seed=99, **U)
     force_field_case("ref_forcingp_15x8x8_r2x2_s4", 15, 8, 8, 2, 2, 4, seed=5, **U)

@@ -24,7 +24,27 @@ def load(path):
 
 
 def test_fixtures_exist():
-    assert len(CASES) >= 6
+    assert len(CASES) >= 9
+
+
+def _check_stats(z, meta, rows1, rows2, diag, tol=1e-11):
+    """profiles.dat / profiles2.dat rows and the diag.dat line against what the reference wrote"""
+    for got, want, what in ((rows1, z["profiles"], "profiles"), (rows2, z["profiles2"], "profiles2")):
+        if got is None:
+            continue
+        scale = np.maximum(np.max(np.abs(want), axis=0), 1e-30)
+        # the second moments are differences <ab> - <a><b> (saveload.f90:1291-1296): their rounding error is
+        # relative to the product of the means, not to the (much smaller) difference
+        m = np.max(np.abs(want), axis=0)
+        for col, (a, b) in {5: (2, 2), 6: (3, 3), 7: (4, 4), 8: (2, 4), 9: (2, 3), 10: (3, 4), 12: (11, 11)}.items():
+            scale[col] = max(scale[col], m[a] * m[b])
+        assert np.all(np.abs(got - want) <= tol * scale), (what, float(np.max(np.abs(got - want) / scale)))
+    d = z["diag"]
+    assert (int(d[2]), int(d[3]), int(d[4])) == (diag["imout"], diag["jmout"], diag["kmout"])
+    assert abs(d[1] - diag["vmax"]) <= 1e-14 * d[1]
+    assert d[12] == diag["rhomax"] and d[13] == diag["rhomin"]
+    for k, v in zip(("umean", "vmean", "wmean", "urms", "vrms", "wrms", "volf"), d[5:12]):
+        assert abs(v - diag[k]) <= tol * max(abs(v), 1e-3), k
 
 
 def oracle_overrides(meta):
@@ -50,6 +70,28 @@ def test_oracle_reproduces_reference_output(path, ranks):
             assert getattr(para, k) == v, k
     w = orc.World(para)
     w.FORCING()
+    if meta["kind"] == "stats":
+        # statistc / statistc2 / diag (saveload.f90:1202-1676) on the state the reference had
+        solid = None
+        w.set_f(z["f"])
+        if meta["solid"]:
+            w.close()
+            para = orc.make_para(nx, ny, nz, laminar=False, nprocY=npy, nprocZ=npz, ipart=1, **oracle_overrides(meta))
+            w = orc.World(para)
+            w.FORCING(); w.set_f(z["f"])
+            w.set_solid(z["ib"], z["isn"]); w.set_particles(z["ypglb"], z["wp"], z["omgp"])
+            solid = z["ib"] > 0
+        w.macrovar()
+        for k in FIELDS:
+            assert np.array_equal(w.get(k), z[k]), k
+        rows = entry.load_package().ChannelFlow.statistc_rows
+        ustar, ystar = meta["scalars"]["ustar"], meta["scalars"]["ystar"]
+        sums_all, _ = orc.plane_sums(w)                     # statistc sums every node, solid ones included (:1241-1266)
+        sums_fl, cnt = orc.plane_sums(w, solid)
+        _check_stats(z, meta, rows(sums_all, ny * nz, ustar, ystar),
+                     rows(sums_fl, cnt, ustar, ystar, with_volf=True, nynz=ny * nz), orc.diag_line(w, ustar, solid))
+        w.close()
+        return
     w.set_f(z["f0"])
     if meta["kind"] == "prerelax":
         for k in FIELDS:
@@ -104,6 +146,23 @@ def test_cuda_path_reproduces_reference_output(path, scheme, math_mode):
     pkg, sim = _sim(meta, capi.SCHEME_AA if scheme == "aa" else capi.SCHEME_AB,
                     capi.MATH_STRICT if math_mode == "strict" else capi.MATH_FAST)
     strict = math_mode == "strict"
+    if meta["kind"] == "stats":
+        # device-side statistc / statistc2 / diag against the numbers the reference wrote to its files
+        if meta["solid"]:
+            sim.close()
+            ov = meta["overrides"]
+            sim = pkg.ChannelFlow(meta["nx"], meta["ny"], meta["nz"], laminar=False, ipart=True, math_mode=capi.MATH_STRICT,
+                                  scheme=capi.SCHEME_AA if scheme == "aa" else capi.SCHEME_AB, ustar=ov["ustar"],
+                                  force_in_y=2.0 * ov["ustar"] * ov["ustar"] / float(meta["nx"]), ystar=0.0036 / ov["ustar"])
+        sim.FORCING()
+        sim.upload_f(np.ascontiguousarray(z["f"]))
+        rows1 = sim.statistc()
+        if meta["solid"]:
+            sim.set_solid_mask(z["ib"], z["isn"]); sim.set_particles(z["ypglb"], z["wp"], z["omgp"])
+            rows1 = None          # statistc sums the rigid-body velocity inside particles too: host arrays, not the device path
+        _check_stats(z, meta, rows1, sim.statistc2(), sim.diag())
+        sim.close()
+        return
     sim.f[...] = z["f0"]
     sim.host_f_changed()
     sim.FORCING()

@@ -295,18 +295,10 @@ def test_device_init_channel_matches_host_initvel_initpop(oracle, scheme):
 
 
 def reference_diag(w, ustar, solid=None):
-    """numpy mirror of diag (saveload.f90:1535-1640) on the oracle's macroscopic arrays"""
-    ux, uy, uz, rho = (w.get(k) for k in ("ux", "uy", "uz", "rho"))
-    fluid = np.ones(ux.shape, bool) if solid is None else ~solid
-    nf = int(fluid.sum())
-    um, vm, wm = (a[fluid].sum() / nf for a in (ux, uy, uz))
-    rms = [np.sqrt((a[fluid] ** 2).sum() / nf - m * m) / ustar for a, m in ((ux, um), (uy, vm), (uz, wm))]
-    vel = np.sqrt(ux * ux + uy * uy + uz * uz)
-    vel[~fluid] = 0.0
-    k, j, i = np.unravel_index(int(np.argmax(vel)), vel.shape)        # first occurrence in (z, y, x) order
-    return dict(vmax=float(vel.max()), imout=i + 1, jmout=j + 1, kmout=k + 1, umean=um / ustar, vmean=vm / ustar,
-                wmean=wm / ustar, urms=rms[0], vrms=rms[1], wrms=rms[2], volf=1.0 - nf / vel.size,
-                rhomax=float(rho[fluid].max()), rhomin=float(rho[fluid].min()), nfluid=nf)
+    """diag (saveload.f90:1535-1640) on the oracle's macroscopic arrays; the numpy restatement is pinned to the
+    translated reference's diag.dat line in tests/test_oracle_ref.py"""
+    from oracle import oracle as orc
+    return orc.diag_line(w, ustar, solid)
 
 
 @pytest.mark.parametrize("scheme", SCHEMES)

@@ -244,3 +244,51 @@ def test_vortcalc_solid_nodes():
     ox, oy, oz = _vort_equal(rw, ow, "solid")
     assert np.all(ox[solid] == 2e-3) and np.all(oy[solid] == 4e-3) and np.all(oz[solid] == -2e-3)
     rw.close(); ow.close()
+
+
+# ---- saveload.f90 monitors: the numbers the translated reference writes to its files ----------------------
+def _stat_rows():
+    import __graft_entry__ as entry
+    return entry.load_package().ChannelFlow.statistc_rows
+
+
+@pytest.mark.parametrize("npy,npz", [(1, 1), (2, 2), (1, 4)])
+def test_statistc_and_diag_file_output(npy, npz):
+    # profiles.dat (statistc, saveload.f90:1202-1342), profiles2.dat (statistc2, :1348-1502) and diag.dat
+    # (diag, :1507-1676) as the reference writes them, vs the numpy restatements the GPU tests check the
+    # device reductions against, and the host-side normalisation of the plane sums (channel.py statistc_rows)
+    nx, ny, nz = 11, 12, 12
+    rw, ow, p = pair(nx, ny, nz, npy, npz, False, A9=0.3)
+    rw.run("macrovar"); ow.macrovar()
+    for step in range(5):
+        rw.run("collision_mrt"); rw.run("macrovar")
+        ow.collision_MRT(); ow.macrovar()
+    rw.set_scalar("istep", 5)
+    rw.clear_captured()
+    rw.run("statistc"); rw.run("statistc2"); rw.run("diag")
+    ustar, ystar = rw.scalar("ustar"), rw.scalar("ystar")
+    out27 = rw.captured(27)
+    # unit 27 holds: istep, lx rows of 13 (statistc), istep, lx rows of 15 (statistc2)
+    assert out27.size == 1 + 13 * nx + 1 + 15 * nx and out27[0] == 5 and out27[1 + 13 * nx] == 5
+    rows1 = out27[1:1 + 13 * nx].reshape(nx, 13)
+    rows2 = out27[2 + 13 * nx:].reshape(nx, 15)
+    sums, cnt = orc.plane_sums(ow)
+    mine1 = _stat_rows()(sums, ny * nz, ustar, ystar)
+    mine2 = _stat_rows()(sums, cnt, ustar, ystar, with_volf=True, nynz=ny * nz)
+    for got, want in ((mine1, rows1), (mine2, rows2)):
+        scale = np.maximum(np.max(np.abs(want), axis=0), 1e-30)
+        m = np.max(np.abs(want), axis=0)       # second moments are differences <ab> - <a><b>: error relative to <a><b>
+        for col, (a, b) in {5: (2, 2), 6: (3, 3), 7: (4, 4), 8: (2, 4), 9: (2, 3), 10: (3, 4), 12: (11, 11)}.items():
+            scale[col] = max(scale[col], m[a] * m[b])
+        assert np.all(np.abs(got - want) <= 1e-11 * scale), np.max(np.abs(got - want) / scale)
+    assert np.array_equal(mine1[:, :2], rows1[:, :2])                   # x and y+ columns are exact
+    assert np.all(rows2[:, 13] == 1.0) and np.all(rows2[:, 14] == 0.0)  # no solids: volume fractions
+    d = rw.captured(26)
+    assert d.size == 14
+    mine = orc.diag_line(ow, ustar)
+    assert d[0] == 5.0
+    assert (int(d[2]), int(d[3]), int(d[4])) == (mine["imout"], mine["jmout"], mine["kmout"])
+    assert d[1] == mine["vmax"] and d[12] == mine["rhomax"] and d[13] == mine["rhomin"]
+    for k, v in zip(("umean", "vmean", "wmean", "urms", "vrms", "wrms", "volf"), d[5:12]):
+        assert abs(v - mine[k]) <= 1e-11 * max(abs(v), 1e-3), k
+    rw.close(); ow.close()
