@@ -334,12 +334,12 @@ class ChannelFlow:
 
     def statistc(self):
         """rows of profiles.dat (saveload.f90:1202-1342) from device-side plane sums"""
-        return self.statistc_rows(self.profiles(), self.ny * self.nz, self.v.ustar, self.v.ystar)
+        return self.statistc_rows(self.profiles(), self.v.ny * self.v.nz, self.v.ustar, self.v.ystar)
 
     def statistc2(self):
         """rows of profiles2.dat (saveload.f90:1348-1502): fluid nodes only, with the solid volume fraction"""
         s = self.profiles2()
-        return self.statistc_rows(s[:11], s[11], self.v.ustar, self.v.ystar, with_volf=True, nynz=self.ny * self.nz)
+        return self.statistc_rows(s[:11], s[11], self.v.ustar, self.v.ystar, with_volf=True, nynz=self.v.ny * self.v.nz)
 
     def vortcalc(self):
         """saveload.f90:3929-4054 on the device: vorticity of the velocity field of the last macrovar;
