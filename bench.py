@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
-    ap.add_argument("--halo", default="nccl", choices=["peer", "nccl"],
+    ap.add_argument("--halo", default="nccl", choices=["peer", "put", "nccl"],
                     help="z-face exchange: NCCL send/recv of the packed faces on a second stream, overlapped with the interior "
                          "(default; equal or faster in every configuration measured, profiles/r01d_halo_transports.md) or "
                          "stores into the neighbour GPU's memory over NVLink inside the step kernel")
@@ -272,14 +272,15 @@ def main():
         halo = "none"
         if world > 1:
             halo = "nccl"
-            if halo_req == "peer":
+            if halo_req in ("peer", "put"):
                 def allgather_bytes(b):
                     t = torch.tensor(list(b), dtype=torch.uint8)
                     out = [torch.zeros_like(t) for _ in range(world)]
                     dist.all_gather(out, t)
                     return [bytes(o.tolist()) for o in out]
                 # collective: either every rank maps its neighbours or none does (d3q19_ipc_connect agrees by all-reduce)
-                halo = "peer" if sim.connect_halo(allgather_bytes) else "nccl"
+                ok_ = sim.connect_halo(allgather_bytes, mode="put" if halo_req == "put" else "fused")
+                halo = halo_req if ok_ else "nccl"
         # synthetic initial state (turbulent set: log-law + perturbation + seeded noise)
         if device_init:
             sim.FORCING()
@@ -325,7 +326,7 @@ def main():
         ok = False
         sys.stderr.write("bench[rank %d]: %s\n" % (rank, exc))
     if not all_ok(ok):
-        if halo != "peer":
+        if halo not in ("peer", "put"):
             raise SystemExit("bench: the warm-up failed")
         # the peer-memory halo does not work on this box: rebuild everything on the NCCL transport
         if rank == 0:
@@ -413,8 +414,10 @@ def main():
                        "per_gpu": "%dx%dx%d z-slab" % (nx, ny, sim.lz), "scheme": args.scheme, "math": args.math,
                        "particles": ("%d moving spheres of radius %g: links, interpolated bounce-back, momentum-exchange force, "
                                      "lubrication, move, refill every step" % (args.particles, args.rad)) if args.particles else "none",
-                       "parallelism": ("z-slab x%d, faces %s" % (world, "stored into the neighbour GPU's memory over NVLink "
-                                       "inside the step kernel" if halo == "peer" else "by NCCL send/recv")) if world > 1 else "1 GPU",
+                       "parallelism": ("z-slab x%d, faces %s" % (world, {
+                           "peer": "stored into the neighbour GPU's memory over NVLink inside the step kernel",
+                           "put": "stored into the neighbour GPU's memory over NVLink by a copy kernel on a second stream",
+                           "nccl": "by NCCL send/recv"}[halo])) if world > 1 else "1 GPU",
                        "l2": "populations %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (c1["population_bytes"] / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "impl": "ours",

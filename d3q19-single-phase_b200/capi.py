@@ -17,11 +17,12 @@ MATH_FAST, MATH_STRICT = 0, 1
 MACRO_MAIN, MACRO_PRERELAX, MACRO_EXTERNAL = 0, 1, 2
 NPOP = 19
 IPC_BYTES = 256
+HALO_FUSED, HALO_PUT = 0, 1
 
 # every symbol include/d3q19_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "d3q19_create", "d3q19_destroy", "d3q19_sync", "d3q19_last_error", "d3q19_nccl_unique_id", "d3q19_device_count",
-    "d3q19_ipc_export", "d3q19_ipc_connect", "d3q19_upload_f", "d3q19_download_f", "d3q19_set_macro", "d3q19_download_macro",
+    "d3q19_ipc_export", "d3q19_ipc_connect", "d3q19_set_halo_mode", "d3q19_upload_f", "d3q19_download_f", "d3q19_set_macro", "d3q19_download_macro",
     "d3q19_init_channel", "d3q19_set_force_uniform", "d3q19_set_force_field", "d3q19_forcingp", "d3q19_download_force_field",
     "d3q19_collide_stream", "d3q19_run", "d3q19_macrovar", "d3q19_rhoupdat", "d3q19_avedensity", "d3q19_probe",
     "d3q19_prerelax", "d3q19_set_solid_mask", "d3q19_set_particles", "d3q19_profiles", "d3q19_profiles2", "d3q19_diag",
@@ -102,6 +103,7 @@ def load():
     L.d3q19_device_count.argtypes = [C.POINTER(C.c_int32)]
     L.d3q19_ipc_export.argtypes = [vp, C.POINTER(C.c_ubyte)]
     L.d3q19_ipc_connect.argtypes = [vp, C.POINTER(C.c_ubyte)]
+    L.d3q19_set_halo_mode.argtypes = [vp, C.c_int32]
     L.d3q19_upload_f.argtypes = [vp, dp]
     L.d3q19_download_f.argtypes = [vp, dp]
     L.d3q19_set_macro.argtypes = [vp, dp, dp, dp, dp]

@@ -478,7 +478,10 @@ class ChannelFlow:
         return own
 
     # ---- halo in NVLink peer memory (collective; `allgather(bytes) -> [bytes per rank]`) ----------
-    def connect_halo(self, allgather):
+    def connect_halo(self, allgather, mode=None):
+        """mode: None (library default / D3Q19_HALO_MODE), "fused" (stores inside the step kernel) or "put" (copy kernel)"""
+        if mode is not None:
+            capi.check(self.L.d3q19_set_halo_mode(self.h, {"fused": capi.HALO_FUSED, "put": capi.HALO_PUT}[mode]))
         blob = (C.c_ubyte * capi.IPC_BYTES)()
         capi.check(self.L.d3q19_ipc_export(self.h, blob))
         blobs = allgather(bytes(blob))

@@ -84,6 +84,7 @@ struct d3q19_handle {
     cudaEvent_t evB = nullptr, evX = nullptr, t0 = nullptr, t1 = nullptr, evC[2] = {nullptr, nullptr},
                 evS[2] = {nullptr, nullptr};
     bool exchange_pending = false;
+    bool put_pending = false;     // "put" transport: the last k_face_put (on sx, event evX) may still be reading my planes
     NcclComm comm = nullptr;
     double *send_up = nullptr, *send_dn = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
     double *stage[2] = {nullptr, nullptr};
@@ -108,6 +109,7 @@ struct d3q19_handle {
     double amp = 0, aip = 0;
     // halo in peer memory (cudaIpc): [0] = lower neighbour (mzm), [1] = upper neighbour (mzp)
     bool halo_on = false;
+    int halo_mode = D3Q19_HALO_FUSED;            // D3Q19_HALO_FUSED: stores inside the step kernel; D3Q19_HALO_PUT: a copy kernel on sx
     unsigned int halo_epoch = 0;
     unsigned int *halo_flags = nullptr;          // local: [0] wait_lo, [1] wait_hi, [2..3] block counters, [8] watchdog
     int halo_split_min = 64;      // peer-memory halo: slabs at least this thick run boundary and interior as two launches
@@ -164,9 +166,10 @@ static int wait_exchange(d3q19_handle *h) {
         k_halo_wait<<<1, 1, 0, h->sc>>>(h->halo_flags, h->halo_flags + 1, h->halo_epoch, h->halo_flags + 8, h->halo_timeout_ns);
         CK(cudaGetLastError());
     }
-    if (h->exchange_pending) {
+    if (h->exchange_pending || h->put_pending) {
         CK(cudaStreamWaitEvent(h->sc, h->evX, 0));
         h->exchange_pending = false;
+        h->put_pending = false;
     }
     return 0;
 }
@@ -473,11 +476,22 @@ extern "C" int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs) {
         return 2;
     }
     if (const char *t = getenv("D3Q19_HALO_SPLIT_MIN")) h->halo_split_min = atoi(t);
+    if (const char *t = getenv("D3Q19_HALO_MODE")) {
+        if (!strcmp(t, "put")) h->halo_mode = D3Q19_HALO_PUT;
+        else if (!strcmp(t, "fused")) h->halo_mode = D3Q19_HALO_FUSED;
+    }
     if (const char *t = getenv("D3Q19_HALO_TIMEOUT_S")) {
         const double sec = atof(t);
         if (sec > 0.0) h->halo_timeout_ns = (unsigned long long)(sec * 1e9);
     }
     h->halo_on = true;
+    return 0;
+}
+
+extern "C" int d3q19_set_halo_mode(d3q19_handle *h, int32_t mode) {
+    if (mode != D3Q19_HALO_FUSED && mode != D3Q19_HALO_PUT) return fail("d3q19_set_halo_mode: unknown mode %d", mode);
+    if (h->halo_on && h->halo_epoch > 0) return fail("d3q19_set_halo_mode: steps were already taken in the other mode");
+    h->halo_mode = mode;
     return 0;
 }
 
@@ -775,6 +789,60 @@ static int launch_step_halo(d3q19_handle *h, const StepParams &p0) {
     return 0;
 }
 
+// Third transport ("put"): plain step kernels, boundary planes first; a small copy kernel on the
+// high-priority stream stores both faces into the neighbours' arrays and raises their flags
+// (kernels.cuh k_face_put).  Ordering: this step's boundary kernel runs after (a) my own previous put has
+// finished reading my planes (evX) and (b) both neighbours' previous puts have landed (flags >= epoch-1);
+// (b) also implies the neighbours are done reading the ghost planes this step's put overwrites.
+template <int SK, bool STRICT, bool GENERIC>
+static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written) {
+    const int lz = h->g.lz;
+    const Geom &g = h->g;
+    const unsigned int epoch = ++h->halo_epoch;
+    if (h->put_pending) { CK(cudaStreamWaitEvent(h->sc, h->evX, 0)); h->put_pending = false; }
+    if (epoch > 1) {
+        k_halo_wait<<<1, 1, 0, h->sc>>>(h->halo_flags, h->halo_flags + 1, epoch - 1u, h->halo_flags + 8, h->halo_timeout_ns);
+        CK(cudaGetLastError());
+    }
+    if (lz > 2) {
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 2, h->sc, lz - 1)));   // planes 1 and lz in one launch
+        CK(cudaEventRecord(h->evB, h->sc));
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 2, lz - 2, h->sc)));
+    } else {
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, lz, h->sc)));
+        CK(cudaEventRecord(h->evB, h->sc));
+    }
+    CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
+    const bool ab = SK == STEP_AB;
+    FacePut fp;
+    memset(&fp, 0, sizeof fp);
+    fp.src = written;
+    fp.dst[0] = ab ? h->peer_B[1] : h->peer_A[1];       // upper neighbour
+    fp.dst[1] = ab ? h->peer_B[0] : h->peer_A[0];       // lower neighbour
+    fp.slab_dst[0] = h->peer_slab[1]; fp.slab_dst[1] = h->peer_slab[0];
+    switch (SK) {                                       // the planes and slots of exchange_after_step
+    case STEP_AB:      fp.zsrc[0] = lz; fp.slots[0] = SLOTS_PZ; fp.zdst[0] = 0; fp.zsrc[1] = 1; fp.slots[1] = SLOTS_MZ; fp.zdst[1] = h->peer_lz[0] + 1; break;
+    case STEP_AA_EVEN: fp.zsrc[0] = lz; fp.slots[0] = SLOTS_MZ; fp.zdst[0] = 0; fp.zsrc[1] = 1; fp.slots[1] = SLOTS_PZ; fp.zdst[1] = h->peer_lz[0] + 1; break;
+    default:           fp.zsrc[0] = lz + 1; fp.slots[0] = SLOTS_PZ; fp.zdst[0] = 1; fp.zsrc[1] = 0; fp.slots[1] = SLOTS_MZ; fp.zdst[1] = h->peer_lz[0];
+                       fp.exclude_walls = 1; break;
+    }
+    fp.ctr = h->halo_flags + 2;
+    fp.sig[0] = h->peer_flags[1];                       // the upper neighbour's wait_lo
+    fp.sig[1] = h->peer_flags[0] + 1;                   // the lower neighbour's wait_hi
+    fp.epoch = epoch;
+    const dim3 gp((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 10u);
+    fp.nblk = gp.x * gp.y * gp.z;
+    k_face_put<<<gp, BLOCK_X, 0, h->sx>>>(g, fp);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->evX, h->sx));
+    h->put_pending = true;
+    h->n_other_kernels += 1 + (epoch > 1 ? 1 : 0);
+    if (ab) {                             // the neighbours swap their arrays in lockstep
+        for (int d = 0; d < 2; ++d) { double *t = h->peer_A[d]; h->peer_A[d] = h->peer_B[d]; h->peer_B[d] = t; }
+    }
+    return 0;
+}
+
 template <int SK, bool STRICT, bool GENERIC>
 static int step_impl(d3q19_handle *h, const StepParams &p, double *written) {
     const int lz = h->g.lz;
@@ -784,6 +852,7 @@ static int step_impl(d3q19_handle *h, const StepParams &p, double *written) {
             CK(cudaStreamWaitEvent(h->sc, h->evX, 0));
             h->exchange_pending = false;
         }
+        if (h->halo_mode == D3Q19_HALO_PUT) return launch_step_put<SK, STRICT, GENERIC>(h, p, written);
         return launch_step_halo<SK, STRICT, GENERIC>(h, p);
     }
     // boundary planes first, so that their faces travel while the interior is computed

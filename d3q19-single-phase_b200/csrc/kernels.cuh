@@ -812,6 +812,57 @@ __global__ void __launch_bounds__(BLOCK_X) k_face_unpack(Geom g, double *A, Face
         fp.buf[face][(long long)s * g.plane + (long long)y * g.xp + x];
 }
 
+// ---- z-face "put" (third halo transport) ---------------------------------------------
+// A small copy kernel on the high-priority stream stores the five outgoing populations of both faces
+// straight into the neighbour GPUs' arrays (cudaIpc-mapped) and its last block raises the neighbours'
+// flags -- the halo_spin protocol of the fused path, but the remote stores and their system fence sit in
+// 128-thread blocks that need few registers and so co-reside with the interior step kernel (NCCL's
+// send/recv kernel needs most of an SM and, measured, only runs once the interior kernel drains).
+// Source / destination planes and slots are those of exchange_after_step: AB and AA-even copy my boundary
+// plane into the neighbour's ghost plane; AA-odd copies my ghost plane (where the step pushed across the
+// face) into the neighbour's real plane with the wall-adjacent exclusions of collision.f90:361-368.
+struct FacePut {
+    const double *src;            // my array (the one the step wrote)
+    double *dst[2];               // [0]: the upper neighbour's array, [1]: the lower neighbour's
+    long long slab_dst[2];
+    int zsrc[2], zdst[2];         // ghosted plane indices
+    FaceSlots slots[2];
+    int exclude_walls;
+    unsigned int *ctr;            // local block counter
+    unsigned int *sig[2];         // the upper neighbour's wait_lo, the lower neighbour's wait_hi
+    unsigned int epoch, nblk;
+};
+__global__ void __launch_bounds__(BLOCK_X) k_face_put(Geom g, FacePut fp) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    const int y = blockIdx.y, face = blockIdx.z / 5, s = blockIdx.z % 5;
+    if (x < g.lx) {
+        const int slot = fp.slots[face].s[s];
+        bool skip = false;
+        if (fp.exclude_walls) {
+            const int cx = (slot == 11 || slot == 13 || slot == 7 || slot == 9 || slot == 1) ? 1
+                         : ((slot == 12 || slot == 14 || slot == 8 || slot == 10 || slot == 2) ? -1 : 0);
+            skip = (cx > 0 && x == 0) || (cx < 0 && x == g.lx - 1);
+        }
+        if (!skip) {
+            const long long inpl = (long long)y * g.xp + x;
+            fp.dst[face][(long long)slot * fp.slab_dst[face] + (long long)fp.zdst[face] * g.plane + inpl] =
+                fp.src[(long long)slot * g.slab + (long long)fp.zsrc[face] * g.plane + inpl];
+        }
+    }
+    // the last block of the grid: every remote store is visible -> raise both neighbours' flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(fp.ctr, 1u);
+        if (prev == fp.nblk - 1u) {
+            *fp.ctr = 0u;
+            __threadfence_system();
+            *(volatile unsigned int *)fp.sig[0] = fp.epoch;
+            *(volatile unsigned int *)fp.sig[1] = fp.epoch;
+        }
+    }
+}
+
 // ---- reductions ------------------------------------------------------------------------------------
 // avedensity (collision.f90:497-498): per-block partial (count, sum) over fluid nodes, fixed order.
 __global__ void __launch_bounds__(256) k_rho_partial(int lx, int xp, long long nrows, const double *rho,

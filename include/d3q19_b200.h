@@ -109,6 +109,13 @@ int d3q19_device_count(int32_t *n);
 #define D3Q19_IPC_BYTES 256
 int d3q19_ipc_export(d3q19_handle *h, unsigned char *blob);
 int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs_in_rank_order);
+/* How the peer-memory halo moves the faces (call before the first step; the environment variable
+ * D3Q19_HALO_MODE=fused|put read by d3q19_ipc_connect does the same):
+ *   D3Q19_HALO_FUSED  the boundary planes of the step kernel store into the neighbour's array themselves
+ *   D3Q19_HALO_PUT    plain step kernels; a small copy kernel on the high-priority stream stores both faces
+ *                     into the neighbours' arrays while the interior is computed                            */
+enum { D3Q19_HALO_FUSED = 0, D3Q19_HALO_PUT = 1 };
+int d3q19_set_halo_mode(d3q19_handle *h, int32_t mode);
 
 /* ---- state transfer (canonical AoS layout, see above) --------------------------------- */
 int d3q19_upload_f(d3q19_handle *h, const double *f_aos);

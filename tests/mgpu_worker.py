@@ -55,10 +55,13 @@ def main():
              ((24, 6, 4 * world), True, "peer"), ((33, 5, 3 * world + 1), True, "peer"), ((40, 3, 2 * world), True, "peer"),
              ((130, 7, 2 * world + 1), True, "peer"),
              # thick-slab mode of the peer halo: boundary planes and interior as two launches
-             ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split")]
+             ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split"),
+             # third transport: plain step kernels + a copy kernel that stores the faces into the neighbours' arrays
+             ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"), ((40, 3, 2 * world), True, "put"),
+             ((130, 7, 2 * world + 1), True, "put")]
     only = os.environ.get("MGPU_ONLY", "")          # e.g. "peer": just the peer-memory halo cases (short runs on many GPUs)
     if only:
-        cases = [c for c in cases if c[2].startswith(only)]
+        cases = [c for c in cases if c[2].startswith(only) or (only == "peer" and c[2] == "put")]
     for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
         for (nx, ny, nz), overlap, halo in cases:
             ctx[0] = "scheme %d case %s overlap %s halo %s" % (scheme, (nx, ny, nz), overlap, halo)
@@ -69,10 +72,10 @@ def main():
                                   math_mode=capi.MATH_STRICT, nccl_id=new_id(), overlap=overlap)
             z0, z1 = sim.globalz, sim.globalz + sim.lz
             sim.FORCING()
-            if halo.startswith("peer"):
+            if halo.startswith("peer") or halo == "put":
                 if halo == "peer-split":
                     os.environ["D3Q19_HALO_SPLIT_MIN"] = "3"
-                connected = sim.connect_halo(allgather_bytes)
+                connected = sim.connect_halo(allgather_bytes, mode="put" if halo == "put" else "fused")
                 os.environ.pop("D3Q19_HALO_SPLIT_MIN", None)
                 if not connected:
                     raise RuntimeError("peer-memory halo unavailable between the GPUs of this box: " + ctx[0])
