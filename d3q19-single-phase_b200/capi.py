@@ -29,7 +29,7 @@ SYMBOLS = [
     "d3q19_vortcalc", "d3q19_download_vort",
     "d3q19_particles_init", "d3q19_beads_links", "d3q19_beads_collision", "d3q19_beads_lubforce", "d3q19_beads_move",
     "d3q19_beads_filling", "d3q19_particle_step", "d3q19_get_particles", "d3q19_get_links", "d3q19_get_mask",
-    "d3q19_timer_start", "d3q19_timer_stop", "d3q19_get_counters",
+    "d3q19_timer_start", "d3q19_timer_stop", "d3q19_get_counters", "d3q19_trace_enable", "d3q19_trace_fetch",
     "d3q19_shim_bind", "d3q19_shim_bind_arrays", "d3q19_shim_set_schedule", "d3q19_shim_forcing", "d3q19_shim_rhoupdat", "d3q19_shim_collision_mrt",
     "d3q19_shim_prerelax_state",
     "d3q19_shim_macrovar", "d3q19_shim_avedensity", "d3q19_shim_sync_f_to_host", "d3q19_shim_sync_f_to_device",
@@ -104,6 +104,8 @@ def load():
     L.d3q19_ipc_export.argtypes = [vp, C.POINTER(C.c_ubyte)]
     L.d3q19_ipc_connect.argtypes = [vp, C.POINTER(C.c_ubyte)]
     L.d3q19_set_halo_mode.argtypes = [vp, C.c_int32]
+    L.d3q19_trace_enable.argtypes = [vp, C.c_int32]
+    L.d3q19_trace_fetch.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_int32]
     L.d3q19_upload_f.argtypes = [vp, dp]
     L.d3q19_download_f.argtypes = [vp, dp]
     L.d3q19_set_macro.argtypes = [vp, dp, dp, dp, dp]

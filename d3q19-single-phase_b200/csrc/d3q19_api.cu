@@ -84,6 +84,10 @@ struct d3q19_handle {
     cudaEvent_t evB = nullptr, evX = nullptr, t0 = nullptr, t1 = nullptr, evC[2] = {nullptr, nullptr},
                 evS[2] = {nullptr, nullptr};
     bool exchange_pending = false;
+    // optional per-step timeline (d3q19_trace_enable): 4 timing events per step -- [0] before the boundary launch,
+    // [1] after it, [2] after the interior launch (all on sc), [3] after the exchange / put (on sx)
+    cudaEvent_t *trace_ev = nullptr;
+    int trace_cap = 0, trace_n = 0;
     bool put_pending = false;     // "put" transport: the last k_face_put (on sx, event evX) may still be reading my planes
     NcclComm comm = nullptr;
     double *send_up = nullptr, *send_dn = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
@@ -174,6 +178,13 @@ static int wait_exchange(d3q19_handle *h) {
     return 0;
 }
 
+static inline void trace_mark(d3q19_handle *h, int which, cudaStream_t s) {
+    if (h->trace_ev && h->trace_n < h->trace_cap) cudaEventRecord(h->trace_ev[4 * h->trace_n + which], s);
+}
+static inline void trace_next(d3q19_handle *h) {
+    if (h->trace_ev && h->trace_n < h->trace_cap) h->trace_n++;
+}
+
 // ---- z-face exchange (collisionExchnge's z phase, collision.f90:337-370) --------------------------
 // "up" data goes to the +z neighbour, which stores it at plane lo_dst; "dn" data goes to the
 // -z neighbour, which stores it at plane hi_dst.  Runs on h->sx after `after` (an event on sc).
@@ -262,6 +273,10 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
         h->solid = h->isn = nullptr; h->ypglb = h->wp = h->omgp = nullptr;
     }
     if (h->halo_flags) cudaFree(h->halo_flags);
+    if (h->trace_ev) {
+        for (int i = 0; i < 4 * h->trace_cap; ++i) cudaEventDestroy(h->trace_ev[i]);
+        delete[] h->trace_ev;
+    }
     if (h->comm) nccl_api().CommDestroy(h->comm);
     void *ptrs[] = {h->A_alloc, h->B_alloc, h->rho, h->ux, h->uy, h->uz, h->ffx, h->ffy, h->ffz, h->solid, h->isn, h->ypglb,
                     h->wp, h->omgp, h->send_up, h->send_dn, h->recv_lo, h->recv_hi, h->stage[0], h->stage[1],
@@ -804,14 +819,18 @@ static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written
         k_halo_wait<<<1, 1, 0, h->sc>>>(h->halo_flags, h->halo_flags + 1, epoch - 1u, h->halo_flags + 8, h->halo_timeout_ns);
         CK(cudaGetLastError());
     }
+    trace_mark(h, 0, h->sc);
     if (lz > 2) {
         RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 2, h->sc, lz - 1)));   // planes 1 and lz in one launch
         CK(cudaEventRecord(h->evB, h->sc));
+        trace_mark(h, 1, h->sc);
         RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 2, lz - 2, h->sc)));
     } else {
         RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, lz, h->sc)));
         CK(cudaEventRecord(h->evB, h->sc));
+        trace_mark(h, 1, h->sc);
     }
+    trace_mark(h, 2, h->sc);
     CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
     const bool ab = SK == STEP_AB;
     FacePut fp;
@@ -835,6 +854,8 @@ static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written
     k_face_put<<<gp, BLOCK_X, 0, h->sx>>>(g, fp);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->evX, h->sx));
+    trace_mark(h, 3, h->sx);
+    trace_next(h);
     h->put_pending = true;
     h->n_other_kernels += 1 + (epoch > 1 ? 1 : 0);
     if (ab) {                             // the neighbours swap their arrays in lockstep
@@ -846,28 +867,44 @@ static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written
 template <int SK, bool STRICT, bool GENERIC>
 static int step_impl(d3q19_handle *h, const StepParams &p, double *written) {
     const int lz = h->g.lz;
-    if (h->cfg.nranks == 1) return launch_step_range<SK, STRICT, GENERIC>(h, p, 1, lz, h->sc);
+    if (h->cfg.nranks == 1) {
+        trace_mark(h, 0, h->sc); trace_mark(h, 1, h->sc);
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, lz, h->sc)));
+        trace_mark(h, 2, h->sc); trace_mark(h, 3, h->sc);
+        trace_next(h);
+        return 0;
+    }
     if (h->halo_on) {
         if (h->exchange_pending) {          // a ghost fill by NCCL (upload, init) precedes the first halo step
             CK(cudaStreamWaitEvent(h->sc, h->evX, 0));
             h->exchange_pending = false;
         }
         if (h->halo_mode == D3Q19_HALO_PUT) return launch_step_put<SK, STRICT, GENERIC>(h, p, written);
-        return launch_step_halo<SK, STRICT, GENERIC>(h, p);
+        trace_mark(h, 0, h->sc); trace_mark(h, 1, h->sc);
+        RK_((launch_step_halo<SK, STRICT, GENERIC>(h, p)));
+        trace_mark(h, 2, h->sc); trace_mark(h, 3, h->sc);
+        trace_next(h);
+        return 0;
     }
     // boundary planes first, so that their faces travel while the interior is computed
     RK_(wait_exchange(h));
+    trace_mark(h, 0, h->sc);
     if (h->cfg.overlap && lz > 2) {
         RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 2, h->sc, lz - 1)));   // planes 1 and lz in one launch
         CK(cudaEventRecord(h->evB, h->sc));
+        trace_mark(h, 1, h->sc);
         RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 2, lz - 2, h->sc)));
     } else {
         RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, lz, h->sc)));
         CK(cudaEventRecord(h->evB, h->sc));
+        trace_mark(h, 1, h->sc);
     }
+    trace_mark(h, 2, h->sc);
     CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
     RK_(exchange_after_step(h, SK, written, h->sx));
     CK(cudaEventRecord(h->evX, h->sx));
+    trace_mark(h, 3, h->sx);
+    trace_next(h);
     h->exchange_pending = true;
     return 0;
 }
@@ -1502,6 +1539,36 @@ extern "C" int d3q19_timer_stop(d3q19_handle *h, float *ms) {
     CK(cudaEventRecord(h->t1, h->sc));
     CK(cudaEventSynchronize(h->t1));
     CK(cudaEventElapsedTime(ms, h->t0, h->t1));
+    return 0;
+}
+
+// ---- per-step timeline (development aid: where does a multi-GPU step spend its time) -----------------------------
+extern "C" int d3q19_trace_enable(d3q19_handle *h, int32_t max_steps) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->trace_ev) {
+        for (int i = 0; i < 4 * h->trace_cap; ++i) cudaEventDestroy(h->trace_ev[i]);
+        delete[] h->trace_ev;
+        h->trace_ev = nullptr;
+    }
+    h->trace_cap = h->trace_n = 0;
+    if (max_steps <= 0) return 0;
+    h->trace_ev = new (std::nothrow) cudaEvent_t[4 * (size_t)max_steps];
+    if (!h->trace_ev) return fail("d3q19_trace_enable: out of host memory");
+    for (int i = 0; i < 4 * max_steps; ++i) CK(cudaEventCreate(&h->trace_ev[i]));
+    h->trace_cap = max_steps;
+    return 0;
+}
+
+// out[4*s + k] = milliseconds from the first mark of step 0 to mark k of step s (k: 0 before the boundary launch,
+// 1 after it, 2 after the interior launch, 3 after the exchange); returns the number of recorded steps
+extern "C" int d3q19_trace_fetch(d3q19_handle *h, int32_t *nsteps, float *out, int32_t capacity_steps) {
+    CK(cudaSetDevice(h->cfg.device));
+    RK_(d3q19_sync(h));
+    const int n = h->trace_n < capacity_steps ? h->trace_n : capacity_steps;
+    for (int s = 0; s < n; ++s)
+        for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&out[4 * s + k], h->trace_ev[0], h->trace_ev[4 * s + k]));
+    *nsteps = n;
+    h->trace_n = 0;
     return 0;
 }
 

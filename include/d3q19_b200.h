@@ -219,6 +219,11 @@ int d3q19_timer_stop(d3q19_handle *h, float *elapsed_ms);
  *           [3] steps taken, [4] bytes of populations resident, [5] storage phase,
  *           [6] x pitch, [7] scheme in use                                                 */
 int d3q19_get_counters(d3q19_handle *h, int64_t out[8]);
+/* per-step timeline (development aid, tools/step_timeline.py): four CUDA timing events per step for the next
+ * max_steps steps -- before / after the boundary-plane launch, after the interior launch (compute stream), after
+ * the z-face exchange (exchange stream); fetch returns milliseconds relative to the first mark, out[4*s + k]   */
+int d3q19_trace_enable(d3q19_handle *h, int32_t max_steps);
+int d3q19_trace_fetch(d3q19_handle *h, int32_t *nsteps, float *out, int32_t capacity_steps);
 
 /* ---- the shim state machine (what the replacement collision.f90 calls) ------------------ */
 /* These carry the download policy of SURVEY.md section 8(b): device-resident f is
