@@ -45,5 +45,26 @@ def build(force=False, verbose=False):
     return LIB
 
 
+DRIVER_SRC = os.path.join(HERE, "host", "channel_driver.cpp")
+DRIVER = os.path.join(HERE, "host", "channel_driver")
+
+
+def build_driver(force=False):
+    """The compiled-language host above the C-ABI (host/channel_driver.cpp: main.f90 + para + initial in C++),
+    linked against the in-tree library.  -ffp-contract=off: IEEE evaluation of the reference's expression order."""
+    lib = build()
+    hdr = os.path.join(HERE, "..", "include", "d3q19_b200.h")
+    if not force and os.path.exists(DRIVER) and os.path.getmtime(DRIVER) >= max(
+            os.path.getmtime(DRIVER_SRC), os.path.getmtime(hdr), os.path.getmtime(lib)):
+        return DRIVER
+    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-I", os.path.join(HERE, "..", "include"),
+           "-o", DRIVER, DRIVER_SRC, "-L", HERE, "-ld3q19b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/.."]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout)
+    return DRIVER
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_driver(force=True))
