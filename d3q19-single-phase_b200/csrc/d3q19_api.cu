@@ -62,6 +62,8 @@ struct Shim {
     bool in_prerelax = false;     // the last rhoupdat has not been followed by its collision_MRT yet
     int prerelax_iter = 0;        // main.f90's istep inside the pre-relaxation loop
     double prerelax_err = 0.0;    // max|rho - rhop| over all ranks of the current iteration (main.f90:79-80)
+    void *pinned[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // host arrays this library page-locked (shim_pin)
+    int npinned = 0;
 };
 
 struct d3q19_handle {
@@ -126,6 +128,8 @@ struct d3q19_handle {
     int peer_lz[2] = {0, 0};
     Shim shim;
 };
+
+static void shim_unpin(d3q19_handle *h);
 
 static const size_t POP_PAD = 32;     // doubles (256 B) in front of and behind the populations
 
@@ -254,6 +258,7 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->sc) cudaStreamSynchronize(h->sc);
     if (h->sx) cudaStreamSynchronize(h->sx);
+    shim_unpin(h);
     if (h->halo_on) {
         // nobody may still be storing into our planes, and we must let go of theirs before they free them
         for (int d = 0; d < 2; ++d)
@@ -1580,9 +1585,35 @@ extern "C" int d3q19_get_counters(d3q19_handle *h, int64_t out[8]) {
 }
 
 // ---- shim state machine (SURVEY.md section 8(b) "state coherence") ----------------------------------------------------
+// The driver's arrays are ordinary pageable memory (Fortran ALLOCATE, para.f90:418-503).  Copies from and to
+// pageable memory are staged by the CUDA driver at a fraction of the PCIe rate, and they are what the end-to-end
+// time of the intact driver consists of beyond the step kernels (f up once, rho,u down on output steps), so
+// large arrays are page-locked in place.  Arrays below 64 MB (tests) are left alone; memory that is pinned
+// already (bench.py, torch) reports so and is left alone too; D3Q19_NO_PIN=1 switches this off.
+static void shim_unpin(d3q19_handle *h) {
+    for (int i = 0; i < h->shim.npinned; ++i)
+        if (h->shim.pinned[i] && cudaHostUnregister(h->shim.pinned[i]) != cudaSuccess) cudaGetLastError();
+    h->shim.npinned = 0;
+}
+static void shim_pin(d3q19_handle *h) {
+    if (getenv("D3Q19_NO_PIN")) return;
+    const size_t n = (size_t)h->g.lx * h->g.ly * h->g.lz * sizeof(double);
+    if (n < ((size_t)64 << 20)) return;
+    cudaSetDevice(h->cfg.device);
+    void *ptr[5] = {h->shim.a.f, h->shim.a.rho, h->shim.a.ux, h->shim.a.uy, h->shim.a.uz};
+    const size_t bytes[5] = {NPOP * n, n, n, n, n};
+    for (int i = 0; i < 5; ++i) {
+        if (!ptr[i]) continue;
+        if (cudaHostRegister(ptr[i], bytes[i], cudaHostRegisterDefault) == cudaSuccess) h->shim.pinned[h->shim.npinned++] = ptr[i];
+        else cudaGetLastError();          // already pinned by the caller, or not lockable: copies still work, only slower
+    }
+}
+
 extern "C" int d3q19_shim_bind(d3q19_handle *h, const d3q19_shim_arrays *a) {
     if (!a || !a->f) return fail("d3q19_shim_bind: f is required");
+    shim_unpin(h);
     h->shim.a = *a;
+    shim_pin(h);
     h->shim.bound = true;
     h->shim.f_host_valid = true;
     h->shim.f_dev_valid = false;

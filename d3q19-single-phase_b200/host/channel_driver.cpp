@@ -24,6 +24,7 @@
 //
 // Build (d3q19-single-phase_b200/build.py build_driver): g++ -std=c++17 -O2 -ffp-contract=off, so that every
 // expression below is the IEEE evaluation of the Fortran source order.
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -327,11 +328,15 @@ int main(int argc, char **argv) {
         }
         // saveinitflow (main.f90:101) would write the host f here: the shim made it current in the last iteration
     }
-    macrovar(v);                                                    // main.f90:102
+    const auto t_up0 = std::chrono::steady_clock::now();
+    macrovar(v);                                                    // main.f90:102 (uploads f if nothing has yet)
+    std::printf("first macrovar (incl. upload of f when it is the first device call) %.3f s\n",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_up0).count());
     v.istep0 = 0;
     v.istep = v.istep0;
     FORCING(v);                                                     // main.f90:132
     macrovar(v);                                                    // main.f90:136
+    const auto t_loop0 = std::chrono::steady_clock::now();          // time_start = MPI_WTIME(), main.f90:137
     for (v.istep = v.istep0 + 1; v.istep <= v.istep0 + v.nsteps; ++v.istep) {       // main.f90:142-208
         collision_MRT();                                            // :157
         macrovar(v);                                                // :161
@@ -339,6 +344,11 @@ int main(int argc, char **argv) {
         if (v.nflowout > 0 && v.istep % v.nflowout == 0) outputuy(v);   // :184 -> saveload.f90:696,848
     }
     v.istep = v.istep0 + v.nsteps;
+    check(d3q19_sync(H), "d3q19_sync");
+    {
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop0).count();   // main.f90:214-218
+        std::printf("time loop %.3f s, %.1f MLUPS\n", dt, (double)v.nx * v.ny * v.nz * v.nsteps / dt / 1e6);
+    }
     probe(v);                                                       // main.f90:221
     if (!dump_path.empty()) {
         check(d3q19_shim_sync_f_to_host(H), "sync f to host");      // what savecntdflow needs (saveload.f90:227)
