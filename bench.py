@@ -74,6 +74,11 @@ def workload_dims(name):
     return nx, ny, nz
 
 
+def workload_name(nx, ny, nz):
+    return ("D3Q19 MRT channel %dx%dx%d (nx x ny x nz, x wall-normal), turbulent set Re_tau=180, "
+            "uniform body force, half-way bounce-back walls" % (nx, ny, nz))
+
+
 # ---- clocks during the timed region (B200_PROFILING.md "clocks line") -------------------------
 class ClockSampler:
     def __init__(self, index):
@@ -200,8 +205,9 @@ def main():
             "n_gpus": n_gpus, "steps": cpu_steps, "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "D3Q19 MRT channel %dx%dx%d (nx x ny x nz), turbulent set Re_tau=180" % (nx, ny, nz_unit),
-                       "note": "CPU arm: the reference's own hot path on the host cores; bounded sample of the per-GPU block"},
+            "config": {"workload": workload_name(nx, ny, nz),
+                       "note": "CPU arm: the reference's own hot path on the host cores; bounded sample = the per-GPU block "
+                               "%dx%dx%d, %d step(s)" % (nx, ny, nz_unit, cpu_steps)},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -409,8 +415,7 @@ def main():
             "metric": "MLUPS (fp64)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "D3Q19 MRT channel %dx%dx%d (nx x ny x nz, x wall-normal), turbulent set Re_tau=180, "
-                                   "uniform body force, half-way bounce-back walls" % (nx, ny, nz),
+            "config": {"workload": workload_name(nx, ny, nz),
                        "per_gpu": "%dx%dx%d z-slab" % (nx, ny, sim.lz), "scheme": args.scheme, "math": args.math,
                        "particles": ("%d moving spheres of radius %g: links, interpolated bounce-back, momentum-exchange force, "
                                      "lubrication, move, refill every step" % (args.particles, args.rad)) if args.particles else "none",
