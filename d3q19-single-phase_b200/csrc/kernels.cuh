@@ -71,7 +71,11 @@ constexpr int BLOCK_X = D3Q_BLOCK_X;
 // 4 CTAs/SM, AA even 1.519 -> 1.503 ms); >= 1 plane ahead thrashes L2; the two-array AB step gets
 // SLOWER with any distance (1.512 -> 1.58 ms) and does not prefetch.
 __device__ __forceinline__ void prefetch_l2(const void *p) {
+#if defined(__CUDACC__)
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;            // tests/host compiles this file with g++ (index logic checked on the GPU-less build box)
+#endif
 }
 
 __device__ __forceinline__ double pop_load(const double *p) {
@@ -119,9 +123,13 @@ struct Halo {
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
+#if defined(__CUDACC__)
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+#else
+    return 0ull;
+#endif
 }
 // Spin until *flag >= want.  A neighbour that died (or a broken peer mapping) must not hang the GPU:
 // after timeout_ns the waiter records `want` in *err and goes on -- the results are then void and
