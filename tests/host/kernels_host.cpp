@@ -8,12 +8,15 @@
 //
 // Mirrors, in d3q19_api.cu: d3q19_create (geometry), d3q19_upload_f / d3q19_download_f, exchange_faces /
 // exchange_after_step, launch_step_range / launch_step_halo / launch_step_put / step_impl / step_dispatch,
-// macro_launch, d3q19_vortcalc, d3q19_forcingp, d3q19_init_channel, profiles_impl.
+// macro_launch, d3q19_vortcalc, d3q19_forcingp, d3q19_init_channel, profiles_impl, d3q19_diag, d3q19_avedensity,
+// d3q19_prerelax, and the particle sequence d3q19_beads_links / _collision / _lubforce / _move / _filling /
+// d3q19_particle_step (kernels with barriers, shuffles or shared memory run with one fiber per thread).
 #include <cuda_runtime.h>
 
 #include <vector>
 
 #include "kernels.cuh"
+#include "particles.cuh"
 
 using namespace d3q;
 
@@ -37,6 +40,14 @@ struct Rank {
     unsigned int epoch = 0;
     // the neighbours' arrays as this rank sees them ([0] lower, [1] upper), swapped in lockstep for AB
     double *peer_A[2] = {nullptr, nullptr}, *peer_B[2] = {nullptr, nullptr};
+    // particle path (per slab: masks and links; the particle tables are replicated, here per slab as on the GPUs)
+    std::vector<int32_t> own, own0;
+    std::vector<double> ypglb, ypglb0, wp, omgp, fHIp, torqp, flubp, forcepp, torqpp, thetap;
+    std::vector<uint32_t> lnode;
+    std::vector<int32_t> ldir, lpart;
+    std::vector<double> lq;
+    std::vector<long long> lcount, loffset;
+    unsigned long long nfilled = 0;
 };
 
 struct Sim {
@@ -45,9 +56,17 @@ struct Sim {
     Mrt mrt;
     double Fx = 0, Fy = 0, Fz = 0, rho_shift = 0;
     long long pf_rows = 0;
+    unsigned long long rhoerr_bits = 0;      // PRERELAX: max |rho_new - rho_old| (one word = the MAX all-reduce)
+    bool want_rhoerr = false;
     bool force_field = false, has_solid = false;
     std::vector<double> ypglb, wp, omgp;      // (3,npart) tables of the solid branches (macrovar, vortcalc)
     double rhopart = 0.0;
+    // particle path
+    bool part_on = false, links_valid = false, mask_built = false;
+    int npart = 0;
+    double rad = 0, rho0 = 1, amp = 0, aip = 0, gforce[3] = {0, 0, 0};
+    LubParams lub = {0, 0, 0, 0, 0, 0, 0};
+    long long maxlink = 0;
     std::vector<Rank> r;
 };
 
@@ -99,6 +118,11 @@ void exchange_after_step(Sim &s, int step_kind, bool use_B) {
 // ---- the step ------------------------------------------------------------------------------------------------
 template <int SK, bool STRICT, bool GENERIC, bool HALO>
 void launch_k_step(const Sim &s, const Geom &g, const StepParams &p, int nplanes) {
+    if (GENERIC && p.macro_mode == 1 && p.rhoerr_bits) {       // block maximum of |rho - rhop|: shuffles + a barrier
+        if (!s.idx64) hs_launch_coop(grid_nodes(g, nplanes), BLOCK_X, k_step<SK, STRICT, GENERIC, uint32_t, HALO>, p);
+        else hs_launch_coop(grid_nodes(g, nplanes), BLOCK_X, k_step<SK, STRICT, GENERIC, unsigned long long, HALO>, p);
+        return;
+    }
     if (!s.idx64) hs_launch(grid_nodes(g, nplanes), BLOCK_X, k_step<SK, STRICT, GENERIC, uint32_t, HALO>, p);
     else hs_launch(grid_nodes(g, nplanes), BLOCK_X, k_step<SK, STRICT, GENERIC, unsigned long long, HALO>, p);
 }
@@ -128,7 +152,9 @@ void step_all_ranks(Sim &s, int macro_mode) {
         p.rho = q.rho.data(); p.ux = q.ux.data(); p.uy = q.uy.data(); p.uz = q.uz.data();
         if (s.force_field) { p.ffx = q.ffx.data(); p.ffy = q.ffy.data(); p.ffz = q.ffz.data(); }
         if (s.has_solid) p.solid = q.solid.data();
+        if (s.part_on) p.solid = q.own.data() + q.g.plane;
         p.A = q.A; p.B = ab ? q.B : nullptr;
+        if (s.want_rhoerr) p.rhoerr_bits = &s.rhoerr_bits;
     }
     if (n == 1) {
         launch_step_range<SK, STRICT, GENERIC>(s, s.r[0].g, ps[0], 1, s.r[0].g.lz);
@@ -240,7 +266,7 @@ void step_dispatch(Sim &s, int macro_mode) {
 }
 
 void collide_stream(Sim &s, int macro_mode) {
-    const bool generic = macro_mode != 0 || s.force_field || s.has_solid || s.rho_shift != 0.0;
+    const bool generic = macro_mode != 0 || s.force_field || s.has_solid || s.part_on || s.rho_shift != 0.0;
     if (generic) { if (s.strict) step_dispatch<true, true>(s, macro_mode); else step_dispatch<false, true>(s, macro_mode); }
     else { if (s.strict) step_dispatch<true, false>(s, macro_mode); else step_dispatch<false, false>(s, macro_mode); }
     if (macro_mode == 0) s.rho_shift = 0.0;
@@ -273,6 +299,109 @@ void profiles_rank(const Sim &s, Rank &q, int rows_per_chunk, int nchunks, doubl
               rows_per_chunk, partial);
     hs_launch(dim3((unsigned)((q.g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)NPROF, 1u), BLOCK_X, k_profiles_final, q.g.lx, nchunks,
               (const double *)partial, out);
+}
+
+
+PartGeom part_geom(const Sim &s, const Rank &q) {
+    PartGeom pg;
+    pg.g = q.g; pg.nx = s.nx; pg.ny = s.ny; pg.nz = s.nz; pg.globalz = q.globalz; pg.rad = s.rad;
+    return pg;
+}
+
+Links links_of(Rank &q) { return Links{q.lnode.data(), q.ldir.data(), q.lpart.data(), q.lq.data()}; }
+
+// d3q19_beads_links on every slab
+void beads_links(Sim &s) {
+    for (Rank &q : s.r) {
+        const PartGeom pg = part_geom(s, q);
+        std::swap(q.own, q.own0);
+        std::fill(q.own.begin(), q.own.end(), -1);
+        const dim3 gp((unsigned)s.npart, PART_SPLIT);
+        hs_launch(gp, 256, k_beads_mask, pg, s.npart, (const double *)q.ypglb.data(), q.own.data());
+        if (!s.mask_built) q.own0 = q.own;
+        const int nslot = s.npart * PART_SPLIT;
+        hs_launch_coop(gp, 256, k_beads_links<false>, pg, s.npart, (const double *)q.ypglb.data(), (const int32_t *)q.own.data(),
+                       q.lcount.data(), (const long long *)q.loffset.data(), s.maxlink, links_of(q));
+        hs_launch_coop(dim3(1), 1024, k_beads_scan, nslot, (const long long *)q.lcount.data(), q.loffset.data());
+        hs_launch_coop(gp, 256, k_beads_links<true>, pg, s.npart, (const double *)q.ypglb.data(), (const int32_t *)q.own.data(),
+                       q.lcount.data(), (const long long *)q.loffset.data(), s.maxlink, links_of(q));
+        if (q.loffset[nslot] > s.maxlink) hs::trap("more links than maxlink");
+    }
+    s.mask_built = true;
+    s.links_valid = true;
+}
+
+template <int RK>
+void ibb_rank(Sim &s, Rank &q) {
+    IbbParams P;
+    P.pg = part_geom(s, q); P.S = q.A; P.own = q.own.data(); P.L = links_of(q);
+    P.nlink_dev = q.loffset.data() + (size_t)s.npart * PART_SPLIT; P.maxlink = s.maxlink;
+    P.ypglb = q.ypglb.data(); P.wp = q.wp.data(); P.omgp = q.omgp.data(); P.rho0 = s.rho0;
+    P.fHIp = q.fHIp.data(); P.torqp = q.torqp.data();
+    // like the device path when the host does not know the count: threads for a multiple of the capacity's blocks;
+    // here the count is at hand, rounded up so that whole idle warps exist too
+    const long long nthreads = *P.nlink_dev + 200;
+    hs_launch_coop(dim3((unsigned)((nthreads + 127) / 128)), 128, k_beads_ibb<RK>, P);
+}
+void beads_collision(Sim &s) {
+    for (Rank &q : s.r) {
+        std::fill(q.fHIp.begin(), q.fHIp.end(), 0.0);
+        std::fill(q.torqp.begin(), q.torqp.end(), 0.0);
+        switch (read_kind(s)) {
+        case READ_DIRECT: ibb_rank<READ_DIRECT>(s, q); break;
+        case READ_PULL_NAT: ibb_rank<READ_PULL_NAT>(s, q); break;
+        default: ibb_rank<READ_PULL_SWAP>(s, q); break;
+        }
+    }
+    if (s.nranks > 1) {          // ncclAllReduce(SUM) of (fHIp, torqp) over the slabs, in rank order
+        std::vector<double> f(3 * s.npart, 0.0), t(3 * s.npart, 0.0);
+        for (Rank &q : s.r)
+            for (int i = 0; i < 3 * s.npart; ++i) { f[i] += q.fHIp[i]; t[i] += q.torqp[i]; }
+        for (Rank &q : s.r) { q.fHIp = f; q.torqp = t; }
+    }
+}
+void beads_lubforce(Sim &s) {
+    for (Rank &q : s.r)
+        hs_launch(dim3((unsigned)((s.npart + 127) / 128)), 128, k_beads_lubforce, part_geom(s, q), s.npart,
+                  (const double *)q.ypglb.data(), s.lub, q.flubp.data());
+}
+void beads_move(Sim &s) {
+    for (Rank &q : s.r) {
+        MoveParams M = {s.amp, s.aip, s.gforce[0], s.gforce[1], s.gforce[2], q.fHIp.data(), q.torqp.data(), q.flubp.data(),
+                        q.forcepp.data(), q.torqpp.data(), q.ypglb.data(), q.ypglb0.data(), q.wp.data(), q.omgp.data(),
+                        q.thetap.data()};
+        hs_launch(dim3((unsigned)((s.npart + 127) / 128)), 128, k_beads_move, part_geom(s, q), s.npart, M);
+    }
+    s.links_valid = false;
+}
+template <int RK>
+void fill_rank(Sim &s, Rank &q) {
+    FillParams P;
+    P.pg = part_geom(s, q); P.S = q.A; P.own0 = q.own0.data(); P.own = q.own.data(); P.ypglb0 = q.ypglb0.data();
+    P.ypglb = q.ypglb.data(); P.wp = q.wp.data(); P.omgp = q.omgp.data(); P.nfilled = &q.nfilled;
+    hs_launch(dim3((unsigned)s.npart, PART_SPLIT), 128, k_beads_fill<RK>, P);
+}
+void beads_filling(Sim &s) {
+    for (Rank &q : s.r) {
+        q.nfilled = 0;
+        switch (read_kind(s)) {
+        case READ_DIRECT: fill_rank<READ_DIRECT>(s, q); break;
+        case READ_PULL_NAT: fill_rank<READ_PULL_NAT>(s, q); break;
+        default: fill_rank<READ_PULL_SWAP>(s, q); break;
+        }
+    }
+}
+
+template <int RK>
+void diag_rank(const Sim &s, Rank &q, int rows_per_chunk, std::vector<double> &out) {
+    const long long nrows = (long long)q.g.ly * q.g.lz;
+    const int nchunks = (int)((nrows + rows_per_chunk - 1) / rows_per_chunk);
+    const dim3 gd((unsigned)((q.g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)nchunks, 1u);
+    std::vector<double> partial((size_t)gd.x * gd.y * NDIAG, 0.0);
+    const int32_t *solid = s.part_on ? q.own.data() + q.g.plane : (s.has_solid ? q.solid.data() : nullptr);
+    hs_launch_coop(gd, BLOCK_X, k_diag<RK>, q.g, (const double *)q.A, s.Fx, s.Fy, s.Fz, solid, rows_per_chunk, partial.data());
+    out.assign(NDIAG, 0.0);
+    hs_launch(dim3(1), 1, k_diag_final, (int)(gd.x * gd.y), (const double *)partial.data(), out.data());
 }
 
 }  // namespace
@@ -490,6 +619,152 @@ void hs_forcingp(void *h, int ihh, int ixs0, double force_in_y, double Amp0, dou
         field_out(s, q, p.fx, fx); field_out(s, q, p.fy, fy); field_out(s, q, p.fz, fz);
     }
     s.force_field = true;
+}
+
+// ---- reductions ---------------------------------------------------------------------------------------------------
+// d3q19_avedensity: two-stage fixed-order sum per slab, all-reduce in rank order, shift of every node (collision.f90:497-511)
+double hs_avedensity(void *h, long long *nfluid) {
+    Sim &s = *(Sim *)h;
+    const int nblk = 1024;
+    double sum = 0.0;
+    long long cnt = 0;
+    for (Rank &q : s.r) {
+        std::vector<double> pd(nblk, 0.0);
+        std::vector<long long> pc(nblk + 8, 0);
+        double s1 = 0.0;
+        long long c1 = 0;
+        const int32_t *solid = s.part_on ? q.own.data() + q.g.plane : (s.has_solid ? q.solid.data() : nullptr);
+        hs_launch_coop(dim3(nblk), 256, k_rho_partial, q.g.lx, q.g.xp, (long long)q.g.ly * q.g.lz, (const double *)q.rho.data(),
+                       solid, pd.data(), pc.data());
+        hs_launch(dim3(1), 32, k_rho_final, nblk, (const double *)pd.data(), (const long long *)pc.data(), &s1, &c1);
+        sum += s1; cnt += c1;
+    }
+    const double mean = sum / (double)cnt;
+    for (Rank &q : s.r)
+        hs_launch(grid_nodes(q.g, q.g.lz), BLOCK_X, k_rho_shift, q.g.lx, q.g.xp, q.rho.data(), (const double *)&mean);
+    s.rho_shift += mean;
+    if (nfluid) *nfluid = cnt;
+    return mean;
+}
+
+// d3q19_prerelax (main.f90:70-90): fused rhoupdat + collision with frozen u, max |rho - rhop| over all slabs
+int hs_prerelax(void *h, double tol, int maxiter, double *rhoerrmax) {
+    Sim &s = *(Sim *)h;
+    int istep = 0;
+    double err = 0.0;
+    for (;;) {
+        unsigned long long bits = 0;
+        s.rhoerr_bits = 0;                 // one word shared by all slabs = the all-reduce(MAX) of the per-slab words
+        s.want_rhoerr = true;
+        if (s.strict) {
+            if (s.ab) step_all_ranks<STEP_AB, true, true>(s, 1);
+            else if (s.phase == 0) { step_all_ranks<STEP_AA_EVEN, true, true>(s, 1); s.phase = 1; }
+            else { step_all_ranks<STEP_AA_ODD, true, true>(s, 1); s.phase = 0; }
+        } else {
+            if (s.ab) step_all_ranks<STEP_AB, false, true>(s, 1);
+            else if (s.phase == 0) { step_all_ranks<STEP_AA_EVEN, false, true>(s, 1); s.phase = 1; }
+            else { step_all_ranks<STEP_AA_ODD, false, true>(s, 1); s.phase = 0; }
+        }
+        s.want_rhoerr = false;
+        bits = s.rhoerr_bits;
+        std::memcpy(&err, &bits, sizeof err);
+        if (err <= tol || istep > maxiter) break;
+        istep++;
+    }
+    if (rhoerrmax) *rhoerrmax = err;
+    return istep;
+}
+
+// d3q19_diag: out[12] per slab merged like the host side of d3q19_diag does (first occurrence of the maximum wins)
+void hs_diag(void *h, int rows_per_chunk, double *out12_per_rank) {
+    Sim &s = *(Sim *)h;
+    for (int k = 0; k < s.nranks; ++k) {
+        std::vector<double> o;
+        switch (read_kind(s)) {
+        case READ_DIRECT: diag_rank<READ_DIRECT>(s, s.r[k], rows_per_chunk, o); break;
+        case READ_PULL_NAT: diag_rank<READ_PULL_NAT>(s, s.r[k], rows_per_chunk, o); break;
+        default: diag_rank<READ_PULL_SWAP>(s, s.r[k], rows_per_chunk, o); break;
+        }
+        std::memcpy(out12_per_rank + (size_t)k * NDIAG, o.data(), NDIAG * sizeof(double));
+    }
+}
+
+// ---- particle path --------------------------------------------------------------------------------------------------
+void hs_particles_init(void *h, int npart, double rad, double rho0, double rhopart, const double *lub7, const double *gforce,
+                       const double *ypglb, const double *wp, const double *omgp) {
+    Sim &s = *(Sim *)h;
+    s.part_on = true; s.npart = npart; s.rad = rad; s.rho0 = rho0;
+    s.lub = LubParams{lub7[0], lub7[1], lub7[2], lub7[3], lub7[4], lub7[5], lub7[6]};
+    for (int d = 0; d < 3; ++d) s.gforce[d] = gforce[d];
+    const double pi = 4.0 * std::atan(1.0);
+    s.maxlink = (long long)(8.0 * npart * 4.0 * pi * (rad + 1.0) * (rad + 1.0)) + 64;
+    const double volp = 4.0 / 3.0 * pi * rad * rad * rad;
+    s.amp = rhopart * volp;
+    s.aip = 0.4 * s.amp * rad * rad;
+    s.ypglb.assign(ypglb, ypglb + 3 * npart); s.wp.assign(wp, wp + 3 * npart); s.omgp.assign(omgp, omgp + 3 * npart);
+    s.rhopart = rhopart;
+    for (Rank &q : s.r) {
+        const size_t nown = (size_t)q.g.plane * (q.g.lz + 2), tb = (size_t)3 * npart;
+        q.own.assign(nown, -1); q.own0.assign(nown, -1);
+        q.ypglb.assign(ypglb, ypglb + tb); q.ypglb0 = q.ypglb;
+        q.wp.assign(wp, wp + tb); q.omgp.assign(omgp, omgp + tb);
+        for (std::vector<double> *v : {&q.fHIp, &q.torqp, &q.flubp, &q.forcepp, &q.torqpp, &q.thetap}) v->assign(tb, 0.0);
+        q.lnode.assign(s.maxlink, 0u); q.ldir.assign(s.maxlink, 0); q.lpart.assign(s.maxlink, 0); q.lq.assign(s.maxlink, 0.0);
+        q.lcount.assign((size_t)npart * PART_SPLIT + 1, 0); q.loffset.assign((size_t)npart * PART_SPLIT + 1, 0);
+    }
+}
+
+long long hs_beads_links(void *h) {
+    Sim &s = *(Sim *)h;
+    beads_links(s);
+    long long n = 0;
+    for (Rank &q : s.r) n += q.loffset[(size_t)s.npart * PART_SPLIT];
+    return n;
+}
+
+void hs_particle_step(void *h, int move) {
+    Sim &s = *(Sim *)h;
+    if (!s.links_valid) beads_links(s);
+    collide_stream(s, 0);
+    beads_collision(s);
+    if (move) {
+        beads_lubforce(s);
+        beads_move(s);
+        beads_links(s);
+        beads_filling(s);
+    }
+}
+
+// global owner mask own[iz][iy][ix]
+void hs_get_mask(void *h, int32_t *own) {
+    Sim &s = *(Sim *)h;
+    for (Rank &q : s.r)
+        for (int z = 0; z < q.g.lz; ++z)
+            for (int y = 0; y < q.g.ly; ++y)
+                std::memcpy(own + ((size_t)(q.globalz + z) * s.ny + y) * s.nx,
+                            q.own.data() + (size_t)q.g.plane * (z + 1) + (size_t)q.g.xp * y, (size_t)s.nx * sizeof(int32_t));
+}
+
+// links of slab k in its order (global 1-based node coordinates); returns the count
+long long hs_get_links(void *h, int k, int32_t *x, int32_t *y, int32_t *z, int32_t *ip, int32_t *part, double *qv) {
+    Sim &s = *(Sim *)h;
+    Rank &q = s.r[k];
+    const long long n = q.loffset[(size_t)s.npart * PART_SPLIT];
+    if (n > 0 && x) {
+        hs_launch(dim3((unsigned)((n + 127) / 128)), 128, k_links_export, q.g, q.globalz, n, links_of(q), x, y, z);
+        std::memcpy(ip, q.ldir.data(), n * sizeof(int32_t));
+        std::memcpy(part, q.lpart.data(), n * sizeof(int32_t));
+        std::memcpy(qv, q.lq.data(), n * sizeof(double));
+    }
+    return n;
+}
+
+void hs_get_particles(void *h, double *ypglb, double *wp, double *omgp, double *fHIp, double *torqp) {
+    Sim &s = *(Sim *)h;
+    const Rank &q = s.r[0];
+    const size_t tb = (size_t)3 * s.npart * sizeof(double);
+    std::memcpy(ypglb, q.ypglb.data(), tb); std::memcpy(wp, q.wp.data(), tb); std::memcpy(omgp, q.omgp.data(), tb);
+    std::memcpy(fHIp, q.fHIp.data(), tb); std::memcpy(torqp, q.torqp.data(), tb);
 }
 
 }  // extern "C"

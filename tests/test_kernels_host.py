@@ -52,6 +52,18 @@ def hk():
     L.hs_profiles.argtypes = [vp, C.c_int, dp]
     L.hs_init_channel.argtypes = [vp] + [C.c_double] * 4 + [C.c_uint64, C.c_int]
     L.hs_forcingp.argtypes = [vp, C.c_int, C.c_int] + [C.c_double] * 5 + [dp, dp, dp]
+    L.hs_avedensity.restype = C.c_double
+    L.hs_avedensity.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.hs_prerelax.argtypes = [vp, C.c_double, C.c_int, dp]
+    L.hs_diag.argtypes = [vp, C.c_int, dp]
+    L.hs_particles_init.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, dp, dp, dp, dp, dp]
+    L.hs_beads_links.restype = C.c_longlong
+    L.hs_beads_links.argtypes = [vp]
+    L.hs_particle_step.argtypes = [vp, C.c_int]
+    L.hs_get_mask.argtypes = [vp, ip]
+    L.hs_get_links.restype = C.c_longlong
+    L.hs_get_links.argtypes = [vp, C.c_int, ip, ip, ip, ip, ip, dp]
+    L.hs_get_particles.argtypes = [vp, dp, dp, dp, dp, dp]
     return L
 
 
@@ -362,4 +374,221 @@ def test_forcingp_against_the_translated_reference(oracle, hk, nranks):
     for a, k in zip(out, ("fx", "fy", "fz")):
         assert np.max(np.abs(a - z[k])) <= 1e-15 * scale, k
     assert np.ptp(out[0]) > 0 and np.ptp(out[2]) > 0
+    sim.close()
+
+
+# ---- kernels that cooperate inside a block (barriers, shared memory, shuffles): one fiber per thread ------------------
+@pytest.mark.parametrize("scheme", [AA, AB])
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_device_prerelax_loop(oracle, hk, scheme, nranks):
+    # d3q19_prerelax: fused rhoupdat + collision, block maximum of |rho - rhop| (shuffles + atomicMax on the bits)
+    nx, ny, nz = 32, 8, 8
+    tol, maxiter = 2e-5, 12
+
+    def start():
+        w, p = oracle.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+        w.set_f(w.get_f() + 1e-4 * np.random.default_rng(5).normal(size=(nz, ny, nx, 19)))      # rho no longer relaxed
+        return w, p
+    w, p = start()
+    it_ref = 0
+    while True:
+        rhop = w.get("rho").copy()
+        w.rhoupdat()
+        w.collision_MRT()
+        err_ref = np.max(np.abs(w.get("rho") - rhop))
+        if err_ref <= tol or it_ref > maxiter:                  # main.f90:85
+            break
+        it_ref += 1
+    w0, _ = start()
+    sim = HostSim(hk, p, nranks=nranks, scheme=scheme)
+    sim.upload(w0.get_f())
+    hk.hs_set_macro(sim.h, *[_d(np.ascontiguousarray(w0.get(k))) for k in ("rho", "ux", "uy", "uz")])
+    err = C.c_double(0.0)
+    it = hk.hs_prerelax(sim.h, tol, maxiter, C.byref(err))
+    assert it == it_ref and err.value == err_ref and it >= 2, (it, it_ref, err.value, err_ref)
+    assert np.array_equal(sim.download(), w.get_f())
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", [AA, AB])
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_avedensity_reduction(oracle, hk, scheme, nranks):
+    w, p, sim = pair(oracle, hk, (20, 6, 6), perturb=1e-3, scheme=scheme, nranks=nranks)
+    for _ in range(2):
+        w.collision_MRT(); w.macrovar()
+    sim.steps(2)
+    sim.macrovar()
+    mean_ref, n_ref = w.avedensity()
+    n = C.c_longlong(0)
+    mean = hk.hs_avedensity(sim.h, C.byref(n))
+    assert n.value == n_ref == 20 * 6 * 6
+    assert abs(mean - mean_ref) <= 1e-13 * np.max(np.abs(w.get_f()))          # the order of the sum differs
+    w.collision_MRT()
+    sim.steps(1)
+    assert relerr(sim.download(), w.get_f()) < 1e-13
+    sim.close()
+
+
+def _diag_from_partials(out, p, nranks, lzs, ustar):
+    """host side of d3q19_diag: merge of the per-slab results"""
+    nx, ny, nz = p.nx, p.ny, p.nz
+    sums = out[:, :7].sum(axis=0)
+    vmax, loc = 0.0, (0, 0, 0)
+    gz = 0
+    for r in range(nranks):
+        if out[r, 7] > vmax and out[r, 8] >= 0:
+            li = int(out[r, 8])
+            vmax, loc = out[r, 7], (li % nx + 1, (li // nx) % ny + 1, li // (nx * ny) + 1 + gz)
+        gz += lzs[r]
+    nf = sums[0]
+    um, vm, wm = sums[1] / nf, sums[2] / nf, sums[3] / nf
+    return dict(vmax=vmax, imout=loc[0], jmout=loc[1], kmout=loc[2], umean=um / ustar, vmean=vm / ustar, wmean=wm / ustar,
+                urms=np.sqrt(sums[4] / nf - um * um) / ustar, vrms=np.sqrt(sums[5] / nf - vm * vm) / ustar,
+                wrms=np.sqrt(sums[6] / nf - wm * wm) / ustar, volf=1.0 - nf / (nx * ny * nz),
+                rhomax=out[:, 9].max(), rhomin=out[:, 10].min(), nfluid=int(nf))
+
+
+@pytest.mark.parametrize("scheme", [AA, AB])
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_diag_reduction(oracle, hk, scheme, nranks):
+    from oracle import oracle as orc
+    nx, ny, nz = 140, 6, 4                     # two x-blocks: the block merge sees two columns sets
+    w, p, sim = pair(oracle, hk, (nx, ny, nz), perturb=1e-4, scheme=scheme, nranks=nranks)
+    for _ in range(3):
+        w.collision_MRT(); w.macrovar()
+    sim.steps(3)
+    out = np.zeros((nranks, 12))
+    hk.hs_diag(sim.h, 5, _d(out))
+    lzs = [pkg.slab(nz, nranks, r)[0] for r in range(nranks)]
+    got = _diag_from_partials(out, p, nranks, lzs, p.ustar)
+    ref = orc.diag_line(w, p.ustar)
+    for k in ("imout", "jmout", "kmout", "nfluid"):
+        assert got[k] == ref[k], k
+    assert got["vmax"] == ref["vmax"] and got["rhomax"] == ref["rhomax"] and got["rhomin"] == ref["rhomin"]
+    for k in ("umean", "vmean", "wmean", "urms", "vrms", "wrms"):
+        assert abs(got[k] - ref[k]) <= 1e-11 * max(abs(ref[k]), 1e-3), k
+    sim.close()
+
+
+# ---- the particle path against oracle/particles_oracle.c (parity unpinned against the reference: partlib.f90 is absent) ---
+PNX, PNY, PNZ, PRAD = 24, 20, 22, 4.3
+PPOS = [[11.7, 1.2, 20.9], [5.1, 12.0, 9.0], [15.5, 8.4, 13.2]]      # across the periodic y/z faces, near a wall, in the bulk
+PVEL = [[0.010, 0.020, -0.010], [0.0, 0.015, 0.0], [-0.005, 0.0, 0.012]]
+POMG = [[1e-3, 0.0, 2e-3], [0.0, -1e-3, 0.0], [5e-4, 5e-4, 0.0]]
+PU = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / PNX)
+
+
+def _particle_pair(oracle, hk, scheme, strict, nranks):
+    from oracle import particles as P
+    w, p = oracle.make_initial_state(PNX, PNY, PNZ, laminar=False, noise=True, ipart=1, **PU)
+    sim = HostSim(hk, p, nranks=nranks, scheme=scheme, strict=strict)
+    sim.upload(w.get_f())
+    pt = P.Particles(PNX, PNY, PNZ, PRAD, PPOS, PVEL, POMG)
+    lub = np.array(pt.lub, dtype=np.float64)
+    gf = np.zeros(3)
+    hk.hs_particles_init(sim.h, 3, PRAD, 1.0, 1.0, _d(lub), _d(gf), _d(pt.ypglb), _d(pt.wp), _d(pt.omgp))
+    return w, p, sim, pt
+
+
+def _host_links(hk, sim, nranks, cap):
+    keys = ("x", "y", "z", "ip", "part")
+    parts = []
+    for k in range(nranks):
+        a = [np.zeros(cap, dtype=np.int32) for _ in range(5)]
+        q = np.zeros(cap)
+        n = hk.hs_get_links(sim.h, k, *[_i(t) for t in a], _d(q))
+        parts.append(dict(zip(keys, [t[:n] for t in a]), q=q[:n]))
+    return parts
+
+
+def _host_particles(hk, sim):
+    o = [np.zeros((3, 3)) for _ in range(5)]
+    hk.hs_get_particles(sim.h, *[_d(a) for a in o])
+    return dict(zip(("ypglb", "wp", "omgp", "fHIp", "torqp"), o))
+
+
+def _set_oracle_mask(w, pt):
+    w.set_solid(np.where(pt.own > 0, 1, -1).astype(np.int32), pt.own)
+    w.set_particles(pt.ypglb, pt.wp, pt.omgp)
+
+
+@pytest.mark.parametrize("scheme", [AA, AB])
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+def test_particle_mask_and_links_bit_exact(oracle, hk, scheme, nranks):
+    w, p, sim, pt = _particle_pair(oracle, hk, scheme, True, nranks)
+    own = pt.build_mask()
+    k = pt.build_links()
+    n = hk.hs_beads_links(sim.h)
+    assert n == len(k["q"]) and n > 1000
+    got = np.zeros((PNZ, PNY, PNX), dtype=np.int32)
+    hk.hs_get_mask(sim.h, _i(got))
+    assert np.array_equal(got, own)
+    parts = _host_links(hk, sim, nranks, n + 8)
+    if nranks == 1:
+        for key in ("x", "y", "z", "ip", "part", "q"):
+            assert np.array_equal(parts[0][key], k[key]), key          # same links, same order, same q bits
+    else:
+        # every slab lists the links whose fluid node it owns, in the canonical order restricted to the slab
+        lzs = [pkg.slab(PNZ, nranks, r)[0] for r in range(nranks)]
+        gz = 0
+        for r in range(nranks):
+            sel = (k["z"] > gz) & (k["z"] <= gz + lzs[r])
+            for key in ("x", "y", "z", "ip", "part", "q"):
+                assert np.array_equal(parts[r][key], k[key][sel]), (r, key)
+            gz += lzs[r]
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", [AA, AB])
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_particle_ibb_and_force(oracle, hk, scheme, strict, nranks):
+    w, p, sim, pt = _particle_pair(oracle, hk, scheme, strict, nranks)
+    pt.build_mask(); pt.build_links()
+    _set_oracle_mask(w, pt)
+    w.macrovar()
+    fluid = pt.own < 0
+    for step in range(4):                                   # both storage phases of AA, fixed particles
+        w.collision_MRT()
+        f = w.get_f(); pt.ibb(f); w.set_f(f); w.macrovar()
+        hk.hs_particle_step(sim.h, 0)
+        out = sim.download()
+        scale = np.max(np.abs(f[fluid]))
+        assert np.max(np.abs(out[fluid] - f[fluid])) < 1e-12 * scale, step
+        g = _host_particles(hk, sim)
+        assert np.max(np.abs(g["fHIp"] - pt.fHIp)) < 1e-10 * np.max(np.abs(pt.fHIp)), step
+        assert np.max(np.abs(g["torqp"] - pt.torqp)) < 1e-10 * np.max(np.abs(pt.torqp)), step
+    assert np.dot(pt.fHIp[2], PVEL[2]) < 0                  # drag opposes the motion of the bulk particle
+    sim.close()
+
+
+@pytest.mark.parametrize("scheme", [AA, AB])
+def test_moving_particles_with_refill(oracle, hk, scheme):
+    w, p, sim, pt = _particle_pair(oracle, hk, scheme, False, 1)
+    pt.build_mask(); pt.build_links()
+    _set_oracle_mask(w, pt)
+    w.macrovar()
+    nfill_total = 0
+    for step in range(12):
+        w.collision_MRT()
+        f = w.get_f(); pt.ibb(f)
+        pt.lubforce(); pt.move()
+        pt.build_mask(); pt.build_links()
+        nfill_total += pt.refill(f)
+        w.set_f(f); _set_oracle_mask(w, pt); w.macrovar()
+        hk.hs_particle_step(sim.h, 1)
+        g = _host_particles(hk, sim)
+        assert np.max(np.abs(g["ypglb"] - pt.ypglb)) < 1e-11, step
+        got = np.zeros((PNZ, PNY, PNX), dtype=np.int32)
+        hk.hs_get_mask(sim.h, _i(got))
+        assert np.array_equal(got, pt.own), step
+        fluid = pt.own < 0
+        out = sim.download()
+        scale = np.max(np.abs(f[fluid]))
+        assert np.max(np.abs(out[fluid] - f[fluid])) < 1e-9 * scale, step
+        assert np.max(np.abs(g["fHIp"] - pt.fHIp)) < 1e-9 * np.max(np.abs(pt.fHIp)), step
+    assert nfill_total > 0
+    k, gl = pt.links, _host_links(hk, sim, 1, len(pt.links["q"]) + 8)[0]
+    for key in ("x", "y", "z", "ip", "part"):
+        assert np.array_equal(gl[key], k[key]), key
     sim.close()
