@@ -1173,6 +1173,7 @@ extern "C" int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_
     if (h->halo_on) return fail("d3q19_particles_init: the particle path exchanges its halo through NCCL (do not call d3q19_ipc_connect)");
     if (!h->idx32) return fail("d3q19_particles_init: slab too large for 32-bit link indices");
     if (2.0 * prm->rad + 4.0 > h->cfg.ny || 2.0 * prm->rad + 4.0 > h->cfg.nz) return fail("d3q19_particles_init: particle larger than the periodic box");
+    if (prm->rad > 600.0) return fail("d3q19_particles_init: rad %g: a particle's bounding box must hold fewer than 2^31 nodes", prm->rad);
     h->pp = *prm;
     if (h->ypglb) { cudaFree(h->ypglb); cudaFree(h->wp); cudaFree(h->omgp); }
     if (h->solid) { cudaFree(h->solid); h->solid = nullptr; }
