@@ -56,7 +56,11 @@ def parse_args():
                     help="z-face exchange: NCCL send/recv of the packed faces on a second stream, overlapped with the interior "
                          "(default; equal or faster in every configuration measured, profiles/r01d_halo_transports.md) or "
                          "stores into the neighbour GPU's memory over NVLink inside the step kernel")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--boundary-stream", action="store_true",
+                    help="NCCL transport, opt-in: launch the two boundary planes of a step on their own high-priority stream next "
+                         "to the interior launch instead of in front of it (D3Q19_BOUNDARY_STREAM=1)")
+    ap.add_argument("--cpu-steps", type=int, default=20,
+                    help="timed steps of the CPU arm (20 steps of 512x256x256 = about 10 s on 16 cores)")
     ap.add_argument("--particles", type=int, default=0,
                     help="configs[4]: N finite-size spheres (interpolated bounce-back, refill, momentum-exchange force); "
                          "a step is then links + collide-stream + IBB + lubrication + move + refill")
@@ -270,6 +274,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return bool(t.item() > 0.5)
 
+    if args.boundary_stream and world > 1 and args.particles == 0:
+        os.environ["D3Q19_BOUNDARY_STREAM"] = "1"
+
     def build_sim(halo_req, nccl_id):
         """the channel on this rank's slab with its synthetic initial state; returns (sim, halo actually in use)"""
         sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local_rank, scheme=scheme,
@@ -422,7 +429,8 @@ def main():
                        "parallelism": ("z-slab x%d, faces %s" % (world, {
                            "peer": "stored into the neighbour GPU's memory over NVLink inside the step kernel",
                            "put": "stored into the neighbour GPU's memory over NVLink by a copy kernel on a second stream",
-                           "nccl": "by NCCL send/recv"}[halo])) if world > 1 else "1 GPU",
+                           "nccl": "by NCCL send/recv" + (", boundary planes on their own stream" if os.environ.get(
+                               "D3Q19_BOUNDARY_STREAM") == "1" else "")}[halo])) if world > 1 else "1 GPU",
                        "l2": "populations %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (c1["population_bytes"] / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "impl": "ours",

@@ -86,6 +86,12 @@ struct d3q19_handle {
     cudaEvent_t evB = nullptr, evX = nullptr, t0 = nullptr, t1 = nullptr, evC[2] = {nullptr, nullptr},
                 evS[2] = {nullptr, nullptr};
     bool exchange_pending = false;
+    // opt-in (D3Q19_BOUNDARY_STREAM=1): the boundary-plane launch of the NCCL transport runs on its own high-priority
+    // stream sb, concurrently with the interior launch of the SAME step (step_impl, "boundary stream")
+    cudaStream_t sb = nullptr;
+    cudaEvent_t evI = nullptr;
+    bool bstream = false;
+    bool b_pending = false;       // the last boundary launch (event evB on sb) has not been waited for by sc yet
     // optional per-step timeline (d3q19_trace_enable): 4 timing events per step -- [0] before the boundary launch,
     // [1] after it, [2] after the interior launch (all on sc), [3] after the exchange / put (on sx)
     cudaEvent_t *trace_ev = nullptr;
@@ -179,6 +185,10 @@ static int wait_exchange(d3q19_handle *h) {
         h->exchange_pending = false;
         h->put_pending = false;
     }
+    if (h->b_pending) {                  // boundary stream: the planes next to the faces are written on sb
+        CK(cudaStreamWaitEvent(h->sc, h->evB, 0));
+        h->b_pending = false;
+    }
     return 0;
 }
 
@@ -258,6 +268,7 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->sc) cudaStreamSynchronize(h->sc);
     if (h->sx) cudaStreamSynchronize(h->sx);
+    if (h->sb) cudaStreamSynchronize(h->sb);
     shim_unpin(h);
     if (h->halo_on) {
         // nobody may still be storing into our planes, and we must let go of theirs before they free them
@@ -287,10 +298,11 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
                     h->wp, h->omgp, h->send_up, h->send_dn, h->recv_lo, h->recv_hi, h->stage[0], h->stage[1],
                     h->scal, h->red_d, h->red_c, h->prof_partial, h->prof_out, h->vort, h->vort_halo};
     for (void *p : ptrs) if (p) cudaFree(p);
-    cudaEvent_t evs[] = {h->evB, h->evX, h->t0, h->t1, h->evC[0], h->evC[1], h->evS[0], h->evS[1]};
+    cudaEvent_t evs[] = {h->evB, h->evX, h->evI, h->t0, h->t1, h->evC[0], h->evC[1], h->evS[0], h->evS[1]};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     if (h->sc) cudaStreamDestroy(h->sc);
     if (h->sx) cudaStreamDestroy(h->sx);
+    if (h->sb) cudaStreamDestroy(h->sb);
     delete h;
     return 0;
 }
@@ -354,6 +366,14 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
     CKH(cudaStreamCreateWithPriority(&h->sx, cudaStreamNonBlocking, hi));
     CKH(cudaEventCreateWithFlags(&h->evB, cudaEventDisableTiming));
     CKH(cudaEventCreateWithFlags(&h->evX, cudaEventDisableTiming));
+    if (cfg->nranks > 1 && !cfg->ipart) {
+        const char *t = getenv("D3Q19_BOUNDARY_STREAM");
+        h->bstream = t && atoi(t) > 0;
+    }
+    if (h->bstream) {
+        CKH(cudaStreamCreateWithPriority(&h->sb, cudaStreamNonBlocking, hi));
+        CKH(cudaEventCreateWithFlags(&h->evI, cudaEventDisableTiming));
+    }
     for (int i = 0; i < 2; ++i) {
         CKH(cudaEventCreateWithFlags(&h->evC[i], cudaEventDisableTiming));
         CKH(cudaEventCreateWithFlags(&h->evS[i], cudaEventDisableTiming));
@@ -392,9 +412,10 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
 
 extern "C" int d3q19_sync(d3q19_handle *h) {
     CK(cudaSetDevice(h->cfg.device));
-    if (h->halo_on) RK_(wait_exchange(h));       // the neighbours' stores of the last step have landed
+    if (h->halo_on || h->b_pending) RK_(wait_exchange(h));       // the neighbours' stores of the last step have landed
     CK(cudaStreamSynchronize(h->sc));
     CK(cudaStreamSynchronize(h->sx));
+    if (h->sb) CK(cudaStreamSynchronize(h->sb));
     if (h->halo_on) {
         // watchdog of the flag waits (kernels.cuh halo_spin): a neighbour's flag that never came
         unsigned int bad = 0;
@@ -889,6 +910,38 @@ static int step_impl(d3q19_handle *h, const StepParams &p, double *written) {
         RK_((launch_step_halo<SK, STRICT, GENERIC>(h, p)));
         trace_mark(h, 2, h->sc); trace_mark(h, 3, h->sc);
         trace_next(h);
+        return 0;
+    }
+    if (h->bstream && !GENERIC && lz > 2) {
+        // "Boundary stream": only the two boundary planes of step k need the faces of step k-1; the interior needs the
+        // boundary planes of step k-1 and nothing that travels.  So the interior launches follow one another on sc
+        // without ever waiting for an exchange, and the boundary launch of step k runs NEXT TO the interior launch of
+        // step k on a high-priority stream instead of in front of it (no drain/refill of the GPU around a 2-plane
+        // kernel, which is what the in-order sequence loses on thin slabs).  Order:
+        //   B(k) after everything enqueued on sc so far (I(k-1), readers) and after X(k-1);   on sb
+        //   I(k) after I(k-1) (stream order) and B(k-1);                                      on sc
+        //   X(k) after B(k) and X(k-1) (stream order);                                        on sx
+        // No node of B(k) touches an address a node of I(k) touches (disjoint nodes; in the in-place odd step every
+        // address belongs to exactly one node), X(k) runs next to I(k) as before, and X(k) next to I(k+1) is new but
+        // disjoint as well: X touches ghost planes, or after an odd step the slots of planes 1 / lz that only the
+        // neighbour's nodes own, or reads (packs) face slots that the next interior launch does not write.
+        if (h->b_pending) CK(cudaStreamWaitEvent(h->sc, h->evB, 0));
+        CK(cudaEventRecord(h->evI, h->sc));
+        CK(cudaStreamWaitEvent(h->sb, h->evI, 0));
+        if (h->exchange_pending) CK(cudaStreamWaitEvent(h->sb, h->evX, 0));
+        trace_mark(h, 0, h->sb);
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 2, h->sb, lz - 1)));       // planes 1 and lz in one launch
+        CK(cudaEventRecord(h->evB, h->sb));
+        trace_mark(h, 1, h->sb);
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 2, lz - 2, h->sc)));
+        trace_mark(h, 2, h->sc);
+        CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
+        RK_(exchange_after_step(h, SK, written, h->sx));
+        CK(cudaEventRecord(h->evX, h->sx));
+        trace_mark(h, 3, h->sx);
+        trace_next(h);
+        h->exchange_pending = true;
+        h->b_pending = true;
         return 0;
     }
     // boundary planes first, so that their faces travel while the interior is computed

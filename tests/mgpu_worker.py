@@ -62,6 +62,34 @@ def main():
     only = os.environ.get("MGPU_ONLY", "")          # e.g. "peer": just the peer-memory halo cases (short runs on many GPUs)
     if only:
         cases = [c for c in cases if c[2].startswith(only) or (only == "peer" and c[2] == "put")]
+    if only == "bstream":
+        # opt-in "boundary stream" of the NCCL transport (D3Q19_BOUNDARY_STREAM=1, d3q19_api.cu step_impl): the
+        # boundary launch of a step runs next to the interior launch on its own stream.  Bursts of steps WITHOUT a
+        # reader in between, so that the cross-stream ordering is what is being tested.
+        os.environ["D3Q19_BOUNDARY_STREAM"] = "1"
+        for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
+            for (nx, ny, nz) in [(24, 6, 4 * world), (33, 5, 3 * world + 1), (130, 7, 5 * world + 2), (64, 32, 16 * world)]:
+                ctx[0] = "bstream scheme %d case %s" % (scheme, (nx, ny, nz))
+                w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+                w.set_f(w.get_f() + 1e-4 * np.random.default_rng(7).normal(size=(nz, ny, nx, 19)))
+                sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local, scheme=scheme,
+                                      math_mode=capi.MATH_STRICT, nccl_id=new_id(), overlap=True)
+                z0, z1 = sim.globalz, sim.globalz + sim.lz
+                sim.FORCING()
+                sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
+                w.macrovar()
+                out = np.empty((sim.lz, ny, nx, 19))
+                for burst in (1, 2, 5, 1, 8, 3):
+                    for _ in range(burst):
+                        w.collision_MRT(); w.macrovar()
+                    sim.run_device(burst)
+                    sim.download_f(out)
+                    chk("burst of %d" % burst, bool(np.array_equal(out, w.get_f()[z0:z1])))
+                    sim.device_macrovar()                      # a reader on sc between two bursts
+                    chk("macrovar", bool(np.array_equal(sim.uy, w.get("uy")[z0:z1])))
+                sim.close(); w.close()
+        del os.environ["D3Q19_BOUNDARY_STREAM"]
+        cases = []
     for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
         for (nx, ny, nz), overlap, halo in cases:
             ctx[0] = "scheme %d case %s overlap %s halo %s" % (scheme, (nx, ny, nz), overlap, halo)
@@ -208,7 +236,7 @@ def main():
 
     # halo watchdog: the last rank never steps; a neighbour waiting for its flag must give up after the
     # timeout and d3q19_sync must say so (kernels.cuh halo_spin) -- a dead rank may not hang the others' GPUs
-    if ok:
+    if ok and only != "bstream":
         ctx[0] = "halo watchdog"
         os.environ["D3Q19_HALO_TIMEOUT_S"] = "1.5"
         nx, ny, nz = 24, 6, 4 * world
