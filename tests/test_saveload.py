@@ -66,3 +66,89 @@ def test_reslab(tmp_path):
         t = Stub(nx, ny, lz, rank=r)
         sl.loadcntdflow(t, str(tmp_path / "out"), 1000)
         assert np.array_equal(t.f, full[gz:gz + lz])
+
+
+class StubM(Stub):
+    """with the macroscopic arrays saveprerelax writes"""
+
+    def __init__(self, lx, ly, lz, rank=0):
+        super().__init__(lx, ly, lz, rank)
+        rng = np.random.default_rng(100 + rank)
+        self.rho, self.ux, self.uy, self.uz = (rng.normal(size=(lz, ly, lx)) for _ in range(4))
+        self.istep = 0
+
+
+def test_initflow_and_prerelax_files(tmp_path):
+    s = StubM(5, 4, 3, rank=12)
+    path = sl.saveinitflow(s, str(tmp_path), istat=7)
+    assert path.endswith("finit.012")                                # saveload.f90:113-114
+    raw = open(path, "rb").read()
+    assert struct.unpack("<3i", raw[:12]) == (4, 7, 4)                # record 1: istat
+    nbytes = 19 * 5 * 4 * 3 * 8
+    assert struct.unpack("<i", raw[12:16])[0] == nbytes and len(raw) == 12 + 8 + nbytes
+    t = StubM(5, 4, 3, rank=12)
+    t.f[...] = 0
+    assert sl.loadinitflow(t, str(tmp_path)) == 7 and np.array_equal(t.f, s.f) and t.changed == 1
+    # prerelax: (f, rho) share ONE record, (ux, uy, uz) the next (saveload.f90:67-69)
+    path = sl.saveprerelax(s, str(tmp_path), istep=345)
+    assert path.endswith("prerelax_01/finit.012")
+    raw = open(path, "rb").read()
+    assert struct.unpack("<3i", raw[:12]) == (4, 345, 4)
+    n = 5 * 4 * 3
+    assert struct.unpack("<i", raw[12:16])[0] == (19 * n + n) * 8
+    u = StubM(5, 4, 3, rank=12)
+    for a in (u.f, u.rho, u.ux, u.uy, u.uz):
+        a[...] = 0
+    assert sl.loadprerelax(u, str(tmp_path)) == 345
+    for k in ("f", "rho", "ux", "uy", "uz"):
+        assert np.array_equal(getattr(u, k), getattr(s, k)), k
+
+
+def _write_frm(dirname, istp, rank, head, f):
+    import os
+    os.makedirs(dirname, exist_ok=True)
+    with open(sl.frm_filename(dirname, istp, rank), "wb") as fh:
+        sl.write_record(fh, np.array(head, dtype="<i4").tobytes())
+        sl.write_record(fh, np.ascontiguousarray(f))
+
+
+def test_reference_reslab_loaders(tmp_path):
+    nx, ny, nz = 4, 3, 12
+    full = np.random.default_rng(8).normal(size=(nz, ny, nx, 19))
+    # files of a 6-rank run, read by a 2-rank run (iprocrate = 3): saveload.f90:336-385
+    for r in range(6):
+        _write_frm(str(tmp_path / "six"), 4200, r, (4200, 1, 2), full[2 * r:2 * r + 2])
+    assert sl.frm_filename("d", 4200, 5).endswith("endrunflow.004200.005")
+    for r in range(2):
+        t = Stub(nx, ny, 6, rank=r)
+        assert sl.loadcntdflow_frmmore(t, str(tmp_path / "six"), 4200, 3) == (4200, 1, 2)
+        assert np.array_equal(t.f, full[6 * r:6 * r + 6]) and t.v.istep0 == 4200
+    # files of a 2-rank run, read by a 6-rank run: saveload.f90:388-434
+    for r in range(2):
+        _write_frm(str(tmp_path / "two"), 4200, r, (4200, 0, 0), full[6 * r:6 * r + 6])
+    for r in range(6):
+        t = Stub(nx, ny, 2, rank=r)
+        sl.loadcntdflow_frmless(t, str(tmp_path / "two"), 4200, 3)
+        assert np.array_equal(t.f, full[2 * r:2 * r + 2])
+
+
+def test_cpu_yz_decomposition_to_gpu_slabs(tmp_path, oracle):
+    # a CPU run on nprocY x nprocZ = 3 x 2 ranks with uneven blocks (para.f90:229-262) -> 4 z-slabs
+    nx, ny, nz, npy, npz = 5, 8, 7, 3, 2
+    full = np.random.default_rng(9).normal(size=(nz, ny, nx, 19))
+    w, p = oracle.make_initial_state(nx, ny, nz, laminar=True, noise=False, nprocY=npy, nprocZ=npz)
+    for rid in range(npy * npz):
+        d = w.rank_dims(rid)                                      # the oracle's para: extents and offsets per rank
+        indy, indz = rid % npy, rid // npy
+        assert (d["ly"], d["globaly"]) == sl.yz_block(ny, npy, indy)
+        assert (d["lz"], d["globalz"]) == sl.yz_block(nz, npz, indz)
+        s = Stub(nx, d["ly"], d["lz"], rank=rid)
+        s.f = np.ascontiguousarray(full[d["globalz"]:d["globalz"] + d["lz"], d["globaly"]:d["globaly"] + d["ly"]])
+        sl.savecntdflow(s, str(tmp_path / "cpu"))
+    sl.from_yz_ranks(str(tmp_path / "cpu"), str(tmp_path / "gpu"), 1000, nx, ny, nz, npy, npz, 4, pkg.slab)
+    for r in range(4):
+        lz, gz = pkg.slab(nz, 4, r)
+        t = Stub(nx, ny, lz, rank=r)
+        assert sl.loadcntdflow(t, str(tmp_path / "gpu"), 1000)[0] == 1000
+        assert np.array_equal(t.f, full[gz:gz + lz])
+    w.close()
