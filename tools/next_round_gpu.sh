@@ -1,0 +1,58 @@
+#!/bin/bash
+# What the first gpurun calls of the next round should run (DESIGN.md "Next").  Everything lands in gpurun_out/;
+# copy what is to be judged into profiles/ afterwards.  A number printed under ncu is never a bench value.
+#
+#   gpurun --timeout 1500 -- 'bash tools/next_round_gpu.sh one'        # 1 GPU, ~12 min
+#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/next_round_gpu.sh two'   # 2 GPUs, ~8 min
+#   gpurun --gpus 8 --timeout 900 -- 'bash tools/next_round_gpu.sh eight'  # 8 GPUs, ~5 min
+set -u
+mkdir -p gpurun_out
+tag=${TAG:-r02a}
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+
+case "${1:-one}" in
+one)
+    # 1. the whole GPU suite (particle kernels changed since the last GPU run)
+    timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.log 2>&1
+    tail -3 gpurun_out/${tag}_pytest_gpu.log
+    # 2. headline line, particle line (round 1c: 2.44 ms per step), in-place line
+    timeout 300 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+    timeout 300 python bench.py --particles 100 --no-cpu --steps 100 > gpurun_out/${tag}_bench_part.json 2>> gpurun_out/${tag}_bench.err
+    timeout 300 python bench.py --scheme aa --no-cpu > gpurun_out/${tag}_bench_aa.json 2>> gpurun_out/${tag}_bench.err
+    # 3. launch list of the particle step (shares of the bookkeeping kernels) and of the plain step
+    timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${tag}_launches_particles.csv \
+        python bench.py --particles 100 --no-cpu --no-e2e --steps 3 --warmup 1 > /dev/null 2>&1
+    timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/${tag}_launches.csv \
+        python bench.py --no-cpu --no-e2e --steps 5 --warmup 3 > /dev/null 2>&1
+    ;;
+two)
+    # boundary stream: parity first, then its effect on thin and thick slabs, then the timelines
+    MGPU_ONLY=bstream timeout 600 $TR --nproc-per-node 2 --master-port 29611 tests/mgpu_worker.py > gpurun_out/${tag}_mgpu_bstream_n2.log 2>&1
+    tail -2 gpurun_out/${tag}_mgpu_bstream_n2.log
+    for sc in strong weak; do
+        for bs in "" "--boundary-stream"; do
+            name=${tag}_n2_${sc}${bs:+_bstream}
+            timeout 300 $TR --nproc-per-node 2 --master-port 29612 bench.py --gpus 2 --scaling $sc --no-e2e $bs > gpurun_out/$name.json 2> gpurun_out/$name.err
+        done
+    done
+    # 8-GPU strong scaling per-GPU block on 2 GPUs: 512x256x64 total = 32 planes each
+    for bs in "" "--boundary-stream"; do
+        name=${tag}_n2_thin${bs:+_bstream}
+        timeout 300 $TR --nproc-per-node 2 --master-port 29613 bench.py --gpus 2 --scaling strong --workload 512x256x64 --no-e2e $bs > gpurun_out/$name.json 2> gpurun_out/$name.err
+    done
+    grep -h '"value"' gpurun_out/${tag}_n2_*.json | python -c "
+import json, sys
+for l in sys.stdin:
+    d = json.loads(l); print(d['config']['parallelism'][:70], d['config']['per_gpu'], d['scaling'], round(d['value']), 'MLUPS', round(d['ms_per_step'], 4), 'ms')"
+    ;;
+eight)
+    for sc in strong weak; do
+        for bs in "" "--boundary-stream"; do
+            name=${tag}_n8_${sc}${bs:+_bstream}
+            timeout 300 $TR --nproc-per-node 8 --master-port 29614 bench.py --gpus 8 --scaling $sc --no-e2e $bs > gpurun_out/$name.json 2> gpurun_out/$name.err
+        done
+    done
+    MGPU_ONLY=bstream timeout 400 $TR --nproc-per-node 8 --master-port 29615 tests/mgpu_worker.py > gpurun_out/${tag}_mgpu_bstream_n8.log 2>&1
+    tail -2 gpurun_out/${tag}_mgpu_bstream_n8.log
+    ;;
+esac
