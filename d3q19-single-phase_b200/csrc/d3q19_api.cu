@@ -118,6 +118,7 @@ struct d3q19_handle {
     long long maxlink = 0, nlink = 0;
     long long *lcount = nullptr, *loffset = nullptr;
     unsigned long long *nfilled_dev = nullptr;
+    double *fill_halo = nullptr;                 // z-slab refill: [send up][send dn][ghost lo][ghost hi], 19 x plane each
     double amp = 0, aip = 0;
     // halo in peer memory (cudaIpc): [0] = lower neighbour (mzm), [1] = upper neighbour (mzp)
     bool halo_on = false;
@@ -284,7 +285,7 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
     }
     if (h->part_on) {
         void *pp_[] = {h->own, h->own0, h->pbuf, h->links.node, h->links.dir, h->links.part, h->links.q, h->lcount, h->loffset,
-                       h->nfilled_dev};
+                       h->nfilled_dev, h->fill_halo};
         for (void *q : pp_) if (q) cudaFree(q);
         h->solid = h->isn = nullptr; h->ypglb = h->wp = h->omgp = nullptr;
     }
@@ -1386,6 +1387,36 @@ extern "C" int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled) {
     FillParams P;
     P.pg = part_geom(h); P.S = h->A; P.own0 = h->own0; P.own = h->own; P.ypglb0 = h->ypglb0;
     P.ypglb = h->ypglb; P.wp = h->wp; P.omgp = h->omgp; P.nfilled = h->nfilled_dev;
+    P.ghost_lo = P.ghost_hi = nullptr;
+    if (h->cfg.nranks > 1) {
+        // source nodes across a slab face: all 19 canonical populations of the neighbours' planes next to the faces
+        // (the ghost planes of the population array carry 5), so that the refill does not depend on the decomposition
+        const Geom &g = h->g;
+        const size_t cnt = (size_t)NPOP * g.plane;
+        if (!h->fill_halo) CK(cudaMalloc(&h->fill_halo, 4 * cnt * sizeof(double)));
+        double *send_up = h->fill_halo, *send_dn = send_up + cnt, *ghost_lo = send_dn + cnt, *ghost_hi = ghost_lo + cnt;
+        const dim3 gp = grid_nodes(h, 1);
+        switch (read_kind(h)) {
+        case READ_DIRECT: k_plane_gather<READ_DIRECT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz);
+                          k_plane_gather<READ_DIRECT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_dn, 1); break;
+        case READ_PULL_NAT: k_plane_gather<READ_PULL_NAT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz);
+                            k_plane_gather<READ_PULL_NAT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_dn, 1); break;
+        default: k_plane_gather<READ_PULL_SWAP><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz);
+                 k_plane_gather<READ_PULL_SWAP><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_dn, 1); break;
+        }
+        CK(cudaGetLastError());
+        const int up = (h->cfg.rank + 1) % h->cfg.nranks, dn = (h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks;
+        NcclApi &n = nccl_api();
+        NK(n.GroupStart());
+        NK(n.Send(send_up, cnt, NCCL_FLOAT64, up, h->comm, h->sc));
+        NK(n.Send(send_dn, cnt, NCCL_FLOAT64, dn, h->comm, h->sc));
+        NK(n.Recv(ghost_lo, cnt, NCCL_FLOAT64, dn, h->comm, h->sc));
+        NK(n.Recv(ghost_hi, cnt, NCCL_FLOAT64, up, h->comm, h->sc));
+        NK(n.GroupEnd());
+        h->n_other_kernels += 2;
+        h->n_nccl += 4;
+        P.ghost_lo = ghost_lo; P.ghost_hi = ghost_hi;
+    }
     const dim3 gp((unsigned)h->npart, PART_SPLIT);
     switch (read_kind(h)) {
     case READ_DIRECT: k_beads_fill<READ_DIRECT><<<gp, 128, 0, h->sc>>>(P); break;

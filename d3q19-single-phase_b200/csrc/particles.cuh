@@ -381,7 +381,25 @@ struct FillParams {
     const double *ypglb0;         // positions before the move (their boxes cover every uncovered node)
     const double *ypglb, *wp, *omgp;
     unsigned long long *nfilled;
+    // z-slab runs: the 19 canonical populations of the neighbours' planes next to the faces ([i][y][x], pitch xp),
+    // lo = the lower neighbour's plane lz, hi = the upper neighbour's plane 1 (k_plane_gather + send/recv before the
+    // refill).  A ghost plane of the population array holds only the 5 populations that cross the face, not a
+    // node's 19; with these copies a refill next to a face sees the same source nodes as on a single domain.
+    const double *ghost_lo, *ghost_hi;
 };
+
+// canonical populations of one plane -> out[i][y][x] (pitch xp), whatever the storage phase
+template <int RK>
+__global__ void __launch_bounds__(BLOCK_X) k_plane_gather(Geom g, const double *A, double *out, int zg) {
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.lx) return;
+    const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, blockIdx.y, zg);
+    double f[NPOP];
+    gather19<RK>(A, g, k, f);
+    const long long o = (long long)blockIdx.y * g.xp + x;
+#pragma unroll
+    for (int i = 0; i < NPOP; ++i) out[(long long)i * g.plane + o] = f[i];
+}
 
 __device__ __forceinline__ void feq19(double rho, double ux, double uy, double uz, double (&fe)[NPOP]) {
     const double usqr = 1.5 * (ux * ux + uy * uy + uz * uz);
@@ -438,13 +456,23 @@ __global__ void __launch_bounds__(128) k_beads_fill(const __grid_constant__ Fill
             if (kx < 0 || kx >= g.lx) continue;
             const int ky = (y + cy < 0) ? g.ly - 1 : (y + cy >= g.ly ? 0 : y + cy);
             int kz = zg + cz;
+            const double *gh = nullptr;
             if (g.zlo_src != 0) kz = kz < 1 ? g.lz : (kz > g.lz ? 1 : kz);       // single slab: periodic wrap
-            else if (kz < 1 || kz > g.lz) continue;                                // neighbours in a ghost plane are not sources
-            const long long m = (long long)kx + (long long)g.xp * (ky + (long long)g.ly * kz);
+            else if (kz < 1 || kz > g.lz) {                                        // a neighbour across a slab face
+                gh = kz < 1 ? P.ghost_lo : P.ghost_hi;
+                if (!gh) continue;
+            }
+            const long long m = (long long)kx + (long long)g.xp * (ky + (long long)g.ly * kz);     // the masks are ghosted
             if (P.own0[m] > 0 || P.own[m] > 0) continue;
-            const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, kx, ky, kz);
             double fm[NPOP];
-            gather19<RK>(P.S, g, k, fm);
+            if (gh) {
+                const long long o = (long long)ky * g.xp + kx;
+#pragma unroll
+                for (int i = 0; i < NPOP; ++i) fm[i] = gh[(long long)i * g.plane + o];
+            } else {
+                const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, kx, ky, kz);
+                gather19<RK>(P.S, g, k, fm);
+            }
             double r = 0.0;
 #pragma unroll
             for (int i = 0; i < NPOP; ++i) r += fm[i];

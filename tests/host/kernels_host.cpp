@@ -47,6 +47,7 @@ struct Rank {
     std::vector<int32_t> ldir, lpart;
     std::vector<double> lq;
     std::vector<long long> lcount, loffset;
+    std::vector<double> fill_send_up, fill_send_dn, fill_ghost_lo, fill_ghost_hi;      // 19 x plane each
     unsigned long long nfilled = 0;
 };
 
@@ -379,9 +380,32 @@ void fill_rank(Sim &s, Rank &q) {
     FillParams P;
     P.pg = part_geom(s, q); P.S = q.A; P.own0 = q.own0.data(); P.own = q.own.data(); P.ypglb0 = q.ypglb0.data();
     P.ypglb = q.ypglb.data(); P.wp = q.wp.data(); P.omgp = q.omgp.data(); P.nfilled = &q.nfilled;
+    P.ghost_lo = P.ghost_hi = nullptr;
+    if (s.nranks > 1) { P.ghost_lo = q.fill_ghost_lo.data(); P.ghost_hi = q.fill_ghost_hi.data(); }
     hs_launch(dim3((unsigned)s.npart, PART_SPLIT), 128, k_beads_fill<RK>, P);
 }
+template <int RK>
+void plane_gather_rank(Rank &q) {
+    const size_t cnt = (size_t)NPOP * q.g.plane;
+    q.fill_send_up.assign(cnt, 0.0); q.fill_send_dn.assign(cnt, 0.0);
+    hs_launch(grid_nodes(q.g, 1), BLOCK_X, k_plane_gather<RK>, q.g, (const double *)q.A, q.fill_send_up.data(), q.g.lz);
+    hs_launch(grid_nodes(q.g, 1), BLOCK_X, k_plane_gather<RK>, q.g, (const double *)q.A, q.fill_send_dn.data(), 1);
+}
 void beads_filling(Sim &s) {
+    if (s.nranks > 1) {
+        for (Rank &q : s.r) {
+            switch (read_kind(s)) {
+            case READ_DIRECT: plane_gather_rank<READ_DIRECT>(q); break;
+            case READ_PULL_NAT: plane_gather_rank<READ_PULL_NAT>(q); break;
+            default: plane_gather_rank<READ_PULL_SWAP>(q); break;
+            }
+        }
+        const int n = s.nranks;
+        for (int k = 0; k < n; ++k) {
+            s.r[(k + 1) % n].fill_ghost_lo = s.r[k].fill_send_up;
+            s.r[(k + n - 1) % n].fill_ghost_hi = s.r[k].fill_send_dn;
+        }
+    }
     for (Rank &q : s.r) {
         q.nfilled = 0;
         switch (read_kind(s)) {
