@@ -26,6 +26,9 @@ one)
         python bench.py --no-cpu --no-e2e --steps 5 --warmup 3 > /dev/null 2>&1
     ;;
 two)
+    # the established multi-GPU suite first (its particle section now exchanges the refill source planes over NCCL)
+    timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_zzz_gpu_experimental.py -m gpu -q > gpurun_out/${tag}_pytest_gpu_2gpu.log 2>&1
+    tail -3 gpurun_out/${tag}_pytest_gpu_2gpu.log
     # boundary stream: parity first, then its effect on thin and thick slabs, then the timelines
     MGPU_ONLY=bstream timeout 600 $TR --nproc-per-node 2 --master-port 29611 tests/mgpu_worker.py > gpurun_out/${tag}_mgpu_bstream_n2.log 2>&1
     tail -2 gpurun_out/${tag}_mgpu_bstream_n2.log
@@ -54,5 +57,7 @@ eight)
     done
     MGPU_ONLY=bstream timeout 400 $TR --nproc-per-node 8 --master-port 29615 tests/mgpu_worker.py > gpurun_out/${tag}_mgpu_bstream_n8.log 2>&1
     tail -2 gpurun_out/${tag}_mgpu_bstream_n8.log
+    # configs[4]: particle-laden channel on 8 GPUs (100 spheres per 512x256x256 slab, weak)
+    timeout 300 $TR --nproc-per-node 8 --master-port 29616 bench.py --gpus 8 --particles 800 --no-e2e --steps 100 > gpurun_out/${tag}_n8_particles.json 2> gpurun_out/${tag}_n8_particles.err
     ;;
 esac
