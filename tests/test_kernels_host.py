@@ -30,7 +30,7 @@ MACRO_MAIN, MACRO_PRERELAX, MACRO_EXTERNAL = 0, 1, 2
 def hk():
     out = os.path.join(HOST, "libkernels_host.so")
     deps = [os.path.join(HOST, "kernels_host.cpp"), os.path.join(HOST, "fake", "cuda_runtime.h")] + \
-           [os.path.join(CSRC, n) for n in ("kernels.cuh", "collide.cuh", "lattice.cuh")]
+           [os.path.join(CSRC, n) for n in ("kernels.cuh", "particles.cuh", "collide.cuh", "lattice.cuh")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                         "-I", os.path.join(HOST, "fake"), "-I", CSRC, "-o", out, os.path.join(HOST, "kernels_host.cpp")],
