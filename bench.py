@@ -42,7 +42,9 @@ BYTES_PER_NODE = 304.0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000,
+                    help="timed steps (default 1000 = 1.5 s on one B200: long enough for several clock samples, and the "
+                         "reference's own nsteps, para.f90:43, so that e2e sees the driver's output cadence)")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
