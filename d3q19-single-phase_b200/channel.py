@@ -386,11 +386,15 @@ class ChannelFlow:
         capi.check(self.L.d3q19_shim_set_schedule(self.h, v.ndiag, v.nflowout, v.nsteps, v.istep0))
 
     # ---- main.f90:142-208 -------------------------------------------------------------------
-    def run(self, nsteps=None, on_step=None):
+    def run(self, nsteps=None, on_step=None, time_bond=None):
+        """the time loop; `time_bond` (seconds) is the wall-clock budget of main.f90:197-206: every `ntime` steps the
+        loop is left when it is spent (the shim makes rho,u current on those steps for `probe`)"""
+        import time
         v = self.v
         nsteps = v.nsteps if nsteps is None else nsteps
         v.nsteps = nsteps
         self.set_schedule()
+        t0 = time.perf_counter()
         for self.istep in range(v.istep0 + 1, v.istep0 + nsteps + 1):
             self.collision_MRT()
             self.macrovar()
@@ -398,6 +402,8 @@ class ChannelFlow:
                 self.avedensity()
             if on_step:
                 on_step(self)
+            if time_bond is not None and self.istep % v.ntime == 0 and time.perf_counter() - t0 > time_bond:
+                break
         return self.istep
 
     # ---- particles (the reference's beads_* phases; device-side bookkeeping) -----------------------

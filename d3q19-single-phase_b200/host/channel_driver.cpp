@@ -264,6 +264,8 @@ int main(int argc, char **argv) {
     int scheme = D3Q19_SCHEME_AUTO, math = D3Q19_MATH_FAST, mrttype = 0;
     bool laminar = true, prerelax = false, dry = false;
     double A9 = 0.0, ustar_over = 0.0;
+    double time_lmt = 720.0, time_buff = 10.0;          // wall-clock limit and save buffer in minutes (para.f90:50-52)
+    int ntime = 10000;                                  // var_inc.f90:59
     std::string dump_path;
     for (int a = 1; a < argc; ++a) {
         const std::string s = argv[a];
@@ -283,6 +285,9 @@ int main(int argc, char **argv) {
         else if (s == "--mrttype") mrttype = std::atoi(next());
         else if (s == "--strict") math = D3Q19_MATH_STRICT;
         else if (s == "--scheme") { const std::string t = next(); scheme = t == "aa" ? D3Q19_SCHEME_AA : (t == "ab" ? D3Q19_SCHEME_AB : D3Q19_SCHEME_AUTO); }
+        else if (s == "--time-lmt") time_lmt = std::atof(next());
+        else if (s == "--time-buff") time_buff = std::atof(next());
+        else if (s == "--ntime") ntime = std::atoi(next());
         else if (s == "--dump") dump_path = next();
         else if (s == "--dry-run") dry = true;
         else { std::fprintf(stderr, "unknown option %s (see the header of channel_driver.cpp)\n", s.c_str()); return 1; }
@@ -296,7 +301,8 @@ int main(int argc, char **argv) {
     }
     if (mrttype) v.MRTtype = mrttype;
     para_mrt(v);
-    v.nsteps = nsteps; v.ndiag = ndiag; v.nflowout = nflowout;
+    v.nsteps = nsteps; v.ndiag = ndiag; v.nflowout = nflowout; v.ntime = ntime;
+    const double time_bond = (time_lmt - time_buff) * 60.0;        // para.f90:54
     allocarray(v);                                                  // main.f90:44
     std::printf("para nx %d ny %d nz %d visc %.17g ustar %.17g force_in_y %.17g ystar %.17g tau %.17g MRTtype %d\n", v.nx, v.ny,
                 v.nz, v.visc, v.ustar, v.force_in_y, v.ystar, v.tau, v.MRTtype);
@@ -337,17 +343,26 @@ int main(int argc, char **argv) {
     FORCING(v);                                                     // main.f90:132
     macrovar(v);                                                    // main.f90:136
     const auto t_loop0 = std::chrono::steady_clock::now();          // time_start = MPI_WTIME(), main.f90:137
+    int stopped_at = 0;
     for (v.istep = v.istep0 + 1; v.istep <= v.istep0 + v.nsteps; ++v.istep) {       // main.f90:142-208
         collision_MRT();                                            // :157
         macrovar(v);                                                // :161
         if (v.ndiag > 0 && v.istep % v.ndiag == 0) diag(v);         // :171
         if (v.nflowout > 0 && v.istep % v.nflowout == 0) outputuy(v);   // :184 -> saveload.f90:696,848
+        if (v.ntime > 0 && v.istep % v.ntime == 0) {                // :197-206: leave the loop when the wall-clock budget is spent
+            const double time_max = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop0).count();
+            if (time_max > time_bond) {                             // (the shim made rho,u current on this step for probe)
+                std::printf("time budget: %.1f s > %.1f s, leaving the loop after step %d\n", time_max, time_bond, v.istep);
+                stopped_at = v.istep;
+                break;
+            }
+        }
     }
-    v.istep = v.istep0 + v.nsteps;
+    v.istep = stopped_at ? stopped_at : v.istep0 + v.nsteps;
     check(d3q19_sync(H), "d3q19_sync");
     {
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop0).count();   // main.f90:214-218
-        std::printf("time loop %.3f s, %.1f MLUPS\n", dt, (double)v.nx * v.ny * v.nz * v.nsteps / dt / 1e6);
+        std::printf("time loop %.3f s, %.1f MLUPS\n", dt, (double)v.nx * v.ny * v.nz * (v.istep - v.istep0) / dt / 1e6);
     }
     probe(v);                                                       // main.f90:221
     if (!dump_path.empty()) {
