@@ -24,6 +24,13 @@ one)
         python bench.py --particles 100 --no-cpu --no-e2e --steps 3 --warmup 1 > /dev/null 2>&1
     timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/${tag}_launches.csv \
         python bench.py --no-cpu --no-e2e --steps 5 --warmup 3 > /dev/null 2>&1
+    # 4. sanitizers on the small case (SURVEY.md section 5 "race detection"): memcheck over smoke(), racecheck over the
+    #    particle tests (shared-memory scans and reductions)
+    timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" \
+        > gpurun_out/${tag}_memcheck_smoke.log 2>&1; echo "memcheck exit $?" >> gpurun_out/${tag}_memcheck_smoke.log
+    timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_particles.py -m gpu -q -k "mask_and_links" \
+        > gpurun_out/${tag}_racecheck_particles.log 2>&1; echo "racecheck exit $?" >> gpurun_out/${tag}_racecheck_particles.log
+    tail -2 gpurun_out/${tag}_memcheck_smoke.log gpurun_out/${tag}_racecheck_particles.log
     ;;
 two)
     # the established multi-GPU suite first (its particle section now exchanges the refill source planes over NCCL)
