@@ -201,6 +201,20 @@ def test_slabs_peer_memory_halo_bit_identical(oracle, hk, scheme, nranks, lz, tr
 
 
 @pytest.mark.parametrize("scheme", [AA, AB])
+@pytest.mark.parametrize("transport", [PACKED, FUSED, PUT])
+def test_slabs_fast_arithmetic_and_64bit_indices(oracle, hk, scheme, transport):
+    # production arithmetic is node-local too: FAST on 3 slabs == FAST on one domain, bit for bit; same for the
+    # 64-bit-index instantiations of every transport
+    shape = (40, 5, 9)
+    w, p, one = pair(oracle, hk, shape, perturb=1e-4, scheme=scheme, strict=False)
+    _, _, many = pair(oracle, hk, shape, perturb=1e-4, scheme=scheme, strict=False, nranks=3, transport=transport, idx64=True)
+    for n in (1, 2, 4):
+        one.steps(n); many.steps(n)
+        assert np.array_equal(one.download(), many.download()), n
+    one.close(); many.close()
+
+
+@pytest.mark.parametrize("scheme", [AA, AB])
 @pytest.mark.parametrize("nranks", [1, 2])
 def test_two_x_blocks_and_pitch_padding(oracle, hk, scheme, nranks):
     # lx = 130: two 128-thread blocks per row, pitch 144 -- 14 padding elements per row that no kernel may touch
@@ -213,12 +227,13 @@ def test_two_x_blocks_and_pitch_padding(oracle, hk, scheme, nranks):
 
 
 @pytest.mark.parametrize("scheme", [AA, AB])
-@pytest.mark.parametrize("nranks", [1, 3])
-def test_prerelax_and_external_macro_modes(oracle, hk, scheme, nranks):
-    # main.f90:70-90: rhoupdat; collision_MRT with frozen u -- the fused PRERELAX mode of the step kernel
+@pytest.mark.parametrize("nranks,transport", [(1, PACKED), (3, PACKED), (3, FUSED), (2, FUSED_SPLIT), (3, PUT)])
+def test_prerelax_and_external_macro_modes(oracle, hk, scheme, nranks, transport):
+    # main.f90:70-90: rhoupdat; collision_MRT with frozen u -- the fused PRERELAX mode of the step kernel; the run-time
+    # modes are the GENERIC instantiations, which also exist with the halo stores (pre-relaxation over peer memory)
     nx, ny, nz = 20, 4, 6
     w, p = oracle.make_initial_state(nx, ny, nz, laminar=False, noise=True)
-    sim = HostSim(hk, p, nranks=nranks, scheme=scheme)
+    sim = HostSim(hk, p, nranks=nranks, scheme=scheme, transport=transport)
     sim.upload(w.get_f())
     hk.hs_set_macro(sim.h, *[_d(np.ascontiguousarray(w.get(k))) for k in ("rho", "ux", "uy", "uz")])
     for it in range(5):
