@@ -1118,14 +1118,14 @@ extern "C" int d3q19_avedensity(d3q19_handle *h, double *rhomean, int64_t *nflui
     CK(cudaSetDevice(h->cfg.device));
     RK_(ensure_macro_arrays(h));
     const Geom &g = h->g;
-    const int nblk = 1024;
-    if (!h->red_d) {
-        CK(cudaMalloc(&h->red_d, nblk * sizeof(double)));
-        CK(cudaMalloc(&h->red_c, (nblk + 8) * sizeof(long long)));
-    }
     const long long nrows = (long long)g.ly * g.lz;
+    const int nblk = nrows < 1024 ? (int)nrows : 1024;             // a block per (y,z) row at most
+    if (!h->red_d) {
+        CK(cudaMalloc(&h->red_d, 1024 * sizeof(double)));
+        CK(cudaMalloc(&h->red_c, (1024 + 8) * sizeof(long long)));
+    }
     double *sum_dev = h->scal + 8;
-    long long *cnt_dev = h->red_c + nblk;
+    long long *cnt_dev = h->red_c + 1024;
     k_rho_partial<<<nblk, 256, 0, h->sc>>>(g.lx, g.xp, nrows, h->rho, h->solid, h->red_d, h->red_c);
     k_rho_final<<<1, 32, 0, h->sc>>>(nblk, h->red_d, h->red_c, sum_dev, cnt_dev);
     CK(cudaGetLastError());

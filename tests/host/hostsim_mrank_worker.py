@@ -1,0 +1,257 @@
+"""TEST INFRASTRUCTURE ONLY.  The multi-GPU parity worker (tests/mgpu_worker.py) for the host-sim build of the library
+(tests/host/make_hostsim.py): every rank is a THREAD of this process, NCCL is tests/host/fake/fake_nccl.h, peer memory
+is the process's own address space.  Run as a subprocess with D3Q19_LIB pointing at the host-sim library:
+
+    D3Q19_LIB=tests/host/_gen/libd3q19b200_hostsim.so python tests/host/hostsim_mrank_worker.py <world> [section ...]
+
+What it shows: the REAL orchestration of csrc/d3q19_api.cu (slab geometry, face exchange, send-back after odd steps,
+peer-memory connect + flag protocol, put transport, boundary stream, reductions, particle link partition, force
+all-reduce, refill source exchange) computes, on 2-4 slabs, bit for bit what the single-domain oracle computes.
+What it cannot show: ordering between CUDA streams (the fake device is synchronous; see test_halo_schedule_model.py).
+"""
+import os
+import sys
+import threading
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+from oracle import particles as P  # noqa: E402
+
+pkg = entry.load_package()
+capi = pkg.capi
+
+
+class Comm:
+    """what torch.distributed does for the real worker"""
+
+    def __init__(self, world):
+        self.world, self.bar, self.slots, self.lock = world, threading.Barrier(world), [None] * world, threading.Lock()
+        self.failed = []
+
+    def allgather(self, rank, item):
+        self.bar.wait()
+        self.slots[rank] = item
+        self.bar.wait()
+        out = list(self.slots)
+        self.bar.wait()
+        return out
+
+    def new_id(self, rank):
+        return self.allgather(rank, bytes(capi.nccl_unique_id()) if rank == 0 else None)[0]
+
+    def fail(self, rank, what):
+        with self.lock:
+            self.failed.append("rank %d: %s" % (rank, what))
+
+
+def section_fluid(rank, world, comm, chk, ctx):
+    # (size, overlap, transport)
+    cases = [((24, 6, 4 * world), True, "nccl"), ((33, 5, 3 * world + 1), True, "nccl"), ((16, 4, world), True, "nccl"),
+             ((24, 6, 4 * world), False, "nccl"), ((130, 3, 2 * world + 1), True, "nccl"),
+             ((24, 6, 4 * world), True, "peer"), ((33, 5, 3 * world + 1), True, "peer"), ((130, 3, 2 * world + 1), True, "peer"),
+             ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split"),
+             ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"),
+             ((24, 6, 4 * world), True, "bstream"), ((33, 5, 3 * world + 1), True, "bstream")]
+    if os.environ.get("HOSTSIM_SHORT"):          # the default CPU suite: one uneven case per transport
+        cases = [((33, 5, 3 * world + 1), True, h) for h in ("nccl", "peer", "peer-split", "put", "bstream")] + \
+                [((24, 6, 4 * world), False, "nccl")]
+    import time
+    for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
+        for (nx, ny, nz), overlap, halo in cases:
+            t_case = time.perf_counter()
+            ctx[0] = "scheme %d case %s overlap %s halo %s" % (scheme, (nx, ny, nz), overlap, halo)
+            w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+            w.set_f(w.get_f() + 1e-4 * np.random.default_rng(7).normal(size=(nz, ny, nx, 19)))
+            # environment knobs are read at create / connect: all ranks share one environment, so set them together
+            comm.bar.wait()
+            if rank == 0:
+                os.environ.pop("D3Q19_BOUNDARY_STREAM", None); os.environ.pop("D3Q19_HALO_SPLIT_MIN", None)
+                if halo == "bstream":
+                    os.environ["D3Q19_BOUNDARY_STREAM"] = "1"
+                if halo == "peer-split":
+                    os.environ["D3Q19_HALO_SPLIT_MIN"] = "3"
+            comm.bar.wait()
+            sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=scheme,
+                                  math_mode=capi.MATH_STRICT, nccl_id=comm.new_id(rank), overlap=overlap)
+            z0, z1 = sim.globalz, sim.globalz + sim.lz
+            sim.FORCING()
+            if halo.startswith("peer") or halo == "put":
+                ok_ = sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if halo == "put" else "fused")
+                chk("peer halo connects", ok_)
+            sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
+            w.macrovar()
+            out = np.empty((sim.lz, ny, nx, 19))
+            for burst in (1, 1, 2, 1, 3):
+                for _ in range(burst):
+                    w.collision_MRT(); w.macrovar()
+                sim.run_device(burst)
+                sim.download_f(out)
+                # (no early exit: the ranks must stay in lockstep for the collectives that follow)
+                chk("populations after a burst of %d" % burst, bool(np.array_equal(out, w.get_f()[z0:z1])))
+            sim.device_macrovar()
+            for k in ("rho", "ux", "uy", "uz"):
+                chk("macrovar " + k, bool(np.array_equal(getattr(sim, k), w.get(k)[z0:z1])))
+            if sim.lz >= 2 and ny >= 2:
+                for name, got, want in zip(("ox", "oy", "oz"), sim.vortcalc(), w.vortcalc()):
+                    chk("vortcalc " + name, bool(np.array_equal(got, want[z0:z1])))
+            pr = sim.profiles()
+            ref = w.get("uy").sum(axis=(0, 1))
+            chk("profiles", bool(np.allclose(pr[1], ref, rtol=1e-12, atol=1e-13 * np.max(np.abs(ref)))))
+            d, dref = sim.diag(), orc.diag_line(w, p.ustar)
+            chk("diag location", (d["imout"], d["jmout"], d["kmout"]) == (dref["imout"], dref["jmout"], dref["kmout"]))
+            chk("diag vmax", d["vmax"] == dref["vmax"] and d["nfluid"] == dref["nfluid"])
+            # avedensity across ranks (MPI_ALLREDUCE, collision.f90:500-501), then the shifted collision
+            import ctypes as C
+            mean_ref, n_ref = w.avedensity()
+            m, n = C.c_double(0), C.c_int64(0)
+            capi.check(sim.L.d3q19_avedensity(sim.h, C.byref(m), C.byref(n)))
+            chk("avedensity count", n.value == n_ref)
+            chk("avedensity mean", abs(m.value - mean_ref) <= 1e-12 * float(np.mean(np.abs(w.get("rho")))) + 1e-300)
+            w.collision_MRT()
+            sim.collide_stream()
+            sim.download_f(out)
+            err = np.max(np.abs(out - w.get_f()[z0:z1])) / np.max(np.abs(w.get_f()))
+            chk("step after avedensity err %g" % err, bool(err < 1e-13))
+            sim.close(); w.close()
+            if rank == 0 and os.environ.get("HOSTSIM_VERBOSE"):
+                print("%-60s %.2f s" % (ctx[0], time.perf_counter() - t_case), flush=True)
+    comm.bar.wait()
+    if rank == 0:
+        os.environ.pop("D3Q19_BOUNDARY_STREAM", None); os.environ.pop("D3Q19_HALO_SPLIT_MIN", None)
+    comm.bar.wait()
+
+
+def section_prerelax(rank, world, comm, chk, ctx):
+    ctx[0] = "device prerelax"
+    nx, ny, nz = 32, 8, 4 * world
+    tol = 2e-5
+
+    def start():
+        w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+        w.set_f(w.get_f() + 1e-4 * np.random.default_rng(5).normal(size=(nz, ny, nx, 19)))
+        return w, p
+    w, p = start()
+    it_ref = 0
+    while True:
+        rhop = w.get("rho").copy()
+        w.rhoupdat(); w.collision_MRT()
+        err_ref = np.max(np.abs(w.get("rho") - rhop))
+        if err_ref <= tol or it_ref > 12:
+            break
+        it_ref += 1
+    w0, _ = start()
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, math_mode=capi.MATH_STRICT,
+                          nccl_id=comm.new_id(rank), rhoepsl=tol)
+    z0, z1 = sim.globalz, sim.globalz + sim.lz
+    sim.f[...] = w0.get_f()[z0:z1]
+    for k in ("rho", "ux", "uy", "uz"):
+        getattr(sim, k)[...] = w0.get(k)[z0:z1]
+    sim.FORCING()
+    it, err = sim.prerelax_device(maxiter=12)
+    chk("iterations %d vs %d" % (it, it_ref), it == it_ref)
+    chk("rhoerr %r vs %r" % (err, err_ref), err == err_ref)
+    chk("f after prerelax", bool(np.array_equal(sim.f, w.get_f()[z0:z1])))
+    sim.close()
+
+
+def section_particles(rank, world, comm, chk, ctx):
+    nx, ny, nz, rad = 24, 20, 8 * world, 3.6
+    U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+    pos = [[11.7, 1.2, 8.0 * world - 0.9], [8.3, 12.0, 8.1], [15.5, 8.4, 4.2]]      # two of them cut by slab faces
+    vel = [[0.010, 0.020, -0.010], [0.0, 0.015, 0.0], [-0.005, 0.0, 0.012]]
+    omg = [[1e-3, 0.0, 2e-3], [0.0, -1e-3, 0.0], [5e-4, 5e-4, 0.0]]
+    for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
+        ctx[0] = "particles scheme %d" % scheme
+        w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True, ipart=1, **U)
+        pt = P.Particles(nx, ny, nz, rad, pos, vel, omg)
+        pt.build_mask(); pt.build_links()
+        w.set_solid(np.where(pt.own > 0, 1, -1).astype(np.int32), pt.own)
+        w.set_particles(pt.ypglb, pt.wp, pt.omgp)
+        sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=scheme,
+                              nccl_id=comm.new_id(rank), ipart=True, **U)
+        z0, z1 = sim.globalz, sim.globalz + sim.lz
+        sim.FORCING()
+        sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
+        sim.particles_init(pos, rad, vel, omg)
+        nl = sim.beads_links()
+        tot = sum(comm.allgather(rank, nl))
+        chk("link count %d vs %d" % (tot, len(pt.links["q"])), tot == len(pt.links["q"]))
+        chk("mask", bool(np.array_equal(sim.get_mask(), pt.own[z0:z1])))
+        gl = sim.get_links()
+        mine = (pt.links["z"] > z0) & (pt.links["z"] <= z1)
+        for key in ("x", "y", "z", "ip", "part", "q"):
+            chk("links " + key, bool(np.array_equal(gl[key], pt.links[key][mine])))
+        w.macrovar()
+        out = np.empty((sim.lz, ny, nx, 19))
+        for step in range(3):
+            w.collision_MRT()
+            f = w.get_f(); pt.ibb(f); w.set_f(f); w.macrovar()
+            sim.particle_step(move=False)
+            sim.download_f(out)
+            fluid = pt.own[z0:z1] < 0
+            err = np.max(np.abs(out[fluid] - f[z0:z1][fluid])) / np.max(np.abs(f))
+            chk("ibb step %d err %g" % (step, err), bool(err < 1e-12))
+            g = sim.get_particles()
+            ferr = np.max(np.abs(g["fHIp"] - pt.fHIp)) / np.max(np.abs(pt.fHIp))
+            chk("force step %d err %g" % (step, ferr), bool(ferr < 1e-10))
+        for step in range(8):                          # moving, with the refill sources exchanged across the faces
+            w.collision_MRT()
+            f = w.get_f(); pt.ibb(f); pt.lubforce(); pt.move(); pt.build_mask(); pt.build_links(); pt.refill(f)
+            w.set_f(f); w.set_solid(np.where(pt.own > 0, 1, -1).astype(np.int32), pt.own)
+            w.set_particles(pt.ypglb, pt.wp, pt.omgp); w.macrovar()
+            sim.particle_step(move=True)
+            g = sim.get_particles()
+            chk("moving positions %d" % step, bool(np.max(np.abs(g["ypglb"] - pt.ypglb)) < 1e-9))
+            chk("moving mask %d" % step, bool(np.array_equal(sim.get_mask(), pt.own[z0:z1])))
+            ferr = np.max(np.abs(g["fHIp"] - pt.fHIp)) / np.max(np.abs(pt.fHIp))
+            chk("moving force %d err %g" % (step, ferr), bool(ferr < 1e-9))
+            sim.download_f(out)
+            fluid = pt.own[z0:z1] < 0
+            err = np.max(np.abs(out[fluid] - f[z0:z1][fluid])) / np.max(np.abs(f))
+            chk("moving populations %d err %g" % (step, err), bool(err < 1e-9))
+        sim.close(); w.close()
+
+
+SECTIONS = {"fluid": section_fluid, "prerelax": section_prerelax, "particles": section_particles}
+
+
+def rank_main(rank, world, comm, sections):
+    ctx = [""]
+
+    def chk(name, cond):
+        if not cond:
+            comm.fail(rank, "CHECK FAILED %s [%s]" % (name, ctx[0]))
+        return cond
+    try:
+        for s in sections:
+            SECTIONS[s](rank, world, comm, chk, ctx)
+    except Exception:
+        comm.fail(rank, "EXCEPTION [%s]\n%s" % (ctx[0], traceback.format_exc()))
+        comm.bar.abort()
+
+
+def main():
+    world = int(sys.argv[1])
+    sections = sys.argv[2:] or list(SECTIONS)
+    if "hostsim" not in os.path.basename(capi.LIB_PATH):
+        print("this worker drives the host-sim build only (set D3Q19_LIB)")
+        return 2
+    comm = Comm(world)
+    threads = [threading.Thread(target=rank_main, args=(r, world, comm, sections)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for line in comm.failed[:20]:
+        print(line)
+    print("HOSTSIM_MRANK_OK" if not comm.failed else "HOSTSIM_MRANK_FAILED")
+    return 0 if not comm.failed else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

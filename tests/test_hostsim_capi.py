@@ -1,0 +1,53 @@
+"""The C-ABI library ITSELF on the GPU-less build box: tests/host/make_hostsim.py compiles csrc/d3q19_api.cu and the
+kernels with g++ against a synchronous stand-in for the CUDA runtime (tests/host/fake/, every kernel launch rewritten
+into a loop nest / fibers, NCCL = mailboxes between threads) and the GPU test files are run against it in
+subprocesses, unchanged, through the same ctypes binding and the same C++ driver:
+
+* single rank: tests/test_gpu_parity.py, test_golden.py, test_gpu_particles.py, test_zz_cpp_driver.py -- handle life
+  cycle, transfers in every storage phase, the shim state machine and its download policy, pre-relaxation, reductions;
+* 2 and 3 ranks (threads): tests/host/hostsim_mrank_worker.py -- slab geometry, the face exchange and the send-back
+  after odd in-place steps, peer-memory connect and flag protocol (fused, split, put), the opt-in boundary stream,
+  all-reduced scalars, the particle link partition, force all-reduce and the refill source exchange; all bit for
+  bit against the single-domain oracle.
+
+What this cannot show is anything about time or about ordering between CUDA streams (tests/test_halo_schedule_model.py
+covers the latter).  TEST INFRASTRUCTURE: the package never builds, finds or loads the host-sim library; the GPU box
+runs the same files against libd3q19b200.so.
+"""
+import importlib.util
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    spec = importlib.util.spec_from_file_location("make_hostsim", os.path.join(ROOT, "tests", "host", "make_hostsim.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return {"lib": m.build(), "driver": m.build_driver()}
+
+
+def run(cmd, hostsim, timeout=900, **extra):
+    env = dict(os.environ, D3Q19_LIB=hostsim["lib"], D3Q19_DRIVER=hostsim["driver"], **extra)
+    return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, env=env, cwd=ROOT)
+
+
+def test_single_rank_gpu_test_files_pass_on_the_host_sim(hostsim):
+    # left out: the 1000-step cases (minutes on a CPU) and the moving-particle case (tests/test_kernels_host.py has it)
+    res = run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_golden.py", "tests/test_gpu_particles.py",
+               "tests/test_zz_cpp_driver.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+               "-k", "not 1000_steps and not moving_particles"], hostsim)
+    tail = res.stdout[-3000:]
+    assert res.returncode == 0, tail
+    assert " passed" in tail and "failed" not in tail and "error" not in tail.lower(), tail
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_rank_orchestration_on_the_host_sim(hostsim, world):
+    res = run([sys.executable, os.path.join("tests", "host", "hostsim_mrank_worker.py"), str(world)], hostsim)
+    assert res.returncode == 0 and "HOSTSIM_MRANK_OK" in res.stdout, res.stdout[-4000:]

@@ -22,6 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def driver():
+    if os.environ.get("D3Q19_DRIVER"):          # tests/test_hostsim_capi.py: the same driver linked against the host-sim build
+        return os.environ["D3Q19_DRIVER"]
     bm = entry._load_build_module()
     return bm.build_driver()
 
