@@ -217,7 +217,70 @@ def section_particles(rank, world, comm, chk, ctx):
         sim.close(); w.close()
 
 
-SECTIONS = {"fluid": section_fluid, "prerelax": section_prerelax, "particles": section_particles}
+def section_shim(rank, world, comm, chk, ctx):
+    """main.f90's own call sequence on every rank, through the entry points the Fortran shim binds: pre-relaxation by
+    rhoupdat / collision_MRT (the library predicts the loop exit from the all-reduced max|rho - rhop|, and makes the
+    host f current in that iteration for saveinitflow), then the time loop with the diag / output cadence -- the host
+    arrays must be current exactly when the driver reads them, on every rank."""
+    nx, ny, nz, tol, itmax, nsteps = 23, 6, 3 * world + 1, 2e-5, 15000, 12          # main.f90:85 bounds the loop at 15000
+    for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
+        ctx[0] = "shim scheme %d" % scheme
+
+        def start():
+            w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+            w.set_f(w.get_f() + 1e-4 * np.random.default_rng(5).normal(size=(nz, ny, nx, 19)))
+            return w, p
+        w, p = start()
+        sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=scheme,
+                              math_mode=capi.MATH_STRICT, nccl_id=comm.new_id(rank), rhoepsl=tol, ndiag=5, nflowout=4)
+        z0, z1 = sim.globalz, sim.globalz + sim.lz
+        sim.f[...] = w.get_f()[z0:z1]
+        for k in ("rho", "ux", "uy", "uz"):
+            getattr(sim, k)[...] = w.get(k)[z0:z1]
+        sim.host_f_changed()
+        sim.FORCING()
+        # main.f90:70-90 on the oracle
+        it_ref = 0
+        while True:
+            rhop = w.get("rho").copy()
+            w.rhoupdat(); w.collision_MRT()
+            err_ref = float(np.max(np.abs(w.get("rho") - rhop)))
+            if err_ref <= tol or it_ref > itmax:
+                break
+            it_ref += 1
+        it, err = sim.prerelax(allreduce_max=lambda x: max(comm.allgather(rank, x)), maxiter=itmax)
+        chk("prerelax iterations %d vs %d" % (it, it_ref), it == it_ref)
+        chk("prerelax error %r vs %r" % (err, err_ref), err == err_ref)
+        chk("host f current for saveinitflow", bool(np.array_equal(sim.f, w.get_f()[z0:z1])))
+        chk("host rho current", bool(np.array_equal(sim.rho, w.get("rho")[z0:z1])))
+        # main.f90:102-136, then the loop :142-208
+        w.macrovar()
+        sim.macrovar()
+        sim.istep = 0
+        sim.FORCING()
+        sim.macrovar()
+        for k in ("rho", "ux", "uy", "uz"):
+            chk("initial macrovar " + k, bool(np.array_equal(getattr(sim, k), w.get(k)[z0:z1])))
+        seen = []
+
+        def on_step(s_):
+            if s_.istep % s_.v.ndiag == 0 or s_.istep % s_.v.nflowout == 0 or s_.istep == nsteps:
+                seen.append((s_.istep, [getattr(s_, k).copy() for k in ("rho", "ux", "uy", "uz")]))
+        ref = {}
+        sim.v.istep0 = 0
+        for step in range(1, nsteps + 1):
+            w.collision_MRT(); w.macrovar()
+            if step % 5 == 0 or step % 4 == 0 or step == nsteps:
+                ref[step] = [w.get(k)[z0:z1].copy() for k in ("rho", "ux", "uy", "uz")]
+        sim.run(nsteps, on_step=on_step)
+        chk("output steps %r" % [t for t, _ in seen], [t for t, _ in seen] == sorted(ref))
+        for t, arrs in seen:
+            chk("host rho,u current on step %d" % t, all(bool(np.array_equal(a, b)) for a, b in zip(arrs, ref[t])))
+        chk("f after the loop", bool(np.array_equal(sim.sync_f_to_host(), w.get_f()[z0:z1])))
+        sim.close(); w.close()
+
+
+SECTIONS = {"fluid": section_fluid, "prerelax": section_prerelax, "particles": section_particles, "shim": section_shim}
 
 
 def rank_main(rank, world, comm, sections):
