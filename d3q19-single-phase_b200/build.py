@@ -58,7 +58,7 @@ def build_driver(force=False):
             os.path.getmtime(DRIVER_SRC), os.path.getmtime(hdr), os.path.getmtime(lib)):
         return DRIVER
     cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-I", os.path.join(HERE, "..", "include"),
-           "-o", DRIVER, DRIVER_SRC, "-L", HERE, "-ld3q19b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/.."]
+           "-o", DRIVER, DRIVER_SRC, "-L", HERE, "-ld3q19b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/..", "-pthread"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + res.stdout)

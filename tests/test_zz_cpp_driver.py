@@ -62,6 +62,68 @@ def test_dry_run_matches_oracle_para_initvel_initpop(driver, tmp_path, shape, la
     w.close()
 
 
+@pytest.mark.parametrize("shape,ranks", [((23, 10, 8), 2), ((39, 4, 9), 3), ((16, 3, 7), 3)])
+def test_dry_run_ranks_cut_the_channel_like_para(driver, tmp_path, shape, ranks):
+    # --ranks N: z-slabs as para.f90:240-262 cuts them (nprocY = 1); the dump is the whole channel again.  The
+    # reference's initvel offsets its perturbation by indz*lz (initial.f90:120), exact for even slabs -- the oracle
+    # restates that too, so uneven slabs agree with it as well
+    nx, ny, nz = shape
+    out = str(tmp_path / "dry.bin")
+    run(driver, "--dry-run", "--ranks", ranks, "--nx", nx, "--ny", ny, "--nz", nz, "--A9", 0.3, "--turbulent", "--dump", out)
+    w, p = orc.make_initial_state(nx, ny, nz, laminar=False, A9=0.3, noise=False, nprocZ=ranks)
+    istep, f, fld = read_dump(out)
+    for k in ("ux", "uy", "uz", "rho"):
+        assert np.array_equal(fld[k], w.get(k)), k
+    assert np.array_equal(f, w.get_f())
+    w.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [2, 3])
+@pytest.mark.parametrize("scheme", ["aa", "ab"])
+def test_driver_ranks_as_threads(driver, tmp_path, scheme, ranks):
+    # the N ranks of the reference's job as N threads, one GPU each; pre-relaxation with the all-reduced error, time
+    # loop with the diag cadence reduced over ranks, probe of every rank's centre node
+    if not os.environ.get("D3Q19_DRIVER") and entry.load_package().capi.device_count() < ranks:
+        pytest.skip("needs %d GPUs" % ranks)
+    nx, ny, nz, nsteps, itmax = 23, 6, 4 * ranks, 12, 15000
+    out = str(tmp_path / "mr.bin")
+    U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+    text = run(driver, "--ranks", ranks, "--nx", nx, "--ny", ny, "--nz", nz, "--turbulent", "--A9", 0.3, "--ustar", 0.0025,
+               "--prerelax", "--nsteps", nsteps, "--ndiag", 5, "--nflowout", 4, "--strict", "--scheme", scheme, "--dump", out)
+    w, p = orc.make_initial_state(nx, ny, nz, laminar=False, A9=0.3, noise=False, nprocZ=ranks, **U)
+    errs, it = [], 0
+    while True:
+        rhop = w.get("rho").copy()
+        w.rhoupdat(); w.collision_MRT()
+        errs.append(float(np.max(np.abs(w.get("rho") - rhop))))
+        if errs[-1] <= 1e-5 or it > itmax:
+            break
+        it += 1
+    got = [float(m.group(2)) for m in re.finditer(r"^prerelax (\d+) (\S+)$", text, re.M)]
+    assert got == errs
+    w.macrovar()
+    diag_ref = {}
+    for step in range(1, nsteps + 1):
+        w.collision_MRT(); w.macrovar()
+        if step % 5 == 0:
+            diag_ref[step] = orc.diag_line(w, p.ustar)
+    istep, f, fld = read_dump(out)
+    assert istep == nsteps and np.array_equal(f, w.get_f())
+    for k in ("rho", "ux", "uy", "uz"):
+        assert np.array_equal(fld[k], w.get(k)), k
+    lines = {int(m.group(1)): m.group(2).split() for m in re.finditer(r"^diag (\d+) (.*)$", text, re.M)}
+    assert sorted(lines) == [5, 10]
+    for step, cols in lines.items():
+        assert float(cols[0]) == diag_ref[step]["vmax"]
+        assert [int(c) for c in cols[1:4]] == [diag_ref[step][k] for k in ("imout", "jmout", "kmout")]
+        assert float(cols[11]) == diag_ref[step]["rhomax"] and float(cols[12]) == diag_ref[step]["rhomin"]
+        assert abs(float(cols[5]) - diag_ref[step]["vmean"]) <= 1e-12 * abs(diag_ref[step]["vmean"])
+    probes = re.findall(r"^probe(?:_rank \d+)? ", text, re.M)
+    assert len(probes) == ranks and len(re.findall(r"^uy_profile ", text, re.M)) == 3
+    w.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("scheme", ["aa", "ab"])
 def test_driver_main_loop_laminar_config1(driver, tmp_path, scheme):

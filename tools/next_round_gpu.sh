@@ -50,6 +50,12 @@ two)
         name=${tag}_n2_thin${bs:+_bstream}
         timeout 300 $TR --nproc-per-node 2 --master-port 29613 bench.py --gpus 2 --scaling strong --workload 512x256x64 --no-e2e $bs > gpurun_out/$name.json 2> gpurun_out/$name.err
     done
+    # the C++ driver with the ranks of the reference's job as threads (tests + one timed run)
+    timeout 600 python -m pytest tests/test_zz_cpp_driver.py -m gpu -q > gpurun_out/${tag}_pytest_cpp_driver_2gpu.log 2>&1
+    tail -2 gpurun_out/${tag}_pytest_cpp_driver_2gpu.log
+    timeout 300 d3q19-single-phase_b200/host/channel_driver --ranks 2 --nx 512 --ny 256 --nz 512 --turbulent --nsteps 1000 \
+        > gpurun_out/${tag}_cpp_driver_n2.log 2>&1
+    grep "time loop" gpurun_out/${tag}_cpp_driver_n2.log
     grep -h '"value"' gpurun_out/${tag}_n2_*.json | python -c "
 import json, sys
 for l in sys.stdin:
