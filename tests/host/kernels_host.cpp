@@ -649,10 +649,11 @@ void hs_forcingp(void *h, int ihh, int ixs0, double force_in_y, double Amp0, dou
 // d3q19_avedensity: two-stage fixed-order sum per slab, all-reduce in rank order, shift of every node (collision.f90:497-511)
 double hs_avedensity(void *h, long long *nfluid) {
     Sim &s = *(Sim *)h;
-    const int nblk = 1024;
     double sum = 0.0;
     long long cnt = 0;
     for (Rank &q : s.r) {
+        const long long nrows_ = (long long)q.g.ly * q.g.lz;
+        const int nblk = nrows_ < 1024 ? (int)nrows_ : 1024;          // d3q19_avedensity: a block per (y,z) row at most
         std::vector<double> pd(nblk, 0.0);
         std::vector<long long> pc(nblk + 8, 0);
         double s1 = 0.0;

@@ -554,9 +554,7 @@ def test_particle_mask_and_links_bit_exact(oracle, hk, scheme, nranks):
     sim.close()
 
 
-@pytest.mark.parametrize("scheme", [AA, AB])
-@pytest.mark.parametrize("strict", [True, False])
-@pytest.mark.parametrize("nranks", [1, 2])
+@pytest.mark.parametrize("scheme,strict,nranks", [(AA, True, 1), (AB, False, 1), (AA, False, 2), (AB, True, 2)])
 def test_particle_ibb_and_force(oracle, hk, scheme, strict, nranks):
     w, p, sim, pt = _particle_pair(oracle, hk, scheme, strict, nranks)
     pt.build_mask(); pt.build_links()
@@ -577,8 +575,7 @@ def test_particle_ibb_and_force(oracle, hk, scheme, strict, nranks):
     sim.close()
 
 
-@pytest.mark.parametrize("scheme", [AA, AB])
-@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("scheme,nranks", [(AA, 1), (AB, 1), (AA, 3), (AB, 2)])
 def test_moving_particles_with_refill(oracle, hk, scheme, nranks):
     # z-slabs: a refill next to a face takes its source nodes from the neighbour slab (k_plane_gather + exchange),
     # so the result is that of the single domain
