@@ -54,3 +54,9 @@ def test_multi_rank_orchestration_on_the_host_sim(hostsim, world):
     extra = {"HOSTSIM_SHORT": "1"} if world == 2 else {}
     res = run([sys.executable, os.path.join("tests", "host", "hostsim_mrank_worker.py"), str(world)], hostsim, **extra)
     assert res.returncode == 0 and "HOSTSIM_MRANK_OK" in res.stdout, res.stdout[-4000:]
+
+
+def test_smoke_entry_point_on_the_host_sim(hostsim):
+    # __graft_entry__.smoke() is what the driver runs on the B200 before the bench: its own logic must not be what fails
+    res = run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], hostsim)
+    assert res.returncode == 0 and "smoke ok" in res.stdout, res.stdout[-3000:]
