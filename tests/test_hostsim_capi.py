@@ -60,3 +60,30 @@ def test_smoke_entry_point_on_the_host_sim(hostsim):
     # __graft_entry__.smoke() is what the driver runs on the B200 before the bench: its own logic must not be what fails
     res = run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], hostsim)
     assert res.returncode == 0 and "smoke ok" in res.stdout, res.stdout[-3000:]
+
+
+@pytest.mark.parametrize("extra", [[], ["--scheme", "aa", "--device-init"], ["--workload", "40x24x24", "--particles", "2", "--rad", "4"]])
+def test_bench_product_arm_prints_its_contract_line(hostsim, extra):
+    # bench.py's own logic (the one JSON line the driver reads) against the host-sim; numbers are meaningless here
+    import json
+    args = ["--workload", "32x8x8", "--steps", "6", "--warmup", "3", "--cpu-steps", "1"] + extra
+    res = run([sys.executable, os.path.join("tests", "host", "bench_on_hostsim.py")] + args, hostsim)
+    assert res.returncode == 0, res.stdout[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, res.stdout[-2000:]
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "impl"):
+        assert k in d, k
+    assert d["impl"] == "ours" and d["metric"] == "MLUPS (fp64)" and d["dtype"] == "f64" and d["n_gpus"] == 1
+    assert d["steps"] == 6 and d["warmup"] == 3 and d["value"] > 0 and d["gpu_launches"] >= 6
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["bytes_per_node"] == 304.0
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and "peak_source" in r
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    if "--particles" in extra or "--device-init" in extra:
+        assert d["e2e"] is None                      # those runs have no host-buffer leg
+    else:
+        e = d["e2e"]
+        assert e["value"] > 0 and e["h2d_bytes_per_step"] == 19 * 8 * 32 * 8 * 8 / 6 and e["d2h_bytes_per_step"] > 32
+    assert d["config"]["workload"].startswith("D3Q19 MRT channel")
