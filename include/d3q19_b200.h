@@ -182,7 +182,9 @@ int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local);
 int d3q19_beads_collision(d3q19_handle *h);
 int d3q19_beads_lubforce(d3q19_handle *h);
 int d3q19_beads_move(d3q19_handle *h);
-/* refill of the nodes uncovered by the last move (after d3q19_beads_links rebuilt the mask)  */
+/* refill of the nodes uncovered by the last move (after d3q19_beads_links rebuilt the mask).  With nranks > 1 the call
+   is COLLECTIVE: every rank sends the 19 canonical populations of its two boundary planes to its neighbours first, so
+   that a refill next to a slab face uses the same source nodes as on a single domain                              */
 int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled_local);
 /* links (if stale); collide_stream; beads_collision; [lubforce; move; links; filling]         */
 int d3q19_particle_step(d3q19_handle *h, int32_t move);
