@@ -61,6 +61,10 @@ def parse_args():
     ap.add_argument("--boundary-stream", action="store_true",
                     help="NCCL transport, opt-in: launch the two boundary planes of a step on their own high-priority stream next "
                          "to the interior launch instead of in front of it (D3Q19_BOUNDARY_STREAM=1)")
+    ap.add_argument("--direct-faces", action="store_true",
+                    help="NCCL transport, opt-in: send the five crossing populations of a face straight out of the population "
+                         "array and receive them in place (20 sends/receives in one group, no pack / unpack kernels; "
+                         "D3Q19_DIRECT_FACES=1)")
     ap.add_argument("--cpu-steps", type=int, default=20,
                     help="timed steps of the CPU arm (20 steps of 512x256x256 = about 10 s on 16 cores)")
     ap.add_argument("--particles", type=int, default=0,
@@ -278,6 +282,8 @@ def main():
 
     if args.boundary_stream and world > 1 and args.particles == 0:
         os.environ["D3Q19_BOUNDARY_STREAM"] = "1"
+    if args.direct_faces and world > 1:
+        os.environ["D3Q19_DIRECT_FACES"] = "1"
 
     def build_sim(halo_req, nccl_id):
         """the channel on this rank's slab with its synthetic initial state; returns (sim, halo actually in use)"""
@@ -432,7 +438,8 @@ def main():
                            "peer": "stored into the neighbour GPU's memory over NVLink inside the step kernel",
                            "put": "stored into the neighbour GPU's memory over NVLink by a copy kernel on a second stream",
                            "nccl": "by NCCL send/recv" + (", boundary planes on their own stream" if os.environ.get(
-                               "D3Q19_BOUNDARY_STREAM") == "1" else "")}[halo])) if world > 1 else "1 GPU",
+                               "D3Q19_BOUNDARY_STREAM") == "1" else "") + (", faces sent in place (no pack/unpack)" if os.environ.get(
+                               "D3Q19_DIRECT_FACES") == "1" else "")}[halo])) if world > 1 else "1 GPU",
                        "l2": "populations %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (c1["population_bytes"] / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "impl": "ours",

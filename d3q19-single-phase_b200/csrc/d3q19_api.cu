@@ -92,6 +92,9 @@ struct d3q19_handle {
     cudaEvent_t evI = nullptr;
     bool bstream = false;
     bool b_pending = false;       // the last boundary launch (event evB on sb) has not been waited for by sc yet
+    // opt-in (D3Q19_DIRECT_FACES=1): faces travel straight out of / into the population array (a population's plane is
+    // contiguous), 10 sends + 10 receives in one NCCL group, no pack / unpack kernels (exchange_faces)
+    bool direct_faces = false;
     // optional per-step timeline (d3q19_trace_enable): 4 timing events per step -- [0] before the boundary launch,
     // [1] after it, [2] after the interior launch (all on sc), [3] after the exchange / put (on sx)
     cudaEvent_t *trace_ev = nullptr;
@@ -209,6 +212,25 @@ static int exchange_faces(d3q19_handle *h, double *arr, int up_src, const FaceSl
     const size_t cnt = (size_t)5 * g.plane;
     const int up = (h->cfg.rank + 1) % h->cfg.nranks;                       // mzp, para.f90:266
     const int dn = (h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks;       // mzm, para.f90:267
+    if (h->direct_faces && !exclude_walls) {
+        // One population of one z plane is plane = xp*ly contiguous doubles, so each of the five
+        // crossing populations can be sent from where it lies and received where it belongs.  Not after an in-place odd
+        // step: its send-back must leave the wall-adjacent nodes alone (exclude_walls), which needs the unpack kernel.
+        NcclApi &n = nccl_api();
+        const size_t pl = (size_t)g.plane;
+        NK(n.GroupStart());
+        for (int q = 0; q < 5; ++q) {            // same order towards either neighbour as the packed exchange: up, dn
+            NK(n.Send(arr + (size_t)up_slots.s[q] * g.slab + (size_t)up_src * pl, pl, NCCL_FLOAT64, up, h->comm, s));
+            NK(n.Send(arr + (size_t)dn_slots.s[q] * g.slab + (size_t)dn_src * pl, pl, NCCL_FLOAT64, dn, h->comm, s));
+        }
+        for (int q = 0; q < 5; ++q) {
+            NK(n.Recv(arr + (size_t)up_slots.s[q] * g.slab + (size_t)lo_dst * pl, pl, NCCL_FLOAT64, dn, h->comm, s));
+            NK(n.Recv(arr + (size_t)dn_slots.s[q] * g.slab + (size_t)hi_dst * pl, pl, NCCL_FLOAT64, up, h->comm, s));
+        }
+        NK(n.GroupEnd());
+        h->n_nccl += 20;
+        return 0;
+    }
     const dim3 gp((unsigned)((g.xp + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 10u);
     FacePair pk;
     pk.buf[0] = h->send_up; pk.zg[0] = up_src; pk.slots[0] = up_slots;
@@ -370,6 +392,10 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
     if (cfg->nranks > 1 && !cfg->ipart) {
         const char *t = getenv("D3Q19_BOUNDARY_STREAM");
         h->bstream = t && atoi(t) > 0;
+    }
+    if (cfg->nranks > 1) {
+        const char *t = getenv("D3Q19_DIRECT_FACES");
+        h->direct_faces = t && atoi(t) > 0;
     }
     if (h->bstream) {
         CKH(cudaStreamCreateWithPriority(&h->sb, cudaStreamNonBlocking, hi));

@@ -56,9 +56,10 @@ def section_fluid(rank, world, comm, chk, ctx):
              ((24, 6, 4 * world), True, "peer"), ((33, 5, 3 * world + 1), True, "peer"), ((130, 3, 2 * world + 1), True, "peer"),
              ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split"),
              ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"),
-             ((24, 6, 4 * world), True, "bstream"), ((33, 5, 3 * world + 1), True, "bstream")]
+             ((24, 6, 4 * world), True, "bstream"), ((33, 5, 3 * world + 1), True, "bstream"),
+             ((24, 6, 4 * world), True, "direct"), ((33, 5, 3 * world + 1), True, "direct"), ((130, 3, 2 * world + 1), True, "direct")]
     if os.environ.get("HOSTSIM_SHORT"):          # the default CPU suite: one uneven case per transport
-        cases = [((33, 5, 3 * world + 1), True, h) for h in ("nccl", "peer", "peer-split", "put", "bstream")] + \
+        cases = [((33, 5, 3 * world + 1), True, h) for h in ("nccl", "peer", "peer-split", "put", "bstream", "direct")] + \
                 [((24, 6, 4 * world), False, "nccl")]
     import time
     for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
@@ -70,9 +71,12 @@ def section_fluid(rank, world, comm, chk, ctx):
             # environment knobs are read at create / connect: all ranks share one environment, so set them together
             comm.bar.wait()
             if rank == 0:
-                os.environ.pop("D3Q19_BOUNDARY_STREAM", None); os.environ.pop("D3Q19_HALO_SPLIT_MIN", None)
+                for k in ("D3Q19_BOUNDARY_STREAM", "D3Q19_HALO_SPLIT_MIN", "D3Q19_DIRECT_FACES"):
+                    os.environ.pop(k, None)
                 if halo == "bstream":
                     os.environ["D3Q19_BOUNDARY_STREAM"] = "1"
+                if halo == "direct":                          # faces sent straight out of the population array
+                    os.environ["D3Q19_DIRECT_FACES"] = "1"
                 if halo == "peer-split":
                     os.environ["D3Q19_HALO_SPLIT_MIN"] = "3"
             comm.bar.wait()
@@ -122,7 +126,8 @@ def section_fluid(rank, world, comm, chk, ctx):
                 print("%-60s %.2f s" % (ctx[0], time.perf_counter() - t_case), flush=True)
     comm.bar.wait()
     if rank == 0:
-        os.environ.pop("D3Q19_BOUNDARY_STREAM", None); os.environ.pop("D3Q19_HALO_SPLIT_MIN", None)
+        for k in ("D3Q19_BOUNDARY_STREAM", "D3Q19_HALO_SPLIT_MIN", "D3Q19_DIRECT_FACES"):
+            os.environ.pop(k, None)
     comm.bar.wait()
 
 

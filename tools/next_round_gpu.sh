@@ -40,14 +40,14 @@ two)
     MGPU_ONLY=bstream timeout 600 $TR --nproc-per-node 2 --master-port 29611 tests/mgpu_worker.py > gpurun_out/${tag}_mgpu_bstream_n2.log 2>&1
     tail -2 gpurun_out/${tag}_mgpu_bstream_n2.log
     for sc in strong weak; do
-        for bs in "" "--boundary-stream"; do
-            name=${tag}_n2_${sc}${bs:+_bstream}
+        for bs in "" "--boundary-stream" "--direct-faces" "--boundary-stream --direct-faces"; do
+            name=${tag}_n2_${sc}$(echo "$bs" | tr -d ' ' | sed 's/--/_/g; s/-//g')
             timeout 300 $TR --nproc-per-node 2 --master-port 29612 bench.py --gpus 2 --scaling $sc --no-e2e $bs > gpurun_out/$name.json 2> gpurun_out/$name.err
         done
     done
     # 8-GPU strong scaling per-GPU block on 2 GPUs: 512x256x64 total = 32 planes each
-    for bs in "" "--boundary-stream"; do
-        name=${tag}_n2_thin${bs:+_bstream}
+    for bs in "" "--boundary-stream" "--direct-faces" "--boundary-stream --direct-faces"; do
+        name=${tag}_n2_thin$(echo "$bs" | tr -d ' ' | sed 's/--/_/g; s/-//g')
         timeout 300 $TR --nproc-per-node 2 --master-port 29613 bench.py --gpus 2 --scaling strong --workload 512x256x64 --no-e2e $bs > gpurun_out/$name.json 2> gpurun_out/$name.err
     done
     # the C++ driver with the ranks of the reference's job as threads (tests + one timed run)
@@ -63,8 +63,8 @@ for l in sys.stdin:
     ;;
 eight)
     for sc in strong weak; do
-        for bs in "" "--boundary-stream"; do
-            name=${tag}_n8_${sc}${bs:+_bstream}
+        for bs in "" "--boundary-stream --direct-faces"; do
+            name=${tag}_n8_${sc}$(echo "$bs" | tr -d ' ' | sed 's/--/_/g; s/-//g')
             timeout 300 $TR --nproc-per-node 8 --master-port 29614 bench.py --gpus 8 --scaling $sc --no-e2e $bs > gpurun_out/$name.json 2> gpurun_out/$name.err
         done
     done
