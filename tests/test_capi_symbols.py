@@ -91,3 +91,13 @@ def test_host_initvel_initpop_match_oracle(pkg, oracle):
         for k in ("ux", "uy", "uz"):
             assert np.allclose(getattr(s, k), w.get(k), rtol=1e-14, atol=1e-18), k
         assert np.allclose(s.f, w.get_f(), rtol=1e-13, atol=1e-18)
+
+
+def test_header_is_plain_c(tmp_path):
+    # the boundary is a C ABI: the header must compile as C99 (the Fortran shim and any C host bind to exactly this)
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "d3q19_b200.h"\nint main(void) { d3q19_config c; d3q19_particle_params p; (void)c; (void)p; return 0; }\n')
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c",
+                          str(src), "-o", str(tmp_path / "hdr.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
