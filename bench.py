@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--boundary-stream", action="store_true",
                     help="NCCL transport, opt-in: launch the two boundary planes of a step on their own high-priority stream next "
                          "to the interior launch instead of in front of it (D3Q19_BOUNDARY_STREAM=1)")
+    ap.add_argument("--vec2", action="store_true",
+                    help="experiment: the main-loop AB step with two nodes per thread and 128-bit loads/stores (D3Q19_VEC2=1)")
     ap.add_argument("--direct-faces", action="store_true",
                     help="NCCL transport, opt-in: send the five crossing populations of a face straight out of the population "
                          "array and receive them in place (20 sends/receives in one group, no pack / unpack kernels; "
@@ -284,6 +286,8 @@ def main():
         os.environ["D3Q19_BOUNDARY_STREAM"] = "1"
     if args.direct_faces and world > 1:
         os.environ["D3Q19_DIRECT_FACES"] = "1"
+    if args.vec2:
+        os.environ["D3Q19_VEC2"] = "1"
 
     def build_sim(halo_req, nccl_id):
         """the channel on this rank's slab with its synthetic initial state; returns (sim, halo actually in use)"""
@@ -393,7 +397,9 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "bytes_per_node": BYTES_PER_NODE, "peak_source": peak_src,
-                "kernel": "k_step<%s>" % ("AA even/odd" if args.scheme == "aa" else "AB pull")}
+                "kernel": ("k_step_ab2<two nodes per thread, 128-bit>" if args.vec2 and args.scheme == "ab" and nx % 2 == 0 and
+                           args.math == "fast" and args.particles == 0
+                           else "k_step<%s>" % ("AA even/odd" if args.scheme == "aa" else "AB pull"))}
 
     # ---- end to end through the reference-facing interface, host buffers ------------------------
     e2e = None
