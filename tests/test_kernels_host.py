@@ -575,7 +575,7 @@ def test_particle_ibb_and_force(oracle, hk, scheme, strict, nranks):
     sim.close()
 
 
-@pytest.mark.parametrize("scheme,nranks", [(AA, 1), (AB, 1), (AA, 3), (AB, 2)])
+@pytest.mark.parametrize("scheme,nranks", [(AA, 1), (AB, 3)])
 def test_moving_particles_with_refill(oracle, hk, scheme, nranks):
     # z-slabs: a refill next to a face takes its source nodes from the neighbour slab (k_plane_gather + exchange),
     # so the result is that of the single domain
