@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <mutex>
+
 namespace d3q {
 
 struct NcclUniqueId { char internal[128]; };            // nccl.h: NCCL_UNIQUE_ID_BYTES = 128
@@ -26,13 +28,18 @@ struct NcclApi {
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 
-    // returns nullptr on success, else a message
+    bool ready = false;
+
+    // returns nullptr on success, else a message.  Several host threads may create handles at the same time (one rank
+    // per thread, host/channel_driver.cpp --ranks): the table is filled once, under a lock, and published last.
     const char *load() {
-        if (lib) return nullptr;
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        if (ready) return nullptr;
         const char *names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char *n : names) {
-            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
             if (lib) break;
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         }
         if (!lib) return "cannot dlopen libnccl.so.2";
 #define D3Q_NCCL_SYM(field, name)                                     \
@@ -49,6 +56,7 @@ struct NcclApi {
         D3Q_NCCL_SYM(GroupEnd, "ncclGroupEnd")
         D3Q_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef D3Q_NCCL_SYM
+        ready = true;
         return nullptr;
     }
 };
