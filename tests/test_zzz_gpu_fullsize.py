@@ -21,14 +21,21 @@ pytestmark = pytest.mark.gpu
 pkg = entry.load_package()
 capi = pkg.capi
 
-NX, NY, NZ = 512, 256, 256
-PROBES = [(1, 1, 1), (NX, NY, NZ), (1, NY, 1), (NX, 1, NZ), (NX // 2, NY // 2, NZ // 2), (2, 17, 255), (511, 256, 2),
-          (128, 1, 128), (129, 128, 256)]
+import os
+
+# D3Q19_TEST_FULLSIZE=AxBxC shrinks the case (tests/test_hostsim_capi.py runs this file's logic on the host-sim build)
+NX, NY, NZ = (int(t) for t in os.environ.get("D3Q19_TEST_FULLSIZE", "512x256x256").split("x"))
+PROBES = [(1, 1, 1), (NX, NY, NZ), (1, NY, 1), (NX, 1, NZ), (NX // 2, NY // 2, NZ // 2), (2, min(17, NY), NZ - 1), (NX - 1, NY, 2),
+          (NX // 4, 1, NZ // 2), (NX // 4 + 1, NY // 2, NZ)]
 EXACT_ROWS = [0, 1, 2, 9, 11]          # sums of ux, uy, uz, rho (pure additions of strict moments) and the node count
 
 
+# a shrunk channel keeps the wall units of the 512-wide one (para.f90:64-66 would give Ma ~ 1 at nx = 64)
+SHRUNK = {} if NX >= 512 else dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / NX)
+
+
 def start(scheme, math_mode):
-    sim = pkg.ChannelFlow(NX, NY, NZ, laminar=False, scheme=scheme, math_mode=math_mode, allocate_host=False)
+    sim = pkg.ChannelFlow(NX, NY, NZ, laminar=False, scheme=scheme, math_mode=math_mode, allocate_host=False, **SHRUNK)
     sim.FORCING()
     sim.init_channel_device(A9=0.3, noise_amp=1e-3 * sim.v.ustar, seed=54321)
     return sim
@@ -75,7 +82,8 @@ def test_download_upload_roundtrip_at_full_size():
     aa.run_device(3)                                       # in-place storage in its swapped phase
     f = np.empty((NZ, NY, NX, 19))
     aa.download_f(f)
-    ab = pkg.ChannelFlow(NX, NY, NZ, laminar=False, scheme=capi.SCHEME_AB, math_mode=capi.MATH_STRICT, allocate_host=False)
+    ab = pkg.ChannelFlow(NX, NY, NZ, laminar=False, scheme=capi.SCHEME_AB, math_mode=capi.MATH_STRICT, allocate_host=False,
+                         **SHRUNK)
     ab.FORCING()
     ab.upload_f(f)
     assert same_bits(fingerprint(aa), fingerprint(ab))
