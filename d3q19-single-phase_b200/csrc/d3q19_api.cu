@@ -1139,9 +1139,9 @@ extern "C" int d3q19_probe(d3q19_handle *h, int32_t ix, int32_t iy, int32_t iz, 
     if (ix < 1 || ix > g.lx || iy < 1 || iy > g.ly || iz < 1 || iz > g.lz) return fail("d3q19_probe: node out of range");
     RK_(wait_exchange(h));
     switch (read_kind(h)) {
-    case READ_DIRECT: k_probe<READ_DIRECT><<<1, 1, 0, h->sc>>>(g, h->A, ix - 1, iy - 1, iz, h->Fx, h->Fy, h->Fz, h->scal); break;
-    case READ_PULL_NAT: k_probe<READ_PULL_NAT><<<1, 1, 0, h->sc>>>(g, h->A, ix - 1, iy - 1, iz, h->Fx, h->Fy, h->Fz, h->scal); break;
-    default: k_probe<READ_PULL_SWAP><<<1, 1, 0, h->sc>>>(g, h->A, ix - 1, iy - 1, iz, h->Fx, h->Fy, h->Fz, h->scal); break;
+    case READ_DIRECT: k_probe<READ_DIRECT><<<1, 1, 0, h->sc>>>(g, h->A, ix - 1, iy - 1, iz, h->Fx, h->Fy, h->Fz, h->ffx, h->ffy, h->ffz, h->scal); break;
+    case READ_PULL_NAT: k_probe<READ_PULL_NAT><<<1, 1, 0, h->sc>>>(g, h->A, ix - 1, iy - 1, iz, h->Fx, h->Fy, h->Fz, h->ffx, h->ffy, h->ffz, h->scal); break;
+    default: k_probe<READ_PULL_SWAP><<<1, 1, 0, h->sc>>>(g, h->A, ix - 1, iy - 1, iz, h->Fx, h->Fy, h->Fz, h->ffx, h->ffy, h->ffz, h->scal); break;
     }
     CK(cudaGetLastError());
     h->n_other_kernels++;
@@ -1556,9 +1556,9 @@ static int profiles_impl(d3q19_handle *h, double *out, int nrows_out) {
     }
     const dim3 gr((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)h->prof_chunks);
     switch (read_kind(h)) {
-    case READ_DIRECT: k_profiles<READ_DIRECT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, h->prof_rows, h->prof_partial); break;
-    case READ_PULL_NAT: k_profiles<READ_PULL_NAT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, h->prof_rows, h->prof_partial); break;
-    default: k_profiles<READ_PULL_SWAP><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, h->prof_rows, h->prof_partial); break;
+    case READ_DIRECT: k_profiles<READ_DIRECT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->ffx, h->ffy, h->ffz, h->solid, h->prof_rows, h->prof_partial); break;
+    case READ_PULL_NAT: k_profiles<READ_PULL_NAT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->ffx, h->ffy, h->ffz, h->solid, h->prof_rows, h->prof_partial); break;
+    default: k_profiles<READ_PULL_SWAP><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->ffx, h->ffy, h->ffz, h->solid, h->prof_rows, h->prof_partial); break;
     }
     const dim3 g2((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), NPROF);
     k_profiles_final<<<g2, BLOCK_X, 0, h->sc>>>(g.lx, h->prof_chunks, h->prof_partial, h->prof_out);
@@ -1591,9 +1591,9 @@ extern "C" int d3q19_diag(d3q19_handle *h, double ustar, double *out14) {
     CK(cudaMalloc(&partial, ((size_t)npartial + 1) * NDIAG * sizeof(double)));
     double *res = partial + (size_t)npartial * NDIAG;
     switch (read_kind(h)) {
-    case READ_DIRECT: k_diag<READ_DIRECT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, rows, partial); break;
-    case READ_PULL_NAT: k_diag<READ_PULL_NAT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, rows, partial); break;
-    default: k_diag<READ_PULL_SWAP><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->solid, rows, partial); break;
+    case READ_DIRECT: k_diag<READ_DIRECT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->ffx, h->ffy, h->ffz, h->solid, rows, partial); break;
+    case READ_PULL_NAT: k_diag<READ_PULL_NAT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->ffx, h->ffy, h->ffz, h->solid, rows, partial); break;
+    default: k_diag<READ_PULL_SWAP><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->ffx, h->ffy, h->ffz, h->solid, rows, partial); break;
     }
     k_diag_final<<<1, 32, 0, h->sc>>>(npartial, partial, res);
     CK(cudaGetLastError());

@@ -666,11 +666,18 @@ __global__ void __launch_bounds__(BLOCK_X) k_macro(const __grid_constant__ Macro
 }
 
 // one node -> out[4] (probe, saveload.f90:4059-4100)
+// (ffx,ffy,ffz: the force field when one is set -- the velocity is momentum + F/2 with the node's own force,
+// collision.f90:415-417 -- else nullptr and the uniform force applies; same in k_profiles and k_diag)
 template <int RK>
-__global__ void k_probe(Geom g, const double *A, int x, int y, int zg, double Fx, double Fy, double Fz, double *out) {
+__global__ void k_probe(Geom g, const double *A, int x, int y, int zg, double Fx, double Fy, double Fz, const double *ffx,
+                        const double *ffy, const double *ffz, double *out) {
     const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, y, zg);
     double f[NPOP];
     gather19<RK>(A, g, k, f);
+    if (ffx) {
+        const long long m = x + (long long)g.xp * (y + (long long)g.ly * (zg - 1));
+        Fx = ffx[m]; Fy = ffy[m]; Fz = ffz[m];
+    }
     moments_strict(f, Fx, Fy, Fz, out[0], out[1], out[2], out[3]);
 }
 
@@ -973,6 +980,7 @@ __global__ void __launch_bounds__(BLOCK_X) k_rho_shift(int lx, int xp, double *r
 constexpr int NPROF = 12;
 template <int RK>
 __global__ void __launch_bounds__(BLOCK_X) k_profiles(Geom g, const double *A, double Fx, double Fy, double Fz,
+                                                      const double *ffx, const double *ffy, const double *ffz,
                                                       const int32_t *solid, int rows_per_chunk, double *partial) {
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     if (x >= g.lx) return;
@@ -988,6 +996,7 @@ __global__ void __launch_bounds__(BLOCK_X) k_profiles(Geom g, const double *A, d
         const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, y, z + 1);
         double f[NPOP], r, a, b, c;
         gather19<RK>(A, g, k, f);
+        if (ffx) { const long long m = row * g.xp + x; Fx = ffx[m]; Fy = ffy[m]; Fz = ffz[m]; }
         moments_strict(f, Fx, Fy, Fz, r, a, b, c);
         acc[0] += a; acc[1] += b; acc[2] += c;
         acc[3] += a * a; acc[4] += b * b; acc[5] += c * c;
@@ -1013,6 +1022,7 @@ __global__ void __launch_bounds__(BLOCK_X) k_profiles_final(int lx, int nchunks,
 constexpr int NDIAG = 12;   // cnt, su, sv, sw, suu, svv, sww, vmax, vidx, rhomax, rhomin, (pad)
 template <int RK>
 __global__ void __launch_bounds__(BLOCK_X) k_diag(Geom g, const double *A, double Fx, double Fy, double Fz,
+                                                  const double *ffx, const double *ffy, const double *ffz,
                                                   const int32_t *solid, int rows_per_chunk, double *partial) {
     __shared__ double sh[BLOCK_X][NDIAG];
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
@@ -1030,6 +1040,7 @@ __global__ void __launch_bounds__(BLOCK_X) k_diag(Geom g, const double *A, doubl
             const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, y, z + 1);
             double f[NPOP], r, a, b, c;
             gather19<RK>(A, g, k, f);
+            if (ffx) { const long long m = row * g.xp + x; Fx = ffx[m]; Fy = ffy[m]; Fz = ffz[m]; }
             moments_strict(f, Fx, Fy, Fz, r, a, b, c);
             acc[0] += 1.0; acc[1] += a; acc[2] += b; acc[3] += c;
             acc[4] += a * a; acc[5] += b * b; acc[6] += c * c;

@@ -1,0 +1,194 @@
+"""TEST INFRASTRUCTURE ONLY.  Random sequences of C-ABI calls on the host-sim build of the library, mirrored on the oracle
+and compared after every call that reads state: steps in bursts (so both in-place storage phases are met by every
+reader), downloads, macrovar, probe, plane sums, re-uploads in either storage phase, uniform force / force field
+switches, frozen-moment (EXTERNAL) and PRERELAX steps, avedensity with the shifted collision that follows.  Strict
+arithmetic: everything but the order-dependent sums must agree bit for bit.
+
+    D3Q19_LIB=tests/host/_gen/libd3q19b200_hostsim.so python tests/host/hostsim_random_calls.py [nseeds]
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+pkg = entry.load_package()
+capi = pkg.capi
+
+
+def run_sequence(seed, scheme, log):
+    rng = np.random.default_rng(seed)
+    nx, ny, nz = int(rng.integers(5, 40)), int(rng.integers(1, 6)), int(rng.integers(1, 6))
+    U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+    w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True, **U)
+    w.set_f(w.get_f() + 1e-4 * rng.normal(size=(nz, ny, nx, 19)))
+    w.macrovar()
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT, **U)
+    sim.FORCING()
+    sim.upload_f(w.get_f())
+    shp = (nz, ny, nx)
+    out = np.empty(shp + (19,))
+    exact = True                      # False between an avedensity and the next re-upload (order-dependent mean)
+    ops = ["step", "step", "step", "download", "macro", "probe", "sums", "reupload", "force", "field", "external", "prerelax",
+           "avedensity"]
+    for k in range(40):
+        op = ops[int(rng.integers(len(ops)))]
+        log.append((seed, scheme, (nx, ny, nz), k, op))
+        if op == "step":
+            n = int(rng.integers(1, 4))
+            for _ in range(n):
+                w.collision_MRT(); w.macrovar()
+            sim.run_device(n)
+        elif op == "download":
+            sim.download_f(out)
+            ref = w.get_f()
+            assert np.array_equal(out, ref) if exact else np.max(np.abs(out - ref)) <= 1e-13 * np.max(np.abs(ref))
+        elif op == "macro":
+            sim.device_macrovar()
+            for name in ("rho", "ux", "uy", "uz"):
+                a, b = getattr(sim, name), w.get(name)
+                assert np.array_equal(a, b) if exact else np.max(np.abs(a - b)) <= 1e-13 * max(np.max(np.abs(w.get_f())), 1e-300), name
+        elif op == "probe":
+            ix, iy, iz = (int(rng.integers(1, n + 1)) for n in (nx, ny, nz))
+            pr = sim.probe(ix, iy, iz)
+            ref = np.array([w.get(name)[iz - 1, iy - 1, ix - 1] for name in ("rho", "ux", "uy", "uz")])
+            assert np.array_equal(pr, ref) if exact else np.max(np.abs(pr - ref)) <= 1e-13
+        elif op == "sums":
+            got = sim.profiles()
+            ref, _ = orc.plane_sums(w)
+            scale = np.max(np.abs(ref), axis=1, keepdims=True) + 1e-30
+            assert np.max(np.abs(got - ref) / np.maximum(scale, np.max(np.abs(ref[1])) * 1e-3)) < 1e-11
+        elif op == "reupload":
+            f = w.get_f() + 1e-5 * rng.normal(size=shp + (19,))
+            w.set_f(f); w.macrovar()
+            sim.upload_f(np.ascontiguousarray(f))
+            exact = True
+        elif op == "force":
+            F = [float(t) for t in 1e-6 * rng.normal(size=3)]
+            for name, v in zip(("fx", "fy", "fz"), F):
+                w.set(name, np.full(shp, v))
+            sim.set_force_uniform(*F)                      # also drops a force field
+            w.macrovar()
+        elif op == "field":
+            F = [1e-6 * rng.normal(size=shp) for _ in range(3)]
+            for name, a in zip(("fx", "fy", "fz"), F):
+                w.set(name, a)
+            sim.set_force_field(*F)
+            w.macrovar()
+        elif op == "external":
+            macro = [1e-4 * rng.normal(size=shp)] + [0.01 * rng.normal(size=shp) for _ in range(3)]
+            for name, a in zip(("rho", "ux", "uy", "uz"), macro):
+                w.set(name, a)
+            sim.set_macro(*macro)
+            w.collision_MRT(); w.macrovar()
+            sim.collide_stream(capi.MACRO_EXTERNAL)
+        elif op == "prerelax":
+            # rhoupdat; collision with frozen u (main.f90:74-76): the arrays must hold what macrovar left
+            sim.device_macrovar(download=False)
+            w.rhoupdat(); w.collision_MRT(); w.macrovar()
+            sim.collide_stream(capi.MACRO_PRERELAX)
+        elif op == "avedensity":
+            sim.device_macrovar(download=False)
+            mean_ref, n_ref = w.avedensity()
+            m, n = C.c_double(0), C.c_int64(0)
+            capi.check(sim.L.d3q19_avedensity(sim.h, C.byref(m), C.byref(n)))
+            assert n.value == n_ref and abs(m.value - mean_ref) <= 1e-13 * max(np.max(np.abs(w.get_f())), 1e-300)
+            w.collision_MRT(); w.macrovar()
+            sim.collide_stream()
+            exact = False
+    sim.download_f(out)
+    ref = w.get_f()
+    assert np.array_equal(out, ref) if exact else np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref))
+    sim.close(); w.close()
+
+
+def run_shim_sequence(seed, scheme, log):
+    """the driver-facing entry points (what collision_b200.f90 binds) in random but legal order: segments of the time
+    loop with random output cadences, a host-side rewrite of f (loadcntdflow) at a random point, pre-relaxation
+    pairs, sync_f_to_host (savecntdflow), avedensity steps -- the host arrays must be current exactly when the intact
+    driver would read them"""
+    rng = np.random.default_rng(1000 + seed)
+    nx, ny, nz = int(rng.integers(6, 30)), int(rng.integers(1, 5)), int(rng.integers(1, 5))
+    U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+    ndiag, nflowout = int(rng.integers(2, 7)), int(rng.integers(2, 7))
+    w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True, **U)
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT, ndiag=ndiag, nflowout=nflowout, **U)
+    sim.f[...] = w.get_f()
+    for k in ("rho", "ux", "uy", "uz"):
+        getattr(sim, k)[...] = w.get(k)
+    sim.host_f_changed()
+    sim.FORCING()
+    names = ("rho", "ux", "uy", "uz")
+
+    def host_macro_current(what):
+        for k in names:
+            assert np.array_equal(getattr(sim, k), w.get(k)), (what, k)
+
+    for seg in range(6):
+        op = ["loop", "loop", "rewrite", "prerelax", "save"][int(rng.integers(5))]
+        log.append((seed, scheme, (nx, ny, nz), seg, "shim:" + op))
+        if op == "loop":
+            nsteps = int(rng.integers(1, 14))
+            sim.v.nsteps = nsteps
+            sim.v.istep0 = int(rng.integers(0, 50))
+            sim.set_schedule()
+            # main.f90:132-136 before every (re)start of the loop
+            sim.FORCING(); w.macrovar()
+            sim.istep = sim.v.istep0
+            sim.macrovar()
+            host_macro_current("initial macrovar")
+            for step in range(sim.v.istep0 + 1, sim.v.istep0 + nsteps + 1):
+                sim.istep = step
+                w.collision_MRT(); w.macrovar()
+                sim.collision_MRT(); sim.macrovar()
+                if step % ndiag == 0 or step % nflowout == 0 or step == sim.v.istep0 + nsteps:
+                    host_macro_current("step %d" % step)
+        elif op == "rewrite":
+            f = w.get_f() + 1e-5 * rng.normal(size=(nz, ny, nx, 19))
+            w.set_f(f)
+            sim.f[...] = f
+            sim.host_f_changed()
+        elif op == "prerelax":
+            # the driver's arrays hold what the last macrovar left; u stays frozen (main.f90:70-90)
+            w.macrovar()
+            sim.istep = 0
+            sim.macrovar()
+            for it in range(int(rng.integers(1, 5))):
+                w.rhoupdat(); w.collision_MRT()
+                sim.rhoupdat(); sim.collision_MRT()
+                assert np.array_equal(sim.rho, w.get("rho")), "rho after rhoupdat"
+        else:
+            got = sim.sync_f_to_host()
+            assert np.array_equal(got, w.get_f()), "sync_f_to_host"
+    assert np.array_equal(sim.sync_f_to_host(), w.get_f())
+    sim.close(); w.close()
+
+
+def main():
+    if "hostsim" not in os.path.basename(capi.LIB_PATH):
+        print("this script drives the host-sim build only (set D3Q19_LIB)")
+        return 2
+    nseeds = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+    log = []
+    try:
+        for seed in range(nseeds):
+            for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
+                run_sequence(seed, scheme, log)
+                run_shim_sequence(seed, scheme, log)
+    except Exception:
+        import traceback
+        traceback.print_exc()
+        print("last calls:", log[-8:])
+        print("HOSTSIM_RANDOM_FAILED")
+        return 1
+    print("HOSTSIM_RANDOM_OK %d sequences" % (4 * nseeds))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

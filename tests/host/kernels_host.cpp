@@ -296,8 +296,10 @@ void gather_rank(Rank &q, double *aos) {
 template <int RK>
 void profiles_rank(const Sim &s, Rank &q, int rows_per_chunk, int nchunks, double *partial, double *out) {
     hs_launch(dim3((unsigned)((q.g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)nchunks, 1u), BLOCK_X, k_profiles<RK>, q.g,
-              (const double *)q.A, s.Fx, s.Fy, s.Fz, s.has_solid ? (const int32_t *)q.solid.data() : (const int32_t *)nullptr,
-              rows_per_chunk, partial);
+              (const double *)q.A, s.Fx, s.Fy, s.Fz, s.force_field ? (const double *)q.ffx.data() : (const double *)nullptr,
+              s.force_field ? (const double *)q.ffy.data() : (const double *)nullptr,
+              s.force_field ? (const double *)q.ffz.data() : (const double *)nullptr,
+              s.has_solid ? (const int32_t *)q.solid.data() : (const int32_t *)nullptr, rows_per_chunk, partial);
     hs_launch(dim3((unsigned)((q.g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)NPROF, 1u), BLOCK_X, k_profiles_final, q.g.lx, nchunks,
               (const double *)partial, out);
 }
@@ -423,7 +425,10 @@ void diag_rank(const Sim &s, Rank &q, int rows_per_chunk, std::vector<double> &o
     const dim3 gd((unsigned)((q.g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)nchunks, 1u);
     std::vector<double> partial((size_t)gd.x * gd.y * NDIAG, 0.0);
     const int32_t *solid = s.part_on ? q.own.data() + q.g.plane : (s.has_solid ? q.solid.data() : nullptr);
-    hs_launch_coop(gd, BLOCK_X, k_diag<RK>, q.g, (const double *)q.A, s.Fx, s.Fy, s.Fz, solid, rows_per_chunk, partial.data());
+    const double *ff[3] = {s.force_field ? q.ffx.data() : nullptr, s.force_field ? q.ffy.data() : nullptr,
+                           s.force_field ? q.ffz.data() : nullptr};
+    hs_launch_coop(gd, BLOCK_X, k_diag<RK>, q.g, (const double *)q.A, s.Fx, s.Fy, s.Fz, ff[0], ff[1], ff[2], solid, rows_per_chunk,
+                   partial.data());
     out.assign(NDIAG, 0.0);
     hs_launch(dim3(1), 1, k_diag_final, (int)(gd.x * gd.y), (const double *)partial.data(), out.data());
 }

@@ -97,3 +97,9 @@ def test_full_size_property_tests_and_experiments_on_the_host_sim(hostsim):
     tail = res.stdout[-3000:]
     assert res.returncode == 0, tail
     assert " passed" in tail and "failed" not in tail, tail
+
+
+def test_random_call_sequences_on_the_host_sim(hostsim):
+    # random but legal orders of the raw C-ABI calls and of the driver-facing shim calls, mirrored on the oracle
+    res = run([sys.executable, os.path.join("tests", "host", "hostsim_random_calls.py"), "5"], hostsim)
+    assert res.returncode == 0 and "HOSTSIM_RANDOM_OK" in res.stdout, res.stdout[-4000:]
