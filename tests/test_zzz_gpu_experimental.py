@@ -36,7 +36,7 @@ def test_refill_is_decomposition_invariant(world):
     assert res.returncode == 0 and "MGPU_PARITY_OK" in res.stdout, res.stdout[-4000:]
 
 
-@pytest.mark.parametrize("shape", [(64, 32, 32), (130, 8, 6), (516, 4, 5)])
+@pytest.mark.parametrize("shape", [(64, 8, 8), (130, 8, 6), (516, 4, 5)])
 def test_vec2_step_matches_the_64bit_step(shape):
     # D3Q19_VEC2=1: k_step_ab2 (two nodes per thread, 128-bit accesses) runs the same collide_fast on the same values;
     # on the host build it is bit-identical, on the device nvcc may contract the inlined arithmetic differently
