@@ -198,6 +198,14 @@ static int wait_exchange(d3q19_handle *h) {
     return 0;
 }
 
+// particle runs: whoever reads the solid mask (the step, macrovar, avedensity, diag, the plane sums) must see the mask of
+// the CURRENT particle table; d3q19_beads_links is a no-op while the table has not changed since the last build
+extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local);
+static int ensure_mask(d3q19_handle *h) {
+    if (h->part_on && !h->links_valid) return d3q19_beads_links(h, nullptr);
+    return 0;
+}
+
 static inline void trace_mark(d3q19_handle *h, int which, cudaStream_t s) {
     if (h->trace_ev && h->trace_n < h->trace_cap) cudaEventRecord(h->trace_ev[4 * h->trace_n + which], s);
 }
@@ -1026,6 +1034,7 @@ static int step_dispatch(d3q19_handle *h, StepParams &p) {
 
 static int collide_stream_impl(d3q19_handle *h, int macro_mode, unsigned long long *rhoerr_bits) {
     if (macro_mode < 0 || macro_mode > 2) return fail("d3q19_collide_stream: bad macro_mode %d", macro_mode);
+    RK_(ensure_mask(h));
     StepParams p;
     memset(&p, 0, sizeof p);
     p.g = h->g;
@@ -1097,6 +1106,7 @@ extern "C" int d3q19_init_channel(d3q19_handle *h, double ustar, double ystar, d
 // ---- macrovar / rhoupdat ---------------------------------------------------------------------------------
 static int macro_launch(d3q19_handle *h, int rho_only, unsigned long long *rhoerr_bits = nullptr) {
     RK_(ensure_macro_arrays(h));
+    RK_(ensure_mask(h));
     RK_(wait_exchange(h));
     MacroParams p;
     memset(&p, 0, sizeof p);
@@ -1154,6 +1164,7 @@ extern "C" int d3q19_probe(d3q19_handle *h, int32_t ix, int32_t iy, int32_t iz, 
 extern "C" int d3q19_avedensity(d3q19_handle *h, double *rhomean, int64_t *nfluid_total) {
     CK(cudaSetDevice(h->cfg.device));
     RK_(ensure_macro_arrays(h));
+    RK_(ensure_mask(h));
     const Geom &g = h->g;
     const long long nrows = (long long)g.ly * g.lz;
     const int nblk = nrows < 1024 ? (int)nrows : 1024;             // a block per (y,z) row at most
@@ -1337,6 +1348,12 @@ static int fetch_nlink(d3q19_handle *h) {
 extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local) {
     CK(cudaSetDevice(h->cfg.device));
     if (!h->part_on) return fail("d3q19_beads_links: call d3q19_particles_init first");
+    if (h->links_valid && h->mask_built) {
+        // the particle table has not changed since the last build (d3q19_set_particles and d3q19_beads_move invalidate):
+        // rebuilding would also overwrite the previous mask that d3q19_beads_filling still has to compare against
+        if (nlink_local) { RK_(fetch_nlink(h)); *nlink_local = h->nlink; }
+        return 0;
+    }
     const PartGeom pg = part_geom(h);
     const size_t nown = (size_t)h->g.plane * (h->g.lz + 2);
     int32_t *t = h->own; h->own = h->own0; h->own0 = t;          // the old mask is what beads_filling compares against
@@ -1544,6 +1561,7 @@ extern "C" int d3q19_profiles2(d3q19_handle *h, double *out) { return profiles_i
 static int profiles_impl(d3q19_handle *h, double *out, int nrows_out) {
     CK(cudaSetDevice(h->cfg.device));
     const Geom &g = h->g;
+    RK_(ensure_mask(h));
     RK_(wait_exchange(h));
     const long long nrows = (long long)g.ly * g.lz;
     if (!h->prof_partial) {
@@ -1579,6 +1597,7 @@ static int profiles_impl(d3q19_handle *h, double *out, int nrows_out) {
 extern "C" int d3q19_diag(d3q19_handle *h, double ustar, double *out14) {
     CK(cudaSetDevice(h->cfg.device));
     const Geom &g = h->g;
+    RK_(ensure_mask(h));
     RK_(wait_exchange(h));
     const long long nrows = (long long)g.ly * g.lz;
     int chunks = 296;

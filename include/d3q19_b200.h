@@ -176,7 +176,9 @@ typedef struct d3q19_particle_params {
     int64_t maxlink;            /* link capacity; 0 = 8 npart 4 pi (rad+1)^2 (cf. para.f90:371) */
 } d3q19_particle_params;
 int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_particle_params *prm);
-/* solid mask (ibnodes/isnodes, ghost planes included) and boundary links from the particle table */
+/* solid mask (ibnodes/isnodes, ghost planes included) and boundary links from the particle table.  A no-op while the
+   table has not changed since the last build (d3q19_set_particles / d3q19_beads_move invalidate); every entry point that
+   reads the mask (collide_stream, macrovar, avedensity, diag, profiles) builds it first if it is stale */
 int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local);
 /* interpolated bounce-back on every link after a collide_stream; force and torque reduced over ranks */
 int d3q19_beads_collision(d3q19_handle *h);

@@ -169,6 +169,96 @@ def run_shim_sequence(seed, scheme, log):
     sim.close(); w.close()
 
 
+def run_particle_sequence(seed, scheme, log):
+    """the particle entry points in random order: fixed and moving particle steps, macrovar with the solid branch,
+    avedensity over the fluid nodes, diag and the masked plane sums, link list and mask read-backs -- against
+    oracle/particles_oracle.c + the fluid oracle (parity unpinned against the reference: partlib.f90 is absent)"""
+    from oracle import particles as P
+    rng = np.random.default_rng(2000 + seed)
+    nx, ny, nz, rad = 20, 16, 18, 3.3
+    U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+    pos = [[9.7, 1.2 + 3 * rng.random(), 16.9], [5.1 + 2 * rng.random(), 10.0, 8.0]]
+    vel = [list(0.02 * (rng.random(3) - 0.5)) for _ in range(2)]
+    omg = [list(2e-3 * (rng.random(3) - 0.5)) for _ in range(2)]
+    w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True, ipart=1, **U)
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_FAST, ipart=True, **U)
+    sim.FORCING()
+    sim.upload_f(w.get_f())
+    pt = P.Particles(nx, ny, nz, rad, pos, vel, omg)
+    sim.particles_init(pos, rad, vel, omg)
+    pt.build_mask(); pt.build_links()
+
+    def oracle_mask():
+        w.set_solid(np.where(pt.own > 0, 1, -1).astype(np.int32), pt.own)
+        w.set_particles(pt.ypglb, pt.wp, pt.omgp)
+    oracle_mask()
+    w.macrovar()
+    out = np.empty((nz, ny, nx, 19))
+    tol = 1e-11
+
+    def fields_agree(what, f):
+        nonlocal tol
+        fluid = pt.own < 0
+        sim.download_f(out)
+        err = np.max(np.abs(out[fluid] - f[fluid])) / np.max(np.abs(f[fluid]))
+        assert err < tol, (what, err)
+
+    for seg in range(7):
+        op = ["fixed", "moving", "macro", "avedensity", "monitors", "links"][int(rng.integers(6))]
+        log.append((seed, scheme, (nx, ny, nz), seg, "particles:" + op))
+        if op == "fixed":
+            for _ in range(int(rng.integers(1, 4))):
+                w.collision_MRT()
+                f = w.get_f(); pt.ibb(f); w.set_f(f); w.macrovar()
+                sim.particle_step(move=False)
+            fields_agree("fixed", f)
+            g = sim.get_particles()
+            assert np.max(np.abs(g["fHIp"] - pt.fHIp)) < 1e-8 * np.max(np.abs(pt.fHIp))
+        elif op == "moving":
+            for _ in range(int(rng.integers(1, 4))):
+                w.collision_MRT()
+                f = w.get_f(); pt.ibb(f); pt.lubforce(); pt.move(); pt.build_mask(); pt.build_links(); pt.refill(f)
+                w.set_f(f); oracle_mask(); w.macrovar()
+                sim.particle_step(move=True)
+            tol = 1e-8                                   # refills extrapolate: differences of 1e-12 grow a little
+            g = sim.get_particles()
+            assert np.max(np.abs(g["ypglb"] - pt.ypglb)) < 1e-10
+            assert np.array_equal(sim.get_mask(), pt.own)
+            fields_agree("moving", f)
+        elif op == "macro":
+            sim.device_macrovar()
+            solid = pt.own > 0
+            for name in ("rho", "ux", "uy", "uz"):
+                a, b = getattr(sim, name), w.get(name)
+                assert np.max(np.abs(a[~solid] - b[~solid])) <= tol * max(np.max(np.abs(b)), 1e-30), name
+                assert np.max(np.abs(a[solid] - b[solid])) <= 1e-9 * max(np.max(np.abs(b)), 1e-30), name   # rigid-body velocity
+        elif op == "avedensity":
+            sim.device_macrovar(download=False)
+            mean_ref, n_ref = w.avedensity()
+            m, n = C.c_double(0), C.c_int64(0)
+            capi.check(sim.L.d3q19_avedensity(sim.h, C.byref(m), C.byref(n)))
+            assert n.value == n_ref == int((pt.own < 0).sum())
+            assert abs(m.value - mean_ref) <= 1e-9 * max(np.max(np.abs(w.get_f())), 1e-300)
+            w.macrovar()                                 # rho recomputed: the shift lives in the arrays only
+            sim.L.d3q19_macrovar(sim.h)
+        elif op == "monitors":
+            d, ref = sim.diag(), orc.diag_line(w, p.ustar, solid=pt.own > 0)
+            assert d["nfluid"] == ref["nfluid"] and abs(d["volf"] - ref["volf"]) < 1e-15
+            assert abs(d["vmax"] - ref["vmax"]) <= 1e-7 * ref["vmax"]
+            p2 = sim.profiles2()
+            sums, cnt = orc.plane_sums(w, solid=pt.own > 0)
+            assert np.array_equal(p2[11], cnt)
+            assert np.max(np.abs(p2[1] - sums[1])) <= 1e-7 * np.max(np.abs(sums[1]))
+        else:
+            n = sim.beads_links()
+            gl = sim.get_links()
+            assert n == len(pt.links["q"])
+            for key in ("x", "y", "z", "ip", "part"):
+                assert np.array_equal(gl[key], pt.links[key]), key
+            assert np.array_equal(sim.get_mask(), pt.own)
+    sim.close(); w.close()
+
+
 def main():
     if "hostsim" not in os.path.basename(capi.LIB_PATH):
         print("this script drives the host-sim build only (set D3Q19_LIB)")
@@ -180,6 +270,8 @@ def main():
             for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
                 run_sequence(seed, scheme, log)
                 run_shim_sequence(seed, scheme, log)
+                if seed < int(os.environ.get("HOSTSIM_PARTICLE_SEEDS", "2")):
+                    run_particle_sequence(seed, scheme, log)
     except Exception:
         import traceback
         traceback.print_exc()
