@@ -329,7 +329,33 @@ def section_vec2(rank, world, comm, chk, ctx):
     comm.bar.wait()
 
 
-SECTIONS = {"vec2": section_vec2, "fluid": section_fluid, "prerelax": section_prerelax, "particles": section_particles, "shim": section_shim}
+def section_random(rank, world, comm, chk, ctx):
+    """random call sequences (tests/host/hostsim_random_calls.py) followed by every rank, one transport per sequence"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("hostsim_random_calls", os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                                                     "hostsim_random_calls.py"))
+    rc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rc)
+    transports = ["nccl", "peer", "peer-split", "put", "bstream", "direct", "bstream+direct"]
+    nseeds = int(os.environ.get("HOSTSIM_RANDOM_SEEDS", "7"))
+    for seed in range(nseeds):
+        for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
+            tr = transports[(seed + scheme) % len(transports)]
+            ctx[0] = "random seed %d scheme %d transport %s" % (seed, scheme, tr)
+            log = []
+            try:
+                rc.run_sequence(500 + seed, scheme, log, rank=rank, world=world, comm=comm, transport=tr)
+            except AssertionError:
+                chk("random sequence, last calls %r\n%s" % (log[-6:], traceback.format_exc()), False)
+                raise                      # the ranks have left lockstep: stop the run
+    comm.bar.wait()
+    if rank == 0:
+        for k in ("D3Q19_BOUNDARY_STREAM", "D3Q19_DIRECT_FACES", "D3Q19_HALO_SPLIT_MIN"):
+            os.environ.pop(k, None)
+    comm.bar.wait()
+
+
+SECTIONS = {"random": section_random, "vec2": section_vec2, "fluid": section_fluid, "prerelax": section_prerelax, "particles": section_particles, "shim": section_shim}
 
 
 def rank_main(rank, world, comm, sections):

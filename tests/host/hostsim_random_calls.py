@@ -21,24 +21,43 @@ pkg = entry.load_package()
 capi = pkg.capi
 
 
-def run_sequence(seed, scheme, log):
+def run_sequence(seed, scheme, log, rank=0, world=1, comm=None, transport="nccl"):
+    """raw C-ABI calls in random order; with world > 1 every rank (a thread, tests/host/hostsim_mrank_worker.py) follows
+    the same seeded sequence on its z-slab, over the given halo transport"""
     rng = np.random.default_rng(seed)
-    nx, ny, nz = int(rng.integers(5, 40)), int(rng.integers(1, 6)), int(rng.integers(1, 6))
+    nx, ny = int(rng.integers(5, 40)), int(rng.integers(1, 6))
+    nz = int(rng.integers(1, 6)) if world == 1 else int(rng.integers(2 * world, 3 * world + 3))
     U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
     w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True, **U)
     w.set_f(w.get_f() + 1e-4 * rng.normal(size=(nz, ny, nx, 19)))
     w.macrovar()
-    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT, **U)
+    if world > 1:
+        comm.bar.wait()
+        if rank == 0:
+            for k in ("D3Q19_BOUNDARY_STREAM", "D3Q19_DIRECT_FACES", "D3Q19_HALO_SPLIT_MIN"):
+                os.environ.pop(k, None)
+            if transport in ("bstream", "bstream+direct"):
+                os.environ["D3Q19_BOUNDARY_STREAM"] = "1"
+            if transport in ("direct", "bstream+direct"):
+                os.environ["D3Q19_DIRECT_FACES"] = "1"
+            if transport == "peer-split":
+                os.environ["D3Q19_HALO_SPLIT_MIN"] = "3"
+        comm.bar.wait()
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT, rank=rank, nranks=world,
+                          device=0, nccl_id=comm.new_id(rank) if world > 1 else None, **U)
     sim.FORCING()
-    sim.upload_f(w.get_f())
-    shp = (nz, ny, nx)
-    out = np.empty(shp + (19,))
+    if transport in ("peer", "peer-split", "put"):
+        assert sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if transport == "put" else "fused")
+    sl = slice(sim.globalz, sim.globalz + sim.lz)
+    sim.upload_f(np.ascontiguousarray(w.get_f()[sl]))
+    shp, lshp = (nz, ny, nx), (sim.lz, ny, nx)
+    out = np.empty(lshp + (19,))
     exact = True                      # False between an avedensity and the next re-upload (order-dependent mean)
     ops = ["step", "step", "step", "download", "macro", "probe", "sums", "reupload", "force", "field", "external", "prerelax",
            "avedensity"]
-    for k in range(40):
+    for k in range(40 if world == 1 else 25):
         op = ops[int(rng.integers(len(ops)))]
-        log.append((seed, scheme, (nx, ny, nz), k, op))
+        log.append((seed, scheme, (nx, ny, nz), k, op, transport))
         if op == "step":
             n = int(rng.integers(1, 4))
             for _ in range(n):
@@ -46,18 +65,19 @@ def run_sequence(seed, scheme, log):
             sim.run_device(n)
         elif op == "download":
             sim.download_f(out)
-            ref = w.get_f()
-            assert np.array_equal(out, ref) if exact else np.max(np.abs(out - ref)) <= 1e-13 * np.max(np.abs(ref))
+            ref = w.get_f()[sl]
+            assert np.array_equal(out, ref) if exact else np.max(np.abs(out - ref)) <= 1e-13 * np.max(np.abs(w.get_f()))
         elif op == "macro":
             sim.device_macrovar()
             for name in ("rho", "ux", "uy", "uz"):
-                a, b = getattr(sim, name), w.get(name)
+                a, b = getattr(sim, name), w.get(name)[sl]
                 assert np.array_equal(a, b) if exact else np.max(np.abs(a - b)) <= 1e-13 * max(np.max(np.abs(w.get_f())), 1e-300), name
         elif op == "probe":
             ix, iy, iz = (int(rng.integers(1, n + 1)) for n in (nx, ny, nz))
-            pr = sim.probe(ix, iy, iz)
-            ref = np.array([w.get(name)[iz - 1, iy - 1, ix - 1] for name in ("rho", "ux", "uy", "uz")])
-            assert np.array_equal(pr, ref) if exact else np.max(np.abs(pr - ref)) <= 1e-13
+            if sim.globalz < iz <= sim.globalz + sim.lz:
+                pr = sim.probe(ix, iy, iz - sim.globalz)
+                ref = np.array([w.get(name)[iz - 1, iy - 1, ix - 1] for name in ("rho", "ux", "uy", "uz")])
+                assert np.array_equal(pr, ref) if exact else np.max(np.abs(pr - ref)) <= 1e-13
         elif op == "sums":
             got = sim.profiles()
             ref, _ = orc.plane_sums(w)
@@ -66,7 +86,7 @@ def run_sequence(seed, scheme, log):
         elif op == "reupload":
             f = w.get_f() + 1e-5 * rng.normal(size=shp + (19,))
             w.set_f(f); w.macrovar()
-            sim.upload_f(np.ascontiguousarray(f))
+            sim.upload_f(np.ascontiguousarray(f[sl]))
             exact = True
         elif op == "force":
             F = [float(t) for t in 1e-6 * rng.normal(size=3)]
@@ -78,13 +98,13 @@ def run_sequence(seed, scheme, log):
             F = [1e-6 * rng.normal(size=shp) for _ in range(3)]
             for name, a in zip(("fx", "fy", "fz"), F):
                 w.set(name, a)
-            sim.set_force_field(*F)
+            sim.set_force_field(*[np.ascontiguousarray(a[sl]) for a in F])
             w.macrovar()
         elif op == "external":
             macro = [1e-4 * rng.normal(size=shp)] + [0.01 * rng.normal(size=shp) for _ in range(3)]
             for name, a in zip(("rho", "ux", "uy", "uz"), macro):
                 w.set(name, a)
-            sim.set_macro(*macro)
+            sim.set_macro(*[np.ascontiguousarray(a[sl]) for a in macro])
             w.collision_MRT(); w.macrovar()
             sim.collide_stream(capi.MACRO_EXTERNAL)
         elif op == "prerelax":
@@ -102,8 +122,8 @@ def run_sequence(seed, scheme, log):
             sim.collide_stream()
             exact = False
     sim.download_f(out)
-    ref = w.get_f()
-    assert np.array_equal(out, ref) if exact else np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref))
+    ref = w.get_f()[sl]
+    assert np.array_equal(out, ref) if exact else np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(w.get_f()))
     sim.close(); w.close()
 
 
