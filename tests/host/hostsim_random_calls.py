@@ -150,7 +150,7 @@ def run_shim_sequence(seed, scheme, log):
             assert np.array_equal(getattr(sim, k), w.get(k)), (what, k)
 
     for seg in range(6):
-        op = ["loop", "loop", "rewrite", "prerelax", "save"][int(rng.integers(5))]
+        op = ["loop", "loop", "rewrite", "prerelax", "save", "checkpoint"][int(rng.integers(6))]
         log.append((seed, scheme, (nx, ny, nz), seg, "shim:" + op))
         if op == "loop":
             nsteps = int(rng.integers(1, 14))
@@ -182,6 +182,19 @@ def run_shim_sequence(seed, scheme, log):
                 w.rhoupdat(); w.collision_MRT()
                 sim.rhoupdat(); sim.collision_MRT()
                 assert np.array_equal(sim.rho, w.get("rho")), "rho after rhoupdat"
+        elif op == "checkpoint":
+            # savecntdflow (saveload.f90:196-231), then a NEW run on the other storage scheme restarts from the file
+            import tempfile
+            with tempfile.TemporaryDirectory() as d:
+                pkg.saveload.savecntdflow(sim, d, istat=3, imovie=1)
+                istep = sim.v.istep0 + sim.v.nsteps
+                sim.close()
+                scheme = capi.SCHEME_AB if scheme == capi.SCHEME_AA else capi.SCHEME_AA
+                sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT, ndiag=ndiag,
+                                      nflowout=nflowout, **U)
+                assert pkg.saveload.loadcntdflow(sim, d, istep) == (istep, 3, 1)
+            sim.FORCING()
+            assert np.array_equal(sim.f, w.get_f()), "checkpoint payload"
         else:
             got = sim.sync_f_to_host()
             assert np.array_equal(got, w.get_f()), "sync_f_to_host"
