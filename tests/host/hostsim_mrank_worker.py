@@ -348,6 +348,15 @@ def section_random(rank, world, comm, chk, ctx):
             except AssertionError:
                 chk("random sequence, last calls %r\n%s" % (log[-6:], traceback.format_exc()), False)
                 raise                      # the ranks have left lockstep: stop the run
+    for seed in range(int(os.environ.get("HOSTSIM_PARTICLE_SEEDS", "1"))):
+        for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
+            ctx[0] = "random particle sequence seed %d scheme %d" % (seed, scheme)
+            log = []
+            try:
+                rc.run_particle_sequence(seed, scheme, log, rank=rank, world=world, comm=comm)
+            except AssertionError:
+                chk("random particle sequence, last calls %r\n%s" % (log[-6:], traceback.format_exc()), False)
+                raise
     comm.bar.wait()
     if rank == 0:
         for k in ("D3Q19_BOUNDARY_STREAM", "D3Q19_DIRECT_FACES", "D3Q19_HALO_SPLIT_MIN"):

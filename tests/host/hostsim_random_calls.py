@@ -202,21 +202,23 @@ def run_shim_sequence(seed, scheme, log):
     sim.close(); w.close()
 
 
-def run_particle_sequence(seed, scheme, log):
+def run_particle_sequence(seed, scheme, log, rank=0, world=1, comm=None):
     """the particle entry points in random order: fixed and moving particle steps, macrovar with the solid branch,
     avedensity over the fluid nodes, diag and the masked plane sums, link list and mask read-backs -- against
     oracle/particles_oracle.c + the fluid oracle (parity unpinned against the reference: partlib.f90 is absent)"""
     from oracle import particles as P
     rng = np.random.default_rng(2000 + seed)
-    nx, ny, nz, rad = 20, 16, 18, 3.3
+    nx, ny, nz, rad = 20, 16, 18 if world == 1 else 7 * world, 3.3
     U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
-    pos = [[9.7, 1.2 + 3 * rng.random(), 16.9], [5.1 + 2 * rng.random(), 10.0, 8.0]]
+    pos = [[9.7, 1.2 + 3 * rng.random(), nz - 1.1], [5.1 + 2 * rng.random(), 10.0, 7.2]]      # both cut by slab faces
     vel = [list(0.02 * (rng.random(3) - 0.5)) for _ in range(2)]
     omg = [list(2e-3 * (rng.random(3) - 0.5)) for _ in range(2)]
     w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True, ipart=1, **U)
-    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_FAST, ipart=True, **U)
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_FAST, ipart=True, rank=rank,
+                          nranks=world, device=0, nccl_id=comm.new_id(rank) if world > 1 else None, **U)
+    sl = slice(sim.globalz, sim.globalz + sim.lz)
     sim.FORCING()
-    sim.upload_f(w.get_f())
+    sim.upload_f(np.ascontiguousarray(w.get_f()[sl]))
     pt = P.Particles(nx, ny, nz, rad, pos, vel, omg)
     sim.particles_init(pos, rad, vel, omg)
     pt.build_mask(); pt.build_links()
@@ -226,14 +228,14 @@ def run_particle_sequence(seed, scheme, log):
         w.set_particles(pt.ypglb, pt.wp, pt.omgp)
     oracle_mask()
     w.macrovar()
-    out = np.empty((nz, ny, nx, 19))
+    out = np.empty((sim.lz, ny, nx, 19))
     tol = 1e-11
 
     def fields_agree(what, f):
         nonlocal tol
-        fluid = pt.own < 0
+        fluid = pt.own[sl] < 0
         sim.download_f(out)
-        err = np.max(np.abs(out[fluid] - f[fluid])) / np.max(np.abs(f[fluid]))
+        err = np.max(np.abs(out[fluid] - f[sl][fluid])) / np.max(np.abs(f[pt.own < 0]))
         assert err < tol, (what, err)
 
     for seg in range(7):
@@ -256,13 +258,13 @@ def run_particle_sequence(seed, scheme, log):
             tol = 1e-8                                   # refills extrapolate: differences of 1e-12 grow a little
             g = sim.get_particles()
             assert np.max(np.abs(g["ypglb"] - pt.ypglb)) < 1e-10
-            assert np.array_equal(sim.get_mask(), pt.own)
+            assert np.array_equal(sim.get_mask(), pt.own[sl])
             fields_agree("moving", f)
         elif op == "macro":
             sim.device_macrovar()
-            solid = pt.own > 0
+            solid = pt.own[sl] > 0
             for name in ("rho", "ux", "uy", "uz"):
-                a, b = getattr(sim, name), w.get(name)
+                a, b = getattr(sim, name), w.get(name)[sl]
                 assert np.max(np.abs(a[~solid] - b[~solid])) <= tol * max(np.max(np.abs(b)), 1e-30), name
                 assert np.max(np.abs(a[solid] - b[solid])) <= 1e-9 * max(np.max(np.abs(b)), 1e-30), name   # rigid-body velocity
         elif op == "avedensity":
@@ -285,10 +287,11 @@ def run_particle_sequence(seed, scheme, log):
         else:
             n = sim.beads_links()
             gl = sim.get_links()
-            assert n == len(pt.links["q"])
+            mine = (pt.links["z"] > sim.globalz) & (pt.links["z"] <= sim.globalz + sim.lz)      # the links whose fluid node I own
+            assert n == int(mine.sum())
             for key in ("x", "y", "z", "ip", "part"):
-                assert np.array_equal(gl[key], pt.links[key]), key
-            assert np.array_equal(sim.get_mask(), pt.own)
+                assert np.array_equal(gl[key], pt.links[key][mine]), key
+            assert np.array_equal(sim.get_mask(), pt.own[sl])
     sim.close(); w.close()
 
 
