@@ -52,7 +52,7 @@ def test_single_rank_gpu_test_files_pass_on_the_host_sim(hostsim):
 def test_multi_rank_orchestration_on_the_host_sim(hostsim, world):
     # 3 ranks: every case of the worker; 2 ranks (both neighbours are the same rank): one uneven case per transport
     extra = {"HOSTSIM_SHORT": "1"} if world == 2 else {}
-    sections = ["fluid", "shim", "particles"] if world == 2 else []            # none named = all of them
+    sections = ["fluid", "shim", "particles", "random"] if world == 2 else []            # none named = all of them
     res = run([sys.executable, os.path.join("tests", "host", "hostsim_mrank_worker.py"), str(world)] + sections, hostsim, **extra)
     assert res.returncode == 0 and "HOSTSIM_MRANK_OK" in res.stdout, res.stdout[-4000:]
 
