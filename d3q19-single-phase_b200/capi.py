@@ -9,7 +9,9 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("D3Q19_LIB") or os.path.join(HERE, "libd3q19b200.so")   # D3Q19_LIB: kernel-variant experiments
+# D3Q19_LIB: another BUILD OF THE SAME LIBRARY -- kernel-variant sweeps (tools/kernel_sweep.py) and, on the GPU-less build box
+# only, the tests' host-sim build of csrc/d3q19_api.cu (tests/host/make_hostsim.py; the package never builds or looks for it)
+LIB_PATH = os.environ.get("D3Q19_LIB") or os.path.join(HERE, "libd3q19b200.so")
 
 ABI_VERSION = 1
 SCHEME_AA, SCHEME_AB, SCHEME_AUTO = 0, 1, 2
