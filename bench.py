@@ -62,7 +62,7 @@ def parse_args():
                     help="NCCL transport, opt-in: launch the two boundary planes of a step on their own high-priority stream next "
                          "to the interior launch instead of in front of it (D3Q19_BOUNDARY_STREAM=1)")
     ap.add_argument("--vec2", action="store_true",
-                    help="experiment: the main-loop AB step with two nodes per thread and 128-bit loads/stores (D3Q19_VEC2=1)")
+                    help="experiment: the main-loop steps with two nodes per thread and 128-bit loads/stores (D3Q19_VEC2=1)")
     ap.add_argument("--direct-faces", action="store_true",
                     help="NCCL transport, opt-in: send the five crossing populations of a face straight out of the population "
                          "array and receive them in place (20 sends/receives in one group, no pack / unpack kernels; "
@@ -397,8 +397,8 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "bytes_per_node": BYTES_PER_NODE, "peak_source": peak_src,
-                "kernel": ("k_step_ab2<two nodes per thread, 128-bit>" if args.vec2 and args.scheme == "ab" and nx % 2 == 0 and
-                           args.math == "fast" and args.particles == 0
+                "kernel": (("k_step_ab2" if args.scheme == "ab" else "k_step_aa2<even/odd>") + " (two nodes per thread, 128-bit)"
+                           if args.vec2 and nx % 2 == 0 and args.math == "fast" and args.particles == 0
                            else "k_step<%s>" % ("AA even/odd" if args.scheme == "aa" else "AB pull"))}
 
     # ---- end to end through the reference-facing interface, host buffers ------------------------

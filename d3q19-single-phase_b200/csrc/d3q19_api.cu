@@ -95,7 +95,7 @@ struct d3q19_handle {
     // opt-in (D3Q19_DIRECT_FACES=1): faces travel straight out of / into the population array (a population's plane is
     // contiguous), 10 sends + 10 receives in one NCCL group, no pack / unpack kernels (exchange_faces)
     bool direct_faces = false;
-    // experiment (D3Q19_VEC2=1): the main-loop AB step with two nodes per thread and 128-bit accesses (k_step_ab2)
+    // experiment (D3Q19_VEC2=1): the main-loop steps with two nodes per thread and 128-bit accesses (k_step_ab2, k_step_aa2)
     bool vec2 = false;
     // optional per-step timeline (d3q19_trace_enable): 4 timing events per step -- [0] before the boundary launch,
     // [1] after it, [2] after the interior launch (all on sc), [3] after the exchange / put (on sx)
@@ -826,10 +826,18 @@ static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int 
     StepParams p = p0;
     p.z0 = z0;
     p.zstride = zstride;
-    if (h->vec2 && SK == STEP_AB && !STRICT && !GENERIC && h->g.lx % 2 == 0) {
+    if (h->vec2 && !STRICT && !GENERIC && h->g.lx % 2 == 0) {
         const dim3 g2((unsigned)((h->g.lx + 2 * BLOCK_X - 1) / (2 * BLOCK_X)), (unsigned)h->g.ly, (unsigned)nplanes);
-        if (h->idx32) k_step_ab2<uint32_t><<<g2, BLOCK_X, 0, s>>>(p);
-        else k_step_ab2<unsigned long long><<<g2, BLOCK_X, 0, s>>>(p);
+        if (SK == STEP_AB) {
+            if (h->idx32) k_step_ab2<uint32_t><<<g2, BLOCK_X, 0, s>>>(p);
+            else k_step_ab2<unsigned long long><<<g2, BLOCK_X, 0, s>>>(p);
+        } else if (SK == STEP_AA_EVEN) {
+            if (h->idx32) k_step_aa2<false, uint32_t><<<g2, BLOCK_X, 0, s>>>(p);
+            else k_step_aa2<false, unsigned long long><<<g2, BLOCK_X, 0, s>>>(p);
+        } else {
+            if (h->idx32) k_step_aa2<true, uint32_t><<<g2, BLOCK_X, 0, s>>>(p);
+            else k_step_aa2<true, unsigned long long><<<g2, BLOCK_X, 0, s>>>(p);
+        }
         CK(cudaGetLastError());
         h->n_step_kernels++;
         return 0;

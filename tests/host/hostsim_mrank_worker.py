@@ -286,12 +286,13 @@ def section_shim(rank, world, comm, chk, ctx):
 
 
 def section_vec2(rank, world, comm, chk, ctx):
-    """experiment D3Q19_VEC2=1 (k_step_ab2: two nodes per thread, 128-bit accesses): the same FAST arithmetic on the
-    same inputs, so bit-identical to the one-node-per-thread step -- walls, odd lx (falls back), several x-blocks,
-    boundary / interior launches of the slab run"""
-    for (nx, ny, nz) in [(24, 6, 4 * world), (34, 5, 3 * world + 1), (130, 3, 2 * world + 1), (23, 4, 2 * world), (516, 2, world + 1),
-                         (2, 3, world + 2)]:
-        ctx[0] = "vec2 case %s" % ((nx, ny, nz),)
+    """experiment D3Q19_VEC2=1 (k_step_ab2 / k_step_aa2: two nodes per thread, 128-bit accesses): the same FAST
+    arithmetic on the same inputs, so bit-identical to the one-node-per-thread steps -- walls, odd lx (falls back),
+    several x-blocks and warps per row, boundary / interior launches of the slab run, both storage schemes"""
+    shapes = [(24, 6, 4 * world), (34, 5, 3 * world + 1), (130, 3, 2 * world + 1), (23, 4, 2 * world), (516, 2, world + 1),
+              (2, 3, world + 2), (64, 1, world), (66, 2, 2 * world)]
+    for (nx, ny, nz), scheme in [(sh, sc) for sh in shapes for sc in (capi.SCHEME_AB, capi.SCHEME_AA)]:
+        ctx[0] = "vec2 case %s scheme %d" % ((nx, ny, nz), scheme)
         w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
         w.set_f(w.get_f() + 1e-4 * np.random.default_rng(7).normal(size=(nz, ny, nx, 19)))
         sims = []
@@ -302,7 +303,7 @@ def section_vec2(rank, world, comm, chk, ctx):
                 if v2:
                     os.environ["D3Q19_VEC2"] = "1"
             comm.bar.wait()
-            sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=capi.SCHEME_AB,
+            sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=scheme,
                                   math_mode=capi.MATH_FAST, nccl_id=comm.new_id(rank) if world > 1 else None)
             sim.FORCING()
             z0, z1 = sim.globalz, sim.globalz + sim.lz
@@ -311,7 +312,7 @@ def section_vec2(rank, world, comm, chk, ctx):
         a, b = sims
         oa, ob = np.empty((a.lz, ny, nx, 19)), np.empty((a.lz, ny, nx, 19))
         w.macrovar()
-        for burst in (1, 2, 3):
+        for burst in (1, 2, 3, 1):                   # readers meet both in-place phases
             for _ in range(burst):
                 w.collision_MRT(); w.macrovar()
             a.run_device(burst); b.run_device(burst)

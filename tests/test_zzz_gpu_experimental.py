@@ -36,9 +36,10 @@ def test_refill_is_decomposition_invariant(world):
     assert res.returncode == 0 and "MGPU_PARITY_OK" in res.stdout, res.stdout[-4000:]
 
 
+@pytest.mark.parametrize("scheme_name", ["ab", "aa"])
 @pytest.mark.parametrize("shape", [(64, 8, 8), (130, 8, 6), (516, 4, 5)])
-def test_vec2_step_matches_the_64bit_step(shape):
-    # D3Q19_VEC2=1: k_step_ab2 (two nodes per thread, 128-bit accesses) runs the same collide_fast on the same values;
+def test_vec2_step_matches_the_64bit_step(shape, scheme_name):
+    # D3Q19_VEC2=1: k_step_ab2 / k_step_aa2 (two nodes per thread, 128-bit accesses) run the same collide_fast on the same values;
     # on the host build it is bit-identical, on the device nvcc may contract the inlined arithmetic differently
     import numpy as np
     from oracle import oracle as orc
@@ -52,7 +53,8 @@ def test_vec2_step_matches_the_64bit_step(shape):
         if v2:
             os.environ["D3Q19_VEC2"] = "1"
         try:
-            sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=capi.SCHEME_AB, math_mode=capi.MATH_FAST)
+            sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=capi.SCHEME_AB if scheme_name == "ab" else capi.SCHEME_AA,
+                                  math_mode=capi.MATH_FAST)
         finally:
             os.environ.pop("D3Q19_VEC2", None)
         sim.FORCING()

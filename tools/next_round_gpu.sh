@@ -21,6 +21,7 @@ one)
     timeout 300 python bench.py --scheme aa --no-cpu > gpurun_out/${tag}_bench_aa.json 2>> gpurun_out/${tag}_bench.err
     # the 128-bit / two-nodes-per-thread AB step (k_step_ab2, 168 registers, 3 CTAs per SM): bench line + full capture
     timeout 300 python bench.py --vec2 --no-cpu --no-e2e > gpurun_out/${tag}_bench_vec2.json 2>> gpurun_out/${tag}_bench.err
+    timeout 300 python bench.py --vec2 --scheme aa --no-cpu --no-e2e > gpurun_out/${tag}_bench_vec2_aa.json 2>> gpurun_out/${tag}_bench.err
     D3Q19_VEC2=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_step_ab2 -s 4 -c 2 \
         -o gpurun_out/prof_${tag}_vec2 python tools/prof_step.py --scheme ab --steps 8 > /dev/null 2>&1
     # 3. launch list of the particle step (shares of the bookkeeping kernels) and of the plain step
