@@ -24,6 +24,8 @@ one)
     timeout 300 python bench.py --vec2 --scheme aa --no-cpu --no-e2e > gpurun_out/${tag}_bench_vec2_aa.json 2>> gpurun_out/${tag}_bench.err
     D3Q19_VEC2=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_step_ab2 -s 4 -c 2 \
         -o gpurun_out/prof_${tag}_vec2 python tools/prof_step.py --scheme ab --steps 8 > /dev/null 2>&1
+    D3Q19_VEC2=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_step_aa2 -s 4 -c 2 \
+        -o gpurun_out/prof_${tag}_vec2_aa python tools/prof_step.py --scheme aa --steps 8 > /dev/null 2>&1
     # 3. launch list of the particle step (shares of the bookkeeping kernels) and of the plain step
     timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${tag}_launches_particles.csv \
         python bench.py --particles 100 --no-cpu --no-e2e --steps 3 --warmup 1 > /dev/null 2>&1
