@@ -43,8 +43,11 @@ def run_sequence(seed, scheme, log, rank=0, world=1, comm=None, transport="nccl"
             if transport == "peer-split":
                 os.environ["D3Q19_HALO_SPLIT_MIN"] = "3"
         comm.bar.wait()
-    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_STRICT, rank=rank, nranks=world,
-                          device=0, nccl_id=comm.new_id(rank) if world > 1 else None, **U)
+    # HOSTSIM_FAST=1: production arithmetic (with D3Q19_VEC2=1 the main-loop steps are then the 128-bit kernels, mixed
+    # with the one-node-per-thread kernels of the run-time modes); agreement to rounding instead of bit for bit
+    fast = bool(os.environ.get("HOSTSIM_FAST"))
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_FAST if fast else capi.MATH_STRICT,
+                          rank=rank, nranks=world, device=0, nccl_id=comm.new_id(rank) if world > 1 else None, **U)
     sim.FORCING()
     if transport in ("peer", "peer-split", "put"):
         assert sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if transport == "put" else "fused")
@@ -52,7 +55,8 @@ def run_sequence(seed, scheme, log, rank=0, world=1, comm=None, transport="nccl"
     sim.upload_f(np.ascontiguousarray(w.get_f()[sl]))
     shp, lshp = (nz, ny, nx), (sim.lz, ny, nx)
     out = np.empty(lshp + (19,))
-    exact = True                      # False between an avedensity and the next re-upload (order-dependent mean)
+    exact = not fast                  # False between an avedensity and the next re-upload (order-dependent mean)
+    rtol = 1e-11 if fast else 1e-13
     ops = ["step", "step", "step", "download", "macro", "probe", "sums", "reupload", "force", "field", "external", "prerelax",
            "avedensity"]
     for k in range(40 if world == 1 else 25):
@@ -66,18 +70,18 @@ def run_sequence(seed, scheme, log, rank=0, world=1, comm=None, transport="nccl"
         elif op == "download":
             sim.download_f(out)
             ref = w.get_f()[sl]
-            assert np.array_equal(out, ref) if exact else np.max(np.abs(out - ref)) <= 1e-13 * np.max(np.abs(w.get_f()))
+            assert np.array_equal(out, ref) if exact else np.max(np.abs(out - ref)) <= rtol * np.max(np.abs(w.get_f()))
         elif op == "macro":
             sim.device_macrovar()
             for name in ("rho", "ux", "uy", "uz"):
                 a, b = getattr(sim, name), w.get(name)[sl]
-                assert np.array_equal(a, b) if exact else np.max(np.abs(a - b)) <= 1e-13 * max(np.max(np.abs(w.get_f())), 1e-300), name
+                assert np.array_equal(a, b) if exact else np.max(np.abs(a - b)) <= rtol * max(np.max(np.abs(w.get_f())), 1e-300), name
         elif op == "probe":
             ix, iy, iz = (int(rng.integers(1, n + 1)) for n in (nx, ny, nz))
             if sim.globalz < iz <= sim.globalz + sim.lz:
                 pr = sim.probe(ix, iy, iz - sim.globalz)
                 ref = np.array([w.get(name)[iz - 1, iy - 1, ix - 1] for name in ("rho", "ux", "uy", "uz")])
-                assert np.array_equal(pr, ref) if exact else np.max(np.abs(pr - ref)) <= 1e-13
+                assert np.array_equal(pr, ref) if exact else np.max(np.abs(pr - ref)) <= rtol
         elif op == "sums":
             got = sim.profiles()
             ref, _ = orc.plane_sums(w)
@@ -87,7 +91,7 @@ def run_sequence(seed, scheme, log, rank=0, world=1, comm=None, transport="nccl"
             f = w.get_f() + 1e-5 * rng.normal(size=shp + (19,))
             w.set_f(f); w.macrovar()
             sim.upload_f(np.ascontiguousarray(f[sl]))
-            exact = True
+            exact = not fast
         elif op == "force":
             F = [float(t) for t in 1e-6 * rng.normal(size=3)]
             for name, v in zip(("fx", "fy", "fz"), F):
@@ -117,13 +121,13 @@ def run_sequence(seed, scheme, log, rank=0, world=1, comm=None, transport="nccl"
             mean_ref, n_ref = w.avedensity()
             m, n = C.c_double(0), C.c_int64(0)
             capi.check(sim.L.d3q19_avedensity(sim.h, C.byref(m), C.byref(n)))
-            assert n.value == n_ref and abs(m.value - mean_ref) <= 1e-13 * max(np.max(np.abs(w.get_f())), 1e-300)
+            assert n.value == n_ref and abs(m.value - mean_ref) <= rtol * max(np.max(np.abs(w.get_f())), 1e-300)
             w.collision_MRT(); w.macrovar()
             sim.collide_stream()
             exact = False
     sim.download_f(out)
     ref = w.get_f()[sl]
-    assert np.array_equal(out, ref) if exact else np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(w.get_f()))
+    assert np.array_equal(out, ref) if exact else np.max(np.abs(out - ref)) <= 10 * rtol * np.max(np.abs(w.get_f()))
     sim.close(); w.close()
 
 
