@@ -1,6 +1,6 @@
-"""The CUDA kernels of csrc/kernels.cuh compiled for the HOST (tests/host/kernels_host.cpp + a 60-line CUDA
-vocabulary, tests/host/fake/cuda_runtime.h) and run through the launch sequences of d3q19_api.cu: index logic of
-the three storage phases, wall select, y/z wraps, pitch padding, 32/64-bit indices, the five-population face
+"""The CUDA kernels of csrc/kernels.cuh and csrc/particles.cuh compiled for the HOST (tests/host/kernels_host.cpp + a
+small CUDA vocabulary, tests/host/fake/cuda_runtime.h: launches as loop nests, cooperating blocks as fibers) and run
+through the launch sequences of d3q19_api.cu: index logic of the three storage phases, wall select, y/z wraps, pitch padding, 32/64-bit indices, the five-population face
 pack/unpack, the send-back after an in-place odd step and the stores into a neighbour's array of the peer-memory
 and "put" halos -- all bit for bit against the oracle, without a GPU.  The GPU suite (tests/test_gpu_*.py) proves
 the same through the C-ABI on the device; this file keeps the kernels' logic checked on the build box.
