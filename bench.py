@@ -236,6 +236,8 @@ def main():
     capi = pkg.capi
     if not torch.cuda.is_available() or capi.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if capi.is_hostsim() and os.environ.get("D3Q19_HOSTSIM_BENCH_STRUCTURE_TEST") != "1":
+        raise SystemExit("bench.py: D3Q19_LIB points at the tests' host-sim build; it is never benchmarked")
     torch.cuda.set_device(local_rank)
     nccl_id = None
     if world > 1:

@@ -86,6 +86,15 @@ class D3Q19Error(RuntimeError):
 _lib = None
 
 
+def is_hostsim(L=None):
+    """True when the loaded library is the tests' host-sim build (it alone exports d3q19_hostsim_marker)"""
+    L = L if L is not None else _lib
+    try:
+        return L is not None and getattr(L, "d3q19_hostsim_marker") is not None
+    except AttributeError:
+        return False
+
+
 def load():
     """dlopen the CUDA library; raises if it has not been built (no fallback)."""
     global _lib
@@ -96,6 +105,11 @@ def load():
             "libd3q19b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`; "
             "this package has no CPU fallback." % LIB_PATH)
     L = C.CDLL(LIB_PATH)
+    if is_hostsim(L):
+        # only the tests' host-sim build exports this marker (tests/host/make_hostsim.py): never silent
+        import sys
+        sys.stderr.write("d3q19_b200: %s is the HOST-SIM test build -- the lattice is stepped on the CPU; nothing it "
+                         "prints is a GPU result or a timing\n" % LIB_PATH)
     dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
     L.d3q19_last_error.restype = C.c_char_p
     L.d3q19_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]

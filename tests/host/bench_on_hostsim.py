@@ -8,6 +8,7 @@ import sys
 
 import torch
 
+os.environ["D3Q19_HOSTSIM_BENCH_STRUCTURE_TEST"] = "1"      # bench.py refuses the host-sim build otherwise
 torch.cuda.is_available = lambda: True
 torch.cuda.set_device = lambda *a, **k: None
 torch.Tensor.pin_memory = lambda self, *a, **k: self

@@ -47,6 +47,7 @@ class Comm:
     def fail(self, rank, what):
         with self.lock:
             self.failed.append("rank %d: %s" % (rank, what))
+            print("rank %d: %s" % (rank, what), flush=True)       # at once: the other ranks may hang in a collective now
 
 
 def section_fluid(rank, world, comm, chk, ctx):
@@ -346,7 +347,7 @@ def section_random(rank, world, comm, chk, ctx):
             log = []
             try:
                 rc.run_sequence(500 + seed, scheme, log, rank=rank, world=world, comm=comm, transport=tr)
-            except AssertionError:
+            except Exception:
                 chk("random sequence, last calls %r\n%s" % (log[-6:], traceback.format_exc()), False)
                 raise                      # the ranks have left lockstep: stop the run
     for seed in range(int(os.environ.get("HOSTSIM_PARTICLE_SEEDS", "1"))):
@@ -355,7 +356,7 @@ def section_random(rank, world, comm, chk, ctx):
             log = []
             try:
                 rc.run_particle_sequence(seed, scheme, log, rank=rank, world=world, comm=comm)
-            except AssertionError:
+            except Exception:
                 chk("random particle sequence, last calls %r\n%s" % (log[-6:], traceback.format_exc()), False)
                 raise
     comm.bar.wait()
@@ -380,7 +381,9 @@ def rank_main(rank, world, comm, sections):
             SECTIONS[s](rank, world, comm, chk, ctx)
     except Exception:
         comm.fail(rank, "EXCEPTION [%s]\n%s" % (ctx[0], traceback.format_exc()))
-        comm.bar.abort()
+        # the other ranks are (or will be) waiting for this one in a barrier or a collective: end the whole run here
+        print("HOSTSIM_MRANK_FAILED", flush=True)
+        os._exit(1)
 
 
 def main():

@@ -270,7 +270,8 @@ def run_particle_sequence(seed, scheme, log, rank=0, world=1, comm=None):
             for name in ("rho", "ux", "uy", "uz"):
                 a, b = getattr(sim, name), w.get(name)[sl]
                 assert np.max(np.abs(a[~solid] - b[~solid])) <= tol * max(np.max(np.abs(b)), 1e-30), name
-                assert np.max(np.abs(a[solid] - b[solid])) <= 1e-9 * max(np.max(np.abs(b)), 1e-30), name   # rigid-body velocity
+                if solid.any():                           # (a thin slab may hold no solid node)
+                    assert np.max(np.abs(a[solid] - b[solid])) <= 1e-9 * max(np.max(np.abs(b)), 1e-30), name   # rigid-body velocity
         elif op == "avedensity":
             sim.device_macrovar(download=False)
             mean_ref, n_ref = w.avedensity()
