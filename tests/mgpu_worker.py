@@ -181,7 +181,7 @@ def main():
     # particle path across slab faces: links partition exactly, IBB + forces as on one domain
     # (MGPU_ONLY=refill: just this section, with the moving-particle forces held to the single-domain tolerance --
     #  the refill takes its source nodes across a slab face from the neighbour's planes since the exchange in
-    #  d3q19_beads_filling; run from tests/test_zzz_gpu_experimental.py until it has been seen on GPUs)
+    #  d3q19_beads_filling; run from tests/test_zzzz_gpu_experimental.py until it has been seen on GPUs)
     tight = only == "refill"
     if ok and (not only or tight):
         from oracle import particles as P

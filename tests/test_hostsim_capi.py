@@ -92,7 +92,7 @@ def test_bench_product_arm_prints_its_contract_line(hostsim, extra):
 
 def test_full_size_property_tests_and_experiments_on_the_host_sim(hostsim):
     # the logic of tests/test_zzz_gpu_fullsize.py on a shrunk channel, and the vec2 step of the experimental file
-    res = run([sys.executable, "-m", "pytest", "tests/test_zzz_gpu_fullsize.py", "tests/test_zzz_gpu_experimental.py", "-m", "gpu",
+    res = run([sys.executable, "-m", "pytest", "tests/test_zzz_gpu_fullsize.py", "tests/test_zzzz_gpu_experimental.py", "-m", "gpu",
                "-q", "-p", "no:cacheprovider", "-k", "not (vec2 and shape2)"],        # (the 516-wide vec2 case: the worker has it)
               hostsim, D3Q19_TEST_FULLSIZE="64x16x16")
     tail = res.stdout[-3000:]

@@ -41,7 +41,7 @@ one)
     ;;
 two)
     # the established multi-GPU suite first (its particle section now exchanges the refill source planes over NCCL)
-    timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_zzz_gpu_experimental.py -m gpu -q > gpurun_out/${tag}_pytest_gpu_2gpu.log 2>&1
+    timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_zzzz_gpu_experimental.py -m gpu -q > gpurun_out/${tag}_pytest_gpu_2gpu.log 2>&1
     tail -3 gpurun_out/${tag}_pytest_gpu_2gpu.log
     # boundary stream: parity first, then its effect on thin and thick slabs, then the timelines
     MGPU_ONLY=bstream timeout 600 $TR --nproc-per-node 2 --master-port 29611 tests/mgpu_worker.py > gpurun_out/${tag}_mgpu_bstream_n2.log 2>&1
