@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the bit-exact check of the reference's golden vector on this job's ranks before the timed region")
     ap.add_argument("--halo", default="nccl", choices=["peer", "put", "nccl"],
                     help="z-face exchange: NCCL send/recv of the packed faces on a second stream, overlapped with the interior "
                          "(default; equal or faster in every configuration measured, profiles/r01d_halo_transports.md) or "
@@ -61,8 +63,6 @@ def parse_args():
     ap.add_argument("--boundary-stream", action="store_true",
                     help="NCCL transport, opt-in: launch the two boundary planes of a step on their own high-priority stream next "
                          "to the interior launch instead of in front of it (D3Q19_BOUNDARY_STREAM=1)")
-    ap.add_argument("--vec2", action="store_true",
-                    help="experiment: the main-loop steps with two nodes per thread and 128-bit loads/stores (D3Q19_VEC2=1)")
     ap.add_argument("--direct-faces", action="store_true",
                     help="NCCL transport, opt-in: send the five crossing populations of a face straight out of the population "
                          "array and receive them in place (20 sends/receives in one group, no pack / unpack kernels; "
@@ -194,6 +194,100 @@ def cpu_reference_run(nx, ny, nz, steps, warmup):
             "ms_per_step": dt / steps * 1e3}
 
 
+# ---- parity of the path being timed, inside the run that times it ---------------------------------------
+def parity_check(pkg, rank, world, local_rank, fresh_nccl_id, connect, gather_ok, bcast, particles=True):
+    """Before the timed region: (a) the committed golden vector of the REFERENCE (tests/golden/ref_slabs_*.npz, made by
+    tests/golden/make_golden.py from the machine-translated Fortran; 16 z planes, 9 steps) run in STRICT arithmetic on
+    this job's ranks -- one z-slab per GPU, the halo transport the bench uses -- must come back BIT FOR BIT, in both
+    storage schemes, after 8 steps and after 9 (both in-place phases, the send-back after odd steps), with `macrovar`
+    and the all-reduced `avedensity` (collision.f90:337-370, :500-501); (b) a moving-particle case on the N slabs must
+    agree with the same case on ONE domain (run on rank 0's GPU) -- the particle path has no reference code (SURVEY
+    fact 2), what is checked is that the decomposition does not change the answer.  Raises on mismatch."""
+    import ctypes as C
+    import numpy as np
+    capi = pkg.capi
+    path = os.path.join(ROOT, "tests", "golden", "ref_slabs_21x4x16_r1x4_s9.npz")
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    nx, ny, nz = meta["nx"], meta["ny"], meta["nz"]
+    ustar = meta["overrides"]["ustar"]
+    kw = dict(ustar=ustar, force_in_y=2.0 * ustar * ustar / float(nx), ystar=0.0036 / ustar)     # para.f90:64-66
+    res = {"case": os.path.basename(path)[:-4], "ranks": world, "steps": meta["steps"], "schemes": [], "bit_exact": True}
+    if nz < world:
+        res.update(bit_exact=None, skipped="more ranks than z planes in the golden case")
+        return res
+    for name, scheme in (("aa", capi.SCHEME_AA), ("ab", capi.SCHEME_AB)):
+        sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local_rank, scheme=scheme,
+                              math_mode=capi.MATH_STRICT, nccl_id=fresh_nccl_id(), **kw)
+        for k, v in meta["scalars"].items():
+            if k != "mrttype" and getattr(sim.v, k) != v:
+                raise SystemExit("bench parity: scalar %s differs from the reference's para (%r vs %r)" % (k, getattr(sim.v, k), v))
+        connect(sim)
+        z0, z1 = sim.globalz, sim.globalz + sim.lz
+        sim.FORCING()
+        sim.upload_f(np.ascontiguousarray(z["f0"][z0:z1]))
+        out = np.empty((sim.lz, ny, nx, 19))
+        ok = True
+        sim.run_device(meta["snap"])
+        sim.download_f(out)
+        ok &= bool(np.array_equal(out, z["f_snap"][z0:z1]))
+        sim.run_device(meta["steps"] - meta["snap"])
+        sim.download_f(out)
+        ok &= bool(np.array_equal(out, z["f"][z0:z1]))
+        sim.device_macrovar()
+        for k in ("rho", "ux", "uy", "uz"):
+            ok &= bool(np.array_equal(getattr(sim, k), z[k][z0:z1]))
+        m, n = C.c_double(0), C.c_int64(0)
+        capi.check(sim.L.d3q19_avedensity(sim.h, C.byref(m), C.byref(n)))
+        mean_ref, scale = float(np.mean(z["rho"])), float(np.mean(np.abs(z["rho"])))
+        ok &= n.value == nx * ny * nz and abs(m.value - mean_ref) <= 1e-12 * scale     # the sum is order dependent
+        sim.close()
+        ok = gather_ok(ok)
+        res["schemes"].append({"scheme": name, "bit_exact": ok})
+        res["bit_exact"] = bool(res["bit_exact"] and ok)
+    if particles and world > 1:
+        # three spheres, two of them cut by slab faces; 3 resting + 6 moving steps (links, IBB, force all-reduce,
+        # lubrication, move, refill with its source exchange); N slabs against one domain
+        nx, ny, nz, rad = 24, 20, 8 * world, 3.6
+        U = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+        pos = [[11.7, 1.2, 8.0 * world - 0.9], [8.3, 12.0, 8.1], [15.5, 8.4, 4.2]]
+        vel = [[0.010, 0.020, -0.010], [0.0, 0.015, 0.0], [-0.005, 0.0, 0.012]]
+        omg = [[1e-3, 0.0, 2e-3], [0.0, -1e-3, 0.0], [5e-4, 5e-4, 0.0]]
+
+        def run_case(r, nr, dev, nid):
+            sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=r, nranks=nr, device=dev, scheme=capi.SCHEME_AB,
+                                  nccl_id=nid, ipart=True, **U)
+            sim.FORCING()
+            sim.init_channel_device(A9=0.3, noise_amp=1e-3 * sim.v.ustar, seed=777)
+            sim.particles_init(pos, rad, vel, omg)
+            for _ in range(3):
+                sim.particle_step(move=False)
+            for _ in range(6):
+                sim.particle_step(move=True)
+            out = np.empty((sim.lz, ny, nx, 19))
+            sim.download_f(out)
+            g = sim.get_particles()
+            mask = sim.get_mask()
+            span = (sim.globalz, sim.globalz + sim.lz)
+            sim.close()
+            return out, g, mask, span
+
+        ref = run_case(0, 1, local_rank, None) if rank == 0 else None
+        f_ref, g_ref, mask_ref = bcast(None if ref is None else (ref[0], ref[1], ref[2]))
+        out, g, mask, (z0, z1) = run_case(rank, world, local_rank, fresh_nccl_id())
+        fluid = mask_ref[z0:z1] < 0
+        ferr = float(np.max(np.abs(out[fluid] - f_ref[z0:z1][fluid])) / np.max(np.abs(f_ref)))
+        perr = float(np.max(np.abs(g["ypglb"] - g_ref["ypglb"])))
+        herr = float(np.max(np.abs(g["fHIp"] - g_ref["fHIp"])) / np.max(np.abs(g_ref["fHIp"])))
+        okp = bool(np.array_equal(mask, mask_ref[z0:z1])) and ferr < 1e-10 and perr < 1e-11 and herr < 1e-9
+        okp = gather_ok(okp)
+        res["particles"] = {"case": "3 moving spheres, %dx%dx%d, 9 steps, %d slabs vs 1 domain" % (nx, ny, nz, world),
+                            "mask_bit_exact": bool(np.array_equal(mask, mask_ref[z0:z1])), "f_rel_err": ferr,
+                            "position_err": perr, "force_rel_err": herr, "ok": okp}
+        res["bit_exact"] = bool(res["bit_exact"] and okp)
+    return res
+
+
 def main():
     args = parse_args()
     # rank 0 prints exactly ONE line on stdout: keep NCCL's "NCCL version ..." banner off it
@@ -288,8 +382,6 @@ def main():
         os.environ["D3Q19_BOUNDARY_STREAM"] = "1"
     if args.direct_faces and world > 1:
         os.environ["D3Q19_DIRECT_FACES"] = "1"
-    if args.vec2:
-        os.environ["D3Q19_VEC2"] = "1"
 
     def build_sim(halo_req, nccl_id):
         """the channel on this rank's slab with its synthetic initial state; returns (sim, halo actually in use)"""
@@ -330,6 +422,36 @@ def main():
             pos = np.array([slots[int(i * stride)] for i in range(args.particles)], dtype=np.float64)
             sim.particles_init(pos, args.rad)
         return sim, halo
+
+    # ---- parity of what is about to be timed: the reference's golden vector on this job's ranks and transport ----------
+    parity = None
+    if not args.no_parity:
+        def allgather_bytes_(b):
+            t = torch.tensor(list(b), dtype=torch.uint8)
+            out = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+            return [bytes(o.tolist()) for o in out]
+
+        def connect_(sim_):
+            if world > 1 and args.halo in ("peer", "put"):
+                if not sim_.connect_halo(allgather_bytes_, mode="put" if args.halo == "put" else "fused"):
+                    raise SystemExit("bench parity: peer-memory halo unavailable on this box")
+
+        def bcast_(obj):
+            if world == 1:
+                return obj
+            box = [obj]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+
+        parity = parity_check(pkg, rank, world, local_rank, fresh_nccl_id, connect_, all_ok, bcast_)
+        if parity["bit_exact"] is False:
+            if rank == 0:
+                sys.stderr.write("bench: PARITY CHECK FAILED before the timed region: %s\n" % json.dumps(parity))
+                print(json.dumps({"impl": "ours", "parity_check": parity, "error": "parity check failed; nothing was timed"}))
+            if world > 1:
+                dist.destroy_process_group()
+            return 3
 
     sim, halo = build_sim(args.halo, nccl_id)
     args.scheme = "ab" if sim.counters()["scheme"] == capi.SCHEME_AB else "aa"     # what AUTO resolved to
@@ -399,9 +521,7 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "bytes_per_node": BYTES_PER_NODE, "peak_source": peak_src,
-                "kernel": (("k_step_ab2" if args.scheme == "ab" else "k_step_aa2<even/odd>") + " (two nodes per thread, 128-bit)"
-                           if args.vec2 and nx % 2 == 0 and args.math == "fast" and args.particles == 0
-                           else "k_step<%s>" % ("AA even/odd" if args.scheme == "aa" else "AB pull"))}
+                "kernel": "k_step<%s>" % ("AA even/odd" if args.scheme == "aa" else "AB pull")}
 
     # ---- end to end through the reference-facing interface, host buffers ------------------------
     e2e = None
@@ -449,7 +569,7 @@ def main():
                                "D3Q19_BOUNDARY_STREAM") == "1" else "") + (", faces sent in place (no pack/unpack)" if os.environ.get(
                                "D3Q19_DIRECT_FACES") == "1" else "")}[halo])) if world > 1 else "1 GPU",
                        "l2": "populations %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (c1["population_bytes"] / 1e9)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "parity_check": parity,
             "clocks": clocks, "impl": "ours",
         }
         print(json.dumps(line))

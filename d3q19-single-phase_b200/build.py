@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libd3q19b200.so")
 SOURCES = ["d3q19_api.cu"]
-HEADERS = ["kernels.cuh", "collide.cuh", "lattice.cuh", "nccl_dl.h", os.path.join("..", "..", "include", "d3q19_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "d3q19_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

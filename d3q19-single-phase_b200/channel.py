@@ -386,10 +386,15 @@ class ChannelFlow:
         capi.check(self.L.d3q19_shim_set_schedule(self.h, v.ndiag, v.nflowout, v.nsteps, v.istep0))
 
     # ---- main.f90:142-208 -------------------------------------------------------------------
-    def run(self, nsteps=None, on_step=None, time_bond=None):
+    def run(self, nsteps=None, on_step=None, time_bond=None, allreduce_max=None):
         """the time loop; `time_bond` (seconds) is the wall-clock budget of main.f90:197-206: every `ntime` steps the
-        loop is left when it is spent (the shim makes rho,u current on those steps for `probe`)"""
+        loop is left when it is spent (the shim makes rho,u current on those steps for `probe`).  The reference decides
+        from the MPI_ALLREDUCE MAX of the elapsed time (main.f90:200-204) so that every rank leaves at the same step;
+        with nranks > 1 `allreduce_max(float) -> float` must do the same, otherwise the ranks would part ways and the
+        remaining ones hang in the halo exchange"""
         import time
+        if time_bond is not None and self.nranks > 1 and allreduce_max is None:
+            raise ValueError("run(time_bond=...) on %d ranks needs allreduce_max (main.f90:200-204)" % self.nranks)
         v = self.v
         nsteps = v.nsteps if nsteps is None else nsteps
         v.nsteps = nsteps
@@ -402,8 +407,12 @@ class ChannelFlow:
                 self.avedensity()
             if on_step:
                 on_step(self)
-            if time_bond is not None and self.istep % v.ntime == 0 and time.perf_counter() - t0 > time_bond:
-                break
+            if time_bond is not None and self.istep % v.ntime == 0:
+                elapsed = time.perf_counter() - t0
+                if allreduce_max is not None:
+                    elapsed = allreduce_max(elapsed)
+                if elapsed > time_bond:
+                    break
         return self.istep
 
     # ---- particles (the reference's beads_* phases; device-side bookkeeping) -----------------------

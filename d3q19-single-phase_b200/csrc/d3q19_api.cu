@@ -95,8 +95,6 @@ struct d3q19_handle {
     // opt-in (D3Q19_DIRECT_FACES=1): faces travel straight out of / into the population array (a population's plane is
     // contiguous), 10 sends + 10 receives in one NCCL group, no pack / unpack kernels (exchange_faces)
     bool direct_faces = false;
-    // experiment (D3Q19_VEC2=1): the main-loop steps with two nodes per thread and 128-bit accesses (k_step_ab2, k_step_aa2)
-    bool vec2 = false;
     // optional per-step timeline (d3q19_trace_enable): 4 timing events per step -- [0] before the boundary launch,
     // [1] after it, [2] after the interior launch (all on sc), [3] after the exchange / put (on sx)
     cudaEvent_t *trace_ev = nullptr;
@@ -110,6 +108,8 @@ struct d3q19_handle {
     double *red_d = nullptr;      // reduction partials
     long long *red_c = nullptr;
     double *prof_partial = nullptr, *prof_out = nullptr;
+    double *diag_partial = nullptr, *diag_red = nullptr;   // d3q19_diag scratch (allocated once: no cudaMalloc/cudaFree in the loop)
+    int diag_npartial = 0;
     int prof_chunks = 0, prof_rows = 0;
     long long n_step_kernels = 0, n_other_kernels = 0, n_nccl = 0, n_steps = 0;
     // particle path (particles.cuh)
@@ -201,6 +201,7 @@ static int wait_exchange(d3q19_handle *h) {
 // particle runs: whoever reads the solid mask (the step, macrovar, avedensity, diag, the plane sums) must see the mask of
 // the CURRENT particle table; d3q19_beads_links is a no-op while the table has not changed since the last build
 extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local);
+static int check_link_overflow(d3q19_handle *h, const char *who);
 static int ensure_mask(d3q19_handle *h) {
     if (h->part_on && !h->links_valid) return d3q19_beads_links(h, nullptr);
     return 0;
@@ -329,7 +330,7 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
     if (h->comm) nccl_api().CommDestroy(h->comm);
     void *ptrs[] = {h->A_alloc, h->B_alloc, h->rho, h->ux, h->uy, h->uz, h->ffx, h->ffy, h->ffz, h->solid, h->isn, h->ypglb,
                     h->wp, h->omgp, h->send_up, h->send_dn, h->recv_lo, h->recv_hi, h->stage[0], h->stage[1],
-                    h->scal, h->red_d, h->red_c, h->prof_partial, h->prof_out, h->vort, h->vort_halo};
+                    h->scal, h->red_d, h->red_c, h->prof_partial, h->prof_out, h->vort, h->vort_halo, h->diag_partial, h->diag_red};
     for (void *p : ptrs) if (p) cudaFree(p);
     cudaEvent_t evs[] = {h->evB, h->evX, h->evI, h->t0, h->t1, h->evC[0], h->evC[1], h->evS[0], h->evS[1]};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -407,7 +408,6 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
         const char *t = getenv("D3Q19_DIRECT_FACES");
         h->direct_faces = t && atoi(t) > 0;
     }
-    if (const char *t = getenv("D3Q19_VEC2")) h->vec2 = atoi(t) > 0;
     if (h->bstream) {
         CKH(cudaStreamCreateWithPriority(&h->sb, cudaStreamNonBlocking, hi));
         CKH(cudaEventCreateWithFlags(&h->evI, cudaEventDisableTiming));
@@ -463,7 +463,7 @@ extern "C" int d3q19_sync(d3q19_handle *h) {
                         "are void (a neighbour rank died or peer memory is broken)", h->cfg.rank,
                         (double)h->halo_timeout_ns * 1e-9, bad);
     }
-    return 0;
+    return check_link_overflow(h, "d3q19_sync");
 }
 
 // ---- halo in peer memory: cudaIpc bootstrap ---------------------------------------------------------------
@@ -629,6 +629,10 @@ extern "C" int d3q19_upload_f(d3q19_handle *h, const double *f_aos) {
         }
     }
     h->phase = 0;
+    // the shim's coherence flags live in the primitives, so that raw and shim calls can be mixed
+    h->shim.f_dev_valid = true;
+    h->shim.f_host_valid = h->shim.bound && f_aos == h->shim.a.f;
+    h->shim.macro_dev_valid = false;
     CK(cudaStreamSynchronize(h->sx));
     CK(cudaStreamSynchronize(h->sc));
     return halo_barrier(h);
@@ -661,11 +665,14 @@ extern "C" int d3q19_download_f(d3q19_handle *h, double *f_aos) {
     CK(cudaSetDevice(h->cfg.device));
     RK_(ensure_stage(h));
     RK_(wait_exchange(h));
+    int rc;
     switch (read_kind(h)) {
-    case READ_DIRECT: return download_f_impl<READ_DIRECT>(h, f_aos);
-    case READ_PULL_NAT: return download_f_impl<READ_PULL_NAT>(h, f_aos);
-    default: return download_f_impl<READ_PULL_SWAP>(h, f_aos);
+    case READ_DIRECT: rc = download_f_impl<READ_DIRECT>(h, f_aos); break;
+    case READ_PULL_NAT: rc = download_f_impl<READ_PULL_NAT>(h, f_aos); break;
+    default: rc = download_f_impl<READ_PULL_SWAP>(h, f_aos); break;
     }
+    if (rc == 0 && h->shim.bound && f_aos == h->shim.a.f) h->shim.f_host_valid = true;
+    return rc;
 }
 
 // pitched device field <-> host (lx,ly,lz) through the staging buffer
@@ -695,6 +702,7 @@ extern "C" int d3q19_set_macro(d3q19_handle *h, const double *rho, const double 
     RK_(field_from_host(h, h->rho, rho)); RK_(field_from_host(h, h->ux, ux));
     RK_(field_from_host(h, h->uy, uy)); RK_(field_from_host(h, h->uz, uz));
     CK(cudaStreamSynchronize(h->sc));
+    h->shim.macro_dev_valid = false;    // the device arrays are what the caller set, not the moments of f
     return 0;
 }
 
@@ -826,22 +834,6 @@ static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int 
     StepParams p = p0;
     p.z0 = z0;
     p.zstride = zstride;
-    if (h->vec2 && !STRICT && !GENERIC && h->g.lx % 2 == 0) {
-        const dim3 g2((unsigned)((h->g.lx + 2 * BLOCK_X - 1) / (2 * BLOCK_X)), (unsigned)h->g.ly, (unsigned)nplanes);
-        if (SK == STEP_AB) {
-            if (h->idx32) k_step_ab2<uint32_t><<<g2, BLOCK_X, 0, s>>>(p);
-            else k_step_ab2<unsigned long long><<<g2, BLOCK_X, 0, s>>>(p);
-        } else if (SK == STEP_AA_EVEN) {
-            if (h->idx32) k_step_aa2<false, uint32_t><<<g2, BLOCK_X, 0, s>>>(p);
-            else k_step_aa2<false, unsigned long long><<<g2, BLOCK_X, 0, s>>>(p);
-        } else {
-            if (h->idx32) k_step_aa2<true, uint32_t><<<g2, BLOCK_X, 0, s>>>(p);
-            else k_step_aa2<true, unsigned long long><<<g2, BLOCK_X, 0, s>>>(p);
-        }
-        CK(cudaGetLastError());
-        h->n_step_kernels++;
-        return 0;
-    }
     if (h->idx32) k_step<SK, STRICT, GENERIC, uint32_t><<<grid_nodes(h, nplanes), BLOCK_X, 0, s>>>(p);
     else k_step<SK, STRICT, GENERIC, unsigned long long><<<grid_nodes(h, nplanes), BLOCK_X, 0, s>>>(p);
     CK(cudaGetLastError());
@@ -1064,6 +1056,8 @@ static int collide_stream_impl(d3q19_handle *h, int macro_mode, unsigned long lo
     else rc = strict ? step_dispatch<true, false>(h, p) : step_dispatch<false, false>(h, p);
     if (rc) return rc;
     if (macro_mode == D3Q19_MACRO_MAIN) h->rho_shift = 0.0;   // the shift lives for one collision (macrovar recomputes rho)
+    h->shim.f_host_valid = false;       // also for the raw entry points (d3q19_run, d3q19_collide_stream, d3q19_prerelax)
+    h->shim.macro_dev_valid = false;
     return 0;
 }
 
@@ -1143,7 +1137,9 @@ static int macro_launch(d3q19_handle *h, int rho_only, unsigned long long *rhoer
 extern "C" int d3q19_macrovar(d3q19_handle *h) {
     CK(cudaSetDevice(h->cfg.device));
     h->rho_shift = 0.0;     // macrovar recomputes rho from f: a pending avedensity shift is gone (collision.f90:418)
-    return macro_launch(h, 0);
+    RK_(macro_launch(h, 0));
+    h->shim.macro_dev_valid = true;
+    return 0;
 }
 
 extern "C" int d3q19_rhoupdat(d3q19_handle *h) {
@@ -1250,21 +1246,26 @@ extern "C" int d3q19_set_solid_mask(d3q19_handle *h, const int32_t *ibnodes_ghos
     const size_t nb = h->nfield * sizeof(int32_t);
     if (!h->solid) CK(cudaMalloc(&h->solid, nb));
     const size_t nghost = (size_t)(g.lx + 2) * (g.ly + 2) * (g.lz + 2);
+    if (isnodes && !h->isn) CK(cudaMalloc(&h->isn, nb));
     int32_t *tmp = nullptr;
     CK(cudaMalloc(&tmp, nghost * sizeof(int32_t)));
-    CK(cudaMemcpyAsync(tmp, ibnodes_ghosted, nghost * sizeof(int32_t), cudaMemcpyHostToDevice, h->sc));
-    k_field_unpack_i32<<<grid_nodes(h, g.lz), BLOCK_X, 0, h->sc>>>(g.lx, g.xp, h->solid, tmp, 1, g.ly);
-    CK(cudaGetLastError());
-    h->n_other_kernels++;
-    if (isnodes) {
-        if (!h->isn) CK(cudaMalloc(&h->isn, nb));
-        CK(cudaMemcpyAsync(tmp, isnodes, (size_t)g.lx * g.ly * g.lz * sizeof(int32_t), cudaMemcpyHostToDevice, h->sc));
-        k_field_unpack_i32<<<grid_nodes(h, g.lz), BLOCK_X, 0, h->sc>>>(g.lx, g.xp, h->isn, tmp, 0, g.ly);
-        CK(cudaGetLastError());
+    cudaError_t e = cudaMemcpyAsync(tmp, ibnodes_ghosted, nghost * sizeof(int32_t), cudaMemcpyHostToDevice, h->sc);
+    if (e == cudaSuccess) {
+        k_field_unpack_i32<<<grid_nodes(h, g.lz), BLOCK_X, 0, h->sc>>>(g.lx, g.xp, h->solid, tmp, 1, g.ly);
+        e = cudaGetLastError();
         h->n_other_kernels++;
     }
-    CK(cudaStreamSynchronize(h->sc));
-    cudaFree(tmp);
+    if (e == cudaSuccess && isnodes) {
+        e = cudaMemcpyAsync(tmp, isnodes, (size_t)g.lx * g.ly * g.lz * sizeof(int32_t), cudaMemcpyHostToDevice, h->sc);
+        if (e == cudaSuccess) {
+            k_field_unpack_i32<<<grid_nodes(h, g.lz), BLOCK_X, 0, h->sc>>>(g.lx, g.xp, h->isn, tmp, 0, g.ly);
+            e = cudaGetLastError();
+            h->n_other_kernels++;
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->sc);
+    cudaFree(tmp);                      // also on the error paths
+    if (e != cudaSuccess) return fail("d3q19_set_solid_mask: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -1308,7 +1309,8 @@ extern "C" int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_
     CK(cudaMalloc(&h->links.q, h->maxlink * sizeof(double)));
     CK(cudaMalloc(&h->lcount, ((size_t)npart * PART_SPLIT + 1) * sizeof(long long)));
     CK(cudaMalloc(&h->loffset, ((size_t)npart * PART_SPLIT + 1) * sizeof(long long)));
-    CK(cudaMalloc(&h->nfilled_dev, sizeof(unsigned long long)));
+    CK(cudaMalloc(&h->nfilled_dev, 2 * sizeof(unsigned long long)));      // [0] refilled nodes, [1] link-list overflow word
+    CK(cudaMemsetAsync(h->nfilled_dev, 0, 2 * sizeof(unsigned long long), h->sc));
     const double volp = 4.0 / 3.0 * pi * prm->rad * prm->rad * prm->rad;      // para.f90:340
     h->amp = h->cfg.rhopart * volp;                                           // :341
     h->aip = 0.4 * h->amp * prm->rad * prm->rad;                              // :342
@@ -1352,6 +1354,17 @@ static int fetch_nlink(d3q19_handle *h) {
     return 0;
 }
 
+// k_beads_scan raises a device word when a link list did not fit (entries beyond maxlink are dropped by k_beads_links and
+// skipped by k_beads_ibb, which would let mass and momentum leak through the particle surface); call after a sync of sc
+static int check_link_overflow(d3q19_handle *h, const char *who) {
+    if (!h->part_on) return 0;
+    unsigned long long n = 0;
+    CK(cudaMemcpy(&n, h->nfilled_dev + 1, sizeof n, cudaMemcpyDeviceToHost));
+    if (n) return fail("%s: a step built %llu boundary links, capacity maxlink = %lld -- links were dropped, the populations "
+                       "are void (d3q19_particle_params.maxlink)", who, n, h->maxlink);
+    return 0;
+}
+
 // beads_links: solid mask from the particle table, then the boundary-link list
 extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local) {
     CK(cudaSetDevice(h->cfg.device));
@@ -1375,7 +1388,7 @@ extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local) {
     }
     const int nslot = h->npart * PART_SPLIT;
     k_beads_links<false><<<gp, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
-    k_beads_scan<<<1, 1024, 0, h->sc>>>(nslot, h->lcount, h->loffset);
+    k_beads_scan<<<1, 1024, 0, h->sc>>>(nslot, h->lcount, h->loffset, h->maxlink, h->nfilled_dev + 1);
     k_beads_links<true><<<gp, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
     CK(cudaGetLastError());
     h->n_other_kernels += 4;
@@ -1521,7 +1534,7 @@ extern "C" int d3q19_get_particles(d3q19_handle *h, double *ypglb, double *wp, d
     double *dst[5] = {ypglb, wp, omgp, fHIp, torqp};
     for (int i = 0; i < 5; ++i) if (dst[i]) CK(cudaMemcpyAsync(dst[i], src[i], tb, cudaMemcpyDeviceToHost, h->sc));
     CK(cudaStreamSynchronize(h->sc));
-    return 0;
+    return check_link_overflow(h, "d3q19_get_particles");
 }
 
 // the link list of this slab in list order: global 1-based node coordinates, direction, particle, q
@@ -1538,15 +1551,14 @@ extern "C" int d3q19_get_links(d3q19_handle *h, int64_t capacity, int32_t *x, in
     CK(cudaMalloc(&tmp, 3 * nb));
     k_links_export<<<(unsigned)((h->nlink + 127) / 128), 128, 0, h->sc>>>(h->g, h->cfg.globalz, h->nlink, h->links, tmp,
                                                                         tmp + h->nlink, tmp + 2 * h->nlink);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(x, tmp, nb, cudaMemcpyDeviceToHost, h->sc));
-    CK(cudaMemcpyAsync(y, tmp + h->nlink, nb, cudaMemcpyDeviceToHost, h->sc));
-    CK(cudaMemcpyAsync(z, tmp + 2 * h->nlink, nb, cudaMemcpyDeviceToHost, h->sc));
-    CK(cudaMemcpyAsync(ip, h->links.dir, nb, cudaMemcpyDeviceToHost, h->sc));
-    CK(cudaMemcpyAsync(part, h->links.part, nb, cudaMemcpyDeviceToHost, h->sc));
-    CK(cudaMemcpyAsync(q, h->links.q, (size_t)h->nlink * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
-    CK(cudaStreamSynchronize(h->sc));
-    cudaFree(tmp);
+    cudaError_t e = cudaGetLastError();
+    const void *src[6] = {tmp, tmp + h->nlink, tmp + 2 * h->nlink, h->links.dir, h->links.part, h->links.q};
+    void *dst[6] = {x, y, z, ip, part, q};
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+        e = cudaMemcpyAsync(dst[i], src[i], i < 5 ? nb : (size_t)h->nlink * sizeof(double), cudaMemcpyDeviceToHost, h->sc);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->sc);
+    cudaFree(tmp);                      // also on the error paths
+    if (e != cudaSuccess) return fail("d3q19_get_links: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -1614,8 +1626,12 @@ extern "C" int d3q19_diag(d3q19_handle *h, double ustar, double *out14) {
     chunks = (int)((nrows + rows - 1) / rows);
     const dim3 gr((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)chunks);
     const int npartial = (int)(gr.x * gr.y);
-    double *partial = nullptr;
-    CK(cudaMalloc(&partial, ((size_t)npartial + 1) * NDIAG * sizeof(double)));
+    if (!h->diag_partial || h->diag_npartial < npartial) {
+        if (h->diag_partial) { CK(cudaStreamSynchronize(h->sc)); cudaFree(h->diag_partial); h->diag_partial = nullptr; }
+        CK(cudaMalloc(&h->diag_partial, ((size_t)npartial + 1) * NDIAG * sizeof(double)));
+        h->diag_npartial = npartial;
+    }
+    double *partial = h->diag_partial;
     double *res = partial + (size_t)npartial * NDIAG;
     switch (read_kind(h)) {
     case READ_DIRECT: k_diag<READ_DIRECT><<<gr, BLOCK_X, 0, h->sc>>>(g, h->A, h->Fx, h->Fy, h->Fz, h->ffx, h->ffy, h->ffz, h->solid, rows, partial); break;
@@ -1628,7 +1644,6 @@ extern "C" int d3q19_diag(d3q19_handle *h, double ustar, double *out14) {
     double loc[NDIAG];
     CK(cudaMemcpyAsync(loc, res, sizeof loc, cudaMemcpyDeviceToHost, h->sc));
     CK(cudaStreamSynchronize(h->sc));
-    cudaFree(partial);
     // this rank's maximum in global coordinates (saveload.f90:1566-1574)
     double mine[4] = {loc[7], 0, 0, 0};
     if (loc[8] >= 0.0) {
@@ -1643,8 +1658,8 @@ extern "C" int d3q19_diag(d3q19_handle *h, double ustar, double *out14) {
     if (h->cfg.nranks > 1) {
         // MPI_ALLREDUCE of the sums, the per-rank maxima and rho extrema (saveload.f90:1544-1551,1582-1586,1617-1622)
         const int nr = h->cfg.nranks;
-        double *d = nullptr;
-        CK(cudaMalloc(&d, (size_t)(9 + 4 + 4 * nr) * sizeof(double)));
+        if (!h->diag_red) CK(cudaMalloc(&h->diag_red, (size_t)(9 + 4 + 4 * nr) * sizeof(double)));
+        double *d = h->diag_red;
         double pack[13] = {sums[0], sums[1], sums[2], sums[3], sums[4], sums[5], sums[6], rmax, -rmin, mine[0], mine[1], mine[2], mine[3]};
         CK(cudaMemcpyAsync(d, pack, sizeof pack, cudaMemcpyHostToDevice, h->sc));
         NcclApi &n = nccl_api();
@@ -1657,7 +1672,6 @@ extern "C" int d3q19_diag(d3q19_handle *h, double ustar, double *out14) {
         CK(cudaMemcpyAsync(pack, d, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
         CK(cudaMemcpyAsync(all.data(), d + 13, (size_t)4 * nr * sizeof(double), cudaMemcpyDeviceToHost, h->sc));
         CK(cudaStreamSynchronize(h->sc));
-        cudaFree(d);
         for (int q = 0; q < 7; ++q) sums[q] = pack[q];
         rmax = pack[7]; rmin = -pack[8];
     } else {

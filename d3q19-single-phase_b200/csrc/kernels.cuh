@@ -429,146 +429,11 @@ k_step(const __grid_constant__ StepParams p) {
     if (GENERIC && p.macro_mode == 1 && p.rhoerr_bits) block_max_to(p.rhoerr_bits, rhoerr);
 }
 
-// ---- AB step, two x-adjacent nodes per thread, 128-bit accesses (experiment, D3Q19_VEC2=1) -----------------------
-// The one-node-per-thread step above already moves exactly the algorithmic bytes (a warp reads and writes 256
-// contiguous bytes per population), so wider accesses cannot save DRAM traffic; what they change is the number of
-// load/store instructions per node (19 + 19 -> 9.5 + 9.5 and ten shuffles) and the bytes a thread keeps in flight
-// (38 x 8 B instead of 19 x 8 B at 3 instead of 4 resident CTAs per SM: +50 % per SM).  Since ncu shows these kernels
-// waiting on memory latency at 81-83 % of the DRAM peak, that is worth one measurement.  Main-loop instantiation only
-// (FAST arithmetic, uniform force, no mask, halo by NCCL or none), lx even.
-//   c_x = 0   populations: one aligned double2 at (x0, x0+1) of the source row;
-//   c_x = +1  (pulled from x-1): node x0+1 takes element x0 of the same aligned double2, node x0 takes element x0-1 =
-//             the previous lane's second element (shuffle; lane 0 loads it);
-//   c_x = -1  (pulled from x+1): node x0 takes element x0+1, node x0+1 takes x0+2 = the next lane's first element
-//             (shuffle; lane 31 loads it);
-//   at the walls the bounced population comes from the node's own opposite slot, as in Gather<>.
-#ifndef D3Q_MIN_BLOCKS_V2
-#define D3Q_MIN_BLOCKS_V2 3
-#endif
-template <class IDX>
-__global__ void __launch_bounds__(BLOCK_X, D3Q_MIN_BLOCKS_V2) k_step_ab2(const __grid_constant__ StepParams p) {
-    const Geom &g = p.g;
-    const int x0 = 2 * (int)(blockIdx.x * BLOCK_X + threadIdx.x);
-    const int y = blockIdx.y, zg = p.z0 + (int)blockIdx.z * p.zstride;
-    const int lane = threadIdx.x & 31;
-    const bool act0 = x0 < g.lx, act1 = x0 + 1 < g.lx;          // whole warps stay alive for the shuffles
-    const int ym = (y == 0) ? g.ly - 1 : y - 1, yp = (y == g.ly - 1) ? 0 : y + 1;
-    const int zm = (zg == 1) ? g.zlo_src : zg - 1, zp = (zg == g.lz) ? g.zhi_src : zg + 1;
-    const IDX oy[3] = {(IDX)ym * (IDX)g.xp, (IDX)y * (IDX)g.xp, (IDX)yp * (IDX)g.xp};
-    const IDX oz[3] = {(IDX)zm * (IDX)g.plane, (IDX)zg * (IDX)g.plane, (IDX)zp * (IDX)g.plane};
-    const IDX n0 = oy[1] + oz[1] + (IDX)x0;                      // own node x0 inside a population
-    double fa[NPOP], fb[NPOP];
-    static_for<NPOP>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        constexpr int cx = dir_cx(i), cy = dir_cy(i), cz = dir_cz(i), opp = dir_opp(i);
-        const double *src = p.A + (long long)i * g.slab + (long long)(oy[1 - cy] + oz[1 - cz]);      // source row, x = 0
-        double2 v = make_double2(0.0, 0.0);
-        if (act0) v = *reinterpret_cast<const double2 *>(src + x0);
-        if (cx == 0) {
-            fa[i] = v.x; fb[i] = v.y;
-        } else if (cx > 0) {
-            double left = __shfl_up_sync(0xffffffffu, v.y, 1);
-            if (lane == 0 && act0 && x0 > 0) left = src[x0 - 1];
-            fa[i] = left; fb[i] = v.x;
-            if (x0 == 0 && act0) fa[i] = p.A[(long long)opp * g.slab + (long long)n0];              // wall below node 0
-        } else {
-            double right = __shfl_down_sync(0xffffffffu, v.x, 1);
-            if (lane == 31 && x0 + 2 < g.lx) right = src[x0 + 2];
-            fa[i] = v.y; fb[i] = right;
-            if (x0 + 1 == g.lx - 1) fb[i] = p.A[(long long)opp * g.slab + (long long)n0 + 1];       // wall above node lx-1
-            if (x0 == g.lx - 1) fa[i] = p.A[(long long)opp * g.slab + (long long)n0];               // (lx odd)
-        }
-    });
-    if (!act0) return;
-    collide_fast<true>(fa, 0, 0, 0, 0, p.Fx, p.Fy, p.Fz, 0.0, p.mrt);
-    if (act1) collide_fast<true>(fb, 0, 0, 0, 0, p.Fx, p.Fy, p.Fz, 0.0, p.mrt);
-    static_for<NPOP>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        double *dst = p.B + (long long)i * g.slab + (long long)n0;
-        if (act1) *reinterpret_cast<double2 *>(dst) = make_double2(fa[i], fb[i]);
-        else *dst = fa[i];
-    });
-}
-
-// The same for the in-place scheme.  Even step: every access is the thread's own aligned pair.  Odd step: the loads are
-// those of k_step_ab2 (slot opp(i), wall: the node's own slot i); every value goes back to the address its partner came
-// from, so an aligned pair of slot opp(i) holds, for c_x = +1, the values of node x0+1 and of the NEXT lane's node x0+2
-// (shuffle down; lane 31 stores its element alone and lane 0 stores the element in front of its pair), for c_x = -1 the
-// value of the PREVIOUS lane's node x0-1 and of node x0 (shuffle up; lane 0 stores its element alone, lane 31 the one
-// behind its pair).  The element of such a pair that would lie on the far side of a wall belongs to another node's
-// bounce-back and is never written here.
-template <bool ODD, class IDX>
-__global__ void __launch_bounds__(BLOCK_X, D3Q_MIN_BLOCKS_V2) k_step_aa2(const __grid_constant__ StepParams p) {
-    const Geom &g = p.g;
-    const int x0 = 2 * (int)(blockIdx.x * BLOCK_X + threadIdx.x);
-    const int y = blockIdx.y, zg = p.z0 + (int)blockIdx.z * p.zstride;
-    const int lane = threadIdx.x & 31;
-    const bool act = x0 < g.lx;                                  // lx is even: both nodes or none
-    const int ym = (y == 0) ? g.ly - 1 : y - 1, yp = (y == g.ly - 1) ? 0 : y + 1;
-    const int zm = (zg == 1) ? g.zlo_src : zg - 1, zp = (zg == g.lz) ? g.zhi_src : zg + 1;
-    const IDX oy[3] = {(IDX)ym * (IDX)g.xp, (IDX)y * (IDX)g.xp, (IDX)yp * (IDX)g.xp};
-    const IDX oz[3] = {(IDX)zm * (IDX)g.plane, (IDX)zg * (IDX)g.plane, (IDX)zp * (IDX)g.plane};
-    const IDX n0 = oy[1] + oz[1] + (IDX)x0;
-    const bool last = x0 + 2 >= g.lx;                            // node x0+1 sits at the upper wall
-    if (p.pf_ahead > 0 && act && (threadIdx.x & 7) == 0) {       // one lane per 128-byte line (section "Software prefetch")
-        const long long ahead = (long long)n0 + p.pf_ahead;
-        if (ahead < g.slab) {
-#pragma unroll
-            for (int i = 0; i < NPOP; ++i) prefetch_l2(p.A + (long long)i * g.slab + ahead);
-        }
-    }
-    double fa[NPOP], fb[NPOP];
-    static_for<NPOP>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        constexpr int cx = ODD ? dir_cx(i) : 0, cy = ODD ? dir_cy(i) : 0, cz = ODD ? dir_cz(i) : 0;
-        constexpr int slot = ODD ? dir_opp(i) : i;
-        const double *src = p.A + (long long)slot * g.slab + (long long)(oy[1 - cy] + oz[1 - cz]);
-        double2 v = make_double2(0.0, 0.0);
-        if (act) v = *reinterpret_cast<const double2 *>(src + x0);
-        if (cx == 0) {
-            fa[i] = v.x; fb[i] = v.y;
-        } else if (cx > 0) {
-            double left = __shfl_up_sync(0xffffffffu, v.y, 1);
-            if (lane == 0 && act && x0 > 0) left = src[x0 - 1];
-            fa[i] = left; fb[i] = v.x;
-            if (x0 == 0 && act) fa[i] = p.A[(long long)i * g.slab + (long long)n0];                  // wall: own slot i
-        } else {
-            double right = __shfl_down_sync(0xffffffffu, v.x, 1);
-            if (lane == 31 && act && !last) right = src[x0 + 2];
-            fa[i] = v.y; fb[i] = right;
-            if (last && act) fb[i] = p.A[(long long)i * g.slab + (long long)n0 + 1];
-        }
-    });
-    collide_fast<true>(fa, 0, 0, 0, 0, p.Fx, p.Fy, p.Fz, 0.0, p.mrt);
-    collide_fast<true>(fb, 0, 0, 0, 0, p.Fx, p.Fy, p.Fz, 0.0, p.mrt);
-    static_for<NPOP>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        constexpr int cx = ODD ? dir_cx(i) : 0, cy = ODD ? dir_cy(i) : 0, cz = ODD ? dir_cz(i) : 0;
-        // even: f*_i -> slot opp(i) of the own node; odd: f*_opp(i) -> where f_i came from
-        constexpr int slot = dir_opp(i);
-        const double ga = ODD ? fa[dir_opp(i)] : fa[i], gb = ODD ? fb[dir_opp(i)] : fb[i];
-        double *dst = p.A + (long long)slot * g.slab + (long long)(oy[1 - cy] + oz[1 - cz]);
-        if (cx == 0) {
-            if (act) *reinterpret_cast<double2 *>(dst + x0) = make_double2(ga, gb);
-        } else if (cx > 0) {
-            const double nxt = __shfl_down_sync(0xffffffffu, ga, 1);        // the next lane's node x0+2
-            if (act) {
-                if (lane < 31 && !last) *reinterpret_cast<double2 *>(dst + x0) = make_double2(gb, nxt);
-                else dst[x0] = gb;
-                if (x0 == 0) p.A[(long long)i * g.slab + (long long)n0] = ga;                        // wall
-                else if (lane == 0) dst[x0 - 1] = ga;
-            }
-        } else {
-            const double prv = __shfl_up_sync(0xffffffffu, gb, 1);          // the previous lane's node x0-1
-            if (act) {
-                if (lane > 0) *reinterpret_cast<double2 *>(dst + x0) = make_double2(prv, ga);
-                else dst[x0 + 1] = ga;
-                if (last) p.A[(long long)i * g.slab + (long long)n0 + 1] = gb;                       // wall
-                else if (lane == 31) dst[x0 + 2] = gb;
-            }
-        }
-    });
-}
+// 128-bit accesses (two x-adjacent nodes per thread, aligned double2 + lane shuffles for the c_x = +-1 populations)
+// were built and measured in rounds 1-2 and REMOVED: 168 registers -> 3 CTAs/SM; on B200, 512x256x256, sustained:
+// AB 1.823 ms vs 1.553 ms for the 64-bit kernel above, AA 1.692 vs 1.630 ms (profiles/r02_switch_decisions.md).  A warp
+// of the 64-bit kernel already moves whole 128-byte lines and the DRAM bytes are the algorithmic ones; what the kernel
+// needs is resident warps, not wider instructions.
 
 // ---- initvel + initpop on the device (initial.f90:75-147, :19-46) -----------------------------------
 // For fields too large to stage through the host (configs[3]: 150 GB of populations per GPU).  The

@@ -231,7 +231,11 @@ __global__ void __launch_bounds__(256) k_beads_links(PartGeom pg, int npart, con
 
 // exclusive scan over the npart * PART_SPLIT block counts: one block of 1024 threads, each owns a
 // contiguous group of entries (a few thousand entries in all)
-__global__ void __launch_bounds__(1024) k_beads_scan(int n, const long long *count, long long *offset) {
+// `overflow` (device word, or nullptr): raised to the total when it exceeds the link capacity -- k_beads_links<true> drops
+// the entries beyond maxlink, and mass would then leak through the particle surface unnoticed (checked by d3q19_sync,
+// d3q19_get_particles and whoever asks for the count)
+__global__ void __launch_bounds__(1024) k_beads_scan(int n, const long long *count, long long *offset, long long maxlink = 0,
+                                                      unsigned long long *overflow = nullptr) {
     __shared__ long long wsum[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int per = (n + 1023) / 1024;
@@ -254,7 +258,10 @@ __global__ void __launch_bounds__(1024) k_beads_scan(int n, const long long *cou
             if (lane >= o) inc2 += t;
         }
         wsum[lane] = inc2 - v;                 // exclusive prefix of the warp totals
-        if (lane == 31) offset[n] = inc2;      // grand total
+        if (lane == 31) {
+            offset[n] = inc2;                  // grand total
+            if (overflow && inc2 > maxlink) atomicMax(overflow, (unsigned long long)inc2);
+        }
     }
     __syncthreads();
     long long acc = wsum[wid] + incl - mine;

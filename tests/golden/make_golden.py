@@ -54,19 +54,23 @@ def save(name, meta, **arrays):
     print("wrote %s.npz: %s" % (name, {k: v.shape for k, v in arrays.items()}))
 
 
-def main_loop_case(name, nx, ny, nz, npy, npz, laminar, steps, seed, a9=0.0, vort=False, **ov):
+def main_loop_case(name, nx, ny, nz, npy, npz, laminar, steps, seed, a9=0.0, vort=False, snap=None, **ov):
     w = start(nx, ny, nz, npy, npz, laminar, seed, a9, **ov)
     f0 = w.get_f().copy()
     w.run("macrovar")                                  # main.f90:136
-    for _ in range(steps):
+    extra = {}
+    for it in range(1, steps + 1):
         w.run("collision_mrt")                         # main.f90:157
         w.run("macrovar")                              # main.f90:161
-    extra = {}
+        if snap is not None and it == snap:            # an intermediate state (the other in-place storage phase)
+            extra["f_snap"] = w.get_f().copy()
     if vort:
         w.run("vortcalc")                              # saveload.f90:3929 (as called by outputvort1, :1138)
-        extra = {k: w.get(k) for k in ("ox", "oy", "oz")}
+        extra.update({k: w.get(k) for k in ("ox", "oy", "oz")})
     meta = dict(kind="main_loop", nx=nx, ny=ny, nz=nz, ranks=[npy, npz], laminar=laminar, steps=steps,
                 overrides=ov, scalars=scalars(w))
+    if snap is not None:
+        meta["snap"] = snap
     save(name, meta, f0=f0, f=w.get_f(), **extra, **{k: w.get(k) for k in FIELDS})
     w.close()
 
@@ -153,6 +157,10 @@ if __name__ == "__main__":
     main_loop_case("ref_turb_mrt3_9x10x7_r3x2_s10", 9, 10, 7, 3, 2, False, 10, seed=777, mrttype=3, **U)
     main_loop_case("ref_turb_mrt1_39x4x3_r1x1_s8", 39, 4, 3, 1, 1, False, 8, seed=4242, **U)   # reaches the log-law branch
     main_loop_case("ref_turb_vort_21x6x5_r2x2_s6", 21, 6, 5, 2, 2, False, 6, seed=31337, a9=0.3, vort=True, **U)
+    # z-slab parity case of bench.py (world > 1) and tests/test_gpu_multi.py: 16 planes cut into 2 / 4 / 8 (or 3, 5: uneven)
+    # slabs, 9 steps (odd: the in-place scheme ends in its swapped phase and has sent its ghost planes back four times),
+    # the state after 8 steps stored as well
+    main_loop_case("ref_slabs_21x4x16_r1x4_s9", 21, 4, 16, 1, 4, False, 9, seed=8086, a9=0.3, snap=8, **U)
     stats_case("ref_stats_21x8x6_r2x2_s6", 21, 8, 6, 2, 2, 6, seed=2024, **U)
     stats_case("ref_stats_solid_24x12x12_r1x2", 24, 12, 12, 1, 2, 0, seed=11, solid=True, **U)
     prerelax_case("ref_prerelax_7x8x8_r2x2_i6", 7, 8, 8, 2, 2, 6, seed=99, **U)

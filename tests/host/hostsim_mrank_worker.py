@@ -286,49 +286,26 @@ def section_shim(rank, world, comm, chk, ctx):
         sim.close(); w.close()
 
 
-def section_vec2(rank, world, comm, chk, ctx):
-    """experiment D3Q19_VEC2=1 (k_step_ab2 / k_step_aa2: two nodes per thread, 128-bit accesses): the same FAST
-    arithmetic on the same inputs, so bit-identical to the one-node-per-thread steps -- walls, odd lx (falls back),
-    several x-blocks and warps per row, boundary / interior launches of the slab run, both storage schemes"""
-    shapes = [(24, 6, 4 * world), (34, 5, 3 * world + 1), (130, 3, 2 * world + 1), (23, 4, 2 * world), (516, 2, world + 1),
-              (2, 3, world + 2), (64, 1, world), (66, 2, 2 * world)]
-    for (nx, ny, nz), scheme in [(sh, sc) for sh in shapes for sc in (capi.SCHEME_AB, capi.SCHEME_AA)]:
-        ctx[0] = "vec2 case %s scheme %d" % ((nx, ny, nz), scheme)
-        w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
-        w.set_f(w.get_f() + 1e-4 * np.random.default_rng(7).normal(size=(nz, ny, nx, 19)))
-        sims = []
-        for v2 in (False, True):
-            comm.bar.wait()
-            if rank == 0:
-                os.environ.pop("D3Q19_VEC2", None)
-                if v2:
-                    os.environ["D3Q19_VEC2"] = "1"
-            comm.bar.wait()
-            sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=scheme,
-                                  math_mode=capi.MATH_FAST, nccl_id=comm.new_id(rank) if world > 1 else None)
-            sim.FORCING()
-            z0, z1 = sim.globalz, sim.globalz + sim.lz
-            sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
-            sims.append(sim)
-        a, b = sims
-        oa, ob = np.empty((a.lz, ny, nx, 19)), np.empty((a.lz, ny, nx, 19))
-        w.macrovar()
-        for burst in (1, 2, 3, 1):                   # readers meet both in-place phases
-            for _ in range(burst):
-                w.collision_MRT(); w.macrovar()
-            a.run_device(burst); b.run_device(burst)
-            a.download_f(oa); b.download_f(ob)
-            chk("vec2 == scalar after a burst of %d" % burst, bool(np.array_equal(oa, ob)))
-            err = np.max(np.abs(ob - w.get_f()[z0:z1])) / np.max(np.abs(w.get_f()))
-            if nx >= 16:                      # (a 2-node-wide channel is a lattice test, not a flow: Ma >> 1)
-                chk("vec2 vs oracle %g" % err, bool(err < 1e-12))
-        ca, cb = a.counters(), b.counters()
-        chk("same number of step launches", ca["step_kernels"] == cb["step_kernels"])
-        a.close(); b.close(); w.close()
-    comm.bar.wait()
-    if rank == 0:
-        os.environ.pop("D3Q19_VEC2", None)
-    comm.bar.wait()
+def section_benchparity(rank, world, comm, chk, ctx):
+    """bench.py's own pre-timing parity check (the reference's golden vector on this job's slabs, every transport; the
+    moving-particle case against one domain), with the ranks as threads"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for halo in ("nccl", "peer", "put"):
+        ctx[0] = "bench parity_check, halo " + halo
+
+        def connect(sim):
+            if halo != "nccl":
+                assert sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if halo == "put" else "fused")
+
+        res = bench.parity_check(pkg, rank, world, 0, lambda: comm.new_id(rank), connect,
+                                 lambda ok: all(comm.allgather(rank, bool(ok))), lambda obj: comm.allgather(rank, obj)[0],
+                                 particles=halo == "nccl")
+        chk("parity_check %r" % (res,), res["bit_exact"] is True and len(res["schemes"]) == 2)
+        if halo == "nccl":
+            chk("particle leg present", res["particles"]["ok"] is True)
 
 
 def section_random(rank, world, comm, chk, ctx):
@@ -366,7 +343,7 @@ def section_random(rank, world, comm, chk, ctx):
     comm.bar.wait()
 
 
-SECTIONS = {"random": section_random, "vec2": section_vec2, "fluid": section_fluid, "prerelax": section_prerelax, "particles": section_particles, "shim": section_shim}
+SECTIONS = {"random": section_random, "benchparity": section_benchparity, "fluid": section_fluid, "prerelax": section_prerelax, "particles": section_particles, "shim": section_shim}
 
 
 def rank_main(rank, world, comm, sections):

@@ -52,7 +52,7 @@ def test_single_rank_gpu_test_files_pass_on_the_host_sim(hostsim):
 def test_multi_rank_orchestration_on_the_host_sim(hostsim, world):
     # 3 ranks: every case of the worker; 2 ranks (both neighbours are the same rank): one uneven case per transport
     extra = {"HOSTSIM_SHORT": "1"} if world == 2 else {}
-    sections = ["fluid", "shim", "particles", "random"] if world == 2 else []            # none named = all of them
+    sections = ["fluid", "shim", "particles", "random", "benchparity"] if world == 2 else []            # none named = all of them
     res = run([sys.executable, os.path.join("tests", "host", "hostsim_mrank_worker.py"), str(world)] + sections, hostsim, **extra)
     assert res.returncode == 0 and "HOSTSIM_MRANK_OK" in res.stdout, res.stdout[-4000:]
 
@@ -88,12 +88,14 @@ def test_bench_product_arm_prints_its_contract_line(hostsim, extra):
         e = d["e2e"]
         assert e["value"] > 0 and e["h2d_bytes_per_step"] == 19 * 8 * 32 * 8 * 8 / 6 and e["d2h_bytes_per_step"] > 32
     assert d["config"]["workload"].startswith("D3Q19 MRT channel")
+    pc = d["parity_check"]                            # the reference's golden vector, checked before the timed region
+    assert pc["bit_exact"] is True and pc["ranks"] == 1 and [t["scheme"] for t in pc["schemes"]] == ["aa", "ab"]
 
 
 def test_full_size_property_tests_and_experiments_on_the_host_sim(hostsim):
-    # the logic of tests/test_zzz_gpu_fullsize.py on a shrunk channel, and the vec2 step of the experimental file
+    # the logic of tests/test_zzz_gpu_fullsize.py on a shrunk channel, and the experimental file
     res = run([sys.executable, "-m", "pytest", "tests/test_zzz_gpu_fullsize.py", "tests/test_zzzz_gpu_experimental.py", "-m", "gpu",
-               "-q", "-p", "no:cacheprovider", "-k", "not (vec2 and shape2)"],        # (the 516-wide vec2 case: the worker has it)
+               "-q", "-p", "no:cacheprovider"],
               hostsim, D3Q19_TEST_FULLSIZE="64x16x16")
     tail = res.stdout[-3000:]
     assert res.returncode == 0, tail
