@@ -57,16 +57,11 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true",
                     help="skip the bit-exact check of the reference's golden vector on this job's ranks before the timed region")
     ap.add_argument("--halo", default="nccl", choices=["peer", "put", "nccl"],
-                    help="z-face exchange: NCCL send/recv of the packed faces on a second stream, overlapped with the interior "
-                         "(default; equal or faster in every configuration measured, profiles/r01d_halo_transports.md) or "
-                         "stores into the neighbour GPU's memory over NVLink inside the step kernel")
-    ap.add_argument("--boundary-stream", action="store_true",
-                    help="NCCL transport, opt-in: launch the two boundary planes of a step on their own high-priority stream next "
-                         "to the interior launch instead of in front of it (D3Q19_BOUNDARY_STREAM=1)")
-    ap.add_argument("--direct-faces", action="store_true",
-                    help="NCCL transport, opt-in: send the five crossing populations of a face straight out of the population "
-                         "array and receive them in place (20 sends/receives in one group, no pack / unpack kernels; "
-                         "D3Q19_DIRECT_FACES=1)")
+                    help="z-face exchange: nccl = NCCL send/recv of the packed faces on a second stream, overlapped with the "
+                         "interior; put = the copy engines move the faces into the neighbour GPU's memory over NVLink (no SM "
+                         "involved); peer = stores into the neighbour's memory inside the step kernel")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0,
+                    help="d3q19_config.nccl_max_ctas: CTAs NCCL may use for the face send/recv (0 = the library's default, 4)")
     ap.add_argument("--cpu-steps", type=int, default=20,
                     help="timed steps of the CPU arm (20 steps of 512x256x256 = about 10 s on 16 cores)")
     ap.add_argument("--particles", type=int, default=0,
@@ -293,6 +288,7 @@ def main():
     # rank 0 prints exactly ONE line on stdout: keep NCCL's "NCCL version ..." banner off it
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -378,16 +374,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return bool(t.item() > 0.5)
 
-    if args.boundary_stream and world > 1 and args.particles == 0:
-        os.environ["D3Q19_BOUNDARY_STREAM"] = "1"
-    if args.direct_faces and world > 1:
-        os.environ["D3Q19_DIRECT_FACES"] = "1"
 
     def build_sim(halo_req, nccl_id):
         """the channel on this rank's slab with its synthetic initial state; returns (sim, halo actually in use)"""
         sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local_rank, scheme=scheme,
                               math_mode=math_mode, nccl_id=nccl_id, overlap=not args.no_overlap, allocate_host=False,
-                              ipart=args.particles > 0)
+                              nccl_max_ctas=args.nccl_max_ctas, ipart=args.particles > 0)
         halo = "none"
         if world > 1:
             halo = "nccl"
@@ -564,10 +556,8 @@ def main():
                                      "lubrication, move, refill every step" % (args.particles, args.rad)) if args.particles else "none",
                        "parallelism": ("z-slab x%d, faces %s" % (world, {
                            "peer": "stored into the neighbour GPU's memory over NVLink inside the step kernel",
-                           "put": "stored into the neighbour GPU's memory over NVLink by a copy kernel on a second stream",
-                           "nccl": "by NCCL send/recv" + (", boundary planes on their own stream" if os.environ.get(
-                               "D3Q19_BOUNDARY_STREAM") == "1" else "") + (", faces sent in place (no pack/unpack)" if os.environ.get(
-                               "D3Q19_DIRECT_FACES") == "1" else "")}[halo])) if world > 1 else "1 GPU",
+                           "put": "copied into the neighbour GPU's memory over NVLink by the copy engines on a second stream",
+                           "nccl": "by NCCL send/recv (at most %d CTAs)" % (args.nccl_max_ctas or 4)}[halo])) if world > 1 else "1 GPU",
                        "l2": "populations %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (c1["population_bytes"] / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "parity_check": parity,
             "clocks": clocks, "impl": "ours",

@@ -28,7 +28,7 @@ SYMBOLS = [
     "d3q19_init_channel", "d3q19_set_force_uniform", "d3q19_set_force_field", "d3q19_forcingp", "d3q19_download_force_field",
     "d3q19_collide_stream", "d3q19_run", "d3q19_macrovar", "d3q19_rhoupdat", "d3q19_avedensity", "d3q19_probe",
     "d3q19_prerelax", "d3q19_set_solid_mask", "d3q19_set_particles", "d3q19_profiles", "d3q19_profiles2", "d3q19_diag",
-    "d3q19_vortcalc", "d3q19_download_vort",
+    "d3q19_vortcalc", "d3q19_download_vort", "d3q19_sijstat", "d3q19_download_sij2",
     "d3q19_particles_init", "d3q19_beads_links", "d3q19_beads_collision", "d3q19_beads_lubforce", "d3q19_beads_move",
     "d3q19_beads_filling", "d3q19_particle_step", "d3q19_get_particles", "d3q19_get_links", "d3q19_get_mask",
     "d3q19_timer_start", "d3q19_timer_stop", "d3q19_get_counters", "d3q19_trace_enable", "d3q19_trace_fetch",
@@ -48,7 +48,8 @@ class Config(C.Structure):
         ("rank", C.c_int32), ("nranks", C.c_int32),
         ("device", C.c_int32),
         ("scheme", C.c_int32), ("math", C.c_int32), ("ipart", C.c_int32), ("overlap", C.c_int32),
-        ("reserved_i", C.c_int32 * 5),
+        ("nccl_max_ctas", C.c_int32), ("pf_blocks", C.c_int32), ("halo_timeout_s", C.c_int32),
+        ("halo_split_min", C.c_int32), ("force_idx64", C.c_int32),
         ("s1", C.c_double), ("s2", C.c_double), ("s4", C.c_double), ("s9", C.c_double),
         ("s10", C.c_double), ("s13", C.c_double), ("s16", C.c_double),
         ("omegepsl", C.c_double), ("omegepslj", C.c_double), ("omegxx", C.c_double),
@@ -145,6 +146,8 @@ def load():
     L.d3q19_download_force_field.argtypes = [vp, dp, dp, dp]
     L.d3q19_vortcalc.argtypes = [vp]
     L.d3q19_download_vort.argtypes = [vp, dp, dp, dp]
+    L.d3q19_sijstat.argtypes = [vp]
+    L.d3q19_download_sij2.argtypes = [vp, dp]
     i64p = C.POINTER(C.c_int64)
     L.d3q19_particles_init.argtypes = [vp, C.c_int32, C.POINTER(ParticleParams)]
     L.d3q19_beads_links.argtypes = [vp, i64p]

@@ -108,7 +108,10 @@ class ChannelFlow:
     """One rank (= one GPU) of a Channel-Flow run behind the reference's subroutine names."""
 
     def __init__(self, nx, ny, nz, laminar=True, rank=0, nranks=1, device=None, scheme=capi.SCHEME_AA,
-                 math_mode=capi.MATH_FAST, nccl_id=None, overlap=True, allocate_host=True, **overrides):
+                 math_mode=capi.MATH_FAST, nccl_id=None, overlap=True, allocate_host=True, nccl_max_ctas=0, pf_blocks=0,
+                 halo_timeout_s=0, halo_split_min=0, force_idx64=False, **overrides):
+        """the last five keywords are d3q19_config's tuning knobs (0 = the measured default); **overrides are scalars
+        of `module var_inc` as `para` would set them"""
         self.v = VarInc(nx, ny, nz, laminar, **overrides)
         self.rank, self.nranks = int(rank), int(nranks)
         self.lx, self.ly = self.v.nx, self.v.ny
@@ -125,6 +128,8 @@ class ChannelFlow:
         cfg.scheme, cfg.math = int(scheme), int(math_mode)
         cfg.ipart = int(bool(self.v.ipart))
         cfg.overlap = int(bool(overlap))
+        cfg.nccl_max_ctas, cfg.pf_blocks, cfg.halo_timeout_s = int(nccl_max_ctas), int(pf_blocks), int(halo_timeout_s)
+        cfg.halo_split_min, cfg.force_idx64 = int(halo_split_min), int(bool(force_idx64))
         for k in ("s1", "s2", "s4", "s9", "s10", "s13", "s16", "omegepsl", "omegepslj", "omegxx", "rhopart"):
             setattr(cfg, k, float(getattr(self.v, k)))
         if self.nranks > 1:
@@ -349,6 +354,14 @@ class ChannelFlow:
         capi.check(self.L.d3q19_download_vort(self.h, *[capi.dptr(a) for a in o]))
         return o
 
+    def sijstat(self):
+        """first loop nest of sijstat00 (saveload.f90:2031-2091) on the device: Sij*Sij of this rank's fluid nodes from the
+        non-equilibrium moments of the current populations and the rho,u of the last macrovar; [iz, iy, ix]"""
+        o = np.zeros((self.lz, self.ly, self.lx))
+        capi.check(self.L.d3q19_sijstat(self.h))
+        capi.check(self.L.d3q19_download_sij2(self.h, capi.dptr(o)))
+        return o
+
     def profiles(self):
         out = np.zeros((11, self.lx))
         capi.check(self.L.d3q19_profiles(self.h, capi.dptr(out)))
@@ -471,7 +484,9 @@ class ChannelFlow:
         capi.check(self.L.d3q19_get_particles(self.h, *(capi.dptr(out[k]) for k in ("ypglb", "wp", "omgp", "fHIp", "torqp"))))
         return out
 
-    def get_links(self):
+    def get_links(self, canonical=True):
+        """the boundary links of this slab.  The device list is a SET (warps append their rows as they finish);
+        canonical=True returns it sorted by (particle, z, y, x, direction) so that two lists can be compared"""
         n = C.c_int64(0)
         cap = 1 << 16
         while True:
@@ -485,7 +500,11 @@ class ChannelFlow:
                 continue
             capi.check(rc)
         m = n.value
-        return dict(x=a[0][:m], y=a[1][:m], z=a[2][:m], ip=a[3][:m], part=a[4][:m], q=q[:m])
+        d = dict(x=a[0][:m], y=a[1][:m], z=a[2][:m], ip=a[3][:m], part=a[4][:m], q=q[:m])
+        if canonical:
+            o = np.lexsort((d["ip"], d["x"], d["y"], d["z"], d["part"]))
+            d = {k: v[o] for k, v in d.items()}
+        return d
 
     def get_mask(self):
         own = np.zeros((self.lz, self.ly, self.lx), dtype=np.int32)
@@ -494,7 +513,7 @@ class ChannelFlow:
 
     # ---- halo in NVLink peer memory (collective; `allgather(bytes) -> [bytes per rank]`) ----------
     def connect_halo(self, allgather, mode=None):
-        """mode: None (library default / D3Q19_HALO_MODE), "fused" (stores inside the step kernel) or "put" (copy kernel)"""
+        """mode: None (library default: fused), "fused" (stores inside the step kernel) or "put" (copy engines)"""
         if mode is not None:
             capi.check(self.L.d3q19_set_halo_mode(self.h, {"fused": capi.HALO_FUSED, "put": capi.HALO_PUT}[mode]))
         blob = (C.c_ubyte * capi.IPC_BYTES)()

@@ -78,6 +78,7 @@ struct d3q19_handle {
     double *ffx = nullptr, *ffy = nullptr, *ffz = nullptr;
     double *vort = nullptr;       // ox, oy, oz: 3 x nfield (vortcalc)
     double *vort_halo = nullptr;  // exchanged velocity planes: [lo: ux,uy,uz][hi: ux,uy,uz]
+    double *sij2 = nullptr;       // Sij*Sij, nfield (sijstat)
     int32_t *solid = nullptr, *isn = nullptr;
     double *ypglb = nullptr, *wp = nullptr, *omgp = nullptr;
     int npart = 0;
@@ -86,15 +87,6 @@ struct d3q19_handle {
     cudaEvent_t evB = nullptr, evX = nullptr, t0 = nullptr, t1 = nullptr, evC[2] = {nullptr, nullptr},
                 evS[2] = {nullptr, nullptr};
     bool exchange_pending = false;
-    // opt-in (D3Q19_BOUNDARY_STREAM=1): the boundary-plane launch of the NCCL transport runs on its own high-priority
-    // stream sb, concurrently with the interior launch of the SAME step (step_impl, "boundary stream")
-    cudaStream_t sb = nullptr;
-    cudaEvent_t evI = nullptr;
-    bool bstream = false;
-    bool b_pending = false;       // the last boundary launch (event evB on sb) has not been waited for by sc yet
-    // opt-in (D3Q19_DIRECT_FACES=1): faces travel straight out of / into the population array (a population's plane is
-    // contiguous), 10 sends + 10 receives in one NCCL group, no pack / unpack kernels (exchange_faces)
-    bool direct_faces = false;
     // optional per-step timeline (d3q19_trace_enable): 4 timing events per step -- [0] before the boundary launch,
     // [1] after it, [2] after the interior launch (all on sc), [3] after the exchange / put (on sx)
     cudaEvent_t *trace_ev = nullptr;
@@ -111,18 +103,19 @@ struct d3q19_handle {
     double *diag_partial = nullptr, *diag_red = nullptr;   // d3q19_diag scratch (allocated once: no cudaMalloc/cudaFree in the loop)
     int diag_npartial = 0;
     int prof_chunks = 0, prof_rows = 0;
-    long long n_step_kernels = 0, n_other_kernels = 0, n_nccl = 0, n_steps = 0;
+    long long n_step_kernels = 0, n_other_kernels = 0, n_nccl = 0, n_steps = 0, n_copies = 0;
     // particle path (particles.cuh)
     bool part_on = false, links_valid = false, mask_built = false;
     d3q19_particle_params pp;
-    int32_t *own = nullptr, *own0 = nullptr;     // ghosted owner masks [lz+2][ly][xp], now / before the last move
+    int32_t *own = nullptr;                      // ghosted owner mask [lz+2][ly][xp]: particles.cuh "the solid mask follows the particles"
     double *pbuf = nullptr;                      // 10 tables of (3,npart)
-    double *ypglb0 = nullptr, *fHIp = nullptr, *torqp = nullptr, *flubp = nullptr, *forcepp = nullptr, *torqpp = nullptr,
-           *thetap = nullptr;
+    double *ypmask = nullptr,                    // the positions the mask was built with
+           *fHIp = nullptr, *torqp = nullptr, *flubp = nullptr, *forcepp = nullptr, *torqpp = nullptr, *thetap = nullptr;
     Links links = {nullptr, nullptr, nullptr, nullptr};
+    FillList fill = {nullptr, nullptr, nullptr, 0};   // nodes the last mask update uncovered (what beads_filling rebuilds)
     long long maxlink = 0, nlink = 0;
-    long long *lcount = nullptr, *loffset = nullptr;
-    unsigned long long *nfilled_dev = nullptr;
+    unsigned long long *pcnt = nullptr;          // device counters: [0] links, [1] refill list, [2] refilled nodes
+    int part_rows = 0;                           // rows of the largest bounding box (grid of the sweep kernels)
     double *fill_halo = nullptr;                 // z-slab refill: [send up][send dn][ghost lo][ghost hi], 19 x plane each
     double amp = 0, aip = 0;
     // halo in peer memory (cudaIpc): [0] = lower neighbour (mzm), [1] = upper neighbour (mzp)
@@ -191,10 +184,6 @@ static int wait_exchange(d3q19_handle *h) {
         h->exchange_pending = false;
         h->put_pending = false;
     }
-    if (h->b_pending) {                  // boundary stream: the planes next to the faces are written on sb
-        CK(cudaStreamWaitEvent(h->sc, h->evB, 0));
-        h->b_pending = false;
-    }
     return 0;
 }
 
@@ -223,25 +212,6 @@ static int exchange_faces(d3q19_handle *h, double *arr, int up_src, const FaceSl
     const size_t cnt = (size_t)5 * g.plane;
     const int up = (h->cfg.rank + 1) % h->cfg.nranks;                       // mzp, para.f90:266
     const int dn = (h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks;       // mzm, para.f90:267
-    if (h->direct_faces && !exclude_walls) {
-        // One population of one z plane is plane = xp*ly contiguous doubles, so each of the five
-        // crossing populations can be sent from where it lies and received where it belongs.  Not after an in-place odd
-        // step: its send-back must leave the wall-adjacent nodes alone (exclude_walls), which needs the unpack kernel.
-        NcclApi &n = nccl_api();
-        const size_t pl = (size_t)g.plane;
-        NK(n.GroupStart());
-        for (int q = 0; q < 5; ++q) {            // same order towards either neighbour as the packed exchange: up, dn
-            NK(n.Send(arr + (size_t)up_slots.s[q] * g.slab + (size_t)up_src * pl, pl, NCCL_FLOAT64, up, h->comm, s));
-            NK(n.Send(arr + (size_t)dn_slots.s[q] * g.slab + (size_t)dn_src * pl, pl, NCCL_FLOAT64, dn, h->comm, s));
-        }
-        for (int q = 0; q < 5; ++q) {
-            NK(n.Recv(arr + (size_t)up_slots.s[q] * g.slab + (size_t)lo_dst * pl, pl, NCCL_FLOAT64, dn, h->comm, s));
-            NK(n.Recv(arr + (size_t)dn_slots.s[q] * g.slab + (size_t)hi_dst * pl, pl, NCCL_FLOAT64, up, h->comm, s));
-        }
-        NK(n.GroupEnd());
-        h->n_nccl += 20;
-        return 0;
-    }
     const dim3 gp((unsigned)((g.xp + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 10u);
     FacePair pk;
     pk.buf[0] = h->send_up; pk.zg[0] = up_src; pk.slots[0] = up_slots;
@@ -302,7 +272,6 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->sc) cudaStreamSynchronize(h->sc);
     if (h->sx) cudaStreamSynchronize(h->sx);
-    if (h->sb) cudaStreamSynchronize(h->sb);
     shim_unpin(h);
     if (h->halo_on) {
         // nobody may still be storing into our planes, and we must let go of theirs before they free them
@@ -317,8 +286,8 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
         h->halo_on = false;
     }
     if (h->part_on) {
-        void *pp_[] = {h->own, h->own0, h->pbuf, h->links.node, h->links.dir, h->links.part, h->links.q, h->lcount, h->loffset,
-                       h->nfilled_dev, h->fill_halo};
+        void *pp_[] = {h->own, h->pbuf, h->links.node, h->links.dir, h->links.part, h->links.q, h->fill.node, h->fill.part,
+                       h->pcnt, h->fill_halo};
         for (void *q : pp_) if (q) cudaFree(q);
         h->solid = h->isn = nullptr; h->ypglb = h->wp = h->omgp = nullptr;
     }
@@ -330,13 +299,12 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
     if (h->comm) nccl_api().CommDestroy(h->comm);
     void *ptrs[] = {h->A_alloc, h->B_alloc, h->rho, h->ux, h->uy, h->uz, h->ffx, h->ffy, h->ffz, h->solid, h->isn, h->ypglb,
                     h->wp, h->omgp, h->send_up, h->send_dn, h->recv_lo, h->recv_hi, h->stage[0], h->stage[1],
-                    h->scal, h->red_d, h->red_c, h->prof_partial, h->prof_out, h->vort, h->vort_halo, h->diag_partial, h->diag_red};
+                    h->scal, h->red_d, h->red_c, h->prof_partial, h->prof_out, h->vort, h->vort_halo, h->diag_partial, h->diag_red, h->sij2};
     for (void *p : ptrs) if (p) cudaFree(p);
-    cudaEvent_t evs[] = {h->evB, h->evX, h->evI, h->t0, h->t1, h->evC[0], h->evC[1], h->evS[0], h->evS[1]};
+    cudaEvent_t evs[] = {h->evB, h->evX, h->t0, h->t1, h->evC[0], h->evC[1], h->evS[0], h->evS[1]};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     if (h->sc) cudaStreamDestroy(h->sc);
     if (h->sx) cudaStreamDestroy(h->sx);
-    if (h->sb) cudaStreamDestroy(h->sb);
     delete h;
     return 0;
 }
@@ -370,9 +338,8 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
     h->nfield = (size_t)g.plane * g.lz;
     {
         // prefetch about 128 thread blocks ahead of the running front, in whole x-rows (measured optimum on
-        // B200: profiles/r01c_prefetch_sweep.md); D3Q19_PF_BLOCKS overrides, 0 switches it off
-        int pf_blocks = 128;
-        if (const char *t = getenv("D3Q19_PF_BLOCKS")) pf_blocks = atoi(t);
+        // B200: profiles/r01c_prefetch_sweep.md); d3q19_config.pf_blocks overrides, < 0 switches it off
+        const int pf_blocks = cfg->pf_blocks == 0 ? 128 : (cfg->pf_blocks < 0 ? 0 : cfg->pf_blocks);
         const int blocks_per_row = (g.lx + BLOCK_X - 1) / BLOCK_X;
         const long long rows = pf_blocks > 0 ? (pf_blocks + blocks_per_row - 1) / blocks_per_row : 0;
         h->pf_ahead = rows * g.xp;
@@ -400,18 +367,6 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
     CKH(cudaStreamCreateWithPriority(&h->sx, cudaStreamNonBlocking, hi));
     CKH(cudaEventCreateWithFlags(&h->evB, cudaEventDisableTiming));
     CKH(cudaEventCreateWithFlags(&h->evX, cudaEventDisableTiming));
-    if (cfg->nranks > 1 && !cfg->ipart) {
-        const char *t = getenv("D3Q19_BOUNDARY_STREAM");
-        h->bstream = t && atoi(t) > 0;
-    }
-    if (cfg->nranks > 1) {
-        const char *t = getenv("D3Q19_DIRECT_FACES");
-        h->direct_faces = t && atoi(t) > 0;
-    }
-    if (h->bstream) {
-        CKH(cudaStreamCreateWithPriority(&h->sb, cudaStreamNonBlocking, hi));
-        CKH(cudaEventCreateWithFlags(&h->evI, cudaEventDisableTiming));
-    }
     for (int i = 0; i < 2; ++i) {
         CKH(cudaEventCreateWithFlags(&h->evC[i], cudaEventDisableTiming));
         CKH(cudaEventCreateWithFlags(&h->evS[i], cudaEventDisableTiming));
@@ -420,7 +375,9 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
     CKH(cudaEventCreate(&h->t1));
     const size_t PAD = POP_PAD;
     const size_t fbytes = ((size_t)NPOP * g.slab + 2 * PAD) * sizeof(double);
-    h->idx32 = (unsigned long long)g.slab + 2 < 0xffffffffull && !getenv("D3Q19_FORCE_IDX64");
+    h->idx32 = (unsigned long long)g.slab + 2 < 0xffffffffull && !cfg->force_idx64;
+    if (cfg->halo_timeout_s > 0) h->halo_timeout_ns = (unsigned long long)cfg->halo_timeout_s * 1000000000ull;
+    if (cfg->halo_split_min > 0) h->halo_split_min = cfg->halo_split_min;
     CKH(cudaMalloc(&h->A_alloc, fbytes));
     CKH(cudaMemsetAsync(h->A_alloc, 0, fbytes, h->sc));
     h->A = h->A_alloc + PAD;
@@ -436,7 +393,11 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
         if (const char *m = n.load()) { fail("d3q19_create: %s", m); d3q19_destroy(h); return 1; }
         NcclUniqueId id;
         memcpy(id.internal, cfg->nccl_id, 128);
-        int e = n.CommInitRank(&h->comm, cfg->nranks, id, cfg->rank);
+        // the faces are a few MB per step: a handful of NCCL CTAs carries them, and each one holds an SM that the interior
+        // kernel then does not have (d3q19_config.nccl_max_ctas, default 4)
+        NcclConfig218 nc = nccl_config_max_ctas(cfg->nccl_max_ctas > 0 ? cfg->nccl_max_ctas : 4);
+        int e = n.CommInitRankConfig ? n.CommInitRankConfig(&h->comm, cfg->nranks, id, cfg->rank, &nc)
+                                     : n.CommInitRank(&h->comm, cfg->nranks, id, cfg->rank);
         if (e != 0) { fail("d3q19_create: ncclCommInitRank -> %s", n.GetErrorString(e)); h->comm = nullptr; d3q19_destroy(h); return 1; }
         const size_t fb = (size_t)5 * g.plane * sizeof(double);
         CKH(cudaMalloc(&h->send_up, fb)); CKH(cudaMalloc(&h->send_dn, fb));
@@ -450,10 +411,9 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
 
 extern "C" int d3q19_sync(d3q19_handle *h) {
     CK(cudaSetDevice(h->cfg.device));
-    if (h->halo_on || h->b_pending) RK_(wait_exchange(h));       // the neighbours' stores of the last step have landed
+    if (h->halo_on) RK_(wait_exchange(h));       // the neighbours' stores of the last step have landed
     CK(cudaStreamSynchronize(h->sc));
     CK(cudaStreamSynchronize(h->sx));
-    if (h->sb) CK(cudaStreamSynchronize(h->sb));
     if (h->halo_on) {
         // watchdog of the flag waits (kernels.cuh halo_spin): a neighbour's flag that never came
         unsigned int bad = 0;
@@ -553,15 +513,6 @@ extern "C" int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs) {
         fail("d3q19_ipc_connect: peer memory unavailable on %d rank(s)%s%s; the halo stays on NCCL", (int)nfail,
              failed ? ": " : "", failed ? why.c_str() : "");
         return 2;
-    }
-    if (const char *t = getenv("D3Q19_HALO_SPLIT_MIN")) h->halo_split_min = atoi(t);
-    if (const char *t = getenv("D3Q19_HALO_MODE")) {
-        if (!strcmp(t, "put")) h->halo_mode = D3Q19_HALO_PUT;
-        else if (!strcmp(t, "fused")) h->halo_mode = D3Q19_HALO_FUSED;
-    }
-    if (const char *t = getenv("D3Q19_HALO_TIMEOUT_S")) {
-        const double sec = atof(t);
-        if (sec > 0.0) h->halo_timeout_ns = (unsigned long long)(sec * 1e9);
     }
     h->halo_on = true;
     return 0;
@@ -764,6 +715,41 @@ extern "C" int d3q19_download_vort(d3q19_handle *h, double *ox, double *oy, doub
     return 0;
 }
 
+// ---- local strain rate (sijstat00's first loop nest, saveload.f90:2031-2091) ---------------------------------------
+// Like vortcalc it works on the rho,u arrays d3q19_macrovar made (the reference reads the arrays macrovar left behind)
+// and on the current populations; node-local, so no exchange.
+extern "C" int d3q19_sijstat(d3q19_handle *h) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->rho) return fail("d3q19_sijstat: no rho,u on the device -- call d3q19_macrovar first");
+    RK_(ensure_mask(h));
+    RK_(wait_exchange(h));
+    if (!h->sij2) CK(cudaMalloc(&h->sij2, h->nfield * sizeof(double)));
+    SijParams p;
+    memset(&p, 0, sizeof p);
+    p.g = h->g; p.A = h->A;
+    p.rho = h->rho; p.ux = h->ux; p.uy = h->uy; p.uz = h->uz;
+    p.solid = h->solid;
+    p.s1 = h->cfg.s1; p.s9 = h->cfg.s9;
+    p.sij2 = h->sij2;
+    const dim3 gr = grid_nodes(h, h->g.lz);
+    switch (read_kind(h)) {
+    case READ_DIRECT: k_sijstat<READ_DIRECT><<<gr, BLOCK_X, 0, h->sc>>>(p); break;
+    case READ_PULL_NAT: k_sijstat<READ_PULL_NAT><<<gr, BLOCK_X, 0, h->sc>>>(p); break;
+    default: k_sijstat<READ_PULL_SWAP><<<gr, BLOCK_X, 0, h->sc>>>(p); break;
+    }
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    return 0;
+}
+
+extern "C" int d3q19_download_sij2(d3q19_handle *h, double *sij2) {
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->sij2) return fail("d3q19_download_sij2: call d3q19_sijstat first");
+    RK_(field_to_host(h, h->sij2, sij2));
+    CK(cudaStreamSynchronize(h->sc));
+    return 0;
+}
+
 // ---- forcing ---------------------------------------------------------------------------------------
 extern "C" int d3q19_set_force_uniform(d3q19_handle *h, double fx, double fy, double fz) {
     CK(cudaSetDevice(h->cfg.device));
@@ -904,32 +890,49 @@ static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written
     }
     trace_mark(h, 2, h->sc);
     CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
+    // The faces travel by the COPY ENGINES: one population of one z plane is plane = xp*ly contiguous doubles, so each
+    // of the five crossing populations goes from where it lies in my array to where it belongs in the neighbour's
+    // (cudaIpc-mapped) array with one device-to-device copy over NVLink -- no SM takes part, nothing competes with the
+    // interior kernel for issue slots or registers (measured: NCCL's send/recv CTAs and a copy kernel both slow the
+    // concurrent interior launch by 35-50 us on 32-plane slabs, profiles/r02b_timeline_thin.jsonl).  After an in-place
+    // odd step the ghost planes go back into the neighbour's REAL plane and must leave the wall-adjacent nodes of the
+    // c_x = +-1 populations alone (collision.f90:361-368): those two populations per face are pitched 2-D copies of
+    // lx-1 columns.  Copies of one stream complete in order; a one-thread kernel then raises the neighbours' flags.
     const bool ab = SK == STEP_AB;
-    FacePut fp;
-    memset(&fp, 0, sizeof fp);
-    fp.src = written;
-    fp.dst[0] = ab ? h->peer_B[1] : h->peer_A[1];       // upper neighbour
-    fp.dst[1] = ab ? h->peer_B[0] : h->peer_A[0];       // lower neighbour
-    fp.slab_dst[0] = h->peer_slab[1]; fp.slab_dst[1] = h->peer_slab[0];
+    double *dstA[2] = {ab ? h->peer_B[1] : h->peer_A[1], ab ? h->peer_B[0] : h->peer_A[0]};     // upper, lower neighbour
+    const long long slab_dst[2] = {h->peer_slab[1], h->peer_slab[0]};
+    int zsrc[2], zdst[2], excl = 0;
+    FaceSlots sl[2];
     switch (SK) {                                       // the planes and slots of exchange_after_step
-    case STEP_AB:      fp.zsrc[0] = lz; fp.slots[0] = SLOTS_PZ; fp.zdst[0] = 0; fp.zsrc[1] = 1; fp.slots[1] = SLOTS_MZ; fp.zdst[1] = h->peer_lz[0] + 1; break;
-    case STEP_AA_EVEN: fp.zsrc[0] = lz; fp.slots[0] = SLOTS_MZ; fp.zdst[0] = 0; fp.zsrc[1] = 1; fp.slots[1] = SLOTS_PZ; fp.zdst[1] = h->peer_lz[0] + 1; break;
-    default:           fp.zsrc[0] = lz + 1; fp.slots[0] = SLOTS_PZ; fp.zdst[0] = 1; fp.zsrc[1] = 0; fp.slots[1] = SLOTS_MZ; fp.zdst[1] = h->peer_lz[0];
-                       fp.exclude_walls = 1; break;
+    case STEP_AB:      zsrc[0] = lz; sl[0] = SLOTS_PZ; zdst[0] = 0; zsrc[1] = 1; sl[1] = SLOTS_MZ; zdst[1] = h->peer_lz[0] + 1; break;
+    case STEP_AA_EVEN: zsrc[0] = lz; sl[0] = SLOTS_MZ; zdst[0] = 0; zsrc[1] = 1; sl[1] = SLOTS_PZ; zdst[1] = h->peer_lz[0] + 1; break;
+    default:           zsrc[0] = lz + 1; sl[0] = SLOTS_PZ; zdst[0] = 1; zsrc[1] = 0; sl[1] = SLOTS_MZ; zdst[1] = h->peer_lz[0];
+                       excl = 1; break;
     }
-    fp.ctr = h->halo_flags + 2;
-    fp.sig[0] = h->peer_flags[1];                       // the upper neighbour's wait_lo
-    fp.sig[1] = h->peer_flags[0] + 1;                   // the lower neighbour's wait_hi
-    fp.epoch = epoch;
-    const dim3 gp((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 10u);
-    fp.nblk = gp.x * gp.y * gp.z;
-    k_face_put<<<gp, BLOCK_X, 0, h->sx>>>(g, fp);
+    const size_t pl = (size_t)g.plane;
+    for (int q = 0; q < 5; ++q) {
+        for (int d = 0; d < 2; ++d) {
+            const int slot = sl[d].s[q];
+            const double *src = written + (size_t)slot * g.slab + (size_t)zsrc[d] * pl;
+            double *dst = dstA[d] + (size_t)slot * slab_dst[d] + (size_t)zdst[d] * pl;
+            const int cx = d3q::dir_cx_rt(slot);
+            if (excl && cx != 0) {
+                const size_t off = cx > 0 ? 1 : 0;      // c_x = +1 skips x = 0, c_x = -1 skips x = lx-1
+                CK(cudaMemcpy2DAsync(dst + off, (size_t)g.xp * sizeof(double), src + off, (size_t)g.xp * sizeof(double),
+                                     (size_t)(g.lx - 1) * sizeof(double), (size_t)g.ly, cudaMemcpyDeviceToDevice, h->sx));
+            } else {
+                CK(cudaMemcpyAsync(dst, src, pl * sizeof(double), cudaMemcpyDeviceToDevice, h->sx));
+            }
+        }
+    }
+    k_flag_raise<<<1, 1, 0, h->sx>>>(h->peer_flags[1], h->peer_flags[0] + 1, epoch);    // upper's wait_lo, lower's wait_hi
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->evX, h->sx));
     trace_mark(h, 3, h->sx);
     trace_next(h);
     h->put_pending = true;
     h->n_other_kernels += 1 + (epoch > 1 ? 1 : 0);
+    h->n_copies += 10;
     if (ab) {                             // the neighbours swap their arrays in lockstep
         for (int d = 0; d < 2; ++d) { double *t = h->peer_A[d]; h->peer_A[d] = h->peer_B[d]; h->peer_B[d] = t; }
     }
@@ -956,38 +959,6 @@ static int step_impl(d3q19_handle *h, const StepParams &p, double *written) {
         RK_((launch_step_halo<SK, STRICT, GENERIC>(h, p)));
         trace_mark(h, 2, h->sc); trace_mark(h, 3, h->sc);
         trace_next(h);
-        return 0;
-    }
-    if (h->bstream && !GENERIC && lz > 2) {
-        // "Boundary stream": only the two boundary planes of step k need the faces of step k-1; the interior needs the
-        // boundary planes of step k-1 and nothing that travels.  So the interior launches follow one another on sc
-        // without ever waiting for an exchange, and the boundary launch of step k runs NEXT TO the interior launch of
-        // step k on a high-priority stream instead of in front of it (no drain/refill of the GPU around a 2-plane
-        // kernel, which is what the in-order sequence loses on thin slabs).  Order:
-        //   B(k) after everything enqueued on sc so far (I(k-1), readers) and after X(k-1);   on sb
-        //   I(k) after I(k-1) (stream order) and B(k-1);                                      on sc
-        //   X(k) after B(k) and X(k-1) (stream order);                                        on sx
-        // No node of B(k) touches an address a node of I(k) touches (disjoint nodes; in the in-place odd step every
-        // address belongs to exactly one node), X(k) runs next to I(k) as before, and X(k) next to I(k+1) is new but
-        // disjoint as well: X touches ghost planes, or after an odd step the slots of planes 1 / lz that only the
-        // neighbour's nodes own, or reads (packs) face slots that the next interior launch does not write.
-        if (h->b_pending) CK(cudaStreamWaitEvent(h->sc, h->evB, 0));
-        CK(cudaEventRecord(h->evI, h->sc));
-        CK(cudaStreamWaitEvent(h->sb, h->evI, 0));
-        if (h->exchange_pending) CK(cudaStreamWaitEvent(h->sb, h->evX, 0));
-        trace_mark(h, 0, h->sb);
-        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 2, h->sb, lz - 1)));       // planes 1 and lz in one launch
-        CK(cudaEventRecord(h->evB, h->sb));
-        trace_mark(h, 1, h->sb);
-        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 2, lz - 2, h->sc)));
-        trace_mark(h, 2, h->sc);
-        CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
-        RK_(exchange_after_step(h, SK, written, h->sx));
-        CK(cudaEventRecord(h->evX, h->sx));
-        trace_mark(h, 3, h->sx);
-        trace_next(h);
-        h->exchange_pending = true;
-        h->b_pending = true;
         return 0;
     }
     // boundary planes first, so that their faces travel while the interior is computed
@@ -1283,8 +1254,10 @@ extern "C" int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_
     if (!h->cfg.ipart) return fail("d3q19_particles_init: create the handle with ipart = 1");
     if (h->halo_on) return fail("d3q19_particles_init: the particle path exchanges its halo through NCCL (do not call d3q19_ipc_connect)");
     if (!h->idx32) return fail("d3q19_particles_init: slab too large for 32-bit link indices");
-    if (2.0 * prm->rad + 4.0 > h->cfg.ny || 2.0 * prm->rad + 4.0 > h->cfg.nz) return fail("d3q19_particles_init: particle larger than the periodic box");
+    // a particle's bounding box (< 2 rad + 6 nodes wide) must be smaller than the periodic box: no node is visited twice
+    if (2.0 * prm->rad + 7.0 > h->cfg.ny || 2.0 * prm->rad + 7.0 > h->cfg.nz) return fail("d3q19_particles_init: particle larger than the periodic box (2 rad + 7 <= ny, nz)");
     if (prm->rad > 600.0) return fail("d3q19_particles_init: rad %g: a particle's bounding box must hold fewer than 2^31 nodes", prm->rad);
+    if (npart > 0x3ffffff0) return fail("d3q19_particles_init: too many particles");
     h->pp = *prm;
     if (h->ypglb) { cudaFree(h->ypglb); cudaFree(h->wp); cudaFree(h->omgp); }
     if (h->solid) { cudaFree(h->solid); h->solid = nullptr; }
@@ -1294,23 +1267,25 @@ extern "C" int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_
     CK(cudaMalloc(&h->pbuf, 10 * tb * sizeof(double)));
     CK(cudaMemsetAsync(h->pbuf, 0, 10 * tb * sizeof(double), h->sc));
     double *q = h->pbuf;
-    h->ypglb = q; q += tb; h->ypglb0 = q; q += tb; h->wp = q; q += tb; h->omgp = q; q += tb; h->fHIp = q; q += tb;
+    h->ypglb = q; q += tb; h->ypmask = q; q += tb; h->wp = q; q += tb; h->omgp = q; q += tb; h->fHIp = q; q += tb;
     h->torqp = q; q += tb; h->flubp = q; q += tb; h->forcepp = q; q += tb; h->torqpp = q; q += tb; h->thetap = q;
     const size_t nown = (size_t)h->g.plane * (h->g.lz + 2);
     CK(cudaMalloc(&h->own, nown * sizeof(int32_t)));
-    CK(cudaMalloc(&h->own0, nown * sizeof(int32_t)));
     CK(cudaMemsetAsync(h->own, 0xFF, nown * sizeof(int32_t), h->sc));
-    CK(cudaMemsetAsync(h->own0, 0xFF, nown * sizeof(int32_t), h->sc));
     const double pi = 4.0 * atan(1.0);
     h->maxlink = prm->maxlink > 0 ? prm->maxlink : (long long)(8.0 * npart * 4.0 * pi * (prm->rad + 1.0) * (prm->rad + 1.0)) + 64;
     CK(cudaMalloc(&h->links.node, h->maxlink * sizeof(uint32_t)));
     CK(cudaMalloc(&h->links.dir, h->maxlink * sizeof(int32_t)));
     CK(cudaMalloc(&h->links.part, h->maxlink * sizeof(int32_t)));
     CK(cudaMalloc(&h->links.q, h->maxlink * sizeof(double)));
-    CK(cudaMalloc(&h->lcount, ((size_t)npart * PART_SPLIT + 1) * sizeof(long long)));
-    CK(cudaMalloc(&h->loffset, ((size_t)npart * PART_SPLIT + 1) * sizeof(long long)));
-    CK(cudaMalloc(&h->nfilled_dev, 2 * sizeof(unsigned long long)));      // [0] refilled nodes, [1] link-list overflow word
-    CK(cudaMemsetAsync(h->nfilled_dev, 0, 2 * sizeof(unsigned long long), h->sc));
+    CK(cudaMalloc(&h->pcnt, 4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(h->pcnt, 0, 4 * sizeof(unsigned long long), h->sc));
+    // a mask update uncovers at most a surface layer of every particle: the link capacity bounds it
+    h->fill.cap = h->maxlink;
+    CK(cudaMalloc(&h->fill.node, h->fill.cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->fill.part, h->fill.cap * sizeof(int32_t)));
+    h->fill.count = h->pcnt + 1;
+    h->part_rows = part_max_rows(prm->rad);
     const double volp = 4.0 / 3.0 * pi * prm->rad * prm->rad * prm->rad;      // para.f90:340
     h->amp = h->cfg.rhopart * volp;                                           // :341
     h->aip = 0.4 * h->amp * prm->rad * prm->rad;                              // :342
@@ -1338,7 +1313,13 @@ extern "C" int d3q19_set_particles(d3q19_handle *h, int32_t npart, const double 
     CK(cudaMemcpyAsync(h->ypglb, ypglb, nb, cudaMemcpyHostToDevice, h->sc));
     CK(cudaMemcpyAsync(h->wp, wp, nb, cudaMemcpyHostToDevice, h->sc));
     CK(cudaMemcpyAsync(h->omgp, omgp, nb, cudaMemcpyHostToDevice, h->sc));
-    if (h->part_on) CK(cudaMemcpyAsync(h->ypglb0, ypglb, nb, cudaMemcpyHostToDevice, h->sc));
+    if (h->part_on) {
+        // the particles are PLACED, not moved: the mask starts afresh (nothing counts as uncovered, no refill)
+        const size_t nown = (size_t)h->g.plane * (h->g.lz + 2);
+        CK(cudaMemsetAsync(h->own, 0xFF, nown * sizeof(int32_t), h->sc));
+        CK(cudaMemsetAsync(h->pcnt, 0, 4 * sizeof(unsigned long long), h->sc));
+        h->mask_built = false;
+    }
     CK(cudaStreamSynchronize(h->sc));
     return 0;
 }
@@ -1346,52 +1327,54 @@ extern "C" int d3q19_set_particles(d3q19_handle *h, int32_t npart, const double 
 // the link count lives on the device (the step sequence never waits for it); the host asks when it must
 static int fetch_nlink(d3q19_handle *h) {
     if (h->nlink >= 0) return 0;
-    long long n = 0;
-    CK(cudaMemcpyAsync(&n, h->loffset + (size_t)h->npart * PART_SPLIT, sizeof n, cudaMemcpyDeviceToHost, h->sc));
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, h->pcnt, sizeof n, cudaMemcpyDeviceToHost, h->sc));
     CK(cudaStreamSynchronize(h->sc));
-    if (n > h->maxlink) return fail("d3q19_beads_links: %lld links exceed maxlink %lld", n, h->maxlink);
-    h->nlink = n;
+    if ((long long)n > h->maxlink) return fail("d3q19_beads_links: %llu links exceed maxlink %lld", n, h->maxlink);
+    h->nlink = (long long)n;
     return 0;
 }
 
-// k_beads_scan raises a device word when a link list did not fit (entries beyond maxlink are dropped by k_beads_links and
-// skipped by k_beads_ibb, which would let mass and momentum leak through the particle surface); call after a sync of sc
+// k_beads_links drops the entries beyond maxlink and k_beads_ibb skips them, which would let mass and momentum leak
+// through the particle surface unnoticed; the counters stay on the device, so this is asked where the host waits anyway
 static int check_link_overflow(d3q19_handle *h, const char *who) {
     if (!h->part_on) return 0;
-    unsigned long long n = 0;
-    CK(cudaMemcpy(&n, h->nfilled_dev + 1, sizeof n, cudaMemcpyDeviceToHost));
-    if (n) return fail("%s: a step built %llu boundary links, capacity maxlink = %lld -- links were dropped, the populations "
-                       "are void (d3q19_particle_params.maxlink)", who, n, h->maxlink);
+    unsigned long long n[2] = {0, 0};
+    CK(cudaMemcpy(n, h->pcnt, sizeof n, cudaMemcpyDeviceToHost));
+    if ((long long)n[0] > h->maxlink || (long long)n[1] > h->fill.cap)
+        return fail("%s: the last step built %llu boundary links and %llu refill nodes, capacity maxlink = %lld -- entries were "
+                    "dropped, the populations are void (d3q19_particle_params.maxlink)", who, n[0], n[1], h->maxlink);
     return 0;
 }
 
-// beads_links: solid mask from the particle table, then the boundary-link list
+static inline dim3 sweep_grid(const d3q19_handle *h) {
+    return dim3((unsigned)h->npart, (unsigned)((h->part_rows + PART_WARPS - 1) / PART_WARPS));
+}
+
+// beads_links: the solid mask follows the particle table, then the boundary-link list
 extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local) {
     CK(cudaSetDevice(h->cfg.device));
     if (!h->part_on) return fail("d3q19_beads_links: call d3q19_particles_init first");
     if (h->links_valid && h->mask_built) {
         // the particle table has not changed since the last build (d3q19_set_particles and d3q19_beads_move invalidate):
-        // rebuilding would also overwrite the previous mask that d3q19_beads_filling still has to compare against
+        // a second update would also forget which nodes the last move uncovered, which d3q19_beads_filling still needs
         if (nlink_local) { RK_(fetch_nlink(h)); *nlink_local = h->nlink; }
         return 0;
     }
     const PartGeom pg = part_geom(h);
-    const size_t nown = (size_t)h->g.plane * (h->g.lz + 2);
-    int32_t *t = h->own; h->own = h->own0; h->own0 = t;          // the old mask is what beads_filling compares against
-    h->solid = h->own + h->g.plane; h->isn = h->own + h->g.plane;
-    CK(cudaMemsetAsync(h->own, 0xFF, nown * sizeof(int32_t), h->sc));
-    const dim3 gp((unsigned)h->npart, PART_SPLIT);
-    k_beads_mask<<<gp, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own);
-    if (!h->mask_built) {                                         // first mask: nothing was uncovered
-        CK(cudaMemcpyAsync(h->own0, h->own, nown * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->sc));
-        h->mask_built = true;
+    const dim3 gs = sweep_grid(h);
+    const size_t tb = (size_t)3 * h->npart * sizeof(double);
+    CK(cudaMemsetAsync(h->pcnt, 0, 2 * sizeof(unsigned long long), h->sc));          // links, refill list
+    if (h->mask_built) {
+        k_beads_uncover<<<gs, 32 * PART_WARPS, 0, h->sc>>>(pg, h->npart, h->ypmask, h->ypglb, h->own, h->fill);
+        h->n_other_kernels++;
     }
-    const int nslot = h->npart * PART_SPLIT;
-    k_beads_links<false><<<gp, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
-    k_beads_scan<<<1, 1024, 0, h->sc>>>(nslot, h->lcount, h->loffset, h->maxlink, h->nfilled_dev + 1);
-    k_beads_links<true><<<gp, 256, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->lcount, h->loffset, h->maxlink, h->links);
+    k_beads_cover<<<gs, 32 * PART_WARPS, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own);
+    CK(cudaMemcpyAsync(h->ypmask, h->ypglb, tb, cudaMemcpyDeviceToDevice, h->sc));
+    h->mask_built = true;
+    k_beads_links<<<gs, 32 * PART_WARPS, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->pcnt, h->maxlink, h->links);
     CK(cudaGetLastError());
-    h->n_other_kernels += 4;
+    h->n_other_kernels += 2;
     h->links_valid = true;
     h->nlink = -1;                                                // known on the device; fetched on demand
     if (nlink_local) { RK_(fetch_nlink(h)); *nlink_local = h->nlink; }
@@ -1408,7 +1391,7 @@ extern "C" int d3q19_beads_collision(d3q19_handle *h) {
     {
         IbbParams P;
         P.pg = part_geom(h); P.S = h->A; P.own = h->own; P.L = h->links;
-        P.nlink_dev = h->loffset + (size_t)h->npart * PART_SPLIT; P.maxlink = h->maxlink;
+        P.nlink_dev = h->pcnt; P.maxlink = h->maxlink;
         P.ypglb = h->ypglb; P.wp = h->wp; P.omgp = h->omgp; P.rho0 = h->pp.rho0; P.fHIp = h->fHIp; P.torqp = h->torqp;
         // the count is on the device: size the grid for the known count if the host has it, else for the capacity
         const long long nthreads = h->nlink >= 0 ? h->nlink : h->maxlink;
@@ -1431,26 +1414,28 @@ extern "C" int d3q19_beads_collision(d3q19_handle *h) {
     return 0;
 }
 
+static int lubmove(d3q19_handle *h, int do_lub, int do_move) {
+    LubParams lp = {h->pp.mingap, h->pp.mingap_w, h->pp.stf0, h->pp.stf1, h->pp.stf0_w, h->pp.stf1_w, h->pp.fscale};
+    MoveParams M = {h->amp, h->aip, h->pp.gforce[0], h->pp.gforce[1], h->pp.gforce[2], h->fHIp, h->torqp, h->flubp,
+                    h->forcepp, h->torqpp, h->ypglb, h->wp, h->omgp, h->thetap};
+    const int nt = h->npart < 1024 ? ((h->npart + 31) / 32) * 32 : 1024;
+    k_beads_lubmove<<<1, nt, 0, h->sc>>>(part_geom(h), h->npart, h->ypglb, lp, h->flubp, M, do_lub, do_move);
+    CK(cudaGetLastError());
+    h->n_other_kernels++;
+    if (do_move) h->links_valid = false;
+    return 0;
+}
+
 extern "C" int d3q19_beads_lubforce(d3q19_handle *h) {
     CK(cudaSetDevice(h->cfg.device));
     if (!h->part_on) return fail("d3q19_beads_lubforce: call d3q19_particles_init first");
-    LubParams lp = {h->pp.mingap, h->pp.mingap_w, h->pp.stf0, h->pp.stf1, h->pp.stf0_w, h->pp.stf1_w, h->pp.fscale};
-    k_beads_lubforce<<<(h->npart + 127) / 128, 128, 0, h->sc>>>(part_geom(h), h->npart, h->ypglb, lp, h->flubp);
-    CK(cudaGetLastError());
-    h->n_other_kernels++;
-    return 0;
+    return lubmove(h, 1, 0);
 }
 
 extern "C" int d3q19_beads_move(d3q19_handle *h) {
     CK(cudaSetDevice(h->cfg.device));
     if (!h->part_on) return fail("d3q19_beads_move: call d3q19_particles_init first");
-    MoveParams M = {h->amp, h->aip, h->pp.gforce[0], h->pp.gforce[1], h->pp.gforce[2], h->fHIp, h->torqp, h->flubp,
-                    h->forcepp, h->torqpp, h->ypglb, h->ypglb0, h->wp, h->omgp, h->thetap};
-    k_beads_move<<<(h->npart + 127) / 128, 128, 0, h->sc>>>(part_geom(h), h->npart, M);
-    CK(cudaGetLastError());
-    h->n_other_kernels++;
-    h->links_valid = false;
-    return 0;
+    return lubmove(h, 0, 1);
 }
 
 // beads_filling: populations of the nodes the last move uncovered (needs the rebuilt mask)
@@ -1458,10 +1443,10 @@ extern "C" int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled) {
     CK(cudaSetDevice(h->cfg.device));
     if (!h->part_on || !h->links_valid) return fail("d3q19_beads_filling: rebuild the mask first (d3q19_beads_links)");
     RK_(wait_exchange(h));
-    CK(cudaMemsetAsync(h->nfilled_dev, 0, sizeof(unsigned long long), h->sc));
+    CK(cudaMemsetAsync(h->pcnt + 2, 0, sizeof(unsigned long long), h->sc));
     FillParams P;
-    P.pg = part_geom(h); P.S = h->A; P.own0 = h->own0; P.own = h->own; P.ypglb0 = h->ypglb0;
-    P.ypglb = h->ypglb; P.wp = h->wp; P.omgp = h->omgp; P.nfilled = h->nfilled_dev;
+    P.pg = part_geom(h); P.S = h->A; P.own = h->own; P.F = h->fill;
+    P.ypglb = h->ypglb; P.wp = h->wp; P.omgp = h->omgp; P.nfilled = h->pcnt + 2;
     P.ghost_lo = P.ghost_hi = nullptr;
     if (h->cfg.nranks > 1) {
         // source nodes across a slab face: all 19 canonical populations of the neighbours' planes next to the faces
@@ -1470,14 +1455,11 @@ extern "C" int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled) {
         const size_t cnt = (size_t)NPOP * g.plane;
         if (!h->fill_halo) CK(cudaMalloc(&h->fill_halo, 4 * cnt * sizeof(double)));
         double *send_up = h->fill_halo, *send_dn = send_up + cnt, *ghost_lo = send_dn + cnt, *ghost_hi = ghost_lo + cnt;
-        const dim3 gp = grid_nodes(h, 1);
+        const dim3 gp = grid_nodes(h, 2);             // blockIdx.z: 0 -> plane lz into send_up, 1 -> plane 1 into send_dn
         switch (read_kind(h)) {
-        case READ_DIRECT: k_plane_gather<READ_DIRECT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz);
-                          k_plane_gather<READ_DIRECT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_dn, 1); break;
-        case READ_PULL_NAT: k_plane_gather<READ_PULL_NAT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz);
-                            k_plane_gather<READ_PULL_NAT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_dn, 1); break;
-        default: k_plane_gather<READ_PULL_SWAP><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz);
-                 k_plane_gather<READ_PULL_SWAP><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_dn, 1); break;
+        case READ_DIRECT: k_plane_gather<READ_DIRECT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz, send_dn, 1); break;
+        case READ_PULL_NAT: k_plane_gather<READ_PULL_NAT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz, send_dn, 1); break;
+        default: k_plane_gather<READ_PULL_SWAP><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz, send_dn, 1); break;
         }
         CK(cudaGetLastError());
         const int up = (h->cfg.rank + 1) % h->cfg.nranks, dn = (h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks;
@@ -1488,21 +1470,25 @@ extern "C" int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled) {
         NK(n.Recv(ghost_lo, cnt, NCCL_FLOAT64, dn, h->comm, h->sc));
         NK(n.Recv(ghost_hi, cnt, NCCL_FLOAT64, up, h->comm, h->sc));
         NK(n.GroupEnd());
-        h->n_other_kernels += 2;
+        h->n_other_kernels += 1;
         h->n_nccl += 4;
         P.ghost_lo = ghost_lo; P.ghost_hi = ghost_hi;
     }
-    const dim3 gp((unsigned)h->npart, PART_SPLIT);
+    // the list length is on the device: a grid for a generous share of the capacity, the threads beyond the list leave at once
+    // (one move uncovers a thin layer: far fewer nodes than there are links)
+    const unsigned nb = (unsigned)((h->fill.cap + 127) / 128);
     switch (read_kind(h)) {
-    case READ_DIRECT: k_beads_fill<READ_DIRECT><<<gp, 128, 0, h->sc>>>(P); break;
-    case READ_PULL_NAT: k_beads_fill<READ_PULL_NAT><<<gp, 128, 0, h->sc>>>(P); break;
-    default: k_beads_fill<READ_PULL_SWAP><<<gp, 128, 0, h->sc>>>(P); break;
+    case READ_DIRECT: k_beads_fill<READ_DIRECT><<<nb, 128, 0, h->sc>>>(P); break;
+    case READ_PULL_NAT: k_beads_fill<READ_PULL_NAT><<<nb, 128, 0, h->sc>>>(P); break;
+    default: k_beads_fill<READ_PULL_SWAP><<<nb, 128, 0, h->sc>>>(P); break;
     }
+    // the list is consumed: a second call before the next move fills nothing
+    CK(cudaMemsetAsync(h->pcnt + 1, 0, sizeof(unsigned long long), h->sc));
     CK(cudaGetLastError());
     h->n_other_kernels++;
     if (nfilled) {
         unsigned long long n = 0;
-        CK(cudaMemcpyAsync(&n, h->nfilled_dev, sizeof n, cudaMemcpyDeviceToHost, h->sc));
+        CK(cudaMemcpyAsync(&n, h->pcnt + 2, sizeof n, cudaMemcpyDeviceToHost, h->sc));
         CK(cudaStreamSynchronize(h->sc));
         *nfilled = (int64_t)n;
     }
@@ -1518,8 +1504,7 @@ extern "C" int d3q19_particle_step(d3q19_handle *h, int32_t move) {
     RK_(collide_stream_impl(h, D3Q19_MACRO_MAIN, nullptr));       // fluid nodes only (solid nodes skipped)
     RK_(d3q19_beads_collision(h));
     if (move) {
-        RK_(d3q19_beads_lubforce(h));
-        RK_(d3q19_beads_move(h));
+        RK_(lubmove(h, 1, 1));                                      // beads_lubforce + beads_move
         RK_(d3q19_beads_links(h, nullptr));
         RK_(d3q19_beads_filling(h, nullptr));
     }
@@ -1570,6 +1555,9 @@ extern "C" int d3q19_get_mask(d3q19_handle *h, int32_t *own_lx_ly_lz) {
     CK(cudaMemcpy2DAsync(own_lx_ly_lz, (size_t)g.lx * sizeof(int32_t), h->own + g.plane, (size_t)g.xp * sizeof(int32_t),
                          (size_t)g.lx * sizeof(int32_t), (size_t)g.ly * g.lz, cudaMemcpyDeviceToHost, h->sc));
     CK(cudaStreamSynchronize(h->sc));
+    // "uncovered by q in the last update" (-(q+2), particles.cuh) is fluid: the caller sees isnodes = -1 there
+    const size_t nn = (size_t)g.lx * g.ly * g.lz;
+    for (size_t i = 0; i < nn; ++i) if (own_lx_ly_lz[i] < 0) own_lx_ly_lz[i] = -1;
     return 0;
 }
 
@@ -1752,14 +1740,13 @@ extern "C" int d3q19_get_counters(d3q19_handle *h, int64_t out[8]) {
 // pageable memory are staged by the CUDA driver at a fraction of the PCIe rate, and they are what the end-to-end
 // time of the intact driver consists of beyond the step kernels (f up once, rho,u down on output steps), so
 // large arrays are page-locked in place.  Arrays below 64 MB (tests) are left alone; memory that is pinned
-// already (bench.py, torch) reports so and is left alone too; D3Q19_NO_PIN=1 switches this off.
+// already (bench.py, torch) reports so and is left alone too.
 static void shim_unpin(d3q19_handle *h) {
     for (int i = 0; i < h->shim.npinned; ++i)
         if (h->shim.pinned[i] && cudaHostUnregister(h->shim.pinned[i]) != cudaSuccess) cudaGetLastError();
     h->shim.npinned = 0;
 }
 static void shim_pin(d3q19_handle *h) {
-    if (getenv("D3Q19_NO_PIN")) return;
     const size_t n = (size_t)h->g.lx * h->g.ly * h->g.lz * sizeof(double);
     if (n < ((size_t)64 << 20)) return;
     cudaSetDevice(h->cfg.device);

@@ -52,6 +52,15 @@ constexpr int BLOCK_X = D3Q_BLOCK_X;
 #ifndef D3Q_HINT
 #define D3Q_HINT 0
 #endif
+// 1: warps that hold no wall-adjacent node take accessors without the wall select (see Gather<>::load_nowall)
+#ifndef D3Q_WALLSPLIT
+#define D3Q_WALLSPLIT 1
+#endif
+// 1: the in-place steps' L2 prefetch is issued by lane i for population i (2 instructions per warp), 0: by one lane per
+// 128-byte line for all 19 populations
+#ifndef D3Q_PF_LEAN
+#define D3Q_PF_LEAN 1
+#endif
 #ifndef D3Q_ADDR                 // 0: wall handled by an offset select; 1: by a predicated second access
 #define D3Q_ADDR 0
 #endif
@@ -226,6 +235,18 @@ struct Gather {
         if (!can_bounce) return reg;
         return at_wall(k) ? (long long)slot_wall * g.slab + (long long)k.n : reg;
     }
+    // warps none of whose nodes sits next to a wall (all but the first and the last warp of an x-row): the population
+    // base A + slot*slab is warp-uniform and the element offset is one of the nine row bases minus a literal c_x, so
+    // an access costs no select and no per-thread 64-bit multiply (SASS: 259 integer instructions per node in the
+    // in-place odd step with the select on every access, round 2)
+    template <class IDX>
+    static __device__ __forceinline__ double load_nowall(const double *A, const Geom &g, const NodeIdx<IDX> &k) {
+        return pop_load(A + (long long)slot_nb * g.slab + (long long)index_nb(k));
+    }
+    template <class IDX>
+    static __device__ __forceinline__ void store_back_nowall(double *A, const Geom &g, const NodeIdx<IDX> &k, double v) {
+        pop_store(A + (long long)slot_nb * g.slab + (long long)index_nb(k), v);
+    }
     template <class IDX>
     static __device__ __forceinline__ double load(const double *A, const Geom &g, const NodeIdx<IDX> &k) {
 #if D3Q_EXP & 2
@@ -277,6 +298,14 @@ struct Gather {
 #endif
     }
 };
+
+template <int RK, class IDX>
+__device__ __forceinline__ void gather19_nowall(const double *A, const Geom &g, const NodeIdx<IDX> &k, double (&f)[NPOP]) {
+    static_for<NPOP>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        f[i] = Gather<RK, i>::load_nowall(A, g, k);
+    });
+}
 
 template <int RK, class IDX>
 __device__ __forceinline__ void gather19(const double *A, const Geom &g, const NodeIdx<IDX> &k, double (&f)[NPOP]) {
@@ -334,6 +363,19 @@ k_step(const __grid_constant__ StepParams p) {
         const NodeIdx<IDX> k = make_node<IDX>(g, x, blockIdx.y, zg_blk);
         constexpr int RK = (SK == STEP_AB) ? READ_PULL_NAT : (SK == STEP_AA_EVEN ? READ_DIRECT : READ_PULL_SWAP);
         double f[NPOP];
+#if D3Q_PF_LEAN
+        if (SK != STEP_AB && p.pf_ahead > 0) {
+            // lane i < 19 asks for population i: the two 128-byte lines of this warp's 32 nodes, pf_ahead elements ahead
+            // (2 prefetch instructions per warp instead of 19 per line)
+            const int lane = threadIdx.x & 31;
+            const long long ahead = (long long)k.n - lane + p.pf_ahead;
+            if (lane < NPOP && ahead + 16 < g.slab) {      // stays inside the population
+                const double *q = p.A + (long long)lane * g.slab + ahead;
+                prefetch_l2(q);
+                prefetch_l2(q + 16);
+            }
+        }
+#else
         if (SK != STEP_AB && p.pf_ahead > 0 && (threadIdx.x & 15) == 0) {
             const long long ahead = (long long)k.n + p.pf_ahead;
             if (ahead < g.slab) {          // stays inside the population (the last rows run into the upper ghost plane)
@@ -341,7 +383,12 @@ k_step(const __grid_constant__ StepParams p) {
                 for (int i = 0; i < NPOP; ++i) prefetch_l2(p.A + (long long)i * g.slab + ahead);
             }
         }
-        gather19<RK>(p.A, g, k, f);
+#endif
+        // a warp covers 32 consecutive x: it touches a wall only if it holds x = 0 or x = lx-1 (warp-uniform)
+        const int xw = x & ~31;
+        const bool wallwarp = !D3Q_WALLSPLIT || (RK != READ_DIRECT && (xw == 0 || xw + 31 >= g.lx - 1));
+        if (wallwarp) gather19<RK>(p.A, g, k, f);
+        else gather19_nowall<RK>(p.A, g, k, f);
 
         double Fx = p.Fx, Fy = p.Fy, Fz = p.Fz;
         bool is_solid = false;
@@ -403,11 +450,18 @@ k_step(const __grid_constant__ StepParams p) {
                     pop_store(p.halo.peer_dn + (long long)dir_opp(i) * p.halo.slab_dn + (long long)(p.halo.lz_dn + 1) * g.plane + inplane, f[i]);
             });
         } else {
-            static_for<NPOP>([&](auto ic) {
-                constexpr int i = decltype(ic)::value;
-                if (HALO) Gather<READ_PULL_SWAP, i>::store_back_halo(p.A, g, k, f[dir_opp(i)], p.halo);
-                else Gather<READ_PULL_SWAP, i>::store_back(p.A, g, k, f[dir_opp(i)]);
-            });
+            if (HALO || wallwarp) {
+                static_for<NPOP>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    if (HALO) Gather<READ_PULL_SWAP, i>::store_back_halo(p.A, g, k, f[dir_opp(i)], p.halo);
+                    else Gather<READ_PULL_SWAP, i>::store_back(p.A, g, k, f[dir_opp(i)]);
+                });
+            } else {
+                static_for<NPOP>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    Gather<READ_PULL_SWAP, i>::store_back_nowall(p.A, g, k, f[dir_opp(i)]);
+                });
+            }
         }
     }
     if (HALO) {
@@ -688,6 +742,63 @@ __global__ void __launch_bounds__(BLOCK_X) k_vortcalc(const __grid_constant__ Vo
     p.oz[m] = (pvx - puy).v;
 }
 
+// ---- local strain rate from the non-equilibrium moments (sijstat00, saveload.f90:2031-2091) ----------------
+// Sij*Sij of every fluid node from its 19 populations (canonical = post-streaming, whatever the storage phase) and
+// the rho,u arrays macrovar left on the device: the second-order moments minus their equilibria, times their
+// relaxation rates, ARE the strain-rate tensor up to constants (Yu et al. 2006) -- node-local, no differences, no
+// halo.  The sums are collision_MRT's; the reference's expression order without contraction: bit-identical to the
+// translated reference.  Solid nodes get 0 (the reference leaves its automatic array undefined there).
+struct SijParams {
+    Geom g;
+    const double *A;
+    const double *rho, *ux, *uy, *uz;   // [lz][ly][xp]
+    const int32_t *solid;               // > 0 solid, or nullptr
+    double s1, s9;
+    double *sij2;                       // [lz][ly][xp]
+};
+template <int RK>
+__global__ void __launch_bounds__(BLOCK_X) k_sijstat(const __grid_constant__ SijParams p) {
+    const Geom &g = p.g;
+    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
+    if (x >= g.lx) return;
+    const int y = blockIdx.y, zg = 1 + blockIdx.z;
+    const long long m = x + (long long)g.xp * (y + (long long)g.ly * (zg - 1));
+    if (p.solid && p.solid[m] > 0) { p.sij2[m] = 0.0; return; }
+    const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, y, zg);
+    double f[NPOP];
+    gather19<RK>(p.A, g, k, f);
+    const R coef2(-11.0), coef3(8.0), coef5(2.0);                      // para.f90:144-147
+    const R rho9(p.rho[m]), ux9(p.ux[m]), uy9(p.uy[m]), uz9(p.uz[m]);
+    const R ux9s = ux9 * ux9, uy9s = uy9 * uy9, uz9s = uz9 * uz9;
+    const R eqm1 = -(R(11.0) * rho9) + R(19.0) * ((ux9s + uy9s) + uz9s);
+    const R eqm6 = (R(2.0) * ux9s - uy9s) - uz9s;
+    const R eqm8 = uy9s - uz9s;
+    const R eqm10 = ux9 * uy9, eqm11 = uy9 * uz9, eqm12 = ux9 * uz9;
+    auto F = [&](int i) { return R(f[i]); };
+    const R sum1 = ((((F(1) + F(2)) + F(3)) + F(4)) + F(5)) + F(6);
+    const R sum2 = ((((((((((F(7) + F(8)) + F(9)) + F(10)) + F(11)) + F(12)) + F(13)) + F(14)) + F(15)) + F(16)) + F(17)) + F(18);
+    const R sum6 = F(1) + F(2);
+    const R sum7 = ((F(3) + F(4)) + F(5)) + F(6);
+    const R sum8 = ((((((F(7) + F(8)) + F(9)) + F(10)) + F(11)) + F(12)) + F(13)) + F(14);
+    const R sum9 = ((F(15) + F(16)) + F(17)) + F(18);
+    const R sum10 = ((F(3) + F(4)) - F(5)) - F(6);
+    const R sum11 = ((((((F(7) + F(8)) + F(9)) + F(10)) - F(11)) - F(12)) - F(13)) - F(14);
+    const R evlm1 = (-(R(30.0) * F(0)) + coef2 * sum1) + coef3 * sum2;
+    const R evlm6 = ((coef5 * sum6 - sum7) + sum8) - coef5 * sum9;
+    const R evlm8 = sum10 + sum11;
+    const R evlm10 = ((F(7) - F(8)) - F(9)) + F(10);
+    const R evlm11 = ((F(15) - F(16)) - F(17)) + F(18);
+    const R evlm12 = ((F(11) - F(12)) - F(13)) + F(14);
+    const R s1(p.s1), s9(p.s9);
+    const R neqm1 = s1 * (evlm1 - eqm1), neqm9 = s9 * (evlm6 - eqm6), neqm11 = s9 * (evlm8 - eqm8);
+    const R neqm13 = s9 * (evlm10 - eqm10), neqm14 = s9 * (evlm11 - eqm11), neqm15 = s9 * (evlm12 - eqm12);
+    const R Sxx = -R(__ddiv_rn((neqm1 + R(19.0) * neqm9).v, 38.0));
+    const R Syy = -R(__ddiv_rn((R(2.0) * neqm1 - R(19.0) * (neqm9 - R(3.0) * neqm11)).v, 76.0));
+    const R Szz = -R(__ddiv_rn((R(2.0) * neqm1 - R(19.0) * (neqm9 + R(3.0) * neqm11)).v, 76.0));
+    const R Sxy = -(R(1.5) * neqm13), Syz = -(R(1.5) * neqm14), Szx = -(R(1.5) * neqm15);
+    p.sij2[m] = (((Sxx * Sxx + Syy * Syy) + Szz * Szz) + R(2.0) * ((Sxy * Sxy + Syz * Syz) + Szx * Szx)).v;
+}
+
 // ---- FORCINGP (collision.f90:529-602) ------------------------------------------------------------------
 // Time-dependent perturbation force in two near-wall x-bands on top of the uniform (0, force_in_y, 0):
 // band 1 = nodes ixs0+1 .. ixs0+ihh, band 2 = nodes nx-ixs0-ihh+1 .. nx-ixs0 (1-based), ihh = lxh/2.
@@ -833,55 +944,19 @@ __global__ void __launch_bounds__(BLOCK_X) k_face_unpack(Geom g, double *A, Face
         fp.buf[face][(long long)s * g.plane + (long long)y * g.xp + x];
 }
 
-// ---- z-face "put" (third halo transport) ---------------------------------------------
-// A small copy kernel on the high-priority stream stores the five outgoing populations of both faces
-// straight into the neighbour GPUs' arrays (cudaIpc-mapped) and its last block raises the neighbours'
-// flags -- the halo_spin protocol of the fused path, but the remote stores and their system fence sit in
-// 128-thread blocks that need few registers and so co-reside with the interior step kernel (NCCL's
-// send/recv kernel needs most of an SM and, measured, only runs once the interior kernel drains).
-// Source / destination planes and slots are those of exchange_after_step: AB and AA-even copy my boundary
-// plane into the neighbour's ghost plane; AA-odd copies my ghost plane (where the step pushed across the
-// face) into the neighbour's real plane with the wall-adjacent exclusions of collision.f90:361-368.
-struct FacePut {
-    const double *src;            // my array (the one the step wrote)
-    double *dst[2];               // [0]: the upper neighbour's array, [1]: the lower neighbour's
-    long long slab_dst[2];
-    int zsrc[2], zdst[2];         // ghosted plane indices
-    FaceSlots slots[2];
-    int exclude_walls;
-    unsigned int *ctr;            // local block counter
-    unsigned int *sig[2];         // the upper neighbour's wait_lo, the lower neighbour's wait_hi
-    unsigned int epoch, nblk;
-};
-__global__ void __launch_bounds__(BLOCK_X) k_face_put(Geom g, FacePut fp) {
-    const int x = blockIdx.x * BLOCK_X + threadIdx.x;
-    const int y = blockIdx.y, face = blockIdx.z / 5, s = blockIdx.z % 5;
-    if (x < g.lx) {
-        const int slot = fp.slots[face].s[s];
-        bool skip = false;
-        if (fp.exclude_walls) {
-            const int cx = (slot == 11 || slot == 13 || slot == 7 || slot == 9 || slot == 1) ? 1
-                         : ((slot == 12 || slot == 14 || slot == 8 || slot == 10 || slot == 2) ? -1 : 0);
-            skip = (cx > 0 && x == 0) || (cx < 0 && x == g.lx - 1);
-        }
-        if (!skip) {
-            const long long inpl = (long long)y * g.xp + x;
-            fp.dst[face][(long long)slot * fp.slab_dst[face] + (long long)fp.zdst[face] * g.plane + inpl] =
-                fp.src[(long long)slot * g.slab + (long long)fp.zsrc[face] * g.plane + inpl];
-        }
-    }
-    // the last block of the grid: every remote store is visible -> raise both neighbours' flags
+// ---- z-face "put" (halo transport by the copy engines) --------------------------------
+// The faces are device-to-device copies over NVLink enqueued by the host (d3q19_api.cu launch_step_put); what is
+// left for a kernel is to tell the neighbours that their planes are complete: one thread, after the copies in stream
+// order, raises the upper neighbour's wait_lo and the lower neighbour's wait_hi to the step number (halo_spin protocol).
+__host__ __device__ inline int dir_cx_rt(int slot) {
+    return (slot == 11 || slot == 13 || slot == 7 || slot == 9 || slot == 1) ? 1
+         : ((slot == 12 || slot == 14 || slot == 8 || slot == 10 || slot == 2) ? -1 : 0);
+}
+__global__ void k_flag_raise(unsigned int *sig_up, unsigned int *sig_dn, unsigned int epoch) {
     __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(fp.ctr, 1u);
-        if (prev == fp.nblk - 1u) {
-            *fp.ctr = 0u;
-            __threadfence_system();
-            *(volatile unsigned int *)fp.sig[0] = fp.epoch;
-            *(volatile unsigned int *)fp.sig[1] = fp.epoch;
-        }
-    }
+    *(volatile unsigned int *)sig_up = epoch;
+    *(volatile unsigned int *)sig_dn = epoch;
+    __threadfence_system();
 }
 
 // ---- reductions ------------------------------------------------------------------------------------

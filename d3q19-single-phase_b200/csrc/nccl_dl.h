@@ -15,10 +15,30 @@ typedef struct ncclComm *NcclComm;
 enum { NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8 };   // ncclDataType_t
 enum { NCCL_SUM = 0, NCCL_MAX = 2 };                          // ncclRedOp_t
 
+// ncclConfig_t as of NCCL 2.18 (nccl.h: size, magic, version, then the user fields; later versions append fields and
+// accept an older, shorter struct by its `size` and `version`).  Only maxCTAs is set here: the z faces are a few MB, and
+// every CTA of NCCL's send/recv kernel occupies an SM next to the interior step kernel.
+struct NcclConfig218 {
+    size_t size;
+    unsigned int magic;
+    unsigned int version;
+    int blocking, cgaClusterSize, minCTAs, maxCTAs;
+    const char *netName;
+    int splitShare;
+};
+inline NcclConfig218 nccl_config_max_ctas(int max_ctas) {
+    const int undef = -2147483647 - 1;          // NCCL_CONFIG_UNDEF_INT
+    NcclConfig218 c;
+    c.size = sizeof(NcclConfig218); c.magic = 0xcafebeefu; c.version = 21800u;
+    c.blocking = undef; c.cgaClusterSize = undef; c.minCTAs = undef; c.maxCTAs = max_ctas; c.netName = nullptr; c.splitShare = undef;
+    return c;
+}
+
 struct NcclApi {
     void *lib = nullptr;
     int (*GetUniqueId)(NcclUniqueId *) = nullptr;
     int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+    int (*CommInitRankConfig)(NcclComm *, int, NcclUniqueId, int, NcclConfig218 *) = nullptr;   // NCCL >= 2.14, optional
     int (*CommDestroy)(NcclComm) = nullptr;
     int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
@@ -47,6 +67,7 @@ struct NcclApi {
     if (!field) return "libnccl is missing " name;
         D3Q_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
         D3Q_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        *(void **)(&CommInitRankConfig) = dlsym(lib, "ncclCommInitRankConfig");
         D3Q_NCCL_SYM(CommDestroy, "ncclCommDestroy")
         D3Q_NCCL_SYM(Send, "ncclSend")
         D3Q_NCCL_SYM(Recv, "ncclRecv")

@@ -23,11 +23,24 @@
 
 namespace d3q {
 
-// lattice tables for kernels that index directions at run time (one link = one thread)
-__device__ __constant__ signed char DIR_CX[NPOP] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};
-__device__ __constant__ signed char DIR_CY[NPOP] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1};
-__device__ __constant__ signed char DIR_CZ[NPOP] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
-__device__ __constant__ signed char DIR_OPP[NPOP] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
+// Lattice tables for kernels that index directions at run time (one link = one thread, every lane another
+// direction): two bits per direction packed into a 64-bit literal and decoded in registers.  (A __constant__ array
+// indexed by a per-lane direction serialises the constant cache: 18-way in k_beads_ibb, 150 us for 10^6 links.)
+__host__ __device__ constexpr unsigned long long pack_dirs(int which) {
+    unsigned long long v = 0;
+    for (int i = 0; i < NPOP; ++i) {
+        const int c = which == 0 ? dir_cx(i) : (which == 1 ? dir_cy(i) : dir_cz(i));
+        v |= (unsigned long long)(c + 1) << (2 * i);
+    }
+    return v;
+}
+__device__ __forceinline__ int rt_cx(int i) { return (int)((pack_dirs(0) >> (2 * i)) & 3ull) - 1; }
+__device__ __forceinline__ int rt_cy(int i) { return (int)((pack_dirs(1) >> (2 * i)) & 3ull) - 1; }
+__device__ __forceinline__ int rt_cz(int i) { return (int)((pack_dirs(2) >> (2 * i)) & 3ull) - 1; }
+// ipopp (para.f90:204-206): (1,2)(3,4)(5,6) swap inside the pair, 7..10 -> 17-i, 11..14 -> 25-i, 15..18 -> 33-i
+__device__ __forceinline__ int rt_opp(int i) {
+    return i == 0 ? 0 : (i <= 6 ? ((i & 1) ? i + 1 : i - 1) : (i <= 10 ? 17 - i : (i <= 14 ? 25 - i : 33 - i)));
+}
 
 struct PartGeom {
     Geom g;
@@ -74,26 +87,104 @@ __device__ __forceinline__ int local_planes(const PartGeom &pg, int iz, int out[
     return n;
 }
 
-// ---- beads_links, part 1: solid mask (own must be preset to -1) -----------------------------------
-// grid (npart, PART_SPLIT): the box of a particle is shared by PART_SPLIT blocks
-constexpr int PART_SPLIT = 32;
-__global__ void __launch_bounds__(256) k_beads_mask(PartGeom pg, int npart, const double *ypglb, int32_t *own) {
-    const int p = blockIdx.x;
+// ---- sweeps over a particle's bounding box: one WARP per box row -------------------------------------
+// grid (npart, ceil(max rows / PART_WARPS)), PART_WARPS warps per block; warp w of block (p, by) owns row
+// by * PART_WARPS + w of particle p's box (y fastest), its lanes walk along x: the mask is read and written in
+// coalesced row pieces and a row that cannot hold anything is dropped before any memory access.
+// (Round 1 gave each THREAD a contiguous chunk of the box: 19 scattered mask loads per node, two passes plus a scan
+//  for the canonical order -- 536 us per step for 100 spheres of radius 15, profiles/r02a_launches_particles_summary.md.)
+constexpr int PART_WARPS = 8;
+inline int part_max_rows(double rad) { const int n = (int)ceil(2.0 * rad) + 6; return n * n; }      // box edge < 2 rad + 6
+
+__device__ __forceinline__ bool box_row(const BBox &b, int &jy, int &jz) {
+    const int row = (int)blockIdx.y * PART_WARPS + (int)(threadIdx.x >> 5);
+    if (row >= b.n[1] * b.n[2]) return false;
+    const int rz = row / b.n[1];
+    jz = b.lo[2] + rz;
+    jy = b.lo[1] + (row - rz * b.n[1]);
+    return true;
+}
+
+// Is node (jx, iy, iz) -- iy, iz global and wrapped -- inside the sphere at c?  Evaluated with the unwrapped
+// coordinates the sweep over c's own box uses, so that it is the very arithmetic of k_beads_cover (a box is
+// smaller than the period: d3q19_particles_init checks)
+__device__ __forceinline__ bool in_sphere_of(const PartGeom &pg, const double *c, const BBox &b, int jx, int iy, int iz, double r2) {
+    int ry = (iy - b.lo[1]) % pg.ny, rz = (iz - b.lo[2]) % pg.nz;
+    if (ry < 0) ry += pg.ny;
+    if (rz < 0) rz += pg.nz;
+    if (ry >= b.n[1] || rz >= b.n[2] || jx < b.lo[0] || jx >= b.lo[0] + b.n[0]) return false;
+    return dist2_node(c, jx, b.lo[1] + ry, b.lo[2] + rz) < r2;
+}
+
+// ---- beads_links, part 1: the solid mask follows the particles ---------------------------------------
+// ONE ghosted owner array, updated in place by two sweeps (no second array, no clearing of 4 B per node and step):
+//   k_beads_uncover  over the box of the position the mask was built with (ypmask): a node owned by p that the
+//                    NEW sphere of p no longer covers becomes -(p+2) -- "uncovered by p in this update", fluid to
+//                    every reader (they test own > 0) -- and goes onto the refill list; markers left by the previous
+//                    update (they lie within rad + 1 of ypmask) go back to -1;
+//   k_beads_cover    over the box of the new position: nodes inside the sphere get p+1, the lowest id wins where
+//                    spheres overlap (also over a marker: another particle may cover what p left).
+// After both, own == -1: fluid before and after; own == -(q+2): solid before, fluid now (what beads_filling
+// rebuilds, and never a refill source); own > 0: solid now.  This is what the oracle's pair (own0, own) encodes.
+struct FillList {
+    uint32_t *node;               // ghosted in-slab index of an uncovered node of this slab
+    int32_t *part;                // the particle that left it, 1-based
+    unsigned long long *count;
+    long long cap;
+};
+
+__global__ void __launch_bounds__(32 * PART_WARPS) k_beads_uncover(PartGeom pg, int npart, const double *ypmask, const double *ypglb,
+                                                                   int32_t *own, FillList F) {
+    const int p = blockIdx.x, lane = threadIdx.x & 31;
+    const double *c0 = ypmask + 3 * p, *c1 = ypglb + 3 * p;
+    const BBox b = part_bbox(pg, c0), b1 = part_bbox(pg, c1);
+    int jy, jz;
+    if (!box_row(b, jy, jz)) return;
+    const double r2 = (R(pg.rad) * R(pg.rad)).v;
+    {   // nothing of p and none of its markers lies further than rad + 1 from c0 (a particle moves less than a node per step)
+        const double dy = ((double)jy - 0.5) - c0[1], dz = ((double)jz - 0.5) - c0[2], rr = pg.rad + 1.5;
+        if (dy * dy + dz * dz > rr * rr) return;
+    }
+    const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
+    int zs[3];
+    const int nzs = local_planes(pg, iz, zs);
+    const int32_t marker = -(p + 2);
+    for (int rx = lane; rx < b.n[0]; rx += 32) {
+        const int jx = b.lo[0] + rx;
+        for (int q = 0; q < nzs; ++q) {
+            const long long n = (long long)(jx - 1) + (long long)pg.g.xp * ((iy - 1) + (long long)pg.g.ly * zs[q]);
+            const int32_t v = own[n];
+            if (v == marker) {
+                own[n] = -1;
+            } else if (v == p + 1 && !in_sphere_of(pg, c1, b1, jx, iy, iz, r2)) {
+                own[n] = marker;
+                if (zs[q] >= 1 && zs[q] <= pg.g.lz) {
+                    const unsigned long long w = atomicAdd(F.count, 1ull);
+                    if ((long long)w < F.cap) { F.node[w] = (uint32_t)n; F.part[w] = p + 1; }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * PART_WARPS) k_beads_cover(PartGeom pg, int npart, const double *ypglb, int32_t *own) {
+    const int p = blockIdx.x, lane = threadIdx.x & 31;
     const double *c = ypglb + 3 * p;
     const BBox b = part_bbox(pg, c);
+    int jy, jz;
+    if (!box_row(b, jy, jz)) return;
     const double r2 = (R(pg.rad) * R(pg.rad)).v;
-    const long long nbox = (long long)b.n[0] * b.n[1] * b.n[2];
-    const unsigned n0 = (unsigned)b.n[0], n01 = (unsigned)(b.n[0] * b.n[1]);      // 32-bit decode: nbox < 2^31
-    for (unsigned t = blockIdx.y * blockDim.x + threadIdx.x; t < (unsigned)nbox; t += blockDim.x * gridDim.y) {
-        const unsigned qz = t / n01, rem = t - qz * n01, qy = rem / n0;
-        const int jx = b.lo[0] + (int)(rem - qy * n0);
-        const int jy = b.lo[1] + (int)qy;
-        const int jz = b.lo[2] + (int)qz;
+    {
+        const double dy = ((double)jy - 0.5) - c[1], dz = ((double)jz - 0.5) - c[2], rr = pg.rad + 0.01;      // conservative
+        if (dy * dy + dz * dz > rr * rr) return;
+    }
+    const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
+    int zs[3];
+    const int nzs = local_planes(pg, iz, zs);
+    for (int rx = lane; rx < b.n[0]; rx += 32) {
+        const int jx = b.lo[0] + rx;
         if (!(dist2_node(c, jx, jy, jz) < r2)) continue;
-        const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
-        int zs[3];
-        const int nz = local_planes(pg, iz, zs);
-        for (int q = 0; q < nz; ++q) {
+        for (int q = 0; q < nzs; ++q) {
             int32_t *a = own + ((long long)(jx - 1) + (long long)pg.g.xp * ((iy - 1) + (long long)pg.g.ly * zs[q]));
             int32_t old = *a;                       // the lowest id wins where particles overlap
             while (old < 0 || old > p + 1) {
@@ -106,8 +197,11 @@ __global__ void __launch_bounds__(256) k_beads_mask(PartGeom pg, int npart, cons
 }
 
 // ---- beads_links, part 2: boundary links ------------------------------------------------------------
-// Order: particle, then its box in z,y,x order, then direction 1..18 -- each thread owns a contiguous
-// chunk of the box so that the block-wide exclusive scan of the per-thread counts keeps that order.
+// A link = (fluid node of this slab, direction whose neighbour is owned by particle p).  The list is a SET: warps
+// append their row's links with one atomic per 32 nodes, so the order between rows depends on the run; inside a row it
+// is x, then direction.  Consumers (k_beads_ibb: one thread per link, every link writes its own slot and adds to
+// the particle's force with atomics) do not depend on the order; d3q19_get_links hands the list out as it lies and
+// tests compare after a canonical sort ("bit-exact after a canonical sort").
 struct Links {
     uint32_t *node;      // ghosted in-slab index of the fluid node
     int32_t *dir;        // direction pointing into the solid
@@ -143,129 +237,67 @@ __device__ __forceinline__ double link_q(const double *c, int jx, int jy, int jz
     return q;
 }
 
-// FILL = false: count[p] = number of links of particle p on this slab; FILL = true: write them at offset[p]
-template <bool FILL>
-__global__ void __launch_bounds__(256) k_beads_links(PartGeom pg, int npart, const double *ypglb, const int32_t *own,
-                                                     long long *count, const long long *offset, long long maxlink, Links L) {
-    __shared__ long long sh[256];
-    const int p = blockIdx.x;
+__global__ void __launch_bounds__(32 * PART_WARPS) k_beads_links(PartGeom pg, int npart, const double *ypglb, const int32_t *own,
+                                                                 unsigned long long *nlink, long long maxlink, Links L) {
+    const int p = blockIdx.x, lane = threadIdx.x & 31;
     const double *c = ypglb + 3 * p;
     const BBox b = part_bbox(pg, c);
+    int jy, jz;
+    if (!box_row(b, jy, jz)) return;
     const double r2 = (R(pg.rad) * R(pg.rad)).v;
-    const double rshell2 = (pg.rad + 1.5) * (pg.rad + 1.5);      // sqrt(2) < 1.5: conservative, rounding cannot matter
-    const long long nbox = (long long)b.n[0] * b.n[1] * b.n[2];
-    // block blockIdx.y owns a contiguous part of the box, each of its threads a contiguous chunk of that
-    const long long per_block = (nbox + gridDim.y - 1) / gridDim.y;
-    const long long b0 = (long long)blockIdx.y * per_block, b1 = b0 + per_block < nbox ? b0 + per_block : nbox;
-    const long long chunk = (per_block + blockDim.x - 1) / blockDim.x;
-    long long t0 = b0 + (long long)threadIdx.x * chunk, t1 = t0 + chunk < b1 ? t0 + chunk : b1;
-    if (t0 > b1) t0 = b1;
-    const int slot = p * gridDim.y + blockIdx.y;      // position of this block in the canonical order
-    long long mine = 0;
-    for (int pass = 0; pass < (FILL ? 2 : 1); ++pass) {
-        long long w = 0;
-        if (pass == 1) {                              // exclusive scan of the per-thread counts
-            sh[threadIdx.x] = mine;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                long long acc = offset[slot];
-                for (int i = 0; i < 256; ++i) { const long long v = sh[i]; sh[i] = acc; acc += v; }
-            }
-            __syncthreads();
-            w = sh[threadIdx.x];
-        }
-        // box coordinates of the chunk's first node, then carried along: no division in the loop (a box holds far
-        // fewer than 2^31 nodes, d3q19_particles_init checks)
-        int rx = 0, ry = 0, rz = 0;
-        if (t0 < t1) {
-            rz = (int)(t0 / ((long long)b.n[0] * b.n[1]));
-            ry = (int)((t0 / b.n[0]) % b.n[1]);
-            rx = (int)(t0 % b.n[0]);
-        }
-        auto next = [&]() { if (++rx == b.n[0]) { rx = 0; if (++ry == b.n[1]) { ry = 0; ++rz; } } };
-        for (long long t = t0; t < t1; ++t, next()) {
-            const int jx = b.lo[0] + rx, jy = b.lo[1] + ry, jz = b.lo[2] + rz;
-            // Only a thin shell of the box can hold link nodes: a node with d < rad was claimed by k_beads_mask (same
-            // arithmetic, same arguments) for this or a lower-numbered particle, and a neighbour owned by this
-            // particle lies within rad, so the node itself within rad + |c_i| <= rad + sqrt(2).  The test costs no
-            // memory access and removes ~85 % of the box (19 mask loads per node) at rad = 15.
+    // Only a thin shell can hold link nodes: a node with d < rad was claimed by k_beads_cover (same arithmetic) for this
+    // or a lower-numbered particle, and a neighbour owned by this particle lies within rad, so the node itself within
+    // rad + |c_i| <= rad + sqrt(2) < rad + 1.5.  Rows outside the shell's (y,z) shadow are dropped here.
+    const double rshell2 = (pg.rad + 1.5) * (pg.rad + 1.5);
+    {
+        const double dy = ((double)jy - 0.5) - c[1], dz = ((double)jz - 0.5) - c[2];
+        if (dy * dy + dz * dz > rshell2) return;
+    }
+    const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
+    const int zg = iz - pg.globalz;                  // links belong to the GPU that owns the fluid node
+    if (zg < 1 || zg > pg.g.lz) return;
+    for (int r0 = 0; r0 < b.n[0]; r0 += 32) {        // warp-uniform trip count: the shuffles below need every lane
+        const int jx = b.lo[0] + r0 + lane;
+        unsigned bits = 0u;                           // bit ip-1: the neighbour along ip is owned by p
+        long long n = 0;
+        if (r0 + lane < b.n[0]) {
             const double d2 = dist2_node(c, jx, jy, jz);
-            if (d2 < r2 || !(d2 < rshell2)) continue;
-            const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
-            const int zg = iz - pg.globalz;          // links belong to the GPU that owns the fluid node
-            if (zg < 1 || zg > pg.g.lz) continue;
-            const long long n = (long long)(jx - 1) + (long long)pg.g.xp * ((iy - 1) + (long long)pg.g.ly * zg);
-            if (own[n] > 0) continue;
-            // all 18 neighbour owners first (independent loads), then the links among them
-            int32_t nbo[NPOP - 1];
+            if (!(d2 < r2) && d2 < rshell2) {
+                n = (long long)(jx - 1) + (long long)pg.g.xp * ((iy - 1) + (long long)pg.g.ly * zg);
+                if (!(own[n] > 0)) {
+                    static_for<NPOP - 1>([&](auto ic) {
+                        constexpr int ip = decltype(ic)::value + 1;
+                        if (link_owner<ip>(pg, own, jx, iy, zg) == p + 1) bits |= 1u << (ip - 1);
+                    });
+                }
+            }
+        }
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 31) base = atomicAdd(nlink, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        long long w = (long long)base + incl - cnt;
+        if (bits) {
             static_for<NPOP - 1>([&](auto ic) {
                 constexpr int ip = decltype(ic)::value + 1;
-                nbo[ip - 1] = link_owner<ip>(pg, own, jx, iy, zg);
-            });
-            static_for<NPOP - 1>([&](auto ic) {
-                constexpr int ip = decltype(ic)::value + 1;
-                if (nbo[ip - 1] == p + 1) {
-                    if (pass == 0) {
-                        ++mine;
-                    } else {
-                        if (w < maxlink) {
-                            L.node[w] = (uint32_t)n; L.dir[w] = ip; L.part[w] = p + 1;
-                            L.q[w] = link_q<ip>(c, jx, jy, jz, r2);
-                        }
-                        ++w;
+                if (bits & (1u << (ip - 1))) {
+                    if (w < maxlink) {
+                        L.node[w] = (uint32_t)n; L.dir[w] = ip; L.part[w] = p + 1;
+                        L.q[w] = link_q<ip>(c, jx, jy, jz, r2);
                     }
+                    ++w;
                 }
             });
         }
     }
-    if (!FILL) {
-        sh[threadIdx.x] = mine;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long acc = 0;
-            for (int i = 0; i < 256; ++i) acc += sh[i];
-            count[slot] = acc;
-        }
-    }
-}
-
-// exclusive scan over the npart * PART_SPLIT block counts: one block of 1024 threads, each owns a
-// contiguous group of entries (a few thousand entries in all)
-// `overflow` (device word, or nullptr): raised to the total when it exceeds the link capacity -- k_beads_links<true> drops
-// the entries beyond maxlink, and mass would then leak through the particle surface unnoticed (checked by d3q19_sync,
-// d3q19_get_particles and whoever asks for the count)
-__global__ void __launch_bounds__(1024) k_beads_scan(int n, const long long *count, long long *offset, long long maxlink = 0,
-                                                      unsigned long long *overflow = nullptr) {
-    __shared__ long long wsum[32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int per = (n + 1023) / 1024;
-    const int i0 = tid * per, i1 = i0 + per < n ? i0 + per : n;
-    long long mine = 0;
-    for (int i = i0; i < i1; ++i) mine += count[i];
-    long long incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) wsum[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        long long v = wsum[lane], inc2 = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long t = __shfl_up_sync(0xffffffffu, inc2, o);
-            if (lane >= o) inc2 += t;
-        }
-        wsum[lane] = inc2 - v;                 // exclusive prefix of the warp totals
-        if (lane == 31) {
-            offset[n] = inc2;                  // grand total
-            if (overflow && inc2 > maxlink) atomicMax(overflow, (unsigned long long)inc2);
-        }
-    }
-    __syncthreads();
-    long long acc = wsum[wid] + incl - mine;
-    for (int i = i0; i < i1; ++i) { offset[i] = acc; acc += count[i]; }
 }
 
 // ---- beads_collision: interpolated bounce-back + momentum exchange ---------------------------------
@@ -279,7 +311,7 @@ struct IbbParams {
     double *S;
     const int32_t *own;
     Links L;
-    const long long *nlink_dev;   // total written by k_beads_scan: no host round trip between links and IBB
+    const unsigned long long *nlink_dev;   // the count k_beads_links left on the device: no host round trip between links and IBB
     long long maxlink;
     const double *ypglb, *wp, *omgp;
     double rho0;
@@ -290,7 +322,7 @@ template <int RK>
 __device__ __forceinline__ long long post_addr(const Geom &g, int i, long long n, long long nplus) {
     // address of f*_i of the node with in-slab index n; nplus = index of that node + c_i
     if (RK == READ_PULL_NAT) return (long long)i * g.slab + n;
-    if (RK == READ_PULL_SWAP) return (long long)DIR_OPP[i] * g.slab + n;
+    if (RK == READ_PULL_SWAP) return (long long)rt_opp(i) * g.slab + n;
     return (long long)i * g.slab + nplus;
 }
 
@@ -300,16 +332,16 @@ __global__ void __launch_bounds__(128) k_beads_ibb(const __grid_constant__ IbbPa
     const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double F[6] = {0, 0, 0, 0, 0, 0};
     int part = 0;
-    const long long nlink = *P.nlink_dev < P.maxlink ? *P.nlink_dev : P.maxlink;
+    const long long nlink = (long long)*P.nlink_dev < P.maxlink ? (long long)*P.nlink_dev : P.maxlink;
     if (l < nlink) {
         const uint32_t n = P.L.node[l];
-        const int ip = P.L.dir[l], io = DIR_OPP[ip];
+        const int ip = P.L.dir[l], io = rt_opp(ip);
         part = P.L.part[l];
         const int p = part - 1;
         const double q = P.L.q[l];
         const int x = (int)(n % (uint32_t)g.xp), y = (int)((n / (uint32_t)g.xp) % (uint32_t)g.ly),
                   zg = (int)(n / ((uint32_t)g.xp * (uint32_t)g.ly));
-        const int cx = DIR_CX[ip], cy = DIR_CY[ip], cz = DIR_CZ[ip];
+        const int cx = rt_cx(ip), cy = rt_cy(ip), cz = rt_cz(ip);
         const double ww = ip <= 6 ? 1.0 / 18.0 : 1.0 / 36.0;
         // neighbours along the link: x_s = x_f + c, x_b = x_f - c (periodic y; z through wrap or ghosts)
         auto wrapz = [&](int z) { return z < 1 ? g.zlo_src : (z > g.lz ? g.zhi_src : z); };
@@ -384,8 +416,8 @@ __global__ void __launch_bounds__(128) k_beads_ibb(const __grid_constant__ IbbPa
 struct FillParams {
     PartGeom pg;
     double *S;
-    const int32_t *own0, *own;
-    const double *ypglb0;         // positions before the move (their boxes cover every uncovered node)
+    const int32_t *own;           // after the mask update: -1 fluid before and after, -(q+2) uncovered by q, > 0 solid
+    FillList F;                   // the nodes k_beads_uncover found
     const double *ypglb, *wp, *omgp;
     unsigned long long *nfilled;
     // z-slab runs: the 19 canonical populations of the neighbours' planes next to the faces ([i][y][x], pitch xp),
@@ -395,12 +427,14 @@ struct FillParams {
     const double *ghost_lo, *ghost_hi;
 };
 
-// canonical populations of one plane -> out[i][y][x] (pitch xp), whatever the storage phase
+// canonical populations of two planes -> out[i][y][x] (pitch xp), whatever the storage phase: blockIdx.z = 0 -> plane
+// zg0 into out0, 1 -> plane zg1 into out1 (the two faces of a slab in one launch)
 template <int RK>
-__global__ void __launch_bounds__(BLOCK_X) k_plane_gather(Geom g, const double *A, double *out, int zg) {
+__global__ void __launch_bounds__(BLOCK_X) k_plane_gather(Geom g, const double *A, double *out0, int zg0, double *out1, int zg1) {
     const int x = blockIdx.x * BLOCK_X + threadIdx.x;
     if (x >= g.lx) return;
-    const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, blockIdx.y, zg);
+    double *out = blockIdx.z == 0 ? out0 : out1;
+    const NodeIdx<unsigned long long> k = make_node<unsigned long long>(g, x, blockIdx.y, blockIdx.z == 0 ? zg0 : zg1);
     double f[NPOP];
     gather19<RK>(A, g, k, f);
     const long long o = (long long)blockIdx.y * g.xp + x;
@@ -424,25 +458,16 @@ template <int RK>
 __global__ void __launch_bounds__(128) k_beads_fill(const __grid_constant__ FillParams P) {
     const PartGeom &pg = P.pg;
     const Geom &g = pg.g;
-    const int p = blockIdx.x;
-    const BBox b = part_bbox(pg, P.ypglb0 + 3 * p);
-    const double r2 = (R(pg.rad) * R(pg.rad)).v;
-    const long long nbox = (long long)b.n[0] * b.n[1] * b.n[2];
-    const unsigned n0 = (unsigned)b.n[0], n01 = (unsigned)(b.n[0] * b.n[1]);      // 32-bit decode: nbox < 2^31
-    for (unsigned t = blockIdx.y * blockDim.x + threadIdx.x; t < (unsigned)nbox; t += blockDim.x * gridDim.y) {
-        const unsigned qz = t / n01, rem = t - qz * n01, qy = rem / n0;
-        const int jx = b.lo[0] + (int)(rem - qy * n0);
-        const int jy = b.lo[1] + (int)qy;
-        const int jz = b.lo[2] + (int)qz;
-        // own0 == p+1 only inside the sphere at the OLD position (k_beads_mask's own test, same arithmetic): the
-        // rest of the box is skipped without touching memory
-        if (!(dist2_node(P.ypglb0 + 3 * p, jx, jy, jz) < r2)) continue;
-        const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
-        const int zg = iz - pg.globalz;
-        if (zg < 1 || zg > g.lz) continue;
-        const int x = jx - 1, y = iy - 1;
-        const long long n = (long long)x + (long long)g.xp * (y + (long long)g.ly * zg);
-        if (!(P.own0[n] == p + 1 && P.own[n] < 0)) continue;
+    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nlist = (long long)*P.F.count < P.F.cap ? (long long)*P.F.count : P.F.cap;
+    if (l < nlist) {
+        const uint32_t nn32 = P.F.node[l];
+        const int p = P.F.part[l] - 1;
+        const long long n = (long long)nn32;
+        if (P.own[n] != -(p + 2)) return;                 // another particle covers the node now
+        const int x = (int)(nn32 % (uint32_t)g.xp), y = (int)((nn32 / (uint32_t)g.xp) % (uint32_t)g.ly),
+                  zg = (int)(nn32 / ((uint32_t)g.xp * (uint32_t)g.ly));
+        const int jx = x + 1, iy = y + 1, iz = zg + pg.globalz;
         // surface velocity of the particle that uncovered the node, at the node (state after the move)
         double c0 = P.ypglb[3 * p], c1 = P.ypglb[3 * p + 1], c2 = P.ypglb[3 * p + 2];
         const double xf0 = (double)jx - 0.5, xf1 = (double)iy - 0.5, xf2 = (double)iz - 0.5;
@@ -458,7 +483,7 @@ __global__ void __launch_bounds__(128) k_beads_fill(const __grid_constant__ Fill
         int nn = 0, jbest = 0;
         double fbest[NPOP];
         for (int ip = 1; ip < NPOP; ++ip) {
-            const int cx = DIR_CX[ip], cy = DIR_CY[ip], cz = DIR_CZ[ip];
+            const int cx = rt_cx(ip), cy = rt_cy(ip), cz = rt_cz(ip);
             const int kx = x + cx;
             if (kx < 0 || kx >= g.lx) continue;
             const int ky = (y + cy < 0) ? g.ly - 1 : (y + cy >= g.ly ? 0 : y + cy);
@@ -470,7 +495,7 @@ __global__ void __launch_bounds__(128) k_beads_fill(const __grid_constant__ Fill
                 if (!gh) continue;
             }
             const long long m = (long long)kx + (long long)g.xp * (ky + (long long)g.ly * kz);     // the masks are ghosted
-            if (P.own0[m] > 0 || P.own[m] > 0) continue;
+            if (P.own[m] != -1) continue;                 // solid now, or solid before this update (a marker)
             double fm[NPOP];
             if (gh) {
                 const long long o = (long long)ky * g.xp + kx;
@@ -517,9 +542,7 @@ __global__ void __launch_bounds__(128) k_beads_fill(const __grid_constant__ Fill
 // ---- beads_lubforce / beads_move: npart threads ------------------------------------------------------
 struct LubParams { double mingap, mingap_w, stf0, stf1, stf0_w, stf1_w, fscale; };
 
-__global__ void k_beads_lubforce(PartGeom pg, int npart, const double *ypglb, LubParams lp, double *flubp) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npart) return;
+__device__ __forceinline__ void lubforce_one(const PartGeom &pg, int npart, const double *ypglb, const LubParams &lp, double *flubp, int i) {
     const double *a = ypglb + 3 * i;
     const double Rr = pg.rad;
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
@@ -553,12 +576,10 @@ struct MoveParams {
     double amp, aip;
     double g0, g1, g2;
     const double *fHIp, *torqp, *flubp;
-    double *forcepp, *torqpp, *ypglb, *ypglb0, *wp, *omgp, *thetap;
+    double *forcepp, *torqpp, *ypglb, *wp, *omgp, *thetap;
 };
 
-__global__ void k_beads_move(PartGeom pg, int npart, MoveParams M) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npart) return;
+__device__ __forceinline__ void move_one(const PartGeom &pg, const MoveParams &M, int p) {
     const double gf[3] = {M.g0, M.g1, M.g2};
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -567,7 +588,6 @@ __global__ void k_beads_move(PartGeom pg, int npart, MoveParams M) {
         const double T = 0.5 * (M.torqp[k] + M.torqpp[k]);
         const double wnew = M.wp[k] + F / M.amp;
         const double onew = M.omgp[k] + T / M.aip;
-        M.ypglb0[k] = M.ypglb[k];
         M.ypglb[k] += 0.5 * (M.wp[k] + wnew);
         M.thetap[k] += 0.5 * (M.omgp[k] + onew);
         M.wp[k] = wnew; M.omgp[k] = onew;
@@ -578,6 +598,17 @@ __global__ void k_beads_move(PartGeom pg, int npart, MoveParams M) {
     if (c[1] < 0.0) c[1] += pg.ny;
     if (c[2] >= (double)pg.nz) c[2] -= pg.nz;
     if (c[2] < 0.0) c[2] += pg.nz;
+}
+
+// beads_lubforce and beads_move of all particles in ONE block (npart is a few hundred): every repulsion force is formed
+// from the positions before anybody moves, then the barrier, then the rigid-body update
+__global__ void __launch_bounds__(1024) k_beads_lubmove(PartGeom pg, int npart, const double *ypglb, LubParams lp, double *flubp,
+                                                        MoveParams M, int do_lub, int do_move) {
+    if (do_lub)
+        for (int i = threadIdx.x; i < npart; i += blockDim.x) lubforce_one(pg, npart, ypglb, lp, flubp, i);
+    __syncthreads();
+    if (do_move)
+        for (int p = threadIdx.x; p < npart; p += blockDim.x) move_one(pg, M, p);
 }
 
 // link list -> host-friendly (global 1-based node coordinates)

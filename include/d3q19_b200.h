@@ -80,7 +80,15 @@ typedef struct d3q19_config {
     int32_t math;             /* D3Q19_MATH_*                                                    */
     int32_t ipart;            /* para.f90:332 -- enables the solid-node paths                    */
     int32_t overlap;          /* 1: boundary/interior split with exchange on a second stream     */
-    int32_t reserved_i[5];
+    /* tuning knobs; 0 = the measured default.  (All behaviour switches live here or in d3q19_set_halo_mode: the
+     * library reads no environment variable.)                                                      */
+    int32_t nccl_max_ctas;    /* CTAs NCCL may use for the face send/recv (ncclConfig_t.maxCTAs); default 4: the
+                                 faces are a few MB and every NCCL CTA takes an SM from the interior kernel        */
+    int32_t pf_blocks;        /* in-place steps: L2 software-prefetch distance in thread blocks; default 128, < 0 off */
+    int32_t halo_timeout_s;   /* peer-memory halo: seconds a wait for a neighbour's flag may last; default 30      */
+    int32_t halo_split_min;   /* fused peer halo: slabs at least this thick run boundary and interior as two
+                                 launches; default 64                                                               */
+    int32_t force_idx64;      /* testing: 64-bit in-slab indices even when a population has < 2^32 elements         */
     /* MRT constants, para.f90:106-143 */
     double s1, s2, s4, s9, s10, s13, s16;
     double omegepsl, omegepslj, omegxx;
@@ -109,11 +117,11 @@ int d3q19_device_count(int32_t *n);
 #define D3Q19_IPC_BYTES 256
 int d3q19_ipc_export(d3q19_handle *h, unsigned char *blob);
 int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs_in_rank_order);
-/* How the peer-memory halo moves the faces (call before the first step; the environment variable
- * D3Q19_HALO_MODE=fused|put read by d3q19_ipc_connect does the same):
+/* How the peer-memory halo moves the faces (call before the first step):
  *   D3Q19_HALO_FUSED  the boundary planes of the step kernel store into the neighbour's array themselves
- *   D3Q19_HALO_PUT    plain step kernels; a small copy kernel on the high-priority stream stores both faces
- *                     into the neighbours' arrays while the interior is computed                            */
+ *   D3Q19_HALO_PUT    plain step kernels; the COPY ENGINES move each crossing population from my array into the
+ *                     neighbour's (ten device-to-device copies over NVLink per step, no SM involved) while the
+ *                     interior is computed; a one-thread kernel then raises the neighbours' flags              */
 enum { D3Q19_HALO_FUSED = 0, D3Q19_HALO_PUT = 1 };
 int d3q19_set_halo_mode(d3q19_handle *h, int32_t mode);
 
@@ -214,6 +222,13 @@ int d3q19_diag(d3q19_handle *h, double ustar, double *out14);
  * reference's expression order.  The arrays are the reference's ox,oy,oz(lx,ly,lz) (var_inc.f90:140).  */
 int d3q19_vortcalc(d3q19_handle *h);
 int d3q19_download_vort(d3q19_handle *h, double *ox, double *oy, double *oz);
+
+/* Local strain rate from the non-equilibrium moments (first loop nest of sijstat00, saveload.f90:2031-2091;
+ * SURVEY.md 8(f) rank 4): Sij*Sij of every fluid node from its populations and the device rho,u (call d3q19_macrovar
+ * first) -- node-local, reuses collision_MRT's sums, bit-identical to the reference's expression order; solid
+ * nodes get 0.  The local dissipation rate is 2 visc Sij Sij (:1987-1989).  Array layout (lx,ly,lz).            */
+int d3q19_sijstat(d3q19_handle *h);
+int d3q19_download_sij2(d3q19_handle *h, double *sij2);
 
 /* ---- measurement ----------------------------------------------------------------------- */
 /* CUDA events on the stream the step kernels are launched on */

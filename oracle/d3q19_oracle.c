@@ -857,6 +857,67 @@ void orc_vortcalc(const orc_world *w, double *oxg, double *oyg, double *ozg)
     }
 }
 
+/* ---- saveload.f90:2031-2091 -- local strain rate from the non-equilibrium moments (sijstat00) ------
+ * Sij*Sij of every fluid node (ibnodes < 0) from f (post-streaming) and the rho,u arrays as macrovar
+ * left them (Yu et al., Computers & Fluids 35 (2006) 957, appendix): the six second-order moments
+ * minus their equilibria, times their relaxation rates, are the strain-rate tensor up to constants --
+ * no finite differences, no halo.  The sums are collision_MRT's (:104-138).  Global (nx,ny,nz) layout;
+ * solid nodes are left untouched (the reference's automatic array is undefined there). */
+void orc_sijstat(const orc_world *w, double *sij2g)
+{
+    const orc_para *p = &w->p;
+    const double coef2 = p->coef2, coef3 = p->coef3, coef5 = p->coef5, s1 = p->s1, s9 = p->s9;
+    int id;
+    for (id = 0; id < w->nproc; ++id) {
+        const orc_rank *r = &w->r[id];
+        int ix, iy, iz;
+        for (iz = 1; iz <= r->lz; ++iz)
+        for (iy = 1; iy <= r->ly; ++iy)
+        for (ix = 1; ix <= r->lx; ++ix) {
+            const double *f9;
+            double rho9, ux9, uy9, uz9, ux9s, uy9s, uz9s, eqm1, eqm6, eqm8, eqm10, eqm11, eqm12;
+            double sum1, sum2, sum6, sum7, sum8, sum9, sum10, sum11, evlm1, evlm6, evlm8, evlm10, evlm11, evlm12;
+            double neqm1, neqm9, neqm11, neqm13, neqm14, neqm15, Sxx, Syy, Szz, Sxy, Syz, Szx;
+            if (!(IB_(r, ix, iy, iz) < 0)) continue;                                  /* :2034 */
+            f9 = &F_(r, 0, ix, iy, iz);                                               /* :2036 */
+            rho9 = S_(r, r->rho, ix, iy, iz);
+            ux9 = S_(r, r->ux, ix, iy, iz); uy9 = S_(r, r->uy, ix, iy, iz); uz9 = S_(r, r->uz, ix, iy, iz);
+            ux9s = ux9 * ux9; uy9s = uy9 * uy9; uz9s = uz9 * uz9;
+            eqm1 = -(11.0 * rho9) + 19.0 * ((ux9s + uy9s) + uz9s);                    /* :2046-2051 */
+            eqm6 = (2.0 * ux9s - uy9s) - uz9s;
+            eqm8 = uy9s - uz9s;
+            eqm10 = ux9 * uy9; eqm11 = uy9 * uz9; eqm12 = ux9 * uz9;
+            sum1 = ((((f9[1] + f9[2]) + f9[3]) + f9[4]) + f9[5]) + f9[6];             /* :2053-2064 */
+            sum2 = ((((((((((f9[7] + f9[8]) + f9[9]) + f9[10]) + f9[11]) + f9[12]) + f9[13]) + f9[14]) + f9[15]) + f9[16])
+                    + f9[17]) + f9[18];
+            sum6 = f9[1] + f9[2];
+            sum7 = ((f9[3] + f9[4]) + f9[5]) + f9[6];
+            sum8 = ((((((f9[7] + f9[8]) + f9[9]) + f9[10]) + f9[11]) + f9[12]) + f9[13]) + f9[14];
+            sum9 = ((f9[15] + f9[16]) + f9[17]) + f9[18];
+            sum10 = ((f9[3] + f9[4]) - f9[5]) - f9[6];
+            sum11 = ((((((f9[7] + f9[8]) + f9[9]) + f9[10]) - f9[11]) - f9[12]) - f9[13]) - f9[14];
+            evlm1 = (-(30.0 * f9[0]) + coef2 * sum1) + coef3 * sum2;                  /* :2066-2071 */
+            evlm6 = ((coef5 * sum6 - sum7) + sum8) - coef5 * sum9;
+            evlm8 = sum10 + sum11;
+            evlm10 = ((f9[7] - f9[8]) - f9[9]) + f9[10];
+            evlm11 = ((f9[15] - f9[16]) - f9[17]) + f9[18];
+            evlm12 = ((f9[11] - f9[12]) - f9[13]) + f9[14];
+            neqm1 = s1 * (evlm1 - eqm1);                                              /* :2073-2078 */
+            neqm9 = s9 * (evlm6 - eqm6);
+            neqm11 = s9 * (evlm8 - eqm8);
+            neqm13 = s9 * (evlm10 - eqm10);
+            neqm14 = s9 * (evlm11 - eqm11);
+            neqm15 = s9 * (evlm12 - eqm12);
+            Sxx = -((neqm1 + 19.0 * neqm9) / 38.0);                                   /* :2080-2085 */
+            Syy = -((2.0 * neqm1 - 19.0 * (neqm9 - 3.0 * neqm11)) / 76.0);
+            Szz = -((2.0 * neqm1 - 19.0 * (neqm9 + 3.0 * neqm11)) / 76.0);
+            Sxy = -(1.5 * neqm13); Syz = -(1.5 * neqm14); Szx = -(1.5 * neqm15);
+            sij2g[(size_t)(ix - 1) + (size_t)p->nx * ((size_t)(iy - 1 + r->globaly) + (size_t)p->ny * (size_t)(iz - 1 + r->globalz))] =
+                ((Sxx * Sxx + Syy * Syy) + Szz * Szz) + 2.0 * ((Sxy * Sxy + Syz * Syz) + Szx * Szx);   /* :2087-2088 */
+        }
+    }
+}
+
 /* ---- collision.f90:469-480 ----------------------------------------------------------- */
 static void pf_rhoupdat(void *c, int id);
 void orc_rhoupdat(orc_world *w) { orc_parallel_for(w->nproc, pf_rhoupdat, w); }

@@ -124,6 +124,8 @@ void orc_macrovar(orc_world *w);
 void orc_rhoupdat(orc_world *w);
 /* saveload.f90:3929-4054 (vortcalc + exchng8): vorticity of ux,uy,uz into global (lx,ny,nz) arrays. */
 void orc_vortcalc(const orc_world *w, double *ox_global, double *oy_global, double *oz_global);
+/* saveload.f90:2031-2091 (first loop nest of sijstat00): Sij*Sij of the fluid nodes into a global (nx,ny,nz) array. */
+void orc_sijstat(const orc_world *w, double *sij2_global);
 /* collision.f90:487-513; returns rhomean, writes the global fluid-node count. */
 double orc_avedensity(orc_world *w, int64_t *nfluidtotal);
 

@@ -811,6 +811,10 @@ class Translator:
                 else:
                     self.emit("%s %s = 0; (void)%s;" % (ctype, s.name, s.name))
                 continue
+            if any(lo is None or hi is None for lo, hi in s.dims):
+                # a deferred-shape (allocatable) local: it is allocated, if at all, beyond the translated part
+                self.emit("ref_arr %s; memset(&%s, 0, sizeof %s); (void)%s;" % (s.name, s.name, s.name, s.name))
+                continue
             los = ", ".join("(%s)" % self.cx(parse_expr(lo)) for lo, hi in s.dims)
             his = ", ".join("(%s)" % self.cx(parse_expr(hi)) for lo, hi in s.dims)
             kind = "REF_KIND_R" if s.typ == "real" else "REF_KIND_I"
@@ -822,8 +826,12 @@ class Translator:
                 frees.append("ref_free(&%s);" % s.name)
         return frees
 
-    def translate_sub(self, name, lines, stop_after=None, override_assignments=False):
-        """lines: logical lines of one subroutine (from `subroutine` to `end subroutine`)."""
+    def translate_sub(self, name, lines, stop_after=None, override_assignments=False, capture_local=None):
+        """lines: logical lines of one subroutine (from `subroutine` to `end subroutine`).
+        stop_after: a regex, or (regex, n): translation stops after the n-th statement that matches.
+        capture_local: (array name, unit): before returning, every element of that LOCAL array goes to the capture
+        buffer under `unit` (first dimension fastest) -- how a result that the reference keeps in an automatic array
+        (sijstat00's Sij2) becomes visible to the tests."""
         self.local, self.cur_sub = {}, name
         head = lines[0][1]
         m = re.match(r"subroutine\s+([a-z_0-9]+)\s*(\(([^)]*)\))?", head)
@@ -848,6 +856,7 @@ class Translator:
         sig = ", ".join(["ref_state *S"] + ["void *%s_arg" % d for d in dummies])
         self.emit("\nvoid ref_%s(%s)\n{" % (name, sig))
         frees = self.emit_local_decls()
+        stop_re, stop_n = (stop_after if isinstance(stop_after, tuple) else (stop_after, 1))
         for no, t in body[k:]:
             if re.match(r"^end\s*subroutine", t) or t == "end":
                 break
@@ -855,9 +864,15 @@ class Translator:
                 self.statement(t, override_assignments)
             except Exception as ex:
                 raise type(ex)("%s (line %d of %s: %r)" % (ex, no, name, t)) from ex
-            if stop_after and re.match(stop_after, t):
-                break
+            if stop_re and re.match(stop_re, t):
+                stop_n -= 1
+                if stop_n == 0:
+                    break
         self.emit("ref_end: ;")
+        if capture_local:
+            e = parse_expr(capture_local[0])
+            op, cl, names = self.loops(self.section_shape(e))
+            self.emit("%sref_capture(S, %d, (double)(%s));%s" % (op, capture_local[1], self.cx(e, names), cl))
         for f in frees:
             self.emit(f)
         for s in self.local.values():
@@ -1035,7 +1050,7 @@ class Translator:
     def generate(self):
         self.in_case = False
         self.wanted = ["para", "allocarray", "initpop", "initvel", "collisionexchnge", "collision_mrt", "macrovar",
-                       "rhoupdat", "avedensity", "forcing", "forcingp", "exchng8", "vortcalc",
+                       "rhoupdat", "avedensity", "forcing", "forcingp", "exchng8", "vortcalc", "sijstat00",
                        "statistc", "statistc2", "diag"]
         o = self.emit
         o("/* GENERATED by oracle/f90toc.py from the reference's Fortran sources -- do not edit, do not commit. */")
@@ -1096,6 +1111,10 @@ class Translator:
         # rank 1: profile statistics and the diag monitor; their write(unit, ...) lists are captured
         for n in ("statistc", "statistc2", "diag"):
             self.translate_sub(n, save[n])
+        # rank 4, second half: the local strain rate from the non-equilibrium moments (sijstat00's first loop nest,
+        # saveload.f90:2031-2091; what follows in that routine are particle-centred shell statistics).  Sij2 is an
+        # automatic array there: its elements are captured under unit 99.
+        self.translate_sub("sijstat00", save["sijstat00"], stop_after=(r"^end\s*do$", 3), capture_local=("sij2", 99))
         # ---- dispatch + reflection tables for the Python wrapper
         o("\nint ref_dispatch(ref_state *S, const char *name)\n{")
         for n in self.wanted:

@@ -67,6 +67,8 @@ def lib(fast=False):
             getattr(L, name).restype = None
         L.orc_vortcalc.argtypes = [vp, dp, dp, dp]
         L.orc_vortcalc.restype = None
+        L.orc_sijstat.argtypes = [vp, dp]
+        L.orc_sijstat.restype = None
         L.orc_avedensity.argtypes = [vp, C.POINTER(C.c_int64)]
         L.orc_avedensity.restype = C.c_double
         L.orc_gather_f.argtypes = [vp, dp]
@@ -162,6 +164,12 @@ class World:
         shape = (self.para.nz, self.para.ny, self.para.nx)
         o = [np.zeros(shape) for _ in range(3)]
         self.L.orc_vortcalc(self.h, *[a.ctypes.data_as(C.POINTER(C.c_double)) for a in o])
+        return o
+
+    def sijstat(self):
+        """saveload.f90:2031-2091: Sij*Sij of the fluid nodes from f and the current rho,u -> global [iz,iy,ix] (0 at solid nodes)"""
+        o = np.zeros((self.para.nz, self.para.ny, self.para.nx))
+        self.L.orc_sijstat(self.h, o.ctypes.data_as(C.POINTER(C.c_double)))
         return o
 
     def avedensity(self):

@@ -48,6 +48,14 @@ def _i(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
+def canon(links, select=None):
+    """link list (optionally a boolean selection of it) sorted by (particle, z, y, x, direction): the CUDA path builds
+    its list as a set, comparisons are made after this sort"""
+    d = {k: (v if select is None else v[select]) for k, v in links.items()}
+    o = np.lexsort((d["ip"], d["x"], d["y"], d["z"], d["part"]))
+    return {k: v[o] for k, v in d.items()}
+
+
 class Particles:
     """Particle state + the per-step operations, on one whole channel."""
 

@@ -167,6 +167,20 @@ class RefWorld:
             out[sz, sy] = self.array(name, r)[0]
         return out
 
+    def sij2(self):
+        """sijstat00's first loop nest (saveload.f90:2031-2091): Sij*Sij of every fluid node from the non-equilibrium
+        moments of f and the rho,u arrays macrovar left; the routine keeps it in an automatic array, whose elements the
+        translation hands to the capture buffer (unit 99).  Global [iz,iy,ix]; solid nodes hold 0."""
+        self.clear_captured()
+        self.run("sijstat00")
+        out = np.zeros((self.nz, self.ny, self.nx))
+        for r in range(self.nproc):
+            sz, sy = self._place(r)
+            lz, ly = sz.stop - sz.start, sy.stop - sy.start
+            out[sz, sy] = self.captured(99, rank=r).reshape(lz, ly, self.nx)
+        self.clear_captured()
+        return out
+
     def set_solid(self, ib, isn=None):
         """ib, isn: global (nz,ny,nx) int arrays; fills the interior of the ghosted ibnodes of every rank."""
         for r in range(self.nproc):

@@ -54,7 +54,7 @@ def save(name, meta, **arrays):
     print("wrote %s.npz: %s" % (name, {k: v.shape for k, v in arrays.items()}))
 
 
-def main_loop_case(name, nx, ny, nz, npy, npz, laminar, steps, seed, a9=0.0, vort=False, snap=None, **ov):
+def main_loop_case(name, nx, ny, nz, npy, npz, laminar, steps, seed, a9=0.0, vort=False, snap=None, sij=False, **ov):
     w = start(nx, ny, nz, npy, npz, laminar, seed, a9, **ov)
     f0 = w.get_f().copy()
     w.run("macrovar")                                  # main.f90:136
@@ -67,6 +67,8 @@ def main_loop_case(name, nx, ny, nz, npy, npz, laminar, steps, seed, a9=0.0, vor
     if vort:
         w.run("vortcalc")                              # saveload.f90:3929 (as called by outputvort1, :1138)
         extra.update({k: w.get(k) for k in ("ox", "oy", "oz")})
+    if sij:
+        extra["sij2"] = w.sij2()                       # saveload.f90:2031-2091 (first loop nest of sijstat00)
     meta = dict(kind="main_loop", nx=nx, ny=ny, nz=nz, ranks=[npy, npz], laminar=laminar, steps=steps,
                 overrides=ov, scalars=scalars(w))
     if snap is not None:
@@ -161,6 +163,7 @@ if __name__ == "__main__":
     # slabs, 9 steps (odd: the in-place scheme ends in its swapped phase and has sent its ghost planes back four times),
     # the state after 8 steps stored as well
     main_loop_case("ref_slabs_21x4x16_r1x4_s9", 21, 4, 16, 1, 4, False, 9, seed=8086, a9=0.3, snap=8, **U)
+    main_loop_case("ref_turb_sij_13x6x7_r1x2_s5", 13, 6, 7, 1, 2, False, 5, seed=1618, a9=0.3, sij=True, **U)
     stats_case("ref_stats_21x8x6_r2x2_s6", 21, 8, 6, 2, 2, 6, seed=2024, **U)
     stats_case("ref_stats_solid_24x12x12_r1x2", 24, 12, 12, 1, 2, 0, seed=11, solid=True, **U)
     prerelax_case("ref_prerelax_7x8x8_r2x2_i6", 7, 8, 8, 2, 2, 6, seed=99, **U)

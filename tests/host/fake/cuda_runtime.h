@@ -139,6 +139,7 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int o) {
 }
 struct alignas(16) double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __all_sync(unsigned, int pred) {
     int all = 1;
     for (int l = 0; l < 32; ++l) all &= hs::warp_exchange(pred ? 1 : 0, l);      // 32 rounds: simple, and only in tests
@@ -273,7 +274,7 @@ template <class A> static inline bool hs_needs_coop(const A &) { return false; }
 struct hs_none {};
 template <class K, class A0, class... Rest>
 static void hs_dispatch(const char *name, dim3 grid, unsigned block, K kern, const A0 &a0, const Rest &... rest) {
-    static const char *coop[] = {"k_diag<", "k_rho_partial", "k_beads_links", "k_beads_scan", "k_beads_ibb", "k_face_put", "k_step_ab2", "k_step_aa2"};
+    static const char *coop[] = {"k_diag<", "k_rho_partial", "k_beads_links", "k_beads_lubmove", "k_beads_ibb", "k_face_put"};
     bool c = hs_needs_coop(a0);              // found by ADL for d3q::StepParams (pre-relaxation: block maximum)
     for (const char *n : coop) c = c || !std::strncmp(name, n, std::strlen(n));
     if (c) hs_launch_coop(grid, block, kern, a0, rest...);

@@ -94,8 +94,15 @@ inline int fake_collective(int mode, const void *send, void *recv, size_t count,
     return 0;
 }
 
+struct NcclConfig218 { int maxCTAs; };
+inline NcclConfig218 nccl_config_max_ctas(int max_ctas) { return NcclConfig218{max_ctas}; }
+
 struct NcclApi {
     const char *load() { return nullptr; }
+    static int CommInitRankConfig(NcclComm *out, int nranks, NcclUniqueId id, int rank, NcclConfig218 *c) {
+        if (!c || c->maxCTAs < 1) return 4;               // the library always asks for a positive CTA budget
+        return CommInitRank(out, nranks, id, rank);
+    }
     static int GetUniqueId(NcclUniqueId *id) {
         static std::mutex mu;
         static std::mt19937_64 rng(12345);

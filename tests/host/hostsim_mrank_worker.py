@@ -5,7 +5,7 @@ is the process's own address space.  Run as a subprocess with D3Q19_LIB pointing
     D3Q19_LIB=tests/host/_gen/libd3q19b200_hostsim.so python tests/host/hostsim_mrank_worker.py <world> [section ...]
 
 What it shows: the REAL orchestration of csrc/d3q19_api.cu (slab geometry, face exchange, send-back after odd steps,
-peer-memory connect + flag protocol, put transport, boundary stream, reductions, particle link partition, force
+peer-memory connect + flag protocol, copy-engine put transport, reductions, particle link partition, force
 all-reduce, refill source exchange) computes, on 2-4 slabs, bit for bit what the single-domain oracle computes.
 What it cannot show: ordering between CUDA streams (the fake device is synchronous; see test_halo_schedule_model.py).
 """
@@ -56,11 +56,9 @@ def section_fluid(rank, world, comm, chk, ctx):
              ((24, 6, 4 * world), False, "nccl"), ((130, 3, 2 * world + 1), True, "nccl"),
              ((24, 6, 4 * world), True, "peer"), ((33, 5, 3 * world + 1), True, "peer"), ((130, 3, 2 * world + 1), True, "peer"),
              ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split"),
-             ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"),
-             ((24, 6, 4 * world), True, "bstream"), ((33, 5, 3 * world + 1), True, "bstream"),
-             ((24, 6, 4 * world), True, "direct"), ((33, 5, 3 * world + 1), True, "direct"), ((130, 3, 2 * world + 1), True, "direct")]
+             ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"), ((130, 3, 2 * world + 1), True, "put")]
     if os.environ.get("HOSTSIM_SHORT"):          # the default CPU suite: one uneven case per transport
-        cases = [((33, 5, 3 * world + 1), True, h) for h in ("nccl", "peer", "peer-split", "put", "bstream", "direct")] + \
+        cases = [((33, 5, 3 * world + 1), True, h) for h in ("nccl", "peer", "peer-split", "put")] + \
                 [((24, 6, 4 * world), False, "nccl")]
     import time
     for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
@@ -69,20 +67,9 @@ def section_fluid(rank, world, comm, chk, ctx):
             ctx[0] = "scheme %d case %s overlap %s halo %s" % (scheme, (nx, ny, nz), overlap, halo)
             w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
             w.set_f(w.get_f() + 1e-4 * np.random.default_rng(7).normal(size=(nz, ny, nx, 19)))
-            # environment knobs are read at create / connect: all ranks share one environment, so set them together
-            comm.bar.wait()
-            if rank == 0:
-                for k in ("D3Q19_BOUNDARY_STREAM", "D3Q19_HALO_SPLIT_MIN", "D3Q19_DIRECT_FACES"):
-                    os.environ.pop(k, None)
-                if halo == "bstream":
-                    os.environ["D3Q19_BOUNDARY_STREAM"] = "1"
-                if halo == "direct":                          # faces sent straight out of the population array
-                    os.environ["D3Q19_DIRECT_FACES"] = "1"
-                if halo == "peer-split":
-                    os.environ["D3Q19_HALO_SPLIT_MIN"] = "3"
-            comm.bar.wait()
             sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=scheme,
-                                  math_mode=capi.MATH_STRICT, nccl_id=comm.new_id(rank), overlap=overlap)
+                                  math_mode=capi.MATH_STRICT, nccl_id=comm.new_id(rank), overlap=overlap,
+                                  halo_split_min=3 if halo == "peer-split" else 0)
             z0, z1 = sim.globalz, sim.globalz + sim.lz
             sim.FORCING()
             if halo.startswith("peer") or halo == "put":
@@ -125,11 +112,6 @@ def section_fluid(rank, world, comm, chk, ctx):
             sim.close(); w.close()
             if rank == 0 and os.environ.get("HOSTSIM_VERBOSE"):
                 print("%-60s %.2f s" % (ctx[0], time.perf_counter() - t_case), flush=True)
-    comm.bar.wait()
-    if rank == 0:
-        for k in ("D3Q19_BOUNDARY_STREAM", "D3Q19_HALO_SPLIT_MIN", "D3Q19_DIRECT_FACES"):
-            os.environ.pop(k, None)
-    comm.bar.wait()
 
 
 def section_prerelax(rank, world, comm, chk, ctx):
@@ -189,9 +171,9 @@ def section_particles(rank, world, comm, chk, ctx):
         chk("link count %d vs %d" % (tot, len(pt.links["q"])), tot == len(pt.links["q"]))
         chk("mask", bool(np.array_equal(sim.get_mask(), pt.own[z0:z1])))
         gl = sim.get_links()
-        mine = (pt.links["z"] > z0) & (pt.links["z"] <= z1)
+        mine = P.canon(pt.links, (pt.links["z"] > z0) & (pt.links["z"] <= z1))     # the oracle's links whose fluid node I own
         for key in ("x", "y", "z", "ip", "part", "q"):
-            chk("links " + key, bool(np.array_equal(gl[key], pt.links[key][mine])))
+            chk("links " + key, bool(np.array_equal(gl[key], mine[key])))
         w.macrovar()
         out = np.empty((sim.lz, ny, nx, 19))
         for step in range(3):
@@ -286,6 +268,38 @@ def section_shim(rank, world, comm, chk, ctx):
         sim.close(); w.close()
 
 
+def section_restart(rank, world, comm, chk, ctx):
+    """checkpoint / restart over slabs (saveload.f90:196-231, :296-332: one file per rank), into the other storage scheme"""
+    import tempfile
+    saveload = pkg.saveload
+    nx, ny, nz = 24, 6, 3 * world + 1
+    tmp = comm.allgather(rank, tempfile.mkdtemp(prefix="d3q19_restart_") if rank == 0 else None)[0]
+    for first, second in ((capi.SCHEME_AA, capi.SCHEME_AB), (capi.SCHEME_AB, capi.SCHEME_AA)):
+        ctx[0] = "restart %d -> %d" % (first, second)
+        w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True)
+        a = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=first,
+                            math_mode=capi.MATH_STRICT, nccl_id=comm.new_id(rank))
+        z0, z1 = a.globalz, a.globalz + a.lz
+        a.f[...] = w.get_f()[z0:z1]
+        a.host_f_changed(); a.FORCING(); a.macrovar()
+        a.run(9)
+        saveload.savecntdflow(a, tmp)
+        a.close()
+        comm.bar.wait()
+        b = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=second,
+                            math_mode=capi.MATH_STRICT, nccl_id=comm.new_id(rank))
+        b.FORCING()
+        chk("istep0", saveload.loadcntdflow(b, tmp, 9)[0] == 9)
+        b.macrovar()
+        b.run(11)
+        w.macrovar()
+        for _ in range(20):
+            w.collision_MRT(); w.macrovar()
+        chk("20 steps with a restart after 9", bool(np.array_equal(b.sync_f_to_host(), w.get_f()[z0:z1])))
+        b.close(); w.close()
+        comm.bar.wait()
+
+
 def section_benchparity(rank, world, comm, chk, ctx):
     """bench.py's own pre-timing parity check (the reference's golden vector on this job's slabs, every transport; the
     moving-particle case against one domain), with the ranks as threads"""
@@ -315,7 +329,7 @@ def section_random(rank, world, comm, chk, ctx):
                                                                                      "hostsim_random_calls.py"))
     rc = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(rc)
-    transports = ["nccl", "peer", "peer-split", "put", "bstream", "direct", "bstream+direct"]
+    transports = ["nccl", "peer", "peer-split", "put"]
     nseeds = int(os.environ.get("HOSTSIM_RANDOM_SEEDS", "7"))
     for seed in range(nseeds):
         for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
@@ -336,14 +350,9 @@ def section_random(rank, world, comm, chk, ctx):
             except Exception:
                 chk("random particle sequence, last calls %r\n%s" % (log[-6:], traceback.format_exc()), False)
                 raise
-    comm.bar.wait()
-    if rank == 0:
-        for k in ("D3Q19_BOUNDARY_STREAM", "D3Q19_DIRECT_FACES", "D3Q19_HALO_SPLIT_MIN"):
-            os.environ.pop(k, None)
-    comm.bar.wait()
 
 
-SECTIONS = {"random": section_random, "benchparity": section_benchparity, "fluid": section_fluid, "prerelax": section_prerelax, "particles": section_particles, "shim": section_shim}
+SECTIONS = {"random": section_random, "benchparity": section_benchparity, "restart": section_restart, "fluid": section_fluid, "prerelax": section_prerelax, "particles": section_particles, "shim": section_shim}
 
 
 def rank_main(rank, world, comm, sections):

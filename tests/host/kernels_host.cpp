@@ -41,12 +41,13 @@ struct Rank {
     // the neighbours' arrays as this rank sees them ([0] lower, [1] upper), swapped in lockstep for AB
     double *peer_A[2] = {nullptr, nullptr}, *peer_B[2] = {nullptr, nullptr};
     // particle path (per slab: masks and links; the particle tables are replicated, here per slab as on the GPUs)
-    std::vector<int32_t> own, own0;
-    std::vector<double> ypglb, ypglb0, wp, omgp, fHIp, torqp, flubp, forcepp, torqpp, thetap;
+    std::vector<int32_t> own;
+    std::vector<double> ypglb, ypmask, wp, omgp, fHIp, torqp, flubp, forcepp, torqpp, thetap;
     std::vector<uint32_t> lnode;
     std::vector<int32_t> ldir, lpart;
     std::vector<double> lq;
-    std::vector<long long> lcount, loffset;
+    std::vector<uint32_t> fnode; std::vector<int32_t> fpart;      // refill list
+    unsigned long long pcnt[4] = {0, 0, 0, 0};
     std::vector<double> fill_send_up, fill_send_dn, fill_ghost_lo, fill_ghost_hi;      // 19 x plane each
     unsigned long long nfilled = 0;
 };
@@ -171,7 +172,7 @@ void step_all_ranks(Sim &s, int macro_mode) {
         }
         exchange_after_step(s, SK, ab);
     } else if (s.transport == T_PUT) {
-        // launch_step_put: plain kernels everywhere, then every rank's k_face_put (flags checked below)
+        // launch_step_put: plain kernels everywhere, then every rank's face copies (flags checked below)
         for (int k = 0; k < n; ++k) {
             Rank &q = s.r[k];
             ++q.epoch;
@@ -187,26 +188,35 @@ void step_all_ranks(Sim &s, int macro_mode) {
             Rank &q = s.r[k];
             const Geom &g = q.g;
             const int lz = g.lz, dn = (k + n - 1) % n, up = (k + 1) % n;
-            FacePut fp;
-            std::memset(&fp, 0, sizeof fp);
-            fp.src = ab ? q.B : q.A;
-            fp.dst[0] = ab ? q.peer_B[1] : q.peer_A[1];
-            fp.dst[1] = ab ? q.peer_B[0] : q.peer_A[0];
-            fp.slab_dst[0] = s.r[up].g.slab; fp.slab_dst[1] = s.r[dn].g.slab;
+            // the copy-engine transfers of launch_step_put (d3q19_api.cu): one copy per crossing population and face, the
+            // two c_x = +-1 populations of an in-place odd step as pitched copies of lx-1 columns, then the flags
+            const double *src0 = ab ? q.B : q.A;
+            double *dstA[2] = {ab ? q.peer_B[1] : q.peer_A[1], ab ? q.peer_B[0] : q.peer_A[0]};
+            const long long slab_dst[2] = {s.r[up].g.slab, s.r[dn].g.slab};
             const int lz_dn = s.r[dn].g.lz;
+            int zsrc[2], zdst[2], excl = 0;
+            FaceSlots sl[2];
             switch (SK) {
-            case STEP_AB: fp.zsrc[0] = lz; fp.slots[0] = SLOTS_PZ; fp.zdst[0] = 0; fp.zsrc[1] = 1; fp.slots[1] = SLOTS_MZ; fp.zdst[1] = lz_dn + 1; break;
-            case STEP_AA_EVEN: fp.zsrc[0] = lz; fp.slots[0] = SLOTS_MZ; fp.zdst[0] = 0; fp.zsrc[1] = 1; fp.slots[1] = SLOTS_PZ; fp.zdst[1] = lz_dn + 1; break;
-            default: fp.zsrc[0] = lz + 1; fp.slots[0] = SLOTS_PZ; fp.zdst[0] = 1; fp.zsrc[1] = 0; fp.slots[1] = SLOTS_MZ; fp.zdst[1] = lz_dn;
-                     fp.exclude_walls = 1; break;
+            case STEP_AB: zsrc[0] = lz; sl[0] = SLOTS_PZ; zdst[0] = 0; zsrc[1] = 1; sl[1] = SLOTS_MZ; zdst[1] = lz_dn + 1; break;
+            case STEP_AA_EVEN: zsrc[0] = lz; sl[0] = SLOTS_MZ; zdst[0] = 0; zsrc[1] = 1; sl[1] = SLOTS_PZ; zdst[1] = lz_dn + 1; break;
+            default: zsrc[0] = lz + 1; sl[0] = SLOTS_PZ; zdst[0] = 1; zsrc[1] = 0; sl[1] = SLOTS_MZ; zdst[1] = lz_dn; excl = 1; break;
             }
-            fp.ctr = q.flags + 2;
-            fp.sig[0] = s.r[up].flags;            // the upper neighbour's wait_lo
-            fp.sig[1] = s.r[dn].flags + 1;        // the lower neighbour's wait_hi
-            fp.epoch = q.epoch;
-            const dim3 gp((unsigned)((g.lx + BLOCK_X - 1) / BLOCK_X), (unsigned)g.ly, 10u);
-            fp.nblk = gp.x * gp.y * gp.z;
-            hs_launch(gp, BLOCK_X, k_face_put, g, fp);
+            const size_t pl = (size_t)g.plane;
+            for (int c = 0; c < 5; ++c)
+                for (int d = 0; d < 2; ++d) {
+                    const int slot = sl[d].s[c];
+                    const double *src = src0 + (size_t)slot * g.slab + (size_t)zsrc[d] * pl;
+                    double *dst = dstA[d] + (size_t)slot * slab_dst[d] + (size_t)zdst[d] * pl;
+                    const int cx = dir_cx_rt(slot);
+                    if (excl && cx != 0) {
+                        const size_t off = cx > 0 ? 1 : 0;
+                        for (int y = 0; y < g.ly; ++y)
+                            std::memcpy(dst + off + (size_t)y * g.xp, src + off + (size_t)y * g.xp, (size_t)(g.lx - 1) * sizeof(double));
+                    } else {
+                        std::memcpy(dst, src, pl * sizeof(double));
+                    }
+                }
+            hs_launch(dim3(1), 1, k_flag_raise, (unsigned int *)s.r[up].flags, (unsigned int *)(s.r[dn].flags + 1), q.epoch);
         }
     } else {
         // launch_step_halo: the stores into the neighbours happen inside the step kernel
@@ -313,22 +323,25 @@ PartGeom part_geom(const Sim &s, const Rank &q) {
 
 Links links_of(Rank &q) { return Links{q.lnode.data(), q.ldir.data(), q.lpart.data(), q.lq.data()}; }
 
+static inline dim3 sweep_grid(const Sim &s) {
+    return dim3((unsigned)s.npart, (unsigned)((part_max_rows(s.rad) + PART_WARPS - 1) / PART_WARPS));
+}
+static FillList fill_of(Rank &q, long long cap) { return FillList{q.fnode.data(), q.fpart.data(), &q.pcnt[1], cap}; }
+
 // d3q19_beads_links on every slab
 void beads_links(Sim &s) {
     for (Rank &q : s.r) {
         const PartGeom pg = part_geom(s, q);
-        std::swap(q.own, q.own0);
-        std::fill(q.own.begin(), q.own.end(), -1);
-        const dim3 gp((unsigned)s.npart, PART_SPLIT);
-        hs_launch(gp, 256, k_beads_mask, pg, s.npart, (const double *)q.ypglb.data(), q.own.data());
-        if (!s.mask_built) q.own0 = q.own;
-        const int nslot = s.npart * PART_SPLIT;
-        hs_launch_coop(gp, 256, k_beads_links<false>, pg, s.npart, (const double *)q.ypglb.data(), (const int32_t *)q.own.data(),
-                       q.lcount.data(), (const long long *)q.loffset.data(), s.maxlink, links_of(q));
-        hs_launch_coop(dim3(1), 1024, k_beads_scan, nslot, (const long long *)q.lcount.data(), q.loffset.data());
-        hs_launch_coop(gp, 256, k_beads_links<true>, pg, s.npart, (const double *)q.ypglb.data(), (const int32_t *)q.own.data(),
-                       q.lcount.data(), (const long long *)q.loffset.data(), s.maxlink, links_of(q));
-        if (q.loffset[nslot] > s.maxlink) hs::trap("more links than maxlink");
+        const dim3 gs = sweep_grid(s);
+        q.pcnt[0] = q.pcnt[1] = 0;
+        if (s.mask_built)
+            hs_launch(gs, 32 * PART_WARPS, k_beads_uncover, pg, s.npart, (const double *)q.ypmask.data(), (const double *)q.ypglb.data(),
+                      q.own.data(), fill_of(q, s.maxlink));
+        hs_launch(gs, 32 * PART_WARPS, k_beads_cover, pg, s.npart, (const double *)q.ypglb.data(), q.own.data());
+        q.ypmask = q.ypglb;
+        hs_launch_coop(gs, 32 * PART_WARPS, k_beads_links, pg, s.npart, (const double *)q.ypglb.data(), (const int32_t *)q.own.data(),
+                       &q.pcnt[0], s.maxlink, links_of(q));
+        if ((long long)q.pcnt[0] > s.maxlink) hs::trap("more links than maxlink");
     }
     s.mask_built = true;
     s.links_valid = true;
@@ -338,12 +351,12 @@ template <int RK>
 void ibb_rank(Sim &s, Rank &q) {
     IbbParams P;
     P.pg = part_geom(s, q); P.S = q.A; P.own = q.own.data(); P.L = links_of(q);
-    P.nlink_dev = q.loffset.data() + (size_t)s.npart * PART_SPLIT; P.maxlink = s.maxlink;
+    P.nlink_dev = &q.pcnt[0]; P.maxlink = s.maxlink;
     P.ypglb = q.ypglb.data(); P.wp = q.wp.data(); P.omgp = q.omgp.data(); P.rho0 = s.rho0;
     P.fHIp = q.fHIp.data(); P.torqp = q.torqp.data();
     // like the device path when the host does not know the count: threads for a multiple of the capacity's blocks;
     // here the count is at hand, rounded up so that whole idle warps exist too
-    const long long nthreads = *P.nlink_dev + 200;
+    const long long nthreads = (long long)*P.nlink_dev + 200;
     hs_launch_coop(dim3((unsigned)((nthreads + 127) / 128)), 128, k_beads_ibb<RK>, P);
 }
 void beads_collision(Sim &s) {
@@ -363,35 +376,34 @@ void beads_collision(Sim &s) {
         for (Rank &q : s.r) { q.fHIp = f; q.torqp = t; }
     }
 }
-void beads_lubforce(Sim &s) {
-    for (Rank &q : s.r)
-        hs_launch(dim3((unsigned)((s.npart + 127) / 128)), 128, k_beads_lubforce, part_geom(s, q), s.npart,
-                  (const double *)q.ypglb.data(), s.lub, q.flubp.data());
-}
-void beads_move(Sim &s) {
+static void lubmove(Sim &s, int do_lub, int do_move) {
     for (Rank &q : s.r) {
         MoveParams M = {s.amp, s.aip, s.gforce[0], s.gforce[1], s.gforce[2], q.fHIp.data(), q.torqp.data(), q.flubp.data(),
-                        q.forcepp.data(), q.torqpp.data(), q.ypglb.data(), q.ypglb0.data(), q.wp.data(), q.omgp.data(),
-                        q.thetap.data()};
-        hs_launch(dim3((unsigned)((s.npart + 127) / 128)), 128, k_beads_move, part_geom(s, q), s.npart, M);
+                        q.forcepp.data(), q.torqpp.data(), q.ypglb.data(), q.wp.data(), q.omgp.data(), q.thetap.data()};
+        const int nt = s.npart < 1024 ? ((s.npart + 31) / 32) * 32 : 1024;
+        hs_launch_coop(dim3(1), nt, k_beads_lubmove, part_geom(s, q), s.npart, (const double *)q.ypglb.data(), s.lub, q.flubp.data(), M,
+                       do_lub, do_move);
     }
-    s.links_valid = false;
+    if (do_move) s.links_valid = false;
 }
+void beads_lubforce(Sim &s) { lubmove(s, 1, 0); }
+void beads_move(Sim &s) { lubmove(s, 0, 1); }
 template <int RK>
 void fill_rank(Sim &s, Rank &q) {
     FillParams P;
-    P.pg = part_geom(s, q); P.S = q.A; P.own0 = q.own0.data(); P.own = q.own.data(); P.ypglb0 = q.ypglb0.data();
+    P.pg = part_geom(s, q); P.S = q.A; P.own = q.own.data(); P.F = fill_of(q, s.maxlink);
     P.ypglb = q.ypglb.data(); P.wp = q.wp.data(); P.omgp = q.omgp.data(); P.nfilled = &q.nfilled;
     P.ghost_lo = P.ghost_hi = nullptr;
     if (s.nranks > 1) { P.ghost_lo = q.fill_ghost_lo.data(); P.ghost_hi = q.fill_ghost_hi.data(); }
-    hs_launch(dim3((unsigned)s.npart, PART_SPLIT), 128, k_beads_fill<RK>, P);
+    hs_launch(dim3((unsigned)((q.pcnt[1] + 200 + 127) / 128)), 128, k_beads_fill<RK>, P);
+    q.pcnt[1] = 0;
 }
 template <int RK>
 void plane_gather_rank(Rank &q) {
     const size_t cnt = (size_t)NPOP * q.g.plane;
     q.fill_send_up.assign(cnt, 0.0); q.fill_send_dn.assign(cnt, 0.0);
-    hs_launch(grid_nodes(q.g, 1), BLOCK_X, k_plane_gather<RK>, q.g, (const double *)q.A, q.fill_send_up.data(), q.g.lz);
-    hs_launch(grid_nodes(q.g, 1), BLOCK_X, k_plane_gather<RK>, q.g, (const double *)q.A, q.fill_send_dn.data(), 1);
+    hs_launch(grid_nodes(q.g, 2), BLOCK_X, k_plane_gather<RK>, q.g, (const double *)q.A, q.fill_send_up.data(), q.g.lz,
+              q.fill_send_dn.data(), 1);
 }
 void beads_filling(Sim &s) {
     if (s.nranks > 1) {
@@ -735,12 +747,12 @@ void hs_particles_init(void *h, int npart, double rad, double rho0, double rhopa
     s.rhopart = rhopart;
     for (Rank &q : s.r) {
         const size_t nown = (size_t)q.g.plane * (q.g.lz + 2), tb = (size_t)3 * npart;
-        q.own.assign(nown, -1); q.own0.assign(nown, -1);
-        q.ypglb.assign(ypglb, ypglb + tb); q.ypglb0 = q.ypglb;
+        q.own.assign(nown, -1);
+        q.ypglb.assign(ypglb, ypglb + tb); q.ypmask = q.ypglb;
         q.wp.assign(wp, wp + tb); q.omgp.assign(omgp, omgp + tb);
         for (std::vector<double> *v : {&q.fHIp, &q.torqp, &q.flubp, &q.forcepp, &q.torqpp, &q.thetap}) v->assign(tb, 0.0);
         q.lnode.assign(s.maxlink, 0u); q.ldir.assign(s.maxlink, 0); q.lpart.assign(s.maxlink, 0); q.lq.assign(s.maxlink, 0.0);
-        q.lcount.assign((size_t)npart * PART_SPLIT + 1, 0); q.loffset.assign((size_t)npart * PART_SPLIT + 1, 0);
+        q.fnode.assign(s.maxlink, 0u); q.fpart.assign(s.maxlink, 0);
     }
 }
 
@@ -748,7 +760,7 @@ long long hs_beads_links(void *h) {
     Sim &s = *(Sim *)h;
     beads_links(s);
     long long n = 0;
-    for (Rank &q : s.r) n += q.loffset[(size_t)s.npart * PART_SPLIT];
+    for (Rank &q : s.r) n += (long long)q.pcnt[0];
     return n;
 }
 
@@ -771,15 +783,17 @@ void hs_get_mask(void *h, int32_t *own) {
     for (Rank &q : s.r)
         for (int z = 0; z < q.g.lz; ++z)
             for (int y = 0; y < q.g.ly; ++y)
-                std::memcpy(own + ((size_t)(q.globalz + z) * s.ny + y) * s.nx,
-                            q.own.data() + (size_t)q.g.plane * (z + 1) + (size_t)q.g.xp * y, (size_t)s.nx * sizeof(int32_t));
+                for (int x = 0; x < s.nx; ++x) {          // "uncovered in the last update" (-(q+2)) is fluid to the caller
+                    const int32_t v = q.own[(size_t)q.g.plane * (z + 1) + (size_t)q.g.xp * y + x];
+                    own[((size_t)(q.globalz + z) * s.ny + y) * s.nx + x] = v < 0 ? -1 : v;
+                }
 }
 
 // links of slab k in its order (global 1-based node coordinates); returns the count
 long long hs_get_links(void *h, int k, int32_t *x, int32_t *y, int32_t *z, int32_t *ip, int32_t *part, double *qv) {
     Sim &s = *(Sim *)h;
     Rank &q = s.r[k];
-    const long long n = q.loffset[(size_t)s.npart * PART_SPLIT];
+    const long long n = (long long)q.pcnt[0];
     if (n > 0 && x) {
         hs_launch(dim3((unsigned)((n + 127) / 128)), 128, k_links_export, q.g, q.globalz, n, links_of(q), x, y, z);
         std::memcpy(ip, q.ldir.data(), n * sizeof(int32_t));

@@ -24,7 +24,7 @@ def load(path):
 
 
 def test_fixtures_exist():
-    assert len(CASES) >= 9
+    assert len(CASES) >= 11
 
 
 def _check_stats(z, meta, rows1, rows2, diag, tol=1e-11):
@@ -113,6 +113,8 @@ def test_oracle_reproduces_reference_output(path, ranks):
         if "ox" in z.files:                              # vortcalc, saveload.f90:3929-4054
             for k, a in zip(("ox", "oy", "oz"), w.vortcalc()):
                 assert np.array_equal(a, z[k]), k
+        if "sij2" in z.files:                            # sijstat00's strain rate, saveload.f90:2031-2091
+            assert np.array_equal(w.sijstat(), z["sij2"])
     assert np.array_equal(w.get_f(), z["f"])
     w.close()
 
@@ -198,6 +200,12 @@ def test_cuda_path_reproduces_reference_output(path, scheme, math_mode):
                     assert np.array_equal(a, z[k]), k
                 else:
                     assert np.max(np.abs(a - z[k])) < 1e-11 * vscale, k
+        if "sij2" in z.files:                            # strain rate from the moments of the device populations
+            got, sscale = sim.sijstat(), float(np.max(z["sij2"]))
+            if strict:
+                assert np.array_equal(got, z["sij2"])
+            else:                                        # a difference of nearly equal moments: relative to the largest value
+                assert np.max(np.abs(got - z["sij2"])) < 1e-9 * sscale
     check(sim.sync_f_to_host(), z["f"], "f")
     sim.close()
 

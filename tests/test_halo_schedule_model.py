@@ -1,11 +1,14 @@
 """Stream/event schedules of the multi-GPU step (d3q19_api.cu step_impl) as a small model: every launch is an
 operation with the set of (array, plane, population slot) addresses it reads and writes, every stream order and
 every cudaStreamWaitEvent is a happens-before edge, and the test checks that ANY two operations of a rank that
-touch a common address -- at least one of them writing -- are ordered.  Two schedules:
+touch a common address -- at least one of them writing -- are ordered.  The schedule of the NCCL and the copy-engine
+transports:
 
-  in-order (the default NCCL transport):  sc: B(k) I(k) B(k+1) ...   sx: X(k) after B(k);  B(k+1) after X(k)
-  boundary stream (opt-in):               sb: B(k)   sc: I(k)   sx: X(k)
-        B(k) after I(k-1) and X(k-1);  I(k) after B(k-1);  X(k) after B(k)
+  sc: B(k) I(k) B(k+1) ...   sx: X(k) after B(k);  B(k+1) after X(k)
+
+(A second schedule, "boundary stream" -- B(k) on its own stream next to I(k) -- passed this model in round 1 and FAILED
+bit-exactness on two real GPUs in round 2 (profiles/r02b_pytest_gpu_2gpu.log): the model orders launches of ONE rank and
+takes a message for an edge; it is a necessary check, not a proof.  That schedule was removed.)
 
 B = the two boundary planes, I = the interior planes, X = pack + send/recv + unpack of the faces.  The access sets
 restate kernels.cuh (AB pull / AA even / AA odd) and exchange_after_step; the bit-exact behaviour of those kernels
@@ -73,18 +76,10 @@ def build(scheme, lz, nsteps, schedule):
             ops[(name, k)] = (rd, wr)
         ops[("X", k)] = exchange_access(kind, dst, lz)
     for k in range(1, nsteps + 1):
-        if schedule == "inorder":
-            edges.append((("B", k), ("I", k)))                      # sc: B(k), I(k)
-            if k > 1:
-                edges.append((("I", k - 1), ("B", k)))              # sc: ..., I(k-1), B(k)
-                edges.append((("X", k - 1), ("B", k)))              # wait_exchange
-        else:
-            if k > 1:
-                edges.append((("B", k - 1), ("B", k)))              # sb in order
-                edges.append((("I", k - 1), ("I", k)))              # sc in order
-                edges.append((("I", k - 1), ("B", k)))              # evI recorded on sc at the start of step k
-                edges.append((("X", k - 1), ("B", k)))              # sb waits for evX
-                edges.append((("B", k - 1), ("I", k)))              # sc waits for evB
+        edges.append((("B", k), ("I", k)))                          # sc: B(k), I(k)
+        if k > 1:
+            edges.append((("I", k - 1), ("B", k)))                  # sc: ..., I(k-1), B(k)
+            edges.append((("X", k - 1), ("B", k)))                  # wait_exchange
         edges.append((("B", k), ("X", k)))                          # sx waits for evB
         if k > 1:
             edges.append((("X", k - 1), ("X", k)))                  # sx in order
@@ -122,18 +117,15 @@ def races(scheme, lz, nsteps, schedule):
 
 @pytest.mark.parametrize("scheme", ["ab", "aa"])
 @pytest.mark.parametrize("lz", [3, 4, 5, 8])
-@pytest.mark.parametrize("schedule", ["inorder", "bstream"])
-def test_no_unordered_conflicts(scheme, lz, schedule):
-    assert races(scheme, lz, 7, schedule) == []
+def test_no_unordered_conflicts(scheme, lz):
+    assert races(scheme, lz, 7, "inorder") == []
 
 
 def test_the_model_sees_a_missing_wait():
-    # drop the one edge that makes the interior of step k wait for the boundary planes of step k-1
-    def build_without(scheme, lz, nsteps):
-        ops, edges = build(scheme, lz, nsteps, "bstream")
-        return ops, [e for e in edges if not (e[0][0] == "B" and e[1][0] == "I")]
+    # drop the edge that makes the boundary planes of step k wait for the exchange of step k-1
     for scheme in ("ab", "aa"):
-        ops, edges = build_without(scheme, 5, 5)
+        ops, edges = build(scheme, 5, 5, "inorder")
+        edges = [e for e in edges if not (e[0][0] == "X" and e[1][0] == "B")]
         after = closure(ops, edges)
         found = False
         for a, b in itertools.combinations(ops, 2):
@@ -144,10 +136,10 @@ def test_the_model_sees_a_missing_wait():
 
 
 def test_boundary_and_interior_of_one_step_never_share_an_address():
-    # what lets B(k) run next to I(k) -- in the in-place odd step every address belongs to exactly one node
+    # in the in-place odd step every address belongs to exactly one node
     for scheme in ("ab", "aa"):
         for lz in (3, 4, 6):
-            ops, _ = build(scheme, lz, 4, "bstream")
+            ops, _ = build(scheme, lz, 4, "inorder")
             for k in range(1, 5):
                 (rb, wb), (ri, wi) = ops[("B", k)], ops[("I", k)]
                 assert not (wb & (ri | wi)) and not (wi & rb), (scheme, lz, k)

@@ -6,7 +6,7 @@ subprocesses, unchanged, through the same ctypes binding and the same C++ driver
 * single rank: tests/test_gpu_parity.py, test_golden.py, test_gpu_particles.py, test_zz_cpp_driver.py -- handle life
   cycle, transfers in every storage phase, the shim state machine and its download policy, pre-relaxation, reductions;
 * 2 and 3 ranks (threads): tests/host/hostsim_mrank_worker.py -- slab geometry, the face exchange and the send-back
-  after odd in-place steps, peer-memory connect and flag protocol (fused, split, put), the opt-in boundary stream,
+  after odd in-place steps, peer-memory connect and flag protocol (fused, split, copy-engine put),
   all-reduced scalars, the particle link partition, force all-reduce and the refill source exchange; all bit for
   bit against the single-domain oracle.
 
@@ -92,9 +92,9 @@ def test_bench_product_arm_prints_its_contract_line(hostsim, extra):
     assert pc["bit_exact"] is True and pc["ranks"] == 1 and [t["scheme"] for t in pc["schemes"]] == ["aa", "ab"]
 
 
-def test_full_size_property_tests_and_experiments_on_the_host_sim(hostsim):
-    # the logic of tests/test_zzz_gpu_fullsize.py on a shrunk channel, and the experimental file
-    res = run([sys.executable, "-m", "pytest", "tests/test_zzz_gpu_fullsize.py", "tests/test_zzzz_gpu_experimental.py", "-m", "gpu",
+def test_full_size_property_tests_on_the_host_sim(hostsim):
+    # the logic of tests/test_zzz_gpu_fullsize.py on a shrunk channel
+    res = run([sys.executable, "-m", "pytest", "tests/test_zzz_gpu_fullsize.py", "-m", "gpu",
                "-q", "-p", "no:cacheprovider"],
               hostsim, D3Q19_TEST_FULLSIZE="64x16x16")
     tail = res.stdout[-3000:]

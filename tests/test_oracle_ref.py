@@ -292,3 +292,37 @@ def test_statistc_and_diag_file_output(npy, npz):
     for k, v in zip(("umean", "vmean", "wmean", "urms", "vrms", "wrms", "volf"), d[5:12]):
         assert abs(v - mine[k]) <= 1e-11 * max(abs(v), 1e-3), k
     rw.close(); ow.close()
+
+
+@pytest.mark.parametrize("npy,npz,mrt", [(1, 1, 1), (2, 2, 1), (1, 3, 3), (3, 2, 2)])
+def test_sijstat_strain_rate_bit_exact(npy, npz, mrt):
+    # saveload.f90:2031-2091 (first loop nest of sijstat00): Sij*Sij from the non-equilibrium moments.  The translated
+    # routine keeps it in an automatic array whose elements are captured; the restatement must give the same bits.
+    rw, ow, p = pair(9, 12, 9, npy, npz, False, A9=0.3, mrttype=mrt)
+    rw.run("macrovar"); ow.macrovar()
+    for step in range(3):
+        rw.run("collision_mrt"); rw.run("macrovar")
+        ow.collision_MRT(); ow.macrovar()
+    a, b = rw.sij2(), ow.sijstat()
+    assert np.array_equal(a, b)
+    assert np.min(a) >= 0.0 and np.max(a) > 0.0 and np.isfinite(a).all()
+    rw.close(); ow.close()
+
+
+def test_sijstat_skips_solid_nodes():
+    nx, ny, nz = 11, 12, 12
+    rw = ref.RefWorld(nx, ny, nz, nprocY=1, nprocZ=2, laminar=False, ipart=True)
+    para = orc.make_para(nx, ny, nz, laminar=False, nprocY=1, nprocZ=2, ipart=1)
+    ow = orc.World(para)
+    rw.run("initvel"); ow.initvel(0.0)
+    for k, d in zip(("ux", "uy", "uz"), orc.synthetic_velocity(nx, ny, nz, para.ustar)):
+        rw.set(k, rw.get(k) + d); ow.set(k, ow.get(k) + d)
+    rw.run("forcing"); ow.FORCING()
+    rw.run("initpop"); ow.initpop()
+    zz, yy, xx = np.meshgrid(np.arange(nz) + 0.5, np.arange(ny) + 0.5, np.arange(nx) + 0.5, indexing="ij")
+    mask = (xx - 5.2) ** 2 + (yy - 6.1) ** 2 + (zz - 6.3) ** 2 < 9.0
+    ib, isn = np.where(mask, 1, -1).astype(np.int32), np.where(mask, 1, -1).astype(np.int32)
+    rw.set_solid(ib, isn); ow.set_solid(ib, isn)
+    a, b = rw.sij2(), ow.sijstat()
+    assert np.array_equal(a[~mask], b[~mask]) and np.all(b[mask] == 0.0)
+    rw.close(); ow.close()

@@ -1,6 +1,6 @@
-"""BASELINE.json's full size (configs[1]: 512x256x256, 33.5 M nodes, turbulent set) on the GPU, through
-size-independent properties -- the oracle needs ~0.5 s per step and 20 GB of host arrays at this size, so the
-direct comparisons stay at the sizes of test_gpu_parity.py / test_golden.py:
+"""BASELINE.json's full size (configs[1]: 512x256x256, 33.5 M nodes, turbulent set) on the GPU: three steps against the
+REFERENCE ITSELF (the translated Fortran, ~1 s per step on the host cores, test_reference_bit_for_bit_at_full_size),
+and, for longer runs, size-independent properties:
 
 * the two storage schemes are independent implementations of the same map (one-step pull into a second array
   vs. in-place even/odd): in STRICT arithmetic they must stay BIT-IDENTICAL, seen through probes at corner / wall /
@@ -8,8 +8,6 @@ direct comparisons stay at the sizes of test_gpu_parity.py / test_golden.py:
 * download -> upload into the other scheme is the identity (gather / scatter / un-stream kernels at full size);
 * mass is conserved by collision, forcing, streaming and the bounce-back walls;
 * the production (FAST, FMA) arithmetic stays within BASELINE.json's 1e-12 (1 step) / 1e-9 (here 100 steps) of STRICT.
-
-The file sorts last on purpose: it was written in a session without GPU time.
 """
 import numpy as np
 import pytest
@@ -130,3 +128,76 @@ def test_fast_arithmetic_tracks_strict_at_full_size(scheme):
     rel = np.max(np.abs(ps[:11] - pf[:11]) / row_scales(ps), axis=1)
     assert np.max(rel) < 1e-9, rel
     strict.close(); fast.close()
+
+
+# ---- the reference itself at full size ------------------------------------------------------------------------------
+def _reference_run(nx, ny, nz, steps_at):
+    """the translated reference (oracle/_ref/libref.so: collision.f90 / para.f90 / initial.f90 machine-translated to C,
+    IEEE evaluation of the source order; the hand restatement is bit-identical to it, tests/test_oracle_ref.py) on all
+    host cores, one thread per emulated MPI rank: f0 and f after each step count in `steps_at`"""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref.so was not built (it is built where /root/reference is mounted and travels with the repo)")
+    ncores = os.cpu_count() or 1
+    npz = 1
+    while npz * 2 <= ncores and nz % (npz * 2) == 0 and (npz * 2) ** 2 <= ncores * 2:
+        npz *= 2
+    npy = max(1, ncores // npz)
+    while ny % npy:
+        npy -= 1
+    w = ref.RefWorld(nx, ny, nz, nprocY=npy, nprocZ=npz, laminar=False, a9=0.3, **({} if nx >= 512 else dict(ustar=0.0025)))
+    w.run("initvel")                                   # main.f90:58 (log-law + the A9 perturbation block)
+    rng = np.random.default_rng(54321)
+    for k in ("ux", "uy", "uz"):                       # SURVEY.md 8(d): seeded noise so that every population is distinct
+        w.set(k, w.get(k) + 1e-3 * w.scalar("ustar") * (2.0 * rng.random((nz, ny, nx)) - 1.0))
+    w.run("forcing"); w.run("initpop"); w.run("macrovar")          # main.f90:61,65,136
+    yield w.get_f()
+    done = 0
+    for n in steps_at:
+        w.loop("collision_mrt", "macrovar", n - done)              # main.f90:157-161
+        done = n
+        yield w.get_f()
+    w.close()
+
+
+@pytest.mark.parametrize("shape,schemes", [((NX, NY, NZ), ("aa", "ab")), ((2 * NX, 4 * NY, max(NZ // 16, 4)), ("aa",))],
+                         ids=["configs1", "c4_plane_1024x1024"])
+def test_reference_bit_for_bit_at_full_size(shape, schemes):
+    """configs[1] (512x256x256) and a 1024x1024-wide slab of configs[3]'s planes (in place, as C4 must run): 3 steps of the
+    reference's own code and of the GPU from the same bits -- STRICT arithmetic bit for bit, production arithmetic
+    within BASELINE.json's 1e-12 after one step"""
+    nx, ny, nz = shape
+    kw = {} if nx >= 512 else dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+    gen = _reference_run(nx, ny, nz, (1, 3))
+    f0 = next(gen)
+    sims = []
+    for name in schemes:
+        for mm in (capi.MATH_STRICT, capi.MATH_FAST):
+            if mm == capi.MATH_FAST and name != schemes[-1]:
+                continue                                           # one production-arithmetic run is enough
+            sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=capi.SCHEME_AA if name == "aa" else capi.SCHEME_AB,
+                                  math_mode=mm, allocate_host=False, **kw)
+            sim.FORCING()
+            sim.upload_f(f0)
+            sims.append((name, mm, sim))
+    del f0
+    out = np.empty((nz, ny, nx, 19))
+    done = 0
+    for n in (1, 3):
+        ref_f = next(gen)
+        scale = float(np.max(np.abs(ref_f)))
+        for name, mm, sim in sims:
+            sim.run_device(n - done)
+            sim.download_f(out)
+            if mm == capi.MATH_STRICT:
+                assert np.array_equal(out, ref_f), (name, n)
+            else:
+                np.subtract(out, ref_f, out=out)
+                err = float(np.max(np.abs(out))) / scale
+                assert err < (1e-12 if n == 1 else 1e-11), (name, n, err)
+        done = n
+        del ref_f
+    for _, _, sim in sims:
+        sim.close()
+    for _ in gen:
+        pass
