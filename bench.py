@@ -81,6 +81,23 @@ def workload_dims(name):
     return nx, ny, nz
 
 
+def kernel_source_hash():
+    """sha256 over the sources that define the step kernels (what an ncu capture of k_step is valid for)"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "d3q19-single-phase_b200", "csrc")
+    for n in ("kernels.cuh", "collide.cuh", "lattice.cuh"):
+        h.update(n.encode()); h.update(open(os.path.join(d, n), "rb").read())
+    return h.hexdigest()
+
+
+def shared_config(nx, ny, nz, nz_local, particles, rad):
+    """the `config` object of BOTH arms (the driver compares them): what is computed, not how"""
+    return {"workload": workload_name(nx, ny, nz), "per_gpu": "%dx%dx%d z-slab" % (nx, ny, nz_local), "precision": "fp64",
+            "particles": ("%d moving spheres of radius %g: links, interpolated bounce-back, momentum-exchange force, "
+                          "lubrication, move, refill every step" % (particles, rad)) if particles else "none"}
+
+
 def workload_name(nx, ny, nz):
     return ("D3Q19 MRT channel %dx%dx%d (nx x ny x nz, x wall-normal), turbulent set Re_tau=180, "
             "uniform body force, half-way bounce-back walls" % (nx, ny, nz))
@@ -88,53 +105,84 @@ def workload_name(nx, ny, nz):
 
 # ---- clocks during the timed region (B200_PROFILING.md "clocks line") -------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU, sampled IN PROCESS through NVML by a thread (every 5 ms) while the
+    main thread sits in the library call: works under torchrun, needs no nvidia-smi start-up time, and a 30 ms timed
+    region still gets several samples.  `nvidia-smi` is only the fallback when the NVML binding is missing."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.th, self.stop_flag, self.t_mark, self.err = index, [], None, False, 0.0, None
+        self.nv = self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps ordinals: find the NVML device of CUDA device `index` by its PCI bus id
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                toks = [t.strip() for t in vis.split(",") if t.strip()]
+                if index < len(toks) and toks[index].isdigit():
+                    phys = int(toks[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:                       # no NVML binding / no driver: say so in the record
+            self.err, self.nv = "%s: %s" % (type(exc).__name__, exc), None
+
+    def pin_to_gpu_numa_node(self):
+        """bind this process to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any host buffer is allocated, so
+        that pinned staging memory is first-touched on the GPU's NUMA node; returns a short description"""
+        if not self.nv:
+            return "no NVML"
+        try:
+            self.nv.nvmlDeviceSetCpuAffinity(self.h)
+            cpus = sorted(os.sched_getaffinity(0))
+            return "process bound to the %d CPUs NVML lists for GPU %d (%d..%d)" % (len(cpus), self.index, cpus[0], cpus[-1])
+        except Exception as exc:
+            return "not bound (%s)" % exc
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = None
+                self.rows.append((time.perf_counter(), float(mhz), int(rs), pw))
+            except Exception as exc:
+                self.err = "%s: %s" % (type(exc).__name__, exc)
+                return
+            time.sleep(0.005)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+        if self.nv:
+            self.th = threading.Thread(target=self._loop, daemon=True)
             self.th.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [t.strip() for t in line.split(",")]))
 
     def mark(self):
         """start of the timed region: earlier samples (warm-up) are dropped when later ones exist"""
         self.t_mark = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        t_mark = getattr(self, "t_mark", 0.0)
-        inside = [r for t, r in self.rows if t >= t_mark]
-        rows = inside if inside else [r for t, r in self.rows[-3:]]     # a very short region: the last warm-up samples
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["NVML unavailable: %s" % self.err]}
+        self.stop_flag = True
+        self.th.join(timeout=2)
+        inside = [r for r in self.rows if r[0] >= self.t_mark]
+        rows = inside if inside else self.rows[-3:]
+        mask = 0
         for r in rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            mask |= r[2]
+        pw = [r[3] for r in rows if r[3] is not None]
+        return {"sm_mhz": statistics.median([r[1] for r in rows]) if rows else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(rows), "power_w": statistics.median(pw) if pw else None,
+                "reasons": sorted(k for k, bit in self.REASONS.items() if mask & bit), "how": "NVML in process, 5 ms"}
 
 
 # ---- the CPU arm: the restated reference on the host cores -----------------------------------------
@@ -301,15 +349,17 @@ def main():
             return 0
         # bounded sample: the single-GPU workload (the per-GPU block), a few steps
         cpu_steps = max(1, min(args.steps, args.cpu_steps))
-        res = cpu_reference_run(nx, ny, nz_unit, cpu_steps, min(args.warmup, 1))
+        cpu_warm = max(0, min(args.warmup, 5))          # a CPU warm-up step costs ~0.6 s: the driver's W (>= 3) is honoured up to 5
+        res = cpu_reference_run(nx, ny, nz_unit, cpu_steps, cpu_warm)
+        nz_local = nz // n_gpus if n_gpus > 1 else nz
         line = {
             "impl": "reference", "metric": "MLUPS (fp64)", "value": res["value"], "unit": "MLUPS",
-            "n_gpus": n_gpus, "steps": cpu_steps, "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
+            "n_gpus": n_gpus, "steps": cpu_steps, "warmup": cpu_warm, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(nx, ny, nz),
-                       "note": "CPU arm: the reference's own hot path on the host cores; bounded sample = the per-GPU block "
-                               "%dx%dx%d, %d step(s)" % (nx, ny, nz_unit, cpu_steps)},
+            "config": shared_config(nx, ny, nz, nz_local, args.particles, args.rad),
+            "implementation": {"note": "CPU arm: the reference's own hot path on the host cores; bounded sample = the per-GPU "
+                                       "block %dx%dx%d, %d step(s)" % (nx, ny, nz_unit, cpu_steps)},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -329,6 +379,10 @@ def main():
     if capi.is_hostsim() and os.environ.get("D3Q19_HOSTSIM_BENCH_STRUCTURE_TEST") != "1":
         raise SystemExit("bench.py: D3Q19_LIB points at the tests' host-sim build; it is never benchmarked")
     torch.cuda.set_device(local_rank)
+    # clocks are sampled in process (NVML); with several ranks on one host every rank also binds itself to the CPUs next
+    # to its GPU before it allocates pinned staging memory (the e2e leg uploads 5 GB per rank at the same time)
+    sampler = ClockSampler(local_rank)
+    numa_note = sampler.pin_to_gpu_numa_node() if world > 1 else "single process: not bound"
     nccl_id = None
     if world > 1:
         dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
@@ -456,9 +510,8 @@ def main():
             sim.run_device(n)
 
     # ---- device-timed value -------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()                 # nvidia-smi needs ~0.1 s to deliver its first sample: start before the warm-up
+        sampler.start()
     ok = True
     try:
         advance(args.warmup)
@@ -502,17 +555,25 @@ def main():
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     nodes_local = nx * ny * sim.lz
     achieved = BYTES_PER_NODE * nodes_local / (ms * 1e-3 / args.steps) / 1e9
-    # DRAM bytes per launch of the same kernel at the same per-GPU size from the committed ncu --set full
-    # capture (profiles/traffic.json, made by tools/summarize_ncu.py); null when that size was not captured
-    traffic = None
+    # DRAM bytes per launch of the same kernel at the same per-GPU size from the committed ncu --set full capture
+    # (profiles/traffic.json, made by tools/summarize_ncu.py).  The capture names the library build it was taken on
+    # (sha256 of libd3q19b200.so's kernels source set): null when this run's library is another build or the size was
+    # not captured -- a stale number is worse than none.
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("%s_%dx%dx%d" % (args.scheme, nx, ny, sim.lz), {}).get("gb_per_launch")
+            tj = json.load(open(tp))
+            ent = tj.get("%s_%dx%dx%d" % (args.scheme, nx, ny, sim.lz))
+            if ent and ent.get("kernel_source_sha256") == kernel_source_hash():
+                traffic = ent.get("gb_per_launch")
+                traffic_src = "profiles/traffic.json <- %s (same kernel sources)" % ent.get("source")
+            elif ent:
+                traffic_src = "capture %s was taken on other kernel sources: not reported" % ent.get("source")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "bytes_per_node": BYTES_PER_NODE, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "bytes_per_node": BYTES_PER_NODE, "peak_source": peak_src,
                 "kernel": "k_step<%s>" % ("AA even/odd" if args.scheme == "aa" else "AB pull")}
 
     # ---- end to end through the reference-facing interface, host buffers ------------------------
@@ -525,8 +586,12 @@ def main():
         barrier(); sim.sync()
         t0 = time.perf_counter()
         d2h = 0
+        t_first = None
         for sim.istep in range(1, args.steps + 1):
             sim.collision_MRT()                    # first call uploads f (H2D, pinned)
+            if t_first is None:
+                sim.sync()
+                t_first = time.perf_counter() - t0 # upload of f + one step
             sim.macrovar()                         # shim policy: downloads rho,u on output steps + the last
             pr = sim.probe(nx // 2, ny // 2, max(1, sim.lz // 2))
             d2h += 32
@@ -537,7 +602,11 @@ def main():
         e2e = {"value": nodes_global * args.steps / dt / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": 19 * 8 * nodes_local / args.steps,
                "d2h_bytes_per_step": d2h / args.steps,
-               "what": "upload f from pinned host + K x (collision_MRT; macrovar; probe) through the shim entry points"}
+               "what": "upload f from pinned host + K x (collision_MRT; macrovar; probe) through the shim entry points",
+               # where the time goes: the one upload of f (19 x 8 B per node over PCIe) against K steps
+               "upload_s": max_over_ranks(t_first), "total_s": dt,
+               "upload_gbs_per_gpu": 19 * 8 * nodes_local / max(t_first, 1e-9) / 1e9,
+               "numa": numa_note}
 
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:
@@ -550,10 +619,9 @@ def main():
             "metric": "MLUPS (fp64)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(nx, ny, nz),
-                       "per_gpu": "%dx%dx%d z-slab" % (nx, ny, sim.lz), "scheme": args.scheme, "math": args.math,
-                       "particles": ("%d moving spheres of radius %g: links, interpolated bounce-back, momentum-exchange force, "
-                                     "lubrication, move, refill every step" % (args.particles, args.rad)) if args.particles else "none",
+            "config": shared_config(nx, ny, nz, sim.lz, args.particles, args.rad),
+            "implementation": {
+                       "scheme": args.scheme, "math": args.math,
                        "parallelism": ("z-slab x%d, faces %s" % (world, {
                            "peer": "stored into the neighbour GPU's memory over NVLink inside the step kernel",
                            "put": "copied into the neighbour GPU's memory over NVLink by the copy engines on a second stream",
