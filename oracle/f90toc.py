@@ -73,6 +73,30 @@ def lower_outside_strings(s):
     return "".join(out)
 
 
+def split_concat(s):
+    """pieces of a character expression a // b // c (top level, outside strings)"""
+    out, cur, depth, q, i = [], "", 0, None, 0
+    while i < len(s):
+        ch = s[i]
+        if q:
+            cur += ch
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch; cur += ch
+        elif ch == "(":
+            depth += 1; cur += ch
+        elif ch == ")":
+            depth -= 1; cur += ch
+        elif ch == "/" and s[i:i + 2] == "//" and depth == 0:
+            out.append(cur); cur = ""; i += 1
+        else:
+            cur += ch
+        i += 1
+    out.append(cur)
+    return out
+
+
 def logical_lines(path):
     """[(first_line_number, text)] with comments removed, continuations joined, lower-cased."""
     res, cur, start = [], "", None
@@ -890,6 +914,29 @@ class Translator:
                 return
         if t == "continue":
             return
+        m = re.match(r"^write\s*\(\s*(\d+)\s*\)\s*(.*)$", t)
+        if m:
+            # UNFORMATTED sequential output (checkpoint files, saveload.f90:226-227): one statement = one record.  The
+            # values go to capture unit 9000+u in list order (a whole array: every element, first dimension fastest),
+            # the record structure to unit 9500+u as  -1, (kind, count) per item  with kind = 4 (integer) or 8 (real):
+            # enough to rebuild the record's bytes.  (The 4-byte record markers around them are the compiler runtime's.)
+            u = int(m.group(1))
+            self.emit("ref_capture(S, %d, -1.0);" % (9500 + u))
+            for item in split_top(m.group(2)):
+                item = item.strip()
+                if not item:
+                    continue
+                e = parse_expr(item)
+                kind = 8 if self.typeof(e) == "real" else 4
+                shape = self.section_shape(e) if isinstance(e, (Var, Index)) else None
+                if shape:
+                    op, cl, names = self.loops(shape)
+                    self.emit("{ long cnt_ = 0; %s{ ref_capture(S, %d, (double)(%s)); ++cnt_; }%s ref_capture(S, %d, %d.0); "
+                              "ref_capture(S, %d, (double)cnt_); }" % (op, 9000 + u, self.cx(e, names), cl, 9500 + u, kind, 9500 + u))
+                else:
+                    self.emit("ref_capture(S, %d, (double)(%s)); ref_capture(S, %d, %d.0); ref_capture(S, %d, 1.0);"
+                              % (9000 + u, self.cx(e), 9500 + u, kind, 9500 + u))
+            return
         m = re.match(r"^write\s*\(\s*(\d+)\s*,", t)
         if m:
             # formatted output to a file unit: hand the numeric items to the capture buffer in list order
@@ -1024,7 +1071,19 @@ class Translator:
                 lname = re.match(r"[a-z_0-9]+", t[:i].strip())
                 ls = self.sym(lname.group(0)) if lname else None
                 if ls is not None and ls.typ == "other":
-                    self.emit("/* character assignment skipped */;")
+                    # character assignment (file names, saveload.f90:214-218): the pieces of the concatenation go to
+                    # capture unit 9900 -- a literal as its character codes, char(expr) as the value of expr, anything
+                    # else (trim(directory)) as -1
+                    self.emit("ref_capture(S, 9900, -2.0);")
+                    for piece in split_concat(t[i + 1:].strip()):
+                        piece = piece.strip()
+                        if piece[:1] in "'\"":
+                            for ch in piece[1:-1]:
+                                self.emit("ref_capture(S, 9900, %d.0);" % ord(ch))
+                        elif piece.startswith("char(") and piece.endswith(")"):
+                            self.emit("ref_capture(S, 9900, (double)(%s));" % self.cx(parse_expr(piece[5:-1])))
+                        else:
+                            self.emit("ref_capture(S, 9900, -1.0);")
                     return
                 self.assignment(t[:i].strip(), t[i + 1:].strip(), override_ok=ov)
                 return
@@ -1051,6 +1110,7 @@ class Translator:
         self.in_case = False
         self.wanted = ["para", "allocarray", "initpop", "initvel", "collisionexchnge", "collision_mrt", "macrovar",
                        "rhoupdat", "avedensity", "forcing", "forcingp", "exchng8", "vortcalc", "sijstat00",
+                       "savecntdflow", "saveinitflow", "saveprerelax",
                        "statistc", "statistc2", "diag"]
         o = self.emit
         o("/* GENERATED by oracle/f90toc.py from the reference's Fortran sources -- do not edit, do not commit. */")
@@ -1115,6 +1175,9 @@ class Translator:
         # saveload.f90:2031-2091; what follows in that routine are particle-centred shell statistics).  Sij2 is an
         # automatic array there: its elements are captured under unit 99.
         self.translate_sub("sijstat00", save["sijstat00"], stop_after=(r"^end\s*do$", 3), capture_local=("sij2", 99))
+        # rank 2: the checkpoint writers -- file name pieces and the records of their unformatted writes are captured
+        for n in ("savecntdflow", "saveinitflow", "saveprerelax"):
+            self.translate_sub(n, save[n])
         # ---- dispatch + reflection tables for the Python wrapper
         o("\nint ref_dispatch(ref_state *S, const char *name)\n{")
         for n in self.wanted:

@@ -152,3 +152,90 @@ def test_cpu_yz_decomposition_to_gpu_slabs(tmp_path, oracle):
         assert sl.loadcntdflow(t, str(tmp_path / "gpu"), 1000)[0] == 1000
         assert np.array_equal(t.f, full[gz:gz + lz])
     w.close()
+
+
+# ---- the reference's own writers (saveload.f90) executed: what they name the file and what they put into its records -----
+def _reference_records(w, sub, unit=12, rank=0):
+    """run a translated checkpoint writer and rebuild (file-name pieces, [record payload bytes]) from what it handed to its
+    character assignment and its unformatted write statements (oracle/f90toc.py captures both)"""
+    w.clear_captured()
+    w.run(sub)
+    name = w.captured(9900, rank=rank)
+    start = int(np.max(np.nonzero(name == -2.0)[0]))             # the last character assignment is the file name
+    pieces = name[start + 1:]
+    text = "".join("<dir>" if c == -1.0 else chr(int(c)) for c in pieces)
+    struct_, vals = w.captured(9500 + unit, rank=rank), w.captured(9000 + unit, rank=rank)
+    recs, pos, i = [], 0, 0
+    while i < len(struct_):
+        assert struct_[i] == -1.0
+        i += 1
+        payload = b""
+        while i < len(struct_) and struct_[i] != -1.0:
+            kind, cnt = int(struct_[i]), int(struct_[i + 1])
+            chunk = vals[pos:pos + cnt]
+            payload += chunk.astype("<i4" if kind == 4 else "<f8").tobytes()
+            pos += cnt
+            i += 2
+        recs.append(payload)
+    assert pos == len(vals)
+    w.clear_captured()
+    return text, recs
+
+
+def _file_records(path):
+    out = []
+    with open(path, "rb") as fh:
+        while True:
+            try:
+                out.append(sl.read_record(fh))
+            except struct.error:
+                return out
+
+
+class RankView:
+    """one rank of the translated reference seen through the attributes saveload.py reads"""
+
+    def __init__(self, w, r):
+        self.rank = r
+        self.f = np.ascontiguousarray(w.array("f", r)[0])
+        self.rho, self.ux, self.uy, self.uz = (np.ascontiguousarray(w.array(k, r)[0]) for k in ("rho", "ux", "uy", "uz"))
+        self.lz, self.ly, self.lx = self.f.shape[:3]
+        self.v = type("V", (), dict(istep0=int(w.scalar("istep0", r)), nsteps=int(w.scalar("nsteps", r))))()
+
+    def sync_f_to_host(self):
+        return self.f
+
+
+def test_files_hold_what_the_reference_writes(tmp_path):
+    # saveload.f90:196-231 (savecntdflow), :102-124 (saveinitflow), :50-73 (saveprerelax) machine-translated and RUN on a
+    # 1 x 2 rank grid: file name and record payloads of saveload.py must be the reference's, byte for byte.  (The 4-byte
+    # markers framing each record are the Fortran runtime's convention, not in the reference's source.)
+    import pytest
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref.so not built (no /root/reference here)")
+    nx, ny, nz = 7, 6, 5
+    w = ref.RefWorld(nx, ny, nz, nprocY=1, nprocZ=2, laminar=False, a9=0.3, ustar=0.0025)
+    w.run("initvel"); w.run("forcing"); w.run("initpop"); w.run("macrovar")
+    w.loop("collision_mrt", "macrovar", 3)
+    w.set_scalar("istep0", 1200); w.set_scalar("nsteps", 345); w.set_scalar("istat", 4); w.set_scalar("imovie", 2)
+    for r in (0, 1):
+        view = RankView(w, r)
+        # continued-run file
+        text, recs = _reference_records(w, "savecntdflow", rank=r)
+        path = sl.savecntdflow(view, str(tmp_path), istat=4, imovie=2)
+        assert "<dir>" + path[len(str(tmp_path)) + 1:] == text                      # endrunflow2D16x8.0001545.00r
+        assert _file_records(path) == recs and len(recs) == 2
+        assert np.frombuffer(recs[0], dtype="<i4").tolist() == [1545, 4, 2]
+        # initial-flow file
+        text, recs = _reference_records(w, "saveinitflow", unit=10, rank=r)
+        path = sl.saveinitflow(view, str(tmp_path), istat=4)
+        assert "<dir>" + path[len(str(tmp_path)) + 1:] == text                      # finit.00r
+        assert _file_records(path) == recs and len(recs) == 2
+        # pre-relaxation file: (f, rho) in ONE record, then (ux, uy, uz)
+        w.set_scalar("istep", 77)
+        text, recs = _reference_records(w, "saveprerelax", unit=10, rank=r)
+        path = sl.saveprerelax(view, str(tmp_path), 77)
+        assert "<dir>" + path[len(str(tmp_path)) + 1:] == text                      # prerelax_01/finit.00r
+        assert _file_records(path) == recs and len(recs) == 3
+    w.close()
