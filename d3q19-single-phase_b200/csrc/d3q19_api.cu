@@ -111,10 +111,10 @@ struct d3q19_handle {
     double *pbuf = nullptr;                      // 10 tables of (3,npart)
     double *ypmask = nullptr,                    // the positions the mask was built with
            *fHIp = nullptr, *torqp = nullptr, *flubp = nullptr, *forcepp = nullptr, *torqpp = nullptr, *thetap = nullptr;
-    Links links = {nullptr, nullptr, nullptr, nullptr};
+    Links links = {nullptr, nullptr, nullptr, 0};
     FillList fill = {nullptr, nullptr, nullptr, 0};   // nodes the last mask update uncovered (what beads_filling rebuilds)
     long long maxlink = 0, nlink = 0;
-    unsigned long long *pcnt = nullptr;          // device counters: [0] links, [1] refill list, [2] refilled nodes
+    unsigned long long *pcnt = nullptr;          // device counters: [1] refill list, [2] refilled nodes (the link counts live in links.count)
     int part_rows = 0;                           // rows of the largest bounding box (grid of the sweep kernels)
     double *fill_halo = nullptr;                 // z-slab refill: [send up][send dn][ghost lo][ghost hi], 19 x plane each
     double amp = 0, aip = 0;
@@ -286,7 +286,7 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
         h->halo_on = false;
     }
     if (h->part_on) {
-        void *pp_[] = {h->own, h->pbuf, h->links.node, h->links.dir, h->links.part, h->links.q, h->fill.node, h->fill.part,
+        void *pp_[] = {h->own, h->pbuf, h->links.node, h->links.dir, h->links.count, h->fill.node, h->fill.part,
                        h->pcnt, h->fill_halo};
         for (void *q : pp_) if (q) cudaFree(q);
         h->solid = h->isn = nullptr; h->ypglb = h->wp = h->omgp = nullptr;
@@ -1257,7 +1257,7 @@ extern "C" int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_
     // a particle's bounding box (< 2 rad + 6 nodes wide) must be smaller than the periodic box: no node is visited twice
     if (2.0 * prm->rad + 7.0 > h->cfg.ny || 2.0 * prm->rad + 7.0 > h->cfg.nz) return fail("d3q19_particles_init: particle larger than the periodic box (2 rad + 7 <= ny, nz)");
     if (prm->rad > 600.0) return fail("d3q19_particles_init: rad %g: a particle's bounding box must hold fewer than 2^31 nodes", prm->rad);
-    if (npart > 0x3ffffff0) return fail("d3q19_particles_init: too many particles");
+    if (npart > 65535) return fail("d3q19_particles_init: at most 65535 particles (one grid row per particle)");
     h->pp = *prm;
     if (h->ypglb) { cudaFree(h->ypglb); cudaFree(h->wp); cudaFree(h->omgp); }
     if (h->solid) { cudaFree(h->solid); h->solid = nullptr; }
@@ -1273,11 +1273,14 @@ extern "C" int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_
     CK(cudaMalloc(&h->own, nown * sizeof(int32_t)));
     CK(cudaMemsetAsync(h->own, 0xFF, nown * sizeof(int32_t), h->sc));
     const double pi = 4.0 * atan(1.0);
-    h->maxlink = prm->maxlink > 0 ? prm->maxlink : (long long)(8.0 * npart * 4.0 * pi * (prm->rad + 1.0) * (prm->rad + 1.0)) + 64;
+    // every particle owns a segment of the link list: maxlink (all particles) / npart entries, by default 8 links per
+    // surface node of a sphere of radius rad + 1 (cf. para.f90:371)
+    h->links.cap = prm->maxlink > 0 ? (prm->maxlink + npart - 1) / npart : (long long)(8.0 * 4.0 * pi * (prm->rad + 1.0) * (prm->rad + 1.0)) + 64;
+    h->maxlink = h->links.cap * npart;
     CK(cudaMalloc(&h->links.node, h->maxlink * sizeof(uint32_t)));
     CK(cudaMalloc(&h->links.dir, h->maxlink * sizeof(int32_t)));
-    CK(cudaMalloc(&h->links.part, h->maxlink * sizeof(int32_t)));
-    CK(cudaMalloc(&h->links.q, h->maxlink * sizeof(double)));
+    CK(cudaMalloc(&h->links.count, (size_t)npart * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(h->links.count, 0, (size_t)npart * sizeof(unsigned long long), h->sc));
     CK(cudaMalloc(&h->pcnt, 4 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(h->pcnt, 0, 4 * sizeof(unsigned long long), h->sc));
     // a mask update uncovers at most a surface layer of every particle: the link capacity bounds it
@@ -1324,27 +1327,35 @@ extern "C" int d3q19_set_particles(d3q19_handle *h, int32_t npart, const double 
     return 0;
 }
 
-// the link count lives on the device (the step sequence never waits for it); the host asks when it must
-static int fetch_nlink(d3q19_handle *h) {
-    if (h->nlink >= 0) return 0;
-    unsigned long long n = 0;
-    CK(cudaMemcpyAsync(&n, h->pcnt, sizeof n, cudaMemcpyDeviceToHost, h->sc));
+// the link counts live on the device (the step sequence never waits for them); the host asks when it must.
+// k_beads_links drops the entries beyond a segment's capacity and k_beads_ibb skips them, which would let mass and momentum
+// leak through the particle surface unnoticed: whoever fetches the counts checks them
+static int fetch_link_counts(d3q19_handle *h, std::vector<unsigned long long> &cnt, const char *who) {
+    cnt.assign((size_t)h->npart + 1, 0ull);
+    CK(cudaMemcpyAsync(cnt.data(), h->links.count, (size_t)h->npart * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->sc));
+    CK(cudaMemcpyAsync(&cnt[h->npart], h->pcnt + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->sc));
     CK(cudaStreamSynchronize(h->sc));
-    if ((long long)n > h->maxlink) return fail("d3q19_beads_links: %llu links exceed maxlink %lld", n, h->maxlink);
-    h->nlink = (long long)n;
+    for (int p = 0; p < h->npart; ++p)
+        if ((long long)cnt[p] > h->links.cap)
+            return fail("%s: particle %d has %llu boundary links on this slab, its segment holds %lld -- links were dropped, the "
+                        "populations are void (d3q19_particle_params.maxlink = links of ALL particles)", who, p + 1, cnt[p], h->links.cap);
+    if ((long long)cnt[h->npart] > h->fill.cap)
+        return fail("%s: the last move uncovered %llu nodes, the refill list holds %lld", who, cnt[h->npart], h->fill.cap);
     return 0;
 }
-
-// k_beads_links drops the entries beyond maxlink and k_beads_ibb skips them, which would let mass and momentum leak
-// through the particle surface unnoticed; the counters stay on the device, so this is asked where the host waits anyway
+static int fetch_nlink(d3q19_handle *h) {
+    if (h->nlink >= 0) return 0;
+    std::vector<unsigned long long> cnt;
+    RK_(fetch_link_counts(h, cnt, "d3q19_beads_links"));
+    long long n = 0;
+    for (int p = 0; p < h->npart; ++p) n += (long long)cnt[p];
+    h->nlink = n;
+    return 0;
+}
 static int check_link_overflow(d3q19_handle *h, const char *who) {
     if (!h->part_on) return 0;
-    unsigned long long n[2] = {0, 0};
-    CK(cudaMemcpy(n, h->pcnt, sizeof n, cudaMemcpyDeviceToHost));
-    if ((long long)n[0] > h->maxlink || (long long)n[1] > h->fill.cap)
-        return fail("%s: the last step built %llu boundary links and %llu refill nodes, capacity maxlink = %lld -- entries were "
-                    "dropped, the populations are void (d3q19_particle_params.maxlink)", who, n[0], n[1], h->maxlink);
-    return 0;
+    std::vector<unsigned long long> cnt;
+    return fetch_link_counts(h, cnt, who);
 }
 
 static inline dim3 sweep_grid(const d3q19_handle *h) {
@@ -1364,7 +1375,8 @@ extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local) {
     const PartGeom pg = part_geom(h);
     const dim3 gs = sweep_grid(h);
     const size_t tb = (size_t)3 * h->npart * sizeof(double);
-    CK(cudaMemsetAsync(h->pcnt, 0, 2 * sizeof(unsigned long long), h->sc));          // links, refill list
+    CK(cudaMemsetAsync(h->pcnt, 0, 2 * sizeof(unsigned long long), h->sc));          // refill list
+    CK(cudaMemsetAsync(h->links.count, 0, (size_t)h->npart * sizeof(unsigned long long), h->sc));
     if (h->mask_built) {
         k_beads_uncover<<<gs, 32 * PART_WARPS, 0, h->sc>>>(pg, h->npart, h->ypmask, h->ypglb, h->own, h->fill);
         h->n_other_kernels++;
@@ -1372,7 +1384,7 @@ extern "C" int d3q19_beads_links(d3q19_handle *h, int64_t *nlink_local) {
     k_beads_cover<<<gs, 32 * PART_WARPS, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own);
     CK(cudaMemcpyAsync(h->ypmask, h->ypglb, tb, cudaMemcpyDeviceToDevice, h->sc));
     h->mask_built = true;
-    k_beads_links<<<gs, 32 * PART_WARPS, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->pcnt, h->maxlink, h->links);
+    k_beads_links<<<gs, 32 * PART_WARPS, 0, h->sc>>>(pg, h->npart, h->ypglb, h->own, h->links);
     CK(cudaGetLastError());
     h->n_other_kernels += 2;
     h->links_valid = true;
@@ -1391,20 +1403,17 @@ extern "C" int d3q19_beads_collision(d3q19_handle *h) {
     {
         IbbParams P;
         P.pg = part_geom(h); P.S = h->A; P.own = h->own; P.L = h->links;
-        P.nlink_dev = h->pcnt; P.maxlink = h->maxlink;
         P.ypglb = h->ypglb; P.wp = h->wp; P.omgp = h->omgp; P.rho0 = h->pp.rho0; P.fHIp = h->fHIp; P.torqp = h->torqp;
-        // the count is on the device: size the grid for the known count if the host has it, else for the capacity
-        const long long nthreads = h->nlink >= 0 ? h->nlink : h->maxlink;
-        const unsigned nb = (unsigned)((nthreads + 127) / 128);
-        if (nb > 0) {
-            switch (read_kind(h)) {
-            case READ_DIRECT: k_beads_ibb<READ_DIRECT><<<nb, 128, 0, h->sc>>>(P); break;
-            case READ_PULL_NAT: k_beads_ibb<READ_PULL_NAT><<<nb, 128, 0, h->sc>>>(P); break;
-            default: k_beads_ibb<READ_PULL_SWAP><<<nb, 128, 0, h->sc>>>(P); break;
-            }
-            CK(cudaGetLastError());
-            h->n_other_kernels++;
+        // the counts are on the device: one grid row per particle, wide enough for a full segment; the blocks beyond a
+        // segment's count leave at once
+        const dim3 nb((unsigned)((h->links.cap + 127) / 128), (unsigned)h->npart);
+        switch (read_kind(h)) {
+        case READ_DIRECT: k_beads_ibb<READ_DIRECT><<<nb, 128, 0, h->sc>>>(P); break;
+        case READ_PULL_NAT: k_beads_ibb<READ_PULL_NAT><<<nb, 128, 0, h->sc>>>(P); break;
+        default: k_beads_ibb<READ_PULL_SWAP><<<nb, 128, 0, h->sc>>>(P); break;
         }
+        CK(cudaGetLastError());
+        h->n_other_kernels++;
     }
     if (h->cfg.nranks > 1) {                                       // force reduction over the slabs
         NK(nccl_api().AllReduce(h->fHIp, h->fHIp, (size_t)6 * h->npart, NCCL_FLOAT64, NCCL_SUM, h->comm, h->sc));
@@ -1522,25 +1531,37 @@ extern "C" int d3q19_get_particles(d3q19_handle *h, double *ypglb, double *wp, d
     return check_link_overflow(h, "d3q19_get_particles");
 }
 
-// the link list of this slab in list order: global 1-based node coordinates, direction, particle, q
+// the link list of this slab, the particles' segments concatenated: global 1-based node coordinates, direction, particle, q
+// (inside a particle's segment the order depends on the run: sort before comparing)
 extern "C" int d3q19_get_links(d3q19_handle *h, int64_t capacity, int32_t *x, int32_t *y, int32_t *z, int32_t *ip,
                                int32_t *part, double *q, int64_t *nlink) {
     CK(cudaSetDevice(h->cfg.device));
     if (!h->part_on || !h->links_valid) return fail("d3q19_get_links: no valid link list");
-    RK_(fetch_nlink(h));
+    std::vector<unsigned long long> cnt;
+    RK_(fetch_link_counts(h, cnt, "d3q19_get_links"));
+    std::vector<long long> off((size_t)h->npart + 1, 0);
+    for (int p = 0; p < h->npart; ++p) off[p + 1] = off[p] + (long long)cnt[p];
+    h->nlink = off[h->npart];
     if (nlink) *nlink = h->nlink;
     if (capacity < h->nlink) return fail("d3q19_get_links: capacity %lld < %lld links", (long long)capacity, h->nlink);
     if (h->nlink == 0) return 0;
-    int32_t *tmp = nullptr;
-    const size_t nb = (size_t)h->nlink * sizeof(int32_t);
-    CK(cudaMalloc(&tmp, 3 * nb));
-    k_links_export<<<(unsigned)((h->nlink + 127) / 128), 128, 0, h->sc>>>(h->g, h->cfg.globalz, h->nlink, h->links, tmp,
-                                                                        tmp + h->nlink, tmp + 2 * h->nlink);
-    cudaError_t e = cudaGetLastError();
-    const void *src[6] = {tmp, tmp + h->nlink, tmp + 2 * h->nlink, h->links.dir, h->links.part, h->links.q};
-    void *dst[6] = {x, y, z, ip, part, q};
-    for (int i = 0; i < 6 && e == cudaSuccess; ++i)
-        e = cudaMemcpyAsync(dst[i], src[i], i < 5 ? nb : (size_t)h->nlink * sizeof(double), cudaMemcpyDeviceToHost, h->sc);
+    const size_t n = (size_t)h->nlink;
+    char *tmp = nullptr;
+    const size_t bytes = (size_t)(h->npart + 1) * sizeof(long long) + 5 * n * sizeof(int32_t) + n * sizeof(double) + 64;
+    CK(cudaMalloc(&tmp, bytes));
+    double *dq = reinterpret_cast<double *>(tmp);                                   // 8-byte items first
+    long long *doff = reinterpret_cast<long long *>(dq + n);
+    int32_t *di = reinterpret_cast<int32_t *>(doff + h->npart + 1);
+    cudaError_t e = cudaMemcpyAsync(doff, off.data(), (size_t)(h->npart + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->sc);
+    if (e == cudaSuccess) {
+        const dim3 gr((unsigned)((h->links.cap + 127) / 128), (unsigned)h->npart);
+        k_links_export<<<gr, 128, 0, h->sc>>>(part_geom(h), h->links, h->ypglb, doff, di, di + n, di + 2 * n, di + 3 * n, di + 4 * n, dq);
+        e = cudaGetLastError();
+    }
+    void *dst[5] = {x, y, z, ip, part};
+    for (int i = 0; i < 5 && e == cudaSuccess; ++i)
+        e = cudaMemcpyAsync(dst[i], di + (size_t)i * n, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->sc);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q, dq, n * sizeof(double), cudaMemcpyDeviceToHost, h->sc);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->sc);
     cudaFree(tmp);                      // also on the error paths
     if (e != cudaSuccess) return fail("d3q19_get_links: %s", cudaGetErrorString(e));

@@ -52,7 +52,9 @@ constexpr int BLOCK_X = D3Q_BLOCK_X;
 #ifndef D3Q_HINT
 #define D3Q_HINT 0
 #endif
-// 1: warps that hold no wall-adjacent node take accessors without the wall select (see Gather<>::load_nowall)
+// 1: in the in-place odd step, warps that hold no wall-adjacent node take accessors without the wall select (see
+// Gather<>::load_nowall; B200, 512x256x256, single launches: odd step 1.62 -> 1.55 ms.  The two-array step, whose
+// stores need no select anyway, gains nothing and loses 0.5 % under the power cap: profiles/r02c_variants.md)
 #ifndef D3Q_WALLSPLIT
 #define D3Q_WALLSPLIT 1
 #endif
@@ -365,28 +367,40 @@ k_step(const __grid_constant__ StepParams p) {
         double f[NPOP];
 #if D3Q_PF_LEAN
         if (SK != STEP_AB && p.pf_ahead > 0) {
-            // lane i < 19 asks for population i: the two 128-byte lines of this warp's 32 nodes, pf_ahead elements ahead
-            // (2 prefetch instructions per warp instead of 19 per line)
+            // lane i < 19 asks for direction i: the two 128-byte lines that the warp pf_ahead elements further down will
+            // READ for that direction (2 prefetch instructions per warp instead of 19 per line).  In the odd step that is
+            // slot opp(i) at the node shifted by -c_i: with the shift left out, the ten c_z != 0 directions would ask for
+            // lines that are read a whole z plane earlier or later -- harmless while a plane of all populations
+            // (lx*ly*152 B) fits L2 next to everything else, 25 % extra DRAM reads on 1024x1024 planes (configs[3]),
+            // where it does not (measured: odd step 1.93 ms vs 1.52 ms even, profiles/r02c_variants.jsonl).
             const int lane = threadIdx.x & 31;
-            const long long ahead = (long long)k.n - lane + p.pf_ahead;
-            if (lane < NPOP && ahead + 16 < g.slab) {      // stays inside the population
-                const double *q = p.A + (long long)lane * g.slab + ahead;
-                prefetch_l2(q);
-                prefetch_l2(q + 16);
+            if (lane < NPOP) {
+                const int slot = (RK == READ_PULL_SWAP) ? rt_opp(lane) : lane;
+                const long long delta = (RK == READ_DIRECT) ? 0
+                    : (long long)rt_cx(lane) + (long long)rt_cy(lane) * g.xp + (long long)rt_cz(lane) * g.plane;
+                const long long ahead = (long long)k.n - lane + p.pf_ahead - delta;
+                if (ahead >= 0 && ahead + 16 < g.slab) {      // stays inside the population
+                    const double *q = p.A + (long long)slot * g.slab + ahead;
+                    prefetch_l2(q);
+                    prefetch_l2(q + 16);
+                }
             }
         }
 #else
         if (SK != STEP_AB && p.pf_ahead > 0 && (threadIdx.x & 15) == 0) {
-            const long long ahead = (long long)k.n + p.pf_ahead;
-            if (ahead < g.slab) {          // stays inside the population (the last rows run into the upper ghost plane)
-#pragma unroll
-                for (int i = 0; i < NPOP; ++i) prefetch_l2(p.A + (long long)i * g.slab + ahead);
-            }
+            static_for<NPOP>([&](auto ic) {          // one lane per 128-byte line, all 19 directions (see the lean form)
+                constexpr int i = decltype(ic)::value;
+                constexpr int slot = (RK == READ_PULL_SWAP) ? dir_opp(i) : i;
+                const long long delta = (RK == READ_DIRECT) ? 0
+                    : (long long)dir_cx(i) + (long long)dir_cy(i) * g.xp + (long long)dir_cz(i) * g.plane;
+                const long long ahead = (long long)k.n + p.pf_ahead - delta;
+                if (ahead >= 0 && ahead < g.slab) prefetch_l2(p.A + (long long)slot * g.slab + ahead);
+            });
         }
 #endif
         // a warp covers 32 consecutive x: it touches a wall only if it holds x = 0 or x = lx-1 (warp-uniform)
         const int xw = x & ~31;
-        const bool wallwarp = !D3Q_WALLSPLIT || (RK != READ_DIRECT && (xw == 0 || xw + 31 >= g.lx - 1));
+        const bool wallwarp = !(D3Q_WALLSPLIT && SK == STEP_AA_ODD) || xw == 0 || xw + 31 >= g.lx - 1;
         if (wallwarp) gather19<RK>(p.A, g, k, f);
         else gather19_nowall<RK>(p.A, g, k, f);
 

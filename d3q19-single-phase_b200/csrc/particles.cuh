@@ -23,25 +23,6 @@
 
 namespace d3q {
 
-// Lattice tables for kernels that index directions at run time (one link = one thread, every lane another
-// direction): two bits per direction packed into a 64-bit literal and decoded in registers.  (A __constant__ array
-// indexed by a per-lane direction serialises the constant cache: 18-way in k_beads_ibb, 150 us for 10^6 links.)
-__host__ __device__ constexpr unsigned long long pack_dirs(int which) {
-    unsigned long long v = 0;
-    for (int i = 0; i < NPOP; ++i) {
-        const int c = which == 0 ? dir_cx(i) : (which == 1 ? dir_cy(i) : dir_cz(i));
-        v |= (unsigned long long)(c + 1) << (2 * i);
-    }
-    return v;
-}
-__device__ __forceinline__ int rt_cx(int i) { return (int)((pack_dirs(0) >> (2 * i)) & 3ull) - 1; }
-__device__ __forceinline__ int rt_cy(int i) { return (int)((pack_dirs(1) >> (2 * i)) & 3ull) - 1; }
-__device__ __forceinline__ int rt_cz(int i) { return (int)((pack_dirs(2) >> (2 * i)) & 3ull) - 1; }
-// ipopp (para.f90:204-206): (1,2)(3,4)(5,6) swap inside the pair, 7..10 -> 17-i, 11..14 -> 25-i, 15..18 -> 33-i
-__device__ __forceinline__ int rt_opp(int i) {
-    return i == 0 ? 0 : (i <= 6 ? ((i & 1) ? i + 1 : i - 1) : (i <= 10 ? 17 - i : (i <= 14 ? 25 - i : 33 - i)));
-}
-
 struct PartGeom {
     Geom g;
     int nx, ny, nz, globalz;
@@ -197,16 +178,20 @@ __global__ void __launch_bounds__(32 * PART_WARPS) k_beads_cover(PartGeom pg, in
 }
 
 // ---- beads_links, part 2: boundary links ------------------------------------------------------------
-// A link = (fluid node of this slab, direction whose neighbour is owned by particle p).  The list is a SET: warps
-// append their row's links with one atomic per 32 nodes, so the order between rows depends on the run; inside a row it
-// is x, then direction.  Consumers (k_beads_ibb: one thread per link, every link writes its own slot and adds to
-// the particle's force with atomics) do not depend on the order; d3q19_get_links hands the list out as it lies and
-// tests compare after a canonical sort ("bit-exact after a canonical sort").
+// A link = (fluid node of this slab, direction whose neighbour is owned by particle p).  Every particle has its own
+// SEGMENT of `cap` entries in the list and its own counter: warps append their row's links with one atomic per 32
+// nodes, so inside a segment the order between rows depends on the run (inside a row it is x, then direction) -- the
+// list is a set.  Consumers do not depend on the order (k_beads_ibb: one thread per link, every link writes its own
+// slot; all links of a block belong to one particle, so the force is reduced per warp before it is added);
+// d3q19_get_links hands the segments out concatenated and tests compare after a canonical sort (SURVEY.md appendix B:
+// "bit-exact after a canonical sort").  The fraction q of a link is NOT stored: it is one square root and one division,
+// cheaper to recompute per link by whoever needs it (without divergence) than to evaluate inside the sweep, where a
+// warp would run all 18 directions' roots for the union of its lanes' links (measured: 256 us of a 2.7 ms step).
 struct Links {
-    uint32_t *node;      // ghosted in-slab index of the fluid node
-    int32_t *dir;        // direction pointing into the solid
-    int32_t *part;       // particle id, 1-based
-    double *q;           // fraction of the link on the fluid side, (0,1]
+    uint32_t *node;            // ghosted in-slab index of the fluid node, [npart][cap]
+    int32_t *dir;              // direction pointing into the solid
+    unsigned long long *count; // links of particle p on this slab (may exceed cap: the excess was dropped -> error)
+    long long cap;             // entries per particle
 };
 
 // owner of the neighbour of (jx,jy,zg) along direction IP, or -2 beyond a channel wall
@@ -237,8 +222,33 @@ __device__ __forceinline__ double link_q(const double *c, int jx, int jy, int jz
     return q;
 }
 
-__global__ void __launch_bounds__(32 * PART_WARPS) k_beads_links(PartGeom pg, int npart, const double *ypglb, const int32_t *own,
-                                                                 unsigned long long *nlink, long long maxlink, Links L) {
+// the same for a run-time direction (one thread per link) and the coordinates of a link node as the sweep over the
+// particle's box saw them (jy, jz unwrapped next to the centre): what k_beads_ibb and the export use
+__device__ __forceinline__ double link_q_rt(const double *c, int jx, int jy, int jz, double r2, int ip) {
+    const int cx = rt_cx(ip), cy = rt_cy(ip), cz = rt_cz(ip);
+    const R dx = R((double)jx - 0.5) - R(c[0]), dy = R((double)jy - 0.5) - R(c[1]), dz = R((double)jz - 0.5) - R(c[2]);
+    const R a((double)(cx * cx + cy * cy + cz * cz));
+    const R b = R(2.0) * (R((double)cx) * dx + R((double)cy) * dy + R((double)cz) * dz);
+    const R cc = dx * dx + dy * dy + dz * dz - R(r2);
+    double disc = (b * b - R(4.0) * a * cc).v;
+    if (disc < 0.0) disc = 0.0;
+    double q = __ddiv_rn((-b - R(__dsqrt_rn(disc))).v, (R(2.0) * a).v);
+    if (q < 0.0) q = 0.0;
+    if (q > 1.0) q = 1.0;
+    return q;
+}
+// (jx, jy, jz) of the node with ghosted in-slab index n, unwrapped into particle p's box
+__device__ __forceinline__ void link_node_coords(const PartGeom &pg, const double *c, uint32_t n, int &jx, int &jy, int &jz) {
+    const Geom &g = pg.g;
+    const int x = (int)(n % (uint32_t)g.xp), y = (int)((n / (uint32_t)g.xp) % (uint32_t)g.ly), zg = (int)(n / ((uint32_t)g.xp * (uint32_t)g.ly));
+    const BBox b = part_bbox(pg, c);
+    int ry = (y + 1 - b.lo[1]) % pg.ny, rz = (zg + pg.globalz - b.lo[2]) % pg.nz;
+    if (ry < 0) ry += pg.ny;
+    if (rz < 0) rz += pg.nz;
+    jx = x + 1; jy = b.lo[1] + ry; jz = b.lo[2] + rz;
+}
+
+__global__ void __launch_bounds__(32 * PART_WARPS) k_beads_links(PartGeom pg, int npart, const double *ypglb, const int32_t *own, Links L) {
     const int p = blockIdx.x, lane = threadIdx.x & 31;
     const double *c = ypglb + 3 * p;
     const BBox b = part_bbox(pg, c);
@@ -282,20 +292,13 @@ __global__ void __launch_bounds__(32 * PART_WARPS) k_beads_links(PartGeom pg, in
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         if (total == 0) continue;
         unsigned long long base = 0;
-        if (lane == 31) base = atomicAdd(nlink, (unsigned long long)total);
+        if (lane == 31) base = atomicAdd(L.count + p, (unsigned long long)total);
         base = __shfl_sync(0xffffffffu, base, 31);
         long long w = (long long)base + incl - cnt;
-        if (bits) {
-            static_for<NPOP - 1>([&](auto ic) {
-                constexpr int ip = decltype(ic)::value + 1;
-                if (bits & (1u << (ip - 1))) {
-                    if (w < maxlink) {
-                        L.node[w] = (uint32_t)n; L.dir[w] = ip; L.part[w] = p + 1;
-                        L.q[w] = link_q<ip>(c, jx, jy, jz, r2);
-                    }
-                    ++w;
-                }
-            });
+        const long long seg = (long long)p * L.cap;
+        for (unsigned rest = bits; rest; rest &= rest - 1) {           // the set bits, lowest direction first
+            if (w < L.cap) { L.node[seg + w] = (uint32_t)n; L.dir[seg + w] = __ffs(rest); }
+            ++w;
         }
     }
 }
@@ -310,9 +313,7 @@ struct IbbParams {
     PartGeom pg;
     double *S;
     const int32_t *own;
-    Links L;
-    const unsigned long long *nlink_dev;   // the count k_beads_links left on the device: no host round trip between links and IBB
-    long long maxlink;
+    Links L;                  // the counts stay on the device: no host round trip between links and IBB
     const double *ypglb, *wp, *omgp;
     double rho0;
     double *fHIp, *torqp;     // (3,npart), accumulated with atomics
@@ -329,16 +330,21 @@ __device__ __forceinline__ long long post_addr(const Geom &g, int i, long long n
 template <int RK>
 __global__ void __launch_bounds__(128) k_beads_ibb(const __grid_constant__ IbbParams P) {
     const Geom &g = P.pg.g;
+    // grid (blocks of a segment, npart): all links of a block belong to particle blockIdx.y
+    const int p = blockIdx.y;
     const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double F[6] = {0, 0, 0, 0, 0, 0};
-    int part = 0;
-    const long long nlink = (long long)*P.nlink_dev < P.maxlink ? (long long)*P.nlink_dev : P.maxlink;
+    const long long nlink = (long long)P.L.count[p] < P.L.cap ? (long long)P.L.count[p] : P.L.cap;
+    if ((long long)blockIdx.x * blockDim.x >= nlink) return;          // whole block beyond the segment's end
     if (l < nlink) {
-        const uint32_t n = P.L.node[l];
-        const int ip = P.L.dir[l], io = rt_opp(ip);
-        part = P.L.part[l];
-        const int p = part - 1;
-        const double q = P.L.q[l];
+        const uint32_t n = P.L.node[(long long)p * P.L.cap + l];
+        const int ip = P.L.dir[(long long)p * P.L.cap + l], io = rt_opp(ip);
+        double q;
+        {
+            int jx, jy, jz;
+            link_node_coords(P.pg, P.ypglb + 3 * p, n, jx, jy, jz);
+            q = link_q_rt(P.ypglb + 3 * p, jx, jy, jz, (R(P.pg.rad) * R(P.pg.rad)).v, ip);
+        }
         const int x = (int)(n % (uint32_t)g.xp), y = (int)((n / (uint32_t)g.xp) % (uint32_t)g.ly),
                   zg = (int)(n / ((uint32_t)g.xp * (uint32_t)g.ly));
         const int cx = rt_cx(ip), cy = rt_cy(ip), cz = rt_cz(ip);
@@ -389,26 +395,18 @@ __global__ void __launch_bounds__(128) k_beads_ibb(const __grid_constant__ IbbPa
         F[4] = rz * F[0] - rx * F[2];
         F[5] = rx * F[1] - ry * F[0];
     }
-    // links are ordered by particle: a warp usually serves one particle -> one atomic per component per warp
+    // one particle per block: reduce over the warp, one atomic per component per warp
     const unsigned full = 0xffffffffu;
-    const int p0 = __shfl_sync(full, part, 0);
-    const bool uniform = __all_sync(full, part == p0 || part == 0);
-    if (uniform) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            double v = F[k];
+    for (int k = 0; k < 6; ++k) {
+        double v = F[k];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
-            F[k] = v;
-        }
-        const int pw = __reduce_max_sync(full, part);
-        if ((threadIdx.x & 31) == 0 && pw > 0) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+        F[k] = v;
+    }
+    if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { atomicAdd(P.fHIp + 3 * (pw - 1) + k, F[k]); atomicAdd(P.torqp + 3 * (pw - 1) + k, F[3 + k]); }
-        }
-    } else if (part > 0) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { atomicAdd(P.fHIp + 3 * (part - 1) + k, F[k]); atomicAdd(P.torqp + 3 * (part - 1) + k, F[3 + k]); }
+        for (int k = 0; k < 3; ++k) { atomicAdd(P.fHIp + 3 * p + k, F[k]); atomicAdd(P.torqp + 3 * p + k, F[3 + k]); }
     }
 }
 
@@ -611,14 +609,25 @@ __global__ void __launch_bounds__(1024) k_beads_lubmove(PartGeom pg, int npart, 
         for (int p = threadIdx.x; p < npart; p += blockDim.x) move_one(pg, M, p);
 }
 
-// link list -> host-friendly (global 1-based node coordinates)
-__global__ void k_links_export(Geom g, int globalz, long long nlink, Links L, int32_t *ox, int32_t *oy, int32_t *oz) {
+// link list -> host-friendly, segments concatenated: global 1-based node coordinates, direction, particle, q;
+// grid (blocks of a segment, npart), offset[p] = where particle p's links start in the output
+__global__ void k_links_export(PartGeom pg, Links L, const double *ypglb, const long long *offset, int32_t *ox, int32_t *oy, int32_t *oz,
+                               int32_t *odir, int32_t *opart, double *oq) {
+    const Geom &g = pg.g;
+    const int p = blockIdx.y;
     const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nlink = (long long)L.count[p] < L.cap ? (long long)L.count[p] : L.cap;
     if (l >= nlink) return;
-    const uint32_t n = L.node[l];
-    ox[l] = (int)(n % (uint32_t)g.xp) + 1;
-    oy[l] = (int)((n / (uint32_t)g.xp) % (uint32_t)g.ly) + 1;
-    oz[l] = (int)(n / ((uint32_t)g.xp * (uint32_t)g.ly)) + globalz;
+    const uint32_t n = L.node[(long long)p * L.cap + l];
+    const int ip = L.dir[(long long)p * L.cap + l];
+    const long long o = offset[p] + l;
+    ox[o] = (int)(n % (uint32_t)g.xp) + 1;
+    oy[o] = (int)((n / (uint32_t)g.xp) % (uint32_t)g.ly) + 1;
+    oz[o] = (int)(n / ((uint32_t)g.xp * (uint32_t)g.ly)) + pg.globalz;
+    odir[o] = ip; opart[o] = p + 1;
+    int jx, jy, jz;
+    link_node_coords(pg, ypglb + 3 * p, n, jx, jy, jz);
+    oq[o] = link_q_rt(ypglb + 3 * p, jx, jy, jz, (R(pg.rad) * R(pg.rad)).v, ip);
 }
 
 }  // namespace d3q

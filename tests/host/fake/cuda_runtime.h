@@ -140,6 +140,7 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int o) {
 struct alignas(16) double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __all_sync(unsigned, int pred) {
     int all = 1;
     for (int l = 0; l < 32; ++l) all &= hs::warp_exchange(pred ? 1 : 0, l);      // 32 rounds: simple, and only in tests

@@ -44,8 +44,8 @@ struct Rank {
     std::vector<int32_t> own;
     std::vector<double> ypglb, ypmask, wp, omgp, fHIp, torqp, flubp, forcepp, torqpp, thetap;
     std::vector<uint32_t> lnode;
-    std::vector<int32_t> ldir, lpart;
-    std::vector<double> lq;
+    std::vector<int32_t> ldir;
+    std::vector<unsigned long long> lcount;
     std::vector<uint32_t> fnode; std::vector<int32_t> fpart;      // refill list
     unsigned long long pcnt[4] = {0, 0, 0, 0};
     std::vector<double> fill_send_up, fill_send_dn, fill_ghost_lo, fill_ghost_hi;      // 19 x plane each
@@ -68,7 +68,7 @@ struct Sim {
     int npart = 0;
     double rad = 0, rho0 = 1, amp = 0, aip = 0, gforce[3] = {0, 0, 0};
     LubParams lub = {0, 0, 0, 0, 0, 0, 0};
-    long long maxlink = 0;
+    long long maxlink = 0, linkcap = 0;
     std::vector<Rank> r;
 };
 
@@ -321,7 +321,7 @@ PartGeom part_geom(const Sim &s, const Rank &q) {
     return pg;
 }
 
-Links links_of(Rank &q) { return Links{q.lnode.data(), q.ldir.data(), q.lpart.data(), q.lq.data()}; }
+Links links_of(const Sim &s, Rank &q) { return Links{q.lnode.data(), q.ldir.data(), q.lcount.data(), s.linkcap}; }
 
 static inline dim3 sweep_grid(const Sim &s) {
     return dim3((unsigned)s.npart, (unsigned)((part_max_rows(s.rad) + PART_WARPS - 1) / PART_WARPS));
@@ -333,15 +333,17 @@ void beads_links(Sim &s) {
     for (Rank &q : s.r) {
         const PartGeom pg = part_geom(s, q);
         const dim3 gs = sweep_grid(s);
-        q.pcnt[0] = q.pcnt[1] = 0;
+        q.pcnt[1] = 0;
+        std::fill(q.lcount.begin(), q.lcount.end(), 0ull);
         if (s.mask_built)
             hs_launch(gs, 32 * PART_WARPS, k_beads_uncover, pg, s.npart, (const double *)q.ypmask.data(), (const double *)q.ypglb.data(),
                       q.own.data(), fill_of(q, s.maxlink));
         hs_launch(gs, 32 * PART_WARPS, k_beads_cover, pg, s.npart, (const double *)q.ypglb.data(), q.own.data());
         q.ypmask = q.ypglb;
         hs_launch_coop(gs, 32 * PART_WARPS, k_beads_links, pg, s.npart, (const double *)q.ypglb.data(), (const int32_t *)q.own.data(),
-                       &q.pcnt[0], s.maxlink, links_of(q));
-        if ((long long)q.pcnt[0] > s.maxlink) hs::trap("more links than maxlink");
+                       links_of(s, q));
+        for (int p = 0; p < s.npart; ++p)
+            if ((long long)q.lcount[p] > s.linkcap) hs::trap("more links than a particle's segment holds");
     }
     s.mask_built = true;
     s.links_valid = true;
@@ -350,14 +352,13 @@ void beads_links(Sim &s) {
 template <int RK>
 void ibb_rank(Sim &s, Rank &q) {
     IbbParams P;
-    P.pg = part_geom(s, q); P.S = q.A; P.own = q.own.data(); P.L = links_of(q);
-    P.nlink_dev = &q.pcnt[0]; P.maxlink = s.maxlink;
+    P.pg = part_geom(s, q); P.S = q.A; P.own = q.own.data(); P.L = links_of(s, q);
     P.ypglb = q.ypglb.data(); P.wp = q.wp.data(); P.omgp = q.omgp.data(); P.rho0 = s.rho0;
     P.fHIp = q.fHIp.data(); P.torqp = q.torqp.data();
-    // like the device path when the host does not know the count: threads for a multiple of the capacity's blocks;
-    // here the count is at hand, rounded up so that whole idle warps exist too
-    const long long nthreads = (long long)*P.nlink_dev + 200;
-    hs_launch_coop(dim3((unsigned)((nthreads + 127) / 128)), 128, k_beads_ibb<RK>, P);
+    // like the device path: one grid row per particle, wide enough for the longest segment in use plus idle blocks
+    unsigned long long longest = 0;
+    for (int p = 0; p < s.npart; ++p) longest = q.lcount[p] > longest ? q.lcount[p] : longest;
+    hs_launch_coop(dim3((unsigned)((longest + 300 + 127) / 128), (unsigned)s.npart), 128, k_beads_ibb<RK>, P);
 }
 void beads_collision(Sim &s) {
     for (Rank &q : s.r) {
@@ -739,7 +740,8 @@ void hs_particles_init(void *h, int npart, double rad, double rho0, double rhopa
     s.lub = LubParams{lub7[0], lub7[1], lub7[2], lub7[3], lub7[4], lub7[5], lub7[6]};
     for (int d = 0; d < 3; ++d) s.gforce[d] = gforce[d];
     const double pi = 4.0 * std::atan(1.0);
-    s.maxlink = (long long)(8.0 * npart * 4.0 * pi * (rad + 1.0) * (rad + 1.0)) + 64;
+    s.linkcap = (long long)(8.0 * 4.0 * pi * (rad + 1.0) * (rad + 1.0)) + 64;
+    s.maxlink = s.linkcap * npart;
     const double volp = 4.0 / 3.0 * pi * rad * rad * rad;
     s.amp = rhopart * volp;
     s.aip = 0.4 * s.amp * rad * rad;
@@ -751,7 +753,7 @@ void hs_particles_init(void *h, int npart, double rad, double rho0, double rhopa
         q.ypglb.assign(ypglb, ypglb + tb); q.ypmask = q.ypglb;
         q.wp.assign(wp, wp + tb); q.omgp.assign(omgp, omgp + tb);
         for (std::vector<double> *v : {&q.fHIp, &q.torqp, &q.flubp, &q.forcepp, &q.torqpp, &q.thetap}) v->assign(tb, 0.0);
-        q.lnode.assign(s.maxlink, 0u); q.ldir.assign(s.maxlink, 0); q.lpart.assign(s.maxlink, 0); q.lq.assign(s.maxlink, 0.0);
+        q.lnode.assign(s.maxlink, 0u); q.ldir.assign(s.maxlink, 0); q.lcount.assign(npart, 0ull);
         q.fnode.assign(s.maxlink, 0u); q.fpart.assign(s.maxlink, 0);
     }
 }
@@ -760,7 +762,8 @@ long long hs_beads_links(void *h) {
     Sim &s = *(Sim *)h;
     beads_links(s);
     long long n = 0;
-    for (Rank &q : s.r) n += (long long)q.pcnt[0];
+    for (Rank &q : s.r)
+        for (int p = 0; p < s.npart; ++p) n += (long long)q.lcount[p];
     return n;
 }
 
@@ -793,13 +796,12 @@ void hs_get_mask(void *h, int32_t *own) {
 long long hs_get_links(void *h, int k, int32_t *x, int32_t *y, int32_t *z, int32_t *ip, int32_t *part, double *qv) {
     Sim &s = *(Sim *)h;
     Rank &q = s.r[k];
-    const long long n = (long long)q.pcnt[0];
-    if (n > 0 && x) {
-        hs_launch(dim3((unsigned)((n + 127) / 128)), 128, k_links_export, q.g, q.globalz, n, links_of(q), x, y, z);
-        std::memcpy(ip, q.ldir.data(), n * sizeof(int32_t));
-        std::memcpy(part, q.lpart.data(), n * sizeof(int32_t));
-        std::memcpy(qv, q.lq.data(), n * sizeof(double));
-    }
+    std::vector<long long> off((size_t)s.npart + 1, 0);
+    for (int p = 0; p < s.npart; ++p) off[p + 1] = off[p] + (long long)q.lcount[p];
+    const long long n = off[s.npart];
+    if (n > 0 && x)
+        hs_launch(dim3((unsigned)((s.linkcap + 127) / 128), (unsigned)s.npart), 128, k_links_export, part_geom(s, q), links_of(s, q),
+                  (const double *)q.ypglb.data(), (const long long *)off.data(), x, y, z, ip, part, qv);
     return n;
 }
 

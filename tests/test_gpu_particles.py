@@ -136,3 +136,38 @@ def test_momentum_exchange_balances_fluid_momentum():
     assert impulse < 0
     assert abs(py + impulse) < 0.1 * abs(impulse)          # walls are far: little momentum has reached them
     sim.close(); w.close()
+
+
+@pytest.mark.slow
+def test_stokes_drag_between_two_walls_matches_faxen():
+    """LITERATURE ANCHOR for the parity-unpinned particle path (interpolated bounce-back + momentum exchange): a sphere
+    translating parallel to two plane walls, midway between them, in creeping flow.  Faxen's result (Happel & Brenner,
+    Low Reynolds Number Hydrodynamics, eq. 7-4.27):
+
+        F = 6 pi mu a U / (1 - 1.004 k + 0.418 k^3 + 0.21 k^4 - 0.169 k^5),   k = a / h,  h = distance centre - wall.
+
+    The channel is that geometry (half-way bounce-back walls at x = 0 and x = nx), periodic in y and z with a cell of two
+    gap widths (by the square lattice's symmetry the leading image interaction cancels).  Creeping flow is quasi-steady:
+    the sphere keeps its place and carries its velocity in the moving-wall term, the force is read once it has settled.
+    Tolerance 5 %: a staircase sphere of radius 6 has a hydrodynamic radius within ~2 % of the nominal one."""
+    nx, ny, nz, a, U = 96, 192, 192, 6.0, 1e-3
+    visc = 1.0 / 6.0                                          # tau = 1
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=True, scheme=capi.SCHEME_AB, ipart=True, allocate_host=False, visc=visc)
+    sim.set_force_uniform(0.0, 0.0, 0.0)
+    sim.init_channel_device(A9=0.0, noise_amp=0.0)           # laminar set: fluid at rest
+    sim.particles_init([[nx / 2.0, ny / 2.0, nz / 2.0]], a, [[0.0, U, 0.0]], [[0.0, 0.0, 0.0]])
+    hist = []
+    for blk in range(12):
+        for _ in range(2500):
+            sim.particle_step(move=False)
+        hist.append(float(sim.get_particles()["fHIp"][0, 1]))
+        if blk >= 4 and abs(hist[-1] - hist[-2]) < 2e-4 * abs(hist[-1]):
+            break
+    f = sim.get_particles()["fHIp"][0]
+    k = a / (nx / 2.0)
+    faxen = 6.0 * np.pi * visc * a * U / (1.0 - 1.004 * k + 0.418 * k ** 3 + 0.21 * k ** 4 - 0.169 * k ** 5)
+    print("drag %.6e, Faxen %.6e, ratio %.4f, history %s" % (-f[1], faxen, -f[1] / faxen, ["%.4e" % h for h in hist]))
+    assert abs(hist[-1] - hist[-2]) < 1e-3 * abs(hist[-1]), hist          # settled
+    assert abs(f[0]) < 1e-3 * abs(f[1]) and abs(f[2]) < 1e-3 * abs(f[1])   # by symmetry
+    assert abs(-f[1] / faxen - 1.0) < 0.05, (-f[1], faxen)
+    sim.close()

@@ -14,12 +14,13 @@ pkg = entry.load_package()
 capi = pkg.capi
 nx, ny, nz = (int(t) for t in (sys.argv[1] if len(sys.argv) > 1 else "512x256x256").split("x"))
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+pf = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # d3q19_config.pf_blocks (0 = default 128, < 0 off)
 rng = np.random.default_rng(0)
 f0 = (1e-3 * rng.random((nz, ny, nx, 19))).astype(np.float64)
-out = {"lib": os.path.basename(capi.LIB_PATH), "size": [nx, ny, nz]}
+out = {"lib": os.path.basename(capi.LIB_PATH), "size": [nx, ny, nz], "pf_blocks": pf}
 nodes = nx * ny * nz
 for name, scheme in (("aa", capi.SCHEME_AA), ("ab", capi.SCHEME_AB)):
-    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, allocate_host=False)
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, allocate_host=False, pf_blocks=pf)
     sim.set_force_uniform(0.0, 1e-6, 0.0)
     sim.upload_f(f0)
     sim.run_device(6)
