@@ -62,6 +62,9 @@ def parse_args():
                          "involved); peer = stores into the neighbour's memory inside the step kernel")
     ap.add_argument("--nccl-max-ctas", type=int, default=0,
                     help="d3q19_config.nccl_max_ctas: CTAs NCCL may use for the face send/recv (0 = the library's default, 4)")
+    ap.add_argument("--halo-split-min", type=int, default=0,
+                    help="d3q19_config.halo_split_min: peer-memory transports run slabs at least this thick as boundary + interior "
+                         "launches, thinner ones as one launch (0 = the library's default, 64)")
     ap.add_argument("--cpu-steps", type=int, default=20,
                     help="timed steps of the CPU arm (20 steps of 512x256x256 = about 10 s on 16 cores)")
     ap.add_argument("--particles", type=int, default=0,
@@ -433,7 +436,7 @@ def main():
         """the channel on this rank's slab with its synthetic initial state; returns (sim, halo actually in use)"""
         sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local_rank, scheme=scheme,
                               math_mode=math_mode, nccl_id=nccl_id, overlap=not args.no_overlap, allocate_host=False,
-                              nccl_max_ctas=args.nccl_max_ctas, ipart=args.particles > 0)
+                              nccl_max_ctas=args.nccl_max_ctas, halo_split_min=args.halo_split_min, ipart=args.particles > 0)
         halo = "none"
         if world > 1:
             halo = "nccl"

@@ -832,23 +832,25 @@ static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int 
 // the interior the plain one (which needs fewer registers -- the AA odd step keeps its 4 CTAs/SM); the
 // order of the two launches is free, no node of one reads or writes an address the other writes.
 template <int SK, bool STRICT, bool GENERIC>
-static int launch_step_halo(d3q19_handle *h, const StepParams &p0) {
+static int launch_step_halo(d3q19_handle *h, const StepParams &p0, bool remote = true) {
     StepParams p = p0;
     Halo &q = p.halo;
     const bool ab = SK == STEP_AB;
     // AB: this step writes B here and in the neighbours; AA: the single array
-    q.peer_dn = ab ? h->peer_B[0] : h->peer_A[0];
-    q.peer_up = ab ? h->peer_B[1] : h->peer_A[1];
+    // (remote = false: copy-engine transport -- no stores into the neighbours, the plane counters raise two LOCAL words
+    //  that the copy stream waits for)
+    q.peer_dn = !remote ? nullptr : (ab ? h->peer_B[0] : h->peer_A[0]);
+    q.peer_up = !remote ? nullptr : (ab ? h->peer_B[1] : h->peer_A[1]);
     q.slab_dn = h->peer_slab[0]; q.slab_up = h->peer_slab[1];
     q.lz_dn = h->peer_lz[0];
     q.wait_lo = h->halo_flags; q.wait_hi = h->halo_flags + 1;
-    q.sig_dn = h->peer_flags[0] + 1;      // the lower neighbour's wait_hi
-    q.sig_up = h->peer_flags[1];          // the upper neighbour's wait_lo
+    q.sig_dn = remote ? h->peer_flags[0] + 1 : h->halo_flags + 4;      // the lower neighbour's wait_hi / "my plane 1 is done"
+    q.sig_up = remote ? h->peer_flags[1] : h->halo_flags + 5;          // the upper neighbour's wait_lo / "my plane lz is done"
     q.ctr = h->halo_flags + 2;
     q.err = h->halo_flags + 8;
     q.timeout_ns = h->halo_timeout_ns;
-    q.epoch = ++h->halo_epoch;
-    const bool split = h->g.lz >= h->halo_split_min && h->g.lz > 2;
+    q.epoch = remote ? ++h->halo_epoch : h->halo_epoch;      // (the caller advanced the epoch)
+    const bool split = remote && h->g.lz >= h->halo_split_min && h->g.lz > 2;
     const dim3 gr = grid_nodes(h, split ? 2 : h->g.lz);
     q.nblk_face = gr.x * gr.y;
     if (h->idx32) k_step<SK, STRICT, GENERIC, uint32_t, true><<<gr, BLOCK_X, 0, h->sc>>>(p);
@@ -856,7 +858,7 @@ static int launch_step_halo(d3q19_handle *h, const StepParams &p0) {
     CK(cudaGetLastError());
     h->n_step_kernels++;
     if (split) RK_((launch_step_range<SK, STRICT, GENERIC>(h, p0, 2, h->g.lz - 2, h->sc)));
-    if (ab) {                             // the neighbours swap their arrays in lockstep
+    if (ab && remote) {                   // the neighbours swap their arrays in lockstep
         for (int d = 0; d < 2; ++d) { double *t = h->peer_A[d]; h->peer_A[d] = h->peer_B[d]; h->peer_B[d] = t; }
     }
     return 0;
@@ -878,7 +880,17 @@ static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written
         CK(cudaGetLastError());
     }
     trace_mark(h, 0, h->sc);
-    if (lz > 2) {
+    // Thin slabs (lz < halo_split_min): ONE launch for the whole slab with the two boundary planes first in block order;
+    // their last blocks raise two local words and the copy stream, waiting for them in a one-thread kernel, starts the
+    // transfers while the interior blocks of the same launch are still running -- no drain and refill of the GPU around a
+    // 2-plane launch (measured on 32-plane slabs: the separate boundary launch takes 19 us for 12 us of work).  Thick slabs
+    // keep two launches: the plain instantiation needs fewer registers (in-place odd step: 4 instead of 3 CTAs/SM).
+    const bool single = lz > 2 && lz < h->halo_split_min && !GENERIC;
+    if (single) {
+        CK(cudaEventRecord(h->evB, h->sc));                        // sx may start waiting once the step is enqueued behind this
+        trace_mark(h, 1, h->sc);
+        RK_((launch_step_halo<SK, STRICT, GENERIC>(h, p, false)));
+    } else if (lz > 2) {
         RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 2, h->sc, lz - 1)));   // planes 1 and lz in one launch
         CK(cudaEventRecord(h->evB, h->sc));
         trace_mark(h, 1, h->sc);
@@ -890,6 +902,11 @@ static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written
     }
     trace_mark(h, 2, h->sc);
     CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
+    if (single) {                                                   // the boundary planes of THIS launch are complete
+        k_halo_wait<<<1, 1, 0, h->sx>>>(h->halo_flags + 4, h->halo_flags + 5, epoch, h->halo_flags + 8, h->halo_timeout_ns);
+        CK(cudaGetLastError());
+        h->n_other_kernels++;
+    }
     // The faces travel by the COPY ENGINES: one population of one z plane is plane = xp*ly contiguous doubles, so each
     // of the five crossing populations goes from where it lies in my array to where it belongs in the neighbour's
     // (cudaIpc-mapped) array with one device-to-device copy over NVLink -- no SM takes part, nothing competes with the
@@ -1427,7 +1444,7 @@ static int lubmove(d3q19_handle *h, int do_lub, int do_move) {
     LubParams lp = {h->pp.mingap, h->pp.mingap_w, h->pp.stf0, h->pp.stf1, h->pp.stf0_w, h->pp.stf1_w, h->pp.fscale};
     MoveParams M = {h->amp, h->aip, h->pp.gforce[0], h->pp.gforce[1], h->pp.gforce[2], h->fHIp, h->torqp, h->flubp,
                     h->forcepp, h->torqpp, h->ypglb, h->wp, h->omgp, h->thetap};
-    const int nt = h->npart < 1024 ? ((h->npart + 31) / 32) * 32 : 1024;
+    const int nt = h->npart < 32 ? h->npart * 32 : 1024;          // a warp per particle for the partner loop
     k_beads_lubmove<<<1, nt, 0, h->sc>>>(part_geom(h), h->npart, h->ypglb, lp, h->flubp, M, do_lub, do_move);
     CK(cudaGetLastError());
     h->n_other_kernels++;
@@ -1483,9 +1500,8 @@ extern "C" int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled) {
         h->n_nccl += 4;
         P.ghost_lo = ghost_lo; P.ghost_hi = ghost_hi;
     }
-    // the list length is on the device: a grid for a generous share of the capacity, the threads beyond the list leave at once
-    // (one move uncovers a thin layer: far fewer nodes than there are links)
-    const unsigned nb = (unsigned)((h->fill.cap + 127) / 128);
+    // the list length is on the device: a fixed grid strides over it (one move uncovers a thin layer: a few dozen nodes per particle)
+    const unsigned nb = (unsigned)(h->fill.cap < 148 * 8 * 128 ? (h->fill.cap + 127) / 128 : 148 * 8);
     switch (read_kind(h)) {
     case READ_DIRECT: k_beads_fill<READ_DIRECT><<<nb, 128, 0, h->sc>>>(P); break;
     case READ_PULL_NAT: k_beads_fill<READ_PULL_NAT><<<nb, 128, 0, h->sc>>>(P); break;

@@ -52,12 +52,9 @@ constexpr int BLOCK_X = D3Q_BLOCK_X;
 #ifndef D3Q_HINT
 #define D3Q_HINT 0
 #endif
-// 1: in the in-place odd step, warps that hold no wall-adjacent node take accessors without the wall select (see
-// Gather<>::load_nowall; B200, 512x256x256, single launches: odd step 1.62 -> 1.55 ms.  The two-array step, whose
-// stores need no select anyway, gains nothing and loses 0.5 % under the power cap: profiles/r02c_variants.md)
-#ifndef D3Q_WALLSPLIT
-#define D3Q_WALLSPLIT 1
-#endif
+// (Round 2 also tried accessors without the wall select for warps that hold no wall-adjacent node: 776 -> ~560 executed
+//  instructions per node in the in-place odd step, +4 % while that step's prefetch was mis-aimed, -1 % once it was fixed
+//  -- 128 registers with a spill against 124 without; removed.  profiles/r02c_variants.md, r02d_variants.md)
 // 1: the in-place steps' L2 prefetch is issued by lane i for population i (2 instructions per warp), 0: by one lane per
 // 128-byte line for all 19 populations
 #ifndef D3Q_PF_LEAN
@@ -237,18 +234,6 @@ struct Gather {
         if (!can_bounce) return reg;
         return at_wall(k) ? (long long)slot_wall * g.slab + (long long)k.n : reg;
     }
-    // warps none of whose nodes sits next to a wall (all but the first and the last warp of an x-row): the population
-    // base A + slot*slab is warp-uniform and the element offset is one of the nine row bases minus a literal c_x, so
-    // an access costs no select and no per-thread 64-bit multiply (SASS: 259 integer instructions per node in the
-    // in-place odd step with the select on every access, round 2)
-    template <class IDX>
-    static __device__ __forceinline__ double load_nowall(const double *A, const Geom &g, const NodeIdx<IDX> &k) {
-        return pop_load(A + (long long)slot_nb * g.slab + (long long)index_nb(k));
-    }
-    template <class IDX>
-    static __device__ __forceinline__ void store_back_nowall(double *A, const Geom &g, const NodeIdx<IDX> &k, double v) {
-        pop_store(A + (long long)slot_nb * g.slab + (long long)index_nb(k), v);
-    }
     template <class IDX>
     static __device__ __forceinline__ double load(const double *A, const Geom &g, const NodeIdx<IDX> &k) {
 #if D3Q_EXP & 2
@@ -270,7 +255,7 @@ struct Gather {
     template <class IDX>
     static __device__ __forceinline__ void store_back_halo(double *A, const Geom &g, const NodeIdx<IDX> &k, double v,
                                                            const Halo &h) {
-        if (cz != 0 && !at_wall(k)) {
+        if (cz != 0 && !at_wall(k) && h.peer_up) {  // (peer_up == nullptr: copy-engine transport, the value stays in my ghost plane)
             if (cz < 0 && k.zg == g.lz) {          // pulled from z+1
                 const long long o = (long long)index_nb(k) - (long long)(g.lz + 1) * g.plane + g.plane;
                 pop_store(h.peer_up + (long long)slot_nb * h.slab_up + o, v);
@@ -300,14 +285,6 @@ struct Gather {
 #endif
     }
 };
-
-template <int RK, class IDX>
-__device__ __forceinline__ void gather19_nowall(const double *A, const Geom &g, const NodeIdx<IDX> &k, double (&f)[NPOP]) {
-    static_for<NPOP>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        f[i] = Gather<RK, i>::load_nowall(A, g, k);
-    });
-}
 
 template <int RK, class IDX>
 __device__ __forceinline__ void gather19(const double *A, const Geom &g, const NodeIdx<IDX> &k, double (&f)[NPOP]) {
@@ -398,11 +375,7 @@ k_step(const __grid_constant__ StepParams p) {
             });
         }
 #endif
-        // a warp covers 32 consecutive x: it touches a wall only if it holds x = 0 or x = lx-1 (warp-uniform)
-        const int xw = x & ~31;
-        const bool wallwarp = !(D3Q_WALLSPLIT && SK == STEP_AA_ODD) || xw == 0 || xw + 31 >= g.lx - 1;
-        if (wallwarp) gather19<RK>(p.A, g, k, f);
-        else gather19_nowall<RK>(p.A, g, k, f);
+        gather19<RK>(p.A, g, k, f);
 
         double Fx = p.Fx, Fy = p.Fy, Fz = p.Fz;
         bool is_solid = false;
@@ -449,33 +422,27 @@ k_step(const __grid_constant__ StepParams p) {
             static_for<NPOP>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 pop_store(p.B + (long long)i * g.slab + k.n, f[i]);
-                if (HALO && dir_cz(i) > 0 && zg_blk == g.lz)       // -> the upper neighbour's ghost plane 0
+                // (peer_up == nullptr: the copy engines move the faces, this launch only signals that they are ready)
+                if (HALO && dir_cz(i) > 0 && zg_blk == g.lz && p.halo.peer_up)       // -> the upper neighbour's ghost plane 0
                     pop_store(p.halo.peer_up + (long long)i * p.halo.slab_up + inplane, f[i]);
-                if (HALO && dir_cz(i) < 0 && zg_blk == 1)          // -> the lower neighbour's ghost plane lz_dn+1
+                if (HALO && dir_cz(i) < 0 && zg_blk == 1 && p.halo.peer_up)          // -> the lower neighbour's ghost plane lz_dn+1
                     pop_store(p.halo.peer_dn + (long long)i * p.halo.slab_dn + (long long)(p.halo.lz_dn + 1) * g.plane + inplane, f[i]);
             });
         } else if (SK == STEP_AA_EVEN) {
             static_for<NPOP>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 pop_store(p.A + (long long)dir_opp(i) * g.slab + k.n, f[i]);
-                if (HALO && dir_cz(i) > 0 && zg_blk == g.lz)
+                if (HALO && dir_cz(i) > 0 && zg_blk == g.lz && p.halo.peer_up)
                     pop_store(p.halo.peer_up + (long long)dir_opp(i) * p.halo.slab_up + inplane, f[i]);
-                if (HALO && dir_cz(i) < 0 && zg_blk == 1)
+                if (HALO && dir_cz(i) < 0 && zg_blk == 1 && p.halo.peer_up)
                     pop_store(p.halo.peer_dn + (long long)dir_opp(i) * p.halo.slab_dn + (long long)(p.halo.lz_dn + 1) * g.plane + inplane, f[i]);
             });
         } else {
-            if (HALO || wallwarp) {
-                static_for<NPOP>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    if (HALO) Gather<READ_PULL_SWAP, i>::store_back_halo(p.A, g, k, f[dir_opp(i)], p.halo);
-                    else Gather<READ_PULL_SWAP, i>::store_back(p.A, g, k, f[dir_opp(i)]);
-                });
-            } else {
-                static_for<NPOP>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    Gather<READ_PULL_SWAP, i>::store_back_nowall(p.A, g, k, f[dir_opp(i)]);
-                });
-            }
+            static_for<NPOP>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                if (HALO) Gather<READ_PULL_SWAP, i>::store_back_halo(p.A, g, k, f[dir_opp(i)], p.halo);
+                else Gather<READ_PULL_SWAP, i>::store_back(p.A, g, k, f[dir_opp(i)]);
+            });
         }
     }
     if (HALO) {

@@ -194,17 +194,6 @@ struct Links {
     long long cap;             // entries per particle
 };
 
-// owner of the neighbour of (jx,jy,zg) along direction IP, or -2 beyond a channel wall
-template <int IP>
-__device__ __forceinline__ int32_t link_owner(const PartGeom &pg, const int32_t *own, int jx, int jy, int zg) {
-    constexpr int cx = dir_cx(IP), cy = dir_cy(IP), cz = dir_cz(IP);
-    const int kx = jx + cx;
-    if (kx < 1 || kx > pg.nx) return -2;
-    const int ky = wrap1(jy + cy, pg.ny);
-    const int kzg = zg + cz;                         // ghost planes carry the mask too
-    return own[(long long)(kx - 1) + (long long)pg.g.xp * ((ky - 1) + (long long)pg.g.ly * kzg)];
-}
-
 // fraction of the link from (jx,jy,jz) along IP that lies in the fluid: smallest root of
 // |x_f + t c - r_c|^2 = rad^2, non-contracted arithmetic (bit-identical to the CPU checker)
 template <int IP>
@@ -248,6 +237,10 @@ __device__ __forceinline__ void link_node_coords(const PartGeom &pg, const doubl
     jx = x + 1; jy = b.lo[1] + ry; jz = b.lo[2] + rz;
 }
 
+// One warp per box row.  Lanes 1..30 are 30 consecutive nodes of the row, lanes 0 and 31 their x-neighbours: the nine
+// mask rows around the row (y-1..y+1, z-1..z+1) are read as nine coalesced pieces and the 18 neighbour owners of a node come
+// from its own registers (c_x = 0) or from the adjacent lane (shuffle) -- 9 loads and 10 shuffles per 30 nodes instead of 18
+// scattered loads with their index arithmetic per node (146 us -> see profiles/ for 100 spheres of radius 15).
 __global__ void __launch_bounds__(32 * PART_WARPS) k_beads_links(PartGeom pg, int npart, const double *ypglb, const int32_t *own, Links L) {
     const int p = blockIdx.x, lane = threadIdx.x & 31;
     const double *c = ypglb + 3 * p;
@@ -266,40 +259,64 @@ __global__ void __launch_bounds__(32 * PART_WARPS) k_beads_links(PartGeom pg, in
     const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
     const int zg = iz - pg.globalz;                  // links belong to the GPU that owns the fluid node
     if (zg < 1 || zg > pg.g.lz) return;
-    for (int r0 = 0; r0 < b.n[0]; r0 += 32) {        // warp-uniform trip count: the shuffles below need every lane
-        const int jx = b.lo[0] + r0 + lane;
-        unsigned bits = 0u;                           // bit ip-1: the neighbour along ip is owned by p
-        long long n = 0;
-        if (r0 + lane < b.n[0]) {
-            const double d2 = dist2_node(c, jx, jy, jz);
-            if (!(d2 < r2) && d2 < rshell2) {
-                n = (long long)(jx - 1) + (long long)pg.g.xp * ((iy - 1) + (long long)pg.g.ly * zg);
-                if (!(own[n] > 0)) {
-                    static_for<NPOP - 1>([&](auto ic) {
-                        constexpr int ip = decltype(ic)::value + 1;
-                        if (link_owner<ip>(pg, own, jx, iy, zg) == p + 1) bits |= 1u << (ip - 1);
-                    });
-                }
-            }
-        }
-        const int cnt = __popc(bits);
-        int incl = cnt;
+    // the nine rows: y-1, y, y+1 (periodic) x z-1, z, z+1 (ghost planes carry the mask too)
+    long long rowbase[3][3];
+    {
+        const int ky[3] = {wrap1(iy - 1, pg.ny), iy, wrap1(iy + 1, pg.ny)};
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int bz = 0; bz < 3; ++bz) rowbase[a][bz] = (long long)pg.g.xp * ((ky[a] - 1) + (long long)pg.g.ly * (zg + bz - 1));
+    }
+    const unsigned full = 0xffffffffu;
+    for (int r0 = 0; r0 < b.n[0]; r0 += 30) {        // warp-uniform trip count: the shuffles below need every lane
+        const int jx = b.lo[0] + r0 + lane - 1;      // lanes 0 and 31: the columns next to this piece of the row
+        const bool inside = jx >= 1 && jx <= pg.nx;
+        bool cand = false;
+        if (lane >= 1 && lane <= 30 && r0 + lane - 1 < b.n[0] && inside) {
+            const double d2 = dist2_node(c, jx, jy, jz);
+            cand = !(d2 < r2) && d2 < rshell2;
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (!__any_sync(full, cand)) continue;
+        int32_t o[3][3];                             // owners of the nine rows at column jx (-2 beyond a channel wall)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int bz = 0; bz < 3; ++bz) o[a][bz] = inside ? own[rowbase[a][bz] + (jx - 1)] : -2;
+        if (o[1][1] > 0) cand = false;               // the node itself is solid (this or another particle)
+        unsigned bits = 0u;                           // bit ip-1: the neighbour along ip is owned by p
+        static_for<NPOP - 1>([&](auto ic) {
+            constexpr int ip = decltype(ic)::value + 1;
+            constexpr int cx = dir_cx(ip), cy = dir_cy(ip), cz = dir_cz(ip);
+            int32_t v = o[1 + cy][1 + cz];
+            if (cx != 0) v = __shfl_sync(full, v, (lane + cx) & 31);
+            if (cand && v == p + 1) bits |= 1u << (ip - 1);
+        });
+        // Order inside this piece of the row: DIRECTION first, then x -- consecutive list entries then share their direction
+        // and sit on neighbouring nodes, so the threads of k_beads_ibb that take them read and write neighbouring addresses
+        // of ONE population (its accesses are random 32-byte sectors otherwise, and that kernel is bound by them).
+        const unsigned below = (1u << lane) - 1u;
+        int mine[NPOP - 1];                          // my rank among this piece's links, per direction (valid where my bit is set)
+        int total = 0;
+        static_for<NPOP - 1>([&](auto ic) {
+            constexpr int ip = decltype(ic)::value + 1;
+            const unsigned m = __ballot_sync(full, (bits >> (ip - 1)) & 1u);
+            mine[ip - 1] = total + __popc(m & below);
+            total += __popc(m);
+        });
         if (total == 0) continue;
         unsigned long long base = 0;
-        if (lane == 31) base = atomicAdd(L.count + p, (unsigned long long)total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        long long w = (long long)base + incl - cnt;
+        if (lane == 0) base = atomicAdd(L.count + p, (unsigned long long)total);
+        base = __shfl_sync(full, base, 0);
         const long long seg = (long long)p * L.cap;
-        for (unsigned rest = bits; rest; rest &= rest - 1) {           // the set bits, lowest direction first
-            if (w < L.cap) { L.node[seg + w] = (uint32_t)n; L.dir[seg + w] = __ffs(rest); }
-            ++w;
-        }
+        const uint32_t n = (uint32_t)(rowbase[1][1] + (jx - 1));
+        static_for<NPOP - 1>([&](auto ic) {
+            constexpr int ip = decltype(ic)::value + 1;
+            if (bits & (1u << (ip - 1))) {
+                const long long w = (long long)base + mine[ip - 1];
+                if (w < L.cap) { L.node[seg + w] = n; L.dir[seg + w] = ip; }
+            }
+        });
     }
 }
 
@@ -456,13 +473,13 @@ template <int RK>
 __global__ void __launch_bounds__(128) k_beads_fill(const __grid_constant__ FillParams P) {
     const PartGeom &pg = P.pg;
     const Geom &g = pg.g;
-    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nlist = (long long)*P.F.count < P.F.cap ? (long long)*P.F.count : P.F.cap;
-    if (l < nlist) {
+    // the list length is known on the device only: a fixed grid strides over it
+    for (long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x; l < nlist; l += (long long)gridDim.x * blockDim.x) {
         const uint32_t nn32 = P.F.node[l];
         const int p = P.F.part[l] - 1;
         const long long n = (long long)nn32;
-        if (P.own[n] != -(p + 2)) return;                 // another particle covers the node now
+        if (P.own[n] != -(p + 2)) continue;               // another particle covers the node now
         const int x = (int)(nn32 % (uint32_t)g.xp), y = (int)((nn32 / (uint32_t)g.xp) % (uint32_t)g.ly),
                   zg = (int)(nn32 / ((uint32_t)g.xp * (uint32_t)g.ly));
         const int jx = x + 1, iy = y + 1, iz = zg + pg.globalz;
@@ -540,11 +557,14 @@ __global__ void __launch_bounds__(128) k_beads_fill(const __grid_constant__ Fill
 // ---- beads_lubforce / beads_move: npart threads ------------------------------------------------------
 struct LubParams { double mingap, mingap_w, stf0, stf1, stf0_w, stf1_w, fscale; };
 
-__device__ __forceinline__ void lubforce_one(const PartGeom &pg, int npart, const double *ypglb, const LubParams &lp, double *flubp, int i) {
+// one WARP per particle i: the lanes share the partners j (a particle's partner loop is a chain of square roots), the three
+// components are reduced over the warp, lane 0 adds the two walls and stores
+__device__ __forceinline__ void lubforce_warp(const PartGeom &pg, int npart, const double *ypglb, const LubParams &lp, double *flubp, int i) {
+    const int lane = threadIdx.x & 31;
     const double *a = ypglb + 3 * i;
     const double Rr = pg.rad;
     double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-    for (int j = 0; j < npart; ++j) {
+    for (int j = lane; j < npart; j += 32) {
         if (j == i) continue;
         const double *b = ypglb + 3 * j;
         double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
@@ -559,15 +579,23 @@ __device__ __forceinline__ void lubforce_one(const PartGeom &pg, int npart, cons
         if (gap < 0.0) mag += lp.fscale / lp.stf1 * (-gap / lp.mingap);
         f0 += mag * dx / d; f1 += mag * dy / d; f2 += mag * dz / d;
     }
-    for (int s = 0; s < 2; ++s) {
-        const double dxw = s == 0 ? a[0] : a[0] - (double)pg.nx;
-        const double gap = fabs(dxw) - Rr;
-        if (gap >= lp.mingap_w) continue;
-        double mag = lp.fscale / lp.stf0_w * ((gap - lp.mingap_w) / lp.mingap_w) * ((gap - lp.mingap_w) / lp.mingap_w);
-        if (gap < 0.0) mag += lp.fscale / lp.stf1_w * (-gap / lp.mingap_w);
-        f0 += (dxw >= 0.0 ? mag : -mag);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        f0 += __shfl_xor_sync(0xffffffffu, f0, o);
+        f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+        f2 += __shfl_xor_sync(0xffffffffu, f2, o);
     }
-    flubp[3 * i] = f0; flubp[3 * i + 1] = f1; flubp[3 * i + 2] = f2;
+    if (lane == 0) {
+        for (int s = 0; s < 2; ++s) {
+            const double dxw = s == 0 ? a[0] : a[0] - (double)pg.nx;
+            const double gap = fabs(dxw) - Rr;
+            if (gap >= lp.mingap_w) continue;
+            double mag = lp.fscale / lp.stf0_w * ((gap - lp.mingap_w) / lp.mingap_w) * ((gap - lp.mingap_w) / lp.mingap_w);
+            if (gap < 0.0) mag += lp.fscale / lp.stf1_w * (-gap / lp.mingap_w);
+            f0 += (dxw >= 0.0 ? mag : -mag);
+        }
+        flubp[3 * i] = f0; flubp[3 * i + 1] = f1; flubp[3 * i + 2] = f2;
+    }
 }
 
 struct MoveParams {
@@ -603,7 +631,7 @@ __device__ __forceinline__ void move_one(const PartGeom &pg, const MoveParams &M
 __global__ void __launch_bounds__(1024) k_beads_lubmove(PartGeom pg, int npart, const double *ypglb, LubParams lp, double *flubp,
                                                         MoveParams M, int do_lub, int do_move) {
     if (do_lub)
-        for (int i = threadIdx.x; i < npart; i += blockDim.x) lubforce_one(pg, npart, ypglb, lp, flubp, i);
+        for (int i = threadIdx.x >> 5; i < npart; i += blockDim.x >> 5) lubforce_warp(pg, npart, ypglb, lp, flubp, i);
     __syncthreads();
     if (do_move)
         for (int p = threadIdx.x; p < npart; p += blockDim.x) move_one(pg, M, p);

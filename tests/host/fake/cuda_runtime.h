@@ -120,6 +120,17 @@ template <class T> static inline T warp_exchange(T v, int src_lane) {
     barrier(warp_bar[w], first, 32);
     return from_bits<T>(r);
 }
+// one rendezvous for a whole-warp vote: every lane deposits its predicate, then reads all 32
+static inline unsigned warp_ballot(int pred) {
+    if (cur < 0) trap("warp vote in a sequential launch (use hs_launch_coop)");
+    const int w = cur >> 5, first = cur & ~31;
+    xch[cur] = pred ? 1ull : 0ull;
+    barrier(warp_bar[w], first, 32);
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= (unsigned)(xch[first + l] & 1ull) << l;
+    barrier(warp_bar[w], first, 32);
+    return m;
+}
 }  // namespace hs
 
 static inline void __syncthreads() { hs::barrier(hs::block_bar, 0, (int)blockDim.x); }
@@ -141,14 +152,13 @@ struct alignas(16) double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
-static inline int __all_sync(unsigned, int pred) {
-    int all = 1;
-    for (int l = 0; l < 32; ++l) all &= hs::warp_exchange(pred ? 1 : 0, l);      // 32 rounds: simple, and only in tests
-    return all;
-}
+// votes: one rendezvous (hs::warp_ballot); the maximum as an xor butterfly
+static inline unsigned __ballot_sync(unsigned, int pred) { return hs::warp_ballot(pred); }
+static inline int __all_sync(unsigned, int pred) { return __ballot_sync(0xffffffffu, pred) == 0xffffffffu; }
+static inline int __any_sync(unsigned, int pred) { return __ballot_sync(0xffffffffu, pred) != 0u; }
 static inline int __reduce_max_sync(unsigned, int v) {
     int m = v;
-    for (int l = 0; l < 32; ++l) { const int o = hs::warp_exchange(v, l); m = o > m ? o : m; }
+    for (int o = 16; o > 0; o >>= 1) { const int t = hs::warp_exchange(m, (hs::cur & 31) ^ o); m = t > m ? t : m; }
     return m;
 }
 static inline long long __double_as_longlong(double v) { long long b; std::memcpy(&b, &v, 8); return b; }

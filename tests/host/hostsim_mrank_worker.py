@@ -56,9 +56,10 @@ def section_fluid(rank, world, comm, chk, ctx):
              ((24, 6, 4 * world), False, "nccl"), ((130, 3, 2 * world + 1), True, "nccl"),
              ((24, 6, 4 * world), True, "peer"), ((33, 5, 3 * world + 1), True, "peer"), ((130, 3, 2 * world + 1), True, "peer"),
              ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split"),
-             ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"), ((130, 3, 2 * world + 1), True, "put")]
+             ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"), ((130, 3, 2 * world + 1), True, "put"),
+             ((24, 6, 4 * world), True, "put-split"), ((33, 5, 3 * world + 1), True, "put-split")]
     if os.environ.get("HOSTSIM_SHORT"):          # the default CPU suite: one uneven case per transport
-        cases = [((33, 5, 3 * world + 1), True, h) for h in ("nccl", "peer", "peer-split", "put")] + \
+        cases = [((33, 5, 3 * world + 1), True, h) for h in ("nccl", "peer", "peer-split", "put", "put-split")] + \
                 [((24, 6, 4 * world), False, "nccl")]
     import time
     for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
@@ -69,11 +70,11 @@ def section_fluid(rank, world, comm, chk, ctx):
             w.set_f(w.get_f() + 1e-4 * np.random.default_rng(7).normal(size=(nz, ny, nx, 19)))
             sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=scheme,
                                   math_mode=capi.MATH_STRICT, nccl_id=comm.new_id(rank), overlap=overlap,
-                                  halo_split_min=3 if halo == "peer-split" else 0)
+                                  halo_split_min=3 if halo in ("peer-split", "put-split") else 0)
             z0, z1 = sim.globalz, sim.globalz + sim.lz
             sim.FORCING()
-            if halo.startswith("peer") or halo == "put":
-                ok_ = sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if halo == "put" else "fused")
+            if halo.startswith("peer") or halo.startswith("put"):
+                ok_ = sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if halo.startswith("put") else "fused")
                 chk("peer halo connects", ok_)
             sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
             w.macrovar()
@@ -312,7 +313,7 @@ def section_benchparity(rank, world, comm, chk, ctx):
 
         def connect(sim):
             if halo != "nccl":
-                assert sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if halo == "put" else "fused")
+                assert sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if halo.startswith("put") else "fused")
 
         res = bench.parity_check(pkg, rank, world, 0, lambda: comm.new_id(rank), connect,
                                  lambda ok: all(comm.allgather(rank, bool(ok))), lambda obj: comm.allgather(rank, obj)[0],
@@ -329,7 +330,7 @@ def section_random(rank, world, comm, chk, ctx):
                                                                                      "hostsim_random_calls.py"))
     rc = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(rc)
-    transports = ["nccl", "peer", "peer-split", "put"]
+    transports = ["nccl", "peer", "peer-split", "put", "put-split"]
     nseeds = int(os.environ.get("HOSTSIM_RANDOM_SEEDS", "7"))
     for seed in range(nseeds):
         for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):

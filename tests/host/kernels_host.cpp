@@ -381,7 +381,7 @@ static void lubmove(Sim &s, int do_lub, int do_move) {
     for (Rank &q : s.r) {
         MoveParams M = {s.amp, s.aip, s.gforce[0], s.gforce[1], s.gforce[2], q.fHIp.data(), q.torqp.data(), q.flubp.data(),
                         q.forcepp.data(), q.torqpp.data(), q.ypglb.data(), q.wp.data(), q.omgp.data(), q.thetap.data()};
-        const int nt = s.npart < 1024 ? ((s.npart + 31) / 32) * 32 : 1024;
+        const int nt = s.npart < 32 ? s.npart * 32 : 1024;
         hs_launch_coop(dim3(1), nt, k_beads_lubmove, part_geom(s, q), s.npart, (const double *)q.ypglb.data(), s.lub, q.flubp.data(), M,
                        do_lub, do_move);
     }
@@ -396,7 +396,7 @@ void fill_rank(Sim &s, Rank &q) {
     P.ypglb = q.ypglb.data(); P.wp = q.wp.data(); P.omgp = q.omgp.data(); P.nfilled = &q.nfilled;
     P.ghost_lo = P.ghost_hi = nullptr;
     if (s.nranks > 1) { P.ghost_lo = q.fill_ghost_lo.data(); P.ghost_hi = q.fill_ghost_hi.data(); }
-    hs_launch(dim3((unsigned)((q.pcnt[1] + 200 + 127) / 128)), 128, k_beads_fill<RK>, P);
+    hs_launch(dim3(3), 128, k_beads_fill<RK>, P);                      // a fixed grid strides over the list
     q.pcnt[1] = 0;
 }
 template <int RK>

@@ -58,10 +58,12 @@ def main():
              ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split"),
              # third transport: plain step kernels, the copy engines move the faces into the neighbours' arrays
              ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"), ((40, 3, 2 * world), True, "put"),
-             ((130, 7, 2 * world + 1), True, "put")]
+             ((130, 7, 2 * world + 1), True, "put"),
+             # ... with the boundary planes as a launch of their own (what thick slabs do)
+             ((24, 6, 4 * world), True, "put-split"), ((33, 5, 3 * world + 1), True, "put-split")]
     only = os.environ.get("MGPU_ONLY", "")          # e.g. "peer": just the peer-memory halo cases (short runs on many GPUs)
     if only:
-        cases = [c for c in cases if c[2].startswith(only) or (only == "peer" and c[2] == "put")]
+        cases = [c for c in cases if c[2].startswith(only) or (only == "peer" and c[2].startswith("put"))]
     for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
         for (nx, ny, nz), overlap, halo in cases:
             ctx[0] = "scheme %d case %s overlap %s halo %s" % (scheme, (nx, ny, nz), overlap, halo)
@@ -70,11 +72,11 @@ def main():
             w.set_f(w.get_f() + 1e-4 * rng.normal(size=(nz, ny, nx, 19)))
             sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local, scheme=scheme,
                                   math_mode=capi.MATH_STRICT, nccl_id=new_id(), overlap=overlap,
-                                  halo_split_min=3 if halo == "peer-split" else 0)
+                                  halo_split_min=3 if halo in ("peer-split", "put-split") else 0)
             z0, z1 = sim.globalz, sim.globalz + sim.lz
             sim.FORCING()
-            if halo.startswith("peer") or halo == "put":
-                connected = sim.connect_halo(allgather_bytes, mode="put" if halo == "put" else "fused")
+            if halo.startswith("peer") or halo.startswith("put"):
+                connected = sim.connect_halo(allgather_bytes, mode="put" if halo.startswith("put") else "fused")
                 if not connected:
                     raise RuntimeError("peer-memory halo unavailable between the GPUs of this box: " + ctx[0])
             sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))

@@ -31,6 +31,8 @@ ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
 ap.add_argument("--scheme", default="ab", choices=["aa", "ab"])
 ap.add_argument("--steps", type=int, default=60)
 ap.add_argument("--size", default="512x256x256")
+ap.add_argument("--nccl-max-ctas", type=int, default=0)
+ap.add_argument("--halo-split-min", type=int, default=0)
 a = ap.parse_args()
 
 pkg = entry.load_package()
@@ -50,7 +52,8 @@ nx, ny, nz = (int(t) for t in a.size.split("x"))
 if a.scaling == "weak":
     nz *= world
 sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local, nccl_id=nccl_id,
-                      scheme=capi.SCHEME_AA if a.scheme == "aa" else capi.SCHEME_AB, allocate_host=False)
+                      scheme=capi.SCHEME_AA if a.scheme == "aa" else capi.SCHEME_AB, allocate_host=False,
+                      nccl_max_ctas=a.nccl_max_ctas, halo_split_min=a.halo_split_min)
 if world > 1 and a.halo != "nccl":
     def allgather_bytes(b):
         t = torch.tensor(list(b), dtype=torch.uint8)
@@ -79,7 +82,8 @@ if world > 1:
     rows = [None] * world
     dist.all_gather_object(rows, res)
 if rank == 0:
-    print(json.dumps(dict(halo=a.halo, scaling=a.scaling, scheme=a.scheme, size=[nx, ny, nz], gpus=world, unit="us", ranks=rows)))
+    print(json.dumps(dict(halo=a.halo, nccl_max_ctas=a.nccl_max_ctas, halo_split_min=a.halo_split_min, scaling=a.scaling, scheme=a.scheme,
+                          size=[nx, ny, nz], gpus=world, unit="us", ranks=rows)))
 sim.close()
 if world > 1:
     dist.destroy_process_group()
