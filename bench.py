@@ -56,12 +56,13 @@ def parse_args():
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-parity", action="store_true",
                     help="skip the bit-exact check of the reference's golden vector on this job's ranks before the timed region")
-    ap.add_argument("--halo", default="nccl", choices=["peer", "put", "nccl"],
-                    help="z-face exchange: nccl = NCCL send/recv of the packed faces on a second stream, overlapped with the "
-                         "interior; put = the copy engines move the faces into the neighbour GPU's memory over NVLink (no SM "
-                         "involved); peer = stores into the neighbour's memory inside the step kernel")
+    ap.add_argument("--halo", default="put", choices=["peer", "put", "nccl"],
+                    help="z-face exchange: put (default) = the copy engines move the faces into the neighbour GPU's memory over "
+                         "NVLink next to the interior launch, no SM involved (fastest in every configuration measured, "
+                         "profiles/r02e_two_gpus.md; falls back to nccl when peer memory cannot be mapped); nccl = NCCL send/recv "
+                         "of the packed faces on a second stream; peer = stores into the neighbour's memory inside the step kernel")
     ap.add_argument("--nccl-max-ctas", type=int, default=0,
-                    help="d3q19_config.nccl_max_ctas: CTAs NCCL may use for the face send/recv (0 = the library's default, 4)")
+                    help="d3q19_config.nccl_max_ctas: cap on the CTAs of NCCL's face send/recv (0 = NCCL's own choice, the default)")
     ap.add_argument("--halo-split-min", type=int, default=0,
                     help="d3q19_config.halo_split_min: peer-memory transports run slabs at least this thick as boundary + interior "
                          "launches, thinner ones as one launch (0 = the library's default, 64)")
@@ -304,6 +305,8 @@ def parity_check(pkg, rank, world, local_rank, fresh_nccl_id, connect, gather_ok
             sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=r, nranks=nr, device=dev, scheme=capi.SCHEME_AB,
                                   nccl_id=nid, ipart=True, **U)
             sim.FORCING()
+            if nr > 1:
+                connect(sim, particles=True)
             sim.init_channel_device(A9=0.3, noise_amp=1e-3 * sim.v.ustar, seed=777)
             sim.particles_init(pos, rad, vel, omg)
             for _ in range(3):
@@ -408,8 +411,8 @@ def main():
 
     scheme = {"aa": capi.SCHEME_AA, "ab": capi.SCHEME_AB, "auto": capi.SCHEME_AUTO}[args.scheme]
     math_mode = capi.MATH_FAST if args.math == "fast" else capi.MATH_STRICT
-    if args.particles > 0:
-        args.halo = "nccl"              # the particle path keeps its halo on NCCL
+    if args.particles > 0 and args.halo == "peer":
+        args.halo = "put"               # with particles: copy engines or NCCL (the refill sources and the forces use NCCL anyway)
     nodes_global = nx * ny * nz
     device_init = args.device_init or args.workload == "c4"
     do_e2e = not args.no_e2e and not device_init and args.particles == 0
@@ -481,10 +484,14 @@ def main():
             dist.all_gather(out, t)
             return [bytes(o.tolist()) for o in out]
 
-        def connect_(sim_):
+        def connect_(sim_, particles=False):
             if world > 1 and args.halo in ("peer", "put"):
-                if not sim_.connect_halo(allgather_bytes_, mode="put" if args.halo == "put" else "fused"):
-                    raise SystemExit("bench parity: peer-memory halo unavailable on this box")
+                mode = "put" if (args.halo == "put" or particles) else "fused"
+                if not sim_.connect_halo(allgather_bytes_, mode=mode):
+                    # agreed by all ranks inside d3q19_ipc_connect: no peer memory on this box -> NCCL send/recv from here on
+                    if rank == 0:
+                        sys.stderr.write("bench: peer memory cannot be mapped between these GPUs, the faces travel by NCCL\n")
+                    args.halo = "nccl"
 
         def bcast_(obj):
             if world == 1:
@@ -628,7 +635,7 @@ def main():
                        "parallelism": ("z-slab x%d, faces %s" % (world, {
                            "peer": "stored into the neighbour GPU's memory over NVLink inside the step kernel",
                            "put": "copied into the neighbour GPU's memory over NVLink by the copy engines on a second stream",
-                           "nccl": "by NCCL send/recv (at most %d CTAs)" % (args.nccl_max_ctas or 4)}[halo])) if world > 1 else "1 GPU",
+                           "nccl": "by NCCL send/recv" + (" (at most %d CTAs)" % args.nccl_max_ctas if args.nccl_max_ctas else "")}[halo])) if world > 1 else "1 GPU",
                        "l2": "populations %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (c1["population_bytes"] / 1e9)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "parity_check": parity,
             "clocks": clocks, "impl": "ours",

@@ -393,11 +393,12 @@ extern "C" int d3q19_create(const d3q19_config *cfg, d3q19_handle **out) {
         if (const char *m = n.load()) { fail("d3q19_create: %s", m); d3q19_destroy(h); return 1; }
         NcclUniqueId id;
         memcpy(id.internal, cfg->nccl_id, 128);
-        // the faces are a few MB per step: a handful of NCCL CTAs carries them, and each one holds an SM that the interior
-        // kernel then does not have (d3q19_config.nccl_max_ctas, default 4)
-        NcclConfig218 nc = nccl_config_max_ctas(cfg->nccl_max_ctas > 0 ? cfg->nccl_max_ctas : 4);
-        int e = n.CommInitRankConfig ? n.CommInitRankConfig(&h->comm, cfg->nranks, id, cfg->rank, &nc)
-                                     : n.CommInitRank(&h->comm, cfg->nranks, id, cfg->rank);
+        // d3q19_config.nccl_max_ctas > 0 caps the CTAs of NCCL's send/recv kernel.  Measured (2 B200, 32-plane slabs,
+        // profiles/r02e_two_gpus.md): every cap is a loss -- 1-2 CTAs 0.655 ms per step, 4: 0.419, 8: 0.298, 32 = no cap: 0.230 --
+        // the exchange becomes too slow to hide long before it stops disturbing the interior kernel.  Default: NCCL's own choice.
+        NcclConfig218 nc = nccl_config_max_ctas(cfg->nccl_max_ctas);
+        int e = (cfg->nccl_max_ctas > 0 && n.CommInitRankConfig) ? n.CommInitRankConfig(&h->comm, cfg->nranks, id, cfg->rank, &nc)
+                                                                 : n.CommInitRank(&h->comm, cfg->nranks, id, cfg->rank);
         if (e != 0) { fail("d3q19_create: ncclCommInitRank -> %s", n.GetErrorString(e)); h->comm = nullptr; d3q19_destroy(h); return 1; }
         const size_t fb = (size_t)5 * g.plane * sizeof(double);
         CKH(cudaMalloc(&h->send_up, fb)); CKH(cudaMalloc(&h->send_dn, fb));
@@ -455,7 +456,9 @@ extern "C" int d3q19_ipc_export(d3q19_handle *h, unsigned char *blob) {
 extern "C" int d3q19_ipc_connect(d3q19_handle *h, const unsigned char *blobs) {
     CK(cudaSetDevice(h->cfg.device));
     if (h->cfg.nranks < 2) return fail("d3q19_ipc_connect: needs nranks > 1");
-    if (h->cfg.ipart) return fail("d3q19_ipc_connect: the particle path exchanges its halo through NCCL");
+    if (h->cfg.ipart && h->halo_mode != D3Q19_HALO_PUT)
+        return fail("d3q19_ipc_connect: with particles (ipart) the faces travel by NCCL or by the copy engines -- call "
+                    "d3q19_set_halo_mode(h, D3Q19_HALO_PUT) first");
     if (h->g.lz < 2) return fail("d3q19_ipc_connect: slabs must be at least 2 planes thick");
     if (!h->halo_flags) return fail("d3q19_ipc_connect: call d3q19_ipc_export first");
     if (h->halo_on) return fail("d3q19_ipc_connect: already connected");
@@ -832,25 +835,23 @@ static int launch_step_range(d3q19_handle *h, const StepParams &p0, int z0, int 
 // the interior the plain one (which needs fewer registers -- the AA odd step keeps its 4 CTAs/SM); the
 // order of the two launches is free, no node of one reads or writes an address the other writes.
 template <int SK, bool STRICT, bool GENERIC>
-static int launch_step_halo(d3q19_handle *h, const StepParams &p0, bool remote = true) {
+static int launch_step_halo(d3q19_handle *h, const StepParams &p0) {
     StepParams p = p0;
     Halo &q = p.halo;
     const bool ab = SK == STEP_AB;
     // AB: this step writes B here and in the neighbours; AA: the single array
-    // (remote = false: copy-engine transport -- no stores into the neighbours, the plane counters raise two LOCAL words
-    //  that the copy stream waits for)
-    q.peer_dn = !remote ? nullptr : (ab ? h->peer_B[0] : h->peer_A[0]);
-    q.peer_up = !remote ? nullptr : (ab ? h->peer_B[1] : h->peer_A[1]);
+    q.peer_dn = ab ? h->peer_B[0] : h->peer_A[0];
+    q.peer_up = ab ? h->peer_B[1] : h->peer_A[1];
     q.slab_dn = h->peer_slab[0]; q.slab_up = h->peer_slab[1];
     q.lz_dn = h->peer_lz[0];
     q.wait_lo = h->halo_flags; q.wait_hi = h->halo_flags + 1;
-    q.sig_dn = remote ? h->peer_flags[0] + 1 : h->halo_flags + 4;      // the lower neighbour's wait_hi / "my plane 1 is done"
-    q.sig_up = remote ? h->peer_flags[1] : h->halo_flags + 5;          // the upper neighbour's wait_lo / "my plane lz is done"
+    q.sig_dn = h->peer_flags[0] + 1;      // the lower neighbour's wait_hi
+    q.sig_up = h->peer_flags[1];          // the upper neighbour's wait_lo
     q.ctr = h->halo_flags + 2;
     q.err = h->halo_flags + 8;
     q.timeout_ns = h->halo_timeout_ns;
-    q.epoch = remote ? ++h->halo_epoch : h->halo_epoch;      // (the caller advanced the epoch)
-    const bool split = remote && h->g.lz >= h->halo_split_min && h->g.lz > 2;
+    q.epoch = ++h->halo_epoch;
+    const bool split = h->g.lz >= h->halo_split_min && h->g.lz > 2;
     const dim3 gr = grid_nodes(h, split ? 2 : h->g.lz);
     q.nblk_face = gr.x * gr.y;
     if (h->idx32) k_step<SK, STRICT, GENERIC, uint32_t, true><<<gr, BLOCK_X, 0, h->sc>>>(p);
@@ -858,7 +859,7 @@ static int launch_step_halo(d3q19_handle *h, const StepParams &p0, bool remote =
     CK(cudaGetLastError());
     h->n_step_kernels++;
     if (split) RK_((launch_step_range<SK, STRICT, GENERIC>(h, p0, 2, h->g.lz - 2, h->sc)));
-    if (ab && remote) {                   // the neighbours swap their arrays in lockstep
+    if (ab) {                             // the neighbours swap their arrays in lockstep
         for (int d = 0; d < 2; ++d) { double *t = h->peer_A[d]; h->peer_A[d] = h->peer_B[d]; h->peer_B[d] = t; }
     }
     return 0;
@@ -880,17 +881,10 @@ static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written
         CK(cudaGetLastError());
     }
     trace_mark(h, 0, h->sc);
-    // Thin slabs (lz < halo_split_min): ONE launch for the whole slab with the two boundary planes first in block order;
-    // their last blocks raise two local words and the copy stream, waiting for them in a one-thread kernel, starts the
-    // transfers while the interior blocks of the same launch are still running -- no drain and refill of the GPU around a
-    // 2-plane launch (measured on 32-plane slabs: the separate boundary launch takes 19 us for 12 us of work).  Thick slabs
-    // keep two launches: the plain instantiation needs fewer registers (in-place odd step: 4 instead of 3 CTAs/SM).
-    const bool single = lz > 2 && lz < h->halo_split_min && !GENERIC;
-    if (single) {
-        CK(cudaEventRecord(h->evB, h->sc));                        // sx may start waiting once the step is enqueued behind this
-        trace_mark(h, 1, h->sc);
-        RK_((launch_step_halo<SK, STRICT, GENERIC>(h, p, false)));
-    } else if (lz > 2) {
+    // (One launch for the whole slab with the boundary planes first in block order and a device-side "planes done" signal
+    //  for the copy stream was measured as well: 0.216 ms per step against 0.206 ms for the two launches below on 32-plane
+    //  slabs -- the instantiation that counts blocks is slower than the plain one.  Removed.  profiles/r02e_two_gpus.md)
+    if (lz > 2) {
         RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 2, h->sc, lz - 1)));   // planes 1 and lz in one launch
         CK(cudaEventRecord(h->evB, h->sc));
         trace_mark(h, 1, h->sc);
@@ -902,11 +896,6 @@ static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written
     }
     trace_mark(h, 2, h->sc);
     CK(cudaStreamWaitEvent(h->sx, h->evB, 0));
-    if (single) {                                                   // the boundary planes of THIS launch are complete
-        k_halo_wait<<<1, 1, 0, h->sx>>>(h->halo_flags + 4, h->halo_flags + 5, epoch, h->halo_flags + 8, h->halo_timeout_ns);
-        CK(cudaGetLastError());
-        h->n_other_kernels++;
-    }
     // The faces travel by the COPY ENGINES: one population of one z plane is plane = xp*ly contiguous doubles, so each
     // of the five crossing populations goes from where it lies in my array to where it belongs in the neighbour's
     // (cudaIpc-mapped) array with one device-to-device copy over NVLink -- no SM takes part, nothing competes with the
@@ -1269,7 +1258,9 @@ extern "C" int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_
     if (npart <= 0 || !prm || !(prm->rad > 0.0)) return fail("d3q19_particles_init: bad arguments");
     if (h->part_on) return fail("d3q19_particles_init: already initialised");
     if (!h->cfg.ipart) return fail("d3q19_particles_init: create the handle with ipart = 1");
-    if (h->halo_on) return fail("d3q19_particles_init: the particle path exchanges its halo through NCCL (do not call d3q19_ipc_connect)");
+    if (h->halo_on && h->halo_mode != D3Q19_HALO_PUT)
+        return fail("d3q19_particles_init: with particles the faces travel by NCCL or by the copy engines (D3Q19_HALO_PUT), not by stores "
+                    "inside the step kernel");
     if (!h->idx32) return fail("d3q19_particles_init: slab too large for 32-bit link indices");
     // a particle's bounding box (< 2 rad + 6 nodes wide) must be smaller than the periodic box: no node is visited twice
     if (2.0 * prm->rad + 7.0 > h->cfg.ny || 2.0 * prm->rad + 7.0 > h->cfg.nz) return fail("d3q19_particles_init: particle larger than the periodic box (2 rad + 7 <= ny, nz)");

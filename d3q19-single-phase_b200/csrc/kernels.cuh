@@ -255,7 +255,7 @@ struct Gather {
     template <class IDX>
     static __device__ __forceinline__ void store_back_halo(double *A, const Geom &g, const NodeIdx<IDX> &k, double v,
                                                            const Halo &h) {
-        if (cz != 0 && !at_wall(k) && h.peer_up) {  // (peer_up == nullptr: copy-engine transport, the value stays in my ghost plane)
+        if (cz != 0 && !at_wall(k)) {
             if (cz < 0 && k.zg == g.lz) {          // pulled from z+1
                 const long long o = (long long)index_nb(k) - (long long)(g.lz + 1) * g.plane + g.plane;
                 pop_store(h.peer_up + (long long)slot_nb * h.slab_up + o, v);
@@ -422,19 +422,18 @@ k_step(const __grid_constant__ StepParams p) {
             static_for<NPOP>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 pop_store(p.B + (long long)i * g.slab + k.n, f[i]);
-                // (peer_up == nullptr: the copy engines move the faces, this launch only signals that they are ready)
-                if (HALO && dir_cz(i) > 0 && zg_blk == g.lz && p.halo.peer_up)       // -> the upper neighbour's ghost plane 0
+                if (HALO && dir_cz(i) > 0 && zg_blk == g.lz)       // -> the upper neighbour's ghost plane 0
                     pop_store(p.halo.peer_up + (long long)i * p.halo.slab_up + inplane, f[i]);
-                if (HALO && dir_cz(i) < 0 && zg_blk == 1 && p.halo.peer_up)          // -> the lower neighbour's ghost plane lz_dn+1
+                if (HALO && dir_cz(i) < 0 && zg_blk == 1)          // -> the lower neighbour's ghost plane lz_dn+1
                     pop_store(p.halo.peer_dn + (long long)i * p.halo.slab_dn + (long long)(p.halo.lz_dn + 1) * g.plane + inplane, f[i]);
             });
         } else if (SK == STEP_AA_EVEN) {
             static_for<NPOP>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 pop_store(p.A + (long long)dir_opp(i) * g.slab + k.n, f[i]);
-                if (HALO && dir_cz(i) > 0 && zg_blk == g.lz && p.halo.peer_up)
+                if (HALO && dir_cz(i) > 0 && zg_blk == g.lz)
                     pop_store(p.halo.peer_up + (long long)dir_opp(i) * p.halo.slab_up + inplane, f[i]);
-                if (HALO && dir_cz(i) < 0 && zg_blk == 1 && p.halo.peer_up)
+                if (HALO && dir_cz(i) < 0 && zg_blk == 1)
                     pop_store(p.halo.peer_dn + (long long)dir_opp(i) * p.halo.slab_dn + (long long)(p.halo.lz_dn + 1) * g.plane + inplane, f[i]);
             });
         } else {

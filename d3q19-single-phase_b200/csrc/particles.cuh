@@ -239,8 +239,26 @@ __device__ __forceinline__ void link_node_coords(const PartGeom &pg, const doubl
 
 // One warp per box row.  Lanes 1..30 are 30 consecutive nodes of the row, lanes 0 and 31 their x-neighbours: the nine
 // mask rows around the row (y-1..y+1, z-1..z+1) are read as nine coalesced pieces and the 18 neighbour owners of a node come
-// from its own registers (c_x = 0) or from the adjacent lane (shuffle) -- 9 loads and 10 shuffles per 30 nodes instead of 18
-// scattered loads with their index arithmetic per node (146 us -> see profiles/ for 100 spheres of radius 15).
+// from its own registers (c_x = 0) or from the adjacent lane (shuffle).  The kernel is bound by the LATENCY of its two
+// dependent round trips (mask loads, then the atomic that reserves list space): two pieces of the row are in flight
+// together and share one atomic.
+struct RowPiece {
+    int jx;
+    bool inside, cand;
+    unsigned bits;
+};
+template <class F>
+__device__ __forceinline__ unsigned piece_bits(int p, int lane, bool cand, const int32_t (&o)[3][3], F) {
+    unsigned bits = 0u;                               // bit ip-1: the neighbour along ip is owned by p
+    static_for<NPOP - 1>([&](auto ic) {
+        constexpr int ip = decltype(ic)::value + 1;
+        constexpr int cx = dir_cx(ip), cy = dir_cy(ip), cz = dir_cz(ip);
+        int32_t v = o[1 + cy][1 + cz];
+        if (cx != 0) v = __shfl_sync(0xffffffffu, v, (lane + cx) & 31);
+        if (cand && v == p + 1) bits |= 1u << (ip - 1);
+    });
+    return bits;
+}
 __global__ void __launch_bounds__(32 * PART_WARPS) k_beads_links(PartGeom pg, int npart, const double *ypglb, const int32_t *own, Links L) {
     const int p = blockIdx.x, lane = threadIdx.x & 31;
     const double *c = ypglb + 3 * p;
@@ -259,64 +277,68 @@ __global__ void __launch_bounds__(32 * PART_WARPS) k_beads_links(PartGeom pg, in
     const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
     const int zg = iz - pg.globalz;                  // links belong to the GPU that owns the fluid node
     if (zg < 1 || zg > pg.g.lz) return;
-    // the nine rows: y-1, y, y+1 (periodic) x z-1, z, z+1 (ghost planes carry the mask too)
-    long long rowbase[3][3];
+    // the nine rows: y-1, y, y+1 (periodic) x z-1, z, z+1 (ghost planes carry the mask too); 32-bit: d3q19_particles_init
+    // refuses slabs whose populations need 64-bit indices
+    uint32_t rowbase[3][3];
     {
         const int ky[3] = {wrap1(iy - 1, pg.ny), iy, wrap1(iy + 1, pg.ny)};
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int bz = 0; bz < 3; ++bz) rowbase[a][bz] = (long long)pg.g.xp * ((ky[a] - 1) + (long long)pg.g.ly * (zg + bz - 1));
+            for (int bz = 0; bz < 3; ++bz) rowbase[a][bz] = (uint32_t)pg.g.xp * (uint32_t)((ky[a] - 1) + pg.g.ly * (zg + bz - 1));
     }
     const unsigned full = 0xffffffffu;
-    for (int r0 = 0; r0 < b.n[0]; r0 += 30) {        // warp-uniform trip count: the shuffles below need every lane
-        const int jx = b.lo[0] + r0 + lane - 1;      // lanes 0 and 31: the columns next to this piece of the row
-        const bool inside = jx >= 1 && jx <= pg.nx;
-        bool cand = false;
-        if (lane >= 1 && lane <= 30 && r0 + lane - 1 < b.n[0] && inside) {
-            const double d2 = dist2_node(c, jx, jy, jz);
-            cand = !(d2 < r2) && d2 < rshell2;
+    for (int r0 = 0; r0 < b.n[0]; r0 += 60) {        // warp-uniform trip count: the shuffles below need every lane
+        RowPiece pc[2];
+        int32_t o[2][3][3];                          // owners of the nine rows at column jx (-2 beyond a channel wall)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int rr = r0 + 30 * h;
+            pc[h].jx = b.lo[0] + rr + lane - 1;      // lanes 0 and 31: the columns next to this piece of the row
+            pc[h].inside = pc[h].jx >= 1 && pc[h].jx <= pg.nx;
+            pc[h].cand = false;
+            if (lane >= 1 && lane <= 30 && rr + lane - 1 < b.n[0] && pc[h].inside) {
+                const double d2 = dist2_node(c, pc[h].jx, jy, jz);
+                pc[h].cand = !(d2 < r2) && d2 < rshell2;
+            }
+            const bool live = __any_sync(full, pc[h].cand);       // warp-uniform: a piece without candidates reads nothing
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int bz = 0; bz < 3; ++bz) o[h][a][bz] = (live && pc[h].inside) ? own[rowbase[a][bz] + (uint32_t)(pc[h].jx - 1)] : -2;
         }
-        if (!__any_sync(full, cand)) continue;
-        int32_t o[3][3];                             // owners of the nine rows at column jx (-2 beyond a channel wall)
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int bz = 0; bz < 3; ++bz) o[a][bz] = inside ? own[rowbase[a][bz] + (jx - 1)] : -2;
-        if (o[1][1] > 0) cand = false;               // the node itself is solid (this or another particle)
-        unsigned bits = 0u;                           // bit ip-1: the neighbour along ip is owned by p
-        static_for<NPOP - 1>([&](auto ic) {
-            constexpr int ip = decltype(ic)::value + 1;
-            constexpr int cx = dir_cx(ip), cy = dir_cy(ip), cz = dir_cz(ip);
-            int32_t v = o[1 + cy][1 + cz];
-            if (cx != 0) v = __shfl_sync(full, v, (lane + cx) & 31);
-            if (cand && v == p + 1) bits |= 1u << (ip - 1);
-        });
-        // Order inside this piece of the row: DIRECTION first, then x -- consecutive list entries then share their direction
-        // and sit on neighbouring nodes, so the threads of k_beads_ibb that take them read and write neighbouring addresses
-        // of ONE population (its accesses are random 32-byte sectors otherwise, and that kernel is bound by them).
-        const unsigned below = (1u << lane) - 1u;
-        int mine[NPOP - 1];                          // my rank among this piece's links, per direction (valid where my bit is set)
         int total = 0;
-        static_for<NPOP - 1>([&](auto ic) {
-            constexpr int ip = decltype(ic)::value + 1;
-            const unsigned m = __ballot_sync(full, (bits >> (ip - 1)) & 1u);
-            mine[ip - 1] = total + __popc(m & below);
-            total += __popc(m);
-        });
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (o[h][1][1] > 0) pc[h].cand = false;  // the node itself is solid (this or another particle)
+            pc[h].bits = piece_bits(p, lane, pc[h].cand, o[h], 0);
+            total += __popc(pc[h].bits);
+        }
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) total += __shfl_xor_sync(full, total, of);
         if (total == 0) continue;
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(L.count + p, (unsigned long long)total);
         base = __shfl_sync(full, base, 0);
+        // Order inside the row: piece, then DIRECTION, then x -- consecutive list entries share their direction and sit on
+        // neighbouring nodes, so the threads of k_beads_ibb that take them touch neighbouring addresses of ONE population.
+        const unsigned below = (1u << lane) - 1u;
         const long long seg = (long long)p * L.cap;
-        const uint32_t n = (uint32_t)(rowbase[1][1] + (jx - 1));
-        static_for<NPOP - 1>([&](auto ic) {
-            constexpr int ip = decltype(ic)::value + 1;
-            if (bits & (1u << (ip - 1))) {
-                const long long w = (long long)base + mine[ip - 1];
-                if (w < L.cap) { L.node[seg + w] = n; L.dir[seg + w] = ip; }
-            }
-        });
+        int run = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t n = rowbase[1][1] + (uint32_t)(pc[h].jx - 1);
+            const unsigned bits = pc[h].bits;
+            static_for<NPOP - 1>([&](auto ic) {
+                constexpr int ip = decltype(ic)::value + 1;
+                const unsigned m = __ballot_sync(full, (bits >> (ip - 1)) & 1u);
+                if (bits & (1u << (ip - 1))) {
+                    const long long w = (long long)base + run + __popc(m & below);
+                    if (w < L.cap) { L.node[seg + w] = n; L.dir[seg + w] = ip; }
+                }
+                run += __popc(m);
+            });
+        }
     }
 }
 

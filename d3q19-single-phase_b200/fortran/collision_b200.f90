@@ -56,7 +56,7 @@
         integer(c_int32_t) :: math
         integer(c_int32_t) :: ipart
         integer(c_int32_t) :: overlap
-        integer(c_int32_t) :: reserved_i(5)
+        integer(c_int32_t) :: nccl_max_ctas, pf_blocks, halo_timeout_s, halo_split_min, force_idx64   ! tuning knobs, 0 = default
         real(c_double) :: s1, s2, s4, s9, s10, s13, s16
         real(c_double) :: omegepsl, omegepslj, omegxx
         real(c_double) :: rhopart
@@ -210,7 +210,7 @@
       cfg%math = D3Q19_MATH_FAST
       cfg%ipart = merge(1, 0, ipart)
       cfg%overlap = 1
-      cfg%reserved_i = 0
+      cfg%nccl_max_ctas = 0; cfg%pf_blocks = 0; cfg%halo_timeout_s = 0; cfg%halo_split_min = 0; cfg%force_idx64 = 0
       cfg%s1 = s1;  cfg%s2 = s2;  cfg%s4 = s4;  cfg%s9 = s9
       cfg%s10 = s10;  cfg%s13 = s13;  cfg%s16 = s16
       cfg%omegepsl = omegepsl;  cfg%omegepslj = omegepslj;  cfg%omegxx = omegxx

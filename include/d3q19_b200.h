@@ -82,11 +82,11 @@ typedef struct d3q19_config {
     int32_t overlap;          /* 1: boundary/interior split with exchange on a second stream     */
     /* tuning knobs; 0 = the measured default.  (All behaviour switches live here or in d3q19_set_halo_mode: the
      * library reads no environment variable.)                                                      */
-    int32_t nccl_max_ctas;    /* CTAs NCCL may use for the face send/recv (ncclConfig_t.maxCTAs); default 4: the
-                                 faces are a few MB and every NCCL CTA takes an SM from the interior kernel        */
+    int32_t nccl_max_ctas;    /* > 0: cap on the CTAs of NCCL's face send/recv (ncclConfig_t.maxCTAs); default NCCL's own
+                                 choice -- every cap measured was a loss (profiles/r02e_two_gpus.md)                */
     int32_t pf_blocks;        /* in-place steps: L2 software-prefetch distance in thread blocks; default 128, < 0 off */
     int32_t halo_timeout_s;   /* peer-memory halo: seconds a wait for a neighbour's flag may last; default 30      */
-    int32_t halo_split_min;   /* fused peer halo: slabs at least this thick run boundary and interior as two
+    int32_t halo_split_min;   /* D3Q19_HALO_FUSED: slabs at least this thick run boundary and interior as two
                                  launches; default 64                                                               */
     int32_t force_idx64;      /* testing: 64-bit in-slab indices even when a population has < 2^32 elements         */
     /* MRT constants, para.f90:106-143 */

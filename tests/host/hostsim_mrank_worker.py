@@ -56,10 +56,9 @@ def section_fluid(rank, world, comm, chk, ctx):
              ((24, 6, 4 * world), False, "nccl"), ((130, 3, 2 * world + 1), True, "nccl"),
              ((24, 6, 4 * world), True, "peer"), ((33, 5, 3 * world + 1), True, "peer"), ((130, 3, 2 * world + 1), True, "peer"),
              ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split"),
-             ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"), ((130, 3, 2 * world + 1), True, "put"),
-             ((24, 6, 4 * world), True, "put-split"), ((33, 5, 3 * world + 1), True, "put-split")]
+             ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"), ((130, 3, 2 * world + 1), True, "put")]
     if os.environ.get("HOSTSIM_SHORT"):          # the default CPU suite: one uneven case per transport
-        cases = [((33, 5, 3 * world + 1), True, h) for h in ("nccl", "peer", "peer-split", "put", "put-split")] + \
+        cases = [((33, 5, 3 * world + 1), True, h) for h in ("nccl", "peer", "peer-split", "put")] + \
                 [((24, 6, 4 * world), False, "nccl")]
     import time
     for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
@@ -70,7 +69,7 @@ def section_fluid(rank, world, comm, chk, ctx):
             w.set_f(w.get_f() + 1e-4 * np.random.default_rng(7).normal(size=(nz, ny, nx, 19)))
             sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=0, scheme=scheme,
                                   math_mode=capi.MATH_STRICT, nccl_id=comm.new_id(rank), overlap=overlap,
-                                  halo_split_min=3 if halo in ("peer-split", "put-split") else 0)
+                                  halo_split_min=3 if halo == "peer-split" else 0)
             z0, z1 = sim.globalz, sim.globalz + sim.lz
             sim.FORCING()
             if halo.startswith("peer") or halo.startswith("put"):
@@ -154,8 +153,8 @@ def section_particles(rank, world, comm, chk, ctx):
     pos = [[11.7, 1.2, 8.0 * world - 0.9], [8.3, 12.0, 8.1], [15.5, 8.4, 4.2]]      # two of them cut by slab faces
     vel = [[0.010, 0.020, -0.010], [0.0, 0.015, 0.0], [-0.005, 0.0, 0.012]]
     omg = [[1e-3, 0.0, 2e-3], [0.0, -1e-3, 0.0], [5e-4, 5e-4, 0.0]]
-    for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
-        ctx[0] = "particles scheme %d" % scheme
+    for scheme, halo in ((capi.SCHEME_AA, "nccl"), (capi.SCHEME_AB, "nccl"), (capi.SCHEME_AA, "put"), (capi.SCHEME_AB, "put")):
+        ctx[0] = "particles scheme %d faces by %s" % (scheme, halo)
         w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True, ipart=1, **U)
         pt = P.Particles(nx, ny, nz, rad, pos, vel, omg)
         pt.build_mask(); pt.build_links()
@@ -165,6 +164,8 @@ def section_particles(rank, world, comm, chk, ctx):
                               nccl_id=comm.new_id(rank), ipart=True, **U)
         z0, z1 = sim.globalz, sim.globalz + sim.lz
         sim.FORCING()
+        if halo == "put":                              # faces by the copy engines; the refill sources still travel by NCCL
+            chk("peer halo connects", sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put"))
         sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
         sim.particles_init(pos, rad, vel, omg)
         nl = sim.beads_links()
@@ -311,15 +312,15 @@ def section_benchparity(rank, world, comm, chk, ctx):
     for halo in ("nccl", "peer", "put"):
         ctx[0] = "bench parity_check, halo " + halo
 
-        def connect(sim):
+        def connect(sim, particles=False):
             if halo != "nccl":
-                assert sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if halo.startswith("put") else "fused")
+                assert sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if (halo == "put" or particles) else "fused")
 
         res = bench.parity_check(pkg, rank, world, 0, lambda: comm.new_id(rank), connect,
                                  lambda ok: all(comm.allgather(rank, bool(ok))), lambda obj: comm.allgather(rank, obj)[0],
-                                 particles=halo == "nccl")
+                                 particles=halo != "peer")
         chk("parity_check %r" % (res,), res["bit_exact"] is True and len(res["schemes"]) == 2)
-        if halo == "nccl":
+        if halo != "peer":
             chk("particle leg present", res["particles"]["ok"] is True)
 
 
@@ -330,7 +331,7 @@ def section_random(rank, world, comm, chk, ctx):
                                                                                      "hostsim_random_calls.py"))
     rc = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(rc)
-    transports = ["nccl", "peer", "peer-split", "put", "put-split"]
+    transports = ["nccl", "peer", "peer-split", "put"]
     nseeds = int(os.environ.get("HOSTSIM_RANDOM_SEEDS", "7"))
     for seed in range(nseeds):
         for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):

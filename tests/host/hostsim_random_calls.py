@@ -35,9 +35,9 @@ def run_sequence(seed, scheme, log, rank=0, world=1, comm=None, transport="nccl"
     fast = bool(os.environ.get("HOSTSIM_FAST"))
     sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=scheme, math_mode=capi.MATH_FAST if fast else capi.MATH_STRICT,
                           rank=rank, nranks=world, device=0, nccl_id=comm.new_id(rank) if world > 1 else None,
-                          halo_split_min=3 if transport in ("peer-split", "put-split") else 0, **U)
+                          halo_split_min=3 if transport == "peer-split" else 0, **U)
     sim.FORCING()
-    if transport in ("peer", "peer-split", "put", "put-split"):
+    if transport in ("peer", "peer-split", "put"):
         assert sim.connect_halo(lambda b: comm.allgather(rank, bytes(b)), mode="put" if transport.startswith("put") else "fused")
     sl = slice(sim.globalz, sim.globalz + sim.lz)
     sim.upload_f(np.ascontiguousarray(w.get_f()[sl]))

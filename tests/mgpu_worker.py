@@ -58,9 +58,7 @@ def main():
              ((24, 6, 4 * world), True, "peer-split"), ((33, 5, 3 * world + 1), True, "peer-split"),
              # third transport: plain step kernels, the copy engines move the faces into the neighbours' arrays
              ((24, 6, 4 * world), True, "put"), ((33, 5, 3 * world + 1), True, "put"), ((40, 3, 2 * world), True, "put"),
-             ((130, 7, 2 * world + 1), True, "put"),
-             # ... with the boundary planes as a launch of their own (what thick slabs do)
-             ((24, 6, 4 * world), True, "put-split"), ((33, 5, 3 * world + 1), True, "put-split")]
+             ((130, 7, 2 * world + 1), True, "put")]
     only = os.environ.get("MGPU_ONLY", "")          # e.g. "peer": just the peer-memory halo cases (short runs on many GPUs)
     if only:
         cases = [c for c in cases if c[2].startswith(only) or (only == "peer" and c[2].startswith("put"))]
@@ -72,7 +70,7 @@ def main():
             w.set_f(w.get_f() + 1e-4 * rng.normal(size=(nz, ny, nx, 19)))
             sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, rank=rank, nranks=world, device=local, scheme=scheme,
                                   math_mode=capi.MATH_STRICT, nccl_id=new_id(), overlap=overlap,
-                                  halo_split_min=3 if halo in ("peer-split", "put-split") else 0)
+                                  halo_split_min=3 if halo == "peer-split" else 0)
             z0, z1 = sim.globalz, sim.globalz + sim.lz
             sim.FORCING()
             if halo.startswith("peer") or halo.startswith("put"):
@@ -161,8 +159,8 @@ def main():
         pos = [[11.7, 1.2, 8.0 * world - 0.9], [8.3, 12.0, 8.1], [15.5, 8.4, 4.2]]      # two of them cut by slab faces
         vel = [[0.010, 0.020, -0.010], [0.0, 0.015, 0.0], [-0.005, 0.0, 0.012]]
         omg = [[1e-3, 0.0, 2e-3], [0.0, -1e-3, 0.0], [5e-4, 5e-4, 0.0]]
-        for scheme in (capi.SCHEME_AA, capi.SCHEME_AB):
-            ctx[0] = "particles scheme %d" % scheme
+        for scheme, halo in ((capi.SCHEME_AA, "nccl"), (capi.SCHEME_AB, "nccl"), (capi.SCHEME_AA, "put"), (capi.SCHEME_AB, "put")):
+            ctx[0] = "particles scheme %d faces by %s" % (scheme, halo)
             w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True, ipart=1, **U)
             pt = P.Particles(nx, ny, nz, rad, pos, vel, omg)
             pt.build_mask(); pt.build_links()
@@ -172,6 +170,8 @@ def main():
                                   nccl_id=new_id(), ipart=True, **U)
             z0, z1 = sim.globalz, sim.globalz + sim.lz
             sim.FORCING()
+            if halo == "put" and not sim.connect_halo(allgather_bytes, mode="put"):
+                raise RuntimeError("peer-memory halo unavailable between the GPUs of this box: " + ctx[0])
             sim.upload_f(np.ascontiguousarray(w.get_f()[z0:z1]))
             sim.particles_init(pos, rad, vel, omg)
             nl = sim.beads_links()
