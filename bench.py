@@ -99,7 +99,7 @@ def shared_config(nx, ny, nz, nz_local, particles, rad):
     """the `config` object of BOTH arms (the driver compares them): what is computed, not how"""
     return {"workload": workload_name(nx, ny, nz), "per_gpu": "%dx%dx%d z-slab" % (nx, ny, nz_local), "precision": "fp64",
             "particles": ("%d moving spheres of radius %g: links, interpolated bounce-back, momentum-exchange force, "
-                          "lubrication, move, refill every step" % (particles, rad)) if particles else "none"}
+                          "lubrication, move, refill every step; avedensity every 100 steps (main.f90:163-167)" % (particles, rad)) if particles else "none"}
 
 
 def workload_name(nx, ny, nz):
@@ -512,10 +512,16 @@ def main():
     sim, halo = build_sim(args.halo, nccl_id)
     args.scheme = "ab" if sim.counters()["scheme"] == capi.SCHEME_AB else "aa"     # what AUTO resolved to
 
+    pstep = [0]
+
     def advance(n):
         if args.particles > 0:
             for _ in range(n):
                 sim.particle_step(move=True)
+                pstep[0] += 1
+                if pstep[0] % 100 == 0:            # main.f90:163-167: with particles, avedensity every 100 steps
+                    capi.check(sim.L.d3q19_macrovar(sim.h))
+                    capi.check(sim.L.d3q19_avedensity(sim.h, None, None))
         else:
             sim.run_device(n)
 

@@ -876,21 +876,24 @@ static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written
     const Geom &g = h->g;
     const unsigned int epoch = ++h->halo_epoch;
     if (h->put_pending) { CK(cudaStreamWaitEvent(h->sc, h->evX, 0)); h->put_pending = false; }
+    // (b) is waited for by the blocks of the boundary launch themselves (k_step: "the planes next to a face"); a slab of one
+    // or two planes is all boundary
+    StepParams pb = p;
     if (epoch > 1) {
-        k_halo_wait<<<1, 1, 0, h->sc>>>(h->halo_flags, h->halo_flags + 1, epoch - 1u, h->halo_flags + 8, h->halo_timeout_ns);
-        CK(cudaGetLastError());
+        pb.halo.wait_lo = h->halo_flags; pb.halo.wait_hi = h->halo_flags + 1;
+        pb.halo.epoch = epoch; pb.halo.err = h->halo_flags + 8; pb.halo.timeout_ns = h->halo_timeout_ns;
     }
     trace_mark(h, 0, h->sc);
     // (One launch for the whole slab with the boundary planes first in block order and a device-side "planes done" signal
     //  for the copy stream was measured as well: 0.216 ms per step against 0.206 ms for the two launches below on 32-plane
     //  slabs -- the instantiation that counts blocks is slower than the plain one.  Removed.  profiles/r02e_two_gpus.md)
     if (lz > 2) {
-        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, 2, h->sc, lz - 1)));   // planes 1 and lz in one launch
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, pb, 1, 2, h->sc, lz - 1)));  // planes 1 and lz in one launch
         CK(cudaEventRecord(h->evB, h->sc));
         trace_mark(h, 1, h->sc);
         RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 2, lz - 2, h->sc)));
     } else {
-        RK_((launch_step_range<SK, STRICT, GENERIC>(h, p, 1, lz, h->sc)));
+        RK_((launch_step_range<SK, STRICT, GENERIC>(h, pb, 1, lz, h->sc)));
         CK(cudaEventRecord(h->evB, h->sc));
         trace_mark(h, 1, h->sc);
     }
@@ -937,7 +940,7 @@ static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written
     trace_mark(h, 3, h->sx);
     trace_next(h);
     h->put_pending = true;
-    h->n_other_kernels += 1 + (epoch > 1 ? 1 : 0);
+    h->n_other_kernels += 1;
     h->n_copies += 10;
     if (ab) {                             // the neighbours swap their arrays in lockstep
         for (int d = 0; d < 2; ++d) { double *t = h->peer_A[d]; h->peer_A[d] = h->peer_B[d]; h->peer_B[d] = t; }

@@ -60,6 +60,9 @@ constexpr int BLOCK_X = D3Q_BLOCK_X;
 #ifndef D3Q_PF_LEAN
 #define D3Q_PF_LEAN 1
 #endif
+#ifndef D3Q_PLAIN_WAIT           // 1: the plain step kernel can wait for the neighbours' flags itself (copy-engine transport)
+#define D3Q_PLAIN_WAIT 1
+#endif
 #ifndef D3Q_ADDR                 // 0: wall handled by an offset select; 1: by a predicated second access
 #define D3Q_ADDR 0
 #endif
@@ -327,16 +330,17 @@ k_step(const __grid_constant__ StepParams p) {
     double rhoerr = 0.0;
     const int zg_blk = HALO ? (blockIdx.z == 0 ? 1 : (blockIdx.z == 1 ? g.lz : (int)blockIdx.z))
                             : p.z0 + (int)blockIdx.z * p.zstride;
-    if (HALO) {
-        // the planes next to a face read what the neighbour's previous step stored here
-        if (zg_blk == 1 || zg_blk == g.lz) {
-            if (threadIdx.x == 0) {
-                const volatile unsigned int *fl = (zg_blk == 1) ? p.halo.wait_lo : p.halo.wait_hi;
-                halo_spin(fl, p.halo.epoch - 1u, p.halo.err, p.halo.timeout_ns);
-                __threadfence_system();
-            }
-            __syncthreads();
+    // The planes next to a face read what the neighbour's previous step put here: their blocks wait for the neighbour's flag
+    // (in lock step it arrived a whole interior sweep ago: one volatile load).  HALO: part of the fused transport.  Plain
+    // instantiation: the boundary launch of the copy-engine transport passes the two flags (interior launches and single-GPU
+    // runs pass nullptr) -- a one-thread wait kernel in front of every step would sit on the critical path instead.
+    if (HALO ? (zg_blk == 1 || zg_blk == g.lz) : (D3Q_PLAIN_WAIT && p.halo.wait_lo != nullptr)) {
+        if (threadIdx.x == 0) {
+            const volatile unsigned int *fl = (zg_blk == 1) ? p.halo.wait_lo : p.halo.wait_hi;
+            halo_spin(fl, p.halo.epoch - 1u, p.halo.err, p.halo.timeout_ns);
+            __threadfence_system();
         }
+        __syncthreads();
     }
     if (x < g.lx) {
         const NodeIdx<IDX> k = make_node<IDX>(g, x, blockIdx.y, zg_blk);
