@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(32 * PART_WARPS) k_beads_cover(PartGeom pg, in
 // ---- beads_links, part 2: boundary links ------------------------------------------------------------
 // A link = (fluid node of this slab, direction whose neighbour is owned by particle p).  Every particle has its own
 // SEGMENT of `cap` entries in the list and its own counter: warps append their row's links with one atomic per 32
-// nodes, so inside a segment the order between rows depends on the run (inside a row it is x, then direction) -- the
+// nodes, so inside a segment the order between rows depends on the run (inside a pass it is x, then direction) -- the
 // list is a set.  Consumers do not depend on the order (k_beads_ibb: one thread per link, every link writes its own
 // slot; all links of a block belong to one particle, so the force is reduced per warp before it is added);
 // d3q19_get_links hands the segments out concatenated and tests compare after a canonical sort (SURVEY.md appendix B:
@@ -237,28 +237,15 @@ __device__ __forceinline__ void link_node_coords(const PartGeom &pg, const doubl
     jx = x + 1; jy = b.lo[1] + ry; jz = b.lo[2] + rz;
 }
 
-// One warp per box row.  Lanes 1..30 are 30 consecutive nodes of the row, lanes 0 and 31 their x-neighbours: the nine
-// mask rows around the row (y-1..y+1, z-1..z+1) are read as nine coalesced pieces and the 18 neighbour owners of a node come
-// from its own registers (c_x = 0) or from the adjacent lane (shuffle).  The kernel is bound by the LATENCY of its two
-// dependent round trips (mask loads, then the atomic that reserves list space): two pieces of the row are in flight
-// together and share one atomic.
-struct RowPiece {
-    int jx;
-    bool inside, cand;
-    unsigned bits;
-};
-template <class F>
-__device__ __forceinline__ unsigned piece_bits(int p, int lane, bool cand, const int32_t (&o)[3][3], F) {
-    unsigned bits = 0u;                               // bit ip-1: the neighbour along ip is owned by p
-    static_for<NPOP - 1>([&](auto ic) {
-        constexpr int ip = decltype(ic)::value + 1;
-        constexpr int cx = dir_cx(ip), cy = dir_cy(ip), cz = dir_cz(ip);
-        int32_t v = o[1 + cy][1 + cz];
-        if (cx != 0) v = __shfl_sync(0xffffffffu, v, (lane + cx) & 31);
-        if (cand && v == p + 1) bits |= 1u << (ip - 1);
-    });
-    return bits;
-}
+// One warp per box row.  The link nodes of a row sit in two short runs of columns where the row enters and leaves the
+// shell rad <= d < rad + 1.5 (one run where it only grazes it); each half of the warp takes a 16-column window over one
+// run -- 14 nodes and their two x-neighbours -- so that one pass usually covers the row.  The nine mask rows around the row
+// (y-1..y+1, z-1..z+1) are read as coalesced pieces and the 18 neighbour owners of a node come from its own registers
+// (c_x = 0) or from the adjacent lane (shuffle); list space is reserved with one atomic per pass.  The kernel is bound by
+// instruction issue (ncu, r02f: 105 M warp instructions, 74 % issue slots busy, 130 us for 100 spheres of radius 15 with
+// 30-column pieces, two per row, and a direction-major order that cost 36 votes per row and bought k_beads_ibb nothing).
+__device__ __forceinline__ int wrap_near(int j, int n) { return j < 1 ? j + n : (j > n ? j - n : j); }     // |j - [1,n]| < n
+
 __global__ void __launch_bounds__(32 * PART_WARPS) k_beads_links(PartGeom pg, int npart, const double *ypglb, const int32_t *own, Links L) {
     const int p = blockIdx.x, lane = threadIdx.x & 31;
     const double *c = ypglb + 3 * p;
@@ -270,74 +257,75 @@ __global__ void __launch_bounds__(32 * PART_WARPS) k_beads_links(PartGeom pg, in
     // or a lower-numbered particle, and a neighbour owned by this particle lies within rad, so the node itself within
     // rad + |c_i| <= rad + sqrt(2) < rad + 1.5.  Rows outside the shell's (y,z) shadow are dropped here.
     const double rshell2 = (pg.rad + 1.5) * (pg.rad + 1.5);
-    {
-        const double dy = ((double)jy - 0.5) - c[1], dz = ((double)jz - 0.5) - c[2];
-        if (dy * dy + dz * dz > rshell2) return;
-    }
-    const int iy = wrap1(jy, pg.ny), iz = wrap1(jz, pg.nz);
+    const double dy = ((double)jy - 0.5) - c[1], dz = ((double)jz - 0.5) - c[2];
+    const double rho2 = dy * dy + dz * dz;
+    if (rho2 > rshell2) return;
+    const int iy = wrap_near(jy, pg.ny), iz = wrap_near(jz, pg.nz);        // a box is smaller than the period
     const int zg = iz - pg.globalz;                  // links belong to the GPU that owns the fluid node
     if (zg < 1 || zg > pg.g.lz) return;
+    // columns that can hold a candidate: |x - 0.5 - c_x| in [a_in, a_out); one column of slack on either side of a run,
+    // the exact test below stays the authority
+    const double a_out = sqrt(rshell2 - rho2), a_in = rho2 < r2 ? sqrt(r2 - rho2) : 0.0;
+    int xa0 = (int)floor(c[0] + 0.5 - a_out) - 1, xa1 = (int)ceil(c[0] + 0.5 - a_in) + 1;      // where the row enters
+    int xb0 = (int)floor(c[0] + 0.5 + a_in) - 1, xb1 = (int)ceil(c[0] + 0.5 + a_out) + 1;      // where it leaves
+    if (xb0 <= xa1 + 1) { xa1 = xb1; xb0 = 1; xb1 = 0; }                     // one run (the row grazes the shell)
+    if (xa0 < b.lo[0]) xa0 = b.lo[0];
+    if (xb1 > b.lo[0] + b.n[0] - 1) xb1 = b.lo[0] + b.n[0] - 1;
+    if (xa1 > b.lo[0] + b.n[0] - 1) xa1 = b.lo[0] + b.n[0] - 1;
     // the nine rows: y-1, y, y+1 (periodic) x z-1, z, z+1 (ghost planes carry the mask too); 32-bit: d3q19_particles_init
     // refuses slabs whose populations need 64-bit indices
     uint32_t rowbase[3][3];
     {
-        const int ky[3] = {wrap1(iy - 1, pg.ny), iy, wrap1(iy + 1, pg.ny)};
+        const int ky[3] = {wrap_near(iy - 1, pg.ny), iy, wrap_near(iy + 1, pg.ny)};
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int bz = 0; bz < 3; ++bz) rowbase[a][bz] = (uint32_t)pg.g.xp * (uint32_t)((ky[a] - 1) + pg.g.ly * (zg + bz - 1));
     }
     const unsigned full = 0xffffffffu;
-    for (int r0 = 0; r0 < b.n[0]; r0 += 60) {        // warp-uniform trip count: the shuffles below need every lane
-        RowPiece pc[2];
-        int32_t o[2][3][3];                          // owners of the nine rows at column jx (-2 beyond a channel wall)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int rr = r0 + 30 * h;
-            pc[h].jx = b.lo[0] + rr + lane - 1;      // lanes 0 and 31: the columns next to this piece of the row
-            pc[h].inside = pc[h].jx >= 1 && pc[h].jx <= pg.nx;
-            pc[h].cand = false;
-            if (lane >= 1 && lane <= 30 && rr + lane - 1 < b.n[0] && pc[h].inside) {
-                const double d2 = dist2_node(c, pc[h].jx, jy, jz);
-                pc[h].cand = !(d2 < r2) && d2 < rshell2;
-            }
-            const bool live = __any_sync(full, pc[h].cand);       // warp-uniform: a piece without candidates reads nothing
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int bz = 0; bz < 3; ++bz) o[h][a][bz] = (live && pc[h].inside) ? own[rowbase[a][bz] + (uint32_t)(pc[h].jx - 1)] : -2;
+    const int half = lane >> 4, hl = lane & 15;      // lanes 0-15: the first run, 16-31: the second; hl 0 and 15: x-neighbours
+    const long long seg = (long long)p * L.cap;
+    for (int k = 0; xa0 + 14 * k <= xa1 || xb0 + 14 * k <= xb1; ++k) {       // warp-uniform trip count (the shuffles need every lane)
+        const int x0 = (half ? xb0 : xa0) + 14 * k, x1 = half ? xb1 : xa1;
+        const int jx = x0 + hl - 1;
+        const bool inside = jx >= 1 && jx <= pg.nx;
+        bool cand = false;
+        if (hl >= 1 && hl <= 14 && jx <= x1 && inside) {
+            const double d2 = dist2_node(c, jx, jy, jz);
+            cand = !(d2 < r2) && d2 < rshell2;
         }
-        int total = 0;
+        if (!__any_sync(full, cand)) continue;
+        int32_t o[3][3];                             // owners of the nine rows at column jx (-2 beyond a channel wall)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (o[h][1][1] > 0) pc[h].cand = false;  // the node itself is solid (this or another particle)
-            pc[h].bits = piece_bits(p, lane, pc[h].cand, o[h], 0);
-            total += __popc(pc[h].bits);
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int bz = 0; bz < 3; ++bz) o[a][bz] = inside ? own[rowbase[a][bz] + (uint32_t)(jx - 1)] : -2;
+        if (o[1][1] > 0) cand = false;               // the node itself is solid (this or another particle)
+        unsigned bits = 0u;                           // bit ip-1: the neighbour along ip is owned by p
+        static_for<NPOP - 1>([&](auto ic) {
+            constexpr int ip = decltype(ic)::value + 1;
+            constexpr int cx = dir_cx(ip), cy = dir_cy(ip), cz = dir_cz(ip);
+            int32_t v = o[1 + cy][1 + cz];
+            if (cx != 0) v = __shfl_sync(full, v, (lane + cx) & 31);         // (never across the halves: hl 0 and 15 are no candidates)
+            if (cand && v == p + 1) bits |= 1u << (ip - 1);
+        });
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int of = 1; of < 32; of <<= 1) {
+            const int t = __shfl_up_sync(full, incl, of);
+            if (lane >= of) incl += t;
         }
-#pragma unroll
-        for (int of = 16; of > 0; of >>= 1) total += __shfl_xor_sync(full, total, of);
+        const int total = __shfl_sync(full, incl, 31);
         if (total == 0) continue;
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(L.count + p, (unsigned long long)total);
-        base = __shfl_sync(full, base, 0);
-        // Order inside the row: piece, then DIRECTION, then x -- consecutive list entries share their direction and sit on
-        // neighbouring nodes, so the threads of k_beads_ibb that take them touch neighbouring addresses of ONE population.
-        const unsigned below = (1u << lane) - 1u;
-        const long long seg = (long long)p * L.cap;
-        int run = 0;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint32_t n = rowbase[1][1] + (uint32_t)(pc[h].jx - 1);
-            const unsigned bits = pc[h].bits;
-            static_for<NPOP - 1>([&](auto ic) {
-                constexpr int ip = decltype(ic)::value + 1;
-                const unsigned m = __ballot_sync(full, (bits >> (ip - 1)) & 1u);
-                if (bits & (1u << (ip - 1))) {
-                    const long long w = (long long)base + run + __popc(m & below);
-                    if (w < L.cap) { L.node[seg + w] = n; L.dir[seg + w] = ip; }
-                }
-                run += __popc(m);
-            });
+        if (lane == 31) base = atomicAdd(L.count + p, (unsigned long long)total);
+        base = __shfl_sync(full, base, 31);
+        long long w = (long long)base + incl - cnt;
+        const uint32_t n = rowbase[1][1] + (uint32_t)(jx - 1);
+        for (unsigned rest = bits; rest; rest &= rest - 1) {               // the set bits, lowest direction first
+            if (w < L.cap) { L.node[seg + w] = n; L.dir[seg + w] = __ffs(rest); }
+            ++w;
         }
     }
 }
