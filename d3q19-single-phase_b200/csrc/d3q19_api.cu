@@ -117,6 +117,8 @@ struct d3q19_handle {
     unsigned long long *pcnt = nullptr;          // device counters: [1] refill list, [2] refilled nodes (the link counts live in links.count)
     int part_rows = 0;                           // rows of the largest bounding box (grid of the sweep kernels)
     double *fill_halo = nullptr;                 // z-slab refill: [send up][send dn][ghost lo][ghost hi], 19 x plane each
+    cudaEvent_t evP = nullptr, evF = nullptr;    // refill source exchange on sx next to the bookkeeping kernels on sc
+    bool fill_xchg_pending = false;
     double amp = 0, aip = 0;
     // halo in peer memory (cudaIpc): [0] = lower neighbour (mzm), [1] = upper neighbour (mzp)
     bool halo_on = false;
@@ -301,7 +303,7 @@ extern "C" int d3q19_destroy(d3q19_handle *h) {
                     h->wp, h->omgp, h->send_up, h->send_dn, h->recv_lo, h->recv_hi, h->stage[0], h->stage[1],
                     h->scal, h->red_d, h->red_c, h->prof_partial, h->prof_out, h->vort, h->vort_halo, h->diag_partial, h->diag_red, h->sij2};
     for (void *p : ptrs) if (p) cudaFree(p);
-    cudaEvent_t evs[] = {h->evB, h->evX, h->t0, h->t1, h->evC[0], h->evC[1], h->evS[0], h->evS[1]};
+    cudaEvent_t evs[] = {h->evP, h->evF, h->evB, h->evX, h->t0, h->t1, h->evC[0], h->evC[1], h->evS[0], h->evS[1]};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     if (h->sc) cudaStreamDestroy(h->sc);
     if (h->sx) cudaStreamDestroy(h->sx);
@@ -1458,6 +1460,36 @@ extern "C" int d3q19_beads_move(d3q19_handle *h) {
     return lubmove(h, 0, 1);
 }
 
+// Refill sources across a slab face: all 19 canonical populations of the neighbours' planes next to the faces (the ghost
+// planes of the population array carry 5), so that the refill does not depend on the decomposition.  One launch gathers my
+// two boundary planes, one NCCL group sends them to the neighbours (2 x 19 x plane fp64 per step and GPU).  `s`: the
+// compute stream (stand-alone d3q19_beads_filling) or the second stream (d3q19_particle_step: the populations do not change
+// between the bounce-back and the refill, so the exchange runs next to lubrication / move / mask / links).
+static int fill_exchange(d3q19_handle *h, cudaStream_t s) {
+    const Geom &g = h->g;
+    const size_t cnt = (size_t)NPOP * g.plane;
+    if (!h->fill_halo) CK(cudaMalloc(&h->fill_halo, 4 * cnt * sizeof(double)));
+    double *send_up = h->fill_halo, *send_dn = send_up + cnt, *ghost_lo = send_dn + cnt, *ghost_hi = ghost_lo + cnt;
+    const dim3 gp = grid_nodes(h, 2);             // blockIdx.z: 0 -> plane lz into send_up, 1 -> plane 1 into send_dn
+    switch (read_kind(h)) {
+    case READ_DIRECT: k_plane_gather<READ_DIRECT><<<gp, BLOCK_X, 0, s>>>(g, h->A, send_up, g.lz, send_dn, 1); break;
+    case READ_PULL_NAT: k_plane_gather<READ_PULL_NAT><<<gp, BLOCK_X, 0, s>>>(g, h->A, send_up, g.lz, send_dn, 1); break;
+    default: k_plane_gather<READ_PULL_SWAP><<<gp, BLOCK_X, 0, s>>>(g, h->A, send_up, g.lz, send_dn, 1); break;
+    }
+    CK(cudaGetLastError());
+    const int up = (h->cfg.rank + 1) % h->cfg.nranks, dn = (h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks;
+    NcclApi &n = nccl_api();
+    NK(n.GroupStart());
+    NK(n.Send(send_up, cnt, NCCL_FLOAT64, up, h->comm, s));
+    NK(n.Send(send_dn, cnt, NCCL_FLOAT64, dn, h->comm, s));
+    NK(n.Recv(ghost_lo, cnt, NCCL_FLOAT64, dn, h->comm, s));
+    NK(n.Recv(ghost_hi, cnt, NCCL_FLOAT64, up, h->comm, s));
+    NK(n.GroupEnd());
+    h->n_other_kernels += 1;
+    h->n_nccl += 4;
+    return 0;
+}
+
 // beads_filling: populations of the nodes the last move uncovered (needs the rebuilt mask)
 extern "C" int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled) {
     CK(cudaSetDevice(h->cfg.device));
@@ -1469,30 +1501,12 @@ extern "C" int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled) {
     P.ypglb = h->ypglb; P.wp = h->wp; P.omgp = h->omgp; P.nfilled = h->pcnt + 2;
     P.ghost_lo = P.ghost_hi = nullptr;
     if (h->cfg.nranks > 1) {
-        // source nodes across a slab face: all 19 canonical populations of the neighbours' planes next to the faces
-        // (the ghost planes of the population array carry 5), so that the refill does not depend on the decomposition
-        const Geom &g = h->g;
-        const size_t cnt = (size_t)NPOP * g.plane;
-        if (!h->fill_halo) CK(cudaMalloc(&h->fill_halo, 4 * cnt * sizeof(double)));
-        double *send_up = h->fill_halo, *send_dn = send_up + cnt, *ghost_lo = send_dn + cnt, *ghost_hi = ghost_lo + cnt;
-        const dim3 gp = grid_nodes(h, 2);             // blockIdx.z: 0 -> plane lz into send_up, 1 -> plane 1 into send_dn
-        switch (read_kind(h)) {
-        case READ_DIRECT: k_plane_gather<READ_DIRECT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz, send_dn, 1); break;
-        case READ_PULL_NAT: k_plane_gather<READ_PULL_NAT><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz, send_dn, 1); break;
-        default: k_plane_gather<READ_PULL_SWAP><<<gp, BLOCK_X, 0, h->sc>>>(g, h->A, send_up, g.lz, send_dn, 1); break;
-        }
-        CK(cudaGetLastError());
-        const int up = (h->cfg.rank + 1) % h->cfg.nranks, dn = (h->cfg.rank + h->cfg.nranks - 1) % h->cfg.nranks;
-        NcclApi &n = nccl_api();
-        NK(n.GroupStart());
-        NK(n.Send(send_up, cnt, NCCL_FLOAT64, up, h->comm, h->sc));
-        NK(n.Send(send_dn, cnt, NCCL_FLOAT64, dn, h->comm, h->sc));
-        NK(n.Recv(ghost_lo, cnt, NCCL_FLOAT64, dn, h->comm, h->sc));
-        NK(n.Recv(ghost_hi, cnt, NCCL_FLOAT64, up, h->comm, h->sc));
-        NK(n.GroupEnd());
-        h->n_other_kernels += 1;
-        h->n_nccl += 4;
-        P.ghost_lo = ghost_lo; P.ghost_hi = ghost_hi;
+        // source nodes across a slab face: the neighbours' boundary planes (fill_exchange); d3q19_particle_step started the
+        // exchange on the second stream right after the bounce-back, next to the bookkeeping kernels
+        if (h->fill_xchg_pending) { CK(cudaStreamWaitEvent(h->sc, h->evF, 0)); h->fill_xchg_pending = false; }
+        else RK_(fill_exchange(h, h->sc));
+        const size_t cnt = (size_t)NPOP * h->g.plane;
+        P.ghost_lo = h->fill_halo + 2 * cnt; P.ghost_hi = h->fill_halo + 3 * cnt;
     }
     // the list length is on the device: a fixed grid strides over it (one move uncovers a thin layer: a few dozen nodes per particle)
     const unsigned nb = (unsigned)(h->fill.cap < 148 * 8 * 128 ? (h->fill.cap + 127) / 128 : 148 * 8);
@@ -1523,6 +1537,15 @@ extern "C" int d3q19_particle_step(d3q19_handle *h, int32_t move) {
     RK_(collide_stream_impl(h, D3Q19_MACRO_MAIN, nullptr));       // fluid nodes only (solid nodes skipped)
     RK_(d3q19_beads_collision(h));
     if (move) {
+        if (h->cfg.nranks > 1) {
+            // the refill's sources travel while the particles move and the mask and the links are rebuilt
+            if (!h->evP) { CK(cudaEventCreateWithFlags(&h->evP, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->evF, cudaEventDisableTiming)); }
+            CK(cudaEventRecord(h->evP, h->sc));                     // after the bounce-back (which waited for the faces)
+            CK(cudaStreamWaitEvent(h->sx, h->evP, 0));
+            RK_(fill_exchange(h, h->sx));
+            CK(cudaEventRecord(h->evF, h->sx));
+            h->fill_xchg_pending = true;
+        }
         RK_(lubmove(h, 1, 1));                                      // beads_lubforce + beads_move
         RK_(d3q19_beads_links(h, nullptr));
         RK_(d3q19_beads_filling(h, nullptr));
