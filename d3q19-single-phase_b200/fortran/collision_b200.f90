@@ -153,6 +153,11 @@
           type(c_ptr), value :: h
           integer(c_signed_char), intent(out) :: blob(256)
         end function
+        integer(c_int) function d3q19_set_halo_mode(h, mode) bind(c, name='d3q19_set_halo_mode')
+          import :: c_int, c_ptr, c_int32_t
+          type(c_ptr), value :: h
+          integer(c_int32_t), value :: mode
+        end function
         integer(c_int) function d3q19_ipc_connect(h, blobs) bind(c, name='d3q19_ipc_connect')
           import :: c_int, c_ptr, c_signed_char
           type(c_ptr), value :: h
@@ -192,7 +197,6 @@
       integer :: ierr_
       integer(c_signed_char) :: ipc_mine(256)
       integer(c_signed_char), allocatable :: ipc_all(:)
-      character(len=16) :: halo_env
       if (bound) return
       if (nprocY /= 1) then
         if (myid == 0) write(*,*) 'd3q19_b200: set nprocY = 1 in para.f90:219 (z-slab decomposition, one rank per GPU)'
@@ -223,15 +227,14 @@
         call MPI_BCAST(cfg%nccl_id, 128, MPI_BYTE, 0, MPI_COMM_WORLD, ierr_)
       endif
       call d3q19_b200_check(d3q19_create(cfg, handle), 'd3q19_create')
-      ! The z faces travel by NCCL send/recv on a second stream (the library's default; equal or faster than
-      ! the alternative in every measured configuration, profiles/r01d_halo_transports.md).  D3Q19_HALO=peer
-      ! selects the halo in NVLink peer memory instead: every rank exports its cudaIpc handles and
-      ! MPI_ALLGATHER distributes them -- the bootstrap of what then replaces MPI_ISEND/IRECV/WAITALL
-      ! (collision.f90:349-356) inside the step kernel.  d3q19_ipc_connect returns 2 when all ranks agreed
-      ! that peer memory is unavailable; the halo then stays on NCCL.
-      call get_environment_variable('D3Q19_HALO', halo_env, status=ierr_)
-      if (ierr_ == 0 .and. trim(halo_env) == 'peer' .and. nprocZ > 1 .and. .not. ipart .and. lz >= 2) then
+      ! The z faces travel through NVLink peer memory, moved by the copy engines (D3Q19_HALO_PUT = 1: the fastest
+      ! transport in every configuration measured, profiles/r02e_two_gpus.md, r02g_eight_gpus.md): every rank exports
+      ! its cudaIpc handles and MPI_ALLGATHER distributes them -- the bootstrap of what then replaces
+      ! MPI_ISEND/IRECV/WAITALL (collision.f90:349-356).  d3q19_ipc_connect returns 2 when all ranks agreed that peer
+      ! memory cannot be mapped; the faces then travel by NCCL send/recv.
+      if (nprocZ > 1 .and. lz >= 2) then
         allocate(ipc_all(256*nproc))
+        call d3q19_b200_check(d3q19_set_halo_mode(handle, 1_c_int32_t), 'd3q19_set_halo_mode')
         call d3q19_b200_check(d3q19_ipc_export(handle, ipc_mine), 'd3q19_ipc_export')
         call MPI_ALLGATHER(ipc_mine, 256, MPI_BYTE, ipc_all, 256, MPI_BYTE, MPI_COMM_WORLD, ierr_)
         ierr_ = d3q19_ipc_connect(handle, ipc_all)
