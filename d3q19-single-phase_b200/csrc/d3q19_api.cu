@@ -1441,7 +1441,15 @@ static int lubmove(d3q19_handle *h, int do_lub, int do_move) {
     MoveParams M = {h->amp, h->aip, h->pp.gforce[0], h->pp.gforce[1], h->pp.gforce[2], h->fHIp, h->torqp, h->flubp,
                     h->forcepp, h->torqpp, h->ypglb, h->wp, h->omgp, h->thetap};
     const int nt = h->npart < 32 ? h->npart * 32 : 1024;          // a warp per particle for the partner loop
-    k_beads_lubmove<<<1, nt, 0, h->sc>>>(part_geom(h), h->npart, h->ypglb, lp, h->flubp, M, do_lub, do_move);
+    if (do_lub && do_move && h->npart > 256) {
+        // many particles: the O(npart^2) partner loop on several blocks, then the move as a launch of its own
+        const int nb = (h->npart + 31) / 32;
+        k_beads_lubmove<<<nb, 1024, 0, h->sc>>>(part_geom(h), h->npart, h->ypglb, lp, h->flubp, M, 1, 0);
+        k_beads_lubmove<<<1, 1024, 0, h->sc>>>(part_geom(h), h->npart, h->ypglb, lp, h->flubp, M, 0, 1);
+        h->n_other_kernels++;
+    } else {
+        k_beads_lubmove<<<1, nt, 0, h->sc>>>(part_geom(h), h->npart, h->ypglb, lp, h->flubp, M, do_lub, do_move);
+    }
     CK(cudaGetLastError());
     h->n_other_kernels++;
     if (do_move) h->links_valid = false;

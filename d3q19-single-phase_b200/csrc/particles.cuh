@@ -658,8 +658,10 @@ __device__ __forceinline__ void move_one(const PartGeom &pg, const MoveParams &M
 // from the positions before anybody moves, then the barrier, then the rigid-body update
 __global__ void __launch_bounds__(1024) k_beads_lubmove(PartGeom pg, int npart, const double *ypglb, LubParams lp, double *flubp,
                                                         MoveParams M, int do_lub, int do_move) {
+    // (do_lub without do_move may be launched on several blocks: the partner loop is O(npart^2))
     if (do_lub)
-        for (int i = threadIdx.x >> 5; i < npart; i += blockDim.x >> 5) lubforce_warp(pg, npart, ypglb, lp, flubp, i);
+        for (int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < npart; i += (int)((gridDim.x * blockDim.x) >> 5))
+            lubforce_warp(pg, npart, ypglb, lp, flubp, i);
     __syncthreads();
     if (do_move)
         for (int p = threadIdx.x; p < npart; p += blockDim.x) move_one(pg, M, p);

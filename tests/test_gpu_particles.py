@@ -171,3 +171,39 @@ def test_stokes_drag_between_two_walls_matches_faxen():
     assert abs(f[0]) < 1e-3 * abs(f[1]) and abs(f[2]) < 1e-3 * abs(f[1])   # by symmetry
     assert abs(-f[1] / faxen - 1.0) < 0.05, (-f[1], faxen)
     sim.close()
+
+
+def test_many_particles_take_the_split_lubrication_path():
+    # more than 256 particles: the O(npart^2) repulsion loop runs on several blocks and the move is a launch of its own
+    # (d3q19_api.cu lubmove); overlapping spheres so that the repulsion is not zero; positions and velocities against the
+    # CPU checker after three moving steps
+    nx, ny, nz, rad, n = 24, 48, 48, 1.6, 300
+    rng = np.random.default_rng(3)
+    pos = np.column_stack([rng.uniform(4, nx - 4, n), rng.uniform(0, ny, n), rng.uniform(0, nz, n)])
+    vel = 1e-3 * rng.normal(size=(n, 3))
+    omg = 1e-4 * rng.normal(size=(n, 3))
+    Um = dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx)
+    w, p = orc.make_initial_state(nx, ny, nz, laminar=False, noise=True, ipart=1, **Um)
+    sim = pkg.ChannelFlow(nx, ny, nz, laminar=False, scheme=capi.SCHEME_AB, ipart=True, **Um)
+    sim.f[...] = w.get_f()
+    sim.FORCING()
+    sim.upload_f()
+    pt = P.Particles(nx, ny, nz, rad, pos, vel, omg, fscale=1e-5)
+    sim.particles_init(pos, rad, vel, omg, fscale=1e-5)
+    pt.build_mask(); pt.build_links()
+    set_oracle_mask(w, pt)
+    w.macrovar()
+    for step in range(3):
+        w.collision_MRT()
+        f = w.get_f(); pt.ibb(f)
+        pt.lubforce(); pt.move()
+        pt.build_mask(); pt.build_links()
+        pt.refill(f)
+        w.set_f(f); set_oracle_mask(w, pt); w.macrovar()
+        sim.particle_step(move=True)
+        g = sim.get_particles()
+        assert np.max(np.abs(pt.flubp)) > 0                                   # the repulsion is at work
+        assert np.max(np.abs(g["ypglb"] - pt.ypglb)) < 1e-10, step
+        assert np.max(np.abs(g["wp"] - pt.wp)) < 1e-10 * max(np.max(np.abs(pt.wp)), 1e-30) + 1e-16, step
+        assert np.array_equal(sim.get_mask(), pt.own), step
+    sim.close(); w.close()
