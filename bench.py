@@ -10,19 +10,28 @@ exchange) over the whole channel.  At N=1 the workload is BASELINE.json configs[
 default is weak scaling with one 512x256x256 slab per GPU (global nz = 256 N); `--scaling
 strong` keeps the global 512x256x256 (configs[2]).  One JSON line is printed by rank 0.
 
+Other workloads: `--workload c4` = configs[3] (1024x1024x944 per GPU, 150 GB of populations, in place, initialised on the
+device), `--particles N` = configs[4] (N moving spheres: links, interpolated bounce-back, force, lubrication, move, refill every
+step, avedensity every 100 steps).  With N > 1 the faces travel by the NVLink copy engines (`--halo put`; NCCL send/recv when
+peer memory cannot be mapped).
+
 value      device-timed: populations resident in HBM, K steps between CUDA events on the
            stream the kernels run on, max over ranks.
 e2e        the same K steps through the reference-facing interface with HOST buffers inside
            the timed region: upload of f(0:18,lx,ly,lz) from pinned host memory, then per step
            collision_MRT + macrovar (the shim's download policy: rho,u come back every
            nflowout/ndiag steps and after the last step) + a `probe` read-back of the centre
-           node (32 B D2H) every step.
+           node (32 B D2H) every step.  `upload_s` / `upload_gbs_per_gpu` / `total_s` say where the time goes.
 roofline   304 B per node update (19 fp64 in + 19 fp64 out) / mean step-kernel time, against
-           MEASURED_PEAKS.json's hbm_gbs.
-cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/, built -O3
-           -march=x86-64-v3), one thread per emulated MPI rank on all host cores, on a bounded
-           sample of the same workload.  (The Fortran reference itself cannot be built here:
-           no Fortran compiler, no MPI.)
+           MEASURED_PEAKS.json's hbm_gbs; `traffic` = DRAM bytes per launch from the committed ncu capture, reported only
+           while the kernel sources are those the capture was taken on (profiles/traffic.json).
+parity_check  BEFORE the timed region, on this job's ranks and face transport: a committed golden vector of the reference
+           (16 z planes, 9 steps) must come back bit for bit in both storage schemes; with N > 1 a moving-particle case on the
+           N slabs must agree with one domain.  A mismatch ends the run non-zero with nothing timed.
+clocks     SM clock, power and throttle reasons sampled in process through NVML every 5 ms during the timed region.
+cpu_baseline / --impl reference: the reference's own hot path on all host cores, one thread per emulated MPI rank, on a bounded
+           sample of the same workload: oracle/_ref/libref_fast.so (the Fortran machine-translated to C, kind "reference"), else
+           the hand restatement (kind "port").  (The Fortran itself cannot be built here: no Fortran compiler, no MPI.)
 """
 import argparse
 import json
