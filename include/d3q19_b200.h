@@ -181,7 +181,8 @@ typedef struct d3q19_particle_params {
     double stf0, stf1, stf0_w, stf1_w;   /* para.f90:356-360                                 */
     double fscale;              /* force scale of the repulsion (0 = off)                    */
     double gforce[3];           /* constant body force on each particle (gravity - buoyancy) */
-    int64_t maxlink;            /* link capacity; 0 = 8 npart 4 pi (rad+1)^2 (cf. para.f90:371) */
+    int64_t maxlink;            /* link capacity of ALL particles (split evenly into per-particle segments);
+                                   0 = 8 npart 4 pi (rad+1)^2 (cf. para.f90:371); an overflow is reported by d3q19_sync */
 } d3q19_particle_params;
 int d3q19_particles_init(d3q19_handle *h, int32_t npart, const d3q19_particle_params *prm);
 /* solid mask (ibnodes/isnodes, ghost planes included) and boundary links from the particle table.  A no-op while the
@@ -199,6 +200,9 @@ int d3q19_beads_filling(d3q19_handle *h, int64_t *nfilled_local);
 /* links (if stale); collide_stream; beads_collision; [lubforce; move; links; filling]         */
 int d3q19_particle_step(d3q19_handle *h, int32_t move);
 int d3q19_get_particles(d3q19_handle *h, double *ypglb, double *wp, double *omgp, double *fHIp, double *torqp);
+/* the boundary links of this slab: global 1-based fluid-node coordinates, direction into the solid, particle (1-based),
+ * fraction q of the link on the fluid side.  The list is a SET: the particles' segments come one after the other, inside a
+ * segment the order depends on the run -- sort (particle, z, y, x, direction) before comparing two lists.            */
 int d3q19_get_links(d3q19_handle *h, int64_t capacity, int32_t *x, int32_t *y, int32_t *z, int32_t *ip,
                     int32_t *part, double *q, int64_t *nlink);
 int d3q19_get_mask(d3q19_handle *h, int32_t *own_lx_ly_lz);
