@@ -362,3 +362,20 @@ def test_device_vortcalc_solid_nodes(oracle):
         assert np.array_equal(got, want), name
     assert np.all(got[solid] == -2e-3)
     sim.close(); w.close()
+
+
+def test_wall_clock_budget_exit_needs_a_reduction_on_several_ranks():
+    # main.f90:197-206: the loop is left when MPI_ALLREDUCE(MAX) of the elapsed time exceeds the budget, so that every rank
+    # leaves at the same step; ChannelFlow.run mirrors it and refuses a local decision on several ranks
+    sim = pkg.ChannelFlow(16, 4, 4, laminar=True)
+    sim.FORCING(); sim.initpop(); sim.macrovar()
+    sim.v.ntime = 3
+    assert sim.run(10, time_bond=0.0) == 3                      # budget spent at the first check (istep = ntime)
+    seen = []
+    assert sim.run(10, time_bond=1e9, allreduce_max=lambda t: seen.append(t) or t) == sim.v.istep0 + 10
+    assert len(seen) == 3                                        # asked at steps 3, 6, 9
+    sim.nranks = 2                                               # (what a rank of a 2-rank job would see)
+    with pytest.raises(ValueError):
+        sim.run(10, time_bond=1.0)
+    sim.nranks = 1
+    sim.close()
