@@ -91,7 +91,7 @@ struct d3q19_handle {
     // [1] after it, [2] after the interior launch (all on sc), [3] after the exchange / put (on sx)
     cudaEvent_t *trace_ev = nullptr;
     int trace_cap = 0, trace_n = 0;
-    bool put_pending = false;     // "put" transport: the last k_face_put (on sx, event evX) may still be reading my planes
+    bool put_pending = false;     // copy-engine transport: the last copies (on sx, event evX) may still be reading my planes
     NcclComm comm = nullptr;
     double *send_up = nullptr, *send_dn = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
     double *stage[2] = {nullptr, nullptr};
@@ -867,11 +867,11 @@ static int launch_step_halo(d3q19_handle *h, const StepParams &p0) {
     return 0;
 }
 
-// Third transport ("put"): plain step kernels, boundary planes first; a small copy kernel on the
-// high-priority stream stores both faces into the neighbours' arrays and raises their flags
-// (kernels.cuh k_face_put).  Ordering: this step's boundary kernel runs after (a) my own previous put has
-// finished reading my planes (evX) and (b) both neighbours' previous puts have landed (flags >= epoch-1);
-// (b) also implies the neighbours are done reading the ghost planes this step's put overwrites.
+// Copy-engine transport (D3Q19_HALO_PUT, the default of bench.py): plain step kernels, boundary planes first; the copy
+// engines move both faces into the neighbours' arrays on the second stream and a one-thread kernel raises their flags.
+// Ordering: this step's boundary kernel runs after (a) my own previous copies have finished reading my planes (evX) and
+// (b) both neighbours' previous copies have landed (flags >= epoch-1); (b) also implies the neighbours are done reading
+// the ghost planes this step's copies overwrite.
 template <int SK, bool STRICT, bool GENERIC>
 static int launch_step_put(d3q19_handle *h, const StepParams &p, double *written) {
     const int lz = h->g.lz;

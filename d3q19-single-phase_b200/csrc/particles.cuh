@@ -121,7 +121,7 @@ __device__ __forceinline__ bool in_sphere_of(const PartGeom &pg, const double *c
 //   k_beads_cover    over the box of the new position: nodes inside the sphere get p+1, the lowest id wins where
 //                    spheres overlap (also over a marker: another particle may cover what p left).
 // After both, own == -1: fluid before and after; own == -(q+2): solid before, fluid now (what beads_filling
-// rebuilds, and never a refill source); own > 0: solid now.  This is what the oracle's pair (own0, own) encodes.
+// rebuilds, and never a refill source); own > 0: solid now.  This is what the CPU checker's pair of arrays (mask before / after the move) encodes.
 struct FillList {
     uint32_t *node;               // ghosted in-slab index of an uncovered node of this slab
     int32_t *part;                // the particle that left it, 1-based

@@ -285,7 +285,7 @@ template <class A> static inline bool hs_needs_coop(const A &) { return false; }
 struct hs_none {};
 template <class K, class A0, class... Rest>
 static void hs_dispatch(const char *name, dim3 grid, unsigned block, K kern, const A0 &a0, const Rest &... rest) {
-    static const char *coop[] = {"k_diag<", "k_rho_partial", "k_beads_links", "k_beads_lubmove", "k_beads_ibb", "k_face_put"};
+    static const char *coop[] = {"k_diag<", "k_rho_partial", "k_beads_links", "k_beads_lubmove", "k_beads_ibb"};
     bool c = hs_needs_coop(a0);              // found by ADL for d3q::StepParams (pre-relaxation: block maximum)
     for (const char *n : coop) c = c || !std::strncmp(name, n, std::strlen(n));
     if (c) hs_launch_coop(grid, block, kern, a0, rest...);

@@ -190,7 +190,7 @@ def test_slabs_packed_faces_bit_identical(oracle, hk, scheme, nranks, lz):
 @pytest.mark.parametrize("scheme", [AA, AB])
 @pytest.mark.parametrize("nranks,lz", [(2, None), (3, [2, 2, 3]), (3, [3, 2, 2]), (2, [2, 5])])
 def test_slabs_peer_memory_halo_bit_identical(oracle, hk, scheme, nranks, lz, transport):
-    # halo stored straight into the neighbours' arrays (inside the step kernel, or by k_face_put) + flag protocol:
+    # halo stored straight into the neighbours' arrays (inside the step kernel, or by the copy-engine transfers) + flag protocol:
     # the harness aborts if a flag or block counter is wrong after a step
     w, p, sim = pair(oracle, hk, (21, 6, 7), perturb=1e-4, scheme=scheme, nranks=nranks, lz=lz, transport=transport)
     for step in range(6):
