@@ -207,3 +207,49 @@ def test_many_particles_take_the_split_lubrication_path():
         assert np.max(np.abs(g["wp"] - pt.wp)) < 1e-10 * max(np.max(np.abs(pt.wp)), 1e-30) + 1e-16, step
         assert np.array_equal(sim.get_mask(), pt.own), step
     sim.close(); w.close()
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_near_contact_pair_and_wall_hugging_particle_match_cpu(scheme):
+    # links whose second fluid node lies in ANOTHER particle or behind the wall (the interpolation falls back), fluid nodes
+    # with links to two particles, the repulsion between particles and towards the wall all at work at once
+    pos = [[12.0, 6.0, 8.0], [12.0, 6.0 + 2 * RAD + 0.7, 8.3], [4.85, 14.0, 17.0]]
+    vel = [[0.0, 0.012, 0.0], [0.0, -0.012, 0.0], [-0.004, 0.01, 0.0]]
+    omg = [[0.0, 0.0, 1e-3], [0.0, 0.0, -1e-3], [0.0, 2e-3, 0.0]]
+    w, p = orc.make_initial_state(NX, NY, NZ, laminar=False, noise=True, ipart=1, **U)
+    sim = pkg.ChannelFlow(NX, NY, NZ, laminar=False, scheme=scheme, ipart=True, **U)
+    sim.f[...] = w.get_f()
+    sim.FORCING()
+    sim.upload_f()
+    pt = P.Particles(NX, NY, NZ, RAD, pos, vel, omg, fscale=1e-5)
+    sim.particles_init(pos, RAD, vel, omg, fscale=1e-5)
+    pt.build_mask(); pt.build_links()
+    set_oracle_mask(w, pt)
+    w.macrovar()
+    out = np.empty((NZ, NY, NX, 19))
+    lub = 0.0
+    for step in range(10):
+        w.collision_MRT()
+        f = w.get_f(); pt.ibb(f)
+        pt.lubforce(); pt.move()
+        lub = max(lub, float(np.min(np.max(np.abs(pt.flubp), axis=1))))
+        pt.build_mask(); pt.build_links()
+        pt.refill(f)
+        w.set_f(f); set_oracle_mask(w, pt); w.macrovar()
+        sim.particle_step(move=True)
+        g = sim.get_particles()
+        assert np.max(np.abs(g["ypglb"] - pt.ypglb)) < 1e-11, step
+        assert np.array_equal(sim.get_mask(), pt.own), step
+        fluid = pt.own < 0
+        sim.download_f(out)
+        scale = np.max(np.abs(f[fluid]))
+        assert np.max(np.abs(out[fluid] - f[fluid])) < 1e-9 * scale, step
+        assert np.max(np.abs(g["fHIp"] - pt.fHIp)) < 1e-9 * np.max(np.abs(pt.fHIp)), step
+    assert lub > 0                                            # every one of the three felt a repulsion
+    k, gl = P.canon(pt.links), sim.get_links()
+    for key in ("x", "y", "z", "ip", "part"):
+        assert np.array_equal(gl[key], k[key]), key
+    nodes = [set(zip(k["x"][k["part"] == part].tolist(), k["y"][k["part"] == part].tolist(),
+                     k["z"][k["part"] == part].tolist())) for part in (1, 2)]
+    assert nodes[0] & nodes[1]                                # fluid nodes that carry links to both of the pair
+    sim.close(); w.close()
