@@ -32,9 +32,13 @@
 ! the kernel), so para.f90:219 must read `nprocY = 1` (then nprocZ = nproc, one rank
 ! per GPU).  The shim stops with a message otherwise.
 !
-! NOTE: no Fortran compiler exists in the build image of this repository, so this
-! file is exercised only by inspection; the identical call sequence is exercised by
-! d3q19-single-phase_b200/channel.py (ctypes) in tests/test_gpu_parity.py.
+! NOTE: no Fortran compiler exists in the build image of this repository.  What stands in
+! for one: oracle/shim2c.py (a) checks every bind(c) interface and the d3q19_config mirror
+! below against include/d3q19_b200.h (tests/test_fortran_shim.py) and (b) translates the
+! executable part of this file to C, which is linked with the machine-translated reference
+! MINUS its collision.f90; the reference's own PROGRAM main then runs through this shim and
+! is compared with the all-reference build, bit for bit with cfg%math = STRICT
+! (tests/test_reference_driver.py: host-sim build on the build box, the real library on a B200).
 !=============================================================================
       module d3q19_b200_shim
       use iso_c_binding

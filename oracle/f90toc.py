@@ -14,6 +14,13 @@ This script reads the reference's own sources WHERE THEY LIE (default
     collision.f90 collision_MRT, collisionExchnge, macrovar, rhoupdat, avedensity, FORCING, FORCINGP
     saveload.f90  vortcalc, exchng8, statistc, statistc2, diag (values written to file units are
                   captured: ref_capture)
+    main.f90      PROGRAM main itself -> ref_main (MPI_WTIME reads 0; constructMPItypes and probe are
+                  skipped -- derived MPI types are not used by the mini-MPI, probe only writes files --
+                  and any other call outside the translated set aborts instead of being passed over)
+
+With -DREF_DROPIN the subroutines of collision.f90 are left out and `shim_translated.c` (the translation of
+THIS repository's fortran/collision_b200.f90 by oracle/shim2c.py) is included in their place: the
+reference's driver linked against the drop-in instead of its own collision.f90 (_ref/libref_b200.so).
 
 The translation is statement by statement: every expression keeps the Fortran evaluation
 order (left to right for equal precedence; `**` by repeated multiplication), `real` is double
@@ -545,6 +552,8 @@ class Translator:
                 return "real"
             if n in ("int", "nint", "count", "size"):
                 return "int"
+            if n == "mpi_wtime":
+                return "real"
             if n in ("mod", "abs", "max", "min", "sum", "maxval", "minval", "sign"):
                 ts = [self.typeof(a) for a in e.args if not isinstance(a, (Kw, Range))]
                 return "real" if "real" in ts else "int"
@@ -643,6 +652,8 @@ class Translator:
         a = [self.cx(x, sect) for x in e.args if not isinstance(x, (Kw, Range))]
         if n in ("real", "dfloat", "dble", "float"):
             return "((double)(%s))" % a[0]
+        if n == "mpi_wtime":
+            return "0.0"                       # the wall-clock exit of main.f90:197-207 never fires
         if n == "int":
             return "((int)(%s))" % a[0]
         if n in INTRINSIC_REAL:
@@ -793,6 +804,9 @@ class Translator:
             self.emit("ref_%s(%s);" % (name, ", ".join(["S"] + cargs)))
             for a in after:
                 self.emit(a)
+            return
+        if self.cur_sub == "main" and name not in ("constructmpitypes", "probe"):
+            self.emit('ref_untranslated(S, "%s");' % name)
             return
         self.emit("/* call %s skipped (outside the translated path) */;" % name)
 
@@ -1013,6 +1027,12 @@ class Translator:
             self.emit("case %s: {" % self.cx(parse_expr(m.group(1))))
             self.in_case = True
             return
+        if t == "do":
+            self.emit("{ for (;;) {")
+            return
+        if t == "exit":
+            self.emit("break;")
+            return
         m = re.match(r"^do\s+([a-z_0-9]+)\s*=\s*(.*)$", t)
         if m:
             var = self.cx(parse_expr(m.group(1)))
@@ -1106,6 +1126,19 @@ class Translator:
                     cur = None
         return subs
 
+    def program_of(self, fname):
+        """the PROGRAM unit of a file as the logical lines of an argument-less subroutine `main`"""
+        cur = None
+        for no, t in logical_lines(os.path.join(self.ref, fname)):
+            if re.match(r"^program\s+[a-z_0-9]+$", t):
+                cur = [(no, "subroutine main")]
+            elif cur is not None and re.match(r"^end\s*program", t):
+                cur.append((no, "end subroutine"))
+                return cur
+            elif cur is not None:
+                cur.append((no, t))
+        raise SyntaxError("no PROGRAM unit in %s" % fname)
+
     def generate(self):
         self.in_case = False
         self.wanted = ["para", "allocarray", "initpop", "initvel", "collisionexchnge", "collision_mrt", "macrovar",
@@ -1162,8 +1195,14 @@ class Translator:
         self.translate_sub("allocarray", para["allocarray"])
         self.translate_sub("initpop", init["initpop"])
         self.translate_sub("initvel", init["initvel"], override_assignments=True)
+        o("#ifndef REF_DROPIN")
         for n in ("collision_mrt", "collisionexchnge", "macrovar", "rhoupdat", "avedensity", "forcing", "forcingp"):
             self.translate_sub(n, coll[n])
+        o("#else   /* the drop-in's collision_b200.f90 instead of the reference's collision.f90 */")
+        for n in ("collision_mrt", "macrovar", "rhoupdat", "avedensity", "forcing", "forcingp"):
+            o("void ref_%s(ref_state *S);" % n)
+        o('#include "shim_translated.c"')
+        o("#endif")
         # next-tier diagnostics: vorticity and its ghost-plane exchange
         save = self.subroutines_of("saveload.f90")
         self.translate_sub("vortcalc", save["vortcalc"])
@@ -1178,6 +1217,9 @@ class Translator:
         # rank 2: the checkpoint writers -- file name pieces and the records of their unformatted writes are captured
         for n in ("savecntdflow", "saveinitflow", "saveprerelax"):
             self.translate_sub(n, save[n])
+        # the driver itself: PROGRAM main (main.f90:19-236)
+        self.wanted.append("main")
+        self.translate_sub("main", self.program_of("main.f90"))
         # ---- dispatch + reflection tables for the Python wrapper
         o("\nint ref_dispatch(ref_state *S, const char *name)\n{")
         for n in self.wanted:

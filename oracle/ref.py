@@ -24,20 +24,30 @@ class Arr(C.Structure):
                 ("lo", C.c_int * 4), ("n", C.c_int * 4)]
 
 
-def lib_path(fast=False):
-    return os.path.join(HERE, "_ref", "libref_fast.so" if fast else "libref.so")
+def lib_path(fast=False, dropin=False):
+    return os.path.join(HERE, "_ref", "libref_b200.so" if dropin else ("libref_fast.so" if fast else "libref.so"))
 
 
-def available(fast=False):
-    return os.path.exists(lib_path(fast))
+def available(fast=False, dropin=False):
+    return os.path.exists(lib_path(fast, dropin))
 
 
 _libs = {}
 
 
-def lib(fast=False):
+def lib(fast=False, dropin=None):
+    """dropin: path of the d3q19 library (libd3q19b200.so or the tests' host-sim build) -> the build in which the
+    reference's collision.f90 is replaced by this repository's Fortran shim (oracle/shim2c.py); the d3q19_* entry
+    points the shim binds are resolved from that library, loaded first and globally"""
+    fast = ("dropin", os.path.abspath(dropin)) if dropin else fast
     if fast not in _libs:
-        L = C.CDLL(lib_path(fast))
+        if dropin:
+            C.CDLL(dropin, mode=C.RTLD_GLOBAL)
+            L = C.CDLL(lib_path(dropin=True))
+            L.ref_shim_handle.argtypes = [C.c_void_p]
+            L.ref_shim_handle.restype = C.c_void_p
+        else:
+            L = C.CDLL(lib_path(fast))
         L.ref_world_create.argtypes = [C.c_int]
         L.ref_world_create.restype = C.c_void_p
         L.ref_world_destroy.argtypes = [C.c_void_p]
@@ -60,8 +70,8 @@ def lib(fast=False):
 class RefWorld:
     """All MPI ranks of one run of the translated reference (one thread per rank)."""
 
-    def __init__(self, nx, ny, nz, nprocY=1, nprocZ=1, laminar=True, fast=False, ipart=False, **overrides):
-        self.L = lib(fast)
+    def __init__(self, nx, ny, nz, nprocY=1, nprocZ=1, laminar=True, fast=False, ipart=False, dropin=None, **overrides):
+        self.L = lib(fast, dropin)
         self.nx, self.ny, self.nz = nx, ny, nz
         self.nproc = nprocY * nprocZ
         self.h = self.L.ref_world_create(self.nproc)
@@ -97,6 +107,10 @@ class RefWorld:
     def run(self, name):
         if self.L.ref_world_run(self.h, name.lower().encode()):
             raise KeyError("no translated subroutine %r" % name)
+
+    def shim_handle(self, rank=0):
+        """drop-in build only: the d3q19 handle the Fortran shim created on `rank` (None before its first hot-path call)"""
+        return self.L.ref_shim_handle(self.L.ref_world_state(self.h, rank))
 
     def loop(self, a, b, nsteps):
         self.L.ref_world_loop(self.h, a.lower().encode(), (b or "").lower().encode(), nsteps)

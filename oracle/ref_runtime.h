@@ -272,6 +272,34 @@ static inline void ref_mpi_waitall(void *S, int *n, void *req, void *status, int
     *ierr = 0;
 }
 
+/* what PROGRAM main (main.f90:26-28,233) and the drop-in's Fortran shim use on top of the hot path's calls */
+static inline void ref_mpi_init(void *S, int *ierr) { (void)S; *ierr = 0; }
+static inline void ref_mpi_finalize(void *S, int *ierr) { (void)S; *ierr = 0; }
+static inline void ref_mpi_comm_rank(void *S, int comm, int *rank, int *ierr) { (void)comm; *rank = ((ref_common *)S)->rank; *ierr = 0; }
+static inline void ref_mpi_comm_size(void *S, int comm, int *n, int *ierr) { (void)comm; *n = ((ref_common *)S)->comm->nproc; *ierr = 0; }
+static inline void ref_mpi_abort(void *S, int comm, int *code, int *ierr)
+{
+    (void)comm; (void)ierr;
+    fprintf(stderr, "ref: MPI_ABORT(%d) on rank %d\n", *code, ((ref_common *)S)->rank);
+    abort();
+}
+static inline void ref_untranslated(void *S, const char *name)
+{
+    fprintf(stderr, "ref: rank %d reached `call %s`, which is outside the translated set\n", ((ref_common *)S)->rank, name);
+    abort();
+}
+static inline void ref_mpi_bcast(void *S, void *buf, int *count, int type, int *root, int comm, int *ierr)
+{
+    (void)comm;
+    ref_common *c = (ref_common *)S;
+    ref_comm *cm = c->comm;
+    cm->slot[c->rank] = buf;
+    ref_barrier_(cm);
+    if (c->rank != *root) memcpy(buf, cm->slot[*root], (size_t)*count * ref_type_size(type));
+    ref_barrier_(cm);
+    *ierr = 0;
+}
+
 static inline void ref_mpi_allgather(void *S, void *sbuf, int *scount, int stype, void *rbuf, int *rcount, int rtype,
                                      int comm, int *ierr)
 {

@@ -1,0 +1,93 @@
+"""The reference's own PROGRAM main (main.f90:19-236) driving the library through the Fortran shim.
+
+`make -C oracle ref` (where /root/reference is mounted) builds two libraries from the reference's sources,
+machine-translated to C (oracle/f90toc.py): `_ref/libref.so`, all of it, and `_ref/libref_b200.so`, in which the subroutines
+of collision.f90 are left out and THIS repository's fortran/collision_b200.f90 -- translated by oracle/shim2c.py -- is linked
+in their place, which is the link line INTEGRATION.md gives a maintainer of the reference.  tests/refdriver_worker.py runs
+`main` in both (new run: initvel, FORCING, initpop, the pre-relaxation loop with its host-side max|rho - rhop|,
+saveinitflow, statistc, the time loop with diag every ndiag steps) and compares everything the driver reads or writes:
+with STRICT arithmetic bit for bit, with the production arithmetic within the tolerances below.
+
+On the build box the d3q19 library is the tests' host-sim build (1, 2 and 3 ranks: NCCL id through MPI_BCAST, cudaIpc
+handles through MPI_ALLGATHER, copy-engine faces); on the GPU box the same worker runs against libd3q19b200.so.  Nothing
+here reads /root/reference at run time."""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle import ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "refdriver_worker.py")
+needs_ref = pytest.mark.skipif(not (ref.available() and ref.available(dropin=True)),
+                               reason="oracle/_ref not built (needs /root/reference at build time)")
+# production arithmetic (FMA contraction): populations to 1e-12 of their maximum (BASELINE.json's bound for one step holds
+# after the ~30 here); rho and u are density FLUCTUATIONS and velocities of order 1e-5..1e-2, compared with their own maximum
+TOL = dict(f=1e-12, unit9010=1e-12, unit26=1e-9, rho=1e-9, ux=1e-9, uy=1e-9, uz=1e-9, unit27=1e-9, unit58=1e-9)
+
+
+def run_worker(lib, *args):
+    res = subprocess.run([sys.executable, WORKER, "--lib", lib] + [str(a) for a in args], stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, timeout=900, cwd=ROOT)
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert line, res.stdout[-3000:]
+    out = json.loads(line[-1])
+    assert res.returncode == 0 and not out["bad"], (out["bad"], res.stdout[-2000:])
+    assert out["istep_end"][0] == out["nsteps"] + 1           # the time loop ran to its end (a DO variable ends one past)
+    assert {26, 27, 9010} <= set(out["units"])                # diag, statistc and saveinitflow did write
+    return out
+
+
+def check_fast(out):
+    for k, tol in TOL.items():
+        if k in out["maxrel"]:
+            assert out["maxrel"][k] < tol, (k, out["maxrel"][k])
+    assert out["maxrel"]["f"] > 0.0                           # (it IS another arithmetic: the comparison is not vacuous)
+
+
+@pytest.fixture(scope="module")
+def hostsim_lib():
+    spec = importlib.util.spec_from_file_location("make_hostsim", os.path.join(ROOT, "tests", "host", "make_hostsim.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.build()
+
+
+@needs_ref
+@pytest.mark.parametrize("ranks,scheme", [(1, "auto"), (1, "aa"), (2, "ab"), (3, "aa")])
+def test_reference_main_through_the_shim_is_bit_identical_on_the_host_sim(hostsim_lib, ranks, scheme):
+    run_worker(hostsim_lib, "--ranks", ranks, "--scheme", scheme, "--math", "strict")
+
+
+@needs_ref
+def test_reference_main_laminar_odd_sizes_on_the_host_sim(hostsim_lib):
+    run_worker(hostsim_lib, "--laminar", "--size", "9x4x5", "--nsteps", 7, "--ndiag", 3, "--scheme", "aa")
+
+
+@needs_ref
+def test_reference_main_with_production_arithmetic_on_the_host_sim(hostsim_lib):
+    check_fast(run_worker(hostsim_lib, "--ranks", 2, "--math", "fast"))
+
+
+# ---- the same on a B200, against the product library -----------------------------------------------------------------
+def product_lib():
+    import __graft_entry__ as entry
+    return entry.load_package().capi.LIB_PATH
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("scheme", ["aa", "ab"])
+def test_reference_main_through_the_shim_is_bit_identical_on_the_gpu(scheme):
+    run_worker(product_lib(), "--scheme", scheme, "--math", "strict", "--size", "24x10x12", "--nsteps", 23, "--ndiag", 5)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_reference_main_with_production_arithmetic_on_the_gpu():
+    # the shim as written: SCHEME_AUTO, MATH_FAST
+    check_fast(run_worker(product_lib(), "--math", "fast", "--size", "24x10x12", "--nsteps", 23, "--ndiag", 5))
