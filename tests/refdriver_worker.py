@@ -32,6 +32,8 @@ ap.add_argument("--nsteps", type=int, default=12)
 ap.add_argument("--ndiag", type=int, default=4)
 ap.add_argument("--rhoepsl", type=float, default=1e-6)
 ap.add_argument("--laminar", action="store_true")
+ap.add_argument("--ipart", action="store_true", help="ipart = .true. (para.f90:332) with no particle present: the solid-"
+                "node branches and, every 100 steps, avedensity (main.f90:163-167) are on the path")
 a = ap.parse_args()
 nx, ny, nz = (int(t) for t in a.size.split("x"))
 U = {} if a.laminar else dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx, a9=0.3)
@@ -39,7 +41,7 @@ ov = dict(nsteps=a.nsteps, ndiag=a.ndiag, nflowout=10 ** 8, ntime=5, rhoepsl=a.r
 
 
 def run_main(dropin):
-    w = ref.RefWorld(nx, ny, nz, nprocY=1, nprocZ=a.ranks, laminar=a.laminar, dropin=dropin, **ov)
+    w = ref.RefWorld(nx, ny, nz, nprocY=1, nprocZ=a.ranks, laminar=a.laminar, dropin=dropin, ipart=a.ipart, **ov)
     if dropin:
         w.override("cfg%math", 1 if a.math == "strict" else 0)
         w.override("cfg%scheme", dict(aa=0, ab=1, auto=2)[a.scheme])

@@ -69,6 +69,13 @@ def test_reference_main_laminar_odd_sizes_on_the_host_sim(hostsim_lib):
 
 
 @needs_ref
+def test_reference_main_with_ipart_reaches_avedensity_on_the_host_sim(hostsim_lib):
+    # ipart = .true. with no particle present: solid-node branches compiled in, isnodes bound, and at step 100 the
+    # all-reduced avedensity of main.f90:163-167 (then one more step on the corrected field)
+    run_worker(hostsim_lib, "--ipart", "--ranks", 2, "--scheme", "aa", "--nsteps", 101, "--ndiag", 50)
+
+
+@needs_ref
 def test_reference_main_with_production_arithmetic_on_the_host_sim(hostsim_lib):
     check_fast(run_worker(hostsim_lib, "--ranks", 2, "--math", "fast"))
 
@@ -91,3 +98,9 @@ def test_reference_main_through_the_shim_is_bit_identical_on_the_gpu(scheme):
 def test_reference_main_with_production_arithmetic_on_the_gpu():
     # the shim as written: SCHEME_AUTO, MATH_FAST
     check_fast(run_worker(product_lib(), "--math", "fast", "--size", "24x10x12", "--nsteps", 23, "--ndiag", 5))
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_reference_main_with_ipart_reaches_avedensity_on_the_gpu():
+    run_worker(product_lib(), "--ipart", "--scheme", "ab", "--nsteps", 101, "--ndiag", 50, "--size", "24x10x12")
