@@ -14,9 +14,10 @@ This script reads the reference's own sources WHERE THEY LIE (default
     collision.f90 collision_MRT, collisionExchnge, macrovar, rhoupdat, avedensity, FORCING, FORCINGP
     saveload.f90  vortcalc, exchng8, statistc, statistc2, diag (values written to file units are
                   captured: ref_capture)
-    main.f90      PROGRAM main itself -> ref_main (MPI_WTIME reads 0; constructMPItypes and probe are
-                  skipped -- derived MPI types are not used by the mini-MPI, probe only writes files --
-                  and any other call outside the translated set aborts instead of being passed over)
+    saveload.f90  outputflow, outputuy, outputpress, probe (what main.f90 calls every nflowout steps and at the end)
+    main.f90      PROGRAM main itself -> ref_main (MPI_WTIME reads 0; constructMPItypes is skipped -- derived
+                  MPI types are not used by the mini-MPI -- and any other call outside the translated set
+                  aborts instead of being passed over)
 
 With -DREF_DROPIN the subroutines of collision.f90 are left out and `shim_translated.c` (the translation of
 THIS repository's fortran/collision_b200.f90 by oracle/shim2c.py) is included in their place: the
@@ -481,7 +482,7 @@ def parse_dims(dims_text):
 # translation
 # ------------------------------------------------------------------------------------------------
 INTRINSIC_REAL = {"exp": "exp", "sin": "sin", "cos": "cos", "alog": "log", "log": "log", "dlog": "log",
-                  "atan": "atan", "sqrt": "sqrt", "dsqrt": "sqrt"}
+                  "atan": "atan", "sqrt": "sqrt", "dsqrt": "sqrt", "dcos": "cos", "dsin": "sin", "dexp": "exp"}
 MPI_CONST = {"mpi_real8": "REF_MPI_REAL8", "mpi_integer": "REF_MPI_INTEGER", "mpi_sum": "REF_MPI_SUM",
              "mpi_max": "REF_MPI_MAX", "mpi_min": "REF_MPI_MIN", "mpi_comm_world": "0", "mpi_status_size": "4",
              "mpi_byte": "REF_MPI_BYTE"}
@@ -805,7 +806,7 @@ class Translator:
             for a in after:
                 self.emit(a)
             return
-        if self.cur_sub == "main" and name not in ("constructmpitypes", "probe"):
+        if self.cur_sub == "main" and name != "constructmpitypes":
             self.emit('ref_untranslated(S, "%s");' % name)
             return
         self.emit("/* call %s skipped (outside the translated path) */;" % name)
@@ -942,7 +943,7 @@ class Translator:
                     continue
                 e = parse_expr(item)
                 kind = 8 if self.typeof(e) == "real" else 4
-                shape = self.section_shape(e) if isinstance(e, (Var, Index)) else None
+                shape = self.section_shape(e)
                 if shape:
                     op, cl, names = self.loops(shape)
                     self.emit("{ long cnt_ = 0; %s{ ref_capture(S, %d, (double)(%s)); ++cnt_; }%s ref_capture(S, %d, %d.0); "
@@ -961,7 +962,7 @@ class Translator:
                 if not item or item[0] in "'\"":
                     continue
                 e = parse_expr(item)
-                shape = self.section_shape(e) if isinstance(e, (Var, Index)) else None
+                shape = self.section_shape(e)
                 if shape:
                     op, cl, names = self.loops(shape)
                     self.emit("%sref_capture(S, %s, (double)(%s));%s" % (op, m.group(1), self.cx(e, names), cl))
@@ -1078,6 +1079,13 @@ class Translator:
                 self.emit("ref_free(&%s); %s = ref_alloc(%s, %d, (int[]){%s}, (int[]){%s});"
                           % (self.c_name(s), self.c_name(s), kind, len(dims), los, his))
             return
+        m = re.match(r"^deallocate\s*\((.*)\)$", t)
+        if m:
+            for name in split_top(m.group(1)):
+                sname = self.sym(name.strip())
+                if sname and sname.typ in ("real", "int"):
+                    self.emit("ref_free(&%s);" % self.c_name(sname))
+            return
         # assignment: split at the top-level '=' that is not part of ==, /=, <=, >=
         depth, q = 0, None
         for i, ch in enumerate(t):
@@ -1144,7 +1152,7 @@ class Translator:
         self.wanted = ["para", "allocarray", "initpop", "initvel", "collisionexchnge", "collision_mrt", "macrovar",
                        "rhoupdat", "avedensity", "forcing", "forcingp", "exchng8", "vortcalc", "sijstat00",
                        "savecntdflow", "saveinitflow", "saveprerelax",
-                       "statistc", "statistc2", "diag"]
+                       "statistc", "statistc2", "diag", "outputflow", "outputuy", "outputpress", "probe"]
         o = self.emit
         o("/* GENERATED by oracle/f90toc.py from the reference's Fortran sources -- do not edit, do not commit. */")
         o('#include "../ref_runtime.h"')
@@ -1163,6 +1171,8 @@ class Translator:
         # prototypes (collisionExchnge is called before it is defined)
         o("void ref_collisionexchnge(ref_state *S, void *a, void *b, void *c, void *d);")
         o("void ref_exchng8(ref_state *S, void *a, void *b, void *c, void *d, void *e, void *f, void *g, void *h);")
+        for n in ("outputuy", "outputpress"):                   # called by outputflow before they are defined
+            o("void ref_%s(ref_state *S);" % n)
         # ---- parameters and fixed-shape module arrays
         self.local, self.cur_sub = {}, "var_inc"
         o("\nvoid ref_module_init(ref_state *S)\n{")
@@ -1209,6 +1219,10 @@ class Translator:
         self.translate_sub("exchng8", save["exchng8"])
         # rank 1: profile statistics and the diag monitor; their write(unit, ...) lists are captured
         for n in ("statistc", "statistc2", "diag"):
+            self.translate_sub(n, save[n])
+        # what main.f90 calls every nflowout steps and after the loop: rank 0 collects uy / rho from all ranks
+        # (MPI_SEND/MPI_RECV) and writes a profile and a cut; the centre-node probe of every rank (MPI_GATHER)
+        for n in ("outputflow", "outputuy", "outputpress", "probe"):
             self.translate_sub(n, save[n])
         # rank 4, second half: the local strain rate from the non-equilibrium moments (sijstat00's first loop nest,
         # saveload.f90:2031-2091; what follows in that routine are particle-centred shell statistics).  Sij2 is an

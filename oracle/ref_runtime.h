@@ -300,6 +300,33 @@ static inline void ref_mpi_bcast(void *S, void *buf, int *count, int type, int *
     *ierr = 0;
 }
 
+/* blocking point-to-point (outputuy / outputpress, saveload.f90:871,889) on top of the non-blocking pair */
+static inline void ref_mpi_send(void *S, void *buf, int *count, int type, int *dst, int *tag, int comm, int *ierr)
+{
+    int req = 0;
+    ref_mpi_isend(S, buf, count, type, dst, tag, comm, &req, ierr);
+}
+static inline void ref_mpi_recv(void *S, void *buf, int *count, int type, int *src, int *tag, int comm, void *status, int *ierr)
+{
+    int req = 0, one = 1;
+    ref_mpi_irecv(S, buf, count, type, src, tag, comm, &req, ierr);
+    ref_mpi_waitall(S, &one, &req, status, ierr);
+}
+static inline void ref_mpi_gather(void *S, void *sbuf, int *scount, int stype, void *rbuf, int *rcount, int rtype,
+                                  int *root, int comm, int *ierr)
+{
+    (void)comm; (void)rcount; (void)rtype;
+    ref_common *c = (ref_common *)S;
+    ref_comm *cm = c->comm;
+    size_t b = (size_t)*scount * ref_type_size(stype);
+    cm->slot[c->rank] = sbuf;
+    ref_barrier_(cm);
+    if (c->rank == *root)
+        for (int r = 0; r < cm->nproc; ++r) memcpy((char *)rbuf + (size_t)r * b, cm->slot[r], b);
+    ref_barrier_(cm);
+    *ierr = 0;
+}
+
 static inline void ref_mpi_allgather(void *S, void *sbuf, int *scount, int stype, void *rbuf, int *rcount, int rtype,
                                      int comm, int *ierr)
 {

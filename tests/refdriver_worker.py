@@ -6,7 +6,8 @@ built where /root/reference is mounted; the .so files travel).  Prints one JSON 
                                      [--scheme aa|ab|auto] [--size 12x6x12] [--nsteps 12] [--ndiag 4] [--laminar]
 
 Compared, rank by rank: everything the driver's own output routines were handed (statistc, statistc2 after the
-pre-relaxation, diag every ndiag steps, the records saveinitflow writes = f at the end of the pre-relaxation loop), the
+pre-relaxation, diag every ndiag steps, outputuy + outputpress every nflowout steps (rank 0 collects uy and rho from all
+ranks), probe after the loop, the records saveinitflow writes = f at the end of the pre-relaxation loop), the
 number of pre-relaxation iterations, rho/ux/uy/uz as the driver's host arrays hold them when main ends (what probe would
 read), and f after the shim's explicit write-back."""
 import argparse
@@ -30,6 +31,7 @@ ap.add_argument("--scheme", default="auto", choices=["aa", "ab", "auto"])
 ap.add_argument("--size", default="12x6x12")
 ap.add_argument("--nsteps", type=int, default=12)
 ap.add_argument("--ndiag", type=int, default=4)
+ap.add_argument("--nflowout", type=int, default=5)
 ap.add_argument("--rhoepsl", type=float, default=1e-6)
 ap.add_argument("--laminar", action="store_true")
 ap.add_argument("--ipart", action="store_true", help="ipart = .true. (para.f90:332) with no particle present: the solid-"
@@ -37,7 +39,7 @@ ap.add_argument("--ipart", action="store_true", help="ipart = .true. (para.f90:3
 a = ap.parse_args()
 nx, ny, nz = (int(t) for t in a.size.split("x"))
 U = {} if a.laminar else dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx, a9=0.3)
-ov = dict(nsteps=a.nsteps, ndiag=a.ndiag, nflowout=10 ** 8, ntime=5, rhoepsl=a.rhoepsl, **U)
+ov = dict(nsteps=a.nsteps, ndiag=a.ndiag, nflowout=a.nflowout, ntime=7, rhoepsl=a.rhoepsl, **U)
 
 
 def run_main(dropin):

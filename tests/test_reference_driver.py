@@ -5,7 +5,7 @@ machine-translated to C (oracle/f90toc.py): `_ref/libref.so`, all of it, and `_r
 of collision.f90 are left out and THIS repository's fortran/collision_b200.f90 -- translated by oracle/shim2c.py -- is linked
 in their place, which is the link line INTEGRATION.md gives a maintainer of the reference.  tests/refdriver_worker.py runs
 `main` in both (new run: initvel, FORCING, initpop, the pre-relaxation loop with its host-side max|rho - rhop|,
-saveinitflow, statistc, the time loop with diag every ndiag steps) and compares everything the driver reads or writes:
+saveinitflow, statistc, the time loop with diag every ndiag steps and outputflow every nflowout steps, probe) and compares everything the driver reads or writes:
 with STRICT arithmetic bit for bit, with the production arithmetic within the tolerances below.
 
 On the build box the d3q19 library is the tests' host-sim build (1, 2 and 3 ranks: NCCL id through MPI_BCAST, cudaIpc
@@ -27,7 +27,7 @@ needs_ref = pytest.mark.skipif(not (ref.available() and ref.available(dropin=Tru
                                reason="oracle/_ref not built (needs /root/reference at build time)")
 # production arithmetic (FMA contraction): populations to 1e-12 of their maximum (BASELINE.json's bound for one step holds
 # after the ~30 here); rho and u are density FLUCTUATIONS and velocities of order 1e-5..1e-2, compared with their own maximum
-TOL = dict(f=1e-12, unit9010=1e-12, unit26=1e-9, rho=1e-9, ux=1e-9, uy=1e-9, uz=1e-9, unit27=1e-9, unit58=1e-9)
+TOL = dict(f=1e-12, unit9010=1e-12, unit26=1e-9, unit17=1e-9, unit20=1e-9, unit60=1e-9, rho=1e-9, ux=1e-9, uy=1e-9, uz=1e-9, unit27=1e-9, unit58=1e-9)
 
 
 def run_worker(lib, *args):
@@ -38,7 +38,7 @@ def run_worker(lib, *args):
     out = json.loads(line[-1])
     assert res.returncode == 0 and not out["bad"], (out["bad"], res.stdout[-2000:])
     assert out["istep_end"][0] == out["nsteps"] + 1           # the time loop ran to its end (a DO variable ends one past)
-    assert {26, 27, 9010} <= set(out["units"])                # diag, statistc and saveinitflow did write
+    assert {17, 20, 26, 27, 60, 9010} <= set(out["units"])    # outputuy, outputpress, diag, statistc, probe, saveinitflow wrote
     return out
 
 
