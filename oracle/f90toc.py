@@ -952,6 +952,24 @@ class Translator:
                     self.emit("ref_capture(S, %d, (double)(%s)); ref_capture(S, %d, %d.0); ref_capture(S, %d, 1.0);"
                               % (9000 + u, self.cx(e), 9500 + u, kind, 9500 + u))
             return
+        m = re.match(r"^read\s*\(\s*(\d+)\s*\)\s*(.*)$", t)
+        if m:
+            # UNFORMATTED sequential input (loadcntdflow, saveload.f90:327-328): the items are filled, in list order and
+            # first dimension fastest, from the rank's playback queue -- which a test loads with what the matching
+            # writer handed to its write(unit) (ref_world_set_playback)
+            for item in split_top(m.group(2)):
+                item = item.strip()
+                if not item:
+                    continue
+                e = parse_expr(item)
+                ctype = "double" if self.typeof(e) == "real" else "int"
+                shape = self.section_shape(e)
+                if shape:
+                    op, cl, names = self.loops(shape)
+                    self.emit("%s%s = (%s)ref_play(S, %s);%s" % (op, self.cx(e, names), ctype, m.group(1), cl))
+                else:
+                    self.emit("%s = (%s)ref_play(S, %s);" % (self.cx(e), ctype, m.group(1)))
+            return
         m = re.match(r"^write\s*\(\s*(\d+)\s*,", t)
         if m:
             # formatted output to a file unit: hand the numeric items to the capture buffer in list order
@@ -1152,7 +1170,8 @@ class Translator:
         self.wanted = ["para", "allocarray", "initpop", "initvel", "collisionexchnge", "collision_mrt", "macrovar",
                        "rhoupdat", "avedensity", "forcing", "forcingp", "exchng8", "vortcalc", "sijstat00",
                        "savecntdflow", "saveinitflow", "saveprerelax",
-                       "statistc", "statistc2", "diag", "outputflow", "outputuy", "outputpress", "probe"]
+                       "statistc", "statistc2", "diag", "outputflow", "outputuy", "outputpress", "probe",
+                       "loadcntdflow"]
         o = self.emit
         o("/* GENERATED by oracle/f90toc.py from the reference's Fortran sources -- do not edit, do not commit. */")
         o('#include "../ref_runtime.h"')
@@ -1231,6 +1250,8 @@ class Translator:
         # rank 2: the checkpoint writers -- file name pieces and the records of their unformatted writes are captured
         for n in ("savecntdflow", "saveinitflow", "saveprerelax"):
             self.translate_sub(n, save[n])
+        # ... and the reader of a continued run (main.f90:120): its read(unit) lists are served from a playback queue
+        self.translate_sub("loadcntdflow", save["loadcntdflow"])
         # the driver itself: PROGRAM main (main.f90:19-236)
         self.wanted.append("main")
         self.translate_sub("main", self.program_of("main.f90"))

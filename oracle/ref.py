@@ -61,6 +61,9 @@ def lib(fast=False, dropin=None):
         L.ref_capture_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.ref_capture_get.restype = C.c_int
         L.ref_capture_clear.argtypes = [C.c_void_p]
+        L.ref_world_set_playback.argtypes = [C.c_void_p, C.c_int, C.c_long, C.POINTER(C.c_double)]
+        L.ref_world_playback_left.argtypes = [C.c_void_p, C.c_int]
+        L.ref_world_playback_left.restype = C.c_long
         L.ref_array.argtypes = [C.c_void_p, C.c_char_p]
         L.ref_array.restype = C.POINTER(Arr)
         _libs[fast] = L
@@ -125,6 +128,14 @@ class RefWorld:
         u = np.array(units[:n], dtype=np.int64)
         v = np.array(vals[:n], dtype=np.float64)
         return v if unit is None else v[u == unit]
+
+    def set_playback(self, values, rank=0):
+        """what the translated read(unit) statements of `rank` (loadcntdflow) will be handed, in order"""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self.L.ref_world_set_playback(self.h, rank, v.size, v.ctypes.data_as(C.POINTER(C.c_double)))
+
+    def playback_left(self, rank=0):
+        return self.L.ref_world_playback_left(self.h, rank)
 
     def clear_captured(self):
         self.L.ref_capture_clear(self.h)

@@ -153,7 +153,20 @@ typedef struct ref_common {
     int ncap, capcap;
     int *cap_unit;
     double *cap_val;
+    /* values the translated code will be handed by read(unit) statements (loadcntdflow), in the order read */
+    long nplay, iplay;
+    double *play;
 } ref_common;
+
+static inline double ref_play(void *S, int unit)
+{
+    ref_common *c = (ref_common *)S;
+    if (c->iplay >= c->nplay) {
+        fprintf(stderr, "ref: rank %d reads past the end of the playback queue (unit %d)\n", c->rank, unit);
+        abort();
+    }
+    return c->play[c->iplay++];
+}
 
 static inline void ref_capture(void *S, int unit, double v)
 {
@@ -415,7 +428,7 @@ void ref_world_destroy(ref_world *w)
     if (!w) return;
     for (int r = 0; r < w->nproc; ++r) {
         ref_common *c = (ref_common *)w->st[r];
-        free(c->cap_unit); free(c->cap_val);
+        free(c->cap_unit); free(c->cap_val); free(c->play);
         ref_module_free(w->st[r]); free(w->st[r]);
     }
     while (w->comm.head) { ref_msg *m = w->comm.head; w->comm.head = m->next; free(m->data); free(m); }
@@ -437,6 +450,21 @@ int ref_capture_get(ref_world *w, int rank, int max, int *units, double *vals)
 void ref_capture_clear(ref_world *w)
 {
     for (int r = 0; r < w->nproc; ++r) ((ref_common *)w->st[r])->ncap = 0;
+}
+
+/* what the next read(unit) statements of `rank` will be handed */
+void ref_world_set_playback(ref_world *w, int rank, long n, const double *vals)
+{
+    ref_common *c = (ref_common *)w->st[rank];
+    free(c->play);
+    c->play = (double *)malloc((size_t)(n ? n : 1) * sizeof(double));
+    memcpy(c->play, vals, (size_t)n * sizeof(double));
+    c->nplay = n; c->iplay = 0;
+}
+long ref_world_playback_left(ref_world *w, int rank)
+{
+    ref_common *c = (ref_common *)w->st[rank];
+    return c->nplay - c->iplay;
 }
 
 int ref_world_set_override(ref_world *w, const char *name, double v)

@@ -76,6 +76,16 @@ def test_reference_main_with_ipart_reaches_avedensity_on_the_host_sim(hostsim_li
 
 
 @needs_ref
+@pytest.mark.parametrize("ranks,scheme", [(1, "auto"), (2, "aa"), (3, "ab")])
+def test_reference_continued_run_through_the_shim_on_the_host_sim(hostsim_lib, ranks, scheme):
+    # after the new run: savecntdflow in both builds (the records are compared), then main again with newrun = .false.
+    # (main.f90:118-121): loadcntdflow fills the host f from the checkpoint BEFORE the shim's first upload, the time loop
+    # continues from istep0 = 12; each build restarts from its own checkpoint
+    out = run_worker(hostsim_lib, "--ranks", ranks, "--scheme", scheme, "--restart", 9)
+    assert out["restart_istep_end"] == [22, 22]
+
+
+@needs_ref
 def test_reference_main_with_production_arithmetic_on_the_host_sim(hostsim_lib):
     check_fast(run_worker(hostsim_lib, "--ranks", 2, "--math", "fast"))
 
