@@ -15,7 +15,7 @@ This script reads the reference's own sources WHERE THEY LIE (default
     saveload.f90  vortcalc, exchng8, statistc, statistc2, diag (values written to file units are
                   captured: ref_capture)
     saveload.f90  outputflow, outputuy, outputpress, probe (what main.f90 calls every nflowout steps and at the end)
-    main.f90      PROGRAM main itself -> ref_main (MPI_WTIME reads 0; constructMPItypes is skipped -- derived
+    main.f90      PROGRAM main itself -> ref_main (MPI_WTIME is a call counter; constructMPItypes is skipped -- derived
                   MPI types are not used by the mini-MPI -- and any other call outside the translated set
                   aborts instead of being passed over)
 
@@ -654,7 +654,7 @@ class Translator:
         if n in ("real", "dfloat", "dble", "float"):
             return "((double)(%s))" % a[0]
         if n == "mpi_wtime":
-            return "0.0"                       # the wall-clock exit of main.f90:197-207 never fires
+            return "ref_mpi_wtime(S)"          # a counter: 0 unless the test overrides "wtime_tick" (main.f90:197-207)
         if n == "int":
             return "((int)(%s))" % a[0]
         if n in INTRINSIC_REAL:

@@ -156,6 +156,7 @@ typedef struct ref_common {
     /* values the translated code will be handed by read(unit) statements (loadcntdflow), in the order read */
     long nplay, iplay;
     double *play;
+    long wtime_calls;
 } ref_common;
 
 static inline double ref_play(void *S, int unit)
@@ -295,6 +296,14 @@ static inline void ref_mpi_abort(void *S, int comm, int *code, int *ierr)
     (void)comm; (void)ierr;
     fprintf(stderr, "ref: MPI_ABORT(%d) on rank %d\n", *code, ((ref_common *)S)->rank);
     abort();
+}
+/* MPI_WTIME: the number of calls so far times the override "wtime_tick" (default 0: the wall-clock exit of
+ * main.f90:197-207 never fires; a test sets a tick and `time_bond` to make it fire at a chosen step) */
+static inline double ref_mpi_wtime(void *S)
+{
+    ref_common *c = (ref_common *)S;
+    c->wtime_calls += 1;
+    return (double)c->wtime_calls * ref_override_d(S, "wtime_tick", 0.0);
 }
 static inline void ref_untranslated(void *S, const char *name)
 {

@@ -34,6 +34,9 @@ ap.add_argument("--ndiag", type=int, default=4)
 ap.add_argument("--nflowout", type=int, default=5)
 ap.add_argument("--rhoepsl", type=float, default=1e-6)
 ap.add_argument("--laminar", action="store_true")
+ap.add_argument("--time-bond", type=float, default=0.0, help="MPI_WTIME ticks 1 per call and time_bond is this: the loop "
+                "leaves at the first multiple of ntime where the elapsed ticks exceed it (main.f90:197-207)")
+ap.add_argument("--ntime", type=int, default=7)
 ap.add_argument("--restart", type=int, default=0, metavar="N2", help="afterwards: savecntdflow in both builds (compared), "
                 "then a CONTINUED run of N2 steps (newrun = .false., main.f90:118-121) in both builds, each from its own "
                 "checkpoint: loadcntdflow reads back what savecntdflow wrote")
@@ -42,12 +45,15 @@ ap.add_argument("--ipart", action="store_true", help="ipart = .true. (para.f90:3
 a = ap.parse_args()
 nx, ny, nz = (int(t) for t in a.size.split("x"))
 U = {} if a.laminar else dict(ustar=0.0025, ystar=0.0036 / 0.0025, force_in_y=2.0 * 0.0025 * 0.0025 / nx, a9=0.3)
-ov = dict(nsteps=a.nsteps, ndiag=a.ndiag, nflowout=a.nflowout, ntime=7, rhoepsl=a.rhoepsl, **U)
+ov = dict(nsteps=a.nsteps, ndiag=a.ndiag, nflowout=a.nflowout, ntime=a.ntime, rhoepsl=a.rhoepsl, **U)
 
 
 def run_main(dropin, checkpoint=None):
     extra = dict(newrun=0, nsteps=a.restart) if checkpoint else {}
     w = ref.RefWorld(nx, ny, nz, nprocY=1, nprocZ=a.ranks, laminar=a.laminar, dropin=dropin, ipart=a.ipart, **dict(ov, **extra))
+    if a.time_bond:
+        w.override("wtime_tick", 1.0)
+        w.override("time_bond", a.time_bond)
     if dropin:
         w.override("cfg%math", 1 if a.math == "strict" else 0)
         w.override("cfg%scheme", dict(aa=0, ab=1, auto=2)[a.scheme])

@@ -30,14 +30,15 @@ needs_ref = pytest.mark.skipif(not (ref.available() and ref.available(dropin=Tru
 TOL = dict(f=1e-12, unit9010=1e-12, unit26=1e-9, unit17=1e-9, unit20=1e-9, unit60=1e-9, rho=1e-9, ux=1e-9, uy=1e-9, uz=1e-9, unit27=1e-9, unit58=1e-9)
 
 
-def run_worker(lib, *args):
+def run_worker(lib, *args, end=None):
     res = subprocess.run([sys.executable, WORKER, "--lib", lib] + [str(a) for a in args], stdout=subprocess.PIPE,
                          stderr=subprocess.STDOUT, text=True, timeout=900, cwd=ROOT)
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     assert line, res.stdout[-3000:]
     out = json.loads(line[-1])
     assert res.returncode == 0 and not out["bad"], (out["bad"], res.stdout[-2000:])
-    assert out["istep_end"][0] == out["nsteps"] + 1           # the time loop ran to its end (a DO variable ends one past)
+    # the time loop ran to its end (a DO variable ends one past), or left where the caller says it must
+    assert out["istep_end"] == [end if end is not None else out["nsteps"] + 1] * 2
     assert {17, 20, 26, 27, 60, 9010} <= set(out["units"])    # outputuy, outputpress, diag, statistc, probe, saveinitflow wrote
     return out
 
@@ -83,6 +84,13 @@ def test_reference_continued_run_through_the_shim_on_the_host_sim(hostsim_lib, r
     # continues from istep0 = 12; each build restarts from its own checkpoint
     out = run_worker(hostsim_lib, "--ranks", ranks, "--scheme", scheme, "--restart", 9)
     assert out["restart_istep_end"] == [22, 22]
+
+
+@needs_ref
+def test_reference_main_leaves_on_its_wall_clock_budget_on_the_host_sim(hostsim_lib):
+    # main.f90:197-207: every ntime steps the ranks all-reduce their elapsed time and leave when it exceeds time_bond; probe
+    # then reads the host arrays.  MPI_WTIME ticks once per call here: with ntime = 4 the third check (istep 12) exceeds 2.5
+    run_worker(hostsim_lib, "--ranks", 2, "--nsteps", 30, "--ntime", 4, "--ndiag", 7, "--nflowout", 9, "--time-bond", 2.5, end=12)
 
 
 @needs_ref
