@@ -1171,7 +1171,7 @@ class Translator:
                        "rhoupdat", "avedensity", "forcing", "forcingp", "exchng8", "vortcalc", "sijstat00",
                        "savecntdflow", "saveinitflow", "saveprerelax",
                        "statistc", "statistc2", "diag", "outputflow", "outputuy", "outputpress", "probe",
-                       "loadcntdflow"]
+                       "loadcntdflow", "loadinitflow"]
         o = self.emit
         o("/* GENERATED by oracle/f90toc.py from the reference's Fortran sources -- do not edit, do not commit. */")
         o('#include "../ref_runtime.h"')
@@ -1252,6 +1252,7 @@ class Translator:
             self.translate_sub(n, save[n])
         # ... and the reader of a continued run (main.f90:120): its read(unit) lists are served from a playback queue
         self.translate_sub("loadcntdflow", save["loadcntdflow"])
+        self.translate_sub("loadinitflow", save["loadinitflow"])     # main.f90:112: a new run from a saved pre-relaxed flow
         # the driver itself: PROGRAM main (main.f90:19-236)
         self.wanted.append("main")
         self.translate_sub("main", self.program_of("main.f90"))

@@ -37,6 +37,9 @@ ap.add_argument("--laminar", action="store_true")
 ap.add_argument("--time-bond", type=float, default=0.0, help="MPI_WTIME ticks 1 per call and time_bond is this: the loop "
                 "leaves at the first multiple of ntime where the elapsed ticks exceed it (main.f90:197-207)")
 ap.add_argument("--ntime", type=int, default=7)
+ap.add_argument("--from-initflow", action="store_true", help="with --restart: the second run is a NEW run from the saved "
+                "pre-relaxed flow instead (newinitflow = .false., main.f90:111-118): loadinitflow reads what the first run's "
+                "saveinitflow wrote")
 ap.add_argument("--restart", type=int, default=0, metavar="N2", help="afterwards: savecntdflow in both builds (compared), "
                 "then a CONTINUED run of N2 steps (newrun = .false., main.f90:118-121) in both builds, each from its own "
                 "checkpoint: loadcntdflow reads back what savecntdflow wrote")
@@ -49,7 +52,9 @@ ov = dict(nsteps=a.nsteps, ndiag=a.ndiag, nflowout=a.nflowout, ntime=a.ntime, rh
 
 
 def run_main(dropin, checkpoint=None):
-    extra = dict(newrun=0, nsteps=a.restart) if checkpoint else {}
+    extra = {}
+    if checkpoint:
+        extra = dict(newinitflow=0, nsteps=a.restart) if a.from_initflow else dict(newrun=0, nsteps=a.restart)
     w = ref.RefWorld(nx, ny, nz, nprocY=1, nprocZ=a.ranks, laminar=a.laminar, dropin=dropin, ipart=a.ipart, **dict(ov, **extra))
     if a.time_bond:
         w.override("wtime_tick", 1.0)
@@ -142,6 +147,9 @@ if a.restart and not res["bad"]:
     # d3q19_b200_sync_f_to_host first (collision_b200.f90) -- done above for the comparison of f
     cps = []
     for w in (wr, wb):
+        if a.from_initflow:                                  # the records saveinitflow wrote when the pre-relaxation ended
+            cps.append([w.captured(9010, rank=r) for r in range(a.ranks)])
+            continue
         w.clear_captured()
         w.run("savecntdflow")
         cps.append([w.captured(9012, rank=r) for r in range(a.ranks)])
@@ -169,7 +177,7 @@ if a.restart and not res["bad"]:
         for k in ("rho", "ux", "uy", "uz", "f"):
             note("restart_" + k, wb.array(k, r)[0], wr.array(k, r)[0])
     res["restart_istep_end"] = [int(wr.scalar("istep")), int(wb.scalar("istep"))]
-    if res["restart_istep_end"] != [a.nsteps + a.restart + 1] * 2:
+    if res["restart_istep_end"] != [(0 if a.from_initflow else a.nsteps) + a.restart + 1] * 2:
         res["bad"].append("the continued run ended at istep %s" % res["restart_istep_end"])
 
 release(wb)

@@ -87,6 +87,14 @@ def test_reference_continued_run_through_the_shim_on_the_host_sim(hostsim_lib, r
 
 
 @needs_ref
+def test_reference_new_run_from_a_saved_prerelaxed_flow_on_the_host_sim(hostsim_lib):
+    # newinitflow = .false. (main.f90:111-118): loadinitflow reads the records the first run's saveinitflow wrote, statistc
+    # runs before any macrovar, then FORCING, macrovar and the loop from step 1
+    out = run_worker(hostsim_lib, "--ranks", 2, "--scheme", "ab", "--restart", 9, "--from-initflow")
+    assert out["restart_istep_end"] == [10, 10]
+
+
+@needs_ref
 def test_reference_main_leaves_on_its_wall_clock_budget_on_the_host_sim(hostsim_lib):
     # main.f90:197-207: every ntime steps the ranks all-reduce their elapsed time and leave when it exceeds time_bond; probe
     # then reads the host arrays.  MPI_WTIME ticks once per call here: with ntime = 4 the third check (istep 12) exceeds 2.5
