@@ -1,8 +1,8 @@
 #!/bin/bash
 # The host-compiled kernels (tests/host/kernels_host.cpp) under AddressSanitizer + UBSan: every out-of-range index of a
 # step / face / particle kernel on the small cases of tests/test_kernels_host.py would be a heap-buffer-overflow here
-# (each device array is its own heap block).  ~25 min on 8 cores because of the fiber-run particle cases; not part of
-# the default suite.  compute-sanitizer on the device is in tools/next_round_gpu.sh.
+# (each device array is its own heap block).  ~8 min on 8 cores (fiber-run particle cases); not part of
+# the default suite.  compute-sanitizer on the device: tools/r02_sanitize.sh.
 set -e
 here=$(cd "$(dirname "$0")/.." && pwd)
 cd "$here"
