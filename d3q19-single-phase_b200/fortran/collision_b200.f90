@@ -177,10 +177,10 @@
 
 !     ---- error convention: the reference's subroutines cannot fail (SURVEY 8(b));
 !     a nonzero status is printed and the run is aborted
-      subroutine d3q19_b200_check(rc, where)
+      subroutine d3q19_b200_check(rc, what)
       use mpi
       integer(c_int), intent(in) :: rc
-      character(len=*), intent(in) :: where
+      character(len=*), intent(in) :: what
       type(c_ptr) :: cmsg
       character(kind=c_char), pointer :: fmsg(:)
       integer :: n, ierr_
@@ -188,7 +188,7 @@
       cmsg = d3q19_last_error()
       n = int(c_strlen(cmsg))
       call c_f_pointer(cmsg, fmsg, [n])
-      write(*,*) 'd3q19_b200: ', where, ' failed: ', fmsg(1:n)
+      write(*,*) 'd3q19_b200: ', what, ' failed: ', fmsg(1:n)
       call MPI_ABORT(MPI_COMM_WORLD, 1, ierr_)
       end subroutine d3q19_b200_check
 

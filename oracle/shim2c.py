@@ -608,6 +608,17 @@ class ShimTranslator:
         bad = lint(self.shim)
         if bad:
             raise SystemExit("shim2c: the shim does not match include/d3q19_b200.h:\n  " + "\n  ".join(bad))
+        # what a Fortran compiler would reject and a translator would not notice: a local declaration of a name that is
+        # use-associated (var_inc or the shim's own module), or one name exported by both modules
+        vi = set(self.tr.module)
+        mod = set(self.shim.modvars) | set(self.shim.params) | set(self.shim.iface) | {"d3q19_config"} \
+            | {n for n, sub in self.shim.subs.items() if sub["contained"]}
+        clash = ["module d3q19_b200_shim and var_inc both export %r" % n for n in sorted(mod & vi)]
+        for name, sub in self.shim.subs.items():
+            local = set(sub["decls"]) - set(sub["dummies"])
+            clash += ["%s declares %r, which it also gets from a module" % (name, n) for n in sorted(local & (vi | mod))]
+        if clash:
+            raise SystemExit("shim2c: name clashes in collision_b200.f90:\n  " + "\n  ".join(clash))
         o = self.emit
         o("/* GENERATED by oracle/shim2c.py from d3q19-single-phase_b200/fortran/collision_b200.f90 -- do not edit, do not")
         o(" * commit.  Included by ref_translated.c under -DREF_DROPIN (struct ref_state is complete there). */")

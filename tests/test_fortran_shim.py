@@ -62,3 +62,21 @@ def test_lint_catches_a_broken_binding(k, tmp_path):
     assert bad, "mutation %d went unnoticed" % k
     if word:
         assert any(word.lower() in b.lower() for b in bad), bad
+
+
+def test_free_form_source_limits():
+    # what a compiler checks and the translator does not: free-form lines of at most 132 characters, continuation lines that
+    # end in `&`, no tab characters
+    for no, line in enumerate(open(shim2c.SHIM).read().splitlines(), 1):
+        assert len(line) <= 132, (no, len(line))
+        assert "\t" not in line, no
+
+
+def test_no_local_name_shadows_a_module_entity():
+    # a local declaration of a use-associated name is an error in Fortran; needs the reference's var_inc.f90, so only where
+    # it is mounted (the build box) -- shim2c.generate() refuses to translate on a clash
+    ref = "/root/reference/Channel-Flow"
+    if not os.path.isdir(ref):
+        pytest.skip("reference sources not mounted")
+    text = shim2c.ShimTranslator(ref).generate()
+    assert "void ref_collision_mrt(ref_state *S)" in text and "d3q19_shim_bind_arrays(" in text
